@@ -1,0 +1,472 @@
+// ref_dump — harness around the UNMODIFIED reference (ITBE-Lab/ma) compiled into oracle/_ref/libma_ref.so.
+// TEST INFRASTRUCTURE ONLY: generates golden vectors / parity dumps and times the reference's CPU path.
+// Nothing in the product library (ma_b200/csrc) links or calls this.
+//
+// Drives exactly the reference's own modules, in the order of setUpCompGraph
+// (/root/reference/libs/ma/src/util/export.cpp:72-128):
+//   BinarySeeding::execute            libs/ma/src/module/binarySeeding.cpp:86-178
+//   ExtractSeeds::execute             libs/ma/inc/ma/module/stripOfConsideration.h:138-157
+//   StripOfConsiderationSeeds::execute libs/ma/src/module/stripOfConsideration.cpp:12-161
+//   Harmonization::execute            libs/ma/src/module/harmonization.cpp:374-555
+//   NeedlemanWunsch::execute          libs/ma/inc/ma/module/needlemanWunsch.h:111-134
+// and interposes kswcpp_sse_xx (libs/kswcpp/src/kswcpp_sse_xx.cpp:77) to log every DP call.
+//
+// Sub-commands:
+//   ref_dump index <genome.txt> <prefix>
+//        genome.txt: lines ">name" followed by one line of ACGT. Writes <prefix>.{pac,ann,amb,bwt,sa}
+//   ref_dump align <prefix> <reads.txt> <preset> <out.dump> [srand_base]
+//        reads.txt: one read (ACGTN) per line. Dumps every stage. If srand_base >= 0 the harness calls
+//        srand(srand_base + read_index) right before Harmonization::execute.
+//   ref_dump ksw <pairs.txt> <out.dump>
+//        pairs.txt: lines "w zdrop flag QUERY TARGET" (sequences as digits 0-4). DP only.
+//   ref_dump bench <prefix> <reads.txt> <preset> <threads> [srand_base]
+//        times the five modules over all reads with <threads> host threads; prints one JSON line.
+//   ref_dump kswbench <pairs.txt> <threads> <repeat>
+#include "ma/container/fMIndex.h"
+#include "ma/container/pack.h"
+#include "ma/module/binarySeeding.h"
+#include "ma/module/harmonization.h"
+#include "ma/module/needlemanWunsch.h"
+#include "ma/module/stripOfConsideration.h"
+#include <atomic>
+#include <chrono>
+#include <dlfcn.h>
+#include <fstream>
+#include <thread>
+
+using namespace libMA;
+using namespace libMS;
+
+// ---------------------------------------------------------------- dump container
+struct Dump
+{
+    std::list<std::pair<std::string, std::vector<int64_t>>> vArrays; // list: references stay valid
+    std::vector<int64_t>& arr( const std::string& sName )
+    {
+        for( auto& rP : vArrays )
+            if( rP.first == sName )
+                return rP.second;
+        vArrays.emplace_back( sName, std::vector<int64_t>( ) );
+        return vArrays.back( ).second;
+    }
+    void write( const std::string& sFile )
+    {
+        std::ofstream xOut( sFile, std::ios::binary );
+        xOut << "MADUMP1\n";
+        for( auto& rP : vArrays )
+        {
+            xOut << rP.first << " " << rP.second.size( ) << "\n";
+            xOut.write( (const char*)rP.second.data( ), rP.second.size( ) * sizeof( int64_t ) );
+        }
+    }
+};
+
+// ---------------------------------------------------------------- ksw interposer
+struct KswLog
+{
+    std::vector<int64_t> vCalls; // 16 fields per call
+    std::vector<int64_t> vSeq; // query then target, one base per entry
+    std::vector<int64_t> vCigar;
+};
+static thread_local KswLog* pKswLog = nullptr;
+static std::atomic<int64_t> iKswCells( 0 );
+
+typedef void ( *ksw_fn_t )( int, const uint8_t*, int, const uint8_t*, const KswCppParam<5>&, int, int, int,
+                            kswcpp_extz_t*, AlignedMemoryManager& );
+static const char* sKswSym = "_Z13kswcpp_sse_xxiPKhiS0_RK11KswCppParamILj5EEiiiP13kswcpp_extz_tR20AlignedMemoryManager";
+
+void kswcpp_sse_xx( int qlen, const uint8_t* query, int tlen, const uint8_t* target, const KswCppParam<5>& xParam,
+                    int w, int zdrop, int flag, kswcpp_extz_t* ez, AlignedMemoryManager& rxMemManager )
+{
+    static ksw_fn_t fReal = (ksw_fn_t)dlsym( RTLD_NEXT, sKswSym );
+    if( !fReal )
+    {
+        std::cerr << "ref_dump: cannot resolve the reference's kswcpp_sse_xx" << std::endl;
+        abort( );
+    }
+    fReal( qlen, query, tlen, target, xParam, w, zdrop, flag, ez, rxMemManager );
+    if( pKswLog )
+    {
+        auto& c = pKswLog->vCalls;
+        int64_t a[ 16 ] = { qlen,      tlen,     w,       zdrop,     flag,      (int64_t)ez->max, (int64_t)ez->zdropped,
+                            ez->max_q, ez->max_t, ez->mqe, ez->mqe_t, ez->mte,   ez->mte_q,
+                            ez->score, ez->n_cigar, ez->reach_end };
+        c.insert( c.end( ), a, a + 16 );
+        for( int i = 0; i < qlen; i++ )
+            pKswLog->vSeq.push_back( query[ i ] );
+        for( int i = 0; i < tlen; i++ )
+            pKswLog->vSeq.push_back( target[ i ] );
+        for( int i = 0; i < ez->n_cigar; i++ )
+            pKswLog->vCigar.push_back( ez->cigar[ i ] );
+    }
+}
+
+// ---------------------------------------------------------------- helpers
+static std::vector<std::string> readLines( const std::string& sFile )
+{
+    std::ifstream xIn( sFile );
+    if( !xIn )
+    {
+        std::cerr << "cannot open " << sFile << std::endl;
+        exit( 2 );
+    }
+    std::vector<std::string> vRet;
+    std::string sLine;
+    while( std::getline( xIn, sLine ) )
+        if( !sLine.empty( ) )
+            vRet.push_back( sLine );
+    return vRet;
+}
+
+static void selectPreset( ParameterSetManager& rP, std::string sPreset )
+{
+    for( auto& c : sPreset )
+        c = std::tolower( c );
+    rP.setSelected( sPreset );
+}
+
+static int cmdIndex( int argc, char** argv )
+{
+    auto vLines = readLines( argv[ 2 ] );
+    auto pPack = std::make_shared<Pack>( );
+    for( size_t i = 0; i + 1 < vLines.size( ); i += 2 )
+    {
+        std::string sName = vLines[ i ].substr( 1 );
+        NucSeq xSeq( vLines[ i + 1 ] );
+        pPack->vAppendSequence( sName, "synthetic", xSeq );
+    }
+    pPack->vStoreCollection( argv[ 3 ] );
+    auto pFM = std::make_shared<FMIndex>( pPack );
+    pFM->vStoreFMIndex( argv[ 3 ] );
+    return 0;
+}
+
+struct Stages
+{
+    std::shared_ptr<SegmentVector> pSegments;
+    std::shared_ptr<Seeds> pSeeds;
+    std::shared_ptr<SoCPriorityQueue> pSoCs;
+    std::shared_ptr<ContainerVector<std::shared_ptr<Seeds>>> pHarm;
+    std::shared_ptr<ContainerVector<std::shared_ptr<Alignment>>> pAlignments;
+};
+
+struct Modules
+{
+    BinarySeeding xSeeding;
+    StripOfConsideration xSoC;
+    Harmonization xHarm;
+    NeedlemanWunsch xNW;
+    Modules( const ParameterSetManager& rP ) : xSeeding( rP ), xSoC( rP ), xHarm( rP ), xNW( rP )
+    {}
+};
+
+static int cmdAlign( int argc, char** argv )
+{
+    std::string sPrefix = argv[ 2 ];
+    auto vReads = readLines( argv[ 3 ] );
+    ParameterSetManager xP;
+    selectPreset( xP, argv[ 4 ] );
+    int64_t iSrandBase = argc > 6 ? atoll( argv[ 6 ] ) : -1;
+    auto pPack = std::make_shared<Pack>( sPrefix );
+    auto pFM = std::make_shared<FMIndex>( sPrefix );
+    Modules xM( xP );
+
+    Dump xD;
+    auto& seg_off = xD.arr( "seg_off" );
+    auto& seg = xD.arr( "seg" );
+    auto& seed_off = xD.arr( "seed_off" );
+    auto& seed = xD.arr( "seed" );
+    auto& soc_off = xD.arr( "soc_off" );
+    auto& soc = xD.arr( "soc" );
+    auto& socseed_off = xD.arr( "socseed_off" );
+    auto& socseed = xD.arr( "socseed" );
+    auto& harm_off = xD.arr( "harm_off" );
+    auto& harmseed_off = xD.arr( "harmseed_off" );
+    auto& harmseed = xD.arr( "harmseed" );
+    auto& aln_off = xD.arr( "aln_off" );
+    auto& aln = xD.arr( "aln" );
+    auto& alndata_off = xD.arr( "alndata_off" );
+    auto& alndata = xD.arr( "alndata" );
+    auto& ksw_off = xD.arr( "ksw_off" );
+    KswLog xLog;
+    seg_off.push_back( 0 );
+    seed_off.push_back( 0 );
+    soc_off.push_back( 0 );
+    socseed_off.push_back( 0 );
+    harm_off.push_back( 0 );
+    harmseed_off.push_back( 0 );
+    aln_off.push_back( 0 );
+    alndata_off.push_back( 0 );
+    ksw_off.push_back( 0 );
+
+    for( size_t uiRead = 0; uiRead < vReads.size( ); uiRead++ )
+    {
+        auto pQ = std::make_shared<NucSeq>( vReads[ uiRead ] );
+        pQ->sName = "r" + std::to_string( uiRead );
+        auto pSeg = xM.xSeeding.execute( pFM, pQ );
+        for( const Segment& rS : *pSeg )
+        {
+            int64_t a[ 5 ] = { (int64_t)rS.start( ), (int64_t)rS.size( ), rS.saInterval( ).start( ),
+                               rS.saInterval( ).startRevComp( ), rS.saInterval( ).size( ) };
+            seg.insert( seg.end( ), a, a + 5 );
+        }
+        seg_off.push_back( seg.size( ) / 5 );
+
+        auto pSeeds = xM.xSoC.xExtractHelper.execute( pSeg, pFM, pQ, pPack );
+        for( const Seed& rS : *pSeeds )
+        {
+            int64_t a[ 6 ] = { (int64_t)rS.start( ),  (int64_t)rS.size( ),         (int64_t)rS.start_ref( ),
+                               (int64_t)rS.uiAmbiguity, (int64_t)rS.bOnForwStrand, (int64_t)rS.uiDelta };
+            seed.insert( seed.end( ), a, a + 6 );
+        }
+        seed_off.push_back( seed.size( ) / 6 );
+
+        auto pSoCs = xM.xSoC.xHelper.execute( pSeeds, pQ, pPack );
+        {
+            // pop a deep copy of the queue to record the complete pop order without disturbing the original
+            auto pSeedCopy = std::make_shared<Seeds>( pSoCs->pSeeds );
+            SoCPriorityQueue xCopy( pSeedCopy );
+            for( auto& rT : pSoCs->vMaxima )
+                xCopy.vMaxima.emplace_back( std::get<0>( rT ),
+                                            pSeedCopy->begin( ) + ( std::get<1>( rT ) - pSoCs->pSeeds->begin( ) ),
+                                            pSeedCopy->begin( ) + ( std::get<2>( rT ) - pSoCs->pSeeds->begin( ) ) );
+            while( !xCopy.empty( ) )
+            {
+                SoCOrder xO = std::get<0>( xCopy.vMaxima.front( ) );
+                auto pPop = xCopy.pop( );
+                int64_t a[ 4 ] = { (int64_t)xO.uiAccumulativeLength, (int64_t)xO.uiSeedAmbiguity,
+                                   (int64_t)xO.uiSeedAmount, (int64_t)pPop->xStats.index_of_strip };
+                soc.insert( soc.end( ), a, a + 4 );
+                for( const Seed& rS : *pPop )
+                {
+                    int64_t b[ 4 ] = { (int64_t)rS.start( ), (int64_t)rS.size( ), (int64_t)rS.start_ref( ),
+                                       (int64_t)rS.bOnForwStrand };
+                    socseed.insert( socseed.end( ), b, b + 4 );
+                }
+                socseed_off.push_back( socseed.size( ) / 4 );
+            }
+        }
+        soc_off.push_back( soc.size( ) / 4 );
+
+        if( iSrandBase >= 0 )
+            srand( (unsigned int)( iSrandBase + uiRead ) );
+        auto pHarm = xM.xHarm.execute( pSoCs, pQ, pFM );
+        for( auto pSet : *pHarm )
+        {
+            for( const Seed& rS : *pSet )
+            {
+                int64_t b[ 5 ] = { (int64_t)rS.start( ), (int64_t)rS.size( ), (int64_t)rS.start_ref( ),
+                                   (int64_t)rS.bOnForwStrand, (int64_t)pSet->xStats.index_of_strip };
+                harmseed.insert( harmseed.end( ), b, b + 5 );
+            }
+            harmseed_off.push_back( harmseed.size( ) / 5 );
+        }
+        harm_off.push_back( harmseed_off.size( ) - 1 );
+
+        pKswLog = &xLog;
+        auto pAln = xM.xNW.execute( pHarm, pQ, pPack );
+        pKswLog = nullptr;
+        ksw_off.push_back( xLog.vCalls.size( ) / 16 );
+        for( auto pA : *pAln )
+        {
+            int64_t a[ 8 ] = { (int64_t)pA->uiBeginOnQuery, (int64_t)pA->uiEndOnQuery,
+                               (int64_t)pA->uiBeginOnRef,   (int64_t)pA->uiEndOnRef,
+                               pA->iScore,                  (int64_t)pA->xStats.index_of_strip,
+                               (int64_t)pA->uiLength,       (int64_t)pA->data.size( ) };
+            aln.insert( aln.end( ), a, a + 8 );
+            for( auto& rP : pA->data )
+            {
+                alndata.push_back( (int64_t)rP.first );
+                alndata.push_back( (int64_t)rP.second );
+            }
+            alndata_off.push_back( alndata.size( ) / 2 );
+        }
+        aln_off.push_back( aln.size( ) / 8 );
+    }
+    xD.arr( "ksw_calls" ) = xLog.vCalls;
+    xD.arr( "ksw_seq" ) = xLog.vSeq;
+    xD.arr( "ksw_cigar" ) = xLog.vCigar;
+    xD.write( argv[ 5 ] );
+    return 0;
+}
+
+struct KswPair
+{
+    int w, zdrop, flag;
+    std::vector<uint8_t> q, t;
+};
+static std::vector<KswPair> readPairs( const std::string& sFile )
+{
+    std::vector<KswPair> vRet;
+    std::ifstream xIn( sFile );
+    KswPair xP;
+    std::string sQ, sT;
+    while( xIn >> xP.w >> xP.zdrop >> xP.flag >> sQ >> sT )
+    {
+        xP.q.clear( );
+        xP.t.clear( );
+        for( char c : sQ )
+            if( c != '-' )
+                xP.q.push_back( c - '0' );
+        for( char c : sT )
+            if( c != '-' )
+                xP.t.push_back( c - '0' );
+        vRet.push_back( xP );
+    }
+    return vRet;
+}
+
+static int cmdKsw( int argc, char** argv )
+{
+    auto vPairs = readPairs( argv[ 2 ] );
+    KswCppParam<5> xParam( 2, 4, 4, 2, 24, 1 );
+    KswLog xLog;
+    AlignedMemoryManager xMem;
+    pKswLog = &xLog;
+    for( auto& rP : vPairs )
+    {
+        Wrapper_ksw_extz_t ez;
+        kswcpp_dispatch( (int)rP.q.size( ), rP.q.data( ), (int)rP.t.size( ), rP.t.data( ), xParam, rP.w, rP.zdrop,
+                         rP.flag, ez.ez, xMem );
+    }
+    pKswLog = nullptr;
+    Dump xD;
+    xD.arr( "ksw_calls" ) = xLog.vCalls;
+    xD.arr( "ksw_seq" ) = xLog.vSeq;
+    xD.arr( "ksw_cigar" ) = xLog.vCigar;
+    xD.write( argv[ 3 ] );
+    return 0;
+}
+
+static int cmdBench( int argc, char** argv )
+{
+    std::string sPrefix = argv[ 2 ];
+    auto vReads = readLines( argv[ 3 ] );
+    ParameterSetManager xP;
+    selectPreset( xP, argv[ 4 ] );
+    int iThreads = atoi( argv[ 5 ] );
+    int64_t iSrandBase = argc > 6 ? atoll( argv[ 6 ] ) : -1;
+    auto pPack = std::make_shared<Pack>( sPrefix );
+    auto pFM = std::make_shared<FMIndex>( sPrefix );
+    Modules xM( xP );
+    std::vector<std::shared_ptr<NucSeq>> vQ;
+    for( auto& s : vReads )
+        vQ.push_back( std::make_shared<NucSeq>( s ) );
+    std::atomic<size_t> uiNext( 0 );
+    std::atomic<size_t> uiAligned( 0 );
+    std::atomic<int64_t> iNs[ 5 ];
+    for( auto& x : iNs )
+        x = 0;
+    auto tStart = std::chrono::steady_clock::now( );
+    std::vector<std::thread> vT;
+    for( int t = 0; t < iThreads; t++ )
+        vT.emplace_back( [ & ]( ) {
+            int64_t aNs[ 5 ] = { 0, 0, 0, 0, 0 };
+            size_t uiLocalAligned = 0;
+            while( true )
+            {
+                size_t i = uiNext.fetch_add( 16 );
+                if( i >= vQ.size( ) )
+                    break;
+                for( size_t j = i; j < std::min( i + 16, vQ.size( ) ); j++ )
+                {
+                    auto t0 = std::chrono::steady_clock::now( );
+                    auto pSeg = xM.xSeeding.execute( pFM, vQ[ j ] );
+                    auto t1 = std::chrono::steady_clock::now( );
+                    auto pSeeds = xM.xSoC.xExtractHelper.execute( pSeg, pFM, vQ[ j ], pPack );
+                    auto t2 = std::chrono::steady_clock::now( );
+                    auto pSoCs = xM.xSoC.xHelper.execute( pSeeds, vQ[ j ], pPack );
+                    auto t3 = std::chrono::steady_clock::now( );
+                    if( iSrandBase >= 0 && iThreads == 1 )
+                        srand( (unsigned int)( iSrandBase + j ) );
+                    auto pHarm = xM.xHarm.execute( pSoCs, vQ[ j ], pFM );
+                    auto t4 = std::chrono::steady_clock::now( );
+                    auto pAln = xM.xNW.execute( pHarm, vQ[ j ], pPack );
+                    auto t5 = std::chrono::steady_clock::now( );
+                    if( !pAln->empty( ) && ( *pAln )[ 0 ]->uiLength > 0 )
+                        uiLocalAligned++;
+                    aNs[ 0 ] += ( t1 - t0 ).count( );
+                    aNs[ 1 ] += ( t2 - t1 ).count( );
+                    aNs[ 2 ] += ( t3 - t2 ).count( );
+                    aNs[ 3 ] += ( t4 - t3 ).count( );
+                    aNs[ 4 ] += ( t5 - t4 ).count( );
+                }
+            }
+            for( int k = 0; k < 5; k++ )
+                iNs[ k ] += aNs[ k ];
+            uiAligned += uiLocalAligned;
+        } );
+    for( auto& t : vT )
+        t.join( );
+    double fSec = std::chrono::duration<double>( std::chrono::steady_clock::now( ) - tStart ).count( );
+    printf( "{\"reads\": %zu, \"aligned\": %zu, \"threads\": %d, \"seconds\": %.6f, \"reads_per_s\": %.1f, "
+            "\"stage_cpu_s\": {\"seeding\": %.4f, \"extract\": %.4f, \"soc\": %.4f, \"harmonization\": %.4f, \"dp\": "
+            "%.4f}}\n",
+            vQ.size( ), (size_t)uiAligned, iThreads, fSec, vQ.size( ) / fSec, iNs[ 0 ] * 1e-9, iNs[ 1 ] * 1e-9,
+            iNs[ 2 ] * 1e-9, iNs[ 3 ] * 1e-9, iNs[ 4 ] * 1e-9 );
+    return 0;
+}
+
+static int cmdKswBench( int argc, char** argv )
+{
+    auto vPairs = readPairs( argv[ 2 ] );
+    int iThreads = atoi( argv[ 3 ] );
+    int iRepeat = atoi( argv[ 4 ] );
+    KswCppParam<5> xParam( 2, 4, 4, 2, 24, 1 );
+    std::atomic<size_t> uiNext( 0 );
+    size_t uiTotal = vPairs.size( ) * (size_t)iRepeat;
+    auto tStart = std::chrono::steady_clock::now( );
+    std::vector<std::thread> vT;
+    for( int t = 0; t < iThreads; t++ )
+        vT.emplace_back( [ & ]( ) {
+            AlignedMemoryManager xMem;
+            while( true )
+            {
+                size_t i = uiNext.fetch_add( 4 );
+                if( i >= uiTotal )
+                    break;
+                for( size_t j = i; j < std::min( i + 4, uiTotal ); j++ )
+                {
+                    auto& rP = vPairs[ j % vPairs.size( ) ];
+                    Wrapper_ksw_extz_t ez;
+                    kswcpp_dispatch( (int)rP.q.size( ), rP.q.data( ), (int)rP.t.size( ), rP.t.data( ), xParam, rP.w,
+                                     rP.zdrop, rP.flag, ez.ez, xMem );
+                }
+            }
+        } );
+    for( auto& t : vT )
+        t.join( );
+    double fSec = std::chrono::duration<double>( std::chrono::steady_clock::now( ) - tStart ).count( );
+    printf( "{\"calls\": %zu, \"threads\": %d, \"seconds\": %.6f}\n", uiTotal, iThreads, fSec );
+    return 0;
+}
+
+int main( int argc, char** argv )
+{
+    if( argc < 2 )
+    {
+        std::cerr << "usage: ref_dump index|align|ksw|bench|kswbench ..." << std::endl;
+        return 2;
+    }
+    std::string sCmd = argv[ 1 ];
+    try
+    {
+        if( sCmd == "index" && argc >= 4 )
+            return cmdIndex( argc, argv );
+        if( sCmd == "align" && argc >= 6 )
+            return cmdAlign( argc, argv );
+        if( sCmd == "ksw" && argc >= 4 )
+            return cmdKsw( argc, argv );
+        if( sCmd == "bench" && argc >= 6 )
+            return cmdBench( argc, argv );
+        if( sCmd == "kswbench" && argc >= 5 )
+            return cmdKswBench( argc, argv );
+    }
+    catch( std::exception& e )
+    {
+        std::cerr << "ref_dump: exception: " << e.what( ) << std::endl;
+        return 1;
+    }
+    std::cerr << "ref_dump: bad arguments" << std::endl;
+    return 2;
+}
