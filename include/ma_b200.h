@@ -1,0 +1,109 @@
+/* ma_b200 — C ABI of the B200-native (sm_100a) implementation of MA's read-alignment hot path.
+ *
+ * This is the drop-in boundary: plain C, pointers and sizes only, no torch / STL types.  The reference
+ * (ITBE-Lab/ma) has no FFI for this path; each entry point below names the reference interface it replaces.
+ * The reference-side binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions: every function returns 0 on success and a negative MA_B200_E* code on failure (never throws across
+ * the ABI); ma_b200_last_error() returns a message for the calling context.  A context owns one CUDA device, one
+ * stream and its device buffers; a context is not re-entrant (use one per host thread / per GPU).  All `*_ms`
+ * out-parameters are CUDA-event times measured on the context's stream.  There is NO CPU fallback: without a
+ * CUDA device ma_b200_create fails.
+ *
+ * Nucleotide code: A=0 C=1 G=2 T=3 N=4 (reference: libs/ma/src/container/nucSeq.cpp:17-28).
+ */
+#ifndef MA_B200_H
+#define MA_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MA_B200_OK 0
+#define MA_B200_ECUDA -1 /* CUDA runtime error */
+#define MA_B200_EINVAL -2 /* invalid argument */
+#define MA_B200_ENOMEM -3 /* an output slab supplied by the caller is too small */
+#define MA_B200_ESTATE -4 /* call order violated (e.g. no index uploaded) */
+
+typedef struct ma_b200_ctx ma_b200_ctx;
+
+/* Flattened copy of the values the hot path reads from the reference's ParameterSetManager presets and from
+ * pGlobalParams (libs/ms/inc/ms/util/parameter.h:521-917, 1004-1064, 1079-1132).  ma_b200_params_preset() fills
+ * it for "default" | "illumina" | "illumina_paired" | "pacbio" | "nanopore". */
+typedef struct
+{
+    /* pGlobalParams: scoring (penalties are positive) — parameter.h:1032-1046 */
+    int32_t match, mismatch, gap, extend, gap2, extend2, sv_penalty;
+    /* seeding — parameter.h:671-701 */
+    int32_t seeding_technique; /* 0 = maxSpan, 1 = SMEMs */
+    int32_t min_seed_length; /* "Minimal Seed Length", filter is on segment size => length >= this + 1 */
+    int32_t min_ambiguity, max_ambiguity;
+    int32_t seed_drop_min_size; /* "Seeding Drop-off A" */
+    double seed_drop_factor; /* "Seeding Drop-off B" */
+    /* strip of consideration — parameter.h:703-718 */
+    int32_t max_num_soc, min_num_soc, soc_width, rectangular_soc;
+    /* harmonization heuristics — parameter.h:822-880 */
+    double soc_score_drop; /* "SoC Score Drop-off" */
+    int32_t harm_score_min;
+    double harm_score_min_rel;
+    double score_diff_tolerance;
+    int32_t max_score_lookahead, switch_qlen;
+    double max_delta_dist;
+    int32_t min_delta_dist;
+    int32_t optimistic_gap_estimation, gap_cost_cutting;
+    int32_t max_gap_area; /* "Maximal Gap Size": larger gaps use the dual extension */
+    int64_t genome_size_disable; /* "Minimum Genome Size for Heuristics" */
+    int32_t disable_heuristics;
+    /* dynamic programming — parameter.h:621-639 */
+    int32_t padding, bandwidth_ext, min_bandwidth_gap, zdrop;
+    /* RANSAC draws come from glibc's TYPE_3 rand(); the reference never seeds it itself.  Parity contract
+     * (SURVEY.md A-5): the stream for read i is seeded with srand(srand_base + i). */
+    uint32_t srand_base;
+} ma_b200_params;
+
+int ma_b200_params_preset( const char* name, ma_b200_params* out );
+
+/* ---- context ---------------------------------------------------------------------------------------------- */
+int ma_b200_create( int device, ma_b200_ctx** out );
+void ma_b200_destroy( ma_b200_ctx* ctx );
+const char* ma_b200_last_error( const ma_b200_ctx* ctx );
+int ma_b200_set_params( ma_b200_ctx* ctx, const ma_b200_params* params );
+/* number of kernels this context has launched so far (for bench.py's gpu_launches) */
+int64_t ma_b200_launch_count( const ma_b200_ctx* ctx );
+
+/* ---- banded DP: replaces kswcpp_dispatch (libs/kswcpp/inc/kswcpp.h:165-190) -------------------------------- */
+#define MA_B200_KSW_RIGHT 0x02 /* KSW_EZ_RIGHT */
+#define MA_B200_KSW_EXTZ_ONLY 0x40 /* KSW_EZ_EXTZ_ONLY */
+#define MA_B200_KSW_REV_CIGAR 0x80 /* KSW_EZ_REV_CIGAR */
+
+typedef struct
+{
+    int64_t qoff, toff; /* byte offsets of query / target in the sequence slab */
+    int32_t qlen, tlen, w, zdrop, flag, tag;
+} ma_b200_ksw_task;
+
+/* kswcpp_extz_t (kswcpp.h:31-41); the cigar lives at cigar[cigar_off .. cigar_off + n_cigar), word = len<<4 | op,
+ * op 0 = M, 1 = I, 2 = D.  cells = band cells processed (the GCUPS unit). */
+typedef struct
+{
+    int32_t max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, n_cigar, reach_end, status;
+    int64_t cigar_off;
+    int64_t cells;
+} ma_b200_ksw_result;
+
+/* Three-step form: inputs stay resident in HBM between upload and run (what bench.py times as `value`). */
+int ma_b200_ksw_upload( ma_b200_ctx* ctx, int64_t n, const ma_b200_ksw_task* tasks, const uint8_t* seq,
+                        int64_t seq_bytes );
+int ma_b200_ksw_run( ma_b200_ctx* ctx, float* kernel_ms );
+int ma_b200_ksw_download( ma_b200_ctx* ctx, ma_b200_ksw_result* results, uint32_t* cigar, int64_t cigar_cap_words,
+                          int64_t* cigar_words );
+/* One-call form with host buffers (host<->device copies inside; what bench.py times as `e2e`). */
+int ma_b200_ksw_batch( ma_b200_ctx* ctx, int64_t n, const ma_b200_ksw_task* tasks, const uint8_t* seq,
+                       int64_t seq_bytes, ma_b200_ksw_result* results, uint32_t* cigar, int64_t cigar_cap_words,
+                       int64_t* cigar_words );
+
+#ifdef __cplusplus
+}
+#endif
+#endif

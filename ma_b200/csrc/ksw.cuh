@@ -1,0 +1,490 @@
+// Banded two-piece-affine DP (extension + global) for sm_100a: one warp per DP problem, anti-diagonal wavefront.
+//
+// Replaces, bit-exactly, the reference's kswcpp_dispatch -> kswcpp_inner_core
+//   /root/reference/libs/kswcpp/inc/kswcpp.h:165-190, kswcpp_core.h:308-841 (recurrence + traceback byte),
+//   kswcpp_core.h:157-299 (H row, lane-blocked arg-max, mte/mqe), :22-44 (z-drop), :76-150 (backtrack).
+//
+// B200 mapping:
+//  * lanes run along the anti-diagonal (target index t); the reference's 16-aligned column range [st,en] is kept
+//    because its out-of-band cells feed band-edge cells (they are computed from stale state on purpose);
+//  * the seven int8 difference arrays + the H row live in a per-warp CIRCULAR window in shared memory
+//    (W >= aligned band width + 32 columns, lazily re-initialised as the band moves right), so a 1000-column target
+//    costs 1.4 KB of shared memory per warp instead of 11 KB, and 32..64 warps stay resident per SM;
+//  * neighbour (t-1) state moves by __shfl_up_sync, never through memory;
+//  * one traceback byte per cell is written coalesced to a per-warp slab in HBM (stays L2 resident) and walked by
+//    lane 0 afterwards; the CIGAR is then copied out by the whole warp to a bump-allocated output slab.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ma
+{
+
+struct KswTask
+{
+    long long qoff, toff; // byte offsets into the sequence slab
+    int qlen, tlen, w, zdrop, flag, tag;
+};
+
+struct KswOut
+{
+    int max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, n_cigar, reach_end, status;
+    long long cigar_off; // word offset into the cigar slab
+    long long cells; // band cells processed (st0..en0 over all rows) — the GCUPS unit
+};
+
+struct KswScore
+{
+    int match, mismatch; // mismatch as a (negative) score
+    int q, e, q2, e2; // after the q/q2 swap of kswcpp_core.h:367-375
+    int long_thres, long_diff;
+    int min16; // iOverallMinScr (negative) for the int16/int32 switch, kswcpp.h:101-115
+    int early_return; // -min_sc > 2(q+e): the reference returns right after ksw_reset_extz
+};
+
+#define MA_KSW_RIGHT 0x02
+#define MA_KSW_EXTZ_ONLY 0x40
+#define MA_KSW_REV_CIGAR 0x80
+
+__device__ __forceinline__ int w8( int x )
+{
+    return (int)(signed char)x;
+}
+
+// aligned band width in cells: n_col_ * 16 (kswcpp_core.h:401-402)
+__host__ __device__ inline int ksw_ncol16( int qlen, int tlen, int w )
+{
+    if( w < 0 )
+        w = tlen > qlen ? tlen : qlen;
+    int n = qlen < tlen ? qlen : tlen;
+    n = n < w + 1 ? n : w + 1;
+    return ( ( n + 15 ) / 16 + 1 ) * 16;
+}
+
+// band limits of anti-diagonal r (kswcpp_core.h:541-548); returns false when out of band
+__device__ __forceinline__ bool ksw_band( long long r, int qlen, int tlen, int w, int& st0, int& en0 )
+{
+    long long st = 0, en = tlen - 1;
+    if( st < r - qlen + 1 )
+        st = r - qlen + 1;
+    if( en > r )
+        en = r;
+    if( st < ( ( r - w + 1 ) >> 1 ) )
+        st = ( r - w + 1 ) >> 1;
+    if( en > ( ( r + w ) >> 1 ) )
+        en = ( r + w ) >> 1;
+    st0 = (int)st;
+    en0 = (int)en;
+    return st <= en;
+}
+
+// Shared memory per warp: 7 int8 arrays of W + one int32 array of W.
+template <int W> struct KswSmem
+{
+    signed char u[ W ], v[ W ], x[ W ], y[ W ], x2[ W ], y2[ W ], s[ W ];
+    int H[ W ];
+};
+
+// lane 0 only. Walks the traceback slab (kswcpp_core.h:76-150, is_rot = 1, min_intron_len = 0) and pushes run-length
+// ops in backtrack order into cig[]; returns the number of words or -1 on overflow.
+__device__ inline int ksw_backtrack( const unsigned char* tb, int ncol16, int qlen, int tlen, int w, int i0, int j0,
+                                     unsigned int* cig, int cap )
+{
+    long long i = i0, j = j0;
+    int state = 0, n = 0;
+    unsigned int cur = 0; // current run: len<<4|op, 0 = none
+    auto push = [ & ]( unsigned int op, unsigned int len ) {
+        if( cur != 0 && ( cur & 0xf ) == op )
+            cur += len << 4;
+        else
+        {
+            if( cur != 0 )
+            {
+                if( n < cap )
+                    cig[ n ] = cur;
+                n++;
+            }
+            cur = len << 4 | op;
+        }
+    };
+    while( i >= 0 && j >= 0 )
+    {
+        long long r = i + j;
+        int st0, en0;
+        ksw_band( r, qlen, tlen, w, st0, en0 );
+        int off = st0 & ~15, off_end = en0 | 15;
+        int force_state = -1;
+        if( i < off )
+            force_state = 2;
+        if( i > off_end )
+            force_state = 1;
+        unsigned int tmp = force_state < 0 ? tb[ r * ncol16 + i - off ] : 0;
+        if( state == 0 )
+            state = tmp & 7;
+        else if( !( tmp >> ( state + 2 ) & 1 ) )
+            state = 0;
+        if( state == 0 )
+            state = tmp & 7;
+        if( force_state >= 0 )
+            state = force_state;
+        if( state == 0 )
+            push( 0, 1 ), --i, --j;
+        else if( state == 1 || state == 3 )
+            push( 2, 1 ), --i;
+        else
+            push( 1, 1 ), --j;
+    }
+    if( i >= 0 )
+        push( 2, (unsigned int)i + 1 );
+    if( j >= 0 )
+        push( 1, (unsigned int)j + 1 );
+    if( cur != 0 )
+    {
+        if( n < cap )
+            cig[ n ] = cur;
+        n++;
+    }
+    return n > cap ? -1 : n;
+}
+
+// One warp, one problem. All lanes return the same KswOut (cigar_off/n_cigar are filled by the caller).
+// tb: per-warp traceback slab of >= (qlen+tlen-1)*ncol16 bytes.
+template <int W>
+__device__ void ksw_warp( const KswScore& P, const unsigned char* __restrict__ query, int qlen,
+                          const unsigned char* __restrict__ target, int tlen, int w, int zdrop, int flag,
+                          KswSmem<W>& sm, unsigned char* __restrict__ tb, KswOut& ez )
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int M = W - 1;
+    ez.max_q = ez.max_t = ez.mqe_t = ez.mte_q = -1;
+    ez.max = 0;
+    ez.score = ez.mqe = ez.mte = (int)0x80000000;
+    ez.n_cigar = 0, ez.zdropped = 0, ez.reach_end = 0, ez.status = 0, ez.cells = 0;
+    if( qlen <= 0 || tlen <= 0 || P.early_return )
+        return;
+    if( w < 0 )
+        w = tlen > qlen ? tlen : qlen;
+    const int q = P.q, e = P.e, q2 = P.q2, e2 = P.e2, qe = q + e, qe2 = q2 + e2;
+    const int T16 = ( ( tlen + 15 ) / 16 ) * 16;
+    const int ncol16 = ksw_ncol16( qlen, tlen, w );
+    const bool bLeft = !( flag & MA_KSW_RIGHT );
+    // kswcpp_sse_xx.cpp:38: int16 scores iff no risk of overflow
+    const long long iSize = qlen > tlen ? qlen : tlen;
+    const bool is16 = !( iSize * P.min16 < -32768 || iSize * P.match > 32767 );
+    const int SIZE = is16 ? 8 : 4;
+    const int NEG_INF = is16 ? -32768 : (int)0x80000000;
+    const int init6 = w8( -q - e ), init25 = w8( -q2 - e2 );
+
+    int inited_end = 0; // columns [0, inited_end) of the circular window carry reference-visible state
+    int last_st = -1, last_en = -1;
+    long long cells = 0;
+    const long long nrows = (long long)qlen + tlen - 1;
+    for( long long r = 0; r < nrows; ++r )
+    {
+        int st0, en0;
+        if( !ksw_band( r, qlen, tlen, w, st0, en0 ) )
+        {
+            ez.zdropped = 1;
+            break;
+        }
+        cells += en0 - st0 + 1;
+        const int st = st0 & ~15, en = en0 | 15;
+        const int sEnd = st0 + ( ( ( en0 - st0 ) >> 4 ) + 1 ) * 16; // exclusive end of the score-profile writes
+        {
+            int need = en + 1 > ( ( sEnd + 15 ) & ~15 ) ? en + 1 : ( ( sEnd + 15 ) & ~15 );
+            if( need > T16 )
+                need = T16;
+            if( inited_end < need )
+            {
+                for( int idx = inited_end + lane; idx < need; idx += 32 )
+                {
+                    const int k = idx & M;
+                    sm.u[ k ] = sm.v[ k ] = sm.x[ k ] = sm.y[ k ] = (signed char)init6;
+                    sm.x2[ k ] = sm.y2[ k ] = (signed char)init25;
+                    sm.s[ k ] = 0;
+                    sm.H[ k ] = NEG_INF;
+                }
+                inited_end = need;
+                __syncwarp( );
+            }
+        }
+        const int first_col =
+            w8( r == 0 ? -q - e : r < P.long_thres ? -e : r == P.long_thres ? P.long_diff : -e2 );
+        int cx, cx2, cv; // values entering column st from column st-1 (kswcpp_core.h:562-579)
+        if( st > 0 )
+        {
+            if( st - 1 >= last_st && st - 1 <= last_en )
+                cx = sm.x[ ( st - 1 ) & M ], cx2 = sm.x2[ ( st - 1 ) & M ], cv = sm.v[ ( st - 1 ) & M ];
+            else
+                cx = init6, cx2 = init25, cv = init6;
+        }
+        else
+            cx = init6, cx2 = init25, cv = first_col;
+        if( en >= r && lane == 0 )
+        {
+            sm.y[ r & M ] = (signed char)init6;
+            sm.y2[ r & M ] = (signed char)init25;
+            sm.u[ r & M ] = (signed char)first_col;
+        }
+        // score profile from the unaligned st0 in steps of 16 (kswcpp_core.h:591-616); N scores -e2
+        for( int tt = st0 + lane; tt < sEnd && tt < T16; tt += 32 )
+        {
+            const int a = tt < tlen ? target[ tt ] : 0;
+            const long long qi = r - tt;
+            const int b = ( qi >= 0 && qi < qlen ) ? query[ qi ] : 0;
+            sm.s[ tt & M ] = (signed char)( ( a == 4 || b == 4 ) ? -e2 : ( a == b ? P.match : P.mismatch ) );
+        }
+        __syncwarp( );
+        unsigned char* rowp = tb + r * ncol16 - st;
+        for( int base = st; base <= en; base += 32 )
+        {
+            const int t = base + lane;
+            const bool act = t <= en;
+            const int k = t & M;
+            int xo = 0, vo = 0, x2o = 0, ut = 0, yo = 0, y2o = 0, z = 0;
+            if( act )
+                xo = sm.x[ k ], vo = sm.v[ k ], x2o = sm.x2[ k ], ut = sm.u[ k ], yo = sm.y[ k ], y2o = sm.y2[ k ],
+                z = sm.s[ k ];
+            int xt1 = __shfl_up_sync( FULL, xo, 1 ), vt1 = __shfl_up_sync( FULL, vo, 1 ),
+                x2t1 = __shfl_up_sync( FULL, x2o, 1 );
+            if( lane == 0 )
+                xt1 = cx, vt1 = cv, x2t1 = cx2;
+            cx = __shfl_sync( FULL, xo, 31 ), cv = __shfl_sync( FULL, vo, 31 ), cx2 = __shfl_sync( FULL, x2o, 31 );
+            if( act )
+            {
+                int a = w8( xt1 + vt1 ), b = w8( yo + ut ), a2 = w8( x2t1 + vt1 ), b2 = w8( y2o + ut );
+                int d;
+                if( bLeft )
+                {
+                    d = a > z ? 1 : 0;
+                    z = max( z, a );
+                    d = b > z ? 2 : d;
+                    z = max( z, b );
+                    d = a2 > z ? 3 : d;
+                    z = max( z, a2 );
+                    d = b2 > z ? 4 : d;
+                    z = max( z, b2 );
+                }
+                else
+                { // right-aligned: ties go to the gap, state 4 is never recorded (kswcpp_core.h:693-699)
+                    d = z > a ? 0 : 1;
+                    z = max( z, a );
+                    d = z > b ? d : 2;
+                    z = max( z, b );
+                    d = z > a2 ? d : 3;
+                    z = max( z, a2 );
+                    z = max( z, b2 );
+                }
+                z = min( z, P.match );
+                sm.u[ k ] = (signed char)( z - vt1 );
+                sm.v[ k ] = (signed char)( z - ut );
+                int tmp = w8( z - q );
+                a = w8( a - tmp ), b = w8( b - tmp );
+                tmp = w8( z - q2 );
+                a2 = w8( a2 - tmp ), b2 = w8( b2 - tmp );
+                if( bLeft )
+                {
+                    d |= a > 0 ? 0x08 : 0;
+                    d |= b > 0 ? 0x10 : 0;
+                    d |= a2 > 0 ? 0x20 : 0;
+                    d |= b2 > 0 ? 0x40 : 0;
+                }
+                else
+                {
+                    d |= a >= 0 ? 0x08 : 0;
+                    d |= b >= 0 ? 0x10 : 0;
+                    d |= a2 >= 0 ? 0x20 : 0;
+                    d |= b2 >= 0 ? 0x40 : 0;
+                }
+                sm.x[ k ] = (signed char)( max( a, 0 ) - qe );
+                sm.y[ k ] = (signed char)( max( b, 0 ) - qe );
+                sm.x2[ k ] = (signed char)( max( a2, 0 ) - qe2 );
+                sm.y2[ k ] = (signed char)( max( b2, 0 ) - qe2 );
+                rowp[ t ] = (unsigned char)d;
+            }
+        }
+        __syncwarp( );
+        // ---- calcMaxScore, exact branch (kswcpp_core.h:178-264)
+        int max_H, max_t, Hen0;
+        if( r > 0 )
+        {
+            const int en1 = st0 + ( ( en0 - st0 ) / SIZE ) * SIZE;
+            const int hprev = en0 > 0 ? sm.H[ ( en0 - 1 ) & M ] : sm.H[ en0 & M ];
+            const int dlt = en0 > 0 ? sm.u[ en0 & M ] : sm.v[ en0 & M ];
+            Hen0 = (int)( (unsigned)hprev + (unsigned)dlt );
+            if( is16 )
+                Hen0 = (short)Hen0;
+            __syncwarp( ); // every lane has read the old H[en0-1] before it is updated below
+            int bh = (int)0x80000000, bt = 0x7fffffff;
+            for( int t = st0 + lane; t < en0; t += 32 )
+            {
+                int h = (int)( (unsigned)sm.H[ t & M ] + (unsigned)(int)sm.v[ t & M ] );
+                if( is16 )
+                    h = (short)h;
+                sm.H[ t & M ] = h;
+                if( t < en1 && ( bt == 0x7fffffff || h > bh ) )
+                    bh = h, bt = st0 + ( ( t - st0 ) / SIZE ) * SIZE;
+            }
+            if( lane == 0 )
+                sm.H[ en0 & M ] = Hen0;
+            // lanes with equal (lane % SIZE) form one SSE lane of the reference: first block reaching the lane max
+            for( int o = 16; o >= SIZE; o >>= 1 )
+            {
+                const int oh = __shfl_xor_sync( FULL, bh, o ), ot = __shfl_xor_sync( FULL, bt, o );
+                if( ot != 0x7fffffff && ( bt == 0x7fffffff || oh > bh || ( oh == bh && ot < bt ) ) )
+                    bh = oh, bt = ot;
+            }
+            if( bt == 0x7fffffff || !( bh > Hen0 ) )
+                bh = Hen0, bt = en0;
+            max_H = __reduce_max_sync( FULL, bh );
+            max_t = __reduce_max_sync( FULL, bt );
+            __syncwarp( );
+            for( int t = en1; t < en0; ++t )
+            {
+                const int h = sm.H[ t & M ];
+                if( h > max_H )
+                    max_H = h, max_t = t;
+            }
+        }
+        else
+        {
+            Hen0 = sm.v[ 0 ] - qe;
+            if( is16 )
+                Hen0 = (short)Hen0;
+            __syncwarp( );
+            if( lane == 0 )
+                sm.H[ 0 ] = Hen0;
+            max_H = Hen0;
+            max_t = 0;
+            __syncwarp( );
+        }
+        if( en0 == tlen - 1 && Hen0 > ez.mte )
+            ez.mte = Hen0, ez.mte_q = (int)( r - en ); // sic: the aligned en
+        if( r - st0 == qlen - 1 )
+        {
+            const int hs = sm.H[ st0 & M ];
+            if( hs > ez.mqe )
+                ez.mqe = hs, ez.mqe_t = st0;
+        }
+        { // ksw_apply_zdrop (kswcpp_core.h:22-44)
+            const int rr = (int)r;
+            if( max_H > ez.max )
+                ez.max = max_H, ez.max_t = max_t, ez.max_q = rr - max_t;
+            else if( max_t >= ez.max_t && rr - max_t >= ez.max_q )
+            {
+                const int tl = max_t - ez.max_t, ql = ( rr - max_t ) - ez.max_q;
+                const int l = tl > ql ? tl - ql : ql - tl;
+                if( zdrop >= 0 && ez.max - max_H > zdrop + l * e2 )
+                {
+                    ez.zdropped = 1;
+                    break;
+                }
+            }
+        }
+        if( r == nrows - 1 && en0 == tlen - 1 )
+            ez.score = Hen0;
+        last_st = st, last_en = en;
+    }
+    ez.cells = cells;
+    __syncwarp( );
+}
+
+// decide where the backtrack starts (kswcpp_core.h:796-835); returns false if there is no backtrack
+__device__ __forceinline__ bool ksw_bt_start( KswOut& ez, int qlen, int tlen, int flag, int& i0, int& j0 )
+{
+    if( !ez.zdropped && !( flag & MA_KSW_EXTZ_ONLY ) )
+    {
+        i0 = tlen - 1, j0 = qlen - 1;
+        return true;
+    }
+    if( !ez.zdropped && ( flag & MA_KSW_EXTZ_ONLY ) && ez.mqe > ez.max )
+    {
+        ez.reach_end = 1;
+        i0 = ez.mqe_t, j0 = qlen - 1;
+        return true;
+    }
+    if( ez.max_t >= 0 && ez.max_q >= 0 )
+    {
+        i0 = ez.max_t, j0 = ez.max_q;
+        return true;
+    }
+    return false;
+}
+
+struct KswBatchArgs
+{
+    const KswTask* tasks;
+    const int* order; // task indices of this launch (binned by window size)
+    int n;
+    const unsigned char* seq;
+    KswOut* out;
+    unsigned int* cigar; // output slab
+    long long cigar_cap; // words
+    unsigned long long* cigar_cursor;
+    unsigned char* tb; // per-warp traceback slabs
+    long long tb_stride; // bytes per warp
+    unsigned int* cigscratch; // per-warp cigar scratch
+    int cigscratch_stride; // words per warp
+    int* next; // dynamic task queue
+    int* error;
+    KswScore score;
+};
+
+template <int W> __global__ void __launch_bounds__( 256 ) ksw_batch_kernel( KswBatchArgs A )
+{
+    extern __shared__ __align__( 16 ) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    KswSmem<W>& sm = reinterpret_cast<KswSmem<W>*>( smem_raw )[ warp ];
+    const long long gw = (long long)blockIdx.x * ( blockDim.x >> 5 ) + warp;
+    unsigned char* tb = A.tb + gw * A.tb_stride;
+    unsigned int* cs = A.cigscratch + gw * A.cigscratch_stride;
+    while( true )
+    {
+        int slot = 0;
+        if( lane == 0 )
+            slot = atomicAdd( A.next, 1 );
+        slot = __shfl_sync( 0xffffffffu, slot, 0 );
+        if( slot >= A.n )
+            break;
+        const int ti = A.order[ slot ];
+        const KswTask T = A.tasks[ ti ];
+        KswOut ez;
+        ksw_warp<W>( A.score, A.seq + T.qoff, T.qlen, A.seq + T.toff, T.tlen, T.w, T.zdrop, T.flag, sm, tb, ez );
+        ez.cigar_off = 0;
+        int i0 = 0, j0 = 0, n = 0;
+        const bool bBt = ( T.qlen > 0 && T.tlen > 0 && !A.score.early_return ) &&
+                         ksw_bt_start( ez, T.qlen, T.tlen, T.flag, i0, j0 );
+        if( bBt )
+        {
+            if( lane == 0 )
+                n = ksw_backtrack( tb, ksw_ncol16( T.qlen, T.tlen, T.w ), T.qlen, T.tlen,
+                                   T.w < 0 ? ( T.tlen > T.qlen ? T.tlen : T.qlen ) : T.w, i0, j0, cs,
+                                   A.cigscratch_stride );
+            n = __shfl_sync( 0xffffffffu, n, 0 );
+            unsigned long long o = 0;
+            if( n > 0 && lane == 0 )
+                o = atomicAdd( A.cigar_cursor, (unsigned long long)n );
+            o = __shfl_sync( 0xffffffffu, o, 0 );
+            if( n < 0 || (long long)( o + ( n > 0 ? n : 0 ) ) > A.cigar_cap )
+            {
+                if( lane == 0 )
+                    atomicExch( A.error, 1 );
+                ez.status = 1;
+                n = 0;
+            }
+            __syncwarp( );
+            // the walk produced ops end-to-start; the reference reverses unless REV_CIGAR is set
+            const bool rev = T.flag & MA_KSW_REV_CIGAR;
+            for( int k = lane; k < n; k += 32 )
+                A.cigar[ o + k ] = rev ? cs[ k ] : cs[ n - 1 - k ];
+            ez.n_cigar = n;
+            ez.cigar_off = (long long)o;
+        }
+        if( lane == 0 )
+            A.out[ ti ] = ez;
+        __syncwarp( );
+    }
+}
+
+} // namespace ma

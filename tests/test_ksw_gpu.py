@@ -1,0 +1,109 @@
+"""GPU parity: the sm_100a banded-DP kernel through the C ABI (ma_b200_ksw_batch) vs golden vectors and the oracle.
+
+Bit-exact bar: every kswcpp_extz_t field and every CIGAR word (integer work)."""
+import os
+
+import numpy as np
+import pytest
+
+import dpgen
+import helpers as H
+from ma_b200 import api
+
+pytestmark = pytest.mark.gpu
+FIELDS = ["max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "n_cigar", "reach_end"]
+
+
+def check_against_oracle(ctx, pairs):
+    tasks, seq = api.pack_ksw_tasks(pairs)
+    res, cig = ctx.ksw_batch(tasks, seq)
+    assert (res["status"] == 0).all()
+    cells = 0
+    for i, (w, zd, fl, q, t) in enumerate(pairs):
+        exp, ecig, ecells = H.oracle_ksw(q, t, w, zd, fl)
+        for k in FIELDS:
+            assert int(res[k][i]) == exp[k], (i, k, int(res[k][i]), exp[k], len(q), len(t), w, zd, fl)
+        got = cig[res["cigar_off"][i]:res["cigar_off"][i] + res["n_cigar"][i]]
+        assert np.array_equal(got, ecig), (i, got[:6], ecig[:6])
+        assert int(res["cells"][i]) == ecells
+        cells += ecells
+    return cells
+
+
+def test_golden_reference_vectors(gpu_ctx):
+    g = np.load(os.path.join(H.GOLDEN, "ksw_golden.npz"))
+    d = {"ksw_calls": g["calls"].astype(np.int64), "ksw_seq": g["seq"], "ksw_cigar": g["cigar"]}
+    calls = list(H.split_ksw_dump(d))
+    tasks, seq = api.pack_ksw_tasks([(f["w"], f["zdrop"], f["flag"], q, t) for f, q, t, c in calls])
+    res, cig = gpu_ctx.ksw_batch(tasks, seq)
+    for i, (f, q, t, c) in enumerate(calls):
+        for k in FIELDS:
+            assert int(res[k][i]) == f[k], (i, k, int(res[k][i]), f[k], f)
+        got = cig[res["cigar_off"][i]:res["cigar_off"][i] + res["n_cigar"][i]]
+        assert np.array_equal(got, c), (i, f)
+
+
+def test_random_mixed_vs_oracle(gpu_ctx):
+    check_against_oracle(gpu_ctx, dpgen.random_pairs(1500, seed=4242))
+
+
+@pytest.mark.parametrize("mode", [dpgen.GLOBAL, dpgen.EXT, dpgen.EXT_RIGHT])
+@pytest.mark.parametrize("length,w", [(100, 16), (300, 64), (1000, 128), (1366, 32), (3000, 256), (5000, 512)])
+def test_sweep_points_vs_oracle(gpu_ctx, mode, length, w):
+    n = 24 if length <= 1000 else 6
+    check_against_oracle(gpu_ctx, dpgen.sweep_pairs(n, length, w, mode, 0.05, seed=length * 7 + w))
+
+
+def test_illumina_like_end_extensions(gpu_ctx):
+    """The dominant DP shape of the Illumina preset: ~50 bp read tail against a 1000 bp padded window, w=512."""
+    rng = np.random.Generator(np.random.PCG64(31))
+    pairs = []
+    for i in range(200):
+        t = rng.integers(0, 4, size=int(rng.integers(950, 1060)), dtype=np.uint8)
+        q = dpgen.mutate(rng, t[:int(rng.integers(1, 90))], 0.03)
+        if len(q) == 0:
+            q = t[:1].copy()
+        pairs.append((512, 200, dpgen.EXT if i % 2 else dpgen.EXT_RIGHT, q, t))
+    check_against_oracle(gpu_ctx, pairs)
+
+
+def test_edge_cases(gpu_ctx):
+    e = np.zeros(0, np.uint8)
+    one = np.array([2], np.uint8)
+    allN = np.full(40, 4, np.uint8)
+    t = np.arange(64, dtype=np.uint8) & 3
+    pairs = [(10, -1, 0, e, one), (10, -1, 0, one, e), (10, -1, 0, one, one), (10, 200, dpgen.EXT, one, t),
+             (20, -1, 0, allN, t[:40]), (512, 200, dpgen.EXT_RIGHT, t, t), (0, -1, 0, t[:20], t[:20]),
+             (-1, -1, 0, t[:30], t[:50])]
+    check_against_oracle(gpu_ctx, pairs)
+
+
+def test_three_step_form_matches_batch(gpu_ctx):
+    pairs = dpgen.random_pairs(200, seed=5)
+    tasks, seq = api.pack_ksw_tasks(pairs)
+    r1, c1 = gpu_ctx.ksw_batch(tasks, seq)
+    gpu_ctx.ksw_upload(tasks, seq)
+    ms = gpu_ctx.ksw_run()
+    r2, c2 = gpu_ctx.ksw_download()
+    assert ms > 0
+    for k in FIELDS:
+        assert np.array_equal(r1[k], r2[k])
+    for i in range(len(pairs)):  # cigar slab order is allocation order (non-deterministic); compare per task
+        a = c1[r1["cigar_off"][i]:r1["cigar_off"][i] + r1["n_cigar"][i]]
+        b = c2[r2["cigar_off"][i]:r2["cigar_off"][i] + r2["n_cigar"][i]]
+        assert np.array_equal(a, b)
+
+
+def test_linearity_property_large_batch(gpu_ctx):
+    """Size-independent property at bench scale: identical sequences score 2*len, CIGAR = one M run; duplicating a
+    batch gives identical per-task results."""
+    rng = np.random.Generator(np.random.PCG64(8))
+    pairs = []
+    for i in range(20000):
+        t = rng.integers(0, 4, size=int(rng.integers(20, 200)), dtype=np.uint8)
+        pairs.append((20, -1, 0, t, t))
+    tasks, seq = api.pack_ksw_tasks(pairs)
+    res, cig = gpu_ctx.ksw_batch(tasks, seq)
+    assert np.array_equal(res["score"], 2 * tasks["qlen"])
+    assert (res["n_cigar"] == 1).all()
+    assert np.array_equal(cig[res["cigar_off"]], (tasks["qlen"].astype(np.uint32) << 4))
