@@ -1,0 +1,177 @@
+// CPU ORACLE — test infrastructure only (see oracle.h).
+// Runs the restated path over a read file and writes the same MADUMP1 container as oracle/ref_dump.cpp, so that
+// tests can compare oracle and compiled reference array by array.
+#include "ma_oracle.h"
+#include <cstdlib>
+#include <fstream>
+#include <list>
+#include <stdexcept>
+
+using namespace oracle;
+
+namespace
+{
+struct Dump
+{
+    std::list<std::pair<std::string, std::vector<int64_t>>> v;
+    std::vector<int64_t>& arr( const std::string& n )
+    {
+        for( auto& p : v )
+            if( p.first == n )
+                return p.second;
+        v.emplace_back( n, std::vector<int64_t>( ) );
+        return v.back( ).second;
+    }
+    void write( const std::string& f )
+    {
+        std::ofstream o( f, std::ios::binary );
+        o << "MADUMP1\n";
+        for( auto& p : v )
+        {
+            o << p.first << " " << p.second.size( ) << "\n";
+            o.write( (const char*)p.second.data( ), p.second.size( ) * 8 );
+        }
+    }
+};
+} // namespace
+
+// stages: 1 = seeding, 2 = + extract, 3 = + SoC, 4 = + harmonization, 5 = + DP/alignments
+extern "C" int ma_oracle_align_dump( const char* prefix, const char* reads_txt, const char* preset, const char* out,
+                                     long long srand_base, int stages, char* err, int errcap )
+{
+    try
+    {
+        Index I;
+        I.load( prefix );
+        Params P;
+        if( !P.preset( preset ) )
+            throw std::runtime_error( "unknown preset" );
+        std::ifstream in( reads_txt );
+        if( !in )
+            throw std::runtime_error( "cannot open reads" );
+        Dump D;
+        auto& seg_off = D.arr( "seg_off" );
+        auto& seg = D.arr( "seg" );
+        auto& seed_off = D.arr( "seed_off" );
+        auto& seed = D.arr( "seed" );
+        auto& soc_off = D.arr( "soc_off" );
+        auto& soc = D.arr( "soc" );
+        auto& socseed_off = D.arr( "socseed_off" );
+        auto& socseed = D.arr( "socseed" );
+        auto& harm_off = D.arr( "harm_off" );
+        auto& harmseed_off = D.arr( "harmseed_off" );
+        auto& harmseed = D.arr( "harmseed" );
+        auto& aln_off = D.arr( "aln_off" );
+        auto& aln = D.arr( "aln" );
+        auto& alndata_off = D.arr( "alndata_off" );
+        auto& alndata = D.arr( "alndata" );
+        auto& ksw_off = D.arr( "ksw_off" );
+        auto& ksw_calls = D.arr( "ksw_calls" );
+        auto& ksw_seq = D.arr( "ksw_seq" );
+        auto& ksw_cigar = D.arr( "ksw_cigar" );
+        auto& work = D.arr( "work" ); // per read: n_ext
+        for( auto* p : { &seg_off, &seed_off, &soc_off, &socseed_off, &harm_off, &harmseed_off, &aln_off,
+                         &alndata_off, &ksw_off } )
+            p->push_back( 0 );
+        std::string line;
+        size_t uiRead = 0;
+        while( std::getline( in, line ) )
+        {
+            if( line.empty( ) )
+                continue;
+            std::vector<uint8_t> q;
+            for( char c : line )
+                q.push_back( c == 'A' || c == 'a' ? 0 : c == 'C' || c == 'c' ? 1 : c == 'G' || c == 'g' ? 2
+                                                     : c == 'T' || c == 't' ? 3 : 4 );
+            int64_t nExt = 0;
+            auto segs = binary_seeding( I, P, q, &nExt );
+            work.push_back( nExt );
+            for( auto& s : segs )
+            {
+                int64_t a[ 5 ] = { s.start, s.size, s.sa.start, s.sa.rev, s.sa.size };
+                seg.insert( seg.end( ), a, a + 5 );
+            }
+            seg_off.push_back( seg.size( ) / 5 );
+            if( stages >= 2 )
+            {
+                auto seeds = extract_seeds( I, P, segs, (int64_t)q.size( ), nullptr );
+                for( auto& s : seeds )
+                {
+                    int64_t a[ 6 ] = { s.q, s.len, s.r, s.amb, s.fw, s.delta };
+                    seed.insert( seed.end( ), a, a + 6 );
+                }
+                seed_off.push_back( seed.size( ) / 6 );
+                if( stages >= 3 )
+                {
+                    SoCQueue Q = strip_of_consideration( I, P, seeds, (int64_t)q.size( ) );
+                    {
+                        SoCQueue C = Q; // pop a copy completely to record the whole pop order
+                        while( !C.maxima.empty( ) )
+                        {
+                            SoCOrder o = C.maxima.front( ).order;
+                            unsigned idx;
+                            auto pop = soc_pop( C, &idx );
+                            int64_t a[ 4 ] = { (int64_t)o.acc_len, o.amb, o.count, idx };
+                            soc.insert( soc.end( ), a, a + 4 );
+                            for( auto& s : pop )
+                            {
+                                int64_t b[ 4 ] = { s.q, s.len, s.r, s.fw };
+                                socseed.insert( socseed.end( ), b, b + 4 );
+                            }
+                            socseed_off.push_back( socseed.size( ) / 4 );
+                        }
+                    }
+                    soc_off.push_back( soc.size( ) / 4 );
+                    if( stages >= 4 )
+                    {
+                        if( srand_base >= 0 )
+                            srand( (unsigned)( srand_base + uiRead ) );
+                        auto sets = harmonization( I, P, Q, (int64_t)q.size( ) );
+                        for( auto& S : sets )
+                        {
+                            for( auto& s : S.seeds )
+                            {
+                                int64_t b[ 5 ] = { s.q, s.len, s.r, s.fw, S.soc_index };
+                                harmseed.insert( harmseed.end( ), b, b + 5 );
+                            }
+                            harmseed_off.push_back( harmseed.size( ) / 5 );
+                        }
+                        harm_off.push_back( harmseed_off.size( ) - 1 );
+                        if( stages >= 5 )
+                        {
+                            std::vector<KswCall> log;
+                            auto alns = needleman_wunsch( I, P, sets, q, &log );
+                            for( auto& c : log )
+                            {
+                                ksw_calls.insert( ksw_calls.end( ), c.f, c.f + 16 );
+                                ksw_seq.insert( ksw_seq.end( ), c.q.begin( ), c.q.end( ) );
+                                ksw_seq.insert( ksw_seq.end( ), c.t.begin( ), c.t.end( ) );
+                                ksw_cigar.insert( ksw_cigar.end( ), c.cigar.begin( ), c.cigar.end( ) );
+                            }
+                            ksw_off.push_back( ksw_calls.size( ) / 16 );
+                            for( auto& A : alns )
+                            {
+                                int64_t a[ 8 ] = { A.begin_q, A.end_q,      A.begin_ref, A.end_ref,
+                                                   A.score,   A.soc_index, A.length,    (int64_t)A.data.size( ) };
+                                aln.insert( aln.end( ), a, a + 8 );
+                                for( auto& d : A.data )
+                                    alndata.push_back( d.first ), alndata.push_back( d.second );
+                                alndata_off.push_back( alndata.size( ) / 2 );
+                            }
+                            aln_off.push_back( aln.size( ) / 8 );
+                        }
+                    }
+                }
+            }
+            uiRead++;
+        }
+        D.write( out );
+        return 0;
+    }
+    catch( const std::exception& e )
+    {
+        if( err && errcap > 0 )
+            snprintf( err, errcap, "%s", e.what( ) );
+        return -1;
+    }
+}

@@ -106,3 +106,15 @@ def write_pairs(path: str, pairs) -> None:
             qs = "".join(map(str, q.tolist())) or "-"
             ts = "".join(map(str, t.tolist())) or "-"
             f.write("%d %d %d %s %s\n" % (w, zdrop, flag, qs, ts))
+
+
+def oracle_align_dump(prefix: str, reads_txt: str, preset: str, out: str, srand_base: int = -1, stages: int = 5):
+    lib = oracle_lib()
+    err = ctypes.create_string_buffer(512)
+    lib.ma_oracle_align_dump.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p,
+                                         ctypes.c_longlong, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
+    rc = lib.ma_oracle_align_dump(prefix.encode(), reads_txt.encode(), preset.encode(), out.encode(), srand_base,
+                                  stages, err, 512)
+    if rc != 0:
+        raise RuntimeError("oracle: " + err.value.decode())
+    return load_dump(out)
