@@ -1,0 +1,469 @@
+// FM-index / pack accessors and the per-read seeding routine (BinarySeeding + seed enumeration), host+device.
+//
+// Replaces, bit-exactly:
+//   FMIndex::bwt_occ4 / bwt_2occ4      libs/ma/inc/ma/container/fMIndex.h:446-510, 671-754
+//   FMIndex::extend_backward           libs/ma/src/container/fMIndex.cpp:21-101
+//   FMIndex::bwt_sa / bwt_invPsi       fMIndex.h:329-343, 788-814
+//   BinarySeeding::execute / procesInterval / maximallySpanningExtension / smemExtension
+//                                       libs/ma/src/module/binarySeeding.cpp:32-178, inc/ma/module/binarySeeding.h:55-452
+//   SegmentVector::forEachSeed filter   libs/ma/inc/ma/container/segment.h:316-349
+//
+// HBM layout: the occurrence table keeps the reference's 64-byte block per 128 BWT symbols
+// (4 x u64 cumulative counts + 8 x u32 of 16 two-bit symbols), 64-byte aligned, so one bwt_occ4 is exactly one
+// 64-byte line fetched with four 128-bit loads; counting uses popcount on the two bit-planes instead of the
+// reference's 256-entry byte LUT (same values).
+#pragma once
+#include "stl_exact.cuh"
+#include <stdint.h>
+
+namespace ma
+{
+
+struct U4
+{
+    unsigned int x, y, z, w;
+};
+
+struct DevIndex
+{
+    const U4* bwt; // 4 x U4 per block
+    const long long* sa;
+    const unsigned char* pac;
+    const long long* contig_start;
+    const long long* contig_len;
+    long long L2[ 5 ];
+    long long primary, ref_len, fwd_len;
+    int sa_intv, n_contigs;
+};
+
+MA_HD inline int popc32( unsigned int v )
+{
+#if defined( __CUDA_ARCH__ )
+    return __popc( v );
+#else
+    return __builtin_popcount( v );
+#endif
+}
+
+MA_HD inline U4 ld_u4( const U4* p )
+{
+#if defined( __CUDA_ARCH__ )
+    const uint4 v = __ldg( reinterpret_cast<const uint4*>( p ) );
+    return U4{ v.x, v.y, v.z, v.w };
+#else
+    return *p;
+#endif
+}
+
+// counts of C, G, T among the first `nvalid` (0..16) symbols of a 16-symbol word (MSB first)
+MA_HD inline void count_word( unsigned int w, int nvalid, int& c, int& g, int& t )
+{
+    if( nvalid <= 0 )
+        return;
+    if( nvalid < 16 )
+        w &= 0xFFFFFFFFu << ( 32 - 2 * nvalid );
+    const unsigned int hi = ( w >> 1 ) & 0x55555555u, lo = w & 0x55555555u;
+    t += popc32( hi & lo );
+    g += popc32( hi & ~lo );
+    c += popc32( lo & ~hi );
+}
+
+// bwt_occ4: number of A,C,G,T in BWT[0..k] (k == -1 -> zeros)
+MA_HD inline void occ4( const DevIndex& I, long long k, long long cnt[ 4 ] )
+{
+    if( k == -1 )
+    {
+        cnt[ 0 ] = cnt[ 1 ] = cnt[ 2 ] = cnt[ 3 ] = 0;
+        return;
+    }
+    k -= ( k >= I.primary );
+    const U4* blk = I.bwt + ( ( k >> 7 ) << 2 );
+    const U4 c0 = ld_u4( blk ), c1 = ld_u4( blk + 1 ), w0 = ld_u4( blk + 2 ), w1 = ld_u4( blk + 3 );
+    const int n = (int)( k & 127 ) + 1; // symbols of this block to count
+    int c = 0, g = 0, t = 0;
+    count_word( w0.x, n, c, g, t );
+    count_word( w0.y, n - 16, c, g, t );
+    count_word( w0.z, n - 32, c, g, t );
+    count_word( w0.w, n - 48, c, g, t );
+    count_word( w1.x, n - 64, c, g, t );
+    count_word( w1.y, n - 80, c, g, t );
+    count_word( w1.z, n - 96, c, g, t );
+    count_word( w1.w, n - 112, c, g, t );
+    cnt[ 0 ] = (long long)( ( (unsigned long long)c0.y << 32 ) | c0.x ) + ( n - c - g - t );
+    cnt[ 1 ] = (long long)( ( (unsigned long long)c0.w << 32 ) | c0.z ) + c;
+    cnt[ 2 ] = (long long)( ( (unsigned long long)c1.y << 32 ) | c1.x ) + g;
+    cnt[ 3 ] = (long long)( ( (unsigned long long)c1.w << 32 ) | c1.z ) + t;
+}
+
+struct SAI
+{
+    long long start, rev, size;
+};
+
+MA_HD inline SAI sai_rc( const SAI& a )
+{
+    return SAI{ a.rev, a.start, a.size };
+}
+
+MA_HD inline SAI init_interval( const DevIndex& I, int c )
+{
+    return SAI{ I.L2[ c ] + 1, I.L2[ 3 - c ] + 1, I.L2[ c + 1 ] - I.L2[ c ] };
+}
+
+MA_HD inline SAI extend_backward( const DevIndex& I, const SAI& ik, int c )
+{
+    if( c >= 4 )
+        return SAI{ 0, 0, 0 };
+    long long ck[ 4 ], cl[ 4 ];
+    occ4( I, ik.start - 1, ck );
+    occ4( I, ik.start + ik.size - 1, cl );
+    const long long s0 = cl[ 0 ] - ck[ 0 ], s1 = cl[ 1 ] - ck[ 1 ], s2 = cl[ 2 ] - ck[ 2 ], s3 = cl[ 3 ] - ck[ 3 ];
+    long long k2_0 = ik.rev;
+    if( ik.start <= I.primary && ik.start + ik.size > I.primary )
+        k2_0++;
+    const long long k2_1 = k2_0 + s3, k2_2 = k2_1 + s2, k2_3 = k2_2 + s1; // cntk_2[i] = cntk_2[i-1] + cnts[3-(i-1)]
+    switch( c )
+    {
+        case 0: return SAI{ I.L2[ 0 ] + ck[ 0 ] + 1, k2_3, s0 };
+        case 1: return SAI{ I.L2[ 1 ] + ck[ 1 ] + 1, k2_2, s1 };
+        case 2: return SAI{ I.L2[ 2 ] + ck[ 2 ] + 1, k2_1, s2 };
+        default: return SAI{ I.L2[ 3 ] + ck[ 3 ] + 1, k2_0, s3 };
+    }
+}
+
+// bwt_invPsi (fMIndex.h:329-343): one block read (B0 and occ hit the same 64-byte block)
+MA_HD inline long long inv_psi( const DevIndex& I, long long k )
+{
+    if( k == I.primary )
+        return 0;
+    const long long x = k - ( k > I.primary );
+    // occ(k, c): k == ref_len -> total count; else inclusive count through k - (k >= primary) == x for k != primary
+    const U4* blk = I.bwt + ( ( x >> 7 ) << 2 );
+    const U4 c0 = ld_u4( blk ), c1 = ld_u4( blk + 1 ), w0 = ld_u4( blk + 2 ), w1 = ld_u4( blk + 3 );
+    const unsigned int words[ 8 ] = { w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w };
+    const int pos = (int)( x & 127 );
+    const int ch = (int)( words[ pos >> 4 ] >> ( ( ~pos & 15 ) << 1 ) & 3 );
+    if( k == I.ref_len )
+        return I.L2[ ch ] + ( I.L2[ ch + 1 ] - I.L2[ ch ] );
+    const int n = pos + 1;
+    int c = 0, g = 0, t = 0;
+    for( int j = 0; j < 8; j++ )
+        count_word( words[ j ], n - 16 * j, c, g, t );
+    long long occ;
+    switch( ch )
+    {
+        case 0: occ = (long long)( ( (unsigned long long)c0.y << 32 ) | c0.x ) + ( n - c - g - t ); break;
+        case 1: occ = (long long)( ( (unsigned long long)c0.w << 32 ) | c0.z ) + c; break;
+        case 2: occ = (long long)( ( (unsigned long long)c1.y << 32 ) | c1.x ) + g; break;
+        default: occ = (long long)( ( (unsigned long long)c1.w << 32 ) | c1.z ) + t; break;
+    }
+    return I.L2[ ch ] + occ;
+}
+
+// bwt_sa (fMIndex.h:788-814); *pSteps receives the number of invPsi steps (roofline accounting)
+MA_HD inline long long bwt_sa( const DevIndex& I, long long k, int* pSteps )
+{
+    long long s = 0;
+    const long long mask = I.sa_intv - 1;
+    while( k & mask )
+    {
+        ++s;
+        k = inv_psi( I, k );
+    }
+    if( pSteps )
+        *pSteps = (int)s;
+    return s + I.sa[ k / I.sa_intv ];
+}
+
+// ---- pack --------------------------------------------------------------------------------------------------
+MA_HD inline int pack_nuc( const DevIndex& I, long long pos )
+{
+    return I.pac[ pos >> 2 ] >> ( ( ~pos & 3 ) << 1 ) & 3;
+}
+// base of the virtual text forward ++ reverse-complement at position p (Pack::vExtract, pack.h:1429-1435)
+MA_HD inline int pack_virtual( const DevIndex& I, long long p )
+{
+    return p < I.fwd_len ? pack_nuc( I, p ) : 3 - pack_nuc( I, 2 * I.fwd_len - 1 - p );
+}
+// Pack::uiSequenceIdForPosition (pack.h:933-990) including the fall-through of its binary search
+MA_HD inline long long seq_id_for_position( const DevIndex& I, long long pos )
+{
+    const long long a = pos >= I.fwd_len ? 2 * I.fwd_len - ( pos + 1 ) : pos;
+    unsigned long long l = 0, m = 0, r = (unsigned long long)I.n_contigs;
+    while( l < r )
+    {
+        m = ( l + r ) / 2;
+        if( a >= I.contig_start[ m ] )
+        {
+            if( m == (unsigned long long)I.n_contigs - 1 )
+                break;
+            if( a < I.contig_start[ m + 1 ] )
+                break;
+            l = m + 1;
+        }
+        else
+            r = m;
+    }
+    return (long long)m;
+}
+MA_HD inline long long seq_id_or_rev( const DevIndex& I, long long pos ) // pack.h:1029-1034
+{
+    if( pos >= I.fwd_len )
+        return seq_id_for_position( I, 2 * I.fwd_len - ( pos + 1 ) ) * 2 + 1;
+    return seq_id_for_position( I, pos ) * 2;
+}
+MA_HD inline long long end_of_seq_or_rev( const DevIndex& I, long long id ) // pack.h:1040-1045
+{
+    if( id % 2 == 1 )
+        return ( 2 * I.fwd_len - ( I.contig_start[ id / 2 ] + 1 ) ) - 1;
+    return I.contig_start[ id / 2 ] + I.contig_len[ id / 2 ];
+}
+MA_HD inline long long start_of_seq_or_rev( const DevIndex& I, long long id ) // pack.h:1047-1052
+{
+    if( id % 2 == 1 )
+        return ( 2 * I.fwd_len - ( I.contig_start[ id / 2 ] + I.contig_len[ id / 2 ] + 1 ) ) + 1;
+    return I.contig_start[ id / 2 ];
+}
+MA_HD inline bool bridging_subsection( const DevIndex& I, long long begin, long long size ) // pack.h:1072-1087
+{
+    if( size <= 0 )
+        return false;
+    return ( begin >= I.fwd_len ) != ( begin + size - 1 >= I.fwd_len ) ||
+           seq_id_or_rev( I, begin ) != seq_id_or_rev( I, begin + size - 1 );
+}
+
+// ---- seeding -------------------------------------------------------------------------------------------------
+struct SeedParams
+{
+    int technique; // 0 maxSpan, 1 SMEM
+    int min_amb, max_amb;
+    int min_seed_len;
+    int drop_min_size;
+    double drop_factor;
+    int disable_heuristics;
+    long long genome_size_disable;
+};
+
+struct SegRec // one segment (query interval + SA interval); size = length - 1
+{
+    int start, size;
+    SAI sa;
+};
+
+// Per-thread working memory for the SMEM interval lists (two ping-pong lists of up to cap entries)
+struct SeedScratch
+{
+    SegRec* listA;
+    SegRec* listB;
+    int cap;
+};
+
+// Sink interface: void seg( const SegRec& ) is called for every segment in the reference's emission order
+// (DFS pre-order).  Returns false in *pOverflow if a list overflowed its capacity.
+template <class Sink> struct Seeder
+{
+    const DevIndex& I;
+    const SeedParams& P;
+    const unsigned char* q;
+    const int L;
+    SeedScratch S;
+    Sink& sink;
+    long long nExt = 0;
+    bool overflow = false;
+    int lastStart = -1, lastEnd = -1; // start/end() of the most recently emitted segment (maxSpan duplicate check)
+
+    MA_HD Seeder( const DevIndex& I, const SeedParams& P, const unsigned char* q, int L, SeedScratch S, Sink& sink )
+        : I( I ), P( P ), q( q ), L( L ), S( S ), sink( sink )
+    {}
+    MA_HD static int comp( int c )
+    {
+        return c < 4 ? 3 - c : 5;
+    }
+    MA_HD SAI ext( const SAI& ik, int c )
+    {
+        nExt++;
+        return extend_backward( I, ik, c );
+    }
+    MA_HD bool stop( const SAI& ok, const SAI& ik ) const
+    {
+        return ok.size <= 0 || ( ok.size <= P.min_amb && ik.size <= P.max_amb );
+    }
+    MA_HD void emit( int start, int size, const SAI& sa )
+    {
+        SegRec r{ start, size, sa };
+        lastStart = start, lastEnd = start + size;
+        sink.seg( r );
+    }
+    // binarySeeding.h:55-252. cs/ce = covered start / end() (index of the last covered base, or center+1 for N)
+    MA_HD void maxSpan( int center, int& cs, int& ce )
+    {
+        if( q[ center ] >= 4 )
+        {
+            cs = center, ce = center + 1;
+            return;
+        }
+        SAI ik = init_interval( I, comp( q[ center ] ) );
+        if( ik.size == 0 )
+        {
+            cs = center, ce = center + 1;
+            return;
+        }
+        int end = center;
+        for( int i = center + 1; i < L; i++ )
+        {
+            SAI ok = ext( ik, comp( q[ i ] ) );
+            if( stop( ok, ik ) )
+                break;
+            end = i, ik = ok;
+        }
+        ik = sai_rc( ik );
+        int start = center;
+        for( int i = center - 1; i >= 0; i-- )
+        {
+            SAI ok = ext( ik, q[ i ] );
+            if( stop( ok, ik ) )
+                break;
+            start = i, ik = ok;
+        }
+        emit( start, end - start, ik );
+        const int s1 = start, e1 = end;
+        ik = init_interval( I, q[ center ] );
+        start = center;
+        for( int i = center - 1; i >= 0; i-- )
+        {
+            SAI ok = ext( ik, q[ i ] );
+            if( stop( ok, ik ) )
+                break;
+            start = i, ik = ok;
+        }
+        ik = sai_rc( ik );
+        end = center;
+        for( int i = center + 1; i < L; i++ )
+        {
+            SAI ok = ext( ik, comp( q[ i ] ) );
+            if( stop( ok, ik ) )
+                break;
+            end = i, ik = ok;
+        }
+        if( s1 == start && e1 == end )
+        {
+            cs = s1, ce = e1;
+            return;
+        }
+        emit( start, end - start, sai_rc( ik ) );
+        cs = s1 < start ? s1 : start;
+        ce = e1 > end ? e1 : end;
+    }
+    // binarySeeding.h:261-452
+    MA_HD void smem( int center, int& cs, int& ce )
+    {
+        cs = center, ce = center;
+        if( q[ center ] >= 4 )
+        {
+            ce = center + 1;
+            return;
+        }
+        SAI ik = init_interval( I, comp( q[ center ] ) );
+        SegRec* curr = S.listA;
+        SegRec* next = S.listB;
+        int nCurr = 0, nNext = 0;
+        for( int i = center + 1; i < L; i++ )
+        {
+            SAI ok = ext( ik, comp( q[ i ] ) );
+            if( ok.size != ik.size )
+            {
+                if( nCurr < S.cap )
+                    curr[ nCurr ] = SegRec{ center, i - center - 1, sai_rc( ik ) };
+                else
+                    overflow = true;
+                nCurr++;
+            }
+            if( i == L - 1 && ok.size != 0 )
+            {
+                if( nCurr < S.cap )
+                    curr[ nCurr ] = SegRec{ center, i - center, sai_rc( ok ) };
+                else
+                    overflow = true;
+                nCurr++;
+            }
+            if( ok.size == 0 )
+                break;
+            if( ok.size <= P.min_amb && ik.size <= P.max_amb )
+                break;
+            ik = ok;
+            ce = i;
+        }
+        if( nCurr > S.cap )
+            nCurr = S.cap;
+        for( int a = 0, b = nCurr - 1; a < b; a++, b-- ) // std::reverse
+            stl::swp( curr[ a ], curr[ b ] );
+        if( center != 0 )
+            for( int i = center - 1; i >= 0; i-- )
+            {
+                bool bHaveOne = false;
+                nNext = 0;
+                for( int j = 0; j < nCurr; j++ )
+                {
+                    const SegRec s = curr[ j ];
+                    SAI ok = ext( s.sa, q[ i ] );
+                    if( ok.size <= P.min_amb && !bHaveOne )
+                    {
+                        emit( s.start, s.size, s.sa );
+                        bHaveOne = true;
+                    }
+                    // sic: s.size is the query-interval size field (binarySeeding.h:404)
+                    else if( ok.size > P.min_amb || ( ok.size > 0 && s.size >= P.max_amb ) )
+                        next[ nNext++ ] = SegRec{ i, s.size + 1, ok };
+                }
+                SegRec* t = curr;
+                curr = next, next = t;
+                nCurr = nNext;
+                if( nCurr == 0 )
+                    break;
+                cs = i;
+                if( i == 0 )
+                    break;
+            }
+        if( nCurr != 0 )
+            emit( curr[ 0 ].start, curr[ 0 ].size, curr[ 0 ].sa );
+    }
+    // binarySeeding.cpp:32-84 with the recursion replaced by an explicit LIFO of pending right-hand areas
+    MA_HD void run( )
+    {
+        if( L <= 0 )
+            return;
+        const int STK = 64;
+        int stS[ STK ], stN[ STK ];
+        int sp = 0;
+        stS[ sp ] = 0, stN[ sp ] = L, sp++;
+        while( sp > 0 )
+        {
+            --sp;
+            const int aStart = stS[ sp ], aSize = stN[ sp ];
+            const int center = aStart + aSize / 2;
+            int cs, ce;
+            if( P.technique == 0 )
+                maxSpan( center, cs, ce );
+            else
+                smem( center, cs, ce );
+            const int aEnd = aStart + aSize;
+            // the right remainder is processed after the complete left subtree: push it first
+            if( aEnd > ce + 1 )
+            {
+                if( sp < STK )
+                    stS[ sp ] = ce, stN[ sp ] = aEnd - ce, sp++;
+                else
+                    overflow = true;
+            }
+            if( cs != 0 && aStart + 1 < cs )
+            {
+                if( sp < STK )
+                    stS[ sp ] = aStart, stN[ sp ] = cs - aStart, sp++;
+                else
+                    overflow = true;
+            }
+        }
+    }
+};
+
+} // namespace ma

@@ -14,37 +14,13 @@
 //  * one traceback byte per cell is written coalesced to a per-warp slab in HBM (stays L2 resident) and walked by
 //    lane 0 afterwards; the CIGAR is then copied out by the whole warp to a bump-allocated output slab.
 #pragma once
+#include "fmindex.cuh"
+#include "ksw_types.cuh"
 #include <cstdint>
 #include <cuda_runtime.h>
 
 namespace ma
 {
-
-struct KswTask
-{
-    long long qoff, toff; // byte offsets into the sequence slab
-    int qlen, tlen, w, zdrop, flag, tag;
-};
-
-struct KswOut
-{
-    int max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, n_cigar, reach_end, status;
-    long long cigar_off; // word offset into the cigar slab
-    long long cells; // band cells processed (st0..en0 over all rows) — the GCUPS unit
-};
-
-struct KswScore
-{
-    int match, mismatch; // mismatch as a (negative) score
-    int q, e, q2, e2; // after the q/q2 swap of kswcpp_core.h:367-375
-    int long_thres, long_diff;
-    int min16; // iOverallMinScr (negative) for the int16/int32 switch, kswcpp.h:101-115
-    int early_return; // -min_sc > 2(q+e): the reference returns right after ksw_reset_extz
-};
-
-#define MA_KSW_RIGHT 0x02
-#define MA_KSW_EXTZ_ONLY 0x40
-#define MA_KSW_REV_CIGAR 0x80
 
 __device__ __forceinline__ int w8( int x )
 {
@@ -147,11 +123,38 @@ __device__ inline int ksw_backtrack( const unsigned char* tb, int ncol16, int ql
     return n > cap ? -1 : n;
 }
 
+// Where the two sequences of a problem live. Standalone batches (ma_b200_ksw_batch) read both from a byte slab;
+// the alignment pipeline reads the query from the read slab (forwards or backwards) and the target straight from
+// the 2-bit pack through its virtual forward+reverse-complement text, so no reference window is ever materialised.
+struct SeqAccess
+{
+    const unsigned char* qbase;
+    long long qoff;
+    int qstep;
+    const unsigned char* tslab;
+    const unsigned char* pac;
+    long long fwd_len;
+    long long toff;
+    int tstep;
+    __device__ __forceinline__ int Q( long long i ) const
+    {
+        return qbase[ qoff + qstep * i ];
+    }
+    __device__ __forceinline__ int T( long long i ) const
+    {
+        const long long p = toff + tstep * i;
+        if( pac == nullptr )
+            return tslab[ p ];
+        const long long f = p < fwd_len ? p : 2 * fwd_len - 1 - p;
+        const int b = pac[ f >> 2 ] >> ( ( ~f & 3 ) << 1 ) & 3;
+        return p < fwd_len ? b : 3 - b;
+    }
+};
+
 // One warp, one problem. All lanes return the same KswOut (cigar_off/n_cigar are filled by the caller).
 // tb: per-warp traceback slab of >= (qlen+tlen-1)*ncol16 bytes.
 template <int W>
-__device__ void ksw_warp( const KswScore& P, const unsigned char* __restrict__ query, int qlen,
-                          const unsigned char* __restrict__ target, int tlen, int w, int zdrop, int flag,
+__device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int tlen, int w, int zdrop, int flag,
                           KswSmem<W>& sm, unsigned char* __restrict__ tb, KswOut& ez )
 {
     const unsigned FULL = 0xffffffffu;
@@ -230,9 +233,9 @@ __device__ void ksw_warp( const KswScore& P, const unsigned char* __restrict__ q
         // score profile from the unaligned st0 in steps of 16 (kswcpp_core.h:591-616); N scores -e2
         for( int tt = st0 + lane; tt < sEnd && tt < T16; tt += 32 )
         {
-            const int a = tt < tlen ? target[ tt ] : 0;
+            const int a = tt < tlen ? seq.T( tt ) : 0;
             const long long qi = r - tt;
-            const int b = ( qi >= 0 && qi < qlen ) ? query[ qi ] : 0;
+            const int b = ( qi >= 0 && qi < qlen ) ? seq.Q( qi ) : 0;
             sm.s[ tt & M ] = (signed char)( ( a == 4 || b == 4 ) ? -e2 : ( a == b ? P.match : P.mismatch ) );
         }
         __syncwarp( );
@@ -417,7 +420,9 @@ struct KswBatchArgs
     const KswTask* tasks;
     const int* order; // task indices of this launch (binned by window size)
     int n;
-    const unsigned char* seq;
+    const unsigned char* seq; // byte slab (standalone batches) or the read slab (pipeline)
+    const unsigned char* pac; // pack of the uploaded index (pipeline tasks with MA_TASK_TPACK)
+    long long fwd_len;
     KswOut* out;
     unsigned int* cigar; // output slab
     long long cigar_cap; // words
@@ -450,7 +455,11 @@ template <int W> __global__ void __launch_bounds__( 256 ) ksw_batch_kernel( KswB
         const int ti = A.order[ slot ];
         const KswTask T = A.tasks[ ti ];
         KswOut ez;
-        ksw_warp<W>( A.score, A.seq + T.qoff, T.qlen, A.seq + T.toff, T.tlen, T.w, T.zdrop, T.flag, sm, tb, ez );
+        SeqAccess sa;
+        sa.qbase = A.seq, sa.qoff = T.qoff, sa.qstep = ( T.tag & MA_TASK_QREV ) ? -1 : 1;
+        sa.tslab = A.seq, sa.toff = T.toff, sa.tstep = ( T.tag & MA_TASK_TREV ) ? -1 : 1;
+        sa.pac = ( T.tag & MA_TASK_TPACK ) ? A.pac : nullptr, sa.fwd_len = A.fwd_len;
+        ksw_warp<W>( A.score, sa, T.qlen, T.tlen, T.w, T.zdrop, T.flag, sm, tb, ez );
         ez.cigar_off = 0;
         int i0 = 0, j0 = 0, n = 0;
         const bool bBt = ( T.qlen > 0 && T.tlen > 0 && !A.score.early_return ) &&

@@ -322,6 +322,7 @@ static int ksw_run_once( ma_b200_ctx* ctx )
         A.order = ctx->ksw_order.p + o;
         A.n = (int)bin.order.size( );
         A.seq = ctx->ksw_seq.p;
+        A.pac = nullptr, A.fwd_len = 0;
         A.out = ctx->ksw_out.p;
         A.cigar = ctx->ksw_cigar.p;
         A.cigar_cap = ctx->ksw_cigar_cap;
