@@ -103,6 +103,109 @@ int ma_b200_ksw_batch( ma_b200_ctx* ctx, int64_t n, const ma_b200_ksw_task* task
                        int64_t seq_bytes, ma_b200_ksw_result* results, uint32_t* cigar, int64_t cigar_cap_words,
                        int64_t* cigar_words );
 
+/* ---- index: replaces FMIndex / Pack loading (fMIndex.h:854-884, pack.h:513-525, 799-812) --------------------- */
+/* Uploads (replicates) the reference's own index arrays into HBM:
+ *   bwt_words : FMIndex::bwt, 16 x u32 per 128 symbols = 4 x u64 counts + 8 x u32 symbols (fMIndex.h:434-437)
+ *   L2[5]     : cumulative counts, L2[0] = 0 (fMIndex.h:195);  primary (fMIndex.h:200);  ref_len = forward + reverse
+ *   sa        : one sample per sa_intv rows, sa[0] = -1 (fMIndex.h:602-663)
+ *   pac       : Pack::xPackedNucSeqs, 2 bit per forward-strand base (pack.h:172-176);  fwd_len = forward length
+ *   contig_start / contig_len : Pack::xVectorOfSequenceDescriptors (pack.h:823-860) */
+int ma_b200_index_upload( ma_b200_ctx* ctx, const uint32_t* bwt_words, int64_t n_words, const int64_t* L2,
+                          int64_t primary, int64_t ref_len, const int64_t* sa, int64_t n_sa, int32_t sa_intv,
+                          const uint8_t* pac, int64_t n_pac_bytes, int64_t fwd_len, const int64_t* contig_start,
+                          const int64_t* contig_len, int32_t n_contigs );
+/* Builds the same index on the GPU from the forward strand (1 byte per base, codes 0..3, contigs concatenated):
+ * suffix array of forward ++ reverse-complement by prefix doubling, BWT, occurrence blocks, SA samples.  The result
+ * is bit-identical to FMIndex(pPack) (fMIndex.cpp:316-391) and stays resident; ma_b200_index_download copies it
+ * out in the layout of ma_b200_index_upload (sizes via ma_b200_index_sizes). */
+int ma_b200_index_build( ma_b200_ctx* ctx, const uint8_t* fwd, int64_t fwd_len, const int64_t* contig_start,
+                         const int64_t* contig_len, int32_t n_contigs );
+int ma_b200_index_sizes( ma_b200_ctx* ctx, int64_t* n_words, int64_t* n_sa, int64_t* n_pac_bytes, int64_t* primary,
+                         int64_t* L2 /* 5 */ );
+int ma_b200_index_download( ma_b200_ctx* ctx, uint32_t* bwt_words, int64_t* sa, uint8_t* pac );
+
+/* ---- the alignment path ------------------------------------------------------------------------------------ */
+/* replaces, per read, the chain wired by setUpCompGraph (libs/ma/src/util/export.cpp:99-126):
+ *   BinarySeeding::execute -> StripOfConsideration::execute (ExtractSeeds + StripOfConsiderationSeeds)
+ *   -> Harmonization::execute -> NeedlemanWunsch::execute */
+#define MA_B200_STAGE_SEEDS 1 /* BinarySeeding + ExtractSeeds: located seeds in emission order */
+#define MA_B200_STAGE_SETS 2 /* + StripOfConsiderationSeeds + Harmonization: harmonized seed sets */
+#define MA_B200_STAGE_ALIGN 3 /* + NeedlemanWunsch: alignments */
+
+typedef struct /* Seed (seed.h:34-43) */
+{
+    int32_t q, len;
+    int64_t r; /* start on the (folded) forward strand, see segment.h:99-105 */
+    uint32_t ambiguity;
+    int32_t on_forward;
+    int64_t delta;
+} ma_b200_seed;
+
+typedef struct /* Segment (segment.h:31-115): query interval (size = length - 1) + SAInterval */
+{
+    int32_t start, size;
+    int64_t sa_start, sa_rev_start, sa_size;
+} ma_b200_segment;
+
+typedef struct /* one harmonized seed set (Seeds + xStats.index_of_strip) */
+{
+    int32_t read, ordinal;
+    uint32_t soc_index;
+    int32_t n;
+    int64_t seed_off;
+    int32_t task_off, n_tasks;
+    uint64_t win_begin, win_end;
+    int32_t valid, pad;
+} ma_b200_seed_set;
+
+typedef struct /* Alignment (alignment.h:55-95); runs: word = len << 3 | MatchType (seed 0, match 1, missmatch 2, */
+{ /*              insertion 3, deletion 4), alignment.h:40-47 */
+    int64_t begin_ref, end_ref, score;
+    int32_t begin_q, end_q;
+    int32_t length, n_runs;
+    uint32_t soc_index;
+    int32_t read;
+    int64_t run_off;
+    int32_t rank; /* position in the read's result vector after the reference's final sort */
+    int32_t pad;
+} ma_b200_alignment;
+
+typedef struct /* per read: where its seeds / sets / alignments are */
+{
+    int64_t seed_off;
+    int32_t n_seeds;
+    int32_t set_off; /* also the offset of the read's alignments (one per set) */
+    int32_t n_sets;
+    int32_t pad;
+} ma_b200_read_info;
+
+typedef struct
+{
+    int64_t n_reads, n_seeds, n_sets, n_set_seeds, n_tasks, n_runs, n_cigar_words;
+    int64_t n_ext; /* FMIndex::extend_backward calls: 128 algorithmic bytes each */
+    int64_t n_invpsi; /* bwt_invPsi steps: 64 algorithmic bytes each */
+    int64_t n_dropped; /* reads cleared by the seeding drop-off */
+    int64_t dp_cells; /* band cells */
+    float ms_seed, ms_locate, ms_socharm, ms_plan, ms_dp, ms_assemble, ms_total;
+    int32_t launches;
+} ma_b200_align_stats;
+
+/* reads: concatenated, 1 byte per base; offsets[n_reads + 1].  Stays resident until the next upload. */
+int ma_b200_align_upload( ma_b200_ctx* ctx, int64_t n_reads, const uint8_t* reads, const int64_t* offsets );
+/* keep_segments > 0: additionally record up to keep_segments segments per read (parity tests of BinarySeeding). */
+int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t keep_segments, ma_b200_align_stats* stats );
+int ma_b200_align_download_info( ma_b200_ctx* ctx, ma_b200_read_info* info );
+int ma_b200_align_download_segments( ma_b200_ctx* ctx, ma_b200_segment* segs, int32_t* n_segs );
+int ma_b200_align_download_seeds( ma_b200_ctx* ctx, ma_b200_seed* seeds, int64_t cap );
+int ma_b200_align_download_sets( ma_b200_ctx* ctx, ma_b200_seed_set* sets, int64_t cap_sets, ma_b200_seed* seeds,
+                                 int64_t cap_seeds );
+int ma_b200_align_download( ma_b200_ctx* ctx, ma_b200_read_info* info, ma_b200_alignment* alns, int64_t cap_alns,
+                            uint32_t* runs, int64_t cap_runs );
+/* One call, host buffers in and out (upload + all stages + download): the drop-in for a batch of reads. */
+int ma_b200_align_batch( ma_b200_ctx* ctx, int64_t n_reads, const uint8_t* reads, const int64_t* offsets,
+                         ma_b200_read_info* info, ma_b200_alignment* alns, int64_t cap_alns, uint32_t* runs,
+                         int64_t cap_runs, ma_b200_align_stats* stats );
+
 #ifdef __cplusplus
 }
 #endif

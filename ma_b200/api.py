@@ -46,6 +46,30 @@ KSW_RESULT_DTYPE = np.dtype([("max", "<i4"), ("zdropped", "<i4"), ("max_q", "<i4
                              ("n_cigar", "<i4"), ("reach_end", "<i4"), ("status", "<i4"), ("cigar_off", "<i8"),
                              ("cells", "<i8")])
 
+SEED_DTYPE = np.dtype([("q", "<i4"), ("len", "<i4"), ("r", "<i8"), ("amb", "<u4"), ("fw", "<i4"), ("delta", "<i8")])
+SEGMENT_DTYPE = np.dtype([("start", "<i4"), ("size", "<i4"), ("sa_start", "<i8"), ("sa_rev", "<i8"),
+                          ("sa_size", "<i8")])
+SET_DTYPE = np.dtype([("read", "<i4"), ("ordinal", "<i4"), ("soc_index", "<u4"), ("n", "<i4"), ("seed_off", "<i8"),
+                      ("task_off", "<i4"), ("n_tasks", "<i4"), ("win_begin", "<u8"), ("win_end", "<u8"),
+                      ("valid", "<i4"), ("pad", "<i4")])
+ALN_DTYPE = np.dtype([("begin_ref", "<i8"), ("end_ref", "<i8"), ("score", "<i8"), ("begin_q", "<i4"),
+                      ("end_q", "<i4"), ("length", "<i4"), ("n_runs", "<i4"), ("soc_index", "<u4"), ("read", "<i4"),
+                      ("run_off", "<i8"), ("rank", "<i4"), ("pad", "<i4")])
+INFO_DTYPE = np.dtype([("seed_off", "<i8"), ("n_seeds", "<i4"), ("set_off", "<i4"), ("n_sets", "<i4"),
+                       ("pad", "<i4")])
+STAGE_SEEDS, STAGE_SETS, STAGE_ALIGN = 1, 2, 3
+
+
+class AlignStats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int64) for n in ("n_reads", "n_seeds", "n_sets", "n_set_seeds", "n_tasks", "n_runs",
+                                              "n_cigar_words", "n_ext", "n_invpsi", "n_dropped", "dp_cells")] + \
+               [(n, ctypes.c_float) for n in ("ms_seed", "ms_locate", "ms_socharm", "ms_plan", "ms_dp",
+                                              "ms_assemble", "ms_total")] + [("launches", ctypes.c_int32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 _lib = None
 
 
@@ -76,6 +100,19 @@ def load_library():
     lib.ma_b200_ksw_run.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     lib.ma_b200_ksw_download.argtypes = [vp, vp, vp, i64, ctypes.POINTER(i64)]
     lib.ma_b200_ksw_batch.argtypes = [vp, i64, vp, vp, i64, vp, vp, i64, ctypes.POINTER(i64)]
+    lib.ma_b200_index_upload.argtypes = [vp, vp, i64, vp, i64, i64, vp, i64, ctypes.c_int32, vp, i64, i64, vp, vp,
+                                         ctypes.c_int32]
+    lib.ma_b200_index_build.argtypes = [vp, vp, i64, vp, vp, ctypes.c_int32]
+    lib.ma_b200_index_sizes.argtypes = [vp] + [ctypes.POINTER(i64)] * 4 + [vp]
+    lib.ma_b200_index_download.argtypes = [vp, vp, vp, vp]
+    lib.ma_b200_align_upload.argtypes = [vp, i64, vp, vp]
+    lib.ma_b200_align_run.argtypes = [vp, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(AlignStats)]
+    lib.ma_b200_align_download_info.argtypes = [vp, vp]
+    lib.ma_b200_align_download_segments.argtypes = [vp, vp, vp]
+    lib.ma_b200_align_download_seeds.argtypes = [vp, vp, i64]
+    lib.ma_b200_align_download_sets.argtypes = [vp, vp, i64, vp, i64]
+    lib.ma_b200_align_download.argtypes = [vp, vp, vp, i64, vp, i64]
+    lib.ma_b200_align_batch.argtypes = [vp, i64, vp, vp, vp, vp, i64, vp, i64, ctypes.POINTER(AlignStats)]
     _lib = lib
     return lib
 
@@ -128,6 +165,102 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.ma_b200_launch_count(self.h))
 
+    # ---- index ----------------------------------------------------------------------------------------------
+    def index_upload(self, ix):
+        """ix: ma_b200.index.Index (the reference's own arrays)."""
+        bwt = np.ascontiguousarray(ix.bwt, dtype=np.uint32)
+        sa = np.ascontiguousarray(ix.sa, dtype=np.int64)
+        pac = np.ascontiguousarray(ix.pac, dtype=np.uint8)
+        L2 = np.ascontiguousarray(ix.L2, dtype=np.int64)
+        cs = np.ascontiguousarray(ix.contig_start, dtype=np.int64)
+        cl = np.ascontiguousarray(ix.contig_len, dtype=np.int64)
+        self._check(self.lib.ma_b200_index_upload(self.h, _ptr(bwt), bwt.size, _ptr(L2), ix.primary, ix.ref_len,
+                                                  _ptr(sa), sa.size, ix.sa_intv, _ptr(pac), pac.size, ix.fwd_len,
+                                                  _ptr(cs), _ptr(cl), len(cs)))
+
+    def index_build(self, fwd_codes: np.ndarray, contig_start, contig_len):
+        """Builds the FM-index on the GPU from the forward strand; it stays resident in HBM."""
+        fwd = np.ascontiguousarray(fwd_codes, dtype=np.uint8)
+        cs = np.ascontiguousarray(contig_start, dtype=np.int64)
+        cl = np.ascontiguousarray(contig_len, dtype=np.int64)
+        self._check(self.lib.ma_b200_index_build(self.h, _ptr(fwd), fwd.size, _ptr(cs), _ptr(cl), len(cs)))
+
+    def index_download(self, names=None):
+        from .index import Index
+        nw, ns, npac, prim = (ctypes.c_int64(0) for _ in range(4))
+        L2 = np.zeros(5, dtype=np.int64)
+        self._check(self.lib.ma_b200_index_sizes(self.h, ctypes.byref(nw), ctypes.byref(ns), ctypes.byref(npac),
+                                                 ctypes.byref(prim), _ptr(L2)))
+        ix = Index()
+        ix.bwt = np.zeros(nw.value, dtype=np.uint32)
+        ix.sa = np.zeros(ns.value, dtype=np.int64)
+        ix.pac = np.zeros(npac.value, dtype=np.uint8)
+        self._check(self.lib.ma_b200_index_download(self.h, _ptr(ix.bwt), _ptr(ix.sa), _ptr(ix.pac)))
+        ix.L2, ix.primary, ix.ref_len, ix.fwd_len = L2, prim.value, int(L2[4]), int(L2[4]) // 2
+        ix.contig_names = names or []
+        return ix
+
+    # ---- alignment path -------------------------------------------------------------------------------------
+    def align_upload(self, reads: np.ndarray, offsets: np.ndarray):
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self._n_reads = len(offsets) - 1
+        self._check(self.lib.ma_b200_align_upload(self.h, self._n_reads, _ptr(reads), _ptr(offsets)))
+
+    def align_run(self, stage: int = STAGE_ALIGN, keep_segments: int = 0) -> dict:
+        st = AlignStats()
+        self._keep_segments = keep_segments
+        self._check(self.lib.ma_b200_align_run(self.h, stage, keep_segments, ctypes.byref(st)))
+        self._stats = st.as_dict()
+        return self._stats
+
+    def download_info(self):
+        info = np.zeros(self._n_reads, dtype=INFO_DTYPE)
+        self._check(self.lib.ma_b200_align_download_info(self.h, _ptr(info)))
+        return info
+
+    def download_segments(self):
+        segs = np.zeros((self._n_reads, self._keep_segments), dtype=SEGMENT_DTYPE)
+        n = np.zeros(self._n_reads, dtype=np.int32)
+        self._check(self.lib.ma_b200_align_download_segments(self.h, _ptr(segs), _ptr(n)))
+        return segs, n
+
+    def download_seeds(self):
+        seeds = np.zeros(max(1, self._stats["n_seeds"]), dtype=SEED_DTYPE)
+        self._check(self.lib.ma_b200_align_download_seeds(self.h, _ptr(seeds), seeds.size))
+        return seeds[:self._stats["n_seeds"]]
+
+    def download_sets(self):
+        sets = np.zeros(max(1, self._stats["n_sets"]), dtype=SET_DTYPE)
+        seeds = np.zeros(max(1, self._stats["n_set_seeds"]), dtype=SEED_DTYPE)
+        self._check(self.lib.ma_b200_align_download_sets(self.h, _ptr(sets), sets.size, _ptr(seeds), seeds.size))
+        return sets[:self._stats["n_sets"]], seeds
+
+    def download_alignments(self):
+        info = np.zeros(self._n_reads, dtype=INFO_DTYPE)
+        alns = np.zeros(max(1, self._stats["n_sets"]), dtype=ALN_DTYPE)
+        runs = np.zeros(max(1, self._stats["n_runs"]), dtype=np.uint32)
+        self._check(self.lib.ma_b200_align_download(self.h, _ptr(info), _ptr(alns), alns.size, _ptr(runs),
+                                                    runs.size))
+        return info, alns[:self._stats["n_sets"]], runs
+
+    def align_batch(self, reads: np.ndarray, offsets: np.ndarray, cap_alns: int | None = None,
+                    cap_runs: int | None = None):
+        """The drop-in call: host buffers in, alignment records out (ma_b200_align_batch)."""
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        cap_alns = cap_alns or 4 * n + 1024
+        cap_runs = cap_runs or 64 * n + 4096
+        info = np.zeros(n, dtype=INFO_DTYPE)
+        alns = np.zeros(cap_alns, dtype=ALN_DTYPE)
+        runs = np.zeros(cap_runs, dtype=np.uint32)
+        st = AlignStats()
+        self._check(self.lib.ma_b200_align_batch(self.h, n, _ptr(reads), _ptr(offsets), _ptr(info), _ptr(alns),
+                                                 cap_alns, _ptr(runs), cap_runs, ctypes.byref(st)))
+        self._stats = st.as_dict()
+        return info, alns[:st.n_sets], runs[:st.n_runs], self._stats
+
     # ---- banded DP ------------------------------------------------------------------------------------------
     def ksw_upload(self, tasks: np.ndarray, seq: np.ndarray):
         tasks = np.ascontiguousarray(tasks, dtype=KSW_TASK_DTYPE)
@@ -165,6 +298,17 @@ class Context:
         self._check(self.lib.ma_b200_ksw_batch(self.h, len(tasks), _ptr(tasks), _ptr(seq), seq.size, _ptr(res),
                                                _ptr(cig), cig.size, ctypes.byref(words)))
         return res, cig[:words.value]
+
+
+def pack_reads(reads):
+    """list of uint8 arrays (or a 2-D array) -> (concatenated bytes, int64 offsets[n+1])."""
+    if isinstance(reads, np.ndarray) and reads.ndim == 2:
+        n, L = reads.shape
+        return np.ascontiguousarray(reads, dtype=np.uint8).reshape(-1), np.arange(n + 1, dtype=np.int64) * L
+    lens = np.array([len(r) for r in reads], dtype=np.int64)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    data = np.concatenate([np.asarray(r, dtype=np.uint8) for r in reads]) if len(reads) else np.zeros(0, np.uint8)
+    return data, off
 
 
 def pack_ksw_tasks(pairs):

@@ -433,6 +433,7 @@ struct KswBatchArgs
     int cigscratch_stride; // words per warp
     int* next; // dynamic task queue
     int* error;
+    unsigned long long* cells_total; // optional: sum of band cells (GCUPS accounting)
     KswScore score;
 };
 
@@ -491,7 +492,11 @@ template <int W> __global__ void __launch_bounds__( 256 ) ksw_batch_kernel( KswB
             ez.cigar_off = (long long)o;
         }
         if( lane == 0 )
+        {
             A.out[ ti ] = ez;
+            if( A.cells_total )
+                atomicAdd( A.cells_total, (unsigned long long)ez.cells );
+        }
         __syncwarp( );
     }
 }

@@ -1,6 +1,8 @@
 // libma_b200.so — C ABI (include/ma_b200.h) over the sm_100a kernels. Host side of the drop-in boundary.
 #include "common.cuh"
 #include "ksw.cuh"
+#include "pipeline.cuh"
+#include "index_build.cuh"
 #include <algorithm>
 #include <numeric>
 #include <stdexcept>
@@ -38,6 +40,43 @@ struct ma_b200_ctx
     DevBuf<unsigned long long> ksw_ctrl; // [0] cigar cursor, [1] next (as int), [2] error (as int)
     std::vector<KswHostBin> ksw_bins;
     unsigned long long ksw_cigar_used = 0;
+
+    // ---- index (replicated per context / GPU)
+    bool have_index = false;
+    DevIndex index;
+    DevBuf<U4> ix_bwt;
+    DevBuf<long long> ix_sa;
+    DevBuf<unsigned char> ix_pac;
+    DevBuf<long long> ix_contigs; // starts then lengths
+    int64_t ix_words = 0, ix_nsa = 0, ix_npac = 0;
+
+    // ---- alignment batch state
+    int64_t n_reads = 0, reads_bytes = 0;
+    int max_read_len = 0;
+    int stage_done = 0;
+    DevBuf<unsigned char> reads;
+    DevBuf<long long> read_off;
+    DevBuf<ReadInfo> info;
+    DevBuf<DSeed> seeds;
+    DevBuf<SegRec> lists;
+    DevBuf<FSeg> fsegs;
+    DevBuf<SegRec> dbg_segs;
+    DevBuf<int> dbg_nsegs;
+    int dbg_cap = 0;
+    DevBuf<unsigned char> harm_scratch;
+    DevBuf<DSeed> set_seeds;
+    DevBuf<SetHeader> sets;
+    DevBuf<KswTask> tasks;
+    DevBuf<int> bin_order;
+    DevBuf<KswOut> task_out;
+    DevBuf<unsigned int> task_cigar;
+    DevBuf<DAln> alns;
+    DevBuf<unsigned int> runs;
+    DevBuf<unsigned int> run_scratch;
+    DevBuf<PipeCtrl> ctrl;
+    PipeCtrl hctrl;
+    int64_t n_seeds = 0, n_sets = 0, n_set_seeds = 0, n_tasks = 0, n_runs = 0, n_task_cigar = 0;
+    cudaEvent_t ev[ 8 ] = { nullptr };
 };
 
 static KswScore make_score( const ma_b200_params& p )
@@ -413,4 +452,598 @@ extern "C" int ma_b200_ksw_batch( ma_b200_ctx* ctx, int64_t n, const ma_b200_ksw
     if( rc )
         return rc;
     return ma_b200_ksw_download( ctx, results, cigar, cigar_cap_words, cigar_words );
+}
+
+// ------------------------------------------------------------------------------------------------ index
+extern "C" int ma_b200_index_upload( ma_b200_ctx* ctx, const uint32_t* bwt_words, int64_t n_words, const int64_t* L2,
+                                     int64_t primary, int64_t ref_len, const int64_t* sa, int64_t n_sa,
+                                     int32_t sa_intv, const uint8_t* pac, int64_t n_pac_bytes, int64_t fwd_len,
+                                     const int64_t* contig_start, const int64_t* contig_len, int32_t n_contigs )
+{
+    MA_API_BEGIN
+    if( !bwt_words || !L2 || !sa || !pac || !contig_start || !contig_len || n_contigs <= 0 || n_words <= 0 ||
+        sa_intv <= 0 || ( sa_intv & ( sa_intv - 1 ) ) || ref_len != 2 * fwd_len ||
+        n_pac_bytes < ( fwd_len + 3 ) / 4 || n_sa < ( ref_len + sa_intv ) / sa_intv )
+        throw std::runtime_error( "index_upload: inconsistent arguments" );
+    ctx->ix_bwt.reserve( (size_t)n_words / 4 + 8 );
+    ctx->ix_sa.reserve( (size_t)n_sa + 1 );
+    ctx->ix_pac.reserve( (size_t)n_pac_bytes + 16 );
+    ctx->ix_contigs.reserve( (size_t)2 * n_contigs );
+    MA_CUDA( cudaMemcpyAsync( ctx->ix_bwt.p, bwt_words, n_words * 4, cudaMemcpyHostToDevice, ctx->stream ) );
+    MA_CUDA( cudaMemcpyAsync( ctx->ix_sa.p, sa, n_sa * 8, cudaMemcpyHostToDevice, ctx->stream ) );
+    MA_CUDA( cudaMemcpyAsync( ctx->ix_pac.p, pac, n_pac_bytes, cudaMemcpyHostToDevice, ctx->stream ) );
+    MA_CUDA( cudaMemcpyAsync( ctx->ix_contigs.p, contig_start, n_contigs * 8, cudaMemcpyHostToDevice, ctx->stream ) );
+    MA_CUDA( cudaMemcpyAsync( ctx->ix_contigs.p + n_contigs, contig_len, n_contigs * 8, cudaMemcpyHostToDevice,
+                              ctx->stream ) );
+    MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    DevIndex& I = ctx->index;
+    I.bwt = ctx->ix_bwt.p, I.sa = ctx->ix_sa.p, I.pac = ctx->ix_pac.p;
+    I.contig_start = ctx->ix_contigs.p, I.contig_len = ctx->ix_contigs.p + n_contigs;
+    for( int i = 0; i < 5; i++ )
+        I.L2[ i ] = L2[ i ];
+    I.primary = primary, I.ref_len = ref_len, I.fwd_len = fwd_len, I.sa_intv = sa_intv, I.n_contigs = n_contigs;
+    ctx->ix_words = n_words, ctx->ix_nsa = n_sa, ctx->ix_npac = n_pac_bytes;
+    ctx->have_index = true;
+    MA_API_END
+}
+
+extern "C" int ma_b200_index_build( ma_b200_ctx* ctx, const uint8_t* fwd, int64_t fwd_len, const int64_t* contig_start,
+                                    const int64_t* contig_len, int32_t n_contigs )
+{
+    MA_API_BEGIN
+    if( !fwd || fwd_len <= 0 || !contig_start || !contig_len || n_contigs <= 0 )
+        throw std::runtime_error( "index_build: bad arguments" );
+    ctx->have_index = false;
+    IndexBuildResult R = build_index_gpu( ctx->stream, ctx->num_sms, fwd, fwd_len, ctx->ix_bwt, ctx->ix_sa,
+                                          ctx->ix_pac, ctx->launches );
+    ctx->ix_contigs.reserve( (size_t)2 * n_contigs );
+    MA_CUDA( cudaMemcpyAsync( ctx->ix_contigs.p, contig_start, n_contigs * 8, cudaMemcpyHostToDevice, ctx->stream ) );
+    MA_CUDA( cudaMemcpyAsync( ctx->ix_contigs.p + n_contigs, contig_len, n_contigs * 8, cudaMemcpyHostToDevice,
+                              ctx->stream ) );
+    MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    DevIndex& I = ctx->index;
+    I.bwt = ctx->ix_bwt.p, I.sa = ctx->ix_sa.p, I.pac = ctx->ix_pac.p;
+    I.contig_start = ctx->ix_contigs.p, I.contig_len = ctx->ix_contigs.p + n_contigs;
+    for( int i = 0; i < 5; i++ )
+        I.L2[ i ] = R.L2[ i ];
+    I.primary = R.primary, I.ref_len = 2 * fwd_len, I.fwd_len = fwd_len, I.sa_intv = 32, I.n_contigs = n_contigs;
+    ctx->ix_words = R.n_words, ctx->ix_nsa = R.n_sa, ctx->ix_npac = R.n_pac;
+    ctx->have_index = true;
+    MA_API_END
+}
+
+extern "C" int ma_b200_index_sizes( ma_b200_ctx* ctx, int64_t* n_words, int64_t* n_sa, int64_t* n_pac_bytes,
+                                    int64_t* primary, int64_t* L2 )
+{
+    if( !ctx || !ctx->have_index )
+        return MA_B200_ESTATE;
+    if( n_words )
+        *n_words = ctx->ix_words;
+    if( n_sa )
+        *n_sa = ctx->ix_nsa;
+    if( n_pac_bytes )
+        *n_pac_bytes = ctx->ix_npac;
+    if( primary )
+        *primary = ctx->index.primary;
+    if( L2 )
+        for( int i = 0; i < 5; i++ )
+            L2[ i ] = ctx->index.L2[ i ];
+    return MA_B200_OK;
+}
+
+extern "C" int ma_b200_index_download( ma_b200_ctx* ctx, uint32_t* bwt_words, int64_t* sa, uint8_t* pac )
+{
+    MA_API_BEGIN
+    if( !ctx->have_index )
+    {
+        ctx->err = "no index";
+        return MA_B200_ESTATE;
+    }
+    if( bwt_words )
+        MA_CUDA( cudaMemcpyAsync( bwt_words, ctx->ix_bwt.p, ctx->ix_words * 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    if( sa )
+        MA_CUDA( cudaMemcpyAsync( sa, ctx->ix_sa.p, ctx->ix_nsa * 8, cudaMemcpyDeviceToHost, ctx->stream ) );
+    if( pac )
+        MA_CUDA( cudaMemcpyAsync( pac, ctx->ix_pac.p, ctx->ix_npac, cudaMemcpyDeviceToHost, ctx->stream ) );
+    MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    MA_API_END
+}
+
+// ------------------------------------------------------------------------------------------------ alignment path
+static SeedParams make_seed_params( const ma_b200_params& p )
+{
+    return SeedParams{ p.seeding_technique, p.min_ambiguity, p.max_ambiguity, p.min_seed_length,
+                       p.seed_drop_min_size, p.seed_drop_factor, p.disable_heuristics, p.genome_size_disable };
+}
+static HarmParams make_harm_params( const ma_b200_params& p )
+{
+    return HarmParams{ p.match, p.gap, p.extend, p.sv_penalty, p.max_num_soc, p.min_num_soc, p.soc_width,
+                       p.rectangular_soc, p.soc_score_drop, p.harm_score_min, p.harm_score_min_rel,
+                       p.score_diff_tolerance, p.max_score_lookahead, p.switch_qlen, p.max_delta_dist,
+                       p.min_delta_dist, p.optimistic_gap_estimation, p.gap_cost_cutting, p.disable_heuristics,
+                       p.genome_size_disable };
+}
+static NwParams make_nw_params( const ma_b200_params& p )
+{
+    return NwParams{ p.match, p.mismatch, p.gap, p.extend, p.sv_penalty, p.max_gap_area, p.padding,
+                     p.bandwidth_ext, p.min_bandwidth_gap, p.zdrop };
+}
+
+extern "C" int ma_b200_align_upload( ma_b200_ctx* ctx, int64_t n_reads, const uint8_t* reads, const int64_t* offsets )
+{
+    MA_API_BEGIN
+    if( n_reads < 0 || n_reads > 0x7ffffff0 || ( n_reads > 0 && ( !reads || !offsets ) ) )
+        throw std::runtime_error( "align_upload: bad arguments" );
+    int maxL = 0;
+    for( int64_t i = 0; i < n_reads; i++ )
+    {
+        const int64_t L = offsets[ i + 1 ] - offsets[ i ];
+        if( L < 0 || L > 0x3fffffff || offsets[ i ] < 0 )
+            throw std::runtime_error( "align_upload: bad offsets" );
+        maxL = std::max<int>( maxL, (int)L );
+    }
+    ctx->n_reads = n_reads, ctx->max_read_len = maxL, ctx->stage_done = 0;
+    ctx->reads_bytes = n_reads ? offsets[ n_reads ] : 0;
+    ctx->reads.reserve( (size_t)ctx->reads_bytes + 16 );
+    ctx->read_off.reserve( (size_t)n_reads + 1 );
+    ctx->info.reserve( (size_t)n_reads + 1 );
+    ctx->ctrl.reserve( 1 );
+    if( n_reads )
+    {
+        MA_CUDA( cudaMemcpyAsync( ctx->reads.p, reads, ctx->reads_bytes, cudaMemcpyHostToDevice, ctx->stream ) );
+        MA_CUDA( cudaMemcpyAsync( ctx->read_off.p, offsets, ( n_reads + 1 ) * 8, cudaMemcpyHostToDevice,
+                                  ctx->stream ) );
+    }
+    MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    MA_API_END
+}
+
+static void read_ctrl( ma_b200_ctx* ctx )
+{
+    MA_CUDA( cudaMemcpyAsync( &ctx->hctrl, ctx->ctrl.p, sizeof( PipeCtrl ), cudaMemcpyDeviceToHost, ctx->stream ) );
+    MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
+}
+template <typename T> static void zero_field( ma_b200_ctx* ctx, T PipeCtrl::*f )
+{
+    MA_CUDA( cudaMemsetAsync( (char*)ctx->ctrl.p + ( (size_t) & ( ( (PipeCtrl*)0 )->*f ) ), 0, sizeof( T ),
+                              ctx->stream ) );
+}
+static float ev_ms( cudaEvent_t a, cudaEvent_t b )
+{
+    float ms = 0;
+    cudaEventElapsedTime( &ms, a, b );
+    return ms;
+}
+
+template <typename K> static int full_grid( ma_b200_ctx* ctx, K kernel, int threads, long long items, size_t smem = 0 )
+{
+    int perSm = 0;
+    MA_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, kernel, threads, smem ) );
+    if( perSm < 1 )
+        perSm = 1;
+    long long g = (long long)perSm * ctx->num_sms;
+    g = std::min<long long>( g, ( items + threads - 1 ) / threads );
+    return (int)std::max<long long>( g, 1 );
+}
+
+// DP over the planned tasks, bins decided on the device by nwplan_kernel
+static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
+{
+    static const int Ws[ 5 ] = { 128, 256, 512, 1024, 2048 };
+    const KswScore score = make_score( ctx->params );
+    if( ctx->hctrl.bin_count[ 5 ] > 0 )
+        throw std::runtime_error( "DP band wider than the largest supported window (2000 columns)" );
+    ctx->task_out.reserve( (size_t)ctx->n_tasks + 1 );
+    ctx->ksw_ctrl.reserve( 4 );
+    long long cigCap = std::max<long long>( ctx->task_cigar.cap, std::max<long long>( 12 * ctx->n_tasks, 1 << 16 ) );
+    for( int attempt = 0; attempt < 2; attempt++ )
+    {
+        ctx->task_cigar.reserve( (size_t)cigCap );
+        cigCap = (long long)ctx->task_cigar.cap;
+        MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p, 0, 4 * sizeof( unsigned long long ), ctx->stream ) );
+        const long long budget = 12ll << 30;
+        long long grids[ 5 ];
+        size_t tbNeed = 0, csNeed = 0;
+        for( int b = 0; b < 5; b++ )
+        {
+            grids[ b ] = 0;
+            if( ctx->hctrl.bin_count[ b ] == 0 )
+                continue;
+            KswHostBin bin;
+            bin.W = Ws[ b ];
+            bin.order.resize( ctx->hctrl.bin_count[ b ] ); // only its size is used
+            bin.tb_stride = (long long)ctx->hctrl.bin_tb[ b ], bin.cig_stride = ctx->hctrl.bin_cig[ b ];
+            switch( b )
+            {
+                case 0: grids[ b ] = ksw_bin_grid<128>( ctx, bin, budget ); break;
+                case 1: grids[ b ] = ksw_bin_grid<256>( ctx, bin, budget ); break;
+                case 2: grids[ b ] = ksw_bin_grid<512>( ctx, bin, budget ); break;
+                case 3: grids[ b ] = ksw_bin_grid<1024>( ctx, bin, budget ); break;
+                default: grids[ b ] = ksw_bin_grid<2048>( ctx, bin, budget ); break;
+            }
+            tbNeed = std::max<size_t>( tbNeed, (size_t)( grids[ b ] * 8 * bin.tb_stride ) );
+            csNeed = std::max<size_t>( csNeed, (size_t)( grids[ b ] * 8 * bin.cig_stride ) );
+        }
+        ctx->ksw_tb.reserve( tbNeed + 256 );
+        ctx->ksw_cigscratch.reserve( csNeed + 64 );
+        for( int b = 0; b < 5; b++ )
+        {
+            if( ctx->hctrl.bin_count[ b ] == 0 )
+                continue;
+            KswBatchArgs A;
+            A.tasks = ctx->tasks.p;
+            A.order = ctx->bin_order.p + (long long)b * task_cap;
+            A.n = ctx->hctrl.bin_count[ b ];
+            A.seq = ctx->reads.p;
+            A.pac = ctx->index.pac, A.fwd_len = ctx->index.fwd_len;
+            A.out = ctx->task_out.p;
+            A.cigar = ctx->task_cigar.p;
+            A.cigar_cap = cigCap;
+            A.cigar_cursor = ctx->ksw_ctrl.p;
+            A.tb = ctx->ksw_tb.p, A.tb_stride = (long long)ctx->hctrl.bin_tb[ b ];
+            A.cigscratch = ctx->ksw_cigscratch.p, A.cigscratch_stride = ctx->hctrl.bin_cig[ b ];
+            A.next = (int*)( ctx->ksw_ctrl.p + 1 );
+            A.error = (int*)( ctx->ksw_ctrl.p + 2 );
+            A.cells_total = ctx->ksw_ctrl.p + 3;
+            A.score = score;
+            MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p + 1, 0, sizeof( unsigned long long ), ctx->stream ) );
+            switch( b )
+            {
+                case 0: launch_ksw_bin<128>( ctx, A, grids[ b ] ); break;
+                case 1: launch_ksw_bin<256>( ctx, A, grids[ b ] ); break;
+                case 2: launch_ksw_bin<512>( ctx, A, grids[ b ] ); break;
+                case 3: launch_ksw_bin<1024>( ctx, A, grids[ b ] ); break;
+                default: launch_ksw_bin<2048>( ctx, A, grids[ b ] ); break;
+            }
+        }
+        unsigned long long c[ 4 ];
+        MA_CUDA( cudaMemcpyAsync( c, ctx->ksw_ctrl.p, sizeof( c ), cudaMemcpyDeviceToHost, ctx->stream ) );
+        MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
+        ctx->n_task_cigar = (int64_t)c[ 0 ];
+        ctx->ksw_cigar_used = c[ 3 ]; // reused as dp cell counter for the pipeline stats
+        if( !(int)c[ 2 ] )
+            return;
+        cigCap = (long long)c[ 0 ] + 1024; // the cursor kept counting: exact size
+    }
+    throw std::runtime_error( "pipeline DP: cigar slab overflow after growing (internal error)" );
+}
+
+extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t keep_segments,
+                                  ma_b200_align_stats* stats )
+{
+    MA_API_BEGIN
+    if( !ctx->have_index )
+    {
+        ctx->err = "align_run: no index uploaded";
+        return MA_B200_ESTATE;
+    }
+    if( upto_stage < 1 || upto_stage > 3 )
+        throw std::runtime_error( "align_run: bad stage" );
+    for( int i = 0; i < 8; i++ )
+        if( !ctx->ev[ i ] )
+            MA_CUDA( cudaEventCreate( &ctx->ev[ i ] ) );
+    ma_b200_align_stats st;
+    memset( &st, 0, sizeof( st ) );
+    const int64_t launches0 = ctx->launches;
+    const int n = (int)ctx->n_reads;
+    st.n_reads = n;
+    ctx->n_seeds = ctx->n_sets = ctx->n_set_seeds = ctx->n_tasks = ctx->n_runs = ctx->n_task_cigar = 0;
+    ctx->stage_done = 0;
+    cudaStream_t s = ctx->stream;
+    MA_CUDA( cudaEventRecord( ctx->ev[ 0 ], s ) );
+    if( n > 0 )
+    {
+        MA_CUDA( cudaMemsetAsync( ctx->ctrl.p, 0, sizeof( PipeCtrl ), s ) );
+        // ---------------- stage 1: seeding
+        const int maxL = ctx->max_read_len;
+        const int list_cap = std::min( maxL + 2, 1024 ), fseg_cap = std::min( 2 * maxL + 8, 1 << 16 );
+        int grid = full_grid( ctx, seed_kernel, 128, n );
+        const size_t perThread = (size_t)2 * list_cap * sizeof( SegRec ) + (size_t)fseg_cap * sizeof( FSeg );
+        grid = (int)std::max<size_t>( 1, std::min<size_t>( grid, ( (size_t)8 << 30 ) / ( perThread * 128 ) ) );
+        ctx->lists.reserve( (size_t)grid * 128 * 2 * list_cap );
+        ctx->fsegs.reserve( (size_t)grid * 128 * fseg_cap );
+        ctx->dbg_cap = keep_segments > 0 ? keep_segments : 0;
+        if( ctx->dbg_cap )
+        {
+            ctx->dbg_segs.reserve( (size_t)n * ctx->dbg_cap );
+            ctx->dbg_nsegs.reserve( (size_t)n );
+        }
+        long long seedCap = std::max<long long>( ctx->seeds.cap, (long long)n * std::max( 8, maxL / 16 ) + 1024 );
+        for( int attempt = 0;; attempt++ )
+        {
+            ctx->seeds.reserve( (size_t)seedCap );
+            seedCap = (long long)ctx->seeds.cap;
+            SeedKernelArgs A;
+            A.I = ctx->index, A.P = make_seed_params( ctx->params );
+            A.reads = ctx->reads.p, A.read_off = ctx->read_off.p, A.n_reads = n, A.info = ctx->info.p;
+            A.seeds = ctx->seeds.p, A.seed_cap = seedCap;
+            A.lists = ctx->lists.p, A.list_cap = list_cap, A.fsegs = ctx->fsegs.p, A.fseg_cap = fseg_cap;
+            A.dbg_segs = ctx->dbg_cap ? ctx->dbg_segs.p : nullptr;
+            A.dbg_nsegs = ctx->dbg_cap ? ctx->dbg_nsegs.p : nullptr, A.dbg_cap = ctx->dbg_cap;
+            A.ctrl = ctx->ctrl.p;
+            seed_kernel<<<grid, 128, 0, s>>>( A );
+            MA_CUDA( cudaGetLastError( ) );
+            ctx->launches++;
+            read_ctrl( ctx );
+            if( ctx->hctrl.overflow_lists || ctx->hctrl.overflow_fseg )
+                throw std::runtime_error( "seeding: per-read interval list capacity exceeded (read too repetitive)" );
+            if( (long long)ctx->hctrl.seed_cursor <= seedCap )
+                break;
+            if( attempt > 0 )
+                throw std::runtime_error( "seeding: seed slab overflow after growing (internal error)" );
+            seedCap = (long long)ctx->hctrl.seed_cursor + 1024;
+            MA_CUDA( cudaMemsetAsync( ctx->ctrl.p, 0, sizeof( PipeCtrl ), s ) );
+        }
+        ctx->n_seeds = (int64_t)ctx->hctrl.seed_cursor;
+        st.n_ext = (int64_t)ctx->hctrl.n_ext, st.n_dropped = (int64_t)ctx->hctrl.n_dropped;
+        MA_CUDA( cudaEventRecord( ctx->ev[ 1 ], s ) );
+        if( ctx->n_seeds > 0 )
+        {
+            LocateArgs A{ ctx->index, ctx->seeds.p, ctx->n_seeds, ctx->read_off.p, ctx->ctrl.p };
+            locate_kernel<<<full_grid( ctx, locate_kernel, 256, ctx->n_seeds ), 256, 0, s>>>( A );
+            MA_CUDA( cudaGetLastError( ) );
+            ctx->launches++;
+        }
+        MA_CUDA( cudaEventRecord( ctx->ev[ 2 ], s ) );
+        ctx->stage_done = 1;
+        // ---------------- stage 2: SoC + harmonization
+        if( upto_stage >= 2 )
+        {
+            const size_t scratchCap = ( ( (size_t)ctx->n_seeds * ( 340 + sizeof( DSeed ) ) + (size_t)n * 400 + 4096 ) + 255 ) & ~(size_t)255;
+            ctx->harm_scratch.reserve( scratchCap );
+            long long setSeedCap = std::max<long long>( ctx->set_seeds.cap, 2 * ctx->n_seeds + 1024 );
+            long long setCap = std::max<long long>( ctx->sets.cap, 2ll * n + 1024 );
+            for( int attempt = 0;; attempt++ )
+            {
+                ctx->set_seeds.reserve( (size_t)setSeedCap );
+                ctx->sets.reserve( (size_t)setCap );
+                setSeedCap = (long long)ctx->set_seeds.cap, setCap = (long long)ctx->sets.cap;
+                SocHarmArgs A;
+                A.I = ctx->index, A.P = make_harm_params( ctx->params ), A.read_off = ctx->read_off.p, A.n_reads = n;
+                A.info = ctx->info.p, A.seeds = ctx->seeds.p;
+                A.scratch = ctx->harm_scratch.p, A.scratch_cap = ctx->harm_scratch.cap;
+                A.set_seeds = ctx->set_seeds.p, A.set_seed_cap = setSeedCap, A.sets = ctx->sets.p, A.set_cap = setCap;
+                A.srand_base = ctx->params.srand_base, A.ctrl = ctx->ctrl.p;
+                socharm_kernel<<<full_grid( ctx, socharm_kernel, 128, n ), 128, 0, s>>>( A );
+                MA_CUDA( cudaGetLastError( ) );
+                ctx->launches++;
+                read_ctrl( ctx );
+                if( ctx->hctrl.overflow_fseg )
+                    throw std::runtime_error( "harmonization: more than 128 seed sets for one read" );
+                if( ctx->hctrl.scratch_cursor > ctx->harm_scratch.cap )
+                    throw std::runtime_error( "harmonization: scratch arena too small (internal error)" );
+                if( (long long)ctx->hctrl.set_seed_cursor <= setSeedCap && (long long)ctx->hctrl.set_cursor <= setCap )
+                    break;
+                if( attempt > 0 )
+                    throw std::runtime_error( "harmonization: slab overflow after growing (internal error)" );
+                setSeedCap = (long long)ctx->hctrl.set_seed_cursor + 1024;
+                setCap = (long long)ctx->hctrl.set_cursor + 1024;
+                zero_field( ctx, &PipeCtrl::set_seed_cursor );
+                zero_field( ctx, &PipeCtrl::set_cursor );
+                zero_field( ctx, &PipeCtrl::scratch_cursor );
+                zero_field( ctx, &PipeCtrl::next_read2 );
+            }
+            ctx->n_sets = (int64_t)ctx->hctrl.set_cursor, ctx->n_set_seeds = (int64_t)ctx->hctrl.set_seed_cursor;
+            ctx->stage_done = 2;
+        }
+        MA_CUDA( cudaEventRecord( ctx->ev[ 3 ], s ) );
+        // ---------------- stage 3: NW
+        if( upto_stage >= 3 )
+        {
+            const int nSets = (int)ctx->n_sets;
+            long long taskCap = std::max<long long>( ( ctx->bin_order.cap / 6 ), 3ll * nSets + 1024 );
+            if( nSets > 0 )
+                for( int attempt = 0;; attempt++ )
+                {
+                    ctx->tasks.reserve( (size_t)taskCap );
+                    ctx->bin_order.reserve( (size_t)taskCap * 6 );
+                    NwPlanArgs A;
+                    A.I = ctx->index, A.P = make_nw_params( ctx->params ), A.read_off = ctx->read_off.p;
+                    A.sets = ctx->sets.p, A.n_sets = nSets, A.set_seeds = ctx->set_seeds.p;
+                    A.tasks = ctx->tasks.p, A.task_cap = taskCap, A.bin_order = ctx->bin_order.p, A.ctrl = ctx->ctrl.p;
+                    nwplan_kernel<<<full_grid( ctx, nwplan_kernel, 128, nSets ), 128, 0, s>>>( A );
+                    MA_CUDA( cudaGetLastError( ) );
+                    ctx->launches++;
+                    read_ctrl( ctx );
+                    if( (long long)ctx->hctrl.task_cursor <= taskCap )
+                        break;
+                    if( attempt > 0 )
+                        throw std::runtime_error( "NW planning: task slab overflow after growing (internal error)" );
+                    taskCap = (long long)ctx->hctrl.task_cursor + 1024;
+                    zero_field( ctx, &PipeCtrl::task_cursor );
+                    MA_CUDA( cudaMemsetAsync( ctx->ctrl.p->bin_count, 0, sizeof( int ) * 8, s ) );
+                    MA_CUDA( cudaMemsetAsync( ctx->ctrl.p->bin_tb, 0, sizeof( unsigned long long ) * 8, s ) );
+                    MA_CUDA( cudaMemsetAsync( ctx->ctrl.p->bin_cig, 0, sizeof( int ) * 8, s ) );
+                }
+            ctx->n_tasks = nSets > 0 ? (int64_t)ctx->hctrl.task_cursor : 0;
+            MA_CUDA( cudaEventRecord( ctx->ev[ 4 ], s ) );
+            if( ctx->n_tasks > 0 )
+                run_pipeline_dp( ctx, taskCap );
+            st.dp_cells = ctx->n_tasks > 0 ? (int64_t)ctx->ksw_cigar_used : 0;
+            MA_CUDA( cudaEventRecord( ctx->ev[ 5 ], s ) );
+            ctx->alns.reserve( (size_t)nSets + 1 );
+            if( nSets > 0 )
+            {
+                const int runScratchCap = 2 * ctx->max_read_len + 4096;
+                int grid = full_grid( ctx, nwasm_kernel, 128, nSets );
+                ctx->run_scratch.reserve( (size_t)grid * 128 * runScratchCap );
+                long long runCap = std::max<long long>( ctx->runs.cap, 16ll * nSets + 4096 );
+                for( int attempt = 0;; attempt++ )
+                {
+                    ctx->runs.reserve( (size_t)runCap );
+                    runCap = (long long)ctx->runs.cap;
+                    NwAsmArgs A;
+                    A.I = ctx->index, A.P = make_nw_params( ctx->params ), A.reads = ctx->reads.p;
+                    A.read_off = ctx->read_off.p, A.sets = ctx->sets.p, A.n_sets = nSets;
+                    A.set_seeds = ctx->set_seeds.p, A.res = ctx->task_out.p, A.cigar = ctx->task_cigar.p;
+                    A.alns = ctx->alns.p, A.runs = ctx->runs.p, A.run_cap = runCap;
+                    A.run_scratch = ctx->run_scratch.p, A.run_scratch_cap = runScratchCap, A.ctrl = ctx->ctrl.p;
+                    nwasm_kernel<<<grid, 128, 0, s>>>( A );
+                    MA_CUDA( cudaGetLastError( ) );
+                    ctx->launches++;
+                    read_ctrl( ctx );
+                    if( ctx->hctrl.overflow_runs )
+                        throw std::runtime_error( "NW assembly: run list scratch too small (internal error)" );
+                    if( (long long)ctx->hctrl.run_cursor <= runCap )
+                        break;
+                    if( attempt > 0 )
+                        throw std::runtime_error( "NW assembly: run slab overflow after growing (internal error)" );
+                    runCap = (long long)ctx->hctrl.run_cursor + 1024;
+                    zero_field( ctx, &PipeCtrl::run_cursor );
+                    zero_field( ctx, &PipeCtrl::next_set );
+                }
+                ctx->n_runs = (int64_t)ctx->hctrl.run_cursor;
+                AlnSortArgs B{ ctx->info.p, n, ctx->alns.p, ctx->ctrl.p };
+                alnsort_kernel<<<full_grid( ctx, alnsort_kernel, 128, n ), 128, 0, s>>>( B );
+                MA_CUDA( cudaGetLastError( ) );
+                ctx->launches++;
+            }
+            ctx->stage_done = 3;
+        }
+        else
+        {
+            MA_CUDA( cudaEventRecord( ctx->ev[ 4 ], s ) );
+            MA_CUDA( cudaEventRecord( ctx->ev[ 5 ], s ) );
+        }
+        read_ctrl( ctx );
+        st.n_invpsi = (int64_t)ctx->hctrl.n_invpsi;
+    }
+    else
+        for( int i = 1; i < 6; i++ )
+            MA_CUDA( cudaEventRecord( ctx->ev[ i ], s ) );
+    MA_CUDA( cudaEventRecord( ctx->ev[ 6 ], s ) );
+    MA_CUDA( cudaEventSynchronize( ctx->ev[ 6 ] ) );
+    st.n_seeds = ctx->n_seeds, st.n_sets = ctx->n_sets, st.n_set_seeds = ctx->n_set_seeds, st.n_tasks = ctx->n_tasks;
+    st.n_runs = ctx->n_runs, st.n_cigar_words = ctx->n_task_cigar;
+    st.ms_seed = ev_ms( ctx->ev[ 0 ], ctx->ev[ 1 ] ), st.ms_locate = ev_ms( ctx->ev[ 1 ], ctx->ev[ 2 ] );
+    st.ms_socharm = ev_ms( ctx->ev[ 2 ], ctx->ev[ 3 ] ), st.ms_plan = ev_ms( ctx->ev[ 3 ], ctx->ev[ 4 ] );
+    st.ms_dp = ev_ms( ctx->ev[ 4 ], ctx->ev[ 5 ] ), st.ms_assemble = ev_ms( ctx->ev[ 5 ], ctx->ev[ 6 ] );
+    st.ms_total = ev_ms( ctx->ev[ 0 ], ctx->ev[ 6 ] );
+    st.launches = (int)( ctx->launches - launches0 );
+    if( stats )
+        *stats = st;
+    MA_API_END
+}
+
+extern "C" int ma_b200_align_download_info( ma_b200_ctx* ctx, ma_b200_read_info* info )
+{
+    MA_API_BEGIN
+    static_assert( sizeof( ma_b200_read_info ) == sizeof( ReadInfo ), "read info layout" );
+    if( ctx->stage_done < 1 )
+    {
+        ctx->err = "nothing to download";
+        return MA_B200_ESTATE;
+    }
+    if( ctx->n_reads )
+        MA_CUDA( cudaMemcpyAsync( info, ctx->info.p, ctx->n_reads * sizeof( ReadInfo ), cudaMemcpyDeviceToHost,
+                                  ctx->stream ) );
+    MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    MA_API_END
+}
+
+extern "C" int ma_b200_align_download_segments( ma_b200_ctx* ctx, ma_b200_segment* segs, int32_t* n_segs )
+{
+    MA_API_BEGIN
+    static_assert( sizeof( ma_b200_segment ) == sizeof( SegRec ), "segment layout" );
+    if( ctx->stage_done < 1 || ctx->dbg_cap == 0 )
+    {
+        ctx->err = "segments were not kept (keep_segments == 0)";
+        return MA_B200_ESTATE;
+    }
+    if( ctx->n_reads )
+    {
+        MA_CUDA( cudaMemcpyAsync( segs, ctx->dbg_segs.p, ctx->n_reads * ctx->dbg_cap * sizeof( SegRec ),
+                                  cudaMemcpyDeviceToHost, ctx->stream ) );
+        MA_CUDA( cudaMemcpyAsync( n_segs, ctx->dbg_nsegs.p, ctx->n_reads * sizeof( int ), cudaMemcpyDeviceToHost,
+                                  ctx->stream ) );
+    }
+    MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    MA_API_END
+}
+
+extern "C" int ma_b200_align_download_seeds( ma_b200_ctx* ctx, ma_b200_seed* seeds, int64_t cap )
+{
+    MA_API_BEGIN
+    static_assert( sizeof( ma_b200_seed ) == sizeof( DSeed ), "seed layout" );
+    if( ctx->stage_done != 1 )
+    {
+        ctx->err = "seeds are only available right after a run with upto_stage == MA_B200_STAGE_SEEDS";
+        return MA_B200_ESTATE;
+    }
+    if( cap < ctx->n_seeds )
+    {
+        ctx->err = "seed buffer too small";
+        return MA_B200_ENOMEM;
+    }
+    if( ctx->n_seeds )
+        MA_CUDA( cudaMemcpyAsync( seeds, ctx->seeds.p, ctx->n_seeds * sizeof( DSeed ), cudaMemcpyDeviceToHost,
+                                  ctx->stream ) );
+    MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    MA_API_END
+}
+
+extern "C" int ma_b200_align_download_sets( ma_b200_ctx* ctx, ma_b200_seed_set* sets, int64_t cap_sets,
+                                            ma_b200_seed* seeds, int64_t cap_seeds )
+{
+    MA_API_BEGIN
+    static_assert( sizeof( ma_b200_seed_set ) == sizeof( SetHeader ), "set layout" );
+    if( ctx->stage_done < 2 )
+    {
+        ctx->err = "no seed sets computed";
+        return MA_B200_ESTATE;
+    }
+    if( cap_sets < ctx->n_sets || cap_seeds < ctx->n_set_seeds )
+    {
+        ctx->err = "set buffers too small";
+        return MA_B200_ENOMEM;
+    }
+    if( ctx->n_sets )
+        MA_CUDA( cudaMemcpyAsync( sets, ctx->sets.p, ctx->n_sets * sizeof( SetHeader ), cudaMemcpyDeviceToHost,
+                                  ctx->stream ) );
+    if( ctx->n_set_seeds )
+        MA_CUDA( cudaMemcpyAsync( seeds, ctx->set_seeds.p, ctx->n_set_seeds * sizeof( DSeed ), cudaMemcpyDeviceToHost,
+                                  ctx->stream ) );
+    MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    MA_API_END
+}
+
+extern "C" int ma_b200_align_download( ma_b200_ctx* ctx, ma_b200_read_info* info, ma_b200_alignment* alns,
+                                       int64_t cap_alns, uint32_t* runs, int64_t cap_runs )
+{
+    MA_API_BEGIN
+    static_assert( sizeof( ma_b200_alignment ) == sizeof( DAln ), "alignment layout" );
+    if( ctx->stage_done < 3 )
+    {
+        ctx->err = "no alignments computed";
+        return MA_B200_ESTATE;
+    }
+    if( cap_alns < ctx->n_sets || cap_runs < ctx->n_runs )
+    {
+        ctx->err = "alignment buffers too small";
+        return MA_B200_ENOMEM;
+    }
+    if( ctx->n_reads && info )
+        MA_CUDA( cudaMemcpyAsync( info, ctx->info.p, ctx->n_reads * sizeof( ReadInfo ), cudaMemcpyDeviceToHost,
+                                  ctx->stream ) );
+    if( ctx->n_sets )
+        MA_CUDA( cudaMemcpyAsync( alns, ctx->alns.p, ctx->n_sets * sizeof( DAln ), cudaMemcpyDeviceToHost,
+                                  ctx->stream ) );
+    if( ctx->n_runs )
+        MA_CUDA( cudaMemcpyAsync( runs, ctx->runs.p, ctx->n_runs * sizeof( unsigned int ), cudaMemcpyDeviceToHost,
+                                  ctx->stream ) );
+    MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    MA_API_END
+}
+
+extern "C" int ma_b200_align_batch( ma_b200_ctx* ctx, int64_t n_reads, const uint8_t* reads, const int64_t* offsets,
+                                    ma_b200_read_info* info, ma_b200_alignment* alns, int64_t cap_alns,
+                                    uint32_t* runs, int64_t cap_runs, ma_b200_align_stats* stats )
+{
+    int rc = ma_b200_align_upload( ctx, n_reads, reads, offsets );
+    if( rc )
+        return rc;
+    rc = ma_b200_align_run( ctx, MA_B200_STAGE_ALIGN, 0, stats );
+    if( rc )
+        return rc;
+    return ma_b200_align_download( ctx, info, alns, cap_alns, runs, cap_runs );
 }

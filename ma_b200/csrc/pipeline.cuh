@@ -1,0 +1,471 @@
+// CUDA kernels of the read-alignment pipeline (sm_100a). Each kernel is a thin, persistent-grid wrapper around the
+// host+device routines in fmindex.cuh / sochar.cuh / nwglue.cuh; ksw.cuh supplies the banded-DP kernel.
+//
+//   seed_kernel     one thread per read   BinarySeeding (+ drop-off) and seed enumeration        HBM random 64 B reads
+//   locate_kernel   one thread per seed   FMIndex::bwt_sa, strand folding, SoC delta             HBM random 64 B reads
+//   socharm_kernel  one thread per read   StripOfConsiderationSeeds + Harmonization              latency / FP64
+//   nwplan_kernel   one thread per set    reference window + DP problem enumeration
+//   ksw_batch_kernel (ksw.cuh)            one warp per DP problem
+//   nwasm_kernel    one thread per set    stitching, scoring, dangling-indel removal
+//   alnsort_kernel  one thread per read   final std::sort of the read's alignments
+//
+// Variable-size outputs are bump-allocated from slabs with one atomicAdd per producer; every kernel keeps counting
+// after a slab is full, so the host can grow the slab to the exact size and re-run the stage.
+#pragma once
+#include "ksw.cuh"
+#include "nwglue.cuh"
+
+namespace ma
+{
+
+// control block in device memory (one cache line per hot counter would be nicer; contention is one atomic per read)
+struct PipeCtrl
+{
+    unsigned long long seed_cursor; // seeds allocated
+    unsigned long long set_seed_cursor; // harmonized seeds allocated
+    unsigned long long set_cursor; // set headers allocated
+    unsigned long long task_cursor; // DP tasks allocated
+    unsigned long long run_cursor; // alignment run words allocated
+    unsigned long long n_ext; // FMIndex::extend_backward calls (roofline unit)
+    unsigned long long n_invpsi; // bwt_invPsi steps
+    unsigned long long n_dropped; // reads cleared by the seeding drop-off heuristic
+    unsigned long long scratch_cursor; // soc/harm scratch bytes
+    int next_read, next_read2, next_set, next_set2, next_read3;
+    int overflow_lists, overflow_fseg, overflow_runs;
+    int bin_count[ 8 ];
+    unsigned long long bin_tb[ 8 ];
+    int bin_cig[ 8 ];
+};
+
+struct ReadInfo // per read
+{
+    long long seed_off; // first seed of the read in the seed slab
+    int n_seeds;
+    int set_off; // first set header
+    int n_sets;
+    int pad;
+};
+
+struct SetHeader
+{
+    int read, ordinal;
+    unsigned int soc_index;
+    int n;
+    long long seed_off;
+    int task_off, n_tasks;
+    unsigned long long win_begin, win_end;
+    int valid, pad;
+};
+
+struct FSeg // segment that passed the ExtractSeeds filter
+{
+    int start, size;
+    long long sa_start;
+    int sa_size, pad;
+};
+
+struct SeedKernelArgs
+{
+    DevIndex I;
+    SeedParams P;
+    const unsigned char* reads;
+    const long long* read_off;
+    int n_reads;
+    ReadInfo* info;
+    DSeed* seeds;
+    long long seed_cap;
+    SegRec* lists; // per thread: 2 * list_cap
+    int list_cap;
+    FSeg* fsegs; // per thread: fseg_cap
+    int fseg_cap;
+    // debug: all segments of every read (tests only)
+    SegRec* dbg_segs;
+    int* dbg_nsegs;
+    int dbg_cap;
+    PipeCtrl* ctrl;
+};
+
+struct SeedSink
+{
+    const SeedParams& P;
+    FSeg* fsegs;
+    int cap, n = 0;
+    long long nSeeds = 0;
+    unsigned long long dropSum = 0;
+    bool overflow = false;
+    SegRec* dbg;
+    int dbgCap, nAll = 0;
+    __device__ SeedSink( const SeedParams& P, FSeg* f, int cap, SegRec* dbg, int dbgCap )
+        : P( P ), fsegs( f ), cap( cap ), dbg( dbg ), dbgCap( dbgCap )
+    {}
+    __device__ void seg( const SegRec& r )
+    {
+        if( dbg && nAll < dbgCap )
+            dbg[ nAll ] = r;
+        nAll++;
+        if( P.drop_min_size != 0 )
+            dropSum += (unsigned long long)r.size / (unsigned long long)P.drop_min_size; // segment.h:278-289
+        // SegmentVector::forEachSeed filter (segment.h:321-336); bSkip is hard-wired to true (:365)
+        if( (unsigned long long)r.size < (unsigned long long)P.min_seed_len )
+            return;
+        if( r.sa.size > (long long)P.max_amb && P.max_amb != 0 )
+            return;
+        if( n < cap )
+            fsegs[ n ] = FSeg{ r.start, r.size, r.sa.start, (int)r.sa.size, 0 };
+        else
+            overflow = true;
+        n++;
+        nSeeds += r.sa.size;
+    }
+};
+
+__global__ void __launch_bounds__( 128 ) seed_kernel( SeedKernelArgs A )
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    SegRec* la = A.lists + (size_t)tid * 2 * A.list_cap;
+    FSeg* fs = A.fsegs + (size_t)tid * A.fseg_cap;
+    unsigned long long nExtLocal = 0, nDropped = 0;
+    while( true )
+    {
+        const int read = atomicAdd( &A.ctrl->next_read, 1 );
+        if( read >= A.n_reads )
+            break;
+        const long long off = A.read_off[ read ];
+        const int L = (int)( A.read_off[ read + 1 ] - off );
+        SegRec* dbg = A.dbg_segs ? A.dbg_segs + (size_t)read * A.dbg_cap : nullptr;
+        SeedSink sink( A.P, fs, A.fseg_cap, dbg, A.dbg_cap );
+        Seeder<SeedSink> S( A.I, A.P, A.reads + off, L, SeedScratch{ la, la + A.list_cap, A.list_cap }, sink );
+        S.run( );
+        nExtLocal += (unsigned long long)S.nExt;
+        if( S.overflow )
+            atomicExch( &A.ctrl->overflow_lists, 1 );
+        if( sink.overflow )
+            atomicExch( &A.ctrl->overflow_fseg, 1 );
+        // drop-off heuristic (binarySeeding.cpp:172-175)
+        bool bClear = !A.P.disable_heuristics && A.P.drop_min_size != 0 &&
+                      (double)sink.dropSum < A.P.drop_factor * (double)L &&
+                      (unsigned long long)A.P.genome_size_disable < (unsigned long long)A.I.ref_len;
+        if( bClear )
+            nDropped++;
+        if( A.dbg_nsegs )
+            A.dbg_nsegs[ read ] = bClear ? 0 : sink.nAll;
+        const long long nSeeds = bClear ? 0 : sink.nSeeds;
+        long long so = 0;
+        if( nSeeds > 0 )
+            so = (long long)atomicAdd( &A.ctrl->seed_cursor, (unsigned long long)nSeeds );
+        ReadInfo ri;
+        ri.seed_off = so, ri.n_seeds = (int)nSeeds, ri.set_off = 0, ri.n_sets = 0, ri.pad = 0;
+        A.info[ read ] = ri;
+        if( nSeeds > 0 && so + nSeeds <= A.seed_cap && !sink.overflow )
+        {
+            long long k = so;
+            const int nf = sink.n;
+            for( int i = 0; i < nf; i++ )
+            {
+                const FSeg f = fs[ i ];
+                for( int j = 0; j < f.sa_size; j++ )
+                {
+                    DSeed d;
+                    d.q = f.start, d.len = f.size + 1;
+                    d.r = f.sa_start + j; // SA row, resolved by locate_kernel
+                    d.amb = (unsigned int)f.sa_size, d.fw = 1, d.delta = read; // delta carries the read id for now
+                    A.seeds[ k++ ] = d;
+                }
+            }
+        }
+    }
+    if( nExtLocal )
+        atomicAdd( &A.ctrl->n_ext, nExtLocal );
+    if( nDropped )
+        atomicAdd( &A.ctrl->n_dropped, nDropped );
+}
+
+struct LocateArgs
+{
+    DevIndex I;
+    DSeed* seeds;
+    long long n_seeds;
+    const long long* read_off;
+    PipeCtrl* ctrl;
+};
+
+// Segment::forEachSeed (segment.h:89-113) + ExtractSeeds::setDeltaOfSeed (stripOfConsideration.h:42-54, 97-112)
+__global__ void __launch_bounds__( 256 ) locate_kernel( LocateArgs A )
+{
+    unsigned long long steps = 0;
+    for( long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < A.n_seeds;
+         i += (long long)gridDim.x * blockDim.x )
+    {
+        DSeed d = A.seeds[ i ];
+        const int read = (int)d.delta;
+        const long long qlen = A.read_off[ read + 1 ] - A.read_off[ read ];
+        int st = 0;
+        long long r = bwt_sa( A.I, d.r, &st );
+        steps += (unsigned long long)st;
+        const bool fw = r < A.I.ref_len / 2;
+        if( !fw )
+            r = A.I.ref_len - r - 1;
+        d.r = r, d.fw = fw ? 1 : 0;
+        d.delta = r + ( qlen - d.q ) + ( qlen + 1 ) * seq_id_for_position( A.I, r );
+        A.seeds[ i ] = d;
+    }
+    // warp-aggregate the accounting counter
+    for( int o = 16; o > 0; o >>= 1 )
+        steps += __shfl_xor_sync( 0xffffffffu, steps, o );
+    if( ( threadIdx.x & 31 ) == 0 && steps )
+        atomicAdd( &A.ctrl->n_invpsi, steps );
+}
+
+struct SocHarmArgs
+{
+    DevIndex I;
+    HarmParams P;
+    const long long* read_off;
+    int n_reads;
+    ReadInfo* info;
+    DSeed* seeds;
+    unsigned char* scratch; // arena, bump allocated per read
+    unsigned long long scratch_cap;
+    DSeed* set_seeds;
+    long long set_seed_cap;
+    SetHeader* sets;
+    long long set_cap;
+    unsigned int srand_base;
+    PipeCtrl* ctrl;
+};
+
+#define MA_MAX_SETS_PER_READ 128
+
+struct DevSetSink
+{
+    DSeed* slab;
+    long long cap;
+    PipeCtrl* ctrl;
+    int read;
+    // per-thread headers of the read under construction
+    long long off[ MA_MAX_SETS_PER_READ ];
+    int n[ MA_MAX_SETS_PER_READ ];
+    unsigned int soc[ MA_MAX_SETS_PER_READ ];
+    int count = 0;
+    bool overflow = false;
+    __device__ void set( const DSeed* p, int m, unsigned int socIndex )
+    {
+        const long long o = (long long)atomicAdd( &ctrl->set_seed_cursor, (unsigned long long)m );
+        if( o + m <= cap )
+            for( int i = 0; i < m; i++ )
+                slab[ o + i ] = p[ i ];
+        if( count < MA_MAX_SETS_PER_READ )
+            off[ count ] = o, n[ count ] = m, soc[ count ] = socIndex;
+        else
+            overflow = true;
+        count++;
+    }
+    __device__ void pop_back( unsigned int counter, unsigned int minTries )
+    {
+        for( unsigned int ui = 0; ui < counter && (unsigned int)count > minTries; ui++ )
+            count--;
+    }
+};
+
+__global__ void __launch_bounds__( 128 ) socharm_kernel( SocHarmArgs A )
+{
+    while( true )
+    {
+        const int read = atomicAdd( &A.ctrl->next_read2, 1 );
+        if( read >= A.n_reads )
+            break;
+        ReadInfo ri = A.info[ read ];
+        ri.n_sets = 0, ri.set_off = 0;
+        if( ri.n_seeds > 0 )
+        {
+            const int n = ri.n_seeds;
+            // the SoC sorts its seeds in place: work on a copy so that the stage can be re-run after a slab grew
+            const size_t copyBytes = ( (size_t)n * sizeof( DSeed ) + 15 ) & ~(size_t)15;
+            const size_t need = harm_scratch_need( (size_t)n ) + copyBytes + 64;
+            const unsigned long long so = atomicAdd( &A.ctrl->scratch_cursor, (unsigned long long)need );
+            if( so + need <= A.scratch_cap )
+            {
+                DSeed* S = (DSeed*)( A.scratch + so );
+                for( int i = 0; i < n; i++ )
+                    S[ i ] = A.seeds[ ri.seed_off + i ];
+                HarmScratch W = harm_scratch_carve( A.scratch + so + copyBytes, (size_t)n );
+                DevSetSink sink;
+                sink.slab = A.set_seeds, sink.cap = A.set_seed_cap, sink.ctrl = A.ctrl, sink.read = read;
+                const int qlen = (int)( A.read_off[ read + 1 ] - A.read_off[ read ] );
+                soc_harm_read( A.I, A.P, S, n, qlen, A.srand_base + (unsigned int)read, W, sink, 0 );
+                if( sink.overflow )
+                    atomicExch( &A.ctrl->overflow_fseg, 1 );
+                const int ns = sink.count < MA_MAX_SETS_PER_READ ? sink.count : MA_MAX_SETS_PER_READ;
+                if( ns > 0 )
+                {
+                    const long long ho = (long long)atomicAdd( &A.ctrl->set_cursor, (unsigned long long)ns );
+                    ri.set_off = (int)ho, ri.n_sets = ns;
+                    if( ho + ns <= A.set_cap )
+                        for( int i = 0; i < ns; i++ )
+                        {
+                            SetHeader h;
+                            h.read = read, h.ordinal = i, h.soc_index = sink.soc[ i ], h.n = sink.n[ i ];
+                            h.seed_off = sink.off[ i ], h.task_off = 0, h.n_tasks = 0;
+                            h.win_begin = h.win_end = 0, h.valid = 0, h.pad = 0;
+                            A.sets[ ho + i ] = h;
+                        }
+                }
+            }
+        }
+        A.info[ read ] = ri;
+    }
+}
+
+struct NwPlanArgs
+{
+    DevIndex I;
+    NwParams P;
+    const long long* read_off;
+    SetHeader* sets;
+    int n_sets;
+    const DSeed* set_seeds;
+    KswTask* tasks;
+    long long task_cap;
+    int* bin_order; // [n_bins][task_cap] task ids per window bin
+    PipeCtrl* ctrl;
+};
+
+__device__ __forceinline__ int ksw_bin_of( int ncol16 )
+{
+    const int need = ncol16 + 48;
+    return need <= 128 ? 0 : need <= 256 ? 1 : need <= 512 ? 2 : need <= 1024 ? 3 : need <= 2048 ? 4 : 5;
+}
+
+__global__ void __launch_bounds__( 128 ) nwplan_kernel( NwPlanArgs A )
+{
+    for( int si = blockIdx.x * blockDim.x + threadIdx.x; si < A.n_sets; si += gridDim.x * blockDim.x )
+    {
+        SetHeader h = A.sets[ si ];
+        const DSeed* S = A.set_seeds + h.seed_off;
+        const long long qbase = A.read_off[ h.read ];
+        const int qlen = (int)( A.read_off[ h.read + 1 ] - qbase );
+        const NwWindow w = nw_window( A.I, A.P, S, h.n );
+        h.valid = w.valid ? 1 : 0, h.win_begin = w.beginRef, h.win_end = w.endRef, h.n_tasks = 0, h.task_off = 0;
+        if( w.valid )
+        {
+            NwPlanner cnt( A.P, nullptr, qbase, (long long)w.beginRef );
+            nw_walk( S, h.n, qlen, w, cnt );
+            h.n_tasks = cnt.n;
+            if( cnt.n > 0 )
+            {
+                const long long to = (long long)atomicAdd( &A.ctrl->task_cursor, (unsigned long long)cnt.n );
+                h.task_off = (int)to;
+                if( to + cnt.n <= A.task_cap )
+                {
+                    NwPlanner pl( A.P, A.tasks + to, qbase, (long long)w.beginRef );
+                    nw_walk( S, h.n, qlen, w, pl );
+                    for( int t = 0; t < cnt.n; t++ )
+                    {
+                        const KswTask& T = A.tasks[ to + t ];
+                        const int nc = ksw_ncol16( T.qlen, T.tlen, T.w );
+                        const int b = ksw_bin_of( nc );
+                        const int slot = atomicAdd( &A.ctrl->bin_count[ b ], 1 );
+                        A.bin_order[ (long long)b * A.task_cap + slot ] = (int)( to + t );
+                        const unsigned long long tb = ( ( (unsigned long long)T.qlen + T.tlen ) * nc + 255 ) & ~255ull;
+                        atomicMax( &A.ctrl->bin_tb[ b ], tb );
+                        atomicMax( &A.ctrl->bin_cig[ b ], ( T.qlen + T.tlen + 2 + 63 ) & ~63 );
+                    }
+                }
+            }
+        }
+        A.sets[ si ] = h;
+    }
+}
+
+struct NwAsmArgs
+{
+    DevIndex I;
+    NwParams P;
+    const unsigned char* reads;
+    const long long* read_off;
+    const SetHeader* sets;
+    int n_sets;
+    const DSeed* set_seeds;
+    const KswOut* res;
+    const unsigned int* cigar;
+    DAln* alns; // one per set, same index
+    unsigned int* runs;
+    long long run_cap;
+    unsigned int* run_scratch; // per thread
+    int run_scratch_cap;
+    PipeCtrl* ctrl;
+};
+
+__global__ void __launch_bounds__( 128 ) nwasm_kernel( NwAsmArgs A )
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int* scratch = A.run_scratch + (size_t)tid * A.run_scratch_cap;
+    while( true )
+    {
+        const int si = atomicAdd( &A.ctrl->next_set, 1 );
+        if( si >= A.n_sets )
+            break;
+        const SetHeader h = A.sets[ si ];
+        DAln a;
+        a.begin_ref = a.end_ref = a.score = 0, a.begin_q = a.end_q = a.length = a.n_runs = 0;
+        a.soc_index = h.soc_index, a.read = h.read, a.run_off = 0, a.rank = h.ordinal, a.pad = 0;
+        if( h.valid )
+        {
+            const long long qbase = A.read_off[ h.read ];
+            const int qlen = (int)( A.read_off[ h.read + 1 ] - qbase );
+            const DSeed* S = A.set_seeds + h.seed_off;
+            NwWindow w{ h.win_begin, h.win_end, true };
+            NwAssembler as( A.I, A.P, A.reads + qbase, h.win_begin, A.res + h.task_off, A.cigar, scratch,
+                            A.run_scratch_cap );
+            nw_walk( S, h.n, qlen, w, as );
+            as.removeDangeling( );
+            if( as.overflow )
+                atomicExch( &A.ctrl->overflow_runs, 1 );
+            a.begin_ref = (long long)as.beginR, a.end_ref = (long long)as.endR, a.score = as.score;
+            a.begin_q = (int)as.beginQ, a.end_q = (int)as.endQ, a.length = (int)as.length;
+            a.n_runs = as.nRuns - as.front;
+            if( a.n_runs > 0 )
+            {
+                const long long ro = (long long)atomicAdd( &A.ctrl->run_cursor, (unsigned long long)a.n_runs );
+                a.run_off = ro;
+                if( ro + a.n_runs <= A.run_cap )
+                    for( int i = 0; i < a.n_runs; i++ )
+                        A.runs[ ro + i ] = scratch[ as.front + i ];
+            }
+        }
+        A.alns[ si ] = a;
+    }
+}
+
+struct AlnSortArgs
+{
+    const ReadInfo* info;
+    int n_reads;
+    DAln* alns;
+    PipeCtrl* ctrl;
+};
+
+// the final std::sort of NeedlemanWunsch::execute with Alignment::larger (needlemanWunsch.h:131-132)
+__global__ void __launch_bounds__( 128 ) alnsort_kernel( AlnSortArgs A )
+{
+    for( int read = blockIdx.x * blockDim.x + threadIdx.x; read < A.n_reads; read += gridDim.x * blockDim.x )
+    {
+        const ReadInfo ri = A.info[ read ];
+        if( ri.n_sets <= 0 )
+            continue;
+        int ord[ MA_MAX_SETS_PER_READ ];
+        const int n = ri.n_sets;
+        DAln* al = A.alns + ri.set_off;
+        for( int i = 0; i < n; i++ )
+            ord[ i ] = i;
+        stl::sort( ord, ord + n, [ & ]( int a, int b ) {
+            if( al[ a ].score == al[ b ].score )
+                return al[ a ].soc_index < al[ b ].soc_index;
+            return al[ a ].score > al[ b ].score;
+        } );
+        for( int i = 0; i < n; i++ )
+            al[ ord[ i ] ].rank = i;
+    }
+}
+
+} // namespace ma

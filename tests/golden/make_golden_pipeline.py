@@ -1,0 +1,61 @@
+"""Generates the pipeline golden fixtures by running the compiled, UNMODIFIED reference (oracle/_ref/ref_dump):
+
+  tests/golden/gold.{bwt,sa,pac,ann,amb}   index of a 3-contig 60 kbp synthetic genome (reference's own builder)
+  tests/golden/gold_reads_short.txt / gold_reads_long.txt
+  tests/golden/gold_<preset>.npz            per-stage dumps (segments, seeds, SoC pops, harmonized sets, DP calls,
+                                            alignments) with srand(1000 + read index) before Harmonization::execute
+
+Run in the build container (needs /root/reference -> `make -C oracle ref`).
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+import helpers as H  # noqa: E402
+from ma_b200 import synth  # noqa: E402
+
+SRAND = 1000
+
+
+def main():
+    g = synth.random_genome([30_000, 20_000, 10_000], 42)
+    # a repeat: copy 400 bp of contig 1 into contig 2 (ambiguous seeds, multiple SoCs)
+    g[1][5000:5400] = g[0][1000:1400]
+    gt = os.path.join(H.GOLDEN, "gold_genome.txt")
+    synth.write_genome_txt(gt, g)
+    H.run_ref("index", gt, os.path.join(H.GOLDEN, "gold"))
+    os.remove(gt)
+    short, _, _, _ = synth.simulate_reads(g, 400, 150, 7, sub_rate=0.02, ins_rate=0.004, del_rate=0.004)
+    short[3, 60] = 4          # an N inside a read
+    short[4, :] = 4           # all-N read
+    short[5, 0] = 4
+    short[6, 149] = 4
+    short[7] = np.random.Generator(np.random.PCG64(5)).integers(0, 4, 150)  # unalignable random read
+    short[8, :75] = g[0][2000:2075]
+    short[8, 75:] = g[2][3000:3075]  # chimeric read
+    synth.write_reads_txt(os.path.join(H.GOLDEN, "gold_reads_short.txt"), short)
+    long_, _, _, _ = synth.simulate_long_reads(g, 12, 2500, 8)
+    synth.write_reads_txt(os.path.join(H.GOLDEN, "gold_reads_long.txt"), long_)
+    for preset, rf in [("illumina", "gold_reads_short.txt"), ("default", "gold_reads_short.txt"),
+                       ("pacbio", "gold_reads_long.txt"), ("nanopore", "gold_reads_long.txt")]:
+        out = os.path.join(H.GOLDEN, "tmp.dump")
+        H.run_ref("align", os.path.join(H.GOLDEN, "gold"), os.path.join(H.GOLDEN, rf), preset, out, SRAND)
+        d = H.load_dump(out)
+        os.remove(out)
+        comp = {}
+        for k, v in d.items():
+            if k == "ksw_seq":
+                comp[k] = v.astype(np.uint8)
+            elif k in ("ksw_cigar",):
+                comp[k] = v.astype(np.uint32)
+            else:
+                comp[k] = v
+        np.savez_compressed(os.path.join(H.GOLDEN, "gold_%s.npz" % preset), **comp)
+        print(preset, {k: len(v) for k, v in d.items() if k.endswith("_off")})
+
+
+if __name__ == "__main__":
+    main()

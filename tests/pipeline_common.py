@@ -1,0 +1,109 @@
+"""Helpers that turn the C-ABI outputs into the same per-stage arrays as the reference dump (oracle/ref_dump.cpp)."""
+import os
+
+import numpy as np
+
+import helpers as H
+from ma_b200 import api, index, synth
+
+SRAND = 1000
+GOLD_PREFIX = os.path.join(H.GOLDEN, "gold")
+
+
+def read_reads_txt(path):
+    with open(path) as f:
+        return [synth.text_to_codes(line.strip()) for line in f if line.strip()]
+
+
+def load_gold(preset):
+    g = np.load(os.path.join(H.GOLDEN, "gold_%s.npz" % preset))
+    return {k: g[k].astype(np.int64) for k in g.files}
+
+
+def gold_reads(preset):
+    name = "gold_reads_short.txt" if preset in ("illumina", "default") else "gold_reads_long.txt"
+    return os.path.join(H.GOLDEN, name)
+
+
+def gpu_stage_dump(ctx, reads, keep_segments=4096):
+    """Runs the path through the C ABI and returns a dict with the reference dump's keys (where exposed)."""
+    data, off = api.pack_reads(reads)
+    n = len(off) - 1
+    out = {}
+    ctx.align_upload(data, off)
+    st1 = ctx.align_run(api.STAGE_SEEDS, keep_segments)
+    info = ctx.download_info()
+    segs, nseg = ctx.download_segments()
+    assert (nseg <= keep_segments).all()
+    seg_rows = []
+    for i in range(n):
+        s = segs[i, :nseg[i]]
+        seg_rows.append(np.stack([s["start"], s["size"], s["sa_start"], s["sa_rev"], s["sa_size"]], axis=1)
+                        .astype(np.int64).reshape(-1))
+    out["seg_off"] = np.concatenate([[0], np.cumsum(nseg)]).astype(np.int64)
+    out["seg"] = np.concatenate(seg_rows) if seg_rows else np.zeros(0, np.int64)
+    seeds = ctx.download_seeds()
+    rows = []
+    for i in range(n):
+        s = seeds[info["seed_off"][i]:info["seed_off"][i] + info["n_seeds"][i]]
+        rows.append(np.stack([s["q"], s["len"], s["r"], s["amb"], s["fw"], s["delta"]], axis=1).astype(np.int64)
+                    .reshape(-1))
+    out["seed_off"] = np.concatenate([[0], np.cumsum(info["n_seeds"])]).astype(np.int64)
+    out["seed"] = np.concatenate(rows) if rows else np.zeros(0, np.int64)
+    st3 = ctx.align_run(api.STAGE_ALIGN, 0)
+    sets, sseeds = ctx.download_sets()
+    info, alns, runs = ctx.download_alignments()
+    harm_off, harmseed_off, harmseed = [0], [0], []
+    aln_off, aln, alndata_off, alndata = [0], [], [0], []
+    for i in range(n):
+        so, ns = int(info["set_off"][i]), int(info["n_sets"][i])
+        for h in sets[so:so + ns]:
+            s = sseeds[h["seed_off"]:h["seed_off"] + h["n"]]
+            harmseed.append(np.stack([s["q"], s["len"], s["r"], s["fw"], np.full(len(s), h["soc_index"])], axis=1)
+                            .astype(np.int64).reshape(-1))
+            harmseed_off.append(harmseed_off[-1] + len(s))
+        harm_off.append(len(harmseed_off) - 1)
+        a = alns[so:so + ns]
+        for k in np.argsort(a["rank"], kind="stable"):
+            x = a[k]
+            aln.append([x["begin_q"], x["end_q"], x["begin_ref"], x["end_ref"], x["score"], x["soc_index"],
+                        x["length"], x["n_runs"]])
+            r = runs[x["run_off"]:x["run_off"] + x["n_runs"]]
+            alndata.append(np.stack([r & 7, r >> 3], axis=1).astype(np.int64).reshape(-1))
+            alndata_off.append(alndata_off[-1] + len(r))
+        aln_off.append(len(aln))
+    out["harm_off"] = np.array(harm_off, dtype=np.int64)
+    out["harmseed_off"] = np.array(harmseed_off, dtype=np.int64)
+    out["harmseed"] = np.concatenate(harmseed) if harmseed else np.zeros(0, np.int64)
+    out["aln_off"] = np.array(aln_off, dtype=np.int64)
+    out["aln"] = np.array(aln, dtype=np.int64).reshape(-1)
+    out["alndata_off"] = np.array(alndata_off, dtype=np.int64)
+    out["alndata"] = np.concatenate(alndata) if alndata else np.zeros(0, np.int64)
+    out["_stats"] = (st1, st3)
+    return out
+
+
+STAGE_KEYS = ["seg_off", "seg", "seed_off", "seed", "harm_off", "harmseed_off", "harmseed", "aln_off", "aln",
+              "alndata_off", "alndata"]
+
+
+def assert_same_stages(got, exp, keys=STAGE_KEYS, what=""):
+    for k in keys:
+        a, b = np.asarray(got[k]), np.asarray(exp[k])
+        assert a.shape == b.shape, "%s %s: shape %s vs %s" % (what, k, a.shape, b.shape)
+        if not np.array_equal(a, b):
+            d = np.nonzero(a != b)[0]
+            raise AssertionError("%s %s: %d mismatching entries, first at %d: %s vs %s" %
+                                 (what, k, len(d), d[0], a[d[:6]], b[d[:6]]))
+
+
+def mismatching_reads(got, exp):
+    """Number of reads whose alignment records differ (used where a floating-point tolerance is stated)."""
+    n = len(exp["aln_off"]) - 1
+    bad = 0
+    for i in range(n):
+        ga = got["aln"][got["aln_off"][i] * 8:got["aln_off"][i + 1] * 8]
+        ea = exp["aln"][exp["aln_off"][i] * 8:exp["aln_off"][i + 1] * 8]
+        if len(ga) != len(ea) or not np.array_equal(ga, ea):
+            bad += 1
+    return bad

@@ -1,0 +1,92 @@
+"""CPU suite: oracle (our restatement) vs golden dumps of the compiled reference; host logic; C-ABI symbol check."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as H
+import pipeline_common as PC
+from ma_b200 import index, synth
+
+PRESETS = ["illumina", "default", "pacbio", "nanopore"]
+
+
+@pytest.mark.parametrize("preset", PRESETS)
+def test_oracle_pipeline_matches_reference_golden(preset, tmp_path):
+    gold = PC.load_gold(preset)
+    o = H.oracle_align_dump(PC.GOLD_PREFIX, PC.gold_reads(preset), preset, str(tmp_path / "o.dump"), PC.SRAND, 5)
+    for k in gold:
+        assert np.array_equal(o[k], gold[k]), k
+
+
+@pytest.mark.skipif(not H.have_ref(), reason="compiled reference (oracle/_ref) not present")
+def test_oracle_matches_live_reference_multi_contig(tmp_path):
+    g = synth.random_genome([120_000, 40_000], 11)
+    synth.write_genome_txt(str(tmp_path / "g.txt"), g)
+    H.run_ref("index", tmp_path / "g.txt", tmp_path / "g")
+    reads, _, _, _ = synth.simulate_reads(g, 600, 150, 12, sub_rate=0.015, ins_rate=0.003, del_rate=0.003)
+    synth.write_reads_txt(str(tmp_path / "r.txt"), reads)
+    H.run_ref("align", tmp_path / "g", tmp_path / "r.txt", "illumina", tmp_path / "r.dump", 5)
+    r = H.load_dump(str(tmp_path / "r.dump"))
+    o = H.oracle_align_dump(str(tmp_path / "g"), str(tmp_path / "r.txt"), "illumina", str(tmp_path / "o.dump"), 5, 5)
+    for k in r:
+        assert np.array_equal(o[k], r[k]), k
+
+
+def test_hostsim_device_routines_match_oracle():
+    """The MA_HD routines that the kernels wrap (seeding, SoC/harmonization, NW glue, exact std::sort/heap), compiled
+    for the host, against the oracle."""
+    d = os.path.join(H.ROOT, "tests", "hostsim")
+    subprocess.check_call(["make", "-s", "-C", d])
+    assert subprocess.call([os.path.join(d, "test_stl_exact")]) == 0
+    for preset in PRESETS:
+        rc = subprocess.call([os.path.join(d, "hostsim"), PC.GOLD_PREFIX, PC.gold_reads(preset), preset,
+                              str(PC.SRAND)])
+        assert rc == 0, preset
+
+
+def test_index_file_roundtrip(tmp_path):
+    ix = index.load_index(PC.GOLD_PREFIX)
+    assert ix.ref_len == 120_000 and ix.fwd_len == 60_000 and len(ix.contig_start) == 3
+    assert np.array_equal(index.pack_forward(ix.forward_codes()), ix.pac)
+    index.store_index(ix, str(tmp_path / "x"))
+    for ext in (".bwt", ".sa", ".pac"):
+        assert open(PC.GOLD_PREFIX + ext, "rb").read() == open(str(tmp_path / "x") + ext, "rb").read(), ext
+    ix2 = index.load_index(str(tmp_path / "x"))
+    assert ix2.contig_names == ix.contig_names and np.array_equal(ix2.contig_len, ix.contig_len)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    lib_path = os.path.join(H.ROOT, "ma_b200", "libma_b200.so")
+    if not os.path.exists(lib_path):
+        import __graft_entry__ as g
+        g.build()
+    lib = ctypes.CDLL(lib_path)
+    hdr = open(os.path.join(H.ROOT, "include", "ma_b200.h")).read()
+    names = set(re.findall(r"\b(ma_b200_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 20
+    for n in sorted(names):
+        assert hasattr(lib, n), n
+
+
+def test_no_cpu_fallback_without_device():
+    from ma_b200 import api
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(api.MaB200Error):
+        api.Context(0)
+
+
+def test_synth_generators_are_deterministic():
+    g1 = synth.random_genome([5000], 3)
+    g2 = synth.random_genome([5000], 3)
+    assert np.array_equal(g1[0], g2[0])
+    r1 = synth.simulate_reads(g1, 50, 150, 4)[0]
+    r2 = synth.simulate_reads(g2, 50, 150, 4)[0]
+    assert np.array_equal(r1, r2) and r1.shape == (50, 150)
+    a, b, *_ = synth.simulate_pairs(g1, 20, 150, 5)
+    assert a.shape == b.shape == (20, 150)

@@ -1,0 +1,165 @@
+"""GPU parity of the whole path through the C ABI: segments, located seeds, harmonized seed sets and alignment
+records must equal the reference's (golden dumps of the compiled reference, and the oracle at larger sizes).
+
+Integer work is compared bit-exactly.  Harmonization contains double-precision libm calls (atan/tan/sin/log); CUDA's
+libm may differ from glibc in the last ulp, so for the LARGE random set the stated tolerance is: at most 0.1 % of
+reads may differ in their alignment records (observed: 0); the golden sets must match exactly."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+import pipeline_common as PC
+from ma_b200 import api, index, synth
+
+pytestmark = pytest.mark.gpu
+PRESETS = ["illumina", "default", "pacbio", "nanopore"]
+
+
+def make_ctx(preset, srand=PC.SRAND):
+    ctx = api.Context(0, preset)
+    p = api.preset(preset)
+    p.srand_base = srand
+    ctx.set_params(p)
+    return ctx
+
+
+@pytest.fixture(scope="module")
+def gold_index():
+    return index.load_index(PC.GOLD_PREFIX)
+
+
+@pytest.mark.parametrize("preset", PRESETS)
+def test_all_stages_match_reference_golden(preset, gold_index):
+    ctx = make_ctx(preset)
+    ctx.index_upload(gold_index)
+    got = PC.gpu_stage_dump(ctx, PC.read_reads_txt(PC.gold_reads(preset)))
+    PC.assert_same_stages(got, PC.load_gold(preset), what=preset)
+    ctx.close()
+
+
+def test_gpu_index_build_is_bit_identical(gold_index):
+    ctx = make_ctx("illumina")
+    ctx.index_build(gold_index.forward_codes(), gold_index.contig_start, gold_index.contig_len)
+    ix = ctx.index_download(gold_index.contig_names)
+    assert ix.primary == gold_index.primary
+    assert np.array_equal(ix.L2, gold_index.L2)
+    assert np.array_equal(ix.bwt, gold_index.bwt)
+    assert np.array_equal(ix.sa, gold_index.sa)
+    assert np.array_equal(ix.pac[:len(gold_index.pac)], gold_index.pac)
+    # and the pipeline on the GPU-built index gives the golden alignments
+    got = PC.gpu_stage_dump(ctx, PC.read_reads_txt(PC.gold_reads("illumina")))
+    PC.assert_same_stages(got, PC.load_gold("illumina"), what="gpu-built index")
+    ctx.close()
+
+
+def test_batch_call_equals_staged_calls_and_sharding(gold_index):
+    """ma_b200_align_batch == upload/run/download; splitting the batch (read sharding) gives the
+    same records when the shard's srand_base is offset by its first read index."""
+    reads = PC.read_reads_txt(PC.gold_reads("illumina"))
+    data, off = api.pack_reads(reads)
+    ctx = make_ctx("illumina")
+    ctx.index_upload(gold_index)
+    info, alns, runs, st = ctx.align_batch(data, off)
+    gold = PC.load_gold("illumina")
+    assert st["n_sets"] == len(gold["aln"]) // 8
+
+    def records(info, alns, runs, lo, hi):
+        out = []
+        for i in range(lo, hi):
+            a = alns[info["set_off"][i]:info["set_off"][i] + info["n_sets"][i]]
+            for k in np.argsort(a["rank"], kind="stable"):
+                x = a[k]
+                out.append((i, int(x["begin_q"]), int(x["end_q"]), int(x["begin_ref"]), int(x["end_ref"]),
+                            int(x["score"]), tuple(runs[x["run_off"]:x["run_off"] + x["n_runs"]].tolist())))
+        return out
+
+    full = records(info, alns, runs, 0, len(reads))
+    half = len(reads) // 2
+    shards = []
+    for lo, hi in [(0, half), (half, len(reads))]:
+        c2 = make_ctx("illumina", PC.SRAND + lo)
+        c2.index_upload(gold_index)
+        d2, o2 = api.pack_reads(reads[lo:hi])
+        i2, a2, r2, _ = c2.align_batch(d2, o2)
+        shards += [(r[0] + lo,) + r[1:] for r in records(i2, a2, r2, 0, hi - lo)]
+        c2.close()
+    assert shards == full
+    ctx.close()
+
+
+def test_edge_batches(gold_index):
+    ctx = make_ctx("illumina")
+    ctx.index_upload(gold_index)
+    # empty batch
+    info, alns, runs, st = ctx.align_batch(np.zeros(0, np.uint8), np.zeros(1, np.int64))
+    assert len(alns) == 0 and st["n_reads"] == 0
+    # empty read, 1-base read, all-N read, read shorter than the minimal seed
+    fwd = gold_index.forward_codes()
+    reads = [np.zeros(0, np.uint8), np.array([2], np.uint8), np.full(40, 4, np.uint8), fwd[100:110].copy(),
+             fwd[2000:2150].copy()]
+    data, off = api.pack_reads(reads)
+    info, alns, runs, st = ctx.align_batch(data, off)
+    assert list(info["n_sets"][:4]) == [0, 0, 0, 0] and info["n_sets"][4] >= 1
+    a = alns[info["set_off"][4]:info["set_off"][4] + info["n_sets"][4]]
+    best = a[np.argmin(a["rank"])]
+    assert (best["begin_ref"], best["end_ref"], best["begin_q"], best["end_q"]) == (2000, 2150, 0, 150)
+    assert best["score"] == 300
+    ctx.close()
+
+
+def test_no_index_is_an_error():
+    ctx = api.Context(0, "illumina")
+    ctx.align_upload(np.zeros(4, np.uint8), np.array([0, 4], np.int64))
+    with pytest.raises(api.MaB200Error):
+        ctx.align_run()
+    ctx.close()
+
+
+def test_config1_scale_against_oracle(tmp_path):
+    """BASELINE.json config 1 (1 Mbp genome, 10 k x 150 bp reads, Illumina preset): GPU-built index, every stage of
+    every read against the oracle."""
+    g = synth.random_genome([1_000_000], 1)
+    reads, _, pos, rev = synth.simulate_reads(g, 10_000, 150, 1)
+    ctx = make_ctx("illumina")
+    ctx.index_build(g[0], np.array([0]), np.array([1_000_000]))
+    ix = ctx.index_download(["chr1"])
+    index.store_index(ix, str(tmp_path / "g1"))
+    synth.write_reads_txt(str(tmp_path / "r.txt"), reads)
+    exp = H.oracle_align_dump(str(tmp_path / "g1"), str(tmp_path / "r.txt"), "illumina", str(tmp_path / "o.dump"),
+                              PC.SRAND, 5)
+    got = PC.gpu_stage_dump(ctx, reads)
+    PC.assert_same_stages(got, exp, keys=["seg_off", "seg", "seed_off", "seed"], what="config1 seeding")
+    bad = PC.mismatching_reads(got, exp)
+    assert bad <= 10, "%d of 10000 reads differ (tolerance 0.1 %%)" % bad
+    if bad == 0:
+        PC.assert_same_stages(got, exp, what="config1")
+    # accuracy sanity: primary alignment within 5 bp of the simulated origin for > 99 % of the reads
+    ok = 0
+    for i in range(len(reads)):
+        lo = got["aln_off"][i]
+        if got["aln_off"][i + 1] > lo:
+            b = got["aln"][lo * 8 + 2]
+            truth = pos[i] if not rev[i] else 2_000_000 - (pos[i] + 150)
+            ok += abs(int(b) - int(truth)) <= 12
+    assert ok > 9900, ok
+    st1, st3 = got["_stats"]
+    assert st3["n_ext"] == int(exp["work"].sum())
+    ctx.close()
+
+
+def test_long_reads_against_oracle(tmp_path):
+    """PacBio preset (maxSpan seeding, long banded DP incl. the 1024-column window): 30 x 4 kbp reads, 12 % error."""
+    g = synth.random_genome([400_000, 200_000], 21)
+    reads, _, _, _ = synth.simulate_long_reads(g, 30, 4000, 22)
+    ctx = make_ctx("pacbio")
+    ctx.index_build(np.concatenate(g), np.array([0, 400_000]), np.array([400_000, 200_000]))
+    ix = ctx.index_download(["c1", "c2"])
+    index.store_index(ix, str(tmp_path / "g"))
+    synth.write_reads_txt(str(tmp_path / "r.txt"), reads)
+    exp = H.oracle_align_dump(str(tmp_path / "g"), str(tmp_path / "r.txt"), "pacbio", str(tmp_path / "o.dump"),
+                              PC.SRAND, 5)
+    got = PC.gpu_stage_dump(ctx, reads, keep_segments=8192)
+    PC.assert_same_stages(got, exp, what="pacbio")
+    ctx.close()
