@@ -177,6 +177,7 @@ class Context:
         self._check(self.lib.ma_b200_index_upload(self.h, _ptr(bwt), bwt.size, _ptr(L2), ix.primary, ix.ref_len,
                                                   _ptr(sa), sa.size, ix.sa_intv, _ptr(pac), pac.size, ix.fwd_len,
                                                   _ptr(cs), _ptr(cl), len(cs)))
+        self._contigs = (cs.copy(), cl.copy())
 
     def index_build(self, fwd_codes: np.ndarray, contig_start, contig_len):
         """Builds the FM-index on the GPU from the forward strand; it stays resident in HBM."""
@@ -184,6 +185,7 @@ class Context:
         cs = np.ascontiguousarray(contig_start, dtype=np.int64)
         cl = np.ascontiguousarray(contig_len, dtype=np.int64)
         self._check(self.lib.ma_b200_index_build(self.h, _ptr(fwd), fwd.size, _ptr(cs), _ptr(cl), len(cs)))
+        self._contigs = (cs.copy(), cl.copy())
 
     def index_download(self, names=None):
         from .index import Index
@@ -197,7 +199,8 @@ class Context:
         ix.pac = np.zeros(npac.value, dtype=np.uint8)
         self._check(self.lib.ma_b200_index_download(self.h, _ptr(ix.bwt), _ptr(ix.sa), _ptr(ix.pac)))
         ix.L2, ix.primary, ix.ref_len, ix.fwd_len = L2, prim.value, int(L2[4]), int(L2[4]) // 2
-        ix.contig_names = names or []
+        ix.contig_start, ix.contig_len = self._contigs
+        ix.contig_names = list(names) if names else ["chr%d" % (i + 1) for i in range(len(ix.contig_start))]
         return ix
 
     # ---- alignment path -------------------------------------------------------------------------------------

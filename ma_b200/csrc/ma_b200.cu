@@ -909,8 +909,11 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
         st.n_invpsi = (int64_t)ctx->hctrl.n_invpsi;
     }
     else
+    {
         for( int i = 1; i < 6; i++ )
             MA_CUDA( cudaEventRecord( ctx->ev[ i ], s ) );
+        ctx->stage_done = upto_stage; // an empty batch has (empty) results for every stage
+    }
     MA_CUDA( cudaEventRecord( ctx->ev[ 6 ], s ) );
     MA_CUDA( cudaEventSynchronize( ctx->ev[ 6 ] ) );
     st.n_seeds = ctx->n_seeds, st.n_sets = ctx->n_sets, st.n_set_seeds = ctx->n_set_seeds, st.n_tasks = ctx->n_tasks;

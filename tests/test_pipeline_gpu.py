@@ -141,7 +141,7 @@ def test_config1_scale_against_oracle(tmp_path):
         lo = got["aln_off"][i]
         if got["aln_off"][i + 1] > lo:
             b = got["aln"][lo * 8 + 2]
-            truth = pos[i] if not rev[i] else 2_000_000 - (pos[i] + 150)
+            truth = pos[i] if not rev[i] else 2_000_000 - (pos[i] + 168)  # reverse read = start of revcomp(168-base template)
             ok += abs(int(b) - int(truth)) <= 12
     assert ok > 9900, ok
     st1, st3 = got["_stats"]
