@@ -1,0 +1,340 @@
+// Host side of the drop-in boundary, C++17, header only: the reference's Module interface for the path
+// (libMS::Module<Ret, IS_VOLATILE, Args...>::execute, libs/ms/inc/ms/module/module.h:63-122), mirrored with the same
+// module names, argument meaning and error behaviour (C++ exceptions), but over BATCHES of reads, because one GPU
+// launch per read would waste the device.  Everything below only marshals std::vector buffers into
+// the C ABI of libma_b200.so (include/ma_b200.h); no algorithm lives here and there is no CPU fallback.
+//
+//   reference (one read per call)                                          here (a batch per call)
+//   BinarySeeding : Module<SegmentVector,false,SuffixArrayInterface,NucSeq>  BinarySeeding::execute(FMIndex, reads)
+//     (binarySeeding.h:26, 571-584)                                          BinarySeeding::seed(FMIndex, reads)
+//   StripOfConsideration : Module<SoCPriorityQueue,false,SegmentVector,NucSeq,Pack,FMIndex> (stripOfConsideration.h:164)
+//   Harmonization : Module<ContainerVector<shared_ptr<Seeds>>,false,SoCPriorityQueue,NucSeq,FMIndex> (harmonization.h:34)
+//                                                                           Harmonization::execute(FMIndex, reads)
+//   NeedlemanWunsch : Module<ContainerVector<shared_ptr<Alignment>>,false,ContainerVector<shared_ptr<Seeds>>,NucSeq,Pack>
+//     (needlemanWunsch.h:51, 111-134)                                       NeedlemanWunsch::execute(FMIndex, reads)
+//   setUpCompGraph (export.cpp:72-128)                                      Aligner::align(reads)
+#pragma once
+#include "ma_b200.h"
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace libMA_b200
+{
+
+typedef uint64_t nucSeqIndex;
+
+// ParameterSetManager (parameter.h:1067-1201): presets by name, the selected set is what modules copy at construction
+class ParameterSetManager
+{
+  public:
+    ma_b200_params xParams;
+    ParameterSetManager( )
+    {
+        ma_b200_params_preset( "default", &xParams );
+    }
+    void setSelected( const std::string& sName )
+    {
+        if( ma_b200_params_preset( sName.c_str( ), &xParams ) != MA_B200_OK )
+            throw std::runtime_error( "unknown preset " + sName );
+    }
+};
+
+// NucSeq (nucSeq.h:61-153): 1 byte per base, A=0 C=1 G=2 T=3 N=4
+class NucSeq
+{
+  public:
+    std::vector<uint8_t> vSeq;
+    std::string sName = "unknown";
+    NucSeq( ) = default;
+    explicit NucSeq( const std::string& sText )
+    {
+        for( char c : sText )
+            vSeq.push_back( c == 'A' || c == 'a' ? 0 : c == 'C' || c == 'c' ? 1 : c == 'G' || c == 'g' ? 2
+                                                   : c == 'T' || c == 't' ? 3 : 4 );
+    }
+    size_t length( ) const
+    {
+        return vSeq.size( );
+    }
+};
+
+struct Segment // segment.h:31-115
+{
+    nucSeqIndex uiStart, uiSize; // size = length - 1
+    int64_t iSaStart, iSaStartRevComp, iSaSize;
+};
+typedef std::vector<Segment> SegmentVector;
+
+struct Seed // seed.h:34-43
+{
+    nucSeqIndex uiStart, uiSize, uiPosOnReference;
+    unsigned int uiAmbiguity;
+    bool bOnForwStrand;
+    nucSeqIndex uiDelta;
+};
+struct Seeds
+{
+    std::vector<Seed> vContent;
+    unsigned int index_of_strip = 0; // xStats.index_of_strip
+};
+
+enum MatchType // alignment.h:40-47
+{
+    seed,
+    match,
+    missmatch,
+    insertion,
+    deletion
+};
+struct Alignment // alignment.h:55-95
+{
+    std::vector<std::pair<MatchType, nucSeqIndex>> data;
+    nucSeqIndex uiLength = 0, uiBeginOnRef = 0, uiEndOnRef = 0, uiBeginOnQuery = 0, uiEndOnQuery = 0;
+    int64_t iScore = 0;
+    unsigned int index_of_strip = 0;
+    int64_t score( ) const
+    {
+        return iScore;
+    }
+};
+
+// One CUDA device: context + the replicated FMIndex / Pack (fMIndex.h, pack.h). Loads the reference's index files.
+class FMIndex
+{
+    ma_b200_ctx* pCtx = nullptr;
+
+  public:
+    explicit FMIndex( int iDevice = 0 )
+    {
+        if( ma_b200_create( iDevice, &pCtx ) != MA_B200_OK )
+            throw std::runtime_error( "ma_b200_create failed: no CUDA device (there is no CPU fallback)" );
+    }
+    FMIndex( const FMIndex& ) = delete;
+    ~FMIndex( )
+    {
+        ma_b200_destroy( pCtx );
+    }
+    ma_b200_ctx* ctx( ) const
+    {
+        return pCtx;
+    }
+    void check( int rc ) const
+    {
+        if( rc != MA_B200_OK )
+            throw std::runtime_error( std::string( "ma_b200: " ) + ma_b200_last_error( pCtx ) );
+    }
+    // FMIndex(prefix) + Pack(prefix): vLoadFMIndex (fMIndex.h:854-884), vLoadCollection (pack.h:799-812)
+    void vLoad( const std::string& sPrefix )
+    {
+        auto slurp = []( const std::string& f ) {
+            std::ifstream in( f, std::ios::binary );
+            if( !in )
+                throw std::runtime_error( "File opening error: " + f );
+            return std::vector<char>( ( std::istreambuf_iterator<char>( in ) ), std::istreambuf_iterator<char>( ) );
+        };
+        auto b = slurp( sPrefix + ".bwt" );
+        int64_t primary, L2[ 5 ] = { 0, 0, 0, 0, 0 };
+        memcpy( &primary, b.data( ), 8 );
+        memcpy( &L2[ 1 ], b.data( ) + 8, 32 );
+        const int64_t nWords = (int64_t)( b.size( ) - 40 ) / 4, refLen = L2[ 4 ];
+        auto s = slurp( sPrefix + ".sa" );
+        int32_t saIntv;
+        memcpy( &saIntv, s.data( ) + 40, 4 );
+        const int64_t nSa = ( refLen + saIntv ) / saIntv;
+        std::vector<int64_t> sa( nSa );
+        sa[ 0 ] = -1;
+        memcpy( &sa[ 1 ], s.data( ) + 52, ( nSa - 1 ) * 8 );
+        std::ifstream ann( sPrefix + ".ann" );
+        if( !ann )
+            throw std::runtime_error( "File opening error: " + sPrefix + ".ann" );
+        int64_t fwdLen, nSeq, seedv;
+        ann >> fwdLen >> nSeq >> seedv;
+        std::vector<int64_t> cs( nSeq ), cl( nSeq );
+        std::string line;
+        std::getline( ann, line );
+        for( int64_t i = 0; i < nSeq; i++ )
+        {
+            std::getline( ann, line );
+            int64_t holes;
+            ann >> cs[ i ] >> cl[ i ] >> holes;
+            std::getline( ann, line );
+        }
+        auto p = slurp( sPrefix + ".pac" );
+        check( ma_b200_index_upload( pCtx, (const uint32_t*)( b.data( ) + 40 ), nWords, L2, primary, refLen, sa.data( ),
+                                     nSa, saIntv, (const uint8_t*)p.data( ), ( fwdLen + 3 ) / 4, fwdLen, cs.data( ),
+                                     cl.data( ), (int32_t)nSeq ) );
+    }
+};
+
+namespace detail
+{
+inline void upload( FMIndex& rIdx, const ParameterSetManager& rP, const std::vector<NucSeq>& vReads )
+{
+    rIdx.check( ma_b200_set_params( rIdx.ctx( ), &rP.xParams ) );
+    std::vector<uint8_t> vData;
+    std::vector<int64_t> vOff( 1, 0 );
+    for( auto& r : vReads )
+    {
+        vData.insert( vData.end( ), r.vSeq.begin( ), r.vSeq.end( ) );
+        vOff.push_back( (int64_t)vData.size( ) );
+    }
+    vData.push_back( 0 );
+    rIdx.check( ma_b200_align_upload( rIdx.ctx( ), (int64_t)vReads.size( ), vData.data( ), vOff.data( ) ) );
+}
+inline Seed toSeed( const ma_b200_seed& s )
+{
+    return Seed{ (nucSeqIndex)s.q, (nucSeqIndex)s.len, (nucSeqIndex)s.r, s.ambiguity, s.on_forward != 0,
+                 (nucSeqIndex)s.delta };
+}
+} // namespace detail
+
+class BinarySeeding
+{
+    const ParameterSetManager& rParams;
+
+  public:
+    explicit BinarySeeding( const ParameterSetManager& rParameters ) : rParams( rParameters )
+    {}
+    // BinarySeeding::execute for every read of the batch (binarySeeding.cpp:86-178)
+    std::vector<SegmentVector> execute( FMIndex& rIdx, const std::vector<NucSeq>& vQueries, int iMaxSegments = 4096 )
+    {
+        detail::upload( rIdx, rParams, vQueries );
+        ma_b200_align_stats st;
+        rIdx.check( ma_b200_align_run( rIdx.ctx( ), MA_B200_STAGE_SEEDS, iMaxSegments, &st ) );
+        std::vector<ma_b200_segment> vSeg( vQueries.size( ) * (size_t)iMaxSegments );
+        std::vector<int32_t> vN( vQueries.size( ) );
+        rIdx.check( ma_b200_align_download_segments( rIdx.ctx( ), vSeg.data( ), vN.data( ) ) );
+        std::vector<SegmentVector> vRet( vQueries.size( ) );
+        for( size_t i = 0; i < vQueries.size( ); i++ )
+        {
+            if( vN[ i ] > iMaxSegments )
+                throw std::runtime_error( "BinarySeeding: more segments than iMaxSegments" );
+            for( int j = 0; j < vN[ i ]; j++ )
+            {
+                const auto& s = vSeg[ i * (size_t)iMaxSegments + j ];
+                vRet[ i ].push_back( Segment{ (nucSeqIndex)s.start, (nucSeqIndex)s.size, s.sa_start, s.sa_rev_start,
+                                              s.sa_size } );
+            }
+        }
+        return vRet;
+    }
+    // BinarySeeding::seed (binarySeeding.h:575-584): execute + extractSeeds, already batched in the reference
+    std::vector<Seeds> seed( FMIndex& rIdx, const std::vector<NucSeq>& vQueries )
+    {
+        detail::upload( rIdx, rParams, vQueries );
+        ma_b200_align_stats st;
+        rIdx.check( ma_b200_align_run( rIdx.ctx( ), MA_B200_STAGE_SEEDS, 0, &st ) );
+        std::vector<ma_b200_read_info> vInfo( vQueries.size( ) );
+        std::vector<ma_b200_seed> vSeeds( (size_t)st.n_seeds + 1 );
+        rIdx.check( ma_b200_align_download_info( rIdx.ctx( ), vInfo.data( ) ) );
+        rIdx.check( ma_b200_align_download_seeds( rIdx.ctx( ), vSeeds.data( ), (int64_t)vSeeds.size( ) ) );
+        std::vector<Seeds> vRet( vQueries.size( ) );
+        for( size_t i = 0; i < vQueries.size( ); i++ )
+            for( int j = 0; j < vInfo[ i ].n_seeds; j++ )
+                vRet[ i ].vContent.push_back( detail::toSeed( vSeeds[ vInfo[ i ].seed_off + j ] ) );
+        return vRet;
+    }
+};
+
+// StripOfConsideration + Harmonization (the SoCPriorityQueue between them never leaves the device)
+class Harmonization
+{
+    const ParameterSetManager& rParams;
+
+  public:
+    explicit Harmonization( const ParameterSetManager& rParameters ) : rParams( rParameters )
+    {}
+    std::vector<std::vector<Seeds>> execute( FMIndex& rIdx, const std::vector<NucSeq>& vQueries )
+    {
+        detail::upload( rIdx, rParams, vQueries );
+        ma_b200_align_stats st;
+        rIdx.check( ma_b200_align_run( rIdx.ctx( ), MA_B200_STAGE_SETS, 0, &st ) );
+        std::vector<ma_b200_read_info> vInfo( vQueries.size( ) );
+        std::vector<ma_b200_seed_set> vSets( (size_t)st.n_sets + 1 );
+        std::vector<ma_b200_seed> vSeeds( (size_t)st.n_set_seeds + 1 );
+        rIdx.check( ma_b200_align_download_info( rIdx.ctx( ), vInfo.data( ) ) );
+        rIdx.check( ma_b200_align_download_sets( rIdx.ctx( ), vSets.data( ), (int64_t)vSets.size( ), vSeeds.data( ),
+                                                 (int64_t)vSeeds.size( ) ) );
+        std::vector<std::vector<Seeds>> vRet( vQueries.size( ) );
+        for( size_t i = 0; i < vQueries.size( ); i++ )
+            for( int k = 0; k < vInfo[ i ].n_sets; k++ )
+            {
+                const auto& h = vSets[ vInfo[ i ].set_off + k ];
+                Seeds xS;
+                xS.index_of_strip = h.soc_index;
+                for( int j = 0; j < h.n; j++ )
+                    xS.vContent.push_back( detail::toSeed( vSeeds[ h.seed_off + j ] ) );
+                vRet[ i ].push_back( xS );
+            }
+        return vRet;
+    }
+};
+
+class NeedlemanWunsch
+{
+    const ParameterSetManager& rParams;
+
+  public:
+    explicit NeedlemanWunsch( const ParameterSetManager& rParameters ) : rParams( rParameters )
+    {}
+    // per read: the alignments in the order of the reference's result vector (best first, needlemanWunsch.h:131-132)
+    std::vector<std::vector<Alignment>> execute( FMIndex& rIdx, const std::vector<NucSeq>& vQueries,
+                                                 ma_b200_align_stats* pStats = nullptr )
+    {
+        detail::upload( rIdx, rParams, vQueries );
+        ma_b200_align_stats st;
+        rIdx.check( ma_b200_align_run( rIdx.ctx( ), MA_B200_STAGE_ALIGN, 0, &st ) );
+        if( pStats )
+            *pStats = st;
+        std::vector<ma_b200_read_info> vInfo( vQueries.size( ) );
+        std::vector<ma_b200_alignment> vAln( (size_t)st.n_sets + 1 );
+        std::vector<uint32_t> vRuns( (size_t)st.n_runs + 1 );
+        rIdx.check( ma_b200_align_download( rIdx.ctx( ), vInfo.data( ), vAln.data( ), (int64_t)vAln.size( ),
+                                            vRuns.data( ), (int64_t)vRuns.size( ) ) );
+        std::vector<std::vector<Alignment>> vRet( vQueries.size( ) );
+        for( size_t i = 0; i < vQueries.size( ); i++ )
+        {
+            vRet[ i ].resize( vInfo[ i ].n_sets );
+            for( int k = 0; k < vInfo[ i ].n_sets; k++ )
+            {
+                const auto& a = vAln[ vInfo[ i ].set_off + k ];
+                Alignment& x = vRet[ i ][ a.rank ];
+                x.uiBeginOnRef = (nucSeqIndex)a.begin_ref, x.uiEndOnRef = (nucSeqIndex)a.end_ref;
+                x.uiBeginOnQuery = (nucSeqIndex)a.begin_q, x.uiEndOnQuery = (nucSeqIndex)a.end_q;
+                x.iScore = a.score, x.uiLength = (nucSeqIndex)a.length, x.index_of_strip = a.soc_index;
+                for( int j = 0; j < a.n_runs; j++ )
+                    x.data.emplace_back( (MatchType)( vRuns[ a.run_off + j ] & 7 ), vRuns[ a.run_off + j ] >> 3 );
+            }
+        }
+        return vRet;
+    }
+};
+
+// The batched graph: what setUpCompGraph (export.cpp:72-128) wires per thread, executed for a whole batch on one GPU.
+class Aligner
+{
+    ParameterSetManager xParams;
+    FMIndex xIndex;
+
+  public:
+    Aligner( const std::string& sIndexPrefix, const std::string& sPreset, int iDevice = 0 ) : xIndex( iDevice )
+    {
+        xParams.setSelected( sPreset );
+        xIndex.vLoad( sIndexPrefix );
+    }
+    ParameterSetManager& params( )
+    {
+        return xParams;
+    }
+    std::vector<std::vector<Alignment>> align( const std::vector<NucSeq>& vReads, ma_b200_align_stats* pStats = nullptr )
+    {
+        return NeedlemanWunsch( xParams ).execute( xIndex, vReads, pStats );
+    }
+};
+
+} // namespace libMA_b200
