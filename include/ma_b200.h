@@ -80,7 +80,7 @@ int64_t ma_b200_launch_count( const ma_b200_ctx* ctx );
 typedef struct
 {
     int64_t qoff, toff; /* byte offsets of query / target in the sequence slab */
-    int32_t qlen, tlen, w, zdrop, flag, tag;
+    int32_t qlen, tlen, w, zdrop, flag, tag; /* tag: caller's cookie, ignored */
 } ma_b200_ksw_task;
 
 /* kswcpp_extz_t (kswcpp.h:31-41); the cigar lives at cigar[cigar_off .. cigar_off + n_cigar), word = len<<4 | op,

@@ -54,11 +54,16 @@ __device__ __forceinline__ bool ksw_band( long long r, int qlen, int tlen, int w
     return st <= en;
 }
 
-// Shared memory per warp: 7 int8 arrays of W + one int32 array of W.
+// Shared memory per warp: a circular window of W columns — 7 int8 difference arrays, the H row, the target codes of
+// the window (decoded once when a column enters) — plus the query (when it fits) so that a row never touches HBM
+// except for its traceback bytes.
 template <int W> struct KswSmem
 {
     signed char u[ W ], v[ W ], x[ W ], y[ W ], x2[ W ], y2[ W ], s[ W ];
+    unsigned char tc[ W ];
     int H[ W ];
+    static constexpr int QC = 2 * W <= 1024 ? 2 * W : 1024;
+    unsigned char qc[ QC ];
 };
 
 // lane 0 only. Walks the traceback slab (kswcpp_core.h:76-150, is_rot = 1, min_intron_len = 0) and pushes run-length
@@ -153,13 +158,16 @@ struct SeqAccess
 
 // One warp, one problem. All lanes return the same KswOut (cigar_off/n_cigar are filled by the caller).
 // tb: per-warp traceback slab of >= (qlen+tlen-1)*ncol16 bytes.
+// Per anti-diagonal ONE fused pass over the aligned column range does: score profile, the difference recurrence with
+// its traceback byte, the H-row update and the candidates of the reference's lane-blocked arg-max.
 template <int W>
 __device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int tlen, int w, int zdrop, int flag,
-                          KswSmem<W>& sm, unsigned char* __restrict__ tb, KswOut& ez )
+                          bool bEarlyStop, KswSmem<W>& sm, unsigned char* __restrict__ tb, KswOut& ez )
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int M = W - 1;
+    const int NONE_T = 0x7fffffff, NONE_H = (int)0x80000000;
     ez.max_q = ez.max_t = ez.mqe_t = ez.mte_q = -1;
     ez.max = 0;
     ez.score = ez.mqe = ez.mte = (int)0x80000000;
@@ -178,11 +186,28 @@ __device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int
     const int SIZE = is16 ? 8 : 4;
     const int NEG_INF = is16 ? -32768 : (int)0x80000000;
     const int init6 = w8( -q - e ), init25 = w8( -q2 - e2 );
+    const int scN = -e2, scM = P.match, scX = P.mismatch;
+    // stage the query in shared memory when it fits
+    const bool qStaged = qlen <= KswSmem<W>::QC;
+    if( qStaged )
+    {
+        for( int i = lane; i < qlen; i += 32 )
+            sm.qc[ i ] = (unsigned char)seq.Q( i );
+        __syncwarp( );
+    }
 
     int inited_end = 0; // columns [0, inited_end) of the circular window carry reference-visible state
     int last_st = -1, last_en = -1;
     long long cells = 0;
     const long long nrows = (long long)qlen + tlen - 1;
+    // Early termination (extensions whose caller consumes only max / max_q / max_t / CIGAR). Because the recurrence
+    // clips z at the match score (kswcpp_core.h:702), every in-band value obeys H_r[t] <= H_{r-2}[t-1] + match, so no
+    // later cell can exceed  B = max over the last two rows of H + match * (query rows still below the cell),  nor
+    //   T = match * qlen - cheapest gap over r+1 target bases  for diagonals that enter through query row 0.
+    // Once max(B_r, B_{r-1}, T_r) <= ez.max the maximum and its position are final; the reference would only go on
+    // to set zdropped / mqe / mte / score, which such callers never read. Validated against the reference
+    // restatement on 120 k adversarial problems (oracle/ksw_oracle.cpp: ma_oracle_ksw_earlystop_check).
+    long long prevB = 0x7fffffffffffll;
     for( long long r = 0; r < nrows; ++r )
     {
         int st0, en0;
@@ -193,7 +218,9 @@ __device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int
         }
         cells += en0 - st0 + 1;
         const int st = st0 & ~15, en = en0 | 15;
-        const int sEnd = st0 + ( ( ( en0 - st0 ) >> 4 ) + 1 ) * 16; // exclusive end of the score-profile writes
+        int sEnd = st0 + ( ( ( en0 - st0 ) >> 4 ) + 1 ) * 16; // exclusive end of the score-profile writes
+        if( sEnd > T16 )
+            sEnd = T16; // the reference spills into its target copy beyond T16; those bytes are never read again
         {
             int need = en + 1 > ( ( sEnd + 15 ) & ~15 ) ? en + 1 : ( ( sEnd + 15 ) & ~15 );
             if( need > T16 )
@@ -207,6 +234,7 @@ __device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int
                     sm.x2[ k ] = sm.y2[ k ] = (signed char)init25;
                     sm.s[ k ] = 0;
                     sm.H[ k ] = NEG_INF;
+                    sm.tc[ k ] = idx < tlen ? (unsigned char)seq.T( idx ) : (unsigned char)0;
                 }
                 inited_end = need;
                 __syncwarp( );
@@ -230,25 +258,40 @@ __device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int
             sm.y2[ r & M ] = (signed char)init25;
             sm.u[ r & M ] = (signed char)first_col;
         }
-        // score profile from the unaligned st0 in steps of 16 (kswcpp_core.h:591-616); N scores -e2
-        for( int tt = st0 + lane; tt < sEnd && tt < T16; tt += 32 )
-        {
-            const int a = tt < tlen ? seq.T( tt ) : 0;
-            const long long qi = r - tt;
-            const int b = ( qi >= 0 && qi < qlen ) ? seq.Q( qi ) : 0;
-            sm.s[ tt & M ] = (signed char)( ( a == 4 || b == 4 ) ? -e2 : ( a == b ? P.match : P.mismatch ) );
-        }
+        // old H of the column left of en0: read before the pass updates it (kswcpp_core.h:194-195)
+        const int hprev = en0 > 0 ? sm.H[ ( en0 - 1 ) & M ] : sm.H[ en0 & M ];
         __syncwarp( );
+        const int en1 = st0 + ( ( en0 - st0 ) / SIZE ) * SIZE;
+        const int qiBase = (int)( r < 0x7fffffff ? r : 0x7fffffff ); // r - t is evaluated in int below
+        int bh = NONE_H, bt = NONE_T; // this lane's SSE-lane candidate: first block reaching the lane maximum
+        int th = NONE_H, tt_ = NONE_T; // candidate among the scalar tail [en1, en0)
+        int hb = NONE_H; // early-stop bound of this lane: H + match * (qlen - 1 - i)
+        const int hbBase = scM * ( qlen - 1 - qiBase ); // + match * t
+        int Hen0l = 0, Hst0l = 0;
         unsigned char* rowp = tb + r * ncol16 - st;
         for( int base = st; base <= en; base += 32 )
         {
             const int t = base + lane;
             const bool act = t <= en;
             const int k = t & M;
-            int xo = 0, vo = 0, x2o = 0, ut = 0, yo = 0, y2o = 0, z = 0;
+            int xo = 0, vo = 0, x2o = 0, ut = 0, yo = 0, y2o = 0, z = 0, hOld = 0;
             if( act )
-                xo = sm.x[ k ], vo = sm.v[ k ], x2o = sm.x2[ k ], ut = sm.u[ k ], yo = sm.y[ k ], y2o = sm.y2[ k ],
-                z = sm.s[ k ];
+            {
+                xo = sm.x[ k ], vo = sm.v[ k ], x2o = sm.x2[ k ], ut = sm.u[ k ], yo = sm.y[ k ], y2o = sm.y2[ k ];
+                hOld = sm.H[ k ];
+                if( t >= st0 && t < sEnd )
+                { // score profile (kswcpp_core.h:591-616); N scores -e2; beyond the sequences the zero padding = 'A'
+                    const int a = sm.tc[ k ];
+                    const int qi = qiBase - t;
+                    int b = 0;
+                    if( qi >= 0 && qi < qlen )
+                        b = qStaged ? (int)sm.qc[ qi ] : seq.Q( qi );
+                    z = ( a == 4 || b == 4 ) ? scN : ( a == b ? scM : scX );
+                    sm.s[ k ] = (signed char)z;
+                }
+                else
+                    z = sm.s[ k ]; // out-of-band cell of the aligned range: stale profile, as in the reference
+            }
             int xt1 = __shfl_up_sync( FULL, xo, 1 ), vt1 = __shfl_up_sync( FULL, vo, 1 ),
                 x2t1 = __shfl_up_sync( FULL, x2o, 1 );
             if( lane == 0 )
@@ -279,9 +322,10 @@ __device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int
                     z = max( z, a2 );
                     z = max( z, b2 );
                 }
-                z = min( z, P.match );
-                sm.u[ k ] = (signed char)( z - vt1 );
-                sm.v[ k ] = (signed char)( z - ut );
+                z = min( z, scM );
+                const int un = w8( z - vt1 ), vn = w8( z - ut );
+                sm.u[ k ] = (signed char)un;
+                sm.v[ k ] = (signed char)vn;
                 int tmp = w8( z - q );
                 a = w8( a - tmp ), b = w8( b - tmp );
                 tmp = w8( z - q2 );
@@ -305,71 +349,93 @@ __device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int
                 sm.x2[ k ] = (signed char)( max( a2, 0 ) - qe2 );
                 sm.y2[ k ] = (signed char)( max( b2, 0 ) - qe2 );
                 rowp[ t ] = (unsigned char)d;
+                // ---- H row (calcMaxScore, kswcpp_core.h:178-250), fused
+                if( r > 0 )
+                {
+                    if( t >= st0 && t < en0 )
+                    {
+                        int h = (int)( (unsigned)hOld + (unsigned)vn );
+                        if( is16 )
+                            h = (short)h;
+                        sm.H[ k ] = h;
+                        hb = max( hb, h + hbBase + scM * t );
+                        if( t == st0 )
+                            Hst0l = h;
+                        if( t < en1 )
+                        { // strict '>' keeps the first block of this SSE lane that reaches its maximum
+                            if( bt == NONE_T || h > bh )
+                                bh = h, bt = st0 + ( ( t - st0 ) / SIZE ) * SIZE;
+                        }
+                        else if( tt_ == NONE_T || h > th )
+                            th = h, tt_ = t;
+                    }
+                    else if( t == en0 )
+                    {
+                        int h = (int)( (unsigned)hprev + (unsigned)( en0 > 0 ? un : vn ) );
+                        if( is16 )
+                            h = (short)h;
+                        sm.H[ k ] = h;
+                        hb = max( hb, h + hbBase + scM * t );
+                        Hen0l = h;
+                        if( t == st0 )
+                            Hst0l = h;
+                    }
+                }
+                else if( t == 0 )
+                {
+                    int h = vn - qe;
+                    if( is16 )
+                        h = (short)h;
+                    sm.H[ 0 ] = h;
+                    Hen0l = h, Hst0l = h;
+                }
             }
         }
-        __syncwarp( );
-        // ---- calcMaxScore, exact branch (kswcpp_core.h:178-264)
-        int max_H, max_t, Hen0;
+        // score-profile entries the reference writes beyond the aligned range (read, stale, by later rows)
+        for( int t = en + 1 + lane; t < sEnd; t += 32 )
+        {
+            const int k = t & M;
+            const int a = sm.tc[ k ];
+            const int qi = qiBase - t;
+            int b = 0;
+            if( qi >= 0 && qi < qlen )
+                b = qStaged ? (int)sm.qc[ qi ] : seq.Q( qi );
+            sm.s[ k ] = (signed char)( ( a == 4 || b == 4 ) ? scN : ( a == b ? scM : scX ) );
+        }
+        const int Hen0 = __shfl_sync( FULL, Hen0l, ( en0 - st ) & 31 );
+        const int Hst0 = __shfl_sync( FULL, Hst0l, ( st0 - st ) & 31 );
+        int max_H, max_t;
         if( r > 0 )
         {
-            const int en1 = st0 + ( ( en0 - st0 ) / SIZE ) * SIZE;
-            const int hprev = en0 > 0 ? sm.H[ ( en0 - 1 ) & M ] : sm.H[ en0 & M ];
-            const int dlt = en0 > 0 ? sm.u[ en0 & M ] : sm.v[ en0 & M ];
-            Hen0 = (int)( (unsigned)hprev + (unsigned)dlt );
-            if( is16 )
-                Hen0 = (short)Hen0;
-            __syncwarp( ); // every lane has read the old H[en0-1] before it is updated below
-            int bh = (int)0x80000000, bt = 0x7fffffff;
-            for( int t = st0 + lane; t < en0; t += 32 )
-            {
-                int h = (int)( (unsigned)sm.H[ t & M ] + (unsigned)(int)sm.v[ t & M ] );
-                if( is16 )
-                    h = (short)h;
-                sm.H[ t & M ] = h;
-                if( t < en1 && ( bt == 0x7fffffff || h > bh ) )
-                    bh = h, bt = st0 + ( ( t - st0 ) / SIZE ) * SIZE;
-            }
-            if( lane == 0 )
-                sm.H[ en0 & M ] = Hen0;
-            // lanes with equal (lane % SIZE) form one SSE lane of the reference: first block reaching the lane max
+            // lanes with equal (lane % SIZE) form one SSE lane of the reference
             for( int o = 16; o >= SIZE; o >>= 1 )
             {
                 const int oh = __shfl_xor_sync( FULL, bh, o ), ot = __shfl_xor_sync( FULL, bt, o );
-                if( ot != 0x7fffffff && ( bt == 0x7fffffff || oh > bh || ( oh == bh && ot < bt ) ) )
+                if( ot != NONE_T && ( bt == NONE_T || oh > bh || ( oh == bh && ot < bt ) ) )
                     bh = oh, bt = ot;
             }
-            if( bt == 0x7fffffff || !( bh > Hen0 ) )
+            if( bt == NONE_T || !( bh > Hen0 ) )
                 bh = Hen0, bt = en0;
             max_H = __reduce_max_sync( FULL, bh );
             max_t = __reduce_max_sync( FULL, bt );
-            __syncwarp( );
-            for( int t = en1; t < en0; ++t )
+            // scalar tail [en1, en0): the first index of the tail maximum, if it beats the vector result
+            const int tm = __reduce_max_sync( FULL, tt_ == NONE_T ? NONE_H : th );
+            if( __any_sync( FULL, tt_ != NONE_T ) && tm > max_H )
             {
-                const int h = sm.H[ t & M ];
-                if( h > max_H )
-                    max_H = h, max_t = t;
+                max_H = tm;
+                max_t = __reduce_min_sync( FULL, ( tt_ != NONE_T && th == tm ) ? tt_ : NONE_T );
             }
         }
         else
         {
-            Hen0 = sm.v[ 0 ] - qe;
-            if( is16 )
-                Hen0 = (short)Hen0;
-            __syncwarp( );
-            if( lane == 0 )
-                sm.H[ 0 ] = Hen0;
             max_H = Hen0;
             max_t = 0;
-            __syncwarp( );
         }
+        __syncwarp( );
         if( en0 == tlen - 1 && Hen0 > ez.mte )
             ez.mte = Hen0, ez.mte_q = (int)( r - en ); // sic: the aligned en
-        if( r - st0 == qlen - 1 )
-        {
-            const int hs = sm.H[ st0 & M ];
-            if( hs > ez.mqe )
-                ez.mqe = hs, ez.mqe_t = st0;
-        }
+        if( r - st0 == qlen - 1 && Hst0 > ez.mqe )
+            ez.mqe = Hst0, ez.mqe_t = st0;
         { // ksw_apply_zdrop (kswcpp_core.h:22-44)
             const int rr = (int)r;
             if( max_H > ez.max )
@@ -388,6 +454,20 @@ __device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int
         if( r == nrows - 1 && en0 == tlen - 1 )
             ez.score = Hen0;
         last_st = st, last_en = en;
+        if( bEarlyStop )
+        {
+            const long long B = r > 0 ? (long long)__reduce_max_sync( FULL, hb ) : 0x7fffffffffffll;
+            if( r >= qlen && prevB != 0x7fffffffffffll )
+            {
+                const long long j = r + 1;
+                const long long g1 = q + (long long)e * j, g2 = q2 + (long long)e2 * j;
+                const long long T = (long long)scM * qlen - ( g1 < g2 ? g1 : g2 );
+                const long long bound = B > prevB ? ( B > T ? B : T ) : ( prevB > T ? prevB : T );
+                if( bound <= (long long)ez.max )
+                    break;
+            }
+            prevB = B;
+        }
     }
     ez.cells = cells;
     __syncwarp( );
@@ -460,7 +540,7 @@ template <int W> __global__ void __launch_bounds__( 256 ) ksw_batch_kernel( KswB
         sa.qbase = A.seq, sa.qoff = T.qoff, sa.qstep = ( T.tag & MA_TASK_QREV ) ? -1 : 1;
         sa.tslab = A.seq, sa.toff = T.toff, sa.tstep = ( T.tag & MA_TASK_TREV ) ? -1 : 1;
         sa.pac = ( T.tag & MA_TASK_TPACK ) ? A.pac : nullptr, sa.fwd_len = A.fwd_len;
-        ksw_warp<W>( A.score, sa, T.qlen, T.tlen, T.w, T.zdrop, T.flag, sm, tb, ez );
+        ksw_warp<W>( A.score, sa, T.qlen, T.tlen, T.w, T.zdrop, T.flag, ( T.tag & MA_TASK_EARLYSTOP ) != 0, sm, tb, ez );
         ez.cigar_off = 0;
         int i0 = 0, j0 = 0, n = 0;
         const bool bBt = ( T.qlen > 0 && T.tlen > 0 && !A.score.early_return ) &&

@@ -305,8 +305,14 @@ extern "C" int ma_b200_ksw_upload( ma_b200_ctx* ctx, int64_t n, const ma_b200_ks
     ctx->ksw_ctrl.reserve( 4 );
     if( n > 0 )
     {
-        MA_CUDA( cudaMemcpyAsync( ctx->ksw_tasks.p, tasks, n * sizeof( KswTask ), cudaMemcpyHostToDevice,
+        // `tag` is the caller's cookie; on the device the field carries the internal addressing mode (0 = byte slab)
+        std::vector<KswTask> vTasks( (size_t)n );
+        memcpy( vTasks.data( ), tasks, n * sizeof( KswTask ) );
+        for( auto& t : vTasks )
+            t.tag = 0;
+        MA_CUDA( cudaMemcpyAsync( ctx->ksw_tasks.p, vTasks.data( ), n * sizeof( KswTask ), cudaMemcpyHostToDevice,
                                   ctx->stream ) );
+        MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
         MA_CUDA( cudaMemcpyAsync( ctx->ksw_seq.p, seq, seq_bytes, cudaMemcpyHostToDevice, ctx->stream ) );
         size_t o = 0;
         for( auto& bin : ctx->ksw_bins )
@@ -372,6 +378,7 @@ static int ksw_run_once( ma_b200_ctx* ctx )
         A.cigscratch_stride = bin.cig_stride;
         A.next = (int*)( ctx->ksw_ctrl.p + 1 );
         A.error = (int*)( ctx->ksw_ctrl.p + 2 );
+        A.cells_total = nullptr;
         A.score = score;
         MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p + 1, 0, sizeof( unsigned long long ), ctx->stream ) );
         switch( bin.W )

@@ -146,6 +146,9 @@ struct NwPlanner
             t.toff = rev ? rbase + (long long)tr - 1 : rbase + (long long)fr;
             t.w = w, t.zdrop = zdrop, t.flag = flag;
             t.tag = MA_TASK_TPACK | ( rev ? ( MA_TASK_QREV | MA_TASK_TREV ) : 0 );
+            // extensions: the glue consumes max_q / max_t / CIGAR only (needlemanWunsch.cpp:262-267, 334-335, 575-579)
+            if( flag & MA_KSW_EXTZ_ONLY )
+                t.tag |= MA_TASK_EARLYSTOP;
             tasks[ n ] = t;
         }
         n++;

@@ -74,10 +74,21 @@ void backtrack( bool is_rev, const std::vector<uint8_t>& p, const std::vector<in
         std::reverse( cig.v.begin( ), cig.v.end( ) );
 }
 
+// Instrumentation for validating the product's early-termination bound: per row
+//   B_r = max over in-band cells of H + match * (qlen - 1 - i),  T_r = match * qlen - mingap(r + 1);
+// the product stops an EXTZ_ONLY problem after row r >= qlen when max(B_r, B_{r-1}, T_r) <= ez.max.
+// The checker records the first such row and whether ANY later row still raised ez.max (a violation).
+struct EarlyStopCheck
+{
+    int64_t stop_row = -1, rows = 0, violated = 0;
+};
+static thread_local EarlyStopCheck* g_pEsc = nullptr;
+
 template <typename TS, int SIZE>
 void core( int qlen, const uint8_t* query, int tlen, const uint8_t* target, const ma_oracle_score_t& sc, int w,
            int zdrop, int flag, ma_oracle_ksw_t* ez, Cigar& cig, int64_t* pCells )
 {
+    int64_t escPrevB = std::numeric_limits<int64_t>::max( );
     const TS NEG_INF = std::numeric_limits<TS>::min( );
     int8_t q = (int8_t)sc.gap, e = (int8_t)sc.extend, q2 = (int8_t)sc.gap2, e2 = (int8_t)sc.extend2;
     const int8_t sc_mch = (int8_t)sc.match, sc_mis = (int8_t)-sc.mismatch;
@@ -252,6 +263,10 @@ void core( int qlen, const uint8_t* query, int tlen, const uint8_t* target, cons
             max_H = H[ 0 ];
             max_t = 0;
         }
+        int64_t escB = std::numeric_limits<int64_t>::min( );
+        if( g_pEsc )
+            for( int64_t t = st0; t <= en0; t++ )
+                escB = std::max<int64_t>( escB, (int64_t)H[ t ] + (int64_t)sc.match * ( qlen - 1 - ( r - t ) ) );
         if( en0 == tlen - 1 && H[ en0 ] > ez->mte )
             ez->mte = H[ en0 ], ez->mte_q = (int)( r - en ); // sic: the 16-aligned en (:254-255, :774)
         if( r - st0 == qlen - 1 && H[ st0 ] > ez->mqe )
@@ -261,7 +276,11 @@ void core( int qlen, const uint8_t* query, int tlen, const uint8_t* target, cons
             const int32_t Hh = max_H;
             bool bStop = false;
             if( Hh > (int32_t)ez->max )
+            {
+                if( g_pEsc && g_pEsc->stop_row >= 0 )
+                    g_pEsc->violated = 1;
                 ez->max = Hh, ez->max_t = tt, ez->max_q = rr - tt;
+            }
             else if( tt >= ez->max_t && rr - tt >= ez->max_q )
             {
                 int tl = tt - ez->max_t, ql = ( rr - tt ) - ez->max_q, l;
@@ -277,6 +296,17 @@ void core( int qlen, const uint8_t* query, int tlen, const uint8_t* target, cons
         }
         if( r == qlen + tlen - 2 && en0 == tlen - 1 )
             ez->score = H[ tlen - 1 ];
+        if( g_pEsc )
+        {
+            g_pEsc->rows = r + 1;
+            const int64_t j = r + 1;
+            const int64_t mingap = std::min<int64_t>( (int64_t)q + (int64_t)e * j, (int64_t)q2 + (int64_t)e2 * j );
+            const int64_t T = (int64_t)sc.match * qlen - mingap;
+            if( g_pEsc->stop_row < 0 && r >= qlen && escPrevB != std::numeric_limits<int64_t>::max( ) &&
+                std::max( { escB, escPrevB, T } ) <= (int64_t)ez->max )
+                g_pEsc->stop_row = r;
+            escPrevB = escB;
+        }
         last_st = st, last_en = en;
     }
     if( pCells )
@@ -293,6 +323,12 @@ void core( int qlen, const uint8_t* query, int tlen, const uint8_t* target, cons
         backtrack( rev_cigar, p, off, off_end, n_col, ez->max_t, ez->max_q, cig );
 }
 } // namespace
+
+// returns rows processed by the reference; *stop_row = row after which the product may stop (-1: never),
+// *violated = 1 if a later row still raised ez.max (must never happen)
+extern "C" int ma_oracle_ksw_earlystop_check( int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                                              const ma_oracle_score_t* sc, int w, int zdrop, int flag,
+                                              int64_t* stop_row, int64_t* violated, int64_t* rows );
 
 extern "C" int ma_oracle_ksw( int qlen, const uint8_t* query, int tlen, const uint8_t* target,
                               const ma_oracle_score_t* sc, int w, int zdrop, int flag, ma_oracle_ksw_t* ez,
@@ -322,4 +358,19 @@ extern "C" int ma_oracle_ksw( int qlen, const uint8_t* query, int tlen, const ui
     if( !cig.v.empty( ) )
         memcpy( cigar, cig.v.data( ), cig.v.size( ) * 4 );
     return 0;
+}
+
+extern "C" int ma_oracle_ksw_earlystop_check( int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                                              const ma_oracle_score_t* sc, int w, int zdrop, int flag,
+                                              int64_t* stop_row, int64_t* violated, int64_t* rows )
+{
+    EarlyStopCheck esc;
+    g_pEsc = &esc;
+    ma_oracle_ksw_t ez;
+    std::vector<uint32_t> cig( (size_t)qlen + tlen + 8 );
+    int64_t cells;
+    int rc = ma_oracle_ksw( qlen, query, tlen, target, sc, w, zdrop, flag, &ez, cig.data( ), (int)cig.size( ), &cells );
+    g_pEsc = nullptr;
+    *stop_row = esc.stop_row, *violated = esc.violated, *rows = esc.rows;
+    return rc;
 }
