@@ -432,7 +432,7 @@ template <class Sink> struct Seeder
     {
         if( L <= 0 )
             return;
-        const int STK = 64;
+        const int STK = 24; // depth <= log2(L) + 2
         int stS[ STK ], stN[ STK ];
         int sp = 0;
         stS[ sp ] = 0, stN[ sp ] = L, sp++;
@@ -463,6 +463,330 @@ template <class Sink> struct Seeder
                     overflow = true;
             }
         }
+    }
+};
+
+
+// Same algorithm as Seeder, re-expressed as a resumable state machine with ONE extend_backward call site.
+// A warp holds 32 reads in different phases (forward sweep, backward sweep over an interval list, ...): with the
+// recursive formulation the lanes diverge and only a few of them have their two 64-byte occ-block loads in flight
+// at any time. Here every lane of the warp reaches the same call site each iteration, so all 64 loads of the warp
+// are issued together; only the cheap bookkeeping around it diverges.
+template <class Sink> struct SeederSM
+{
+    enum Phase
+    {
+        P_NEXT_CENTER,
+        P_SMEM_FWD,
+        P_SMEM_BWD,
+        P_MS1_FWD,
+        P_MS1_BWD,
+        P_MS2_BWD,
+        P_MS2_FWD,
+        P_DONE
+    };
+    const DevIndex& I;
+    const SeedParams& P;
+    const unsigned char* q;
+    int L;
+    SeedScratch S;
+    Sink& sink;
+    long long nExt = 0;
+    bool overflow = false;
+    // interval stack (depth <= log2(L) + 2) in caller-provided memory: keeps this struct array-free (registers)
+    int* stS;
+    int* stN;
+    int sp = 0;
+    // state of the centre being processed
+    int phase = P_NEXT_CENTER;
+    int aStart = 0, aSize = 0, center = 0, cs = 0, ce = 0, i = 0;
+    SAI ik;
+    int start = 0, end = 0, s1 = 0, e1 = 0;
+    SegRec *curr = nullptr, *next = nullptr;
+    int nCurr = 0, nNext = 0, j = 0;
+    bool bHaveOne = false;
+
+    MA_HD SeederSM( const DevIndex& I, const SeedParams& P, const unsigned char* q, int L, SeedScratch S, Sink& sink,
+                    int* pStack /* 2 x 40 ints */ )
+        : I( I ), P( P ), q( q ), L( L ), S( S ), sink( sink ), stS( pStack ), stN( pStack + 40 )
+    {
+        ik = SAI{ 0, 0, 0 };
+        begin( q, L );
+    }
+    // (re)starts the machine on a new read
+    MA_HD void begin( const unsigned char* q_, int L_ )
+    {
+        q = q_, L = L_;
+        nExt = 0, overflow = false, sp = 0;
+        phase = P_NEXT_CENTER;
+        if( L > 0 )
+            stS[ 0 ] = 0, stN[ 0 ] = L, sp = 1;
+        else
+            phase = P_DONE;
+    }
+    MA_HD static int comp( int c )
+    {
+        return c < 4 ? 3 - c : 5;
+    }
+    MA_HD bool stop( const SAI& ok, const SAI& ikk ) const
+    {
+        return ok.size <= 0 || ( ok.size <= P.min_amb && ikk.size <= P.max_amb );
+    }
+    MA_HD void emit( int st, int size, const SAI& sa )
+    {
+        sink.seg( SegRec{ st, size, sa } );
+    }
+    MA_HD void push_list( SegRec* list, int& n, const SegRec& r )
+    {
+        if( n < S.cap )
+            list[ n ] = r;
+        else
+            overflow = true;
+        n++;
+    }
+    // binarySeeding.cpp:58-83 after the extension of one centre
+    MA_HD void finish_center( )
+    {
+        const int aEnd = aStart + aSize;
+        if( aEnd > ce + 1 )
+        {
+            if( sp < 40 )
+                stS[ sp ] = ce, stN[ sp ] = aEnd - ce, sp++;
+            else
+                overflow = true;
+        }
+        if( cs != 0 && aStart + 1 < cs )
+        {
+            if( sp < 40 )
+                stS[ sp ] = aStart, stN[ sp ] = cs - aStart, sp++;
+            else
+                overflow = true;
+        }
+        phase = P_NEXT_CENTER;
+    }
+    MA_HD void smem_fwd_done( )
+    {
+        if( nCurr > S.cap )
+            nCurr = S.cap;
+        for( int a = 0, b = nCurr - 1; a < b; a++, b-- )
+            stl::swp( curr[ a ], curr[ b ] );
+        if( center != 0 )
+        {
+            i = center - 1, j = 0, bHaveOne = false, nNext = 0;
+            phase = P_SMEM_BWD;
+        }
+        else
+            smem_final( );
+    }
+    MA_HD void smem_final( )
+    {
+        if( nCurr != 0 )
+            emit( curr[ 0 ].start, curr[ 0 ].size, curr[ 0 ].sa );
+        finish_center( );
+    }
+    MA_HD void ms_emit_first( )
+    {
+        emit( start, end - start, ik );
+        s1 = start, e1 = end;
+        ik = init_interval( I, q[ center ] );
+        start = center;
+        i = center - 1;
+        phase = P_MS2_BWD;
+    }
+    MA_HD void ms_finish( )
+    {
+        if( s1 == start && e1 == end )
+            cs = s1, ce = e1;
+        else
+        {
+            emit( start, end - start, sai_rc( ik ) );
+            cs = s1 < start ? s1 : start;
+            ce = e1 > end ? e1 : end;
+        }
+        finish_center( );
+    }
+    // Advances the bookkeeping until the next extension is needed. Returns false when the read is finished.
+    MA_HD bool request( SAI& rIk, int& rC )
+    {
+        while( true )
+        {
+            switch( phase )
+            {
+                case P_NEXT_CENTER:
+                {
+                    if( sp == 0 )
+                    {
+                        phase = P_DONE;
+                        return false;
+                    }
+                    --sp;
+                    aStart = stS[ sp ], aSize = stN[ sp ];
+                    center = aStart + aSize / 2;
+                    if( q[ center ] >= 4 )
+                    {
+                        cs = center, ce = center + 1;
+                        finish_center( );
+                        break;
+                    }
+                    ik = init_interval( I, comp( q[ center ] ) );
+                    if( P.technique == 0 )
+                    {
+                        if( ik.size == 0 )
+                        {
+                            cs = center, ce = center + 1;
+                            finish_center( );
+                            break;
+                        }
+                        end = center, i = center + 1;
+                        phase = P_MS1_FWD;
+                    }
+                    else
+                    {
+                        cs = center, ce = center;
+                        curr = S.listA, next = S.listB, nCurr = 0, nNext = 0;
+                        i = center + 1;
+                        phase = P_SMEM_FWD;
+                    }
+                    break;
+                }
+                case P_SMEM_FWD:
+                    if( i < L )
+                    {
+                        rIk = ik, rC = comp( q[ i ] );
+                        return true;
+                    }
+                    smem_fwd_done( );
+                    break;
+                case P_SMEM_BWD:
+                    if( j < nCurr )
+                    {
+                        rIk = curr[ j ].sa, rC = q[ i ];
+                        return true;
+                    }
+                    {
+                        SegRec* t = curr;
+                        curr = next, next = t;
+                        nCurr = nNext;
+                        if( nCurr == 0 )
+                        {
+                            finish_center( ); // nothing left to emit
+                            break;
+                        }
+                        cs = i;
+                        if( i == 0 )
+                        {
+                            smem_final( );
+                            break;
+                        }
+                        i--, j = 0, bHaveOne = false, nNext = 0;
+                    }
+                    break;
+                case P_MS1_FWD:
+                    if( i < L )
+                    {
+                        rIk = ik, rC = comp( q[ i ] );
+                        return true;
+                    }
+                    ik = sai_rc( ik ), start = center, i = center - 1, phase = P_MS1_BWD;
+                    break;
+                case P_MS1_BWD:
+                    if( i >= 0 )
+                    {
+                        rIk = ik, rC = q[ i ];
+                        return true;
+                    }
+                    ms_emit_first( );
+                    break;
+                case P_MS2_BWD:
+                    if( i >= 0 )
+                    {
+                        rIk = ik, rC = q[ i ];
+                        return true;
+                    }
+                    ik = sai_rc( ik ), end = center, i = center + 1, phase = P_MS2_FWD;
+                    break;
+                case P_MS2_FWD:
+                    if( i < L )
+                    {
+                        rIk = ik, rC = comp( q[ i ] );
+                        return true;
+                    }
+                    ms_finish( );
+                    break;
+                default:
+                    return false;
+            }
+        }
+    }
+    // Feeds the result of the requested extension back into the state machine.
+    MA_HD void consume( const SAI& ok )
+    {
+        nExt++;
+        switch( phase )
+        {
+            case P_SMEM_FWD:
+            {
+                if( ok.size != ik.size )
+                    push_list( curr, nCurr, SegRec{ center, i - center - 1, sai_rc( ik ) } );
+                if( i == L - 1 && ok.size != 0 )
+                    push_list( curr, nCurr, SegRec{ center, i - center, sai_rc( ok ) } );
+                if( ok.size == 0 || ( ok.size <= P.min_amb && ik.size <= P.max_amb ) )
+                {
+                    smem_fwd_done( );
+                    break;
+                }
+                ik = ok;
+                ce = i;
+                i++;
+                break;
+            }
+            case P_SMEM_BWD:
+            {
+                const SegRec s = curr[ j ];
+                if( ok.size <= P.min_amb && !bHaveOne )
+                {
+                    emit( s.start, s.size, s.sa );
+                    bHaveOne = true;
+                }
+                else if( ok.size > P.min_amb || ( ok.size > 0 && s.size >= P.max_amb ) )
+                    push_list( next, nNext, SegRec{ i, s.size + 1, ok } );
+                j++;
+                break;
+            }
+            case P_MS1_FWD:
+                if( stop( ok, ik ) )
+                    ik = sai_rc( ik ), start = center, i = center - 1, phase = P_MS1_BWD;
+                else
+                    end = i, ik = ok, i++;
+                break;
+            case P_MS1_BWD:
+                if( stop( ok, ik ) )
+                    ms_emit_first( );
+                else
+                    start = i, ik = ok, i--;
+                break;
+            case P_MS2_BWD:
+                if( stop( ok, ik ) )
+                    ik = sai_rc( ik ), end = center, i = center + 1, phase = P_MS2_FWD;
+                else
+                    start = i, ik = ok, i--;
+                break;
+            case P_MS2_FWD:
+                if( stop( ok, ik ) )
+                    ms_finish( );
+                else
+                    end = i, ik = ok, i++;
+                break;
+            default:
+                break;
+        }
+    }
+    MA_HD void run( )
+    {
+        SAI rIk;
+        int rC;
+        while( request( rIk, rC ) )
+            consume( extend_backward( I, rIk, rC ) );
     }
 };
 

@@ -745,9 +745,9 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
         const int maxL = ctx->max_read_len;
         const int list_cap = std::min( maxL + 2, 1024 ), fseg_cap = std::min( 2 * maxL + 8, 1 << 16 );
         int grid = full_grid( ctx, seed_kernel, 128, n );
-        const size_t perThread = (size_t)2 * list_cap * sizeof( SegRec ) + (size_t)fseg_cap * sizeof( FSeg );
+        const size_t perThread = (size_t)( 2 * list_cap + 8 ) * sizeof( SegRec ) + (size_t)fseg_cap * sizeof( FSeg );
         grid = (int)std::max<size_t>( 1, std::min<size_t>( grid, ( (size_t)8 << 30 ) / ( perThread * 128 ) ) );
-        ctx->lists.reserve( (size_t)grid * 128 * 2 * list_cap );
+        ctx->lists.reserve( (size_t)grid * 128 * ( 2 * list_cap + 8 ) );
         ctx->fsegs.reserve( (size_t)grid * 128 * fseg_cap );
         ctx->dbg_cap = keep_segments > 0 ? keep_segments : 0;
         if( ctx->dbg_cap )
@@ -768,7 +768,12 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
             A.dbg_segs = ctx->dbg_cap ? ctx->dbg_segs.p : nullptr;
             A.dbg_nsegs = ctx->dbg_cap ? ctx->dbg_nsegs.p : nullptr, A.dbg_cap = ctx->dbg_cap;
             A.ctrl = ctx->ctrl.p;
-            seed_kernel<<<grid, 128, 0, s>>>( A );
+            // default: the convergent state-machine kernel; MA_B200_SEED_SM=0 selects the recursive formulation (A/B)
+            static const bool bSM = !( getenv( "MA_B200_SEED_SM" ) && atoi( getenv( "MA_B200_SEED_SM" ) ) == 0 );
+            if( bSM )
+                seed_kernel<<<grid, 128, 0, s>>>( A );
+            else
+                seed_kernel_rec<<<grid, 128, 0, s>>>( A );
             MA_CUDA( cudaGetLastError( ) );
             ctx->launches++;
             read_ctrl( ctx );

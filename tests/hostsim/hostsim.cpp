@@ -120,6 +120,26 @@ int main( int argc, char** argv )
                  sink.v[ i ].sa.size == oseg[ i ].sa.size;
         if( S.nExt != nExt && oseg.size( ) )
             ok = false;
+        { // the state-machine formulation used by seed_kernel must emit exactly the same segments
+            AllSegSink sink2;
+            int stk[ 80 ];
+            SeederSM<AllSegSink> S2( I, SP, q.data( ), (int)q.size( ), SeedScratch{ la.data( ), lb.data( ), 600 }, sink2,
+                                     stk );
+            S2.run( );
+            size_t sum2 = 0;
+            for( auto& s : sink2.v )
+                sum2 += (size_t)s.size / (size_t)SP.drop_min_size;
+            if( !SP.disable_heuristics && SP.drop_min_size != 0 && (double)sum2 < SP.drop_factor * (double)q.size( ) &&
+                (unsigned long long)SP.genome_size_disable < (unsigned long long)I.ref_len )
+                sink2.v.clear( );
+            bool ok2 = sink2.v.size( ) == sink.v.size( ) && !S2.overflow && ( S2.nExt == S.nExt );
+            for( size_t i = 0; ok2 && i < sink.v.size( ); i++ )
+                ok2 = sink2.v[ i ].start == sink.v[ i ].start && sink2.v[ i ].size == sink.v[ i ].size &&
+                      sink2.v[ i ].sa.start == sink.v[ i ].sa.start && sink2.v[ i ].sa.rev == sink.v[ i ].sa.rev &&
+                      sink2.v[ i ].sa.size == sink.v[ i ].sa.size;
+            if( !ok2 )
+                ok = false;
+        }
         // locate
         auto oseeds = oracle::extract_seeds( OI, OP, oseg, (int64_t)q.size( ), nullptr );
         size_t k = 0;
