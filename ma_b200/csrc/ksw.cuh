@@ -159,72 +159,60 @@ struct SeqAccess
 // One warp, one problem. All lanes return the same KswOut (cigar_off/n_cigar are filled by the caller).
 // tb: per-warp traceback slab of >= (qlen+tlen-1)*ncol16 bytes.
 // Per anti-diagonal ONE fused pass over the aligned column range does: score profile, the difference recurrence with
-// its traceback byte, the H-row update and the candidates of the reference's lane-blocked arg-max.
-template <int W>
-__device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int tlen, int w, int zdrop, int flag,
-                          bool bEarlyStop, KswSmem<W>& sm, unsigned char* __restrict__ tb, KswOut& ez )
+// its traceback byte, the H-row update, the candidates of the reference's lane-blocked arg-max and the early-stop
+// bound. The row loop is instantiated for left/right gap alignment and for a staged/unstaged query, runs on 32-bit
+// row arithmetic and keeps all lanes on one instruction stream (out-of-range lanes compute on in-bounds shared
+// memory and only their stores are predicated off).
+//
+// Early termination (extensions whose caller consumes only max / max_q / max_t / CIGAR): the recurrence clips z at
+// the match score (kswcpp_core.h:702), so every in-band value obeys H_r[t] <= H_{r-2}[t-1] + match and no later
+// cell can exceed  B = max over the last two rows of H + match * (query rows still below the cell),  nor
+//   T = match * qlen - cheapest gap over r+1 target bases  for diagonals entering through query row 0.
+// Once max(B_r, B_{r-1}, T_r) <= ez.max the maximum and its position are final; the reference would only go on to
+// set zdropped / mqe / mte / score, which such callers never read. Validated against the reference restatement on
+// adversarial problems (oracle/ksw_oracle.cpp: ma_oracle_ksw_earlystop_check, tests/test_earlystop_bound.py).
+template <int W, bool LEFT, bool QS>
+__device__ __forceinline__ void ksw_rows( const KswScore& P, const SeqAccess& seq, const int qlen, const int tlen,
+                                          const int w, const int zdrop, const bool bEarlyStop, KswSmem<W>& sm,
+                                          unsigned char* __restrict__ tb, KswOut& ez )
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int M = W - 1;
     const int NONE_T = 0x7fffffff, NONE_H = (int)0x80000000;
-    ez.max_q = ez.max_t = ez.mqe_t = ez.mte_q = -1;
-    ez.max = 0;
-    ez.score = ez.mqe = ez.mte = (int)0x80000000;
-    ez.n_cigar = 0, ez.zdropped = 0, ez.reach_end = 0, ez.status = 0, ez.cells = 0;
-    if( qlen <= 0 || tlen <= 0 || P.early_return )
-        return;
-    if( w < 0 )
-        w = tlen > qlen ? tlen : qlen;
     const int q = P.q, e = P.e, q2 = P.q2, e2 = P.e2, qe = q + e, qe2 = q2 + e2;
     const int T16 = ( ( tlen + 15 ) / 16 ) * 16;
     const int ncol16 = ksw_ncol16( qlen, tlen, w );
-    const bool bLeft = !( flag & MA_KSW_RIGHT );
-    // kswcpp_sse_xx.cpp:38: int16 scores iff no risk of overflow
-    const long long iSize = qlen > tlen ? qlen : tlen;
-    const bool is16 = !( iSize * P.min16 < -32768 || iSize * P.match > 32767 );
-    const int SIZE = is16 ? 8 : 4;
+    const int iSize = qlen > tlen ? qlen : tlen;
+    const bool is16 = !( (long long)iSize * P.min16 < -32768 || (long long)iSize * P.match > 32767 );
+    const int SMASK = is16 ? ~7 : ~3; // SSE lanes of the reference's H vectors: 8 x int16 or 4 x int32
     const int NEG_INF = is16 ? -32768 : (int)0x80000000;
     const int init6 = w8( -q - e ), init25 = w8( -q2 - e2 );
     const int scN = -e2, scM = P.match, scX = P.mismatch;
-    // stage the query in shared memory when it fits
-    const bool qStaged = qlen <= KswSmem<W>::QC;
-    if( qStaged )
-    {
-        for( int i = lane; i < qlen; i += 32 )
-            sm.qc[ i ] = (unsigned char)seq.Q( i );
-        __syncwarp( );
-    }
-
+    const int nrows = qlen + tlen - 1;
     int inited_end = 0; // columns [0, inited_end) of the circular window carry reference-visible state
     int last_st = -1, last_en = -1;
     long long cells = 0;
-    const long long nrows = (long long)qlen + tlen - 1;
-    // Early termination (extensions whose caller consumes only max / max_q / max_t / CIGAR). Because the recurrence
-    // clips z at the match score (kswcpp_core.h:702), every in-band value obeys H_r[t] <= H_{r-2}[t-1] + match, so no
-    // later cell can exceed  B = max over the last two rows of H + match * (query rows still below the cell),  nor
-    //   T = match * qlen - cheapest gap over r+1 target bases  for diagonals that enter through query row 0.
-    // Once max(B_r, B_{r-1}, T_r) <= ez.max the maximum and its position are final; the reference would only go on
-    // to set zdropped / mqe / mte / score, which such callers never read. Validated against the reference
-    // restatement on 120 k adversarial problems (oracle/ksw_oracle.cpp: ma_oracle_ksw_earlystop_check).
-    long long prevB = 0x7fffffffffffll;
-    for( long long r = 0; r < nrows; ++r )
+    int prevB = NONE_T;
+    long long rowOff = 0; // r * ncol16
+    for( int r = 0; r < nrows; ++r, rowOff += ncol16 )
     {
-        int st0, en0;
-        if( !ksw_band( r, qlen, tlen, w, st0, en0 ) )
+        // band limits (kswcpp_core.h:541-553)
+        int st0 = 0, en0 = tlen - 1;
+        st0 = max( st0, r - qlen + 1 );
+        en0 = min( en0, r );
+        st0 = max( st0, ( r - w + 1 ) >> 1 );
+        en0 = min( en0, ( r + w ) >> 1 );
+        if( st0 > en0 )
         {
             ez.zdropped = 1;
             break;
         }
         cells += en0 - st0 + 1;
         const int st = st0 & ~15, en = en0 | 15;
-        int sEnd = st0 + ( ( ( en0 - st0 ) >> 4 ) + 1 ) * 16; // exclusive end of the score-profile writes
-        if( sEnd > T16 )
-            sEnd = T16; // the reference spills into its target copy beyond T16; those bytes are never read again
+        const int sEnd = min( st0 + ( ( ( en0 - st0 ) >> 4 ) + 1 ) * 16, T16 ); // end of the score-profile writes
         {
-            int need = en + 1 > ( ( sEnd + 15 ) & ~15 ) ? en + 1 : ( ( sEnd + 15 ) & ~15 );
-            if( need > T16 )
-                need = T16;
+            const int need = min( max( en + 1, ( sEnd + 15 ) & ~15 ), T16 );
             if( inited_end < need )
             {
                 for( int idx = inited_end + lane; idx < need; idx += 32 )
@@ -242,213 +230,188 @@ __device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int
         }
         const int first_col =
             w8( r == 0 ? -q - e : r < P.long_thres ? -e : r == P.long_thres ? P.long_diff : -e2 );
-        int cx, cx2, cv; // values entering column st from column st-1 (kswcpp_core.h:562-579)
+        int cx = init6, cx2 = init25, cv = init6; // values entering column st from column st-1 (:562-579)
         if( st > 0 )
         {
             if( st - 1 >= last_st && st - 1 <= last_en )
                 cx = sm.x[ ( st - 1 ) & M ], cx2 = sm.x2[ ( st - 1 ) & M ], cv = sm.v[ ( st - 1 ) & M ];
-            else
-                cx = init6, cx2 = init25, cv = init6;
         }
         else
-            cx = init6, cx2 = init25, cv = first_col;
+            cv = first_col;
         if( en >= r && lane == 0 )
         {
             sm.y[ r & M ] = (signed char)init6;
             sm.y2[ r & M ] = (signed char)init25;
             sm.u[ r & M ] = (signed char)first_col;
         }
-        // old H of the column left of en0: read before the pass updates it (kswcpp_core.h:194-195)
-        const int hprev = en0 > 0 ? sm.H[ ( en0 - 1 ) & M ] : sm.H[ en0 & M ];
+        // old H left of en0, read before the pass updates it (:194-195); row 0: H[0] = v[0] - (q + e) (:247)
+        const int hprev = r == 0 ? -qe : ( en0 > 0 ? sm.H[ ( en0 - 1 ) & M ] : sm.H[ en0 & M ] );
         __syncwarp( );
-        const int en1 = st0 + ( ( en0 - st0 ) / SIZE ) * SIZE;
-        const int qiBase = (int)( r < 0x7fffffff ? r : 0x7fffffff ); // r - t is evaluated in int below
+        const int en1 = st0 + ( ( en0 - st0 ) & SMASK );
         int bh = NONE_H, bt = NONE_T; // this lane's SSE-lane candidate: first block reaching the lane maximum
         int th = NONE_H, tt_ = NONE_T; // candidate among the scalar tail [en1, en0)
-        int hb = NONE_H; // early-stop bound of this lane: H + match * (qlen - 1 - i)
-        const int hbBase = scM * ( qlen - 1 - qiBase ); // + match * t
+        int hb = NONE_H; // early-stop bound of this lane
+        const int hbBase = scM * ( qlen - 1 - r );
         int Hen0l = 0, Hst0l = 0;
-        unsigned char* rowp = tb + r * ncol16 - st;
+        unsigned char* rowp = tb + rowOff - st;
+        const unsigned nS = (unsigned)( sEnd - st0 ), nB = (unsigned)( en0 - st0 ), nV = (unsigned)( en1 - st0 );
         for( int base = st; base <= en; base += 32 )
         {
             const int t = base + lane;
             const bool act = t <= en;
             const int k = t & M;
-            int xo = 0, vo = 0, x2o = 0, ut = 0, yo = 0, y2o = 0, z = 0, hOld = 0;
-            if( act )
-            {
-                xo = sm.x[ k ], vo = sm.v[ k ], x2o = sm.x2[ k ], ut = sm.u[ k ], yo = sm.y[ k ], y2o = sm.y2[ k ];
-                hOld = sm.H[ k ];
-                if( t >= st0 && t < sEnd )
-                { // score profile (kswcpp_core.h:591-616); N scores -e2; beyond the sequences the zero padding = 'A'
-                    const int a = sm.tc[ k ];
-                    const int qi = qiBase - t;
-                    int b = 0;
-                    if( qi >= 0 && qi < qlen )
-                        b = qStaged ? (int)sm.qc[ qi ] : seq.Q( qi );
-                    z = ( a == 4 || b == 4 ) ? scN : ( a == b ? scM : scX );
+            const int xo = sm.x[ k ], vo = sm.v[ k ], x2o = sm.x2[ k ], ut = sm.u[ k ], yo = sm.y[ k ], y2o = sm.y2[ k ];
+            const int hOld = sm.H[ k ];
+            int z = sm.s[ k ]; // out-of-band cell of the aligned range: stale profile, as in the reference
+            const unsigned dt = (unsigned)( t - st0 );
+            if( dt < nS )
+            { // score profile (:591-616); N scores -e2; beyond the sequences the zero padding compares as 'A'
+                const int a = sm.tc[ k ];
+                const int qi = r - t;
+                int b = 0;
+                if( (unsigned)qi < (unsigned)qlen )
+                    b = QS ? (int)sm.qc[ qi ] : seq.Q( qi );
+                z = ( a == 4 || b == 4 ) ? scN : ( a == b ? scM : scX );
+                if( act )
                     sm.s[ k ] = (signed char)z;
-                }
-                else
-                    z = sm.s[ k ]; // out-of-band cell of the aligned range: stale profile, as in the reference
             }
             int xt1 = __shfl_up_sync( FULL, xo, 1 ), vt1 = __shfl_up_sync( FULL, vo, 1 ),
                 x2t1 = __shfl_up_sync( FULL, x2o, 1 );
             if( lane == 0 )
                 xt1 = cx, vt1 = cv, x2t1 = cx2;
-            cx = __shfl_sync( FULL, xo, 31 ), cv = __shfl_sync( FULL, vo, 31 ), cx2 = __shfl_sync( FULL, x2o, 31 );
+            if( base + 32 <= en )
+                cx = __shfl_sync( FULL, xo, 31 ), cv = __shfl_sync( FULL, vo, 31 ), cx2 = __shfl_sync( FULL, x2o, 31 );
+            int a = w8( xt1 + vt1 ), b = w8( yo + ut ), a2 = w8( x2t1 + vt1 ), b2 = w8( y2o + ut );
+            int d;
+            if( LEFT )
+            {
+                d = a > z ? 1 : 0;
+                z = max( z, a );
+                d = b > z ? 2 : d;
+                z = max( z, b );
+                d = a2 > z ? 3 : d;
+                z = max( z, a2 );
+                d = b2 > z ? 4 : d;
+                z = max( z, b2 );
+            }
+            else
+            { // right-aligned: ties go to the gap, state 4 is never recorded (:693-699)
+                d = z > a ? 0 : 1;
+                z = max( z, a );
+                d = z > b ? d : 2;
+                z = max( z, b );
+                d = z > a2 ? d : 3;
+                z = max( z, a2 );
+                z = max( z, b2 );
+            }
+            z = min( z, scM );
+            const int un = w8( z - vt1 ), vn = w8( z - ut );
+            int tmp = w8( z - q );
+            a = w8( a - tmp ), b = w8( b - tmp );
+            tmp = w8( z - q2 );
+            a2 = w8( a2 - tmp ), b2 = w8( b2 - tmp );
+            if( LEFT )
+            {
+                d |= a > 0 ? 0x08 : 0;
+                d |= b > 0 ? 0x10 : 0;
+                d |= a2 > 0 ? 0x20 : 0;
+                d |= b2 > 0 ? 0x40 : 0;
+            }
+            else
+            {
+                d |= a >= 0 ? 0x08 : 0;
+                d |= b >= 0 ? 0x10 : 0;
+                d |= a2 >= 0 ? 0x20 : 0;
+                d |= b2 >= 0 ? 0x40 : 0;
+            }
+            // H row (calcMaxScore, :178-250): interior columns add v, the last column adds u to its left neighbour
+            const bool inB = dt < nB, isEn = t == en0;
+            int h = (int)( (unsigned)( isEn ? hprev : hOld ) + (unsigned)( ( isEn && en0 > 0 ) ? un : vn ) );
+            if( is16 )
+                h = (short)h;
             if( act )
             {
-                int a = w8( xt1 + vt1 ), b = w8( yo + ut ), a2 = w8( x2t1 + vt1 ), b2 = w8( y2o + ut );
-                int d;
-                if( bLeft )
-                {
-                    d = a > z ? 1 : 0;
-                    z = max( z, a );
-                    d = b > z ? 2 : d;
-                    z = max( z, b );
-                    d = a2 > z ? 3 : d;
-                    z = max( z, a2 );
-                    d = b2 > z ? 4 : d;
-                    z = max( z, b2 );
-                }
-                else
-                { // right-aligned: ties go to the gap, state 4 is never recorded (kswcpp_core.h:693-699)
-                    d = z > a ? 0 : 1;
-                    z = max( z, a );
-                    d = z > b ? d : 2;
-                    z = max( z, b );
-                    d = z > a2 ? d : 3;
-                    z = max( z, a2 );
-                    z = max( z, b2 );
-                }
-                z = min( z, scM );
-                const int un = w8( z - vt1 ), vn = w8( z - ut );
                 sm.u[ k ] = (signed char)un;
                 sm.v[ k ] = (signed char)vn;
-                int tmp = w8( z - q );
-                a = w8( a - tmp ), b = w8( b - tmp );
-                tmp = w8( z - q2 );
-                a2 = w8( a2 - tmp ), b2 = w8( b2 - tmp );
-                if( bLeft )
-                {
-                    d |= a > 0 ? 0x08 : 0;
-                    d |= b > 0 ? 0x10 : 0;
-                    d |= a2 > 0 ? 0x20 : 0;
-                    d |= b2 > 0 ? 0x40 : 0;
-                }
-                else
-                {
-                    d |= a >= 0 ? 0x08 : 0;
-                    d |= b >= 0 ? 0x10 : 0;
-                    d |= a2 >= 0 ? 0x20 : 0;
-                    d |= b2 >= 0 ? 0x40 : 0;
-                }
                 sm.x[ k ] = (signed char)( max( a, 0 ) - qe );
                 sm.y[ k ] = (signed char)( max( b, 0 ) - qe );
                 sm.x2[ k ] = (signed char)( max( a2, 0 ) - qe2 );
                 sm.y2[ k ] = (signed char)( max( b2, 0 ) - qe2 );
                 rowp[ t ] = (unsigned char)d;
-                // ---- H row (calcMaxScore, kswcpp_core.h:178-250), fused
-                if( r > 0 )
+            }
+            if( inB || isEn )
+            {
+                sm.H[ k ] = h;
+                hb = max( hb, h + hbBase + scM * t );
+                if( isEn )
+                    Hen0l = h;
+                if( t == st0 )
+                    Hst0l = h;
+                if( inB )
                 {
-                    if( t >= st0 && t < en0 )
-                    {
-                        int h = (int)( (unsigned)hOld + (unsigned)vn );
-                        if( is16 )
-                            h = (short)h;
-                        sm.H[ k ] = h;
-                        hb = max( hb, h + hbBase + scM * t );
-                        if( t == st0 )
-                            Hst0l = h;
-                        if( t < en1 )
-                        { // strict '>' keeps the first block of this SSE lane that reaches its maximum
-                            if( bt == NONE_T || h > bh )
-                                bh = h, bt = st0 + ( ( t - st0 ) / SIZE ) * SIZE;
-                        }
-                        else if( tt_ == NONE_T || h > th )
-                            th = h, tt_ = t;
+                    if( dt < nV )
+                    { // strict '>' keeps the first block of this SSE lane that reaches its maximum
+                        if( bt == NONE_T || h > bh )
+                            bh = h, bt = st0 + ( (int)dt & SMASK );
                     }
-                    else if( t == en0 )
-                    {
-                        int h = (int)( (unsigned)hprev + (unsigned)( en0 > 0 ? un : vn ) );
-                        if( is16 )
-                            h = (short)h;
-                        sm.H[ k ] = h;
-                        hb = max( hb, h + hbBase + scM * t );
-                        Hen0l = h;
-                        if( t == st0 )
-                            Hst0l = h;
-                    }
-                }
-                else if( t == 0 )
-                {
-                    int h = vn - qe;
-                    if( is16 )
-                        h = (short)h;
-                    sm.H[ 0 ] = h;
-                    Hen0l = h, Hst0l = h;
+                    else if( tt_ == NONE_T || h > th )
+                        th = h, tt_ = t;
                 }
             }
         }
         // score-profile entries the reference writes beyond the aligned range (read, stale, by later rows)
-        for( int t = en + 1 + lane; t < sEnd; t += 32 )
-        {
-            const int k = t & M;
-            const int a = sm.tc[ k ];
-            const int qi = qiBase - t;
-            int b = 0;
-            if( qi >= 0 && qi < qlen )
-                b = qStaged ? (int)sm.qc[ qi ] : seq.Q( qi );
-            sm.s[ k ] = (signed char)( ( a == 4 || b == 4 ) ? scN : ( a == b ? scM : scX ) );
-        }
-        const int Hen0 = __shfl_sync( FULL, Hen0l, ( en0 - st ) & 31 );
-        const int Hst0 = __shfl_sync( FULL, Hst0l, ( st0 - st ) & 31 );
-        int max_H, max_t;
-        if( r > 0 )
-        {
-            // lanes with equal (lane % SIZE) form one SSE lane of the reference
-            for( int o = 16; o >= SIZE; o >>= 1 )
+        if( sEnd > en + 1 )
+            for( int t = en + 1 + lane; t < sEnd; t += 32 )
             {
-                const int oh = __shfl_xor_sync( FULL, bh, o ), ot = __shfl_xor_sync( FULL, bt, o );
-                if( ot != NONE_T && ( bt == NONE_T || oh > bh || ( oh == bh && ot < bt ) ) )
-                    bh = oh, bt = ot;
+                const int k = t & M;
+                const int a = sm.tc[ k ];
+                const int qi = r - t;
+                int b = 0;
+                if( (unsigned)qi < (unsigned)qlen )
+                    b = QS ? (int)sm.qc[ qi ] : seq.Q( qi );
+                sm.s[ k ] = (signed char)( ( a == 4 || b == 4 ) ? scN : ( a == b ? scM : scX ) );
             }
-            if( bt == NONE_T || !( bh > Hen0 ) )
-                bh = Hen0, bt = en0;
-            max_H = __reduce_max_sync( FULL, bh );
-            max_t = __reduce_max_sync( FULL, bt );
-            // scalar tail [en1, en0): the first index of the tail maximum, if it beats the vector result
+        const int Hen0 = __shfl_sync( FULL, Hen0l, ( en0 - st ) & 31 );
+        // lanes with equal (lane % SIZE) form one SSE lane of the reference
+        for( int o = 16; o >= -SMASK; o >>= 1 )
+        {
+            const int oh = __shfl_xor_sync( FULL, bh, o ), ot = __shfl_xor_sync( FULL, bt, o );
+            if( ot != NONE_T && ( bt == NONE_T || oh > bh || ( oh == bh && ot < bt ) ) )
+                bh = oh, bt = ot;
+        }
+        if( bt == NONE_T || !( bh > Hen0 ) )
+            bh = Hen0, bt = en0;
+        int max_H = __reduce_max_sync( FULL, bh );
+        int max_t = __reduce_max_sync( FULL, bt );
+        if( en1 < en0 )
+        { // scalar tail [en1, en0): the first index of the tail maximum, if it beats the vector result
             const int tm = __reduce_max_sync( FULL, tt_ == NONE_T ? NONE_H : th );
-            if( __any_sync( FULL, tt_ != NONE_T ) && tm > max_H )
+            if( tm > max_H )
             {
                 max_H = tm;
                 max_t = __reduce_min_sync( FULL, ( tt_ != NONE_T && th == tm ) ? tt_ : NONE_T );
             }
         }
-        else
-        {
-            max_H = Hen0;
-            max_t = 0;
-        }
         __syncwarp( );
         if( en0 == tlen - 1 && Hen0 > ez.mte )
-            ez.mte = Hen0, ez.mte_q = (int)( r - en ); // sic: the aligned en
-        if( r - st0 == qlen - 1 && Hst0 > ez.mqe )
-            ez.mqe = Hst0, ez.mqe_t = st0;
-        { // ksw_apply_zdrop (kswcpp_core.h:22-44)
-            const int rr = (int)r;
-            if( max_H > ez.max )
-                ez.max = max_H, ez.max_t = max_t, ez.max_q = rr - max_t;
-            else if( max_t >= ez.max_t && rr - max_t >= ez.max_q )
+            ez.mte = Hen0, ez.mte_q = r - en; // sic: the aligned en
+        if( r - st0 == qlen - 1 )
+        {
+            const int Hst0 = __shfl_sync( FULL, Hst0l, ( st0 - st ) & 31 );
+            if( Hst0 > ez.mqe )
+                ez.mqe = Hst0, ez.mqe_t = st0;
+        }
+        // ksw_apply_zdrop (:22-44)
+        if( max_H > ez.max )
+            ez.max = max_H, ez.max_t = max_t, ez.max_q = r - max_t;
+        else if( max_t >= ez.max_t && r - max_t >= ez.max_q )
+        {
+            const int tl = max_t - ez.max_t, ql = ( r - max_t ) - ez.max_q;
+            const int l = tl > ql ? tl - ql : ql - tl;
+            if( zdrop >= 0 && ez.max - max_H > zdrop + l * e2 )
             {
-                const int tl = max_t - ez.max_t, ql = ( rr - max_t ) - ez.max_q;
-                const int l = tl > ql ? tl - ql : ql - tl;
-                if( zdrop >= 0 && ez.max - max_H > zdrop + l * e2 )
-                {
-                    ez.zdropped = 1;
-                    break;
-                }
+                ez.zdropped = 1;
+                break;
             }
         }
         if( r == nrows - 1 && en0 == tlen - 1 )
@@ -456,13 +419,13 @@ __device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int
         last_st = st, last_en = en;
         if( bEarlyStop )
         {
-            const long long B = r > 0 ? (long long)__reduce_max_sync( FULL, hb ) : 0x7fffffffffffll;
-            if( r >= qlen && prevB != 0x7fffffffffffll )
+            const int B = __reduce_max_sync( FULL, hb );
+            if( r >= qlen && prevB != NONE_T )
             {
                 const long long j = r + 1;
                 const long long g1 = q + (long long)e * j, g2 = q2 + (long long)e2 * j;
                 const long long T = (long long)scM * qlen - ( g1 < g2 ? g1 : g2 );
-                const long long bound = B > prevB ? ( B > T ? B : T ) : ( prevB > T ? prevB : T );
+                const long long bound = max( (long long)max( B, prevB ), T );
                 if( bound <= (long long)ez.max )
                     break;
             }
@@ -471,6 +434,44 @@ __device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int
     }
     ez.cells = cells;
     __syncwarp( );
+}
+
+template <int W>
+__device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int tlen, int w, int zdrop, int flag,
+                          bool bEarlyStop, KswSmem<W>& sm, unsigned char* __restrict__ tb, KswOut& ez )
+{
+    const int lane = threadIdx.x & 31;
+    ez.max_q = ez.max_t = ez.mqe_t = ez.mte_q = -1;
+    ez.max = 0;
+    ez.score = ez.mqe = ez.mte = (int)0x80000000;
+    ez.n_cigar = 0, ez.zdropped = 0, ez.reach_end = 0, ez.status = 0, ez.cells = 0;
+    if( qlen <= 0 || tlen <= 0 || P.early_return )
+        return;
+    if( w < 0 )
+        w = tlen > qlen ? tlen : qlen;
+    // stage the query in shared memory when it fits
+    const bool qStaged = qlen <= KswSmem<W>::QC;
+    if( qStaged )
+    {
+        for( int i = lane; i < qlen; i += 32 )
+            sm.qc[ i ] = (unsigned char)seq.Q( i );
+        __syncwarp( );
+    }
+    const bool bLeft = !( flag & MA_KSW_RIGHT );
+    if( qStaged )
+    {
+        if( bLeft )
+            ksw_rows<W, true, true>( P, seq, qlen, tlen, w, zdrop, bEarlyStop, sm, tb, ez );
+        else
+            ksw_rows<W, false, true>( P, seq, qlen, tlen, w, zdrop, bEarlyStop, sm, tb, ez );
+    }
+    else
+    {
+        if( bLeft )
+            ksw_rows<W, true, false>( P, seq, qlen, tlen, w, zdrop, bEarlyStop, sm, tb, ez );
+        else
+            ksw_rows<W, false, false>( P, seq, qlen, tlen, w, zdrop, bEarlyStop, sm, tb, ez );
+    }
 }
 
 // decide where the backtrack starts (kswcpp_core.h:796-835); returns false if there is no backtrack
@@ -517,7 +518,7 @@ struct KswBatchArgs
     KswScore score;
 };
 
-template <int W> __global__ void __launch_bounds__( 256 ) ksw_batch_kernel( KswBatchArgs A )
+template <int W> __global__ void __launch_bounds__( 256, 3 ) ksw_batch_kernel( KswBatchArgs A )
 {
     extern __shared__ __align__( 16 ) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
