@@ -171,8 +171,15 @@ struct SeqAccess
 // Once max(B_r, B_{r-1}, T_r) <= ez.max the maximum and its position are final; the reference would only go on to
 // set zdropped / mqe / mte / score, which such callers never read. Validated against the reference restatement on
 // adversarial problems (oracle/ksw_oracle.cpp: ma_oracle_ksw_earlystop_check, tests/test_earlystop_bound.py).
-template <int W, bool LEFT, bool QS>
-__device__ __forceinline__ void ksw_rows( const KswScore& P, const SeqAccess& seq, const int qlen, const int tlen,
+//
+// FAST mode (extensions with early termination only): as long as the band term of the limits is inactive
+// (rows r <= w: st0 = max(0, r-qlen+1), en0 = min(tlen-1, r)) the band edges are the matrix borders, the reference's
+// out-of-band cells of the 16-aligned range feed no in-band cell and the backtrack cannot reach them, so only the
+// in-band columns are computed. If such a problem is still running when the band is about to limit (r == w + 1,
+// rare: the early-stop bound normally fires after ~2 * qlen rows) it is recomputed from scratch in the exact mode.
+// Returns false in that case.
+template <int W, bool LEFT, bool QS, bool FAST>
+__device__ __forceinline__ bool ksw_rows( const KswScore& P, const SeqAccess& seq, const int qlen, const int tlen,
                                           const int w, const int zdrop, const bool bEarlyStop, KswSmem<W>& sm,
                                           unsigned char* __restrict__ tb, KswOut& ez )
 {
@@ -208,9 +215,23 @@ __device__ __forceinline__ void ksw_rows( const KswScore& P, const SeqAccess& se
             ez.zdropped = 1;
             break;
         }
+        if( FAST && r > w )
+            return false; // the band starts to limit: recompute in the exact mode
         cells += en0 - st0 + 1;
-        const int st = st0 & ~15, en = en0 | 15;
-        const int sEnd = min( st0 + ( ( ( en0 - st0 ) >> 4 ) + 1 ) * 16, T16 ); // end of the score-profile writes
+        const int st = st0 & ~15, en = FAST ? en0 : ( en0 | 15 );
+        const int sEnd = FAST ? en0 + 1 : min( st0 + ( ( ( en0 - st0 ) >> 4 ) + 1 ) * 16, T16 ); // score-profile end
+        if( FAST )
+        { // only the target codes of the columns entering the band are needed
+            if( inited_end <= en0 )
+            {
+                const int idx = inited_end + lane;
+                if( idx < T16 )
+                    sm.tc[ idx & M ] = idx < tlen ? (unsigned char)seq.T( idx ) : (unsigned char)0;
+                inited_end += 32;
+                __syncwarp( );
+            }
+        }
+        else
         {
             const int need = min( max( en + 1, ( sEnd + 15 ) & ~15 ), T16 );
             if( inited_end < need )
@@ -230,15 +251,16 @@ __device__ __forceinline__ void ksw_rows( const KswScore& P, const SeqAccess& se
         }
         const int first_col =
             w8( r == 0 ? -q - e : r < P.long_thres ? -e : r == P.long_thres ? P.long_diff : -e2 );
-        int cx = init6, cx2 = init25, cv = init6; // values entering column st from column st-1 (:562-579)
-        if( st > 0 )
+        int cx = init6, cx2 = init25, cv = init6; // values entering the first column from its left neighbour (:562-579)
+        const int c0 = FAST ? st0 : st; // first column of the pass
+        if( c0 > 0 )
         {
-            if( st - 1 >= last_st && st - 1 <= last_en )
-                cx = sm.x[ ( st - 1 ) & M ], cx2 = sm.x2[ ( st - 1 ) & M ], cv = sm.v[ ( st - 1 ) & M ];
+            if( FAST || ( st - 1 >= last_st && st - 1 <= last_en ) )
+                cx = sm.x[ ( c0 - 1 ) & M ], cx2 = sm.x2[ ( c0 - 1 ) & M ], cv = sm.v[ ( c0 - 1 ) & M ];
         }
         else
             cv = first_col;
-        if( en >= r && lane == 0 )
+        if( ( FAST ? en0 == r : en >= r ) && lane == 0 )
         {
             sm.y[ r & M ] = (signed char)init6;
             sm.y2[ r & M ] = (signed char)init25;
@@ -255,16 +277,16 @@ __device__ __forceinline__ void ksw_rows( const KswScore& P, const SeqAccess& se
         int Hen0l = 0, Hst0l = 0;
         unsigned char* rowp = tb + rowOff - st;
         const unsigned nS = (unsigned)( sEnd - st0 ), nB = (unsigned)( en0 - st0 ), nV = (unsigned)( en1 - st0 );
-        for( int base = st; base <= en; base += 32 )
+        for( int base = c0; base <= en; base += 32 )
         {
             const int t = base + lane;
             const bool act = t <= en;
             const int k = t & M;
             const int xo = sm.x[ k ], vo = sm.v[ k ], x2o = sm.x2[ k ], ut = sm.u[ k ], yo = sm.y[ k ], y2o = sm.y2[ k ];
             const int hOld = sm.H[ k ];
-            int z = sm.s[ k ]; // out-of-band cell of the aligned range: stale profile, as in the reference
+            int z = FAST ? 0 : (int)sm.s[ k ]; // out-of-band cell of the aligned range: stale profile (reference)
             const unsigned dt = (unsigned)( t - st0 );
-            if( dt < nS )
+            if( FAST || dt < nS )
             { // score profile (:591-616); N scores -e2; beyond the sequences the zero padding compares as 'A'
                 const int a = sm.tc[ k ];
                 const int qi = r - t;
@@ -272,7 +294,7 @@ __device__ __forceinline__ void ksw_rows( const KswScore& P, const SeqAccess& se
                 if( (unsigned)qi < (unsigned)qlen )
                     b = QS ? (int)sm.qc[ qi ] : seq.Q( qi );
                 z = ( a == 4 || b == 4 ) ? scN : ( a == b ? scM : scX );
-                if( act )
+                if( !FAST && act )
                     sm.s[ k ] = (signed char)z;
             }
             int xt1 = __shfl_up_sync( FULL, xo, 1 ), vt1 = __shfl_up_sync( FULL, vo, 1 ),
@@ -360,7 +382,7 @@ __device__ __forceinline__ void ksw_rows( const KswScore& P, const SeqAccess& se
             }
         }
         // score-profile entries the reference writes beyond the aligned range (read, stale, by later rows)
-        if( sEnd > en + 1 )
+        if( !FAST && sEnd > en + 1 )
             for( int t = en + 1 + lane; t < sEnd; t += 32 )
             {
                 const int k = t & M;
@@ -371,25 +393,34 @@ __device__ __forceinline__ void ksw_rows( const KswScore& P, const SeqAccess& se
                     b = QS ? (int)sm.qc[ qi ] : seq.Q( qi );
                 sm.s[ k ] = (signed char)( ( a == 4 || b == 4 ) ? scN : ( a == b ? scM : scX ) );
             }
-        const int Hen0 = __shfl_sync( FULL, Hen0l, ( en0 - st ) & 31 );
-        // lanes with equal (lane % SIZE) form one SSE lane of the reference
-        for( int o = 16; o >= -SMASK; o >>= 1 )
+        const int Hen0 = __shfl_sync( FULL, Hen0l, ( en0 - c0 ) & 31 );
+        // the row maximum is the exact maximum of the row (only its POSITION is lane-blocked in the reference)
+        int max_H = __reduce_max_sync( FULL, max( max( bt == NONE_T ? NONE_H : bh, tt_ == NONE_T ? NONE_H : th ), Hen0 ) );
+        int max_t = en0;
+        // the position is consumed only by a new maximum or by a z-drop test that can fire (l >= 0)
+        if( max_H > ez.max || ( zdrop >= 0 && ez.max - max_H > zdrop ) )
         {
-            const int oh = __shfl_xor_sync( FULL, bh, o ), ot = __shfl_xor_sync( FULL, bt, o );
-            if( ot != NONE_T && ( bt == NONE_T || oh > bh || ( oh == bh && ot < bt ) ) )
-                bh = oh, bt = ot;
-        }
-        if( bt == NONE_T || !( bh > Hen0 ) )
-            bh = Hen0, bt = en0;
-        int max_H = __reduce_max_sync( FULL, bh );
-        int max_t = __reduce_max_sync( FULL, bt );
-        if( en1 < en0 )
-        { // scalar tail [en1, en0): the first index of the tail maximum, if it beats the vector result
-            const int tm = __reduce_max_sync( FULL, tt_ == NONE_T ? NONE_H : th );
-            if( tm > max_H )
+            // lanes with equal ((t - st0) % SIZE) form one SSE lane of the reference
+            const int rot = FAST ? 0 : ( ( st0 - st ) & 31 ); // in the exact mode lane % SIZE == (t - st) % SIZE
+            (void)rot;
+            for( int o = 16; o >= -SMASK; o >>= 1 )
             {
-                max_H = tm;
-                max_t = __reduce_min_sync( FULL, ( tt_ != NONE_T && th == tm ) ? tt_ : NONE_T );
+                const int oh = __shfl_xor_sync( FULL, bh, o ), ot = __shfl_xor_sync( FULL, bt, o );
+                if( ot != NONE_T && ( bt == NONE_T || oh > bh || ( oh == bh && ot < bt ) ) )
+                    bh = oh, bt = ot;
+            }
+            if( bt == NONE_T || !( bh > Hen0 ) )
+                bh = Hen0, bt = en0;
+            int mH = __reduce_max_sync( FULL, bh );
+            max_t = __reduce_max_sync( FULL, bt );
+            if( en1 < en0 )
+            { // scalar tail [en1, en0): the first index of the tail maximum, if it beats the vector result
+                const int tm = __reduce_max_sync( FULL, tt_ == NONE_T ? NONE_H : th );
+                if( tm > mH )
+                {
+                    mH = tm;
+                    max_t = __reduce_min_sync( FULL, ( tt_ != NONE_T && th == tm ) ? tt_ : NONE_T );
+                }
             }
         }
         __syncwarp( );
@@ -397,7 +428,7 @@ __device__ __forceinline__ void ksw_rows( const KswScore& P, const SeqAccess& se
             ez.mte = Hen0, ez.mte_q = r - en; // sic: the aligned en
         if( r - st0 == qlen - 1 )
         {
-            const int Hst0 = __shfl_sync( FULL, Hst0l, ( st0 - st ) & 31 );
+            const int Hst0 = __shfl_sync( FULL, Hst0l, ( st0 - c0 ) & 31 );
             if( Hst0 > ez.mqe )
                 ez.mqe = Hst0, ez.mqe_t = st0;
         }
@@ -434,6 +465,7 @@ __device__ __forceinline__ void ksw_rows( const KswScore& P, const SeqAccess& se
     }
     ez.cells = cells;
     __syncwarp( );
+    return true;
 }
 
 template <int W>
@@ -458,19 +490,32 @@ __device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int
         __syncwarp( );
     }
     const bool bLeft = !( flag & MA_KSW_RIGHT );
+    // FAST mode needs the query staged (narrow problems) and a band that cannot limit before the matrix does
+    if( bEarlyStop && qStaged && w >= qlen )
+    {
+        const bool ok = bLeft ? ksw_rows<W, true, true, true>( P, seq, qlen, tlen, w, zdrop, true, sm, tb, ez )
+                              : ksw_rows<W, false, true, true>( P, seq, qlen, tlen, w, zdrop, true, sm, tb, ez );
+        if( ok )
+            return;
+        ez.max_q = ez.max_t = ez.mqe_t = ez.mte_q = -1;
+        ez.max = 0;
+        ez.score = ez.mqe = ez.mte = (int)0x80000000;
+        ez.zdropped = 0, ez.cells = 0;
+        __syncwarp( );
+    }
     if( qStaged )
     {
         if( bLeft )
-            ksw_rows<W, true, true>( P, seq, qlen, tlen, w, zdrop, bEarlyStop, sm, tb, ez );
+            ksw_rows<W, true, true, false>( P, seq, qlen, tlen, w, zdrop, bEarlyStop, sm, tb, ez );
         else
-            ksw_rows<W, false, true>( P, seq, qlen, tlen, w, zdrop, bEarlyStop, sm, tb, ez );
+            ksw_rows<W, false, true, false>( P, seq, qlen, tlen, w, zdrop, bEarlyStop, sm, tb, ez );
     }
     else
     {
         if( bLeft )
-            ksw_rows<W, true, false>( P, seq, qlen, tlen, w, zdrop, bEarlyStop, sm, tb, ez );
+            ksw_rows<W, true, false, false>( P, seq, qlen, tlen, w, zdrop, bEarlyStop, sm, tb, ez );
         else
-            ksw_rows<W, false, false>( P, seq, qlen, tlen, w, zdrop, bEarlyStop, sm, tb, ez );
+            ksw_rows<W, false, false, false>( P, seq, qlen, tlen, w, zdrop, bEarlyStop, sm, tb, ez );
     }
 }
 

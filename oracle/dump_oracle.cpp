@@ -36,6 +36,14 @@ struct Dump
 } // namespace
 
 // stages: 1 = seeding, 2 = + extract, 3 = + SoC, 4 = + harmonization, 5 = + DP/alignments
+// overrides: { bandwidth_ext, zdrop, padding, max_gap_area, min_bandwidth_gap }, -1 keeps the preset's value
+static int g_aiOverride[ 5 ] = { -1, -1, -1, -1, -1 };
+extern "C" void ma_oracle_set_overrides( const int* p )
+{
+    for( int i = 0; i < 5; i++ )
+        g_aiOverride[ i ] = p ? p[ i ] : -1;
+}
+
 extern "C" int ma_oracle_align_dump( const char* prefix, const char* reads_txt, const char* preset, const char* out,
                                      long long srand_base, int stages, char* err, int errcap )
 {
@@ -46,6 +54,16 @@ extern "C" int ma_oracle_align_dump( const char* prefix, const char* reads_txt, 
         Params P;
         if( !P.preset( preset ) )
             throw std::runtime_error( "unknown preset" );
+        if( g_aiOverride[ 0 ] >= 0 )
+            P.bandwidth_ext = g_aiOverride[ 0 ];
+        if( g_aiOverride[ 1 ] >= 0 )
+            P.zdrop = g_aiOverride[ 1 ];
+        if( g_aiOverride[ 2 ] >= 0 )
+            P.padding = g_aiOverride[ 2 ];
+        if( g_aiOverride[ 3 ] >= 0 )
+            P.max_gap_area = g_aiOverride[ 3 ];
+        if( g_aiOverride[ 4 ] >= 0 )
+            P.min_bandwidth_gap = g_aiOverride[ 4 ];
         std::ifstream in( reads_txt );
         if( !in )
             throw std::runtime_error( "cannot open reads" );

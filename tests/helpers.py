@@ -108,8 +108,13 @@ def write_pairs(path: str, pairs) -> None:
             f.write("%d %d %d %s %s\n" % (w, zdrop, flag, qs, ts))
 
 
-def oracle_align_dump(prefix: str, reads_txt: str, preset: str, out: str, srand_base: int = -1, stages: int = 5):
+def oracle_align_dump(prefix: str, reads_txt: str, preset: str, out: str, srand_base: int = -1, stages: int = 5,
+                      overrides=None):
+    """overrides: dict with any of bandwidth_ext, zdrop, padding, max_gap_area, min_bandwidth_gap."""
     lib = oracle_lib()
+    keys = ["bandwidth_ext", "zdrop", "padding", "max_gap_area", "min_bandwidth_gap"]
+    ov = (ctypes.c_int * 5)(*[int((overrides or {}).get(k, -1)) for k in keys])
+    lib.ma_oracle_set_overrides(ov)
     err = ctypes.create_string_buffer(512)
     lib.ma_oracle_align_dump.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p,
                                          ctypes.c_longlong, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]

@@ -163,3 +163,22 @@ def test_long_reads_against_oracle(tmp_path):
     got = PC.gpu_stage_dump(ctx, reads, keep_segments=8192)
     PC.assert_same_stages(got, exp, what="pacbio")
     ctx.close()
+
+
+@pytest.mark.parametrize("overrides", [{"bandwidth_ext": 24}, {"bandwidth_ext": 70, "zdrop": 30},
+                                       {"bandwidth_ext": 40, "padding": 120, "max_gap_area": 5}])
+def test_non_default_dp_parameters_against_oracle(gold_index, overrides, tmp_path):
+    """Narrow extension bands make the in-band fast mode of the DP kernel hit the band limit (r > w) and fall back
+    to the exact 16-aligned mode; small z-drop / padding / gap-area values exercise the dual extension."""
+    ctx = api.Context(0, "illumina")
+    p = api.preset("illumina")
+    p.srand_base = PC.SRAND
+    for k, v in overrides.items():
+        setattr(p, k, v)
+    ctx.set_params(p)
+    ctx.index_upload(gold_index)
+    got = PC.gpu_stage_dump(ctx, PC.read_reads_txt(PC.gold_reads("illumina")))
+    exp = H.oracle_align_dump(PC.GOLD_PREFIX, PC.gold_reads("illumina"), "illumina", str(tmp_path / "o.dump"),
+                              PC.SRAND, 5, overrides)
+    PC.assert_same_stages(got, exp, what=str(overrides))
+    ctx.close()
