@@ -309,6 +309,17 @@ def main():
                 "note": "algorithmic bytes: 128 B per extend_backward, 64 B per invPsi step + 8 B per SA sample, "
                         "1 B traceback per DP cell + sequences (SURVEY.md §8(d)); the DP kernel is integer-ALU "
                         "bound: see kernels.ksw_batch_kernel.GCUPS and dp_int_roofline"}
+    # seeding roofline: measured random 64-byte gather bandwidth over a buffer of the occ table's size
+    occ_bytes = args.genome_mbp * 1_000_000
+    gather_gbs = ctx.gather_probe(occ_bytes)
+    gather_hbm_gbs = ctx.gather_probe(8 << 30)
+    seed_ach = kernels["seed_kernel"]["GB/s"]
+    roofline_seeding = {"kernel": "seed_kernel", "bound": "hbm (random 64-byte blocks; the %d MB occ table is mostly "
+                        "L2-resident on this configuration)" % (occ_bytes // 1_000_000),
+                        "achieved": seed_ach, "peak": gather_gbs, "unit": "GB/s", "frac": seed_ach / gather_gbs,
+                        "peak_hbm_resident_buffer": gather_hbm_gbs,
+                        "peak_source": "ma_b200_gather_probe: independent random 64-byte reads over a buffer of the "
+                                       "occ table's size (and over 8 GiB for the HBM-resident figure), this run"}
     sm_mhz = peaks.get("sm_max_mhz", 1965.0)
     int_ops_peak = 148 * 128 * sm_mhz * 1e6  # INT32 lane-ops/s
     dp_roof = {"gcups": kernels["ksw_batch_kernel"]["GCUPS"], "int32_lane_ops_per_s_peak": int_ops_peak,
@@ -331,6 +342,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max / K},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
+            "roofline_seeding": roofline_seeding,
             "dp_int_roofline": dp_roof, "kernels": kernels, "cpu_baseline": cpu_baseline,
             "aligned_reads_per_step": aligned_all, "index_build_s": t_index,
             "work_per_step": {k: int(last[k]) for k in ("n_reads", "n_seeds", "n_sets", "n_tasks", "n_ext",

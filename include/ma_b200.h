@@ -206,6 +206,11 @@ int ma_b200_align_batch( ma_b200_ctx* ctx, int64_t n_reads, const uint8_t* reads
                          ma_b200_read_info* info, ma_b200_alignment* alns, int64_t cap_alns, uint32_t* runs,
                          int64_t cap_runs, ma_b200_align_stats* stats );
 
+/* ---- measurement helper ----------------------------------------------------------------------------------- */
+/* Measured bandwidth (GB/s) of independent random 64-byte block reads over a buffer of buffer_bytes: the roofline
+ * of the seeding kernels (two such reads per extend_backward), SURVEY.md §8(d). */
+int ma_b200_gather_probe( ma_b200_ctx* ctx, int64_t buffer_bytes, double* gbs );
+
 #ifdef __cplusplus
 }
 #endif

@@ -113,6 +113,7 @@ def load_library():
     lib.ma_b200_align_download_sets.argtypes = [vp, vp, i64, vp, i64]
     lib.ma_b200_align_download.argtypes = [vp, vp, vp, i64, vp, i64]
     lib.ma_b200_align_batch.argtypes = [vp, i64, vp, vp, vp, vp, i64, vp, i64, ctypes.POINTER(AlignStats)]
+    lib.ma_b200_gather_probe.argtypes = [vp, i64, ctypes.POINTER(ctypes.c_double)]
     _lib = lib
     return lib
 
@@ -263,6 +264,12 @@ class Context:
                                                  cap_alns, _ptr(runs), cap_runs, ctypes.byref(st)))
         self._stats = st.as_dict()
         return info, alns[:st.n_sets], runs[:st.n_runs], self._stats
+
+    def gather_probe(self, buffer_bytes: int) -> float:
+        """Measured GB/s of independent random 64-byte reads over a buffer of this size (seeding roofline)."""
+        g = ctypes.c_double(0)
+        self._check(self.lib.ma_b200_gather_probe(self.h, int(buffer_bytes), ctypes.byref(g)))
+        return g.value
 
     # ---- banded DP ------------------------------------------------------------------------------------------
     def ksw_upload(self, tasks: np.ndarray, seq: np.ndarray):

@@ -8,10 +8,13 @@
 //                                       libs/ma/src/module/binarySeeding.cpp:32-178, inc/ma/module/binarySeeding.h:55-452
 //   SegmentVector::forEachSeed filter   libs/ma/inc/ma/container/segment.h:316-349
 //
-// HBM layout: the occurrence table keeps the reference's 64-byte block per 128 BWT symbols
-// (4 x u64 cumulative counts + 8 x u32 of 16 two-bit symbols), 64-byte aligned, so one bwt_occ4 is exactly one
-// 64-byte line fetched with four 128-bit loads; counting uses popcount on the two bit-planes instead of the
-// reference's 256-entry byte LUT (same values).
+// HBM layout: one 64-byte, 64-byte-aligned block per 128 BWT symbols, like the reference
+// (4 x u64 cumulative counts + 32 bytes of symbols), so one bwt_occ4 is exactly one 64-byte line fetched with four
+// 128-bit loads. Inside the block the symbols are re-laid out as two BIT PLANES (4 x u32 high bits, 4 x u32 low
+// bits, symbol j at bit 31 - (j & 31) of word j >> 5) instead of the reference's interleaved 2-bit codes: a rank is
+// then 4 words x (prefix mask, 3 x LOP3, 3 x POPC) instead of 8 words with plane extraction — ~3x fewer integer
+// instructions per extend_backward, which is what bounds seeding once the loads are in flight. relayout_block()
+// converts a reference block; every SAInterval / SA value stays identical (tests + hostsim).
 #pragma once
 #include "stl_exact.cuh"
 #include <stdint.h>
@@ -26,7 +29,7 @@ struct U4
 
 struct DevIndex
 {
-    const U4* bwt; // 4 x U4 per block
+    const U4* bwt; // 4 x U4 per block, PLANE layout (see relayout_block)
     const long long* sa;
     const unsigned char* pac;
     const long long* contig_start;
@@ -55,7 +58,7 @@ MA_HD inline U4 ld_u4( const U4* p )
 #endif
 }
 
-// counts of C, G, T among the first `nvalid` (0..16) symbols of a 16-symbol word (MSB first)
+// counts of C, G, T among the first `nvalid` (0..16) symbols of a 16-symbol word of the REFERENCE layout (MSB first)
 MA_HD inline void count_word( unsigned int w, int nvalid, int& c, int& g, int& t )
 {
     if( nvalid <= 0 )
@@ -68,6 +71,33 @@ MA_HD inline void count_word( unsigned int w, int nvalid, int& c, int& g, int& t
     c += popc32( lo & ~hi );
 }
 
+// reference block (16 x u32: counts, then 8 words of 16 interleaved 2-bit symbols) -> plane block (counts, hi[4], lo[4])
+MA_HD inline void relayout_block( const unsigned int* in, unsigned int* out )
+{
+    for( int i = 0; i < 8; i++ )
+        out[ i ] = in[ i ];
+    for( int wd = 0; wd < 4; wd++ )
+    {
+        unsigned int hi = 0, lo = 0;
+        for( int j = 0; j < 32; j++ )
+        {
+            const int sym = wd * 32 + j;
+            const unsigned int code = in[ 8 + ( sym >> 4 ) ] >> ( ( ~sym & 15 ) << 1 ) & 3;
+            hi |= ( code >> 1 ) << ( 31 - j ), lo |= ( code & 1 ) << ( 31 - j );
+        }
+        out[ 8 + wd ] = hi, out[ 12 + wd ] = lo;
+    }
+}
+
+// counts of C, G, T among the first `nvalid` (<= 0 .. >= 32) symbols of one 32-symbol plane pair
+MA_HD inline void count_planes( unsigned int hi, unsigned int lo, int nvalid, int& c, int& g, int& t )
+{
+    const unsigned int m = nvalid >= 32 ? 0xFFFFFFFFu : ( nvalid <= 0 ? 0u : ~( 0xFFFFFFFFu >> nvalid ) );
+    t += popc32( hi & lo & m );
+    g += popc32( hi & ~lo & m );
+    c += popc32( ~hi & lo & m );
+}
+
 // bwt_occ4: number of A,C,G,T in BWT[0..k] (k == -1 -> zeros)
 MA_HD inline void occ4( const DevIndex& I, long long k, long long cnt[ 4 ] )
 {
@@ -78,17 +108,13 @@ MA_HD inline void occ4( const DevIndex& I, long long k, long long cnt[ 4 ] )
     }
     k -= ( k >= I.primary );
     const U4* blk = I.bwt + ( ( k >> 7 ) << 2 );
-    const U4 c0 = ld_u4( blk ), c1 = ld_u4( blk + 1 ), w0 = ld_u4( blk + 2 ), w1 = ld_u4( blk + 3 );
+    const U4 c0 = ld_u4( blk ), c1 = ld_u4( blk + 1 ), ph = ld_u4( blk + 2 ), pl = ld_u4( blk + 3 );
     const int n = (int)( k & 127 ) + 1; // symbols of this block to count
     int c = 0, g = 0, t = 0;
-    count_word( w0.x, n, c, g, t );
-    count_word( w0.y, n - 16, c, g, t );
-    count_word( w0.z, n - 32, c, g, t );
-    count_word( w0.w, n - 48, c, g, t );
-    count_word( w1.x, n - 64, c, g, t );
-    count_word( w1.y, n - 80, c, g, t );
-    count_word( w1.z, n - 96, c, g, t );
-    count_word( w1.w, n - 112, c, g, t );
+    count_planes( ph.x, pl.x, n, c, g, t );
+    count_planes( ph.y, pl.y, n - 32, c, g, t );
+    count_planes( ph.z, pl.z, n - 64, c, g, t );
+    count_planes( ph.w, pl.w, n - 96, c, g, t );
     cnt[ 0 ] = (long long)( ( (unsigned long long)c0.y << 32 ) | c0.x ) + ( n - c - g - t );
     cnt[ 1 ] = (long long)( ( (unsigned long long)c0.w << 32 ) | c0.z ) + c;
     cnt[ 2 ] = (long long)( ( (unsigned long long)c1.y << 32 ) | c1.x ) + g;
@@ -139,16 +165,20 @@ MA_HD inline long long inv_psi( const DevIndex& I, long long k )
     const long long x = k - ( k > I.primary );
     // occ(k, c): k == ref_len -> total count; else inclusive count through k - (k >= primary) == x for k != primary
     const U4* blk = I.bwt + ( ( x >> 7 ) << 2 );
-    const U4 c0 = ld_u4( blk ), c1 = ld_u4( blk + 1 ), w0 = ld_u4( blk + 2 ), w1 = ld_u4( blk + 3 );
-    const unsigned int words[ 8 ] = { w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w };
+    const U4 c0 = ld_u4( blk ), c1 = ld_u4( blk + 1 ), ph = ld_u4( blk + 2 ), pl = ld_u4( blk + 3 );
     const int pos = (int)( x & 127 );
-    const int ch = (int)( words[ pos >> 4 ] >> ( ( ~pos & 15 ) << 1 ) & 3 );
+    const int wsel = pos >> 5, bit = 31 - ( pos & 31 );
+    const unsigned int hw = wsel == 0 ? ph.x : wsel == 1 ? ph.y : wsel == 2 ? ph.z : ph.w;
+    const unsigned int lw = wsel == 0 ? pl.x : wsel == 1 ? pl.y : wsel == 2 ? pl.z : pl.w;
+    const int ch = (int)( ( ( hw >> bit ) & 1 ) << 1 | ( ( lw >> bit ) & 1 ) );
     if( k == I.ref_len )
         return I.L2[ ch ] + ( I.L2[ ch + 1 ] - I.L2[ ch ] );
     const int n = pos + 1;
     int c = 0, g = 0, t = 0;
-    for( int j = 0; j < 8; j++ )
-        count_word( words[ j ], n - 16 * j, c, g, t );
+    count_planes( ph.x, pl.x, n, c, g, t );
+    count_planes( ph.y, pl.y, n - 32, c, g, t );
+    count_planes( ph.z, pl.z, n - 64, c, g, t );
+    count_planes( ph.w, pl.w, n - 96, c, g, t );
     long long occ;
     switch( ch )
     {

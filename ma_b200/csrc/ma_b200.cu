@@ -44,7 +44,8 @@ struct ma_b200_ctx
     // ---- index (replicated per context / GPU)
     bool have_index = false;
     DevIndex index;
-    DevBuf<U4> ix_bwt;
+    DevBuf<U4> ix_bwt; // reference layout (what index_upload got / index_download returns)
+    DevBuf<U4> ix_bwtp; // bit-plane layout the kernels read (fmindex.cuh relayout_block)
     DevBuf<long long> ix_sa;
     DevBuf<unsigned char> ix_pac;
     DevBuf<long long> ix_contigs; // starts then lengths
@@ -462,6 +463,39 @@ extern "C" int ma_b200_ksw_batch( ma_b200_ctx* ctx, int64_t n, const ma_b200_ksw
 }
 
 // ------------------------------------------------------------------------------------------------ index
+// reference occ blocks -> bit-plane blocks, one thread per 128-symbol block (the trailing counter block, which sits
+// right behind a short last data block, is never taken for symbols)
+__global__ void index_relayout_kernel( const unsigned int* ref, long long n_words, long long N, long long nblk,
+                                       unsigned int* planes )
+{
+    for( long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < nblk;
+         b += (long long)gridDim.x * blockDim.x )
+    {
+        unsigned int in[ 16 ], out[ 16 ];
+        for( int j = 0; j < 16; j++ )
+        {
+            const long long idx = 16 * b + j;
+            const bool ok = idx < n_words && ( j < 8 || 128 * b + 16 * ( j - 8 ) < N );
+            in[ j ] = ok ? ref[ idx ] : 0u;
+        }
+        relayout_block( in, out );
+        for( int j = 0; j < 16; j++ )
+            planes[ 16 * b + j ] = out[ j ];
+    }
+}
+
+static void index_make_planes( ma_b200_ctx* ctx, long long n_words, long long ref_len )
+{
+    const long long nblk = ( ref_len + 127 ) / 128;
+    ctx->ix_bwtp.reserve( (size_t)( nblk + 2 ) * 4 );
+    MA_CUDA( cudaMemsetAsync( ctx->ix_bwtp.p + nblk * 4, 0, 2 * 64, ctx->stream ) );
+    const int grid = (int)std::min<long long>( ( nblk + 255 ) / 256, (long long)ctx->num_sms * 8 );
+    index_relayout_kernel<<<grid, 256, 0, ctx->stream>>>( (const unsigned int*)ctx->ix_bwt.p, n_words, ref_len, nblk,
+                                                          (unsigned int*)ctx->ix_bwtp.p );
+    MA_CUDA( cudaGetLastError( ) );
+    ctx->launches++;
+}
+
 extern "C" int ma_b200_index_upload( ma_b200_ctx* ctx, const uint32_t* bwt_words, int64_t n_words, const int64_t* L2,
                                      int64_t primary, int64_t ref_len, const int64_t* sa, int64_t n_sa,
                                      int32_t sa_intv, const uint8_t* pac, int64_t n_pac_bytes, int64_t fwd_len,
@@ -482,9 +516,10 @@ extern "C" int ma_b200_index_upload( ma_b200_ctx* ctx, const uint32_t* bwt_words
     MA_CUDA( cudaMemcpyAsync( ctx->ix_contigs.p, contig_start, n_contigs * 8, cudaMemcpyHostToDevice, ctx->stream ) );
     MA_CUDA( cudaMemcpyAsync( ctx->ix_contigs.p + n_contigs, contig_len, n_contigs * 8, cudaMemcpyHostToDevice,
                               ctx->stream ) );
+    index_make_planes( ctx, n_words, ref_len );
     MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
     DevIndex& I = ctx->index;
-    I.bwt = ctx->ix_bwt.p, I.sa = ctx->ix_sa.p, I.pac = ctx->ix_pac.p;
+    I.bwt = ctx->ix_bwtp.p, I.sa = ctx->ix_sa.p, I.pac = ctx->ix_pac.p;
     I.contig_start = ctx->ix_contigs.p, I.contig_len = ctx->ix_contigs.p + n_contigs;
     for( int i = 0; i < 5; i++ )
         I.L2[ i ] = L2[ i ];
@@ -507,9 +542,10 @@ extern "C" int ma_b200_index_build( ma_b200_ctx* ctx, const uint8_t* fwd, int64_
     MA_CUDA( cudaMemcpyAsync( ctx->ix_contigs.p, contig_start, n_contigs * 8, cudaMemcpyHostToDevice, ctx->stream ) );
     MA_CUDA( cudaMemcpyAsync( ctx->ix_contigs.p + n_contigs, contig_len, n_contigs * 8, cudaMemcpyHostToDevice,
                               ctx->stream ) );
+    index_make_planes( ctx, R.n_words, 2 * fwd_len );
     MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
     DevIndex& I = ctx->index;
-    I.bwt = ctx->ix_bwt.p, I.sa = ctx->ix_sa.p, I.pac = ctx->ix_pac.p;
+    I.bwt = ctx->ix_bwtp.p, I.sa = ctx->ix_sa.p, I.pac = ctx->ix_pac.p;
     I.contig_start = ctx->ix_contigs.p, I.contig_len = ctx->ix_contigs.p + n_contigs;
     for( int i = 0; i < 5; i++ )
         I.L2[ i ] = R.L2[ i ];
@@ -1061,4 +1097,32 @@ extern "C" int ma_b200_align_batch( ma_b200_ctx* ctx, int64_t n_reads, const uin
     if( rc )
         return rc;
     return ma_b200_align_download( ctx, info, alns, cap_alns, runs, cap_runs );
+}
+
+// ------------------------------------------------------------------------------------------------ roofline probe
+extern "C" int ma_b200_gather_probe( ma_b200_ctx* ctx, int64_t buffer_bytes, double* gbs )
+{
+    MA_API_BEGIN
+    if( buffer_bytes < 4096 || !gbs )
+        throw std::runtime_error( "gather_probe: bad arguments" );
+    DevBuf<U4> buf;
+    DevBuf<unsigned int> sink;
+    const unsigned long long nBlocks = (unsigned long long)buffer_bytes / 64;
+    buf.reserve( (size_t)nBlocks * 4 );
+    sink.reserve( 1 );
+    MA_CUDA( cudaMemsetAsync( buf.p, 1, nBlocks * 64, ctx->stream ) );
+    const int grid = ctx->num_sms * 8, perThread = 256;
+    float best = 1e30f;
+    for( int it = 0; it < 4; it++ )
+    {
+        ctx->timer.start( ctx->stream );
+        gather64_kernel<<<grid, 256, 0, ctx->stream>>>( buf.p, nBlocks, perThread, 1234567ull + it, sink.p );
+        MA_CUDA( cudaGetLastError( ) );
+        const float ms = ctx->timer.stop( ctx->stream );
+        ctx->launches++;
+        if( it > 0 && ms < best )
+            best = ms;
+    }
+    *gbs = (double)grid * 256 * perThread * 64.0 / ( best * 1e6 );
+    MA_API_END
 }

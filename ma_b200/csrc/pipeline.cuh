@@ -557,4 +557,31 @@ __global__ void __launch_bounds__( 128 ) alnsort_kernel( AlnSortArgs A )
     }
 }
 
+
+// Roofline probe for the seeding kernels: independent random 64-byte block reads over a buffer of
+// the index' size, the same access shape as bwt_occ4 (four 128-bit loads of one 64-byte line), no dependent chain.
+__global__ void __launch_bounds__( 256 ) gather64_kernel( const U4* buf, unsigned long long nBlocks, int perThread,
+                                                         unsigned long long seed, unsigned int* sink )
+{
+    unsigned long long x = seed + 0x9E3779B97F4A7C15ull * ( (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x + 1 );
+    unsigned int acc = 0;
+    for( int i = 0; i < perThread; i += 4 )
+    {
+        U4 v[ 4 ][ 4 ];
+#pragma unroll
+        for( int j = 0; j < 4; j++ )
+        { // 4 independent blocks in flight per thread
+            x ^= x >> 12, x ^= x << 25, x ^= x >> 27;
+            const unsigned long long b = ( ( x * 0x2545F4914F6CDD1Dull ) >> 11 ) % nBlocks;
+            const U4* p = buf + 4 * b;
+            v[ j ][ 0 ] = ld_u4( p ), v[ j ][ 1 ] = ld_u4( p + 1 ), v[ j ][ 2 ] = ld_u4( p + 2 ), v[ j ][ 3 ] = ld_u4( p + 3 );
+        }
+#pragma unroll
+        for( int j = 0; j < 4; j++ )
+            acc += v[ j ][ 0 ].x ^ v[ j ][ 1 ].y ^ v[ j ][ 2 ].z ^ v[ j ][ 3 ].w;
+    }
+    if( acc == 0x12345678u )
+        *sink = acc;
+}
+
 } // namespace ma

@@ -52,8 +52,13 @@ int main( int argc, char** argv )
     std::vector<long long> cs, cl;
     for( auto& c : OI.contigs )
         cs.push_back( c.start ), cl.push_back( c.length );
-    std::vector<U4> bwt( ( OI.bwt.size( ) + 3 ) / 4 + 4 );
-    memcpy( bwt.data( ), OI.bwt.data( ), OI.bwt.size( ) * 4 );
+    std::vector<U4> bwt( ( OI.bwt.size( ) + 15 ) / 16 * 4 + 8 );
+    { // reference blocks -> bit-plane blocks (what ma_b200_index_upload does on the device)
+        std::vector<unsigned int> in( ( OI.bwt.size( ) + 15 ) / 16 * 16 + 16, 0 );
+        memcpy( in.data( ), OI.bwt.data( ), OI.bwt.size( ) * 4 );
+        for( size_t b = 0; b * 16 < OI.bwt.size( ); b++ )
+            relayout_block( in.data( ) + 16 * b, (unsigned int*)bwt.data( ) + 16 * b );
+    }
     DevIndex I;
     I.bwt = bwt.data( );
     I.sa = (const long long*)OI.sa.data( );
