@@ -92,6 +92,12 @@ typedef struct
     int64_t cells;
 } ma_b200_ksw_result;
 
+/* Extension tasks (flag & 0x40, KSW_EZ_EXTZ_ONLY) of the batches uploaded afterwards run in the early-termination
+ * mode the alignment path uses for NeedlemanWunsch's end extensions (needlemanWunsch.cpp:486-541 reads only the
+ * maximum, its position and the CIGAR): max, max_q, max_t, n_cigar and the CIGAR are identical to the reference's,
+ * the remaining result fields (zdropped, mqe, mte, score, reach_end) are undefined. Off by default. */
+int ma_b200_ksw_set_extension_only( ma_b200_ctx* ctx, int32_t on );
+
 /* Three-step form: inputs stay resident in HBM between upload and run (what bench.py times as `value`). */
 int ma_b200_ksw_upload( ma_b200_ctx* ctx, int64_t n, const ma_b200_ksw_task* tasks, const uint8_t* seq,
                         int64_t seq_bytes );

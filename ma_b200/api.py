@@ -96,6 +96,7 @@ def load_library():
     lib.ma_b200_launch_count.argtypes = [vp]
     lib.ma_b200_launch_count.restype = i64
     lib.ma_b200_set_params.argtypes = [vp, ctypes.POINTER(Params)]
+    lib.ma_b200_ksw_set_extension_only.argtypes = [vp, ctypes.c_int32]
     lib.ma_b200_ksw_upload.argtypes = [vp, i64, vp, vp, i64]
     lib.ma_b200_ksw_run.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     lib.ma_b200_ksw_download.argtypes = [vp, vp, vp, i64, ctypes.POINTER(i64)]
@@ -272,6 +273,10 @@ class Context:
         return g.value
 
     # ---- banded DP ------------------------------------------------------------------------------------------
+    def ksw_set_extension_only(self, on: bool):
+        """Early-termination mode for extension tasks: only max / max_q / max_t / CIGAR are defined."""
+        self._check(self.lib.ma_b200_ksw_set_extension_only(self.h, 1 if on else 0))
+
     def ksw_upload(self, tasks: np.ndarray, seq: np.ndarray):
         tasks = np.ascontiguousarray(tasks, dtype=KSW_TASK_DTYPE)
         seq = np.ascontiguousarray(seq, dtype=np.uint8)

@@ -288,6 +288,54 @@ struct SeedScratch
     int cap;
 };
 
+// The ONE interval list of the state-machine seeder (SeederSM). The reference keeps two lists per SMEM centre and
+// ping-pongs between them (binarySeeding.h smemExtension); the backward pass reads entry j and appends at most one
+// entry at a position <= j, so it can run in place, and every entry of a pass shares the same query start, which is
+// therefore kept as a scalar. What is left per entry is (length - 1, k, l, s): packed here into 16 + 4 bytes (three
+// 40-bit values, reference length < 2^40) so that the first K entries of every thread fit in shared memory
+// (entry j of thread t at [ j * stride + t ]: bank = t mod 8 for the 16-byte part, conflict free for any mix of j).
+// Entries >= K (long lists: repetitive reads) spill to the thread's global scratch.
+struct SegList
+{
+    U4* pk; // 3 x 40 bit
+    int* sz;
+    int stride, K;
+    SegRec* ovf;
+    int cap; // total capacity (K + overflow entries)
+
+    MA_HD static U4 pack( const SAI& a )
+    {
+        U4 v;
+        v.x = (unsigned int)a.start, v.y = (unsigned int)a.rev, v.z = (unsigned int)a.size;
+        v.w = (unsigned int)( ( a.start >> 32 ) & 0xFF ) | (unsigned int)( ( a.rev >> 32 ) & 0xFF ) << 8 |
+              (unsigned int)( ( a.size >> 32 ) & 0xFF ) << 16;
+        return v;
+    }
+    MA_HD static SAI unpack( const U4& v )
+    {
+        SAI a;
+        a.start = (long long)v.x | (long long)( v.w & 0xFF ) << 32;
+        a.rev = (long long)v.y | (long long)( ( v.w >> 8 ) & 0xFF ) << 32;
+        a.size = (long long)v.z | (long long)( ( v.w >> 16 ) & 0xFF ) << 32;
+        return a;
+    }
+    MA_HD SAI sa( int j ) const
+    {
+        return j < K ? unpack( pk[ j * stride ] ) : ovf[ j - K ].sa;
+    }
+    MA_HD int size( int j ) const
+    {
+        return j < K ? sz[ j * stride ] : ovf[ j - K ].size;
+    }
+    MA_HD void set( int j, int size, const SAI& a )
+    {
+        if( j < K )
+            pk[ j * stride ] = pack( a ), sz[ j * stride ] = size;
+        else
+            ovf[ j - K ] = SegRec{ 0, size, a };
+    }
+};
+
 // Sink interface: void seg( const SegRec& ) is called for every segment in the reference's emission order
 // (DFS pre-order).  Returns false in *pOverflow if a list overflowed its capacity.
 template <class Sink> struct Seeder
@@ -519,7 +567,7 @@ template <class Sink> struct SeederSM
     const SeedParams& P;
     const unsigned char* q;
     int L;
-    SeedScratch S;
+    SegList S;
     Sink& sink;
     long long nExt = 0;
     bool overflow = false;
@@ -532,11 +580,11 @@ template <class Sink> struct SeederSM
     int aStart = 0, aSize = 0, center = 0, cs = 0, ce = 0, i = 0;
     SAI ik;
     int start = 0, end = 0, s1 = 0, e1 = 0;
-    SegRec *curr = nullptr, *next = nullptr;
+    int lstart = 0; // query start shared by all entries of the list
     int nCurr = 0, nNext = 0, j = 0;
     bool bHaveOne = false;
 
-    MA_HD SeederSM( const DevIndex& I, const SeedParams& P, const unsigned char* q, int L, SeedScratch S, Sink& sink,
+    MA_HD SeederSM( const DevIndex& I, const SeedParams& P, const unsigned char* q, int L, SegList S, Sink& sink,
                     int* pStack /* 2 x 40 ints */ )
         : I( I ), P( P ), q( q ), L( L ), S( S ), sink( sink ), stS( pStack ), stN( pStack + 40 )
     {
@@ -566,10 +614,10 @@ template <class Sink> struct SeederSM
     {
         sink.seg( SegRec{ st, size, sa } );
     }
-    MA_HD void push_list( SegRec* list, int& n, const SegRec& r )
+    MA_HD void push_list( int& n, int size, const SAI& sa )
     {
         if( n < S.cap )
-            list[ n ] = r;
+            S.set( n, size, sa );
         else
             overflow = true;
         n++;
@@ -599,7 +647,12 @@ template <class Sink> struct SeederSM
         if( nCurr > S.cap )
             nCurr = S.cap;
         for( int a = 0, b = nCurr - 1; a < b; a++, b-- )
-            stl::swp( curr[ a ], curr[ b ] );
+        {
+            const int sa_ = S.size( a ), sb_ = S.size( b );
+            const SAI ia = S.sa( a ), ib = S.sa( b );
+            S.set( a, sb_, ib ), S.set( b, sa_, ia );
+        }
+        lstart = center;
         if( center != 0 )
         {
             i = center - 1, j = 0, bHaveOne = false, nNext = 0;
@@ -611,7 +664,7 @@ template <class Sink> struct SeederSM
     MA_HD void smem_final( )
     {
         if( nCurr != 0 )
-            emit( curr[ 0 ].start, curr[ 0 ].size, curr[ 0 ].sa );
+            emit( lstart, S.size( 0 ), S.sa( 0 ) );
         finish_center( );
     }
     MA_HD void ms_emit_first( )
@@ -673,7 +726,7 @@ template <class Sink> struct SeederSM
                     else
                     {
                         cs = center, ce = center;
-                        curr = S.listA, next = S.listB, nCurr = 0, nNext = 0;
+                        nCurr = 0, nNext = 0;
                         i = center + 1;
                         phase = P_SMEM_FWD;
                     }
@@ -690,13 +743,12 @@ template <class Sink> struct SeederSM
                 case P_SMEM_BWD:
                     if( j < nCurr )
                     {
-                        rIk = curr[ j ].sa, rC = q[ i ];
+                        rIk = S.sa( j ), rC = q[ i ];
                         return true;
                     }
-                    {
-                        SegRec* t = curr;
-                        curr = next, next = t;
-                        nCurr = nNext;
+                    { // the pass over position i is complete: the entries written in place are the new list
+                        nCurr = nNext < S.cap ? nNext : S.cap;
+                        lstart = i;
                         if( nCurr == 0 )
                         {
                             finish_center( ); // nothing left to emit
@@ -757,9 +809,9 @@ template <class Sink> struct SeederSM
             case P_SMEM_FWD:
             {
                 if( ok.size != ik.size )
-                    push_list( curr, nCurr, SegRec{ center, i - center - 1, sai_rc( ik ) } );
+                    push_list( nCurr, i - center - 1, sai_rc( ik ) );
                 if( i == L - 1 && ok.size != 0 )
-                    push_list( curr, nCurr, SegRec{ center, i - center, sai_rc( ok ) } );
+                    push_list( nCurr, i - center, sai_rc( ok ) );
                 if( ok.size == 0 || ( ok.size <= P.min_amb && ik.size <= P.max_amb ) )
                 {
                     smem_fwd_done( );
@@ -772,14 +824,14 @@ template <class Sink> struct SeederSM
             }
             case P_SMEM_BWD:
             {
-                const SegRec s = curr[ j ];
+                const int sSize = S.size( j );
                 if( ok.size <= P.min_amb && !bHaveOne )
                 {
-                    emit( s.start, s.size, s.sa );
+                    emit( lstart, sSize, S.sa( j ) );
                     bHaveOne = true;
                 }
-                else if( ok.size > P.min_amb || ( ok.size > 0 && s.size >= P.max_amb ) )
-                    push_list( next, nNext, SegRec{ i, s.size + 1, ok } );
+                else if( ok.size > P.min_amb || ( ok.size > 0 && sSize >= P.max_amb ) )
+                    push_list( nNext, sSize + 1, ok ); // in place: nNext <= j, entry j has been consumed
                 j++;
                 break;
             }

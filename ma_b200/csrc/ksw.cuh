@@ -17,6 +17,7 @@
 #include "fmindex.cuh"
 #include "ksw_types.cuh"
 #include <cstdint>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 namespace ma
@@ -468,6 +469,317 @@ __device__ __forceinline__ bool ksw_rows( const KswScore& P, const SeqAccess& se
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Packed fast path: TWO cells per lane and instruction (half2 arithmetic), 64 columns per warp pass.
+//
+// Applies to the problems that dominate the pipeline: extensions with early termination (FAST mode above: only
+// in-band cells matter) in the reference's int16 score mode, with scoring parameters for which the int8 difference
+// arithmetic of the reference can never wrap. For every cell of the recurrence (kswcpp_core.h:640-760)
+//     x' in [-q-e, -e],  u' = z - v >= x >= -Q,  u' <= match + Q   (Q = max(q+e, q2+e2); same for v, y, x2, y2)
+// holds for ANY inputs inside these intervals (z >= a = x + v and z <= match are enforced by the cell itself), so by
+// induction all stored values and all intermediates stay within +-(2Q + match + max(|mismatch|, e2) + max(q, q2)).
+// If that bound is <= 127 (ksw_p2_params_ok) the int8 wrap-around is the identity and small-integer half
+// arithmetic (exact up to 2048) gives the same numbers: HADD2 / HMNMX2 / HSET2 masks work on two cells at once, the
+// six difference arrays and the target / reversed-query codes are kept as halves in shared memory so that one
+// 32-bit LDS/STS moves a pair, and the int16 H row is updated with VIADD.16x2 (wraps exactly like the reference).
+// Pairs are aligned on even columns; the dead cell left of an odd st0 and the cell right of en0 are computed and
+// stored too: both columns are rewritten before any in-band cell reads them (u/y/y2 of column r+1 are initialised
+// at the start of row r+1, x/v/x2/H of a column are only read after the column's first own pass).
+// The lane-blocked position of the row maximum (calcMaxScore, :178-250) is NOT tracked per cell: it is recomputed
+// from the finished H row only in the rows that consume it (new maximum, or a z-drop test that can fire).
+// mqe / mte / score are not produced (never read by early-stop callers, see ksw_rows).
+template <int W> struct KswSmemP
+{
+    __half u[ W ], v[ W ], x[ W ], y[ W ], x2[ W ], y2[ W ], tc[ W ];
+    short H[ W ];
+    __half qa[ W ], qb[ W ]; // qa[j + 2] = code of q[qlen-1-j]; qb[j] = qa[j + 1]
+};
+
+__host__ __device__ inline bool ksw_p2_params_ok( const KswScore& P )
+{
+    const int Q = P.q + P.e > P.q2 + P.e2 ? P.q + P.e : P.q2 + P.e2;
+    const int mis = -P.mismatch > P.e2 ? -P.mismatch : P.e2;
+    const int gq = P.q > P.q2 ? P.q : P.q2;
+    const int ld = P.long_diff < 0 ? -P.long_diff : P.long_diff;
+    return P.match > 0 && P.q >= 0 && P.e >= 0 && P.q2 >= 0 && P.e2 >= 0 && P.mismatch <= 0 &&
+           2 * Q + P.match + mis + gq + ld <= 127;
+}
+
+__device__ __forceinline__ unsigned h2u( __half2 h )
+{
+    return *reinterpret_cast<unsigned*>( &h );
+}
+__device__ __forceinline__ __half2 u2h( unsigned u )
+{
+    return *reinterpret_cast<__half2*>( &u );
+}
+__device__ __forceinline__ __half2 h2i( int v )
+{
+    return __half2half2( __int2half_rn( v ) );
+}
+// (m ? a : b) per 16-bit half, m = 0xFFFF / 0 per half
+__device__ __forceinline__ unsigned sel2( unsigned m, unsigned a, unsigned b )
+{
+    return ( a & m ) | ( b & ~m );
+}
+
+// position of the row maximum exactly as calcMaxScore finds it (SSE lanes of 8 int16, first block reaching the
+// lane maximum, then the scalar tail, then H[en0]), from the finished H row in shared memory
+__device__ __forceinline__ int ksw_p2_argmax( const short* __restrict__ H, const int M, const int st0, const int en0,
+                                              const int lane )
+{
+    const unsigned FULL = 0xffffffffu;
+    const int NONE_T = 0x7fffffff, NONE_H = (int)0x80000000;
+    const int nB = en0 - st0, nV = nB & ~7;
+    int bh = NONE_H, bt = NONE_T, th = NONE_H, tt_ = NONE_T;
+    for( int dt = lane; dt < nB; dt += 32 )
+    {
+        const int h = H[ ( st0 + dt ) & M ];
+        if( dt < nV )
+        {
+            if( bt == NONE_T || h > bh )
+                bh = h, bt = st0 + ( dt & ~7 );
+        }
+        else if( tt_ == NONE_T || h > th )
+            th = h, tt_ = st0 + dt;
+    }
+    const int Hen0 = H[ en0 & M ];
+    for( int o = 16; o >= 8; o >>= 1 )
+    {
+        const int oh = __shfl_xor_sync( FULL, bh, o ), ot = __shfl_xor_sync( FULL, bt, o );
+        if( ot != NONE_T && ( bt == NONE_T || oh > bh || ( oh == bh && ot < bt ) ) )
+            bh = oh, bt = ot;
+    }
+    if( bt == NONE_T || !( bh > Hen0 ) )
+        bh = Hen0, bt = en0;
+    int mH = __reduce_max_sync( FULL, bh );
+    int max_t = __reduce_max_sync( FULL, bt );
+    if( nV < nB )
+    {
+        const int tm = __reduce_max_sync( FULL, tt_ == NONE_T ? NONE_H : th );
+        if( tm > mH )
+            max_t = __reduce_min_sync( FULL, ( tt_ != NONE_T && th == tm ) ? tt_ : NONE_T );
+    }
+    return max_t;
+}
+
+// Returns false if the problem has to be recomputed by ksw_rows (band about to limit).
+template <int W, bool LEFT>
+__device__ __forceinline__ bool ksw_rows_p2( const KswScore& P, const SeqAccess& seq, const int qlen, const int tlen,
+                                             const int w, const int zdrop, KswSmemP<W>& sm,
+                                             unsigned char* __restrict__ tb, KswOut& ez )
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int M = W - 1;
+    const int NONE_T = 0x7fffffff;
+    const int q = P.q, e = P.e, q2 = P.q2, e2 = P.e2, qe = q + e;
+    const int scM = P.match;
+    const int ncol16 = ksw_ncol16( qlen, tlen, w );
+    const int nrows = qlen + tlen - 1;
+    const __half2 hMatch = h2i( scM ), hNegQ = h2i( -q ), hNegQ2 = h2i( -q2 ), hNegQE = h2i( -q - e ),
+                  hNegQE2 = h2i( -q2 - e2 ), hE = h2i( e ), hE2 = h2i( e2 ), hFour = h2i( 4 ), hBias = h2i( 1536 );
+    const unsigned uMatch = h2u( hMatch ), uMis = h2u( h2i( P.mismatch ) ), uN = h2u( h2i( -e2 ) );
+    const __half init6 = __int2half_rn( -q - e ), init25 = __int2half_rn( -q2 - e2 );
+    unsigned* const pu = reinterpret_cast<unsigned*>( sm.u );
+    unsigned* const pv = reinterpret_cast<unsigned*>( sm.v );
+    unsigned* const px = reinterpret_cast<unsigned*>( sm.x );
+    unsigned* const py = reinterpret_cast<unsigned*>( sm.y );
+    unsigned* const px2 = reinterpret_cast<unsigned*>( sm.x2 );
+    unsigned* const py2 = reinterpret_cast<unsigned*>( sm.y2 );
+    unsigned* const ptc = reinterpret_cast<unsigned*>( sm.tc );
+    unsigned* const pH = reinterpret_cast<unsigned*>( sm.H );
+    // reversed query, two copies one element apart so that every row finds its pairs 32-bit aligned
+    for( int j = lane; j < W; j += 32 )
+    {
+        const int a = j - 2, b = j - 1; // qa[j] = rev[j-2], qb[j] = qa[j+1] = rev[j-1]
+        sm.qa[ j ] = __int2half_rn( ( a >= 0 && a < qlen ) ? seq.Q( qlen - 1 - a ) : 0 );
+        sm.qb[ j ] = __int2half_rn( ( b >= 0 && b < qlen ) ? seq.Q( qlen - 1 - b ) : 0 );
+    }
+    int inited_end = 0;
+    long long cells = 0;
+    int prevB = NONE_T;
+    unsigned char* rowBase = tb; // tb + r * ncol16
+    for( int r = 0; r < nrows; ++r, rowBase += ncol16 )
+    {
+        const int st0 = max( 0, r - qlen + 1 ), en0 = min( tlen - 1, r ); // the band term is inactive while r <= w
+        if( r > w )
+            return false;
+        cells += en0 - st0 + 1;
+        if( inited_end <= en0 + 1 )
+        { // target codes of the columns entering the window
+            const int idx = inited_end + lane;
+            sm.tc[ idx & M ] = __int2half_rn( idx < tlen ? seq.T( idx ) : 0 );
+            inited_end += 32;
+        }
+        const int first_col = r == 0 ? -q - e : r < P.long_thres ? -e : r == P.long_thres ? P.long_diff : -e2;
+        if( en0 == r && lane == 0 )
+        {
+            sm.y[ r & M ] = init6;
+            sm.y2[ r & M ] = init25;
+            sm.u[ r & M ] = __int2half_rn( first_col );
+        }
+        const int p0 = st0 & ~1;
+        // left neighbour of the first pair (kswcpp_core.h:562-579)
+        __half cxh = init6, cx2h = init25, cvh = __int2half_rn( first_col );
+        if( p0 > 0 )
+            cxh = sm.x[ ( p0 - 1 ) & M ], cx2h = sm.x2[ ( p0 - 1 ) & M ], cvh = sm.v[ ( p0 - 1 ) & M ];
+        unsigned cX = (unsigned)__half_as_ushort( cxh ) << 16, cX2 = (unsigned)__half_as_ushort( cx2h ) << 16,
+                 cV = (unsigned)__half_as_ushort( cvh ) << 16;
+        // old H left of en0, read before the pass updates it (:194-195); row 0: H[0] = v[0] - (q + e) (:247)
+        const int hprev = r == 0 ? -qe : ( en0 > 0 ? (int)sm.H[ ( en0 - 1 ) & M ] : (int)sm.H[ en0 & M ] );
+        const unsigned hprev2 = ( (unsigned)hprev & 0xFFFFu ) * 0x10001u;
+        __syncwarp( );
+        const int c = qlen - 1 - r; // reversed-query index of column t is t + c
+        const unsigned* const pq = reinterpret_cast<const unsigned*>( ( c & 1 ) ? sm.qb : sm.qa );
+        const int qsh = ( ( c & 1 ) ? c + 1 : c + 2 ); // element offset into the chosen copy (even)
+        unsigned char* const rowp = rowBase - ( st0 & ~15 );
+        const bool bBound = ( r & 1 ) || r + 2 >= nrows || true;
+        unsigned m2 = 0x80008000u, hb2 = 0x80008000u;
+        unsigned term2 = 0; // scM * (qlen - 1 - r + t) for the two cells of this lane
+        {
+            const int t0 = p0 + 2 * lane;
+            const int a0 = scM * ( c + t0 ), a1 = a0 + scM;
+            term2 = ( (unsigned)a0 & 0xFFFFu ) | ( (unsigned)a1 << 16 );
+        }
+        const unsigned termStep = ( ( (unsigned)( scM * 64 ) & 0xFFFFu ) * 0x10001u );
+        (void)bBound;
+        for( int base = p0; base <= en0; base += 64 )
+        {
+            const int t0 = base + 2 * lane;
+            const int kk = ( t0 & M ) >> 1; // pair index in the window
+            const unsigned xo = px[ kk ], vo = pv[ kk ], x2o = px2[ kk ];
+            const __half2 ut = u2h( pu[ kk ] ), yo = u2h( py[ kk ] ), y2o = u2h( py2[ kk ] );
+            const unsigned hOld = pH[ kk ];
+            const __half2 tcp = u2h( ptc[ kk ] );
+            const __half2 qp = u2h( pq[ ( ( t0 + qsh ) & M ) >> 1 ] );
+            unsigned upx = __shfl_up_sync( FULL, xo, 1 ), upv = __shfl_up_sync( FULL, vo, 1 ),
+                     upx2 = __shfl_up_sync( FULL, x2o, 1 );
+            if( lane == 0 )
+                upx = cX, upv = cV, upx2 = cX2;
+            if( base + 64 <= en0 )
+                cX = __shfl_sync( FULL, xo, 31 ), cV = __shfl_sync( FULL, vo, 31 ), cX2 = __shfl_sync( FULL, x2o, 31 );
+            const __half2 xt1 = u2h( __byte_perm( upx, xo, 0x5432 ) ), vt1 = u2h( __byte_perm( upv, vo, 0x5432 ) ),
+                          x2t1 = u2h( __byte_perm( upx2, x2o, 0x5432 ) );
+            // score profile (:591-616): N scores -e2
+            unsigned z0 = sel2( __heq2_mask( tcp, qp ), uMatch, uMis );
+            z0 = sel2( __hge2_mask( __hmax2( tcp, qp ), hFour ), uN, z0 );
+            __half2 z = u2h( z0 );
+            const __half2 a = __hadd2( xt1, vt1 ), b = __hadd2( yo, ut ), a2 = __hadd2( x2t1, vt1 ),
+                          b2 = __hadd2( y2o, ut );
+            unsigned d;
+            if( LEFT )
+            {
+                d = __hgt2_mask( a, z ) & 0x00010001u;
+                z = __hmax2( z, a );
+                d = sel2( __hgt2_mask( b, z ), 0x00020002u, d );
+                z = __hmax2( z, b );
+                d = sel2( __hgt2_mask( a2, z ), 0x00030003u, d );
+                z = __hmax2( z, a2 );
+                d = sel2( __hgt2_mask( b2, z ), 0x00040004u, d );
+                z = __hmax2( z, b2 );
+            }
+            else
+            { // right-aligned: ties go to the gap, state 4 is never recorded (:693-699)
+                d = __hge2_mask( a, z ) & 0x00010001u;
+                z = __hmax2( z, a );
+                d = sel2( __hge2_mask( b, z ), 0x00020002u, d );
+                z = __hmax2( z, b );
+                d = sel2( __hge2_mask( a2, z ), 0x00030003u, d );
+                z = __hmax2( z, a2 );
+                z = __hmax2( z, b2 );
+            }
+            z = __hmin2( z, hMatch );
+            const __half2 un = __hsub2( z, vt1 ), vn = __hsub2( z, ut );
+            // x' = max(a - (z - q), 0) - (q + e) = max(a - z - e, -q - e); the continuation flag is a - z > -q
+            const __half2 az = __hsub2( a, z ), bz = __hsub2( b, z ), a2z = __hsub2( a2, z ), b2z = __hsub2( b2, z );
+            if( LEFT )
+            {
+                d |= __hgt2_mask( az, hNegQ ) & 0x00080008u;
+                d |= __hgt2_mask( bz, hNegQ ) & 0x00100010u;
+                d |= __hgt2_mask( a2z, hNegQ2 ) & 0x00200020u;
+                d |= __hgt2_mask( b2z, hNegQ2 ) & 0x00400040u;
+            }
+            else
+            {
+                d |= __hge2_mask( az, hNegQ ) & 0x00080008u;
+                d |= __hge2_mask( bz, hNegQ ) & 0x00100010u;
+                d |= __hge2_mask( a2z, hNegQ2 ) & 0x00200020u;
+                d |= __hge2_mask( b2z, hNegQ2 ) & 0x00400040u;
+            }
+            // H row (calcMaxScore): interior columns add v, the last column adds u to its left neighbour's old H
+            const int de = en0 - t0; // 0: the low cell is en0, 1: the high cell
+            const unsigned me = (unsigned)de < 2u ? ( 0xFFFFu << ( de << 4 ) ) : 0u;
+            const unsigned add = h2u( __hadd2( u2h( sel2( en0 > 0 ? me : 0u, h2u( un ), h2u( vn ) ) ), hBias ) ) &
+                                 0x03FF03FFu; // 512 + value per half
+            const unsigned h = __vsub2( __vadd2( sel2( me, hprev2, hOld ), add ), 0x02000200u );
+            if( t0 <= en0 )
+            {
+                pu[ kk ] = h2u( un );
+                pv[ kk ] = h2u( vn );
+                px[ kk ] = h2u( __hmax2( __hsub2( az, hE ), hNegQE ) );
+                py[ kk ] = h2u( __hmax2( __hsub2( bz, hE ), hNegQE ) );
+                px2[ kk ] = h2u( __hmax2( __hsub2( a2z, hE2 ), hNegQE2 ) );
+                py2[ kk ] = h2u( __hmax2( __hsub2( b2z, hE2 ), hNegQE2 ) );
+                pH[ kk ] = h;
+                *reinterpret_cast<unsigned short*>( rowp + t0 ) = (unsigned short)__byte_perm( d, 0, 0x4420 );
+            }
+            // in-band cells only: row maximum and the early-stop bound
+            const unsigned vm = ( ( t0 >= st0 && t0 <= en0 ) ? 0xFFFFu : 0u ) | ( t0 + 1 <= en0 ? 0xFFFF0000u : 0u );
+            const unsigned hm = sel2( vm, h, 0x80008000u );
+            m2 = __vmaxs2( m2, hm );
+            hb2 = __vmaxs2( hb2, __vadd2( hm, term2 & vm ) );
+            term2 = __vadd2( term2, termStep );
+        }
+        const int mlo = (short)( m2 & 0xFFFFu ), mhi = (int)m2 >> 16;
+        const int max_H = __reduce_max_sync( FULL, max( mlo, mhi ) );
+        __syncwarp( );
+        int max_t = en0;
+        // the position is consumed only by a new maximum or by a z-drop test that can fire (l >= 0)
+        if( max_H > ez.max || ( zdrop >= 0 && ez.max - max_H > zdrop ) )
+            max_t = ksw_p2_argmax( sm.H, M, st0, en0, lane );
+        // ksw_apply_zdrop (:22-44)
+        if( max_H > ez.max )
+            ez.max = max_H, ez.max_t = max_t, ez.max_q = r - max_t;
+        else if( max_t >= ez.max_t && r - max_t >= ez.max_q )
+        {
+            const int tl = max_t - ez.max_t, ql = ( r - max_t ) - ez.max_q;
+            const int l = tl > ql ? tl - ql : ql - tl;
+            if( zdrop >= 0 && ez.max - max_H > zdrop + l * e2 )
+            {
+                ez.zdropped = 1;
+                break;
+            }
+        }
+        {
+            const int blo = (short)( hb2 & 0xFFFFu ), bhi = (int)hb2 >> 16;
+            const int B = __reduce_max_sync( FULL, max( blo, bhi ) );
+            if( r >= qlen && prevB != NONE_T )
+            {
+                const long long j = r + 1;
+                const long long g1 = q + (long long)e * j, g2 = q2 + (long long)e2 * j;
+                const long long T = (long long)scM * qlen - ( g1 < g2 ? g1 : g2 );
+                const long long bound = max( (long long)max( B, prevB ), T );
+                if( bound <= (long long)ez.max )
+                    break;
+            }
+            prevB = B;
+        }
+    }
+    ez.cells = cells;
+    __syncwarp( );
+    return true;
+}
+
+// bytes of shared memory per warp: the scalar window and, for the narrow bins, the packed one share the space
+template <int W> struct KswSmemBytes
+{
+    static constexpr bool kPacked = W <= 512;
+    static constexpr size_t kScalar = sizeof( KswSmem<W> );
+    static constexpr size_t kP2 = kPacked ? sizeof( KswSmemP < W <= 512 ? W : 2 > ) : 0;
+    static constexpr size_t value = ( ( kScalar > kP2 ? kScalar : kP2 ) + 15 ) / 16 * 16;
+};
+
 template <int W>
 __device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int tlen, int w, int zdrop, int flag,
                           bool bEarlyStop, KswSmem<W>& sm, unsigned char* __restrict__ tb, KswOut& ez )
@@ -481,6 +793,26 @@ __device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int
         return;
     if( w < 0 )
         w = tlen > qlen ? tlen : qlen;
+    const bool bLeft = !( flag & MA_KSW_RIGHT );
+    if constexpr( KswSmemBytes<W>::kPacked )
+    { // packed fast path: early-stop extensions in int16 score mode whose int8 arithmetic cannot wrap
+        const int iSize = qlen > tlen ? qlen : tlen;
+        const bool is16 = !( (long long)iSize * P.min16 < -32768 || (long long)iSize * P.match > 32767 );
+        if( bEarlyStop && w >= qlen && is16 && qlen + 4 <= W && ( qlen < tlen ? qlen : tlen ) + 40 <= W &&
+            ksw_p2_params_ok( P ) )
+        {
+            KswSmemP<W>& sp = reinterpret_cast<KswSmemP<W>&>( sm );
+            const bool ok = bLeft ? ksw_rows_p2<W, true>( P, seq, qlen, tlen, w, zdrop, sp, tb, ez )
+                                  : ksw_rows_p2<W, false>( P, seq, qlen, tlen, w, zdrop, sp, tb, ez );
+            if( ok )
+                return;
+            ez.max_q = ez.max_t = ez.mqe_t = ez.mte_q = -1;
+            ez.max = 0;
+            ez.score = ez.mqe = ez.mte = (int)0x80000000;
+            ez.zdropped = 0, ez.cells = 0;
+            __syncwarp( );
+        }
+    }
     // stage the query in shared memory when it fits
     const bool qStaged = qlen <= KswSmem<W>::QC;
     if( qStaged )
@@ -489,7 +821,6 @@ __device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int
             sm.qc[ i ] = (unsigned char)seq.Q( i );
         __syncwarp( );
     }
-    const bool bLeft = !( flag & MA_KSW_RIGHT );
     // FAST mode needs the query staged (narrow problems) and a band that cannot limit before the matrix does
     if( bEarlyStop && qStaged && w >= qlen )
     {
@@ -567,7 +898,7 @@ template <int W> __global__ void __launch_bounds__( 256, 3 ) ksw_batch_kernel( K
 {
     extern __shared__ __align__( 16 ) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    KswSmem<W>& sm = reinterpret_cast<KswSmem<W>*>( smem_raw )[ warp ];
+    KswSmem<W>& sm = *reinterpret_cast<KswSmem<W>*>( smem_raw + (size_t)warp * KswSmemBytes<W>::value );
     const long long gw = (long long)blockIdx.x * ( blockDim.x >> 5 ) + warp;
     unsigned char* tb = A.tb + gw * A.tb_stride;
     unsigned int* cs = A.cigscratch + gw * A.cigscratch_stride;

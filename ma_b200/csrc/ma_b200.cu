@@ -55,6 +55,7 @@ struct ma_b200_ctx
     int64_t n_reads = 0, reads_bytes = 0;
     int max_read_len = 0;
     int stage_done = 0;
+    bool ksw_extension_only = false; // ma_b200_ksw_set_extension_only
     DevBuf<unsigned char> reads;
     DevBuf<long long> read_off;
     DevBuf<ReadInfo> info;
@@ -227,7 +228,7 @@ static const int kKswWindows[] = { 128, 256, 512, 1024, 2048 };
 template <int W> static long long ksw_bin_grid( ma_b200_ctx* ctx, const KswHostBin& bin, long long tbBudget )
 {
     const int warpsPerCta = 8;
-    const size_t smem = sizeof( KswSmem<W> ) * warpsPerCta;
+    const size_t smem = KswSmemBytes<W>::value * warpsPerCta;
     MA_CUDA( cudaFuncSetAttribute( ksw_batch_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) );
     int perSm = 0;
     MA_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, ksw_batch_kernel<W>, 256, smem ) );
@@ -243,7 +244,7 @@ template <int W> static long long ksw_bin_grid( ma_b200_ctx* ctx, const KswHostB
 
 template <int W> static void launch_ksw_bin( ma_b200_ctx* ctx, const KswBatchArgs& A, long long grid )
 {
-    const size_t smem = sizeof( KswSmem<W> ) * 8;
+    const size_t smem = KswSmemBytes<W>::value * 8;
     ksw_batch_kernel<W><<<(unsigned)grid, 256, smem, ctx->stream>>>( A );
     MA_CUDA( cudaGetLastError( ) );
     ctx->launches++;
@@ -285,6 +286,14 @@ static void ksw_plan( ma_b200_ctx* ctx, int64_t n, const ma_b200_ksw_task* tasks
     ctx->ksw_cigar_bound = bound;
 }
 
+extern "C" int ma_b200_ksw_set_extension_only( ma_b200_ctx* ctx, int32_t on )
+{
+    if( !ctx )
+        return MA_B200_EINVAL;
+    ctx->ksw_extension_only = on != 0;
+    return MA_B200_OK;
+}
+
 extern "C" int ma_b200_ksw_upload( ma_b200_ctx* ctx, int64_t n, const ma_b200_ksw_task* tasks, const uint8_t* seq,
                                    int64_t seq_bytes )
 {
@@ -310,7 +319,7 @@ extern "C" int ma_b200_ksw_upload( ma_b200_ctx* ctx, int64_t n, const ma_b200_ks
         std::vector<KswTask> vTasks( (size_t)n );
         memcpy( vTasks.data( ), tasks, n * sizeof( KswTask ) );
         for( auto& t : vTasks )
-            t.tag = 0;
+            t.tag = ( ctx->ksw_extension_only && ( t.flag & MA_KSW_EXTZ_ONLY ) ) ? MA_TASK_EARLYSTOP : 0;
         MA_CUDA( cudaMemcpyAsync( ctx->ksw_tasks.p, vTasks.data( ), n * sizeof( KswTask ), cudaMemcpyHostToDevice,
                                   ctx->stream ) );
         MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
@@ -780,11 +789,12 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
         // ---------------- stage 1: seeding
         const int maxL = ctx->max_read_len;
         const int list_cap = std::min( maxL + 2, 1024 ), fseg_cap = std::min( 2 * maxL + 8, 1 << 16 );
-        int grid = full_grid( ctx, seed_kernel, 128, n );
+        const int SB = MA_SEED_BLOCK; // seed_kernel_rec runs with the same block size
+        int grid = full_grid( ctx, seed_kernel, SB, n );
         const size_t perThread = (size_t)( 2 * list_cap + 8 ) * sizeof( SegRec ) + (size_t)fseg_cap * sizeof( FSeg );
-        grid = (int)std::max<size_t>( 1, std::min<size_t>( grid, ( (size_t)8 << 30 ) / ( perThread * 128 ) ) );
-        ctx->lists.reserve( (size_t)grid * 128 * ( 2 * list_cap + 8 ) );
-        ctx->fsegs.reserve( (size_t)grid * 128 * fseg_cap );
+        grid = (int)std::max<size_t>( 1, std::min<size_t>( grid, ( (size_t)8 << 30 ) / ( perThread * SB ) ) );
+        ctx->lists.reserve( (size_t)grid * SB * ( 2 * list_cap + 8 ) );
+        ctx->fsegs.reserve( (size_t)grid * SB * fseg_cap );
         ctx->dbg_cap = keep_segments > 0 ? keep_segments : 0;
         if( ctx->dbg_cap )
         {
@@ -807,9 +817,9 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
             // default: the convergent state-machine kernel; MA_B200_SEED_SM=0 selects the recursive formulation (A/B)
             static const bool bSM = !( getenv( "MA_B200_SEED_SM" ) && atoi( getenv( "MA_B200_SEED_SM" ) ) == 0 );
             if( bSM )
-                seed_kernel<<<grid, 128, 0, s>>>( A );
+                seed_kernel<<<grid, SB, 0, s>>>( A );
             else
-                seed_kernel_rec<<<grid, 128, 0, s>>>( A );
+                seed_kernel_rec<<<grid, SB, 0, s>>>( A );
             MA_CUDA( cudaGetLastError( ) );
             ctx->launches++;
             read_ctrl( ctx );

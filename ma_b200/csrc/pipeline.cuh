@@ -182,16 +182,31 @@ __global__ void __launch_bounds__( 128 ) seed_kernel_rec( SeedKernelArgs A )
 
 // Every lane runs the resumable SeederSM of its current read; all lanes of a warp meet at the single
 // extend_backward call site, so the warp always has up to 64 independent 64-byte occ-block loads in flight.
-__global__ void __launch_bounds__( 128 ) seed_kernel( SeedKernelArgs A )
+// The SMEM interval list of every thread lives in shared memory (first MA_SEED_K entries, 20 bytes each, see SegList);
+// only longer lists touch the thread's global scratch.
+#ifndef MA_SEED_BLOCK
+#define MA_SEED_BLOCK 64
+#endif
+#ifndef MA_SEED_K
+#define MA_SEED_K 12
+#endif
+#ifndef MA_SEED_MINB
+#define MA_SEED_MINB 1
+#endif
+__global__ void __launch_bounds__( MA_SEED_BLOCK, MA_SEED_MINB ) seed_kernel( SeedKernelArgs A )
 {
+    __shared__ U4 sPk[ MA_SEED_K * MA_SEED_BLOCK ];
+    __shared__ int sSz[ MA_SEED_K * MA_SEED_BLOCK ];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     SegRec* la = A.lists + (size_t)tid * ( 2 * A.list_cap + 8 );
     FSeg* fs = A.fsegs + (size_t)tid * A.fseg_cap;
     unsigned long long nExtLocal = 0, nDropped = 0;
     SeedSink sink( A.P, fs, A.fseg_cap, nullptr, A.dbg_cap );
     // the first 2 x 40 ints of the thread's list scratch hold the interval stack
-    SeederSM<SeedSink> S( A.I, A.P, A.reads, 0, SeedScratch{ la + 8, la + 8 + A.list_cap, A.list_cap }, sink,
-                          (int*)la );
+    SeederSM<SeedSink> S( A.I, A.P, A.reads, 0,
+                          SegList{ sPk + threadIdx.x, sSz + threadIdx.x, MA_SEED_BLOCK, MA_SEED_K, la + 8,
+                                   MA_SEED_K + 2 * A.list_cap },
+                          sink, (int*)la );
     int read = -1; // -1: needs a new read, -2: queue exhausted
     int L = 0;
     while( true )

@@ -128,8 +128,11 @@ int main( int argc, char** argv )
         { // the state-machine formulation used by seed_kernel must emit exactly the same segments
             AllSegSink sink2;
             int stk[ 80 ];
-            SeederSM<AllSegSink> S2( I, SP, q.data( ), (int)q.size( ), SeedScratch{ la.data( ), lb.data( ), 600 }, sink2,
-                                     stk );
+            // a short "shared" part (stride 3, like the interleaved device layout) so that both halves of SegList run
+            U4 pk[ 3 * 6 ];
+            int sz[ 3 * 6 ];
+            SeederSM<AllSegSink> S2( I, SP, q.data( ), (int)q.size( ),
+                                     SegList{ pk + 1, sz + 1, 3, 6, la.data( ), 606 }, sink2, stk );
             S2.run( );
             size_t sum2 = 0;
             for( auto& s : sink2.v )

@@ -107,3 +107,76 @@ def test_linearity_property_large_batch(gpu_ctx):
     assert np.array_equal(res["score"], 2 * tasks["qlen"])
     assert (res["n_cigar"] == 1).all()
     assert np.array_equal(cig[res["cigar_off"]], (tasks["qlen"].astype(np.uint32) << 4))
+
+
+# ---- early-termination mode of extension tasks (what the alignment path runs; packed half2 kernel when it applies)
+EXT_FIELDS = ["max", "max_q", "max_t", "n_cigar"]
+
+
+def check_extension_only(ctx, pairs):
+    """max / max_q / max_t / CIGAR must equal the reference's full computation; returns the cells the GPU processed."""
+    tasks, seq = api.pack_ksw_tasks(pairs)
+    ctx.ksw_set_extension_only(True)
+    try:
+        res, cig = ctx.ksw_batch(tasks, seq)
+    finally:
+        ctx.ksw_set_extension_only(False)
+    assert (res["status"] == 0).all()
+    full = 0
+    for i, (w, zd, fl, q, t) in enumerate(pairs):
+        exp, ecig, ecells = H.oracle_ksw(q, t, w, zd, fl)
+        if exp["zdropped"] == 0 and exp["mqe"] > exp["max"]:
+            continue  # reach_end back-trace: not an early-stop caller's case (never occurs: mqe <= max)
+        for k in EXT_FIELDS:
+            assert int(res[k][i]) == exp[k], (i, k, int(res[k][i]), exp[k], len(q), len(t), w, zd, fl)
+        got = cig[res["cigar_off"][i]:res["cigar_off"][i] + res["n_cigar"][i]]
+        assert np.array_equal(got, ecig), (i, got[:6], ecig[:6], len(q), len(t), w, zd, fl)
+        full += ecells
+    return int(res["cells"].sum()), full
+
+
+def _ext_pairs(n, seed, qmax, tmin, tmax, err, w=512, zdrop=200, with_n=False):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pairs = []
+    for i in range(n):
+        t = rng.integers(0, 4, size=int(rng.integers(tmin, tmax)), dtype=np.uint8)
+        q = dpgen.mutate(rng, t[:int(rng.integers(1, qmax))], err)
+        if len(q) == 0:
+            q = t[:1].copy()
+        if with_n and i % 3 == 0:
+            q = q.copy()
+            q[rng.integers(0, len(q), size=max(1, len(q) // 10))] = 4
+            t = t.copy()
+            t[rng.integers(0, min(len(t), 2 * len(q)), size=3)] = 4
+        pairs.append((w, zdrop, dpgen.EXT if i % 2 else dpgen.EXT_RIGHT, q, t))
+    return pairs
+
+
+def test_extension_only_illumina_shapes(gpu_ctx):
+    done, full = check_extension_only(gpu_ctx, _ext_pairs(400, 77, 150, 950, 1060, 0.03))
+    assert done < full  # early termination really cuts rows
+
+
+def test_extension_only_noisy_and_n(gpu_ctx):
+    check_extension_only(gpu_ctx, _ext_pairs(300, 78, 200, 300, 1100, 0.15, with_n=True))
+    check_extension_only(gpu_ctx, _ext_pairs(200, 79, 60, 20, 120, 0.3, with_n=True))
+
+
+def test_extension_only_unrelated_and_tiny(gpu_ctx):
+    rng = np.random.Generator(np.random.PCG64(80))
+    pairs = []
+    for i in range(200):
+        q = rng.integers(0, 4, size=int(rng.integers(1, 120)), dtype=np.uint8)
+        t = rng.integers(0, 4, size=int(rng.integers(1, 400)), dtype=np.uint8)
+        pairs.append((512, 200 if i % 4 else -1, dpgen.EXT if i % 2 else dpgen.EXT_RIGHT, q, t))
+    check_extension_only(gpu_ctx, pairs)
+
+
+def test_extension_only_band_limited_falls_back(gpu_ctx):
+    """w < qlen or a band that starts to limit: the packed/fast modes must hand over to the exact mode."""
+    check_extension_only(gpu_ctx, _ext_pairs(120, 81, 300, 350, 700, 0.05, w=32))
+    check_extension_only(gpu_ctx, _ext_pairs(60, 82, 400, 1500, 2500, 0.05, w=100))
+
+
+def test_extension_only_long_int32_mode(gpu_ctx):
+    check_extension_only(gpu_ctx, _ext_pairs(6, 83, 3000, 20000, 21000, 0.05))
