@@ -72,7 +72,7 @@ template <int W> struct KswSmem
 __device__ inline int ksw_backtrack( const unsigned char* tb, int ncol16, int qlen, int tlen, int w, int i0, int j0,
                                      unsigned int* cig, int cap )
 {
-    long long i = i0, j = j0;
+    int i = i0, j = j0; // qlen + tlen < 2^31
     int state = 0, n = 0;
     unsigned int cur = 0; // current run: len<<4|op, 0 = none
     auto push = [ & ]( unsigned int op, unsigned int len ) {
@@ -91,16 +91,17 @@ __device__ inline int ksw_backtrack( const unsigned char* tb, int ncol16, int ql
     };
     while( i >= 0 && j >= 0 )
     {
-        long long r = i + j;
-        int st0, en0;
-        ksw_band( r, qlen, tlen, w, st0, en0 );
-        int off = st0 & ~15, off_end = en0 | 15;
+        const int r = i + j;
+        // band limits of row r (kswcpp_core.h:541-548)
+        const int st0 = max( max( 0, r - qlen + 1 ), ( r - w + 1 ) >> 1 );
+        const int en0 = min( min( tlen - 1, r ), ( r + w ) >> 1 );
+        const int off = st0 & ~15, off_end = en0 | 15;
         int force_state = -1;
         if( i < off )
             force_state = 2;
         if( i > off_end )
             force_state = 1;
-        unsigned int tmp = force_state < 0 ? tb[ r * ncol16 + i - off ] : 0;
+        unsigned int tmp = force_state < 0 ? tb[ (long long)r * ncol16 + ( i - off ) ] : 0;
         if( state == 0 )
             state = tmp & 7;
         else if( !( tmp >> ( state + 2 ) & 1 ) )
@@ -492,6 +493,8 @@ template <int W> struct KswSmemP
 {
     __half u[ W ], v[ W ], x[ W ], y[ W ], x2[ W ], y2[ W ], tc[ W ];
     short H[ W ];
+    short Hs[ W ]; // H row of the row that holds the running maximum
+    // codes are stored as the halves with bit pattern code << 10 (distinct positive normals, ordered like the codes)
     __half qa[ W ], qb[ W ]; // qa[j + 2] = code of q[qlen-1-j]; qb[j] = qa[j + 1]
 };
 
@@ -578,9 +581,15 @@ __device__ __forceinline__ bool ksw_rows_p2( const KswScore& P, const SeqAccess&
     const int ncol16 = ksw_ncol16( qlen, tlen, w );
     const int nrows = qlen + tlen - 1;
     const __half2 hMatch = h2i( scM ), hNegQ = h2i( -q ), hNegQ2 = h2i( -q2 ), hNegQE = h2i( -q - e ),
-                  hNegQE2 = h2i( -q2 - e2 ), hE = h2i( e ), hE2 = h2i( e2 ), hFour = h2i( 4 ), hBias = h2i( 1536 );
+                  hNegQE2 = h2i( -q2 - e2 ), hE = h2i( e ), hE2 = h2i( e2 ), hBias = h2i( 1536 );
+    const __half2 hCodeN = u2h( 0x10001000u ); // base code c is stored as the half with bits c << 10 (see p2_code)
     const unsigned uMatch = h2u( hMatch ), uMis = h2u( h2i( P.mismatch ) ), uN = h2u( h2i( -e2 ) );
-    const __half init6 = __int2half_rn( -q - e ), init25 = __int2half_rn( -q2 - e2 );
+    const unsigned short init6 = __half_as_ushort( __int2half_rn( -q - e ) ),
+                         init25 = __half_as_ushort( __int2half_rn( -q2 - e2 ) );
+    // first-column values of the rows (kswcpp_core.h:562-579): row 0, rows below / at / above the long-gap threshold
+    const unsigned short fc0 = init6, fc1 = __half_as_ushort( __int2half_rn( -e ) ),
+                         fc2 = __half_as_ushort( __int2half_rn( P.long_diff ) ),
+                         fc3 = __half_as_ushort( __int2half_rn( -e2 ) );
     unsigned* const pu = reinterpret_cast<unsigned*>( sm.u );
     unsigned* const pv = reinterpret_cast<unsigned*>( sm.v );
     unsigned* const px = reinterpret_cast<unsigned*>( sm.x );
@@ -589,64 +598,75 @@ __device__ __forceinline__ bool ksw_rows_p2( const KswScore& P, const SeqAccess&
     unsigned* const py2 = reinterpret_cast<unsigned*>( sm.y2 );
     unsigned* const ptc = reinterpret_cast<unsigned*>( sm.tc );
     unsigned* const pH = reinterpret_cast<unsigned*>( sm.H );
+    unsigned* const pHs = reinterpret_cast<unsigned*>( sm.Hs );
+    unsigned short* const su = reinterpret_cast<unsigned short*>( sm.u );
+    unsigned short* const sv = reinterpret_cast<unsigned short*>( sm.v );
+    unsigned short* const sx = reinterpret_cast<unsigned short*>( sm.x );
+    unsigned short* const sy = reinterpret_cast<unsigned short*>( sm.y );
+    unsigned short* const sx2 = reinterpret_cast<unsigned short*>( sm.x2 );
+    unsigned short* const sy2 = reinterpret_cast<unsigned short*>( sm.y2 );
+    unsigned short* const stc = reinterpret_cast<unsigned short*>( sm.tc );
     // reversed query, two copies one element apart so that every row finds its pairs 32-bit aligned
-    for( int j = lane; j < W; j += 32 )
     {
-        const int a = j - 2, b = j - 1; // qa[j] = rev[j-2], qb[j] = qa[j+1] = rev[j-1]
-        sm.qa[ j ] = __int2half_rn( ( a >= 0 && a < qlen ) ? seq.Q( qlen - 1 - a ) : 0 );
-        sm.qb[ j ] = __int2half_rn( ( b >= 0 && b < qlen ) ? seq.Q( qlen - 1 - b ) : 0 );
+        unsigned short* const qa = reinterpret_cast<unsigned short*>( sm.qa );
+        unsigned short* const qb = reinterpret_cast<unsigned short*>( sm.qb );
+        for( int j = lane; j < W; j += 32 )
+        { // qa[j] = rev[j-2], qb[j] = qa[j+1] = rev[j-1], rev[j] = q[qlen-1-j]
+            const int a = j - 2, b = j - 1;
+            qa[ j ] = (unsigned short)( ( ( a >= 0 && a < qlen ) ? seq.Q( qlen - 1 - a ) : 0 ) << 10 );
+            qb[ j ] = (unsigned short)( ( ( b >= 0 && b < qlen ) ? seq.Q( qlen - 1 - b ) : 0 ) << 10 );
+        }
     }
     int inited_end = 0;
-    long long cells = 0;
+    unsigned cells = 0; // < W * 2^16
     int prevB = NONE_T;
+    // the row that holds ez.max: its H row is kept (sm.Hs) and the position is resolved only when it is consumed
+    bool pend = false;
+    int bR = 0, bSt0 = 0, bEn0 = 0;
+    const int T0 = scM * qlen;
     unsigned char* rowBase = tb; // tb + r * ncol16
     for( int r = 0; r < nrows; ++r, rowBase += ncol16 )
     {
         const int st0 = max( 0, r - qlen + 1 ), en0 = min( tlen - 1, r ); // the band term is inactive while r <= w
         if( r > w )
             return false;
-        cells += en0 - st0 + 1;
+        cells += (unsigned)( en0 - st0 + 1 );
         if( inited_end <= en0 + 1 )
         { // target codes of the columns entering the window
             const int idx = inited_end + lane;
-            sm.tc[ idx & M ] = __int2half_rn( idx < tlen ? seq.T( idx ) : 0 );
+            stc[ idx & M ] = (unsigned short)( ( idx < tlen ? seq.T( idx ) : 0 ) << 10 );
             inited_end += 32;
         }
-        const int first_col = r == 0 ? -q - e : r < P.long_thres ? -e : r == P.long_thres ? P.long_diff : -e2;
+        const unsigned short fc = r == 0 ? fc0 : r < P.long_thres ? fc1 : r == P.long_thres ? fc2 : fc3;
         if( en0 == r && lane == 0 )
-        {
-            sm.y[ r & M ] = init6;
-            sm.y2[ r & M ] = init25;
-            sm.u[ r & M ] = __int2half_rn( first_col );
-        }
+            sy[ r & M ] = init6, sy2[ r & M ] = init25, su[ r & M ] = fc;
         const int p0 = st0 & ~1;
-        // left neighbour of the first pair (kswcpp_core.h:562-579)
-        __half cxh = init6, cx2h = init25, cvh = __int2half_rn( first_col );
+        // left neighbour of the first pair (kswcpp_core.h:562-579), kept in the high half
+        unsigned cX = (unsigned)init6 << 16, cX2 = (unsigned)init25 << 16, cV = (unsigned)fc << 16;
         if( p0 > 0 )
-            cxh = sm.x[ ( p0 - 1 ) & M ], cx2h = sm.x2[ ( p0 - 1 ) & M ], cvh = sm.v[ ( p0 - 1 ) & M ];
-        unsigned cX = (unsigned)__half_as_ushort( cxh ) << 16, cX2 = (unsigned)__half_as_ushort( cx2h ) << 16,
-                 cV = (unsigned)__half_as_ushort( cvh ) << 16;
+        {
+            const int kp = ( p0 - 1 ) & M;
+            cX = (unsigned)sx[ kp ] << 16, cX2 = (unsigned)sx2[ kp ] << 16, cV = (unsigned)sv[ kp ] << 16;
+        }
         // old H left of en0, read before the pass updates it (:194-195); row 0: H[0] = v[0] - (q + e) (:247)
-        const int hprev = r == 0 ? -qe : ( en0 > 0 ? (int)sm.H[ ( en0 - 1 ) & M ] : (int)sm.H[ en0 & M ] );
+        const int hprev = r == 0 ? -qe : (int)sm.H[ ( en0 - ( en0 > 0 ? 1 : 0 ) ) & M ];
         const unsigned hprev2 = ( (unsigned)hprev & 0xFFFFu ) * 0x10001u;
         __syncwarp( );
         const int c = qlen - 1 - r; // reversed-query index of column t is t + c
         const unsigned* const pq = reinterpret_cast<const unsigned*>( ( c & 1 ) ? sm.qb : sm.qa );
-        const int qsh = ( ( c & 1 ) ? c + 1 : c + 2 ); // element offset into the chosen copy (even)
+        const int qsh = c + 2 - ( c & 1 ); // element offset into the chosen copy (even)
         unsigned char* const rowp = rowBase - ( st0 & ~15 );
-        const bool bBound = ( r & 1 ) || r + 2 >= nrows || true;
+        const unsigned meEn = en0 > 0 ? 0xFFFFFFFFu : 0u;
         unsigned m2 = 0x80008000u, hb2 = 0x80008000u;
-        unsigned term2 = 0; // scM * (qlen - 1 - r + t) for the two cells of this lane
+        int t0 = p0 + 2 * lane;
+        unsigned term2; // scM * (qlen - 1 - r + t) for the two cells of this lane
         {
-            const int t0 = p0 + 2 * lane;
-            const int a0 = scM * ( c + t0 ), a1 = a0 + scM;
-            term2 = ( (unsigned)a0 & 0xFFFFu ) | ( (unsigned)a1 << 16 );
+            const int a0 = scM * ( c + t0 );
+            term2 = ( (unsigned)a0 & 0xFFFFu ) | ( (unsigned)( a0 + scM ) << 16 );
         }
-        const unsigned termStep = ( ( (unsigned)( scM * 64 ) & 0xFFFFu ) * 0x10001u );
-        (void)bBound;
-        for( int base = p0; base <= en0; base += 64 )
+        const unsigned termStep = ( (unsigned)( scM * 64 ) & 0xFFFFu ) * 0x10001u;
+        for( int base = p0; base <= en0; base += 64, t0 += 64 )
         {
-            const int t0 = base + 2 * lane;
             const int kk = ( t0 & M ) >> 1; // pair index in the window
             const unsigned xo = px[ kk ], vo = pv[ kk ], x2o = px2[ kk ];
             const __half2 ut = u2h( pu[ kk ] ), yo = u2h( py[ kk ] ), y2o = u2h( py2[ kk ] );
@@ -663,7 +683,7 @@ __device__ __forceinline__ bool ksw_rows_p2( const KswScore& P, const SeqAccess&
                           x2t1 = u2h( __byte_perm( upx2, x2o, 0x5432 ) );
             // score profile (:591-616): N scores -e2
             unsigned z0 = sel2( __heq2_mask( tcp, qp ), uMatch, uMis );
-            z0 = sel2( __hge2_mask( __hmax2( tcp, qp ), hFour ), uN, z0 );
+            z0 = sel2( __hge2_mask( __hmax2( tcp, qp ), hCodeN ), uN, z0 );
             __half2 z = u2h( z0 );
             const __half2 a = __hadd2( xt1, vt1 ), b = __hadd2( yo, ut ), a2 = __hadd2( x2t1, vt1 ),
                           b2 = __hadd2( y2o, ut );
@@ -710,10 +730,10 @@ __device__ __forceinline__ bool ksw_rows_p2( const KswScore& P, const SeqAccess&
             // H row (calcMaxScore): interior columns add v, the last column adds u to its left neighbour's old H
             const int de = en0 - t0; // 0: the low cell is en0, 1: the high cell
             const unsigned me = (unsigned)de < 2u ? ( 0xFFFFu << ( de << 4 ) ) : 0u;
-            const unsigned add = h2u( __hadd2( u2h( sel2( en0 > 0 ? me : 0u, h2u( un ), h2u( vn ) ) ), hBias ) ) &
+            const unsigned add = h2u( __hadd2( u2h( sel2( me & meEn, h2u( un ), h2u( vn ) ) ), hBias ) ) &
                                  0x03FF03FFu; // 512 + value per half
             const unsigned h = __vsub2( __vadd2( sel2( me, hprev2, hOld ), add ), 0x02000200u );
-            if( t0 <= en0 )
+            if( de >= 0 )
             {
                 pu[ kk ] = h2u( un );
                 pv[ kk ] = h2u( vn );
@@ -725,46 +745,57 @@ __device__ __forceinline__ bool ksw_rows_p2( const KswScore& P, const SeqAccess&
                 *reinterpret_cast<unsigned short*>( rowp + t0 ) = (unsigned short)__byte_perm( d, 0, 0x4420 );
             }
             // in-band cells only: row maximum and the early-stop bound
-            const unsigned vm = ( ( t0 >= st0 && t0 <= en0 ) ? 0xFFFFu : 0u ) | ( t0 + 1 <= en0 ? 0xFFFF0000u : 0u );
+            const unsigned vm = ( ( t0 >= st0 && de >= 0 ) ? 0xFFFFu : 0u ) | ( de >= 1 ? 0xFFFF0000u : 0u );
             const unsigned hm = sel2( vm, h, 0x80008000u );
             m2 = __vmaxs2( m2, hm );
             hb2 = __vmaxs2( hb2, __vadd2( hm, term2 & vm ) );
             term2 = __vadd2( term2, termStep );
         }
-        const int mlo = (short)( m2 & 0xFFFFu ), mhi = (int)m2 >> 16;
-        const int max_H = __reduce_max_sync( FULL, max( mlo, mhi ) );
+        const int max_H = __reduce_max_sync( FULL, max( (int)(short)( m2 & 0xFFFFu ), (int)m2 >> 16 ) );
         __syncwarp( );
-        int max_t = en0;
-        // the position is consumed only by a new maximum or by a z-drop test that can fire (l >= 0)
-        if( max_H > ez.max || ( zdrop >= 0 && ez.max - max_H > zdrop ) )
-            max_t = ksw_p2_argmax( sm.H, M, st0, en0, lane );
-        // ksw_apply_zdrop (:22-44)
         if( max_H > ez.max )
-            ez.max = max_H, ez.max_t = max_t, ez.max_q = r - max_t;
-        else if( max_t >= ez.max_t && r - max_t >= ez.max_q )
-        {
-            const int tl = max_t - ez.max_t, ql = ( r - max_t ) - ez.max_q;
-            const int l = tl > ql ? tl - ql : ql - tl;
-            if( zdrop >= 0 && ez.max - max_H > zdrop + l * e2 )
+        { // new maximum: keep its H row, the lane-blocked position is resolved when (if) it is consumed
+            ez.max = max_H;
+            pend = true, bR = r, bSt0 = st0, bEn0 = en0;
+            for( int t = p0 + 2 * lane; t <= en0; t += 64 )
+                pHs[ ( t & M ) >> 1 ] = pH[ ( t & M ) >> 1 ];
+        }
+        else if( zdrop >= 0 && ez.max - max_H > zdrop )
+        { // ksw_apply_zdrop (:22-44) can only fire here (l * e2 >= 0)
+            if( pend )
             {
-                ez.zdropped = 1;
-                break;
+                __syncwarp( );
+                ez.max_t = ksw_p2_argmax( sm.Hs, M, bSt0, bEn0, lane ), ez.max_q = bR - ez.max_t;
+                pend = false;
+            }
+            const int max_t = ksw_p2_argmax( sm.H, M, st0, en0, lane );
+            if( max_t >= ez.max_t && r - max_t >= ez.max_q )
+            {
+                const int tl = max_t - ez.max_t, ql = ( r - max_t ) - ez.max_q;
+                const int l = tl > ql ? tl - ql : ql - tl;
+                if( ez.max - max_H > zdrop + l * e2 )
+                {
+                    ez.zdropped = 1;
+                    break;
+                }
             }
         }
         {
-            const int blo = (short)( hb2 & 0xFFFFu ), bhi = (int)hb2 >> 16;
-            const int B = __reduce_max_sync( FULL, max( blo, bhi ) );
+            const int B = __reduce_max_sync( FULL, max( (int)(short)( hb2 & 0xFFFFu ), (int)hb2 >> 16 ) );
             if( r >= qlen && prevB != NONE_T )
-            {
-                const long long j = r + 1;
-                const long long g1 = q + (long long)e * j, g2 = q2 + (long long)e2 * j;
-                const long long T = (long long)scM * qlen - ( g1 < g2 ? g1 : g2 );
-                const long long bound = max( (long long)max( B, prevB ), T );
-                if( bound <= (long long)ez.max )
+            { // all terms are < 2^31: is16 bounds qlen, tlen and the scores
+                const int j = r + 1;
+                const int T = T0 - min( q + e * j, q2 + e2 * j );
+                if( max( max( B, prevB ), T ) <= ez.max )
                     break;
             }
             prevB = B;
         }
+    }
+    if( pend )
+    {
+        __syncwarp( );
+        ez.max_t = ksw_p2_argmax( sm.Hs, M, bSt0, bEn0, lane ), ez.max_q = bR - ez.max_t;
     }
     ez.cells = cells;
     __syncwarp( );
