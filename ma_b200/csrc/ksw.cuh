@@ -925,7 +925,10 @@ struct KswBatchArgs
     KswScore score;
 };
 
-template <int W> __global__ void __launch_bounds__( 256, 3 ) ksw_batch_kernel( KswBatchArgs A )
+#ifndef MA_KSW_MINB
+#define MA_KSW_MINB 3
+#endif
+template <int W> __global__ void __launch_bounds__( 256, MA_KSW_MINB ) ksw_batch_kernel( KswBatchArgs A )
 {
     extern __shared__ __align__( 16 ) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
