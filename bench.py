@@ -318,6 +318,11 @@ def main():
                         "L2-resident on this configuration)" % (occ_bytes // 1_000_000),
                         "achieved": seed_ach, "peak": gather_gbs, "unit": "GB/s", "frac": seed_ach / gather_gbs,
                         "peak_hbm_resident_buffer": gather_hbm_gbs,
+                        "table_reads_GBs": 128.0 * last["n_lookup"] / per["ms_seed"] / 1e6 if per["ms_seed"] > 0 else None,
+                        "lookup_share": last["n_lookup"] / max(1, last["n_ext"]),
+                        "note": "achieved = 128 B x extend_backward calls of the reference algorithm / kernel time; "
+                                "the kernel reads the table for lookup_share of them and reuses the previous result "
+                                "for entries with the same SA interval (table_reads_GBs is that real traffic)",
                         "peak_source": "ma_b200_gather_probe: independent random 64-byte reads over a buffer of the "
                                        "occ table's size (and over 8 GiB for the HBM-resident figure), this run"}
     sm_mhz = peaks.get("sm_max_mhz", 1965.0)
@@ -346,7 +351,7 @@ def main():
             "dp_int_roofline": dp_roof, "kernels": kernels, "cpu_baseline": cpu_baseline,
             "aligned_reads_per_step": aligned_all, "index_build_s": t_index,
             "work_per_step": {k: int(last[k]) for k in ("n_reads", "n_seeds", "n_sets", "n_tasks", "n_ext",
-                                                       "n_invpsi", "dp_cells", "n_dropped")}}
+                                                       "n_lookup", "n_invpsi", "dp_cells", "n_dropped")}}
     print(json.dumps(line))
     ctx.close()
     if world > 1:

@@ -192,6 +192,8 @@ typedef struct
     int64_t n_invpsi; /* bwt_invPsi steps: 64 algorithmic bytes each */
     int64_t n_dropped; /* reads cleared by the seeding drop-off */
     int64_t dp_cells; /* band cells */
+    int64_t n_lookup; /* extend_backward calls that really read the occurrence table (the rest reuse the previous
+                         result of the same SA interval, see fmindex.cuh SeederSM) */
     float ms_seed, ms_locate, ms_socharm, ms_plan, ms_dp, ms_assemble, ms_total;
     int32_t launches;
 } ma_b200_align_stats;

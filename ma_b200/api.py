@@ -62,7 +62,8 @@ STAGE_SEEDS, STAGE_SETS, STAGE_ALIGN = 1, 2, 3
 
 class AlignStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int64) for n in ("n_reads", "n_seeds", "n_sets", "n_set_seeds", "n_tasks", "n_runs",
-                                              "n_cigar_words", "n_ext", "n_invpsi", "n_dropped", "dp_cells")] + \
+                                              "n_cigar_words", "n_ext", "n_invpsi", "n_dropped", "dp_cells",
+                                              "n_lookup")] + \
                [(n, ctypes.c_float) for n in ("ms_seed", "ms_locate", "ms_socharm", "ms_plan", "ms_dp",
                                               "ms_assemble", "ms_total")] + [("launches", ctypes.c_int32)]
 

@@ -295,10 +295,12 @@ struct SeedScratch
 // 40-bit values, reference length < 2^40) so that the first K entries of every thread fit in shared memory
 // (entry j of thread t at [ j * stride + t ]: bank = t mod 8 for the 16-byte part, conflict free for any mix of j).
 // Entries >= K (long lists: repetitive reads) spill to the thread's global scratch.
+// Every entry also carries a multiplicity: the number of reference list entries it stands for (SeederSM::consume_bwd).
 struct SegList
 {
     U4* pk; // 3 x 40 bit
     int* sz;
+    unsigned short* mu; // multiplicity (see SeederSM::consume_bwd)
     int stride, K;
     SegRec* ovf;
     int cap; // total capacity (K + overflow entries)
@@ -327,12 +329,23 @@ struct SegList
     {
         return j < K ? sz[ j * stride ] : ovf[ j - K ].size;
     }
-    MA_HD void set( int j, int size, const SAI& a )
+    MA_HD int mult( int j ) const
+    {
+        return j < K ? (int)mu[ j * stride ] : ovf[ j - K ].start;
+    }
+    MA_HD void add_mult( int j, int m )
     {
         if( j < K )
-            pk[ j * stride ] = pack( a ), sz[ j * stride ] = size;
+            mu[ j * stride ] = (unsigned short)( mu[ j * stride ] + m );
         else
-            ovf[ j - K ] = SegRec{ 0, size, a };
+            ovf[ j - K ].start += m;
+    }
+    MA_HD void set( int j, int size, const SAI& a, int m = 1 )
+    {
+        if( j < K )
+            pk[ j * stride ] = pack( a ), sz[ j * stride ] = size, mu[ j * stride ] = (unsigned short)m;
+        else
+            ovf[ j - K ] = SegRec{ m, size, a };
     }
 };
 
@@ -583,6 +596,10 @@ template <class Sink> struct SeederSM
     int lstart = 0; // query start shared by all entries of the list
     int nCurr = 0, nNext = 0, j = 0;
     bool bHaveOne = false;
+    // last entry pushed in the running backward pass (its SA interval), for the merge of identical intervals
+    long long lastStart = 0;
+    int lastSize = -1; // < 0: none (intervals of 2^31 rows or more are never merged)
+    unsigned int nLookup = 0; // extend_backward calls really made (nExt counts the reference's)
 
     MA_HD SeederSM( const DevIndex& I, const SeedParams& P, const unsigned char* q, int L, SegList S, Sink& sink,
                     int* pStack /* 2 x 40 ints */ )
@@ -595,7 +612,7 @@ template <class Sink> struct SeederSM
     MA_HD void begin( const unsigned char* q_, int L_ )
     {
         q = q_, L = L_;
-        nExt = 0, overflow = false, sp = 0;
+        nExt = 0, nLookup = 0, overflow = false, sp = 0;
         phase = P_NEXT_CENTER;
         if( L > 0 )
             stS[ 0 ] = 0, stN[ 0 ] = L, sp = 1;
@@ -614,10 +631,10 @@ template <class Sink> struct SeederSM
     {
         sink.seg( SegRec{ st, size, sa } );
     }
-    MA_HD void push_list( int& n, int size, const SAI& sa )
+    MA_HD void push_list( int& n, int size, const SAI& sa, int m = 1 )
     {
         if( n < S.cap )
-            S.set( n, size, sa );
+            S.set( n, size, sa, m );
         else
             overflow = true;
         n++;
@@ -650,12 +667,12 @@ template <class Sink> struct SeederSM
         {
             const int sa_ = S.size( a ), sb_ = S.size( b );
             const SAI ia = S.sa( a ), ib = S.sa( b );
-            S.set( a, sb_, ib ), S.set( b, sa_, ia );
+            S.set( a, sb_, ib ), S.set( b, sa_, ia ); // forward-pass entries all have multiplicity 1
         }
         lstart = center;
         if( center != 0 )
         {
-            i = center - 1, j = 0, bHaveOne = false, nNext = 0;
+            i = center - 1, j = 0, bHaveOne = false, nNext = 0, lastSize = -1;
             phase = P_SMEM_BWD;
         }
         else
@@ -760,7 +777,7 @@ template <class Sink> struct SeederSM
                             smem_final( );
                             break;
                         }
-                        i--, j = 0, bHaveOne = false, nNext = 0;
+                        i--, j = 0, bHaveOne = false, nNext = 0, lastSize = -1;
                     }
                     break;
                 case P_MS1_FWD:
@@ -803,7 +820,7 @@ template <class Sink> struct SeederSM
     // Feeds the result of the requested extension back into the state machine.
     MA_HD void consume( const SAI& ok )
     {
-        nExt++;
+        nExt++, nLookup++;
         switch( phase )
         {
             case P_SMEM_FWD:
@@ -824,14 +841,28 @@ template <class Sink> struct SeederSM
             }
             case P_SMEM_BWD:
             {
-                const int sSize = S.size( j );
+                // Entries with the same SA interval (start, size) extend identically for ever and, with
+                // min_amb == 0, only the first of them (the longest match) can ever be emitted: the failing entries of a
+                // pass are a prefix of the list and just the first failing one is reported (bHaveOne). Such entries
+                // are therefore merged into the first one, which keeps count of how many reference entries it stands
+                // for so that nExt stays the reference's number of extend_backward calls.
+                const int sSize = S.size( j ), m = S.mult( j );
+                nExt += m - 1;
                 if( ok.size <= P.min_amb && !bHaveOne )
                 {
                     emit( lstart, sSize, S.sa( j ) );
                     bHaveOne = true;
                 }
                 else if( ok.size > P.min_amb || ( ok.size > 0 && sSize >= P.max_amb ) )
-                    push_list( nNext, sSize + 1, ok ); // in place: nNext <= j, entry j has been consumed
+                {
+                    if( P.min_amb == 0 && ok.start == lastStart && ok.size == (long long)lastSize )
+                        S.add_mult( nNext - 1, m );
+                    else
+                    {
+                        push_list( nNext, sSize + 1, ok, m ); // in place: nNext <= j, entry j has been consumed
+                        lastStart = ok.start, lastSize = ok.size < 0x7fffffffll ? (int)ok.size : -1;
+                    }
+                }
                 j++;
                 break;
             }

@@ -833,7 +833,7 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
             MA_CUDA( cudaMemsetAsync( ctx->ctrl.p, 0, sizeof( PipeCtrl ), s ) );
         }
         ctx->n_seeds = (int64_t)ctx->hctrl.seed_cursor;
-        st.n_ext = (int64_t)ctx->hctrl.n_ext, st.n_dropped = (int64_t)ctx->hctrl.n_dropped;
+        st.n_ext = (int64_t)ctx->hctrl.n_ext, st.n_lookup = (int64_t)ctx->hctrl.n_lookup, st.n_dropped = (int64_t)ctx->hctrl.n_dropped;
         MA_CUDA( cudaEventRecord( ctx->ev[ 1 ], s ) );
         if( ctx->n_seeds > 0 )
         {

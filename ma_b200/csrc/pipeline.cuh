@@ -27,6 +27,7 @@ struct PipeCtrl
     unsigned long long task_cursor; // DP tasks allocated
     unsigned long long run_cursor; // alignment run words allocated
     unsigned long long n_ext; // FMIndex::extend_backward calls (roofline unit)
+    unsigned long long n_lookup; // ... of which read the occurrence table
     unsigned long long n_invpsi; // bwt_invPsi steps
     unsigned long long n_dropped; // reads cleared by the seeding drop-off heuristic
     unsigned long long scratch_cursor; // soc/harm scratch bytes
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__( 128 ) seed_kernel_rec( SeedKernelArgs A )
         }
     }
     if( nExtLocal )
-        atomicAdd( &A.ctrl->n_ext, nExtLocal );
+        atomicAdd( &A.ctrl->n_ext, nExtLocal ), atomicAdd( &A.ctrl->n_lookup, nExtLocal );
     if( nDropped )
         atomicAdd( &A.ctrl->n_dropped, nDropped );
 }
@@ -197,14 +198,15 @@ __global__ void __launch_bounds__( MA_SEED_BLOCK, MA_SEED_MINB ) seed_kernel( Se
 {
     __shared__ U4 sPk[ MA_SEED_K * MA_SEED_BLOCK ];
     __shared__ int sSz[ MA_SEED_K * MA_SEED_BLOCK ];
+    __shared__ unsigned short sMu[ MA_SEED_K * MA_SEED_BLOCK ];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     SegRec* la = A.lists + (size_t)tid * ( 2 * A.list_cap + 8 );
     FSeg* fs = A.fsegs + (size_t)tid * A.fseg_cap;
-    unsigned long long nExtLocal = 0, nDropped = 0;
+    unsigned long long nExtLocal = 0, nLookupLocal = 0, nDropped = 0;
     SeedSink sink( A.P, fs, A.fseg_cap, nullptr, A.dbg_cap );
     // the first 2 x 40 ints of the thread's list scratch hold the interval stack
     SeederSM<SeedSink> S( A.I, A.P, A.reads, 0,
-                          SegList{ sPk + threadIdx.x, sSz + threadIdx.x, MA_SEED_BLOCK, MA_SEED_K, la + 8,
+                          SegList{ sPk + threadIdx.x, sSz + threadIdx.x, sMu + threadIdx.x, MA_SEED_BLOCK, MA_SEED_K, la + 8,
                                    MA_SEED_K + 2 * A.list_cap },
                           sink, (int*)la );
     int read = -1; // -1: needs a new read, -2: queue exhausted
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__( MA_SEED_BLOCK, MA_SEED_MINB ) seed_kernel( Se
             need = S.request( rIk, rC );
             if( !need )
             { // the read is finished: drop-off heuristic (binarySeeding.cpp:172-175) and seed enumeration
-                nExtLocal += (unsigned long long)S.nExt;
+                nExtLocal += (unsigned long long)S.nExt, nLookupLocal += (unsigned long long)S.nLookup;
                 if( S.overflow )
                     atomicExch( &A.ctrl->overflow_lists, 1 );
                 if( sink.overflow )
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__( MA_SEED_BLOCK, MA_SEED_MINB ) seed_kernel( Se
             S.consume( extend_backward( A.I, rIk, rC ) );
     }
     if( nExtLocal )
-        atomicAdd( &A.ctrl->n_ext, nExtLocal );
+        atomicAdd( &A.ctrl->n_ext, nExtLocal ), atomicAdd( &A.ctrl->n_lookup, nLookupLocal );
     if( nDropped )
         atomicAdd( &A.ctrl->n_dropped, nDropped );
 }

@@ -98,6 +98,7 @@ int main( int argc, char** argv )
     std::ifstream in( argv[ 2 ] );
     std::string line;
     long nRead = 0, nBad = 0;
+    unsigned long long nExtTotal = 0, nLookupTotal = 0;
     std::vector<SegRec> la( 600 ), lb( 600 );
     while( std::getline( in, line ) )
     {
@@ -131,8 +132,9 @@ int main( int argc, char** argv )
             // a short "shared" part (stride 3, like the interleaved device layout) so that both halves of SegList run
             U4 pk[ 3 * 6 ];
             int sz[ 3 * 6 ];
+            unsigned short mu[ 3 * 6 ];
             SeederSM<AllSegSink> S2( I, SP, q.data( ), (int)q.size( ),
-                                     SegList{ pk + 1, sz + 1, 3, 6, la.data( ), 606 }, sink2, stk );
+                                     SegList{ pk + 1, sz + 1, mu + 1, 3, 6, la.data( ), 606 }, sink2, stk );
             S2.run( );
             size_t sum2 = 0;
             for( auto& s : sink2.v )
@@ -140,6 +142,7 @@ int main( int argc, char** argv )
             if( !SP.disable_heuristics && SP.drop_min_size != 0 && (double)sum2 < SP.drop_factor * (double)q.size( ) &&
                 (unsigned long long)SP.genome_size_disable < (unsigned long long)I.ref_len )
                 sink2.v.clear( );
+            nExtTotal += (unsigned long long)S2.nExt, nLookupTotal += (unsigned long long)S2.nLookup;
             bool ok2 = sink2.v.size( ) == sink.v.size( ) && !S2.overflow && ( S2.nExt == S.nExt );
             for( size_t i = 0; ok2 && i < sink.v.size( ); i++ )
                 ok2 = sink2.v[ i ].start == sink.v[ i ].start && sink2.v[ i ].size == sink.v[ i ].size &&
@@ -301,5 +304,7 @@ int main( int argc, char** argv )
     }
     printf( "hostsim: %ld reads, seeding mismatches %ld, soc/harm mismatches %ld, alignment mismatches %ld\n", nRead,
             nBad, nBadHarm, nBadAln );
+    printf( "hostsim: %llu extensions, %llu occurrence-table lookups (memo hit rate %.1f%%)\n", nExtTotal, nLookupTotal,
+            nExtTotal ? 100.0 * (double)( nExtTotal - nLookupTotal ) / (double)nExtTotal : 0.0 );
     return ( nBad || nBadHarm || nBadAln ) ? 1 : 0;
 }
