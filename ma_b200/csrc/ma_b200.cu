@@ -862,7 +862,7 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
                 A.scratch = ctx->harm_scratch.p, A.scratch_cap = ctx->harm_scratch.cap;
                 A.set_seeds = ctx->set_seeds.p, A.set_seed_cap = setSeedCap, A.sets = ctx->sets.p, A.set_cap = setCap;
                 A.srand_base = ctx->params.srand_base, A.ctrl = ctx->ctrl.p;
-                socharm_kernel<<<full_grid( ctx, socharm_kernel, 128, n ), 128, 0, s>>>( A );
+                socharm_kernel<<<full_grid( ctx, socharm_kernel, MA_SOC_BLOCK, n ), MA_SOC_BLOCK, 0, s>>>( A );
                 MA_CUDA( cudaGetLastError( ) );
                 ctx->launches++;
                 read_ctrl( ctx );
@@ -909,11 +909,16 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
                         throw std::runtime_error( "NW planning: task slab overflow after growing (internal error)" );
                     taskCap = (long long)ctx->hctrl.task_cursor + 1024;
                     zero_field( ctx, &PipeCtrl::task_cursor );
-                    MA_CUDA( cudaMemsetAsync( ctx->ctrl.p->bin_count, 0, sizeof( int ) * 8, s ) );
-                    MA_CUDA( cudaMemsetAsync( ctx->ctrl.p->bin_tb, 0, sizeof( unsigned long long ) * 8, s ) );
-                    MA_CUDA( cudaMemsetAsync( ctx->ctrl.p->bin_cig, 0, sizeof( int ) * 8, s ) );
                 }
             ctx->n_tasks = nSets > 0 ? (int64_t)ctx->hctrl.task_cursor : 0;
+            if( ctx->n_tasks > 0 )
+            { // window bins of the tasks
+                NwBinArgs B{ ctx->tasks.p, (int)ctx->n_tasks, taskCap, ctx->bin_order.p, ctx->ctrl.p };
+                nwbin_kernel<<<full_grid( ctx, nwbin_kernel, 256, ctx->n_tasks ), 256, 0, s>>>( B );
+                MA_CUDA( cudaGetLastError( ) );
+                ctx->launches++;
+                read_ctrl( ctx );
+            }
             MA_CUDA( cudaEventRecord( ctx->ev[ 4 ], s ) );
             if( ctx->n_tasks > 0 )
                 run_pipeline_dp( ctx, taskCap );

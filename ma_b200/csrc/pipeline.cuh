@@ -373,7 +373,13 @@ struct DevSetSink
     }
 };
 
-__global__ void __launch_bounds__( 128 ) socharm_kernel( SocHarmArgs A )
+#ifndef MA_SOC_BLOCK
+#define MA_SOC_BLOCK 128
+#endif
+#ifndef MA_SOC_MINB
+#define MA_SOC_MINB 12
+#endif
+__global__ void __launch_bounds__( MA_SOC_BLOCK, MA_SOC_MINB ) socharm_kernel( SocHarmArgs A )
 {
     while( true )
     {
@@ -442,44 +448,108 @@ __device__ __forceinline__ int ksw_bin_of( int ncol16 )
     return need <= 128 ? 0 : need <= 256 ? 1 : need <= 512 ? 2 : need <= 1024 ? 3 : need <= 2048 ? 4 : 5;
 }
 
+// One thread per seed set: window, task count, one warp-aggregated slot allocation, tasks.
 __global__ void __launch_bounds__( 128 ) nwplan_kernel( NwPlanArgs A )
 {
-    for( int si = blockIdx.x * blockDim.x + threadIdx.x; si < A.n_sets; si += gridDim.x * blockDim.x )
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    // warp-uniform trip count: every lane of a warp takes part in the aggregated allocation of each round
+    for( int base = ( blockIdx.x * blockDim.x + threadIdx.x ) & ~31; base < A.n_sets; base += gridDim.x * blockDim.x )
     {
-        SetHeader h = A.sets[ si ];
-        const DSeed* S = A.set_seeds + h.seed_off;
-        const long long qbase = A.read_off[ h.read ];
-        const int qlen = (int)( A.read_off[ h.read + 1 ] - qbase );
-        const NwWindow w = nw_window( A.I, A.P, S, h.n );
-        h.valid = w.valid ? 1 : 0, h.win_begin = w.beginRef, h.win_end = w.endRef, h.n_tasks = 0, h.task_off = 0;
-        if( w.valid )
+        const int si = base + lane;
+        const bool live = si < A.n_sets;
+        SetHeader h;
+        const DSeed* S = nullptr;
+        long long qbase = 0;
+        int qlen = 0, nTasks = 0;
+        NwWindow w;
+        w.valid = false;
+        if( live )
         {
-            NwPlanner cnt( A.P, nullptr, qbase, (long long)w.beginRef );
-            nw_walk( S, h.n, qlen, w, cnt );
-            h.n_tasks = cnt.n;
-            if( cnt.n > 0 )
+            h = A.sets[ si ];
+            S = A.set_seeds + h.seed_off;
+            qbase = A.read_off[ h.read ];
+            qlen = (int)( A.read_off[ h.read + 1 ] - qbase );
+            w = nw_window( A.I, A.P, S, h.n );
+            h.valid = w.valid ? 1 : 0, h.win_begin = w.beginRef, h.win_end = w.endRef, h.n_tasks = 0, h.task_off = 0;
+            if( w.valid )
             {
-                const long long to = (long long)atomicAdd( &A.ctrl->task_cursor, (unsigned long long)cnt.n );
-                h.task_off = (int)to;
-                if( to + cnt.n <= A.task_cap )
+                NwPlanner cnt( A.P, nullptr, qbase, (long long)w.beginRef );
+                nw_walk( S, h.n, qlen, w, cnt );
+                nTasks = cnt.n;
+            }
+        }
+        // exclusive scan of the task counts over the warp, one atomic for all of them
+        int incl = nTasks;
+        for( int o = 1; o < 32; o <<= 1 )
+        {
+            const int v = __shfl_up_sync( FULL, incl, o );
+            if( lane >= o )
+                incl += v;
+        }
+        const int total = __shfl_sync( FULL, incl, 31 );
+        long long wbase = 0;
+        if( lane == 0 && total > 0 )
+            wbase = (long long)atomicAdd( &A.ctrl->task_cursor, (unsigned long long)total );
+        wbase = __shfl_sync( FULL, wbase, 0 );
+        if( live )
+        {
+            if( nTasks > 0 )
+            {
+                const long long to = wbase + incl - nTasks;
+                h.n_tasks = nTasks, h.task_off = (int)to;
+                if( to + nTasks <= A.task_cap )
                 {
                     NwPlanner pl( A.P, A.tasks + to, qbase, (long long)w.beginRef );
                     nw_walk( S, h.n, qlen, w, pl );
-                    for( int t = 0; t < cnt.n; t++ )
-                    {
-                        const KswTask& T = A.tasks[ to + t ];
-                        const int nc = ksw_ncol16( T.qlen, T.tlen, T.w );
-                        const int b = ksw_bin_of( nc );
-                        const int slot = atomicAdd( &A.ctrl->bin_count[ b ], 1 );
-                        A.bin_order[ (long long)b * A.task_cap + slot ] = (int)( to + t );
-                        const unsigned long long tb = ( ( (unsigned long long)T.qlen + T.tlen ) * nc + 255 ) & ~255ull;
-                        atomicMax( &A.ctrl->bin_tb[ b ], tb );
-                        atomicMax( &A.ctrl->bin_cig[ b ], ( T.qlen + T.tlen + 2 + 63 ) & ~63 );
-                    }
                 }
             }
+            A.sets[ si ] = h;
         }
-        A.sets[ si ] = h;
+    }
+}
+
+struct NwBinArgs
+{
+    const KswTask* tasks;
+    int n_tasks;
+    long long task_cap;
+    int* bin_order; // [n_bins][task_cap] task ids per window bin
+    PipeCtrl* ctrl;
+};
+
+// One thread per DP task: window bin, slot in the bin's order list (one atomic per warp and bin), slab sizes of the bin
+__global__ void __launch_bounds__( 256 ) nwbin_kernel( NwBinArgs A )
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    for( int base = ( blockIdx.x * blockDim.x + threadIdx.x ) & ~31; base < A.n_tasks; base += gridDim.x * blockDim.x )
+    {
+        const int ti = base + lane;
+        int b = 7; // lanes beyond the end form their own group
+        unsigned int tb = 0, cig = 0;
+        if( ti < A.n_tasks )
+        {
+            const KswTask T = A.tasks[ ti ];
+            const int nc = ksw_ncol16( T.qlen, T.tlen, T.w );
+            b = ksw_bin_of( nc );
+            const unsigned long long bytes = ( ( (unsigned long long)T.qlen + T.tlen ) * nc + 255 ) >> 8;
+            tb = bytes > 0xffffffffull ? 0xffffffffu : (unsigned int)bytes; // in units of 256 bytes
+            cig = (unsigned int)( ( T.qlen + T.tlen + 2 + 63 ) & ~63 );
+        }
+        const unsigned m = __match_any_sync( FULL, b );
+        const int leader = __ffs( m ) - 1;
+        const unsigned mtb = __reduce_max_sync( m, tb ), mcig = __reduce_max_sync( m, cig );
+        int slot0 = 0;
+        if( lane == leader && b < 7 )
+        {
+            slot0 = atomicAdd( &A.ctrl->bin_count[ b ], __popc( m ) );
+            atomicMax( &A.ctrl->bin_tb[ b ], (unsigned long long)mtb << 8 );
+            atomicMax( &A.ctrl->bin_cig[ b ], (int)mcig );
+        }
+        slot0 = __shfl_sync( FULL, slot0, leader );
+        if( b < 6 )
+            A.bin_order[ (long long)b * A.task_cap + slot0 + __popc( m & ( ( 1u << lane ) - 1 ) ) ] = ti;
     }
 }
 
