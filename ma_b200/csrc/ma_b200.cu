@@ -37,7 +37,7 @@ struct ma_b200_ctx
     DevBuf<unsigned char> ksw_tb;
     DevBuf<unsigned int> ksw_cigscratch;
     DevBuf<int> ksw_order;
-    DevBuf<unsigned long long> ksw_ctrl; // [0] cigar cursor, [1] next (as int), [2] error (as int)
+    DevBuf<unsigned long long> ksw_ctrl; // [0] cigar cursor, [16] next (as int), [32] error (as int), [48] cells: one 128-byte line each
     std::vector<KswHostBin> ksw_bins;
     unsigned long long ksw_cigar_used = 0;
 
@@ -312,7 +312,7 @@ extern "C" int ma_b200_ksw_upload( ma_b200_ctx* ctx, int64_t n, const ma_b200_ks
     ctx->ksw_seq.reserve( (size_t)seq_bytes + 1 );
     ctx->ksw_out.reserve( (size_t)n + 1 );
     ctx->ksw_order.reserve( (size_t)n + 1 );
-    ctx->ksw_ctrl.reserve( 4 );
+    ctx->ksw_ctrl.reserve( 64 );
     if( n > 0 )
     {
         // `tag` is the caller's cookie; on the device the field carries the internal addressing mode (0 = byte slab)
@@ -342,7 +342,7 @@ extern "C" int ma_b200_ksw_upload( ma_b200_ctx* ctx, int64_t n, const ma_b200_ks
 
 static int ksw_run_once( ma_b200_ctx* ctx )
 {
-    MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p, 0, 4 * sizeof( unsigned long long ), ctx->stream ) );
+    MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p, 0, 64 * sizeof( unsigned long long ), ctx->stream ) );
     const KswScore score = make_score( ctx->params );
     const long long budget = 12ll << 30;
     // size the per-warp scratch for the largest bin first: DevBuf::reserve may free + reallocate
@@ -386,11 +386,11 @@ static int ksw_run_once( ma_b200_ctx* ctx )
         A.tb_stride = bin.tb_stride;
         A.cigscratch = ctx->ksw_cigscratch.p;
         A.cigscratch_stride = bin.cig_stride;
-        A.next = (int*)( ctx->ksw_ctrl.p + 1 );
-        A.error = (int*)( ctx->ksw_ctrl.p + 2 );
+        A.next = (int*)( ctx->ksw_ctrl.p + 16 );
+        A.error = (int*)( ctx->ksw_ctrl.p + 32 );
         A.cells_total = nullptr;
         A.score = score;
-        MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p + 1, 0, sizeof( unsigned long long ), ctx->stream ) );
+        MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p + 16, 0, sizeof( unsigned long long ), ctx->stream ) );
         switch( bin.W )
         {
             case 128: launch_ksw_bin<128>( ctx, A, grid ); break;
@@ -401,11 +401,11 @@ static int ksw_run_once( ma_b200_ctx* ctx )
         }
         o += bin.order.size( );
     }
-    unsigned long long ctrl[ 3 ];
+    unsigned long long ctrl[ 64 ];
     MA_CUDA( cudaMemcpyAsync( ctrl, ctx->ksw_ctrl.p, sizeof( ctrl ), cudaMemcpyDeviceToHost, ctx->stream ) );
     MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
     ctx->ksw_cigar_used = ctrl[ 0 ];
-    return (int)ctrl[ 2 ];
+    return (int)ctrl[ 32 ];
 }
 
 extern "C" int ma_b200_ksw_run( ma_b200_ctx* ctx, float* kernel_ms )
@@ -686,13 +686,13 @@ static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
     if( ctx->hctrl.bin_count[ 5 ] > 0 )
         throw std::runtime_error( "DP band wider than the largest supported window (2000 columns)" );
     ctx->task_out.reserve( (size_t)ctx->n_tasks + 1 );
-    ctx->ksw_ctrl.reserve( 4 );
+    ctx->ksw_ctrl.reserve( 64 );
     long long cigCap = std::max<long long>( ctx->task_cigar.cap, std::max<long long>( 12 * ctx->n_tasks, 1 << 16 ) );
     for( int attempt = 0; attempt < 2; attempt++ )
     {
         ctx->task_cigar.reserve( (size_t)cigCap );
         cigCap = (long long)ctx->task_cigar.cap;
-        MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p, 0, 4 * sizeof( unsigned long long ), ctx->stream ) );
+        MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p, 0, 64 * sizeof( unsigned long long ), ctx->stream ) );
         const long long budget = 12ll << 30;
         long long grids[ 5 ];
         size_t tbNeed = 0, csNeed = 0;
@@ -734,11 +734,11 @@ static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
             A.cigar_cursor = ctx->ksw_ctrl.p;
             A.tb = ctx->ksw_tb.p, A.tb_stride = (long long)ctx->hctrl.bin_tb[ b ];
             A.cigscratch = ctx->ksw_cigscratch.p, A.cigscratch_stride = ctx->hctrl.bin_cig[ b ];
-            A.next = (int*)( ctx->ksw_ctrl.p + 1 );
-            A.error = (int*)( ctx->ksw_ctrl.p + 2 );
-            A.cells_total = ctx->ksw_ctrl.p + 3;
+            A.next = (int*)( ctx->ksw_ctrl.p + 16 );
+            A.error = (int*)( ctx->ksw_ctrl.p + 32 );
+            A.cells_total = ctx->ksw_ctrl.p + 48;
             A.score = score;
-            MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p + 1, 0, sizeof( unsigned long long ), ctx->stream ) );
+            MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p + 16, 0, sizeof( unsigned long long ), ctx->stream ) );
             switch( b )
             {
                 case 0: launch_ksw_bin<128>( ctx, A, grids[ b ] ); break;
@@ -748,12 +748,12 @@ static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
                 default: launch_ksw_bin<2048>( ctx, A, grids[ b ] ); break;
             }
         }
-        unsigned long long c[ 4 ];
+        unsigned long long c[ 64 ];
         MA_CUDA( cudaMemcpyAsync( c, ctx->ksw_ctrl.p, sizeof( c ), cudaMemcpyDeviceToHost, ctx->stream ) );
         MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
         ctx->n_task_cigar = (int64_t)c[ 0 ];
-        ctx->ksw_cigar_used = c[ 3 ]; // reused as dp cell counter for the pipeline stats
-        if( !(int)c[ 2 ] )
+        ctx->ksw_cigar_used = c[ 48 ]; // reused as dp cell counter for the pipeline stats
+        if( !(int)c[ 32 ] )
             return;
         cigCap = (long long)c[ 0 ] + 1024; // the cursor kept counting: exact size
     }

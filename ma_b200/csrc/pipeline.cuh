@@ -18,24 +18,29 @@
 namespace ma
 {
 
-// control block in device memory (one cache line per hot counter would be nicer; contention is one atomic per read)
+// control block in device memory; every counter that many threads bump at the same time sits in its own 128-byte
+// line (same-line atomics serialise in the L2 slice that owns the line)
 struct PipeCtrl
 {
-    unsigned long long seed_cursor; // seeds allocated
-    unsigned long long set_seed_cursor; // harmonized seeds allocated
-    unsigned long long set_cursor; // set headers allocated
-    unsigned long long task_cursor; // DP tasks allocated
-    unsigned long long run_cursor; // alignment run words allocated
-    unsigned long long n_ext; // FMIndex::extend_backward calls (roofline unit)
+    alignas( 128 ) unsigned long long seed_cursor; // seeds allocated
+    alignas( 128 ) unsigned long long set_seed_cursor; // harmonized seeds allocated
+    alignas( 128 ) unsigned long long set_cursor; // set headers allocated
+    alignas( 128 ) unsigned long long task_cursor; // DP tasks allocated
+    alignas( 128 ) unsigned long long run_cursor; // alignment run words allocated
+    alignas( 128 ) unsigned long long scratch_cursor; // soc/harm scratch bytes
+    alignas( 128 ) int next_read;
+    alignas( 128 ) int next_read2;
+    alignas( 128 ) int next_set;
+    alignas( 128 ) int next_set2;
+    alignas( 128 ) int next_read3;
+    alignas( 128 ) unsigned long long n_ext; // FMIndex::extend_backward calls (roofline unit)
     unsigned long long n_lookup; // ... of which read the occurrence table
     unsigned long long n_invpsi; // bwt_invPsi steps
     unsigned long long n_dropped; // reads cleared by the seeding drop-off heuristic
-    unsigned long long scratch_cursor; // soc/harm scratch bytes
-    int next_read, next_read2, next_set, next_set2, next_read3;
     int overflow_lists, overflow_fseg, overflow_runs;
-    int bin_count[ 8 ];
-    unsigned long long bin_tb[ 8 ];
-    int bin_cig[ 8 ];
+    alignas( 128 ) int bin_count[ 8 ];
+    alignas( 128 ) unsigned long long bin_tb[ 8 ];
+    alignas( 128 ) int bin_cig[ 8 ];
 };
 
 struct ReadInfo // per read
