@@ -802,12 +802,361 @@ __device__ __forceinline__ bool ksw_rows_p2( const KswScore& P, const SeqAccess&
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Packed path, TWO anti-diagonals per pass. A lane keeps its column pair in registers over rows r and r + 1: the
+// state arrays are loaded and stored once per two rows, the left neighbour of row r + 1 comes from a second shuffle
+// of the values just computed, and the per-row bookkeeping (band, staging, reductions, bound test) runs once per
+// pass. Row r + 1 enters column r + 1 (if the band still grows): its u / y / y2 start values are injected in
+// registers. Three rotating H buffers: the input row, the two output rows; the buffer of the row that holds the
+// running maximum is never overwritten (deferred arg-max, see ksw_rows_p2).
+template <int W> struct KswSmemQ
+{
+    __half u[ W ], v[ W ], x[ W ], y[ W ], x2[ W ], y2[ W ], tc[ W ];
+    short H[ 3 ][ W ];
+    __half qa[ W ], qb[ W ]; // qa[j + 2] = code of q[qlen-1-j]; qb[j] = qa[j + 1]
+};
+
+struct P2Cell
+{
+    __half2 un, vn, xn, yn, x2n, y2n;
+    unsigned d;
+};
+
+struct P2Const
+{
+    __half2 hMatch, hNegQ, hNegQ2, hNegQE, hNegQE2, hE, hE2;
+};
+
+// one pair of cells of the recurrence (kswcpp_core.h:640-760) on small-integer halves
+template <bool LEFT>
+__device__ __forceinline__ P2Cell p2_cell( const P2Const& K, const __half2 xt1, const __half2 vt1, const __half2 x2t1,
+                                           const __half2 ut, const __half2 yo, const __half2 y2o, __half2 z )
+{
+    P2Cell o;
+    const __half2 a = __hadd2( xt1, vt1 ), b = __hadd2( yo, ut ), a2 = __hadd2( x2t1, vt1 ), b2 = __hadd2( y2o, ut );
+    unsigned d;
+    if( LEFT )
+    {
+        d = __hgt2_mask( a, z ) & 0x00010001u;
+        z = __hmax2( z, a );
+        d = sel2( __hgt2_mask( b, z ), 0x00020002u, d );
+        z = __hmax2( z, b );
+        d = sel2( __hgt2_mask( a2, z ), 0x00030003u, d );
+        z = __hmax2( z, a2 );
+        d = sel2( __hgt2_mask( b2, z ), 0x00040004u, d );
+        z = __hmax2( z, b2 );
+    }
+    else
+    { // right-aligned: ties go to the gap, state 4 is never recorded (:693-699)
+        d = __hge2_mask( a, z ) & 0x00010001u;
+        z = __hmax2( z, a );
+        d = sel2( __hge2_mask( b, z ), 0x00020002u, d );
+        z = __hmax2( z, b );
+        d = sel2( __hge2_mask( a2, z ), 0x00030003u, d );
+        z = __hmax2( z, a2 );
+        z = __hmax2( z, b2 );
+    }
+    z = __hmin2( z, K.hMatch );
+    o.un = __hsub2( z, vt1 ), o.vn = __hsub2( z, ut );
+    // x' = max(a - (z - q), 0) - (q + e) = max(a - z - e, -q - e); the continuation flag is a - z > -q
+    const __half2 az = __hsub2( a, z ), bz = __hsub2( b, z ), a2z = __hsub2( a2, z ), b2z = __hsub2( b2, z );
+    if( LEFT )
+    {
+        d |= __hgt2_mask( az, K.hNegQ ) & 0x00080008u;
+        d |= __hgt2_mask( bz, K.hNegQ ) & 0x00100010u;
+        d |= __hgt2_mask( a2z, K.hNegQ2 ) & 0x00200020u;
+        d |= __hgt2_mask( b2z, K.hNegQ2 ) & 0x00400040u;
+    }
+    else
+    {
+        d |= __hge2_mask( az, K.hNegQ ) & 0x00080008u;
+        d |= __hge2_mask( bz, K.hNegQ ) & 0x00100010u;
+        d |= __hge2_mask( a2z, K.hNegQ2 ) & 0x00200020u;
+        d |= __hge2_mask( b2z, K.hNegQ2 ) & 0x00400040u;
+    }
+    o.xn = __hmax2( __hsub2( az, K.hE ), K.hNegQE );
+    o.yn = __hmax2( __hsub2( bz, K.hE ), K.hNegQE );
+    o.x2n = __hmax2( __hsub2( a2z, K.hE2 ), K.hNegQE2 );
+    o.y2n = __hmax2( __hsub2( b2z, K.hE2 ), K.hNegQE2 );
+    o.d = d;
+    return o;
+}
+
+// H pair of a row: interior cells add v to their own old H, the cell at en0 adds u (v in row 0) to hleft
+__device__ __forceinline__ unsigned p2_hrow( const unsigned me, const unsigned meEn, const __half2 un, const __half2 vn,
+                                             const unsigned hOwn, const unsigned hLeft )
+{
+    const unsigned add = h2u( __hadd2( u2h( sel2( me & meEn, h2u( un ), h2u( vn ) ) ), u2h( 0x66006600u ) ) ) &
+                         0x03FF03FFu; // 1536 + value: the mantissa holds 512 + value
+    return __vsub2( __vadd2( sel2( me, hLeft, hOwn ), add ), 0x02000200u );
+}
+
+template <int W, bool LEFT>
+__device__ __forceinline__ bool ksw_rows_p2x2( const KswScore& P, const SeqAccess& seq, const int qlen, const int tlen,
+                                               const int w, const int zdrop, KswSmemQ<W>& sm,
+                                               unsigned char* __restrict__ tb, KswOut& ez )
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int M = W - 1;
+    const int q = P.q, e = P.e, q2 = P.q2, e2 = P.e2, qe = q + e;
+    const int scM = P.match;
+    const int ncol16 = ksw_ncol16( qlen, tlen, w );
+    const int nrows = qlen + tlen - 1;
+    P2Const K;
+    K.hMatch = h2i( scM ), K.hNegQ = h2i( -q ), K.hNegQ2 = h2i( -q2 ), K.hNegQE = h2i( -q - e );
+    K.hNegQE2 = h2i( -q2 - e2 ), K.hE = h2i( e ), K.hE2 = h2i( e2 );
+    const __half2 hCodeN = u2h( 0x10001000u ); // base code c is stored as the half with bits c << 10
+    const unsigned uMatch = h2u( K.hMatch ), uMis = h2u( h2i( P.mismatch ) ), uN = h2u( h2i( -e2 ) );
+    const unsigned short init6 = __half_as_ushort( __int2half_rn( -q - e ) ),
+                         init25 = __half_as_ushort( __int2half_rn( -q2 - e2 ) );
+    const unsigned init6x2 = (unsigned)init6 * 0x10001u, init25x2 = (unsigned)init25 * 0x10001u;
+    // first-column values of the rows (kswcpp_core.h:562-579): row 0, rows below / at / above the long-gap threshold
+    const unsigned short fc0 = init6, fc1 = __half_as_ushort( __int2half_rn( -e ) ),
+                         fc2 = __half_as_ushort( __int2half_rn( P.long_diff ) ),
+                         fc3 = __half_as_ushort( __int2half_rn( -e2 ) );
+    unsigned* const pu = reinterpret_cast<unsigned*>( sm.u );
+    unsigned* const pv = reinterpret_cast<unsigned*>( sm.v );
+    unsigned* const px = reinterpret_cast<unsigned*>( sm.x );
+    unsigned* const py = reinterpret_cast<unsigned*>( sm.y );
+    unsigned* const px2 = reinterpret_cast<unsigned*>( sm.x2 );
+    unsigned* const py2 = reinterpret_cast<unsigned*>( sm.y2 );
+    unsigned* const ptc = reinterpret_cast<unsigned*>( sm.tc );
+    unsigned short* const su = reinterpret_cast<unsigned short*>( sm.u );
+    unsigned short* const sv = reinterpret_cast<unsigned short*>( sm.v );
+    unsigned short* const sx = reinterpret_cast<unsigned short*>( sm.x );
+    unsigned short* const sy = reinterpret_cast<unsigned short*>( sm.y );
+    unsigned short* const sx2 = reinterpret_cast<unsigned short*>( sm.x2 );
+    unsigned short* const sy2 = reinterpret_cast<unsigned short*>( sm.y2 );
+    unsigned short* const stc = reinterpret_cast<unsigned short*>( sm.tc );
+    {
+        unsigned short* const qa = reinterpret_cast<unsigned short*>( sm.qa );
+        unsigned short* const qb = reinterpret_cast<unsigned short*>( sm.qb );
+        for( int j = lane; j < W; j += 32 )
+        { // qa[j] = rev[j-2], qb[j] = qa[j+1] = rev[j-1], rev[j] = q[qlen-1-j]
+            const int a = j - 2, b = j - 1;
+            qa[ j ] = (unsigned short)( ( ( a >= 0 && a < qlen ) ? seq.Q( qlen - 1 - a ) : 0 ) << 10 );
+            qb[ j ] = (unsigned short)( ( ( b >= 0 && b < qlen ) ? seq.Q( qlen - 1 - b ) : 0 ) << 10 );
+        }
+    }
+    int inited_end = 0;
+    unsigned cells = 0; // < W * 2^16
+    // H buffers: hin holds the H row of the last finished row; hbest the row of the running maximum (-1: none yet)
+    int hin = 0, hbest = -1;
+    int bR = 0, bSt0 = 0, bEn0 = 0;
+    const int T0 = scM * qlen;
+    unsigned char* rowBase = tb; // tb + r * ncol16
+    bool stop = false;
+    for( int r = 0; r < nrows && !stop; r += 2, rowBase += 2 * ncol16 )
+    {
+        const bool has2 = r + 1 < nrows;
+        if( r + ( has2 ? 1 : 0 ) > w )
+            return false; // the band term of the limits would become active
+        // band of the two rows (the band term is inactive while r <= w)
+        const int st0 = max( 0, r - qlen + 1 ), en0 = min( tlen - 1, r );
+        const int st1 = max( 0, r - qlen + 2 ), en1 = has2 ? min( tlen - 1, r + 1 ) : en0 - 64 * 1024;
+        const int enP = has2 ? en1 : en0; // last column of the pass
+        cells += (unsigned)( en0 - st0 + 1 ) + ( has2 ? (unsigned)( en1 - st1 + 1 ) : 0u );
+        if( inited_end <= enP + 1 )
+        { // target codes of the columns entering the window
+            const int idx = inited_end + lane;
+            stc[ idx & M ] = (unsigned short)( ( idx < tlen ? seq.T( idx ) : 0 ) << 10 );
+            inited_end += 32;
+        }
+        const unsigned short fcA = r == 0 ? fc0 : r < P.long_thres ? fc1 : r == P.long_thres ? fc2 : fc3;
+        const unsigned short fcB = r + 1 < P.long_thres ? fc1 : r + 1 == P.long_thres ? fc2 : fc3;
+        if( en0 == r && lane == 0 )
+            sy[ r & M ] = init6, sy2[ r & M ] = init25, su[ r & M ] = fcA;
+        const int p0 = st0 & ~1;
+        // left neighbour of the first pair (kswcpp_core.h:562-579), kept in the high half; column p0 - 1 is not
+        // touched by row r, so row r + 1 finds the same values there (except for the first-column value)
+        unsigned cX = (unsigned)init6 << 16, cX2 = (unsigned)init25 << 16, cV = (unsigned)fcA << 16,
+                 cVb = (unsigned)fcB << 16;
+        short* const Hin = sm.H[ hin ];
+        // outputs: row r + 1 overwrites the input row in place unless that row holds the maximum
+        const int o1 = hin == hbest ? ( hin + 1 ) % 3 : ( hbest < 0 ? ( hin + 1 ) % 3 : 3 - hin - hbest );
+        const int o2 = hin == hbest ? ( hin + 2 ) % 3 : hin;
+        unsigned* const pHin = reinterpret_cast<unsigned*>( Hin );
+        unsigned* const pH1 = reinterpret_cast<unsigned*>( sm.H[ o1 ] );
+        unsigned* const pH2 = reinterpret_cast<unsigned*>( sm.H[ o2 ] );
+        unsigned cH = 0; // H of column p0 - 1 (high half): only read by a cell at en == p0 (never in band then)
+        if( p0 > 0 )
+        {
+            const int kp = ( p0 - 1 ) & M;
+            cX = (unsigned)sx[ kp ] << 16, cX2 = (unsigned)sx2[ kp ] << 16, cV = cVb = (unsigned)sv[ kp ] << 16;
+            cH = (unsigned)(unsigned short)Hin[ kp ] << 16;
+        }
+        unsigned cXb = cX, cX2b = cX2, cHb = cH; // the same column after row r
+        // old H left of en0, read before the pass updates it (:194-195); row 0: H[0] = v[0] - (q + e) (:247)
+        const int hprev = r == 0 ? -qe : (int)Hin[ ( en0 - ( en0 > 0 ? 1 : 0 ) ) & M ];
+        const unsigned hprev2 = ( (unsigned)hprev & 0xFFFFu ) * 0x10001u;
+        __syncwarp( );
+        const int c = qlen - 1 - r; // reversed-query index of column t is t + c (row r), t + c - 1 (row r + 1)
+        const unsigned* const pqA = reinterpret_cast<const unsigned*>( ( c & 1 ) ? sm.qb : sm.qa );
+        const unsigned* const pqB = reinterpret_cast<const unsigned*>( ( c & 1 ) ? sm.qa : sm.qb );
+        const int qshA = c + 2 - ( c & 1 ), qshB = c + 1 - ( ( c - 1 ) & 1 );
+        unsigned char* const rowpA = rowBase - ( st0 & ~15 );
+        unsigned char* const rowpB = rowBase + ncol16 - ( st1 & ~15 );
+        const int p1 = st1 & ~1;
+        const unsigned meEnA = en0 > 0 ? 0xFFFFFFFFu : 0u;
+        const unsigned injB = ( has2 && en1 == r + 1 ) ? 0xFFFFFFFFu : 0u; // column r + 1 enters in row r + 1
+        const unsigned fcBx2 = (unsigned)fcB * 0x10001u;
+        unsigned mA = 0x80008000u, mB = 0x80008000u, hbA = 0x80008000u, hbB = 0x80008000u;
+        int t0 = p0 + 2 * lane;
+        unsigned termA; // scM * (qlen - 1 - r + t) for the two cells of this lane; row r + 1: one scM less
+        {
+            const int a0 = scM * ( c + t0 );
+            termA = ( (unsigned)a0 & 0xFFFFu ) | ( (unsigned)( a0 + scM ) << 16 );
+        }
+        const unsigned termStep = ( (unsigned)( scM * 64 ) & 0xFFFFu ) * 0x10001u;
+        const unsigned scM2 = ( (unsigned)scM & 0xFFFFu ) * 0x10001u;
+        for( int base = p0; base <= enP; base += 64, t0 += 64 )
+        {
+            const int kk = ( t0 & M ) >> 1; // pair index in the window
+            const unsigned xo = px[ kk ], vo = pv[ kk ], x2o = px2[ kk ];
+            const __half2 ut = u2h( pu[ kk ] ), yo = u2h( py[ kk ] ), y2o = u2h( py2[ kk ] );
+            const unsigned hOld = pHin[ kk ];
+            const __half2 tcp = u2h( ptc[ kk ] );
+            const __half2 qpA = u2h( pqA[ ( ( t0 + qshA ) & M ) >> 1 ] );
+            const __half2 qpB = u2h( pqB[ ( ( t0 + qshB ) & M ) >> 1 ] );
+            const bool more = base + 64 <= enP;
+            // ---------------- row r
+            unsigned upx = __shfl_up_sync( FULL, xo, 1 ), upv = __shfl_up_sync( FULL, vo, 1 ),
+                     upx2 = __shfl_up_sync( FULL, x2o, 1 );
+            if( lane == 0 )
+                upx = cX, upv = cV, upx2 = cX2;
+            if( more )
+                cX = __shfl_sync( FULL, xo, 31 ), cV = __shfl_sync( FULL, vo, 31 ), cX2 = __shfl_sync( FULL, x2o, 31 );
+            unsigned z0 = sel2( __heq2_mask( tcp, qpA ), uMatch, uMis );
+            z0 = sel2( __hge2_mask( __hmax2( tcp, qpA ), hCodeN ), uN, z0 );
+            P2Cell A = p2_cell<LEFT>( K, u2h( __byte_perm( upx, xo, 0x5432 ) ), u2h( __byte_perm( upv, vo, 0x5432 ) ),
+                                      u2h( __byte_perm( upx2, x2o, 0x5432 ) ), ut, yo, y2o, u2h( z0 ) );
+            const int deA = en0 - t0; // 0: the low cell is en0, 1: the high cell
+            const unsigned meA = (unsigned)deA < 2u ? ( 0xFFFFu << ( deA << 4 ) ) : 0u;
+            const unsigned hA = p2_hrow( meA, meEnA, A.un, A.vn, hOld, hprev2 );
+            const unsigned vmA = ( ( t0 >= st0 && deA >= 0 ) ? 0xFFFFu : 0u ) | ( deA >= 1 ? 0xFFFF0000u : 0u );
+            const unsigned hmA = sel2( vmA, hA, 0x80008000u );
+            mA = __vmaxs2( mA, hmA );
+            hbA = __vmaxs2( hbA, __vadd2( hmA, termA & vmA ) );
+            if( deA >= 0 )
+            {
+                pH1[ kk ] = hA;
+                *reinterpret_cast<unsigned short*>( rowpA + t0 ) = (unsigned short)__byte_perm( A.d, 0, 0x4420 );
+            }
+            // ---------------- row r + 1 on the values just computed
+            const int deB = en1 - t0;
+            // (with en1 == 0, a one-column target, the cell at en1 follows the interior formula: own H plus v)
+            const unsigned meB = ( (unsigned)deB < 2u && en1 > 0 ) ? ( 0xFFFFu << ( deB << 4 ) ) : 0u;
+            {
+                const unsigned inj = meB & injB; // the entering column starts from the border values
+                A.un = u2h( sel2( inj, fcBx2, h2u( A.un ) ) );
+                A.yn = u2h( sel2( inj, init6x2, h2u( A.yn ) ) );
+                A.y2n = u2h( sel2( inj, init25x2, h2u( A.y2n ) ) );
+            }
+            const unsigned xn = h2u( A.xn ), vn = h2u( A.vn ), x2n = h2u( A.x2n );
+            unsigned upxb = __shfl_up_sync( FULL, xn, 1 ), upvb = __shfl_up_sync( FULL, vn, 1 ),
+                     upx2b = __shfl_up_sync( FULL, x2n, 1 ), uph = __shfl_up_sync( FULL, hA, 1 );
+            if( lane == 0 )
+                upxb = cXb, upvb = cVb, upx2b = cX2b, uph = cHb;
+            if( more )
+                cXb = __shfl_sync( FULL, xn, 31 ), cVb = __shfl_sync( FULL, vn, 31 ),
+                cX2b = __shfl_sync( FULL, x2n, 31 ), cHb = __shfl_sync( FULL, hA, 31 );
+            unsigned z1 = sel2( __heq2_mask( tcp, qpB ), uMatch, uMis );
+            z1 = sel2( __hge2_mask( __hmax2( tcp, qpB ), hCodeN ), uN, z1 );
+            const P2Cell B = p2_cell<LEFT>( K, u2h( __byte_perm( upxb, xn, 0x5432 ) ),
+                                            u2h( __byte_perm( upvb, vn, 0x5432 ) ),
+                                            u2h( __byte_perm( upx2b, x2n, 0x5432 ) ), A.un, A.yn, A.y2n, u2h( z1 ) );
+            // the cell at en1 adds u to H_r of its left neighbour
+            const unsigned hB = p2_hrow( meB, 0xFFFFFFFFu, B.un, B.vn, hA, __byte_perm( uph, hA, 0x5432 ) );
+            const unsigned vmB = ( ( t0 >= st1 && deB >= 0 ) ? 0xFFFFu : 0u ) | ( deB >= 1 ? 0xFFFF0000u : 0u );
+            const unsigned hmB = sel2( vmB, hB, 0x80008000u );
+            mB = __vmaxs2( mB, hmB );
+            hbB = __vmaxs2( hbB, __vadd2( hmB, __vsub2( termA, scM2 ) & vmB ) );
+            termA = __vadd2( termA, termStep );
+            if( has2 )
+            {
+                if( deB >= 0 )
+                {
+                    pu[ kk ] = h2u( B.un ), pv[ kk ] = h2u( B.vn ), px[ kk ] = h2u( B.xn ), py[ kk ] = h2u( B.yn );
+                    px2[ kk ] = h2u( B.x2n ), py2[ kk ] = h2u( B.y2n );
+                    pH2[ kk ] = hB;
+                    if( t0 >= p1 )
+                        *reinterpret_cast<unsigned short*>( rowpB + t0 ) = (unsigned short)__byte_perm( B.d, 0, 0x4420 );
+                }
+            }
+        }
+        const int maxA = __reduce_max_sync( FULL, max( (int)(short)( mA & 0xFFFFu ), (int)mA >> 16 ) );
+        const int maxB = __reduce_max_sync( FULL, max( (int)(short)( mB & 0xFFFFu ), (int)mB >> 16 ) );
+        __syncwarp( );
+        int hlast = o1; // buffer of the last finished row
+        // ---- row r: ksw_apply_zdrop (:22-44) with the position resolved only when it is consumed
+        for( int k = 0; k < 2; k++ )
+        {
+            if( k == 1 && !has2 )
+                break;
+            const int rr = r + k, sst = k ? st1 : st0, een = k ? en1 : en0, max_H = k ? maxB : maxA, ob = k ? o2 : o1;
+            hlast = ob;
+            if( max_H > ez.max )
+            {
+                ez.max = max_H;
+                hbest = ob, bR = rr, bSt0 = sst, bEn0 = een;
+            }
+            else if( zdrop >= 0 && ez.max - max_H > zdrop )
+            {
+                // resolve the position of the running maximum first
+                int bt = ez.max_t, bq = ez.max_q;
+                if( hbest >= 0 )
+                    bt = ksw_p2_argmax( sm.H[ hbest ], M, bSt0, bEn0, lane ), bq = bR - bt;
+                const int max_t = ksw_p2_argmax( sm.H[ ob ], M, sst, een, lane );
+                if( max_t >= bt && rr - max_t >= bq )
+                {
+                    const int tl = max_t - bt, ql = ( rr - max_t ) - bq;
+                    const int l = tl > ql ? tl - ql : ql - tl;
+                    if( ez.max - max_H > zdrop + l * e2 )
+                    {
+                        ez.zdropped = 1;
+                        stop = true;
+                        break;
+                    }
+                }
+            }
+        }
+        hin = hlast;
+        if( !stop )
+        {
+            const int BA = __reduce_max_sync( FULL, max( (int)(short)( hbA & 0xFFFFu ), (int)hbA >> 16 ) );
+            const int BB = __reduce_max_sync( FULL, max( (int)(short)( hbB & 0xFFFFu ), (int)hbB >> 16 ) );
+            const int rl = r + ( has2 ? 1 : 0 ); // last row of the pass
+            if( has2 && rl >= qlen )
+            { // all terms are < 2^31: is16 bounds qlen, tlen and the scores
+                const int j = rl + 1;
+                const int T = T0 - min( q + e * j, q2 + e2 * j );
+                if( max( max( BA, BB ), T ) <= ez.max )
+                    stop = true;
+            }
+        }
+    }
+    if( hbest >= 0 )
+    {
+        __syncwarp( );
+        ez.max_t = ksw_p2_argmax( sm.H[ hbest ], M, bSt0, bEn0, lane ), ez.max_q = bR - ez.max_t;
+    }
+    ez.cells = cells;
+    __syncwarp( );
+    return true;
+}
+
+#ifndef MA_KSW_P2X2
+#define MA_KSW_P2X2 1
+#endif
 // bytes of shared memory per warp: the scalar window and, for the narrow bins, the packed one share the space
 template <int W> struct KswSmemBytes
 {
     static constexpr bool kPacked = W <= 512;
     static constexpr size_t kScalar = sizeof( KswSmem<W> );
-    static constexpr size_t kP2 = kPacked ? sizeof( KswSmemP < W <= 512 ? W : 2 > ) : 0;
+    static constexpr size_t kP2a = kPacked ? sizeof( KswSmemP < W <= 512 ? W : 2 > ) : 0;
+    static constexpr size_t kP2b = kPacked ? sizeof( KswSmemQ < W <= 512 ? W : 2 > ) : 0;
+    static constexpr size_t kP2 = kP2a > kP2b ? kP2a : kP2b;
     static constexpr size_t value = ( ( kScalar > kP2 ? kScalar : kP2 ) + 15 ) / 16 * 16;
 };
 
@@ -832,9 +1181,15 @@ __device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int
         if( bEarlyStop && w >= qlen && is16 && qlen + 4 <= W && ( qlen < tlen ? qlen : tlen ) + 40 <= W &&
             ksw_p2_params_ok( P ) )
         {
+#if MA_KSW_P2X2
+            KswSmemQ<W>& sp = reinterpret_cast<KswSmemQ<W>&>( sm );
+            const bool ok = bLeft ? ksw_rows_p2x2<W, true>( P, seq, qlen, tlen, w, zdrop, sp, tb, ez )
+                                  : ksw_rows_p2x2<W, false>( P, seq, qlen, tlen, w, zdrop, sp, tb, ez );
+#else
             KswSmemP<W>& sp = reinterpret_cast<KswSmemP<W>&>( sm );
             const bool ok = bLeft ? ksw_rows_p2<W, true>( P, seq, qlen, tlen, w, zdrop, sp, tb, ez )
                                   : ksw_rows_p2<W, false>( P, seq, qlen, tlen, w, zdrop, sp, tb, ez );
+#endif
             if( ok )
                 return;
             ez.max_q = ez.max_t = ez.mqe_t = ez.mte_q = -1;
@@ -926,7 +1281,7 @@ struct KswBatchArgs
 };
 
 #ifndef MA_KSW_MINB
-#define MA_KSW_MINB 3
+#define MA_KSW_MINB 2
 #endif
 template <int W> __global__ void __launch_bounds__( 256, MA_KSW_MINB ) ksw_batch_kernel( KswBatchArgs A )
 {
