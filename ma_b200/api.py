@@ -98,6 +98,7 @@ def load_library():
     lib.ma_b200_launch_count.restype = i64
     lib.ma_b200_set_params.argtypes = [vp, ctypes.POINTER(Params)]
     lib.ma_b200_ksw_set_extension_only.argtypes = [vp, ctypes.c_int32]
+    lib.ma_b200_set_batch_split.argtypes = [vp, i64]
     lib.ma_b200_ksw_upload.argtypes = [vp, i64, vp, vp, i64]
     lib.ma_b200_ksw_run.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     lib.ma_b200_ksw_download.argtypes = [vp, vp, vp, i64, ctypes.POINTER(i64)]
@@ -274,6 +275,10 @@ class Context:
         return g.value
 
     # ---- banded DP ------------------------------------------------------------------------------------------
+    def set_batch_split(self, reads_per_subbatch: int):
+        """Sub-batch size of the pipelined align_batch (batches of >= 2 sub-batches are pipelined)."""
+        self._check(self.lib.ma_b200_set_batch_split(self.h, int(reads_per_subbatch)))
+
     def ksw_set_extension_only(self, on: bool):
         """Early-termination mode for extension tasks: only max / max_q / max_t / CIGAR are defined."""
         self._check(self.lib.ma_b200_ksw_set_extension_only(self.h, 1 if on else 0))

@@ -5,7 +5,10 @@
 #include "index_build.cuh"
 #include <algorithm>
 #include <numeric>
+#include <condition_variable>
+#include <mutex>
 #include <stdexcept>
+#include <thread>
 
 using namespace ma;
 
@@ -56,6 +59,8 @@ struct ma_b200_ctx
     int max_read_len = 0;
     int stage_done = 0;
     bool ksw_extension_only = false; // ma_b200_ksw_set_extension_only
+    int64_t batch_split = 262144; // ma_b200_align_batch: reads per sub-batch of the pipelined form
+    ma_b200_ctx* shadow = nullptr; // second set of slabs + stream for the pipelined ma_b200_align_batch
     DevBuf<unsigned char> reads;
     DevBuf<long long> read_off;
     DevBuf<ReadInfo> info;
@@ -199,6 +204,8 @@ extern "C" void ma_b200_destroy( ma_b200_ctx* ctx )
     if( !ctx )
         return;
     cudaSetDevice( ctx->device );
+    if( ctx->shadow )
+        ma_b200_destroy( ctx->shadow );
     if( ctx->stream )
         cudaStreamDestroy( ctx->stream );
     delete ctx;
@@ -1101,17 +1108,164 @@ extern "C" int ma_b200_align_download( ma_b200_ctx* ctx, ma_b200_read_info* info
     MA_API_END
 }
 
+extern "C" int ma_b200_set_batch_split( ma_b200_ctx* ctx, int64_t reads_per_subbatch )
+{
+    if( !ctx || reads_per_subbatch < 1 )
+        return MA_B200_EINVAL;
+    ctx->batch_split = reads_per_subbatch;
+    return MA_B200_OK;
+}
+
+namespace
+{
+// Pipelined form of ma_b200_align_batch: the batch is cut into sub-batches that alternate between two sets of device
+// slabs (the context and its shadow, one host thread and one stream each), so that the host<->device copies of one
+// sub-batch run under the kernels of the other. Results are identical to the one-shot form: RANSAC streams are
+// seeded by the global read index, outputs are written at their final offsets.
+struct BatchPipe
+{
+    int64_t n_reads, n_sub;
+    const uint8_t* reads;
+    const int64_t* offsets;
+    ma_b200_read_info* info;
+    ma_b200_alignment* alns;
+    int64_t cap_alns;
+    uint32_t* runs;
+    int64_t cap_runs;
+    int64_t split;
+    uint32_t srand_base;
+    std::mutex mtx;
+    std::condition_variable cv;
+    std::vector<int64_t> nAlns, nRuns; // per sub-batch, -1 until its kernels are done
+    std::vector<ma_b200_align_stats> st;
+    int rc = 0;
+    std::string err;
+
+    void fail( int code, const std::string& msg )
+    {
+        std::lock_guard<std::mutex> g( mtx );
+        if( !rc )
+            rc = code, err = msg;
+        cv.notify_all( );
+    }
+    void work( ma_b200_ctx* c, int64_t first )
+    {
+        cudaSetDevice( c->device );
+        std::vector<int64_t> off;
+        for( int64_t k = first; k < n_sub; k += 2 )
+        {
+            {
+                std::lock_guard<std::mutex> g( mtx );
+                if( rc )
+                    return;
+            }
+            const int64_t r0 = k * split, r1 = std::min( n_reads, r0 + split ), n = r1 - r0;
+            off.resize( (size_t)n + 1 );
+            for( int64_t i = 0; i <= n; i++ )
+                off[ i ] = offsets[ r0 + i ] - offsets[ r0 ];
+            c->params.srand_base = srand_base + (uint32_t)r0;
+            int e = ma_b200_align_upload( c, n, reads + offsets[ r0 ], off.data( ) );
+            if( !e )
+                e = ma_b200_align_run( c, MA_B200_STAGE_ALIGN, 0, &st[ k ] );
+            if( e )
+                return fail( e, c->err );
+            int64_t a0 = 0, u0 = 0;
+            {
+                std::unique_lock<std::mutex> g( mtx );
+                nAlns[ k ] = c->n_sets, nRuns[ k ] = c->n_runs;
+                cv.notify_all( );
+                cv.wait( g, [ & ] {
+                    if( rc )
+                        return true;
+                    for( int64_t j = 0; j < k; j++ )
+                        if( nAlns[ j ] < 0 )
+                            return false;
+                    return true;
+                } );
+                if( rc )
+                    return;
+                for( int64_t j = 0; j < k; j++ )
+                    a0 += nAlns[ j ], u0 += nRuns[ j ];
+            }
+            if( a0 + c->n_sets > cap_alns || u0 + c->n_runs > cap_runs )
+                return fail( MA_B200_ENOMEM, "alignment buffers too small" );
+            e = ma_b200_align_download( c, info + r0, alns + a0, cap_alns - a0, runs + u0, cap_runs - u0 );
+            if( e )
+                return fail( e, c->err );
+            // sub-batch-relative indices -> batch-relative (seed_off keeps pointing into the device slab)
+            for( int64_t i = 0; i < n; i++ )
+                info[ r0 + i ].set_off += (int32_t)a0;
+            for( int64_t j = 0; j < c->n_sets; j++ )
+                alns[ a0 + j ].read += (int32_t)r0, alns[ a0 + j ].run_off += u0;
+        }
+    }
+};
+} // namespace
+
 extern "C" int ma_b200_align_batch( ma_b200_ctx* ctx, int64_t n_reads, const uint8_t* reads, const int64_t* offsets,
                                     ma_b200_read_info* info, ma_b200_alignment* alns, int64_t cap_alns,
                                     uint32_t* runs, int64_t cap_runs, ma_b200_align_stats* stats )
 {
-    int rc = ma_b200_align_upload( ctx, n_reads, reads, offsets );
-    if( rc )
-        return rc;
-    rc = ma_b200_align_run( ctx, MA_B200_STAGE_ALIGN, 0, stats );
-    if( rc )
-        return rc;
-    return ma_b200_align_download( ctx, info, alns, cap_alns, runs, cap_runs );
+    if( !ctx )
+        return MA_B200_EINVAL;
+    if( n_reads < 2 * ctx->batch_split || !ctx->have_index || !reads || !offsets || !info || !alns || !runs )
+    { // one shot (also the path that reports argument errors)
+        int rc = ma_b200_align_upload( ctx, n_reads, reads, offsets );
+        if( rc )
+            return rc;
+        rc = ma_b200_align_run( ctx, MA_B200_STAGE_ALIGN, 0, stats );
+        if( rc )
+            return rc;
+        return ma_b200_align_download( ctx, info, alns, cap_alns, runs, cap_runs );
+    }
+    if( !ctx->shadow )
+    {
+        const int rc = ma_b200_create( ctx->device, &ctx->shadow );
+        if( rc )
+        {
+            ctx->err = "align_batch: cannot create the second pipeline context";
+            return rc;
+        }
+    }
+    ma_b200_ctx* sh = ctx->shadow;
+    const ma_b200_params saved = ctx->params;
+    sh->params = ctx->params;
+    sh->index = ctx->index, sh->have_index = true; // a view: the index slabs stay owned by ctx
+    const int64_t l0 = ctx->launches, l1 = sh->launches;
+    BatchPipe P;
+    P.n_reads = n_reads, P.split = ctx->batch_split, P.n_sub = ( n_reads + P.split - 1 ) / P.split;
+    P.reads = reads, P.offsets = offsets, P.info = info, P.alns = alns, P.cap_alns = cap_alns, P.runs = runs;
+    P.cap_runs = cap_runs, P.srand_base = saved.srand_base;
+    P.nAlns.assign( (size_t)P.n_sub, -1 ), P.nRuns.assign( (size_t)P.n_sub, -1 );
+    P.st.assign( (size_t)P.n_sub, ma_b200_align_stats{ } );
+    std::thread other( [ & ] { P.work( sh, 1 ); } );
+    P.work( ctx, 0 );
+    other.join( );
+    cudaSetDevice( ctx->device );
+    ctx->params = saved;
+    ctx->stage_done = 0; // the device slabs hold the last sub-batches only: staged downloads need a staged run
+    sh->stage_done = 0;
+    if( P.rc )
+    {
+        ctx->err = P.err;
+        return P.rc;
+    }
+    if( stats )
+    {
+        ma_b200_align_stats t{ };
+        for( const auto& s : P.st )
+        {
+            t.n_reads += s.n_reads, t.n_seeds += s.n_seeds, t.n_sets += s.n_sets, t.n_set_seeds += s.n_set_seeds;
+            t.n_tasks += s.n_tasks, t.n_runs += s.n_runs, t.n_cigar_words += s.n_cigar_words, t.n_ext += s.n_ext;
+            t.n_invpsi += s.n_invpsi, t.n_dropped += s.n_dropped, t.dp_cells += s.dp_cells, t.n_lookup += s.n_lookup;
+            t.ms_seed += s.ms_seed, t.ms_locate += s.ms_locate, t.ms_socharm += s.ms_socharm, t.ms_plan += s.ms_plan;
+            t.ms_dp += s.ms_dp, t.ms_assemble += s.ms_assemble, t.ms_total += s.ms_total;
+        }
+        t.launches = (int32_t)( ( ctx->launches - l0 ) + ( sh->launches - l1 ) );
+        *stats = t;
+    }
+    ctx->launches += sh->launches - l1; // ma_b200_launch_count counts both pipelines
+    return MA_B200_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ roofline probe

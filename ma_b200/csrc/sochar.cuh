@@ -422,7 +422,7 @@ MA_HD inline double delta_distance( const DSeed& s, double fAngle, long long uiR
 }
 
 // harmonization.cpp:182-249: sh[0..n) -> ends[0..return)
-MA_HD inline int linesweep( const DSeed* S, Shadow* sh, int n, Shadow* ends, long long uiRStart, double fAngle )
+MA_HD MA_NOINLINE inline int linesweep( const DSeed* S, Shadow* sh, int n, Shadow* ends, long long uiRStart, double fAngle )
 {
     stl::sort( sh, sh + n, []( const Shadow& xA, const Shadow& xB ) {
         if( xA.a == xB.a )
@@ -473,7 +473,8 @@ MA_HD inline long long double_to_ll( double d ) // (int64_t)d as x86-64 cvttsd2s
 }
 
 // harmonization.cpp:251-373. in[0..nIn) is compacted in place by the outlier filter; out receives the result.
-MA_HD inline int harmonize_one( DSeed* in, int& nIn, DSeed* out, HarmScratch& W, GlibcRand& rng )
+// (not inlined: two call sites, and the instruction footprint of socharm_kernel is what bounds it)
+MA_HD MA_NOINLINE inline int harmonize_one( DSeed* in, int& nIn, DSeed* out, HarmScratch& W, GlibcRand& rng )
 {
     int nOut = 0;
     if( nIn > 1 )

@@ -8,8 +8,10 @@
 
 #if defined( __CUDACC__ )
 #define MA_HD __host__ __device__
+#define MA_NOINLINE __noinline__
 #else
 #define MA_HD
+#define MA_NOINLINE __attribute__( ( noinline ) )
 #endif
 
 namespace ma

@@ -89,6 +89,43 @@ def test_batch_call_equals_staged_calls_and_sharding(gold_index):
     ctx.close()
 
 
+def _records(info, alns, runs, n):
+    """Per read: its alignment records in the reference's result order (slab order is allocation order, not fixed)."""
+    out = []
+    for i in range(n):
+        a = alns[info["set_off"][i]:info["set_off"][i] + info["n_sets"][i]]
+        assert (a["read"] == i).all()
+        for k in np.argsort(a["rank"], kind="stable"):
+            x = a[k]
+            out.append((i, int(x["begin_q"]), int(x["end_q"]), int(x["begin_ref"]), int(x["end_ref"]), int(x["score"]),
+                        int(x["soc_index"]), tuple(runs[x["run_off"]:x["run_off"] + x["n_runs"]].tolist())))
+    return out
+
+
+def test_pipelined_batch_equals_one_shot(gold_index):
+    """The pipelined form of ma_b200_align_batch (sub-batches alternating between two sets of device slabs) returns
+    the same records and statistics, for split sizes that do and do not divide the batch."""
+    reads = PC.read_reads_txt(PC.gold_reads("illumina"))
+    data, off = api.pack_reads(reads)
+    ctx = make_ctx("illumina")
+    ctx.index_upload(gold_index)
+    info, alns, runs, st = ctx.align_batch(data, off)
+    full = _records(info, alns, runs, len(reads))
+    for split in (7, 64, len(reads) // 2):
+        ctx.set_batch_split(split)
+        i2, a2, r2, s2 = ctx.align_batch(data, off)
+        assert np.array_equal(i2["n_sets"], info["n_sets"])
+        assert _records(i2, a2, r2, len(reads)) == full
+        for k in ("n_reads", "n_seeds", "n_sets", "n_tasks", "n_runs", "n_ext", "n_invpsi", "dp_cells"):
+            assert s2[k] == st[k], k
+    # staged calls still work on the same context afterwards
+    ctx.align_upload(data, off)
+    ctx.align_run()
+    i3, a3, r3 = ctx.download_alignments()
+    assert _records(i3, a3, r3, len(reads)) == full
+    ctx.close()
+
+
 def test_edge_batches(gold_index):
     ctx = make_ctx("illumina")
     ctx.index_upload(gold_index)
