@@ -60,6 +60,10 @@ typedef struct
     /* RANSAC draws come from glibc's TYPE_3 rand(); the reference never seeds it itself.  Parity contract
      * (SURVEY.md A-5): the stream for read i is seeded with srand(srand_base + i). */
     uint32_t srand_base;
+    /* MappingQuality (mappingQuality.h:26-36, parameter.h:721-737) and PairedReads (pairedReads.h:43-55,
+     * parameter.h:649-668); use_paired_reads: reads 2k and 2k+1 of a batch are mates ("Use Paired Reads") */
+    int32_t report_n, min_alignment_score, max_supplementary_per_prim, use_paired_reads;
+    double max_overlap_supplementary, paired_mean, paired_std, paired_bonus;
 } ma_b200_params;
 
 int ma_b200_params_preset( const char* name, ma_b200_params* out );
@@ -137,6 +141,7 @@ int ma_b200_index_download( ma_b200_ctx* ctx, uint32_t* bwt_words, int64_t* sa, 
 #define MA_B200_STAGE_SEEDS 1 /* BinarySeeding + ExtractSeeds: located seeds in emission order */
 #define MA_B200_STAGE_SETS 2 /* + StripOfConsiderationSeeds + Harmonization: harmonized seed sets */
 #define MA_B200_STAGE_ALIGN 3 /* + NeedlemanWunsch: alignments */
+#define MA_B200_STAGE_MAPQ 4 /* + MappingQuality, and PairedReads over reads (2k, 2k+1) if use_paired_reads */
 
 typedef struct /* Seed (seed.h:34-43) */
 {
@@ -173,8 +178,14 @@ typedef struct /* Alignment (alignment.h:55-95); runs: word = len << 3 | MatchTy
     int32_t read;
     int64_t run_off;
     int32_t rank; /* position in the read's result vector after the reference's final sort */
-    int32_t pad;
+    int32_t flags; /* MA_B200_ALN_*; valid after MA_B200_STAGE_MAPQ */
+    double mapq; /* Alignment::fMappingQuality (SAM MAPQ = ceil(mapq * 254)); NaN where the reference leaves it unset */
+    int32_t rank_mq; /* position in MappingQuality's result vector, -1: not reported (n-best / minimal score) */
+    int32_t pair_rank; /* paired mode: position in PairedReads' result vector, -1: not in it */
 } ma_b200_alignment;
+#define MA_B200_ALN_SECONDARY 1
+#define MA_B200_ALN_SUPPLEMENTARY 2
+#define MA_B200_ALN_FIRST_MATE 4
 
 typedef struct /* per read: where its seeds / sets / alignments are */
 {

@@ -36,6 +36,10 @@ class Params(ctypes.Structure):
         ("disable_heuristics", ctypes.c_int32),
         ("padding", ctypes.c_int32), ("bandwidth_ext", ctypes.c_int32), ("min_bandwidth_gap", ctypes.c_int32),
         ("zdrop", ctypes.c_int32), ("srand_base", ctypes.c_uint32),
+        ("report_n", ctypes.c_int32), ("min_alignment_score", ctypes.c_int32),
+        ("max_supplementary_per_prim", ctypes.c_int32), ("use_paired_reads", ctypes.c_int32),
+        ("max_overlap_supplementary", ctypes.c_double), ("paired_mean", ctypes.c_double),
+        ("paired_std", ctypes.c_double), ("paired_bonus", ctypes.c_double),
     ]
 
 
@@ -54,10 +58,12 @@ SET_DTYPE = np.dtype([("read", "<i4"), ("ordinal", "<i4"), ("soc_index", "<u4"),
                       ("valid", "<i4"), ("pad", "<i4")])
 ALN_DTYPE = np.dtype([("begin_ref", "<i8"), ("end_ref", "<i8"), ("score", "<i8"), ("begin_q", "<i4"),
                       ("end_q", "<i4"), ("length", "<i4"), ("n_runs", "<i4"), ("soc_index", "<u4"), ("read", "<i4"),
-                      ("run_off", "<i8"), ("rank", "<i4"), ("pad", "<i4")])
+                      ("run_off", "<i8"), ("rank", "<i4"), ("flags", "<i4"), ("mapq", "<f8"), ("rank_mq", "<i4"),
+                      ("pair_rank", "<i4")])
 INFO_DTYPE = np.dtype([("seed_off", "<i8"), ("n_seeds", "<i4"), ("set_off", "<i4"), ("n_sets", "<i4"),
                        ("pad", "<i4")])
-STAGE_SEEDS, STAGE_SETS, STAGE_ALIGN = 1, 2, 3
+STAGE_SEEDS, STAGE_SETS, STAGE_ALIGN, STAGE_MAPQ = 1, 2, 3, 4
+ALN_SECONDARY, ALN_SUPPLEMENTARY, ALN_FIRST_MATE = 1, 2, 4
 
 
 class AlignStats(ctypes.Structure):

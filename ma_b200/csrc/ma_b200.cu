@@ -81,6 +81,8 @@ struct ma_b200_ctx
     DevBuf<unsigned int> runs;
     DevBuf<unsigned int> run_scratch;
     DevBuf<PipeCtrl> ctrl;
+    DevBuf<long long> pair_sc;
+    DevBuf<int> pair_meta;
     PipeCtrl hctrl;
     int64_t n_seeds = 0, n_sets = 0, n_set_seeds = 0, n_tasks = 0, n_runs = 0, n_task_cigar = 0;
     cudaEvent_t ev[ 8 ] = { nullptr };
@@ -148,22 +150,25 @@ extern "C" int ma_b200_params_preset( const char* name, ma_b200_params* p )
     p->genome_size_disable = 10000000, p->disable_heuristics = 0;
     p->padding = 1000, p->bandwidth_ext = 512, p->min_bandwidth_gap = 20, p->zdrop = 200;
     p->srand_base = 0;
+    p->report_n = 0, p->min_alignment_score = 75, p->max_supplementary_per_prim = 1, p->use_paired_reads = 0;
+    p->max_overlap_supplementary = 0.1, p->paired_mean = 400, p->paired_std = 150, p->paired_bonus = 1.25;
     // ParameterSetManager(), parameter.h:1079-1104
     if( s == "default" )
         return MA_B200_OK;
     if( s == "illumina" || s == "illuminapaired" )
     {
         p->seeding_technique = 1, p->max_ambiguity = 500, p->min_num_soc = 10, p->max_num_soc = 20;
+        p->use_paired_reads = s == "illuminapaired";
         return MA_B200_OK;
     }
     if( s == "pacbio" )
     {
-        p->min_num_soc = 5;
+        p->min_num_soc = 5, p->max_supplementary_per_prim = 100;
         return MA_B200_OK;
     }
     if( s == "nanopore" )
     {
-        p->seeding_technique = 1, p->min_num_soc = 5;
+        p->seeding_technique = 1, p->min_num_soc = 5, p->max_supplementary_per_prim = 100;
         return MA_B200_OK;
     }
     return MA_B200_EINVAL;
@@ -776,7 +781,7 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
         ctx->err = "align_run: no index uploaded";
         return MA_B200_ESTATE;
     }
-    if( upto_stage < 1 || upto_stage > 3 )
+    if( upto_stage < 1 || upto_stage > 4 )
         throw std::runtime_error( "align_run: bad stage" );
     for( int i = 0; i < 8; i++ )
         if( !ctx->ev[ i ] )
@@ -967,8 +972,37 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
                 alnsort_kernel<<<full_grid( ctx, alnsort_kernel, 128, n ), 128, 0, s>>>( B );
                 MA_CUDA( cudaGetLastError( ) );
                 ctx->launches++;
+                if( upto_stage >= 4 )
+                { // ---------------- stage 4: MappingQuality (+ PairedReads)
+                    const ma_b200_params& p = ctx->params;
+                    MapqArgs M;
+                    M.P = MapqParams{ p.match, p.report_n, p.min_alignment_score, p.max_supplementary_per_prim,
+                                      p.max_overlap_supplementary, p.paired_mean, p.paired_std, p.paired_bonus };
+                    M.info = ctx->info.p, M.read_off = ctx->read_off.p, M.n_reads = n, M.alns = ctx->alns.p;
+                    M.runs = ctx->runs.p, M.ref_len = ctx->index.ref_len, M.ctrl = ctx->ctrl.p;
+                    M.pair_sc = nullptr, M.pair_meta = nullptr, M.pair_cap = 0;
+                    mapq_kernel<<<full_grid( ctx, mapq_kernel, 128, n ), 128, 0, s>>>( M );
+                    MA_CUDA( cudaGetLastError( ) );
+                    ctx->launches++;
+                    if( p.use_paired_reads )
+                    {
+                        read_ctrl( ctx );
+                        const int most = std::max( 1, ctx->hctrl.max_reported );
+                        const int grid = full_grid( ctx, pair_kernel, 128, ( n + 1 ) / 2 );
+                        M.pair_cap = most * most;
+                        ctx->pair_sc.reserve( (size_t)grid * 128 * M.pair_cap );
+                        ctx->pair_meta.reserve( (size_t)grid * 128 * 2 * M.pair_cap );
+                        M.pair_sc = ctx->pair_sc.p, M.pair_meta = ctx->pair_meta.p;
+                        pair_kernel<<<grid, 128, 0, s>>>( M );
+                        MA_CUDA( cudaGetLastError( ) );
+                        ctx->launches++;
+                        read_ctrl( ctx );
+                        if( ctx->hctrl.overflow_pair )
+                            throw std::runtime_error( "PairedReads: no candidate pair for two aligned mates" );
+                    }
+                }
             }
-            ctx->stage_done = 3;
+            ctx->stage_done = upto_stage;
         }
         else
         {
@@ -1166,7 +1200,7 @@ struct BatchPipe
             c->params.srand_base = srand_base + (uint32_t)r0;
             int e = ma_b200_align_upload( c, n, reads + offsets[ r0 ], off.data( ) );
             if( !e )
-                e = ma_b200_align_run( c, MA_B200_STAGE_ALIGN, 0, &st[ k ] );
+                e = ma_b200_align_run( c, MA_B200_STAGE_MAPQ, 0, &st[ k ] );
             if( e )
                 return fail( e, c->err );
             int64_t a0 = 0, u0 = 0;
@@ -1208,12 +1242,12 @@ extern "C" int ma_b200_align_batch( ma_b200_ctx* ctx, int64_t n_reads, const uin
 {
     if( !ctx )
         return MA_B200_EINVAL;
-    if( n_reads < 2 * ctx->batch_split || !ctx->have_index || !reads || !offsets || !info || !alns || !runs )
+    if( n_reads < 2 * ( ctx->batch_split + ( ctx->batch_split & 1 ) ) || !ctx->have_index || !reads || !offsets || !info || !alns || !runs )
     { // one shot (also the path that reports argument errors)
         int rc = ma_b200_align_upload( ctx, n_reads, reads, offsets );
         if( rc )
             return rc;
-        rc = ma_b200_align_run( ctx, MA_B200_STAGE_ALIGN, 0, stats );
+        rc = ma_b200_align_run( ctx, MA_B200_STAGE_MAPQ, 0, stats );
         if( rc )
             return rc;
         return ma_b200_align_download( ctx, info, alns, cap_alns, runs, cap_runs );
@@ -1233,7 +1267,7 @@ extern "C" int ma_b200_align_batch( ma_b200_ctx* ctx, int64_t n_reads, const uin
     sh->index = ctx->index, sh->have_index = true; // a view: the index slabs stay owned by ctx
     const int64_t l0 = ctx->launches, l1 = sh->launches;
     BatchPipe P;
-    P.n_reads = n_reads, P.split = ctx->batch_split, P.n_sub = ( n_reads + P.split - 1 ) / P.split;
+    P.n_reads = n_reads, P.split = ctx->batch_split + ( ctx->batch_split & 1 ), P.n_sub = ( n_reads + P.split - 1 ) / P.split;
     P.reads = reads, P.offsets = offsets, P.info = info, P.alns = alns, P.cap_alns = cap_alns, P.runs = runs;
     P.cap_runs = cap_runs, P.srand_base = saved.srand_base;
     P.nAlns.assign( (size_t)P.n_sub, -1 ), P.nRuns.assign( (size_t)P.n_sub, -1 );

@@ -33,7 +33,7 @@ enum
     MT_DELETION = 4
 };
 
-struct DAln // 64 bytes
+struct DAln // 80 bytes
 {
     long long begin_ref, end_ref, score;
     int begin_q, end_q;
@@ -42,7 +42,10 @@ struct DAln // 64 bytes
     int read;
     long long run_off; // into the run slab; run word = len << 3 | MatchType
     int rank; // position among the read's alignments after the reference's final std::sort
-    int pad;
+    int flags; // MA_ALN_* (mapq.cuh), set by the MappingQuality / PairedReads stage
+    double mapq; // Alignment::fMappingQuality
+    int rank_mq; // position in MappingQuality's result, -1: not reported
+    int pair_rank; // position in PairedReads' result, -1: not in it
 };
 
 struct NwWindow

@@ -14,6 +14,7 @@
 #pragma once
 #include "ksw.cuh"
 #include "nwglue.cuh"
+#include "mapq.cuh"
 
 namespace ma
 {
@@ -37,7 +38,8 @@ struct PipeCtrl
     unsigned long long n_lookup; // ... of which read the occurrence table
     unsigned long long n_invpsi; // bwt_invPsi steps
     unsigned long long n_dropped; // reads cleared by the seeding drop-off heuristic
-    int overflow_lists, overflow_fseg, overflow_runs;
+    int overflow_lists, overflow_fseg, overflow_runs, overflow_pair;
+    int max_reported; // largest MappingQuality result vector of the batch
     alignas( 128 ) int bin_count[ 8 ];
     alignas( 128 ) unsigned long long bin_tb[ 8 ];
     alignas( 128 ) int bin_cig[ 8 ];
@@ -589,7 +591,8 @@ __global__ void __launch_bounds__( 128 ) nwasm_kernel( NwAsmArgs A )
         const SetHeader h = A.sets[ si ];
         DAln a;
         a.begin_ref = a.end_ref = a.score = 0, a.begin_q = a.end_q = a.length = a.n_runs = 0;
-        a.soc_index = h.soc_index, a.read = h.read, a.run_off = 0, a.rank = h.ordinal, a.pad = 0;
+        a.soc_index = h.soc_index, a.read = h.read, a.run_off = 0, a.rank = h.ordinal, a.flags = 0;
+        a.mapq = NAN, a.rank_mq = -1, a.pair_rank = -1;
         if( h.valid )
         {
             const long long qbase = A.read_off[ h.read ];
@@ -649,6 +652,63 @@ __global__ void __launch_bounds__( 128 ) alnsort_kernel( AlnSortArgs A )
     }
 }
 
+
+struct MapqArgs
+{
+    MapqParams P;
+    const ReadInfo* info;
+    const long long* read_off;
+    int n_reads;
+    DAln* alns;
+    const unsigned int* runs;
+    long long ref_len;
+    long long* pair_sc; // per thread: pair_cap candidate scores
+    int* pair_meta; // per thread: 2 * pair_cap ints
+    int pair_cap;
+    PipeCtrl* ctrl;
+};
+
+// MappingQuality::execute, one thread per read; also records the largest result vector (sizes the pairing scratch)
+__global__ void __launch_bounds__( 128 ) mapq_kernel( MapqArgs A )
+{
+    int ord[ MA_MAX_SETS_PER_READ ];
+    int most = 0;
+    for( int read = blockIdx.x * blockDim.x + threadIdx.x; read < A.n_reads; read += gridDim.x * blockDim.x )
+    {
+        const ReadInfo ri = A.info[ read ];
+        const int m = mapping_quality_read( A.P, A.alns + ri.set_off, ri.n_sets, A.runs,
+                                            A.read_off[ read + 1 ] - A.read_off[ read ], ord );
+        most = m > most ? m : most;
+    }
+    most = __reduce_max_sync( 0xffffffffu, most );
+    if( ( threadIdx.x & 31 ) == 0 && most > 0 )
+        atomicMax( &A.ctrl->max_reported, most );
+}
+
+// PairedReads::execute, one thread per pair of consecutive reads (2k, 2k + 1); a trailing single read keeps its vector
+__global__ void __launch_bounds__( 128 ) pair_kernel( MapqArgs A )
+{
+    int ord1[ MA_MAX_SETS_PER_READ ], ord2[ MA_MAX_SETS_PER_READ ];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    long long* sc = A.pair_sc + (size_t)tid * A.pair_cap;
+    int* meta = A.pair_meta + (size_t)tid * 2 * A.pair_cap;
+    const int nPairs = ( A.n_reads + 1 ) / 2;
+    for( int p = tid; p < nPairs; p += gridDim.x * blockDim.x )
+    {
+        const int r1 = 2 * p, r2 = 2 * p + 1;
+        const ReadInfo i1 = A.info[ r1 ];
+        ReadInfo i2;
+        i2.set_off = 0, i2.n_sets = 0;
+        long long q2 = 0;
+        if( r2 < A.n_reads )
+            i2 = A.info[ r2 ], q2 = A.read_off[ r2 + 1 ] - A.read_off[ r2 ];
+        const int rc = paired_reads_pair( A.P, A.ref_len, A.alns + i1.set_off, i1.n_sets,
+                                          A.read_off[ r1 + 1 ] - A.read_off[ r1 ], A.alns + i2.set_off, i2.n_sets, q2,
+                                          A.runs, ord1, ord2, sc, meta, A.pair_cap );
+        if( rc < 0 )
+            atomicExch( &A.ctrl->overflow_pair, 1 );
+    }
+}
 
 // Roofline probe for the seeding kernels: independent random 64-byte block reads over a buffer of
 // the index' size, the same access shape as bwt_occ4 (four 128-bit loads of one 64-byte line), no dependent chain.

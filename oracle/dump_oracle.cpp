@@ -3,6 +3,7 @@
 // tests can compare oracle and compiled reference array by array.
 #include "ma_oracle.h"
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <list>
 #include <stdexcept>
@@ -87,6 +88,19 @@ extern "C" int ma_oracle_align_dump( const char* prefix, const char* reads_txt, 
         auto& ksw_calls = D.arr( "ksw_calls" );
         auto& ksw_seq = D.arr( "ksw_seq" );
         auto& ksw_cigar = D.arr( "ksw_cigar" );
+        auto& mq_off = D.arr( "mq_off" );
+        auto& mq = D.arr( "mq" );
+        auto& pr_off = D.arr( "pr_off" );
+        auto& pr = D.arr( "pr" );
+        mq_off.push_back( 0 ), pr_off.push_back( 0 );
+        std::vector<Alignment> prevAlns;
+        std::vector<MqAln> prevMq;
+        int64_t prevQlen = 0;
+        auto fBits = []( double d ) {
+            int64_t i;
+            memcpy( &i, &d, 8 );
+            return i;
+        };
         auto& work = D.arr( "work" ); // per read: n_ext
         for( auto* p : { &seg_off, &seed_off, &soc_off, &socseed_off, &harm_off, &harmseed_off, &aln_off,
                          &alndata_off, &ksw_off } )
@@ -177,6 +191,29 @@ extern "C" int ma_oracle_align_dump( const char* prefix, const char* reads_txt, 
                                 alndata_off.push_back( alndata.size( ) / 2 );
                             }
                             aln_off.push_back( aln.size( ) / 8 );
+                            // MappingQuality per read, PairedReads per pair of consecutive reads (as oracle/ref_dump.cpp)
+                            auto vMq = mapping_quality( P, alns, (int64_t)q.size( ) );
+                            for( auto& m : vMq )
+                            {
+                                int64_t a[ 3 ] = { m.idx, (int64_t)m.secondary | ( (int64_t)m.supplementary << 1 ),
+                                                   fBits( m.mapq ) };
+                                mq.insert( mq.end( ), a, a + 3 );
+                            }
+                            mq_off.push_back( mq.size( ) / 3 );
+                            if( uiRead % 2 == 0 )
+                                prevAlns = alns, prevMq = vMq, prevQlen = (int64_t)q.size( );
+                            else
+                            {
+                                auto vPr = paired_reads( I, P, prevAlns, prevMq, prevQlen, alns, vMq, (int64_t)q.size( ) );
+                                for( auto& x : vPr )
+                                {
+                                    int64_t a[ 4 ] = { x.mate, x.a.idx,
+                                                       (int64_t)x.a.secondary | ( (int64_t)x.a.supplementary << 1 ),
+                                                       fBits( x.a.mapq ) };
+                                    pr.insert( pr.end( ), a, a + 4 );
+                                }
+                                pr_off.push_back( pr.size( ) / 4 );
+                            }
                         }
                     }
                 }

@@ -1,6 +1,7 @@
 // CPU ORACLE — test infrastructure only (see oracle.h).  Internal C++ types of the restatement.
 #pragma once
 #include "oracle.h"
+#include <cmath>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -26,6 +27,10 @@ struct Params
     int64_t genome_size_disable = 10000000;
     int disable_heuristics = 0;
     int padding = 1000, bandwidth_ext = 512, min_bandwidth_gap = 20, zdrop = 200;
+    // MappingQuality / PairedReads (parameter.h:652-668, 721-737)
+    int report_n = 0, min_alignment_score = 75, max_supplementary_per_prim = 1;
+    double max_overlap_supplementary = 0.1, paired_mean = 400, paired_std = 150, paired_bonus = 1.25;
+    int use_paired_reads = 0;
     bool preset( std::string sName );
 };
 
@@ -183,5 +188,22 @@ std::vector<Seed> soc_pop( SoCQueue& Q, unsigned* pIndex );
 std::vector<SeedSet> harmonization( const Index& I, const Params& P, SoCQueue& Q, int64_t qlen );
 std::vector<Alignment> needleman_wunsch( const Index& I, const Params& P, std::vector<SeedSet>& sets,
                                          std::vector<uint8_t>& query, std::vector<KswCall>* pLog );
+
+// one element of MappingQuality's result: an alignment of the NeedlemanWunsch result with its flags and quality
+struct MqAln
+{
+    int idx = 0;
+    bool secondary = false, supplementary = false;
+    double mapq = NAN;
+};
+struct PairAln
+{
+    int mate; // 0 / 1
+    MqAln a;
+};
+std::vector<MqAln> mapping_quality( const Params& P, const std::vector<Alignment>& alns, int64_t qlen );
+std::vector<PairAln> paired_reads( const Index& I, const Params& P, const std::vector<Alignment>& alns1,
+                                   std::vector<MqAln>& mq1, int64_t qlen1, const std::vector<Alignment>& alns2,
+                                   std::vector<MqAln>& mq2, int64_t qlen2 );
 
 } // namespace oracle

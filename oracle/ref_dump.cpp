@@ -26,12 +26,16 @@
 #include "ma/container/pack.h"
 #include "ma/module/binarySeeding.h"
 #include "ma/module/harmonization.h"
+#include "ma/module/mappingQuality.h"
 #include "ma/module/needlemanWunsch.h"
+#include "ma/module/pairedReads.h"
 #include "ma/module/stripOfConsideration.h"
 #include <atomic>
 #include <chrono>
 #include <dlfcn.h>
 #include <fstream>
+#include <map>
+#include <cstring>
 #include <thread>
 
 using namespace libMA;
@@ -156,7 +160,10 @@ struct Modules
     StripOfConsideration xSoC;
     Harmonization xHarm;
     NeedlemanWunsch xNW;
-    Modules( const ParameterSetManager& rP ) : xSeeding( rP ), xSoC( rP ), xHarm( rP ), xNW( rP )
+    MappingQuality xMQ;
+    PairedReads xPR;
+    Modules( const ParameterSetManager& rP )
+        : xSeeding( rP ), xSoC( rP ), xHarm( rP ), xNW( rP ), xMQ( rP ), xPR( rP )
     {}
 };
 
@@ -188,6 +195,18 @@ static int cmdAlign( int argc, char** argv )
     auto& alndata_off = xD.arr( "alndata_off" );
     auto& alndata = xD.arr( "alndata" );
     auto& ksw_off = xD.arr( "ksw_off" );
+    // MappingQuality per read: rows {index in the NeedlemanWunsch result, secondary | supplementary << 1, bits of the
+    // double mapping quality}, in the order of the returned vector. PairedReads per pair of consecutive reads
+    // (2k, 2k+1): rows {mate (0 / 1), index in that mate's NeedlemanWunsch result, flags, mapping quality bits}.
+    auto& mq_off = xD.arr( "mq_off" );
+    auto& mq = xD.arr( "mq" );
+    auto& pr_off = xD.arr( "pr_off" );
+    auto& pr = xD.arr( "pr" );
+    mq_off.push_back( 0 );
+    pr_off.push_back( 0 );
+    std::shared_ptr<NucSeq> pPrevQ;
+    std::shared_ptr<ContainerVector<std::shared_ptr<Alignment>>> pPrevMQ;
+    std::map<const Alignment*, int64_t> xPrevIdx;
     KswLog xLog;
     seg_off.push_back( 0 );
     seed_off.push_back( 0 );
@@ -282,6 +301,40 @@ static int cmdAlign( int argc, char** argv )
             alndata_off.push_back( alndata.size( ) / 2 );
         }
         aln_off.push_back( aln.size( ) / 8 );
+
+        // ---- MappingQuality (mappingQuality.cpp:11-131) on the NeedlemanWunsch result of the read
+        std::map<const Alignment*, int64_t> xIdx;
+        for( size_t i = 0; i < pAln->size( ); i++ )
+            xIdx[ ( *pAln )[ i ].get( ) ] = (int64_t)i;
+        auto fBits = []( double d ) {
+            int64_t i;
+            memcpy( &i, &d, 8 );
+            return i;
+        };
+        auto pMQ = xM.xMQ.execute( pQ, pAln );
+        for( auto pA : *pMQ )
+        {
+            int64_t a[ 3 ] = { xIdx.at( pA.get( ) ), (int64_t)pA->bSecondary | ( (int64_t)pA->bSupplementary << 1 ),
+                               fBits( pA->fMappingQuality ) };
+            mq.insert( mq.end( ), a, a + 3 );
+        }
+        mq_off.push_back( mq.size( ) / 3 );
+        // ---- PairedReads (pairedReads.cpp:15-121) on every pair of consecutive reads
+        if( uiRead % 2 == 0 )
+            pPrevQ = pQ, pPrevMQ = pMQ, xPrevIdx = xIdx;
+        else
+        {
+            auto pPR = xM.xPR.execute( pPrevQ, pQ, pPrevMQ, pMQ, pPack );
+            for( auto pA : *pPR )
+            {
+                const bool bSecondMate = xIdx.count( pA.get( ) ) != 0;
+                int64_t a[ 4 ] = { (int64_t)bSecondMate, bSecondMate ? xIdx.at( pA.get( ) ) : xPrevIdx.at( pA.get( ) ),
+                                   (int64_t)pA->bSecondary | ( (int64_t)pA->bSupplementary << 1 ),
+                                   fBits( pA->fMappingQuality ) };
+                pr.insert( pr.end( ), a, a + 4 );
+            }
+            pr_off.push_back( pr.size( ) / 4 );
+        }
     }
     xD.arr( "ksw_calls" ) = xLog.vCalls;
     xD.arr( "ksw_seq" ) = xLog.vSeq;

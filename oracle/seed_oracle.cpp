@@ -27,16 +27,19 @@ bool Params::preset( std::string s )
     if( t == "illumina" || t == "illuminapaired" ) // parameter.h:1083-1094
     {
         seeding_technique = 1, max_ambiguity = 500, min_num_soc = 10, max_num_soc = 20;
+        use_paired_reads = t == "illuminapaired";
         return true;
     }
     if( t == "pacbio" ) // parameter.h:1096-1098
     {
+        max_supplementary_per_prim = 100;
         min_num_soc = 5;
         return true;
     }
     if( t == "nanopore" ) // parameter.h:1101-1104
     {
         seeding_technique = 1, min_num_soc = 5;
+        max_supplementary_per_prim = 100;
         return true;
     }
     return false;

@@ -1,9 +1,10 @@
 """Generates the pipeline golden fixtures by running the compiled, UNMODIFIED reference (oracle/_ref/ref_dump):
 
   tests/golden/gold.{bwt,sa,pac,ann,amb}   index of a 3-contig 60 kbp synthetic genome (reference's own builder)
-  tests/golden/gold_reads_short.txt / gold_reads_long.txt
+  tests/golden/gold_reads_short.txt / gold_reads_long.txt / gold_reads_pairs.txt (mates interleaved: 2k, 2k+1)
   tests/golden/gold_<preset>.npz            per-stage dumps (segments, seeds, SoC pops, harmonized sets, DP calls,
-                                            alignments) with srand(1000 + read index) before Harmonization::execute
+                                            alignments, MappingQuality results, PairedReads results of consecutive
+                                            reads) with srand(1000 + read index) before Harmonization::execute
 
 Run in the build container (needs /root/reference -> `make -C oracle ref`).
 """
@@ -39,8 +40,17 @@ def main():
     synth.write_reads_txt(os.path.join(H.GOLDEN, "gold_reads_short.txt"), short)
     long_, _, _, _ = synth.simulate_long_reads(g, 12, 2500, 8)
     synth.write_reads_txt(os.path.join(H.GOLDEN, "gold_reads_long.txt"), long_)
+    m1, m2, _, _, _, _ = synth.simulate_pairs(g, 150, 150, 9, sub_rate=0.02, indel_rate=0.01, ins_mean=400, ins_sd=60)
+    pairs = np.empty((300, 150), dtype=np.uint8)
+    pairs[0::2], pairs[1::2] = m1, m2
+    pairs[5] = np.random.Generator(np.random.PCG64(6)).integers(0, 4, 150)  # a mate that does not align
+    pairs[8] = pairs[20]  # a mate from elsewhere (unpaired distance)
+    pairs[12, :] = 4
+    pairs[15] = synth.revcomp(pairs[15]) if hasattr(synth, "revcomp") else (3 - pairs[15][::-1])  # same strand pair
+    synth.write_reads_txt(os.path.join(H.GOLDEN, "gold_reads_pairs.txt"), pairs)
     for preset, rf in [("illumina", "gold_reads_short.txt"), ("default", "gold_reads_short.txt"),
-                       ("pacbio", "gold_reads_long.txt"), ("nanopore", "gold_reads_long.txt")]:
+                       ("pacbio", "gold_reads_long.txt"), ("nanopore", "gold_reads_long.txt"),
+                       ("illuminapaired", "gold_reads_pairs.txt")]:
         out = os.path.join(H.GOLDEN, "tmp.dump")
         H.run_ref("align", os.path.join(H.GOLDEN, "gold"), os.path.join(H.GOLDEN, rf), preset, out, SRAND)
         d = H.load_dump(out)

@@ -2,8 +2,10 @@
 // TEST INFRASTRUCTURE: lets the host+device (MA_HD) routines be checked for bit-exactness without a GPU.
 //   hostsim <index prefix> <reads.txt> <preset> [srand_base]
 #include "../../ma_b200/csrc/nwglue.cuh"
+#include "../../ma_b200/csrc/mapq.cuh"
 #include "../../oracle/oracle.h"
 #include "../../oracle/ma_oracle.h"
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -37,6 +39,15 @@ struct AllSegSink
     {
         v.push_back( r );
     }
+};
+
+struct MateState
+{
+    std::vector<DAln> al;
+    std::vector<unsigned int> runs;
+    std::vector<oracle::Alignment> oalns;
+    std::vector<oracle::MqAln> omq;
+    long long qlen = 0;
 };
 
 int main( int argc, char** argv )
@@ -78,6 +89,8 @@ int main( int argc, char** argv )
                    OP.genome_size_disable };
     const long long srandBase = argc > 4 ? atoll( argv[ 4 ] ) : 1;
     long nBadHarm = 0, nBadAln = 0;
+    MapqParams MP{ OP.match, OP.report_n, OP.min_alignment_score, OP.max_supplementary_per_prim,
+                   OP.max_overlap_supplementary, OP.paired_mean, OP.paired_std, OP.paired_bonus };
     NwParams NP{ OP.match, OP.mismatch, OP.gap, OP.extend, OP.sv_penalty, OP.max_gap_area, OP.padding,
                  OP.bandwidth_ext, OP.min_bandwidth_gap, OP.zdrop };
     ma_oracle_score_t osc{ OP.match, OP.mismatch, OP.gap, OP.extend, OP.gap2, OP.extend2 };
@@ -97,7 +110,9 @@ int main( int argc, char** argv )
     }
     std::ifstream in( argv[ 2 ] );
     std::string line;
-    long nRead = 0, nBad = 0;
+    long nRead = 0, nBad = 0, nBadMq = 0;
+    MateState prev;
+    bool havePrev = false;
     unsigned long long nExtTotal = 0, nLookupTotal = 0;
     std::vector<SegRec> la( 600 ), lb( 600 );
     while( std::getline( in, line ) )
@@ -286,6 +301,75 @@ int main( int argc, char** argv )
                         printf( "read %ld ALN MISMATCH (%zu vs %zu)\n", nRead, mine.size( ), oalns.size( ) );
                     nBadAln++;
                 }
+                // ---- MappingQuality per read, PairedReads per pair of consecutive reads (mapq.cuh vs oracle)
+                if( oka )
+                {
+                    MateState cur;
+                    cur.qlen = (long long)q.size( );
+                    cur.oalns = oalns;
+                    for( size_t i = 0; i < mine.size( ); i++ )
+                    { // slab order = set order; rank = position in the NeedlemanWunsch result
+                        DAln a = mine[ i ].a;
+                        a.run_off = (long long)cur.runs.size( ), a.n_runs = (int)mine[ i ].runs.size( );
+                        cur.runs.insert( cur.runs.end( ), mine[ i ].runs.begin( ), mine[ i ].runs.end( ) );
+                        cur.al.push_back( a );
+                    }
+                    for( size_t i = 0; i < ord.size( ); i++ )
+                        cur.al[ ord[ i ] ].rank = (int)i;
+                    std::vector<int> sc( cur.al.size( ) + 1 );
+                    const int nRep = mapping_quality_read( MP, cur.al.data( ), (int)cur.al.size( ), cur.runs.data( ),
+                                                           cur.qlen, sc.data( ) );
+                    cur.omq = oracle::mapping_quality( OP, oalns, cur.qlen );
+                    bool okm = nRep == (int)cur.omq.size( );
+                    for( size_t k = 0; okm && k < cur.omq.size( ); k++ )
+                    {
+                        okm = false;
+                        for( auto& a : cur.al )
+                            if( a.rank_mq == (int)k )
+                                okm = a.rank == cur.omq[ k ].idx &&
+                                      ( ( a.flags & 1 ) != 0 ) == cur.omq[ k ].secondary &&
+                                      ( ( a.flags & 2 ) != 0 ) == cur.omq[ k ].supplementary &&
+                                      memcmp( &a.mapq, &cur.omq[ k ].mapq, 8 ) == 0;
+                    }
+                    if( okm && ( nRead & 1 ) && havePrev )
+                    {
+                        // the two mates' records live in one slab on the device: concatenate
+                        std::vector<DAln> both = prev.al;
+                        std::vector<unsigned int> runs = prev.runs;
+                        for( DAln a : cur.al )
+                            a.run_off += (long long)prev.runs.size( ), both.push_back( a );
+                        runs.insert( runs.end( ), cur.runs.begin( ), cur.runs.end( ) );
+                        const int n1 = (int)prev.al.size( ), n2 = (int)cur.al.size( );
+                        const int cap = std::max( 1, n1 * n2 );
+                        std::vector<int> o1( n1 + 1 ), o2( n2 + 1 ), meta( 2 * cap );
+                        std::vector<long long> scs( cap );
+                        const int nOut = paired_reads_pair( MP, I.ref_len, both.data( ), n1, prev.qlen, both.data( ) + n1,
+                                                            n2, cur.qlen, runs.data( ), o1.data( ), o2.data( ),
+                                                            scs.data( ), meta.data( ), cap );
+                        auto omq1 = prev.omq, omq2 = cur.omq;
+                        auto opr = oracle::paired_reads( OI, OP, prev.oalns, omq1, prev.qlen, oalns, omq2, cur.qlen );
+                        okm = nOut == (int)opr.size( );
+                        for( size_t k = 0; okm && k < opr.size( ); k++ )
+                        {
+                            okm = false;
+                            for( int i = 0; i < n1 + n2; i++ )
+                                if( both[ i ].pair_rank == (int)k && ( i >= n1 ) == ( opr[ k ].mate == 1 ) )
+                                    okm = both[ i ].rank == opr[ k ].a.idx &&
+                                          ( ( both[ i ].flags & 1 ) != 0 ) == opr[ k ].a.secondary &&
+                                          ( ( both[ i ].flags & 2 ) != 0 ) == opr[ k ].a.supplementary &&
+                                          memcmp( &both[ i ].mapq, &opr[ k ].a.mapq, 8 ) == 0;
+                        }
+                    }
+                    if( !okm )
+                    {
+                        if( nBadMq < 5 )
+                            printf( "read %ld MAPQ/PAIR MISMATCH\n", nRead );
+                        nBadMq++;
+                    }
+                    prev = cur, havePrev = true;
+                }
+                else
+                    havePrev = false;
             }
             if( !okh )
             {
@@ -304,7 +388,8 @@ int main( int argc, char** argv )
     }
     printf( "hostsim: %ld reads, seeding mismatches %ld, soc/harm mismatches %ld, alignment mismatches %ld\n", nRead,
             nBad, nBadHarm, nBadAln );
+    printf( "hostsim: mapping quality / pairing mismatches %ld\n", nBadMq );
     printf( "hostsim: %llu extensions, %llu occurrence-table lookups (memo hit rate %.1f%%)\n", nExtTotal, nLookupTotal,
             nExtTotal ? 100.0 * (double)( nExtTotal - nLookupTotal ) / (double)nExtTotal : 0.0 );
-    return ( nBad || nBadHarm || nBadAln ) ? 1 : 0;
+    return ( nBad || nBadHarm || nBadAln || nBadMq ) ? 1 : 0;
 }

@@ -21,7 +21,8 @@ def load_gold(preset):
 
 
 def gold_reads(preset):
-    name = "gold_reads_short.txt" if preset in ("illumina", "default") else "gold_reads_long.txt"
+    name = ("gold_reads_pairs.txt" if preset == "illuminapaired" else
+            "gold_reads_short.txt" if preset in ("illumina", "default") else "gold_reads_long.txt")
     return os.path.join(H.GOLDEN, name)
 
 
@@ -80,6 +81,54 @@ def gpu_stage_dump(ctx, reads, keep_segments=4096):
     out["alndata_off"] = np.array(alndata_off, dtype=np.int64)
     out["alndata"] = np.concatenate(alndata) if alndata else np.zeros(0, np.int64)
     out["_stats"] = (st1, st3)
+    return out
+
+
+def gpu_mapq_dump(ctx, reads, params):
+    """MappingQuality rows (run without pairing) and PairedReads rows (run with use_paired_reads) in the layout of
+    oracle/ref_dump.cpp: mq = {NW index, secondary | supplementary << 1, mapq bits}, pr = {mate, NW index, flags,
+    mapq bits}."""
+    data, off = api.pack_reads(reads)
+    n = len(off) - 1
+    out = {}
+    saved = params.use_paired_reads
+    for paired in (0, 1):
+        params.use_paired_reads = paired
+        ctx.set_params(params)
+        ctx.align_upload(data, off)
+        ctx.align_run(api.STAGE_MAPQ, 0)
+        info, alns, runs = ctx.download_alignments()
+        bits = alns["mapq"].view(np.int64)
+        if not paired:
+            rows, offs = [], [0]
+            for i in range(n):
+                so, ns = int(info["set_off"][i]), int(info["n_sets"][i])
+                a = alns[so:so + ns]
+                keep = np.nonzero(a["rank_mq"] >= 0)[0]
+                for k in keep[np.argsort(a["rank_mq"][keep], kind="stable")]:
+                    rows.append([a["rank"][k], a["flags"][k] & 3, bits[so + k]])
+                offs.append(len(rows))
+            out["mq_off"] = np.array(offs, dtype=np.int64)
+            out["mq"] = np.array(rows, dtype=np.int64).reshape(-1)
+        else:
+            rows, offs = [], [0]
+            for p in range(n // 2):
+                cand = []
+                for mate in (0, 1):
+                    i = 2 * p + mate
+                    so, ns = int(info["set_off"][i]), int(info["n_sets"][i])
+                    a = alns[so:so + ns]
+                    for k in np.nonzero(a["pair_rank"] >= 0)[0]:
+                        assert bool(a["flags"][k] & api.ALN_FIRST_MATE) == (mate == 0)
+                        cand.append((int(a["pair_rank"][k]), mate, int(a["rank"][k]), int(a["flags"][k] & 3),
+                                     int(bits[so + k])))
+                for c in sorted(cand):
+                    rows.append(list(c[1:]))
+                offs.append(len(rows))
+            out["pr_off"] = np.array(offs, dtype=np.int64)
+            out["pr"] = np.array(rows, dtype=np.int64).reshape(-1)
+    params.use_paired_reads = saved
+    ctx.set_params(params)
     return out
 
 

@@ -11,7 +11,7 @@ import helpers as H
 import pipeline_common as PC
 from ma_b200 import index, synth
 
-PRESETS = ["illumina", "default", "pacbio", "nanopore"]
+PRESETS = ["illumina", "default", "pacbio", "nanopore", "illuminapaired"]
 
 
 @pytest.mark.parametrize("preset", PRESETS)

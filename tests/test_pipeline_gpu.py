@@ -39,6 +39,23 @@ def test_all_stages_match_reference_golden(preset, gold_index):
     ctx.close()
 
 
+@pytest.mark.parametrize("preset", PRESETS + ["illuminapaired"])
+def test_mapping_quality_and_pairing_match_reference_golden(preset, gold_index):
+    """MappingQuality per read and PairedReads per pair of consecutive reads, against the compiled
+    reference (flags, double mapping quality bit for bit, order of the returned vectors)."""
+    ctx = api.Context(0, preset)
+    p = api.preset(preset)
+    p.srand_base = PC.SRAND
+    ctx.set_params(p)
+    ctx.index_upload(gold_index)
+    assert p.use_paired_reads == (1 if preset == "illuminapaired" else 0)
+    got = PC.gpu_mapq_dump(ctx, PC.read_reads_txt(PC.gold_reads(preset)), p)
+    gold = PC.load_gold(preset)
+    for k in ("mq_off", "mq", "pr_off", "pr"):
+        assert np.array_equal(got[k], gold[k]), (preset, k)
+    ctx.close()
+
+
 def test_gpu_index_build_is_bit_identical(gold_index):
     ctx = make_ctx("illumina")
     ctx.index_build(gold_index.forward_codes(), gold_index.contig_start, gold_index.contig_len)
