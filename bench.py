@@ -4,9 +4,9 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--pairs P] [--genome-mbp G]
 
 Workload (N = 1): BASELINE.json configs[1] — synthetic 100 Mbp genome (10 contigs x 10 Mbp, seed 2), 1 M simulated
-2x150 bp Illumina pairs (1 % substitutions + 1 % indels, seed 2) = 2 M reads, Illumina(_Paired) preset; every mate
-is aligned by the path (BinarySeeding -> SoC -> Harmonization -> NeedlemanWunsch); mate pairing (PairedReads) is a
-host-side "next" row of SURVEY.md §8(f) and is not part of the path.  A step = one pass of the path over the 2 M reads.
+2x150 bp Illumina pairs (1 % substitutions + 1 % indels, seed 2) = 2 M reads (mates interleaved), Illumina_Paired
+preset; every mate is aligned by the path (BinarySeeding -> SoC -> Harmonization -> NeedlemanWunsch) and then goes
+through MappingQuality and PairedReads.  A step = one pass over the 2 M reads.
 With N > 1 (torchrun, one rank per GPU) the index is replicated and every rank aligns its own 2 M reads (weak scaling,
 no collective on the path); value = reads of all ranks / max-over-ranks device time.
 
@@ -119,7 +119,7 @@ def run_reference(prefix, reads, threads, srand=-1):
     rf = os.path.join(CACHE, "sample_%d_%d.txt" % (os.getpid(), len(reads)))
     synth.write_reads_txt(rf, reads)
     try:
-        out = subprocess.check_output([REF_DUMP, "bench", prefix, rf, "illumina", str(threads)]).decode()
+        out = subprocess.check_output([REF_DUMP, "bench", prefix, rf, "illuminapaired", str(threads)]).decode()
     finally:
         os.remove(rf)
     return json.loads(out.strip().splitlines()[-1])
@@ -138,14 +138,16 @@ def main():
     ap.add_argument("--pairs", type=int, default=1_000_000, help="read pairs per GPU and step (configs[1]: 1 M)")
     ap.add_argument("--genome-mbp", type=int, default=100)
     ap.add_argument("--cpu-sample", type=int, default=60_000, help="reads of the bounded CPU-reference sample")
+    ap.add_argument("--split", type=int, default=0, help="reads per sub-batch of the pipelined align_batch (0: default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
     seed = 2
     config = {"workload": "configs[1]: synthetic %d Mbp genome (10 contigs), %d simulated 2x150 bp Illumina pairs "
-                          "per GPU and step (1%% subst + 1%% indel), Illumina preset, every mate aligned"
+                          "per GPU and step (1%% subst + 1%% indel), Illumina_Paired preset: every mate aligned, MappingQuality + "
+                          "PairedReads"
                           % (args.genome_mbp, args.pairs),
-              "preset": "illumina", "reads_per_step_per_gpu": 2 * args.pairs, "read_len": 150,
+              "preset": "illumina_paired", "reads_per_step_per_gpu": 2 * args.pairs, "read_len": 150,
               "genome_bp": args.genome_mbp * 1_000_000, "parallelism": "index replicated, reads sharded x%d" % world,
               "l2": "inputs larger than L2 (reads %d MB + index %d MB per step, no flush needed)"
                     % (2 * args.pairs * 150 // 1_000_000, args.genome_mbp * 7 // 4)}
@@ -161,7 +163,7 @@ def main():
         ctx = None
         try:
             from ma_b200 import api
-            ctx = api.Context(0, "illumina")
+            ctx = api.Context(0, "illumina_paired")
             ctx.index_build(np.concatenate(genome), np.cumsum([0] + [len(c) for c in genome[:-1]]),
                             [len(c) for c in genome])
         except Exception:
@@ -201,7 +203,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     genome, reads = make_workload(args.genome_mbp, args.pairs, seed, rank)
-    ctx = api.Context(local_rank, "illumina")
+    ctx = api.Context(local_rank, "illumina_paired")
+    if args.split > 0:
+        ctx.set_batch_split(args.split)
     t0 = time.time()
     fwd = np.concatenate(genome)
     lens = [len(c) for c in genome]
@@ -235,14 +239,14 @@ def main():
     # ---- device-resident timing: `value`
     ctx.align_upload(pin_reads.numpy(), offsets)
     for _ in range(args.warmup):
-        ctx.align_run()
+        ctx.align_run(api.STAGE_MAPQ)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = ctx.launch_count
     dev_ms, stage = 0.0, {}
     for _ in range(args.steps):
-        st = ctx.align_run()
+        st = ctx.align_run(api.STAGE_MAPQ)
         dev_ms += st["ms_total"]
         for k, v in st.items():
             if k.startswith("ms_"):
@@ -299,7 +303,7 @@ def main():
         "ksw_batch_kernel": {"ms": per["ms_dp"], "cells": dp_cells,
                              "GCUPS": dp_cells / per["ms_dp"] / 1e6 if per["ms_dp"] > 0 else None,
                              "algorithmic_bytes": dp_cells * 1.0 + 2.0 * last["n_tasks"] * 600},
-        "nwasm+alnsort_kernel": {"ms": per["ms_assemble"]},
+        "nwasm+alnsort+mapq+pair_kernel": {"ms": per["ms_assemble"]},
     }
     dom = max(("seed_kernel", "locate_kernel", "ksw_batch_kernel"), key=lambda k: kernels[k]["ms"])
     ach = kernels[dom]["algorithmic_bytes"] / kernels[dom]["ms"] / 1e6
@@ -339,7 +343,7 @@ def main():
         cpu_baseline = {"value": r["aligned"] / r["seconds"], "unit": "reads/s", "cores": threads,
                         "kind": "reference",
                         "sample": "first %d reads of the same workload, oracle/_ref/ref_dump bench (the reference's "
-                                  "five modules on %d host threads, index preloaded); stage cpu-seconds %s"
+                                  "seven modules (incl. MappingQuality, PairedReads) on %d host threads, index preloaded); stage cpu-seconds %s"
                                   % (len(sample), threads, json.dumps(r["stage_cpu_s"]))}
     line = {"metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -220,9 +220,11 @@ int ma_b200_align_download_sets( ma_b200_ctx* ctx, ma_b200_seed_set* sets, int64
                                  int64_t cap_seeds );
 int ma_b200_align_download( ma_b200_ctx* ctx, ma_b200_read_info* info, ma_b200_alignment* alns, int64_t cap_alns,
                             uint32_t* runs, int64_t cap_runs );
-/* ma_b200_align_batch cuts batches of at least 2 x reads_per_subbatch reads (default 262144) into sub-batches that
- * alternate between two sets of device slabs, so that the host<->device copies of one sub-batch run under the kernels
- * of the other; results do not depend on the split. */
+/* Optional pipelined form of ma_b200_align_batch: with reads_per_subbatch > 0, batches of at least 2 x that many reads
+ * are cut into sub-batches that alternate between two sets of device slabs (two host threads, two streams), so that
+ * the host<->device copies of one sub-batch run under the kernels of the other; results do not depend on the split.
+ * Off (0) by default: on a PCIe Gen5 B200 box the copies of a 2 M read batch are 7 % of the step and the smaller
+ * launches cost more than the overlap returns (bench.py --split); it pays when the link is slower or shared. */
 int ma_b200_set_batch_split( ma_b200_ctx* ctx, int64_t reads_per_subbatch );
 
 /* One call, host buffers in and out (upload + all stages + download): the drop-in for a batch of reads. */

@@ -20,6 +20,7 @@
 #include <memory>
 #include <sstream>
 #include <stdexcept>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -97,6 +98,9 @@ struct Alignment // alignment.h:55-95
     nucSeqIndex uiLength = 0, uiBeginOnRef = 0, uiEndOnRef = 0, uiBeginOnQuery = 0, uiEndOnQuery = 0;
     int64_t iScore = 0;
     unsigned int index_of_strip = 0;
+    // set by MappingQuality / PairedReads (alignment.h:75-80, xStats.bFirst)
+    double fMappingQuality = std::numeric_limits<double>::quiet_NaN( );
+    bool bSecondary = false, bSupplementary = false, bFirst = false;
     int64_t score( ) const
     {
         return iScore;
@@ -315,7 +319,98 @@ class NeedlemanWunsch
     }
 };
 
-// The batched graph: what setUpCompGraph (export.cpp:72-128) wires per thread, executed for a whole batch on one GPU.
+namespace detail
+{
+inline Alignment toAlignment( const ma_b200_alignment& a, const std::vector<uint32_t>& vRuns )
+{
+    Alignment x;
+    x.uiBeginOnRef = (nucSeqIndex)a.begin_ref, x.uiEndOnRef = (nucSeqIndex)a.end_ref;
+    x.uiBeginOnQuery = (nucSeqIndex)a.begin_q, x.uiEndOnQuery = (nucSeqIndex)a.end_q;
+    x.iScore = a.score, x.uiLength = (nucSeqIndex)a.length, x.index_of_strip = a.soc_index;
+    x.fMappingQuality = a.mapq;
+    x.bSecondary = ( a.flags & MA_B200_ALN_SECONDARY ) != 0, x.bSupplementary = ( a.flags & MA_B200_ALN_SUPPLEMENTARY ) != 0;
+    x.bFirst = ( a.flags & MA_B200_ALN_FIRST_MATE ) != 0;
+    for( int j = 0; j < a.n_runs; j++ )
+        x.data.emplace_back( (MatchType)( vRuns[ a.run_off + j ] & 7 ), vRuns[ a.run_off + j ] >> 3 );
+    return x;
+}
+// runs the path through MA_B200_STAGE_MAPQ and hands every alignment record to fVisit( read, record, runs )
+template <typename F>
+inline void runMapq( FMIndex& rIdx, ParameterSetManager xP, bool bPaired, const std::vector<NucSeq>& vQueries,
+                     ma_b200_align_stats* pStats, F fVisit )
+{
+    xP.xParams.use_paired_reads = bPaired ? 1 : 0;
+    upload( rIdx, xP, vQueries );
+    ma_b200_align_stats st;
+    rIdx.check( ma_b200_align_run( rIdx.ctx( ), MA_B200_STAGE_MAPQ, 0, &st ) );
+    if( pStats )
+        *pStats = st;
+    std::vector<ma_b200_read_info> vInfo( vQueries.size( ) );
+    std::vector<ma_b200_alignment> vAln( (size_t)st.n_sets + 1 );
+    std::vector<uint32_t> vRuns( (size_t)st.n_runs + 1 );
+    rIdx.check( ma_b200_align_download( rIdx.ctx( ), vInfo.data( ), vAln.data( ), (int64_t)vAln.size( ), vRuns.data( ),
+                                        (int64_t)vRuns.size( ) ) );
+    for( size_t i = 0; i < vQueries.size( ); i++ )
+        for( int k = 0; k < vInfo[ i ].n_sets; k++ )
+            fVisit( i, vAln[ vInfo[ i ].set_off + k ], vRuns );
+}
+} // namespace detail
+
+// MappingQuality::execute for every read of the batch (mappingQuality.cpp:11-131): the reported alignments in the
+// order of the reference's result vector, with bSecondary / bSupplementary / fMappingQuality set.
+class MappingQuality
+{
+    const ParameterSetManager& rParams;
+
+  public:
+    explicit MappingQuality( const ParameterSetManager& rParameters ) : rParams( rParameters )
+    {}
+    std::vector<std::vector<Alignment>> execute( FMIndex& rIdx, const std::vector<NucSeq>& vQueries,
+                                                 ma_b200_align_stats* pStats = nullptr )
+    {
+        std::vector<std::vector<Alignment>> vRet( vQueries.size( ) );
+        detail::runMapq( rIdx, rParams, false, vQueries, pStats,
+                         [ & ]( size_t i, const ma_b200_alignment& a, const std::vector<uint32_t>& vRuns ) {
+                             if( a.rank_mq < 0 )
+                                 return;
+                             if( vRet[ i ].size( ) <= (size_t)a.rank_mq )
+                                 vRet[ i ].resize( (size_t)a.rank_mq + 1 );
+                             vRet[ i ][ a.rank_mq ] = detail::toAlignment( a, vRuns );
+                         } );
+        return vRet;
+    }
+};
+
+// PairedReads::execute (pairedReads.cpp:15-121) for the mates vQueries[2k], vQueries[2k+1]: per pair the returned
+// vector (the chosen alignment of each mate, or all alignments of the one mate that aligned).
+class PairedReads
+{
+    const ParameterSetManager& rParams;
+
+  public:
+    explicit PairedReads( const ParameterSetManager& rParameters ) : rParams( rParameters )
+    {}
+    std::vector<std::vector<Alignment>> execute( FMIndex& rIdx, const std::vector<NucSeq>& vQueries,
+                                                 ma_b200_align_stats* pStats = nullptr )
+    {
+        if( vQueries.size( ) % 2 )
+            throw std::runtime_error( "PairedReads: the batch must hold the mates interleaved (2k, 2k+1)" );
+        std::vector<std::vector<Alignment>> vRet( vQueries.size( ) / 2 );
+        detail::runMapq( rIdx, rParams, true, vQueries, pStats,
+                         [ & ]( size_t i, const ma_b200_alignment& a, const std::vector<uint32_t>& vRuns ) {
+                             if( a.pair_rank < 0 )
+                                 return;
+                             auto& v = vRet[ i / 2 ];
+                             if( v.size( ) <= (size_t)a.pair_rank )
+                                 v.resize( (size_t)a.pair_rank + 1 );
+                             v[ a.pair_rank ] = detail::toAlignment( a, vRuns );
+                         } );
+        return vRet;
+    }
+};
+
+// The batched graph: what setUpCompGraph / setUpCompGraphPaired (export.cpp:72-202) wire per thread, executed for a
+// whole batch on one GPU.
 class Aligner
 {
     ParameterSetManager xParams;
@@ -331,9 +426,18 @@ class Aligner
     {
         return xParams;
     }
+    // NeedlemanWunsch results per read
     std::vector<std::vector<Alignment>> align( const std::vector<NucSeq>& vReads, ma_b200_align_stats* pStats = nullptr )
     {
         return NeedlemanWunsch( xParams ).execute( xIndex, vReads, pStats );
+    }
+    // what the writer receives: MappingQuality's vector per read, or PairedReads' vector per pair for paired presets
+    std::vector<std::vector<Alignment>> report( const std::vector<NucSeq>& vReads,
+                                                ma_b200_align_stats* pStats = nullptr )
+    {
+        if( xParams.xParams.use_paired_reads )
+            return PairedReads( xParams ).execute( xIndex, vReads, pStats );
+        return MappingQuality( xParams ).execute( xIndex, vReads, pStats );
     }
 };
 

@@ -59,7 +59,7 @@ struct ma_b200_ctx
     int max_read_len = 0;
     int stage_done = 0;
     bool ksw_extension_only = false; // ma_b200_ksw_set_extension_only
-    int64_t batch_split = 262144; // ma_b200_align_batch: reads per sub-batch of the pipelined form
+    int64_t batch_split = 0; // ma_b200_align_batch: reads per sub-batch of the pipelined form, 0 = one shot
     ma_b200_ctx* shadow = nullptr; // second set of slabs + stream for the pipelined ma_b200_align_batch
     DevBuf<unsigned char> reads;
     DevBuf<long long> read_off;
@@ -1144,7 +1144,7 @@ extern "C" int ma_b200_align_download( ma_b200_ctx* ctx, ma_b200_read_info* info
 
 extern "C" int ma_b200_set_batch_split( ma_b200_ctx* ctx, int64_t reads_per_subbatch )
 {
-    if( !ctx || reads_per_subbatch < 1 )
+    if( !ctx || reads_per_subbatch < 0 )
         return MA_B200_EINVAL;
     ctx->batch_split = reads_per_subbatch;
     return MA_B200_OK;
@@ -1242,7 +1242,7 @@ extern "C" int ma_b200_align_batch( ma_b200_ctx* ctx, int64_t n_reads, const uin
 {
     if( !ctx )
         return MA_B200_EINVAL;
-    if( n_reads < 2 * ( ctx->batch_split + ( ctx->batch_split & 1 ) ) || !ctx->have_index || !reads || !offsets || !info || !alns || !runs )
+    if( ctx->batch_split <= 0 || n_reads < 2 * ( ctx->batch_split + ( ctx->batch_split & 1 ) ) || !ctx->have_index || !reads || !offsets || !info || !alns || !runs )
     { // one shot (also the path that reports argument errors)
         int rc = ma_b200_align_upload( ctx, n_reads, reads, offsets );
         if( rc )

@@ -407,20 +407,22 @@ static int cmdBench( int argc, char** argv )
         vQ.push_back( std::make_shared<NucSeq>( s ) );
     std::atomic<size_t> uiNext( 0 );
     std::atomic<size_t> uiAligned( 0 );
-    std::atomic<int64_t> iNs[ 5 ];
+    std::atomic<int64_t> iNs[ 6 ];
     for( auto& x : iNs )
         x = 0;
+    const bool bPaired = xP.getSelected( )->xUsePairedReads->get( );
     auto tStart = std::chrono::steady_clock::now( );
     std::vector<std::thread> vT;
     for( int t = 0; t < iThreads; t++ )
         vT.emplace_back( [ & ]( ) {
-            int64_t aNs[ 5 ] = { 0, 0, 0, 0, 0 };
+            int64_t aNs[ 6 ] = { 0, 0, 0, 0, 0, 0 };
             size_t uiLocalAligned = 0;
             while( true )
             {
-                size_t i = uiNext.fetch_add( 16 );
+                size_t i = uiNext.fetch_add( 16 ); // even: mates (2k, 2k+1) stay in one chunk
                 if( i >= vQ.size( ) )
                     break;
+                std::shared_ptr<ContainerVector<std::shared_ptr<Alignment>>> pPrevMQ;
                 for( size_t j = i; j < std::min( i + 16, vQ.size( ) ); j++ )
                 {
                     auto t0 = std::chrono::steady_clock::now( );
@@ -438,14 +440,24 @@ static int cmdBench( int argc, char** argv )
                     auto t5 = std::chrono::steady_clock::now( );
                     if( !pAln->empty( ) && ( *pAln )[ 0 ]->uiLength > 0 )
                         uiLocalAligned++;
+                    auto pMQ = xM.xMQ.execute( vQ[ j ], pAln );
+                    if( bPaired )
+                    {
+                        if( j % 2 == 0 )
+                            pPrevMQ = pMQ;
+                        else
+                            xM.xPR.execute( vQ[ j - 1 ], vQ[ j ], pPrevMQ, pMQ, pPack );
+                    }
+                    auto t6 = std::chrono::steady_clock::now( );
                     aNs[ 0 ] += ( t1 - t0 ).count( );
                     aNs[ 1 ] += ( t2 - t1 ).count( );
                     aNs[ 2 ] += ( t3 - t2 ).count( );
                     aNs[ 3 ] += ( t4 - t3 ).count( );
                     aNs[ 4 ] += ( t5 - t4 ).count( );
+                    aNs[ 5 ] += ( t6 - t5 ).count( );
                 }
             }
-            for( int k = 0; k < 5; k++ )
+            for( int k = 0; k < 6; k++ )
                 iNs[ k ] += aNs[ k ];
             uiAligned += uiLocalAligned;
         } );
@@ -454,9 +466,9 @@ static int cmdBench( int argc, char** argv )
     double fSec = std::chrono::duration<double>( std::chrono::steady_clock::now( ) - tStart ).count( );
     printf( "{\"reads\": %zu, \"aligned\": %zu, \"threads\": %d, \"seconds\": %.6f, \"reads_per_s\": %.1f, "
             "\"stage_cpu_s\": {\"seeding\": %.4f, \"extract\": %.4f, \"soc\": %.4f, \"harmonization\": %.4f, \"dp\": "
-            "%.4f}}\n",
+            "%.4f, \"mapq_pairing\": %.4f}}\n",
             vQ.size( ), (size_t)uiAligned, iThreads, fSec, vQ.size( ) / fSec, iNs[ 0 ] * 1e-9, iNs[ 1 ] * 1e-9,
-            iNs[ 2 ] * 1e-9, iNs[ 3 ] * 1e-9, iNs[ 4 ] * 1e-9 );
+            iNs[ 2 ] * 1e-9, iNs[ 3 ] * 1e-9, iNs[ 4 ] * 1e-9, iNs[ 5 ] * 1e-9 );
     return 0;
 }
 

@@ -22,6 +22,21 @@ int main( int argc, char** argv )
             if( !line.empty( ) )
                 vReads.emplace_back( line );
         ma_b200_align_stats st;
+        if( argc > 5 && std::string( argv[ 5 ] ) == "report" )
+        { // what the writer receives: MappingQuality per read / PairedReads per pair (paired presets)
+            auto vRep = xAligner.report( vReads, &st );
+            for( size_t i = 0; i < vRep.size( ); i++ )
+                for( auto& a : vRep[ i ] )
+                {
+                    long long bits;
+                    memcpy( &bits, &a.fMappingQuality, 8 );
+                    printf( "%zu %d %llu %llu %llu %llu %lld %d %lld\n", i, a.bFirst ? 0 : 1,
+                            (unsigned long long)a.uiBeginOnQuery, (unsigned long long)a.uiEndOnQuery,
+                            (unsigned long long)a.uiBeginOnRef, (unsigned long long)a.uiEndOnRef, (long long)a.score( ),
+                            (int)a.bSecondary | ( (int)a.bSupplementary << 1 ), bits );
+                }
+            return 0;
+        }
         auto vAln = xAligner.align( vReads, &st );
         for( size_t i = 0; i < vAln.size( ); i++ )
             for( auto& a : vAln[ i ] )

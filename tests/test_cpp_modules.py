@@ -44,3 +44,27 @@ def test_cpp_aligner_matches_reference_golden(tmp_path):
             runs = gold["alndata"][2 * gold["alndata_off"][j]:2 * gold["alndata_off"][j + 1]].reshape(-1, 2)
             assert [tuple(map(int, x.split(":"))) for x in r[8:]] == [tuple(map(int, x)) for x in runs]
             k += 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset", ["illumina", "illuminapaired"])
+def test_cpp_report_matches_reference_golden(tmp_path, preset):
+    """Aligner::report = MappingQuality per read (single-end presets) / PairedReads per pair (paired preset)."""
+    exe = build(tmp_path)
+    out = subprocess.check_output([exe, PC.GOLD_PREFIX, PC.gold_reads(preset), preset, str(PC.SRAND), "report"]).decode()
+    gold = PC.load_gold(preset)
+    rows = [[int(x) for x in l.split()] for l in out.strip().splitlines()]
+    exp = []
+    if preset == "illuminapaired":
+        pr = gold["pr"].reshape(-1, 4)
+        for p in range(len(gold["pr_off"]) - 1):
+            for mate, idx, flags, bits in pr[gold["pr_off"][p]:gold["pr_off"][p + 1]]:
+                g = gold["aln"][8 * (gold["aln_off"][2 * p + mate] + idx):][:8]
+                exp.append([p, int(mate), int(g[0]), int(g[1]), int(g[2]), int(g[3]), int(g[4]), int(flags), int(bits)])
+    else:
+        mq = gold["mq"].reshape(-1, 3)
+        for i in range(len(gold["mq_off"]) - 1):
+            for idx, flags, bits in mq[gold["mq_off"][i]:gold["mq_off"][i + 1]]:
+                g = gold["aln"][8 * (gold["aln_off"][i] + idx):][:8]
+                exp.append([i, 1, int(g[0]), int(g[1]), int(g[2]), int(g[3]), int(g[4]), int(flags), int(bits)])
+    assert rows == exp
