@@ -947,6 +947,10 @@ __device__ __forceinline__ bool ksw_rows_p2x2( const KswScore& P, const SeqAcces
     const int T0 = scM * qlen;
     unsigned char* rowBase = tb; // tb + r * ncol16
     bool stop = false;
+    // r is even in every pass: the parity of c = qlen - 1 - r, hence the query copy of each of the two rows, is fixed
+    const int cpar = ( qlen - 1 ) & 1;
+    const unsigned* const pqA = reinterpret_cast<const unsigned*>( cpar ? sm.qb : sm.qa );
+    const unsigned* const pqB = reinterpret_cast<const unsigned*>( cpar ? sm.qa : sm.qb );
     for( int r = 0; r < nrows && !stop; r += 2, rowBase += 2 * ncol16 )
     {
         const bool has2 = r + 1 < nrows;
@@ -963,8 +967,12 @@ __device__ __forceinline__ bool ksw_rows_p2x2( const KswScore& P, const SeqAcces
             stc[ idx & M ] = (unsigned short)( ( idx < tlen ? seq.T( idx ) : 0 ) << 10 );
             inited_end += 32;
         }
-        const unsigned short fcA = r == 0 ? fc0 : r < P.long_thres ? fc1 : r == P.long_thres ? fc2 : fc3;
-        const unsigned short fcB = r + 1 < P.long_thres ? fc1 : r + 1 == P.long_thres ? fc2 : fc3;
+        unsigned short fcA = fc3, fcB = fc3;
+        if( r <= P.long_thres )
+        {
+            fcA = r == 0 ? fc0 : r < P.long_thres ? fc1 : fc2;
+            fcB = r + 1 < P.long_thres ? fc1 : r + 1 == P.long_thres ? fc2 : fc3;
+        }
         if( en0 == r && lane == 0 )
             sy[ r & M ] = init6, sy2[ r & M ] = init25, su[ r & M ] = fcA;
         const int p0 = st0 & ~1;
@@ -992,9 +1000,7 @@ __device__ __forceinline__ bool ksw_rows_p2x2( const KswScore& P, const SeqAcces
         const unsigned hprev2 = ( (unsigned)hprev & 0xFFFFu ) * 0x10001u;
         __syncwarp( );
         const int c = qlen - 1 - r; // reversed-query index of column t is t + c (row r), t + c - 1 (row r + 1)
-        const unsigned* const pqA = reinterpret_cast<const unsigned*>( ( c & 1 ) ? sm.qb : sm.qa );
-        const unsigned* const pqB = reinterpret_cast<const unsigned*>( ( c & 1 ) ? sm.qa : sm.qb );
-        const int qshA = c + 2 - ( c & 1 ), qshB = c + 1 - ( ( c - 1 ) & 1 );
+        const int qshA = c + 2 - cpar, qshB = c + cpar; // element offsets into the two copies (even)
         unsigned char* const rowpA = rowBase - ( st0 & ~15 );
         unsigned char* const rowpB = rowBase + ncol16 - ( st1 & ~15 );
         const int p1 = st1 & ~1;
