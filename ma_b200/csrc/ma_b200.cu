@@ -356,7 +356,7 @@ static int ksw_run_once( ma_b200_ctx* ctx )
 {
     MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p, 0, 64 * sizeof( unsigned long long ), ctx->stream ) );
     const KswScore score = make_score( ctx->params );
-    const long long budget = 12ll << 30;
+    const long long budget = 48ll << 30; // traceback + cigar scratch of all resident warps (180 GB of HBM per GPU)
     // size the per-warp scratch for the largest bin first: DevBuf::reserve may free + reallocate
     std::vector<long long> grids;
     size_t tbNeed = 0, csNeed = 0;
@@ -705,7 +705,7 @@ static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
         ctx->task_cigar.reserve( (size_t)cigCap );
         cigCap = (long long)ctx->task_cigar.cap;
         MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p, 0, 64 * sizeof( unsigned long long ), ctx->stream ) );
-        const long long budget = 12ll << 30;
+        const long long budget = 48ll << 30; // traceback + cigar scratch of all resident warps (180 GB of HBM per GPU)
         long long grids[ 5 ];
         size_t tbNeed = 0, csNeed = 0;
         for( int b = 0; b < 5; b++ )
