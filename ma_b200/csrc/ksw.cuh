@@ -1180,11 +1180,16 @@ __device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int
     if( w < 0 )
         w = tlen > qlen ? tlen : qlen;
     const bool bLeft = !( flag & MA_KSW_RIGHT );
+    // The in-band modes are exact only while the band term of the limits is inactive (rows r <= w) and hand over to
+    // the exact mode otherwise, which repeats the work. The early-stop bound cannot fire before the last query row
+    // has been reached on the main diagonal (r ~ 2 qlen), so they are only tried where that row lies inside r <= w
+    // (or the whole matrix does): the alignment path's end extensions (w = 512, read tails) always qualify.
+    const bool bInBandPays = w >= qlen && ( 2 * qlen + 16 <= w || qlen + tlen - 1 <= w + 1 );
     if constexpr( KswSmemBytes<W>::kPacked )
     { // packed fast path: early-stop extensions in int16 score mode whose int8 arithmetic cannot wrap
         const int iSize = qlen > tlen ? qlen : tlen;
         const bool is16 = !( (long long)iSize * P.min16 < -32768 || (long long)iSize * P.match > 32767 );
-        if( bEarlyStop && w >= qlen && is16 && qlen + 4 <= W && ( qlen < tlen ? qlen : tlen ) + 40 <= W &&
+        if( bEarlyStop && bInBandPays && is16 && qlen + 4 <= W && ( qlen < tlen ? qlen : tlen ) + 40 <= W &&
             ksw_p2_params_ok( P ) )
         {
 #if MA_KSW_P2X2
@@ -1214,7 +1219,7 @@ __device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int
         __syncwarp( );
     }
     // FAST mode needs the query staged (narrow problems) and a band that cannot limit before the matrix does
-    if( bEarlyStop && qStaged && w >= qlen )
+    if( bEarlyStop && qStaged && bInBandPays )
     {
         const bool ok = bLeft ? ksw_rows<W, true, true, true>( P, seq, qlen, tlen, w, zdrop, true, sm, tb, ez )
                               : ksw_rows<W, false, true, true>( P, seq, qlen, tlen, w, zdrop, true, sm, tb, ez );
