@@ -489,14 +489,6 @@ __device__ __forceinline__ bool ksw_rows( const KswScore& P, const SeqAccess& se
 // The lane-blocked position of the row maximum (calcMaxScore, :178-250) is NOT tracked per cell: it is recomputed
 // from the finished H row only in the rows that consume it (new maximum, or a z-drop test that can fire).
 // mqe / mte / score are not produced (never read by early-stop callers, see ksw_rows).
-template <int W> struct KswSmemP
-{
-    __half u[ W ], v[ W ], x[ W ], y[ W ], x2[ W ], y2[ W ], tc[ W ];
-    short H[ W ];
-    short Hs[ W ]; // H row of the row that holds the running maximum
-    // codes are stored as the halves with bit pattern code << 10 (distinct positive normals, ordered like the codes)
-    __half qa[ W ], qb[ W ]; // qa[j + 2] = code of q[qlen-1-j]; qb[j] = qa[j + 1]
-};
 
 __host__ __device__ inline bool ksw_p2_params_ok( const KswScore& P )
 {
@@ -566,249 +558,13 @@ __device__ __forceinline__ int ksw_p2_argmax( const short* __restrict__ H, const
     return max_t;
 }
 
-// Returns false if the problem has to be recomputed by ksw_rows (band about to limit).
-template <int W, bool LEFT>
-__device__ __forceinline__ bool ksw_rows_p2( const KswScore& P, const SeqAccess& seq, const int qlen, const int tlen,
-                                             const int w, const int zdrop, KswSmemP<W>& sm,
-                                             unsigned char* __restrict__ tb, KswOut& ez )
-{
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int M = W - 1;
-    const int NONE_T = 0x7fffffff;
-    const int q = P.q, e = P.e, q2 = P.q2, e2 = P.e2, qe = q + e;
-    const int scM = P.match;
-    const int ncol16 = ksw_ncol16( qlen, tlen, w );
-    const int nrows = qlen + tlen - 1;
-    const __half2 hMatch = h2i( scM ), hNegQ = h2i( -q ), hNegQ2 = h2i( -q2 ), hNegQE = h2i( -q - e ),
-                  hNegQE2 = h2i( -q2 - e2 ), hE = h2i( e ), hE2 = h2i( e2 ), hBias = h2i( 1536 );
-    const __half2 hCodeN = u2h( 0x10001000u ); // base code c is stored as the half with bits c << 10 (see p2_code)
-    const unsigned uMatch = h2u( hMatch ), uMis = h2u( h2i( P.mismatch ) ), uN = h2u( h2i( -e2 ) );
-    const unsigned short init6 = __half_as_ushort( __int2half_rn( -q - e ) ),
-                         init25 = __half_as_ushort( __int2half_rn( -q2 - e2 ) );
-    // first-column values of the rows (kswcpp_core.h:562-579): row 0, rows below / at / above the long-gap threshold
-    const unsigned short fc0 = init6, fc1 = __half_as_ushort( __int2half_rn( -e ) ),
-                         fc2 = __half_as_ushort( __int2half_rn( P.long_diff ) ),
-                         fc3 = __half_as_ushort( __int2half_rn( -e2 ) );
-    unsigned* const pu = reinterpret_cast<unsigned*>( sm.u );
-    unsigned* const pv = reinterpret_cast<unsigned*>( sm.v );
-    unsigned* const px = reinterpret_cast<unsigned*>( sm.x );
-    unsigned* const py = reinterpret_cast<unsigned*>( sm.y );
-    unsigned* const px2 = reinterpret_cast<unsigned*>( sm.x2 );
-    unsigned* const py2 = reinterpret_cast<unsigned*>( sm.y2 );
-    unsigned* const ptc = reinterpret_cast<unsigned*>( sm.tc );
-    unsigned* const pH = reinterpret_cast<unsigned*>( sm.H );
-    unsigned* const pHs = reinterpret_cast<unsigned*>( sm.Hs );
-    unsigned short* const su = reinterpret_cast<unsigned short*>( sm.u );
-    unsigned short* const sv = reinterpret_cast<unsigned short*>( sm.v );
-    unsigned short* const sx = reinterpret_cast<unsigned short*>( sm.x );
-    unsigned short* const sy = reinterpret_cast<unsigned short*>( sm.y );
-    unsigned short* const sx2 = reinterpret_cast<unsigned short*>( sm.x2 );
-    unsigned short* const sy2 = reinterpret_cast<unsigned short*>( sm.y2 );
-    unsigned short* const stc = reinterpret_cast<unsigned short*>( sm.tc );
-    // reversed query, two copies one element apart so that every row finds its pairs 32-bit aligned
-    {
-        unsigned short* const qa = reinterpret_cast<unsigned short*>( sm.qa );
-        unsigned short* const qb = reinterpret_cast<unsigned short*>( sm.qb );
-        for( int j = lane; j < W; j += 32 )
-        { // qa[j] = rev[j-2], qb[j] = qa[j+1] = rev[j-1], rev[j] = q[qlen-1-j]
-            const int a = j - 2, b = j - 1;
-            qa[ j ] = (unsigned short)( ( ( a >= 0 && a < qlen ) ? seq.Q( qlen - 1 - a ) : 0 ) << 10 );
-            qb[ j ] = (unsigned short)( ( ( b >= 0 && b < qlen ) ? seq.Q( qlen - 1 - b ) : 0 ) << 10 );
-        }
-    }
-    int inited_end = 0;
-    unsigned cells = 0; // < W * 2^16
-    int prevB = NONE_T;
-    // the row that holds ez.max: its H row is kept (sm.Hs) and the position is resolved only when it is consumed
-    bool pend = false;
-    int bR = 0, bSt0 = 0, bEn0 = 0;
-    const int T0 = scM * qlen;
-    unsigned char* rowBase = tb; // tb + r * ncol16
-    for( int r = 0; r < nrows; ++r, rowBase += ncol16 )
-    {
-        const int st0 = max( 0, r - qlen + 1 ), en0 = min( tlen - 1, r ); // the band term is inactive while r <= w
-        if( r > w )
-            return false;
-        cells += (unsigned)( en0 - st0 + 1 );
-        if( inited_end <= en0 + 1 )
-        { // target codes of the columns entering the window
-            const int idx = inited_end + lane;
-            stc[ idx & M ] = (unsigned short)( ( idx < tlen ? seq.T( idx ) : 0 ) << 10 );
-            inited_end += 32;
-        }
-        const unsigned short fc = r == 0 ? fc0 : r < P.long_thres ? fc1 : r == P.long_thres ? fc2 : fc3;
-        if( en0 == r && lane == 0 )
-            sy[ r & M ] = init6, sy2[ r & M ] = init25, su[ r & M ] = fc;
-        const int p0 = st0 & ~1;
-        // left neighbour of the first pair (kswcpp_core.h:562-579), kept in the high half
-        unsigned cX = (unsigned)init6 << 16, cX2 = (unsigned)init25 << 16, cV = (unsigned)fc << 16;
-        if( p0 > 0 )
-        {
-            const int kp = ( p0 - 1 ) & M;
-            cX = (unsigned)sx[ kp ] << 16, cX2 = (unsigned)sx2[ kp ] << 16, cV = (unsigned)sv[ kp ] << 16;
-        }
-        // old H left of en0, read before the pass updates it (:194-195); row 0: H[0] = v[0] - (q + e) (:247)
-        const int hprev = r == 0 ? -qe : (int)sm.H[ ( en0 - ( en0 > 0 ? 1 : 0 ) ) & M ];
-        const unsigned hprev2 = ( (unsigned)hprev & 0xFFFFu ) * 0x10001u;
-        __syncwarp( );
-        const int c = qlen - 1 - r; // reversed-query index of column t is t + c
-        const unsigned* const pq = reinterpret_cast<const unsigned*>( ( c & 1 ) ? sm.qb : sm.qa );
-        const int qsh = c + 2 - ( c & 1 ); // element offset into the chosen copy (even)
-        unsigned char* const rowp = rowBase - ( st0 & ~15 );
-        const unsigned meEn = en0 > 0 ? 0xFFFFFFFFu : 0u;
-        unsigned m2 = 0x80008000u, hb2 = 0x80008000u;
-        int t0 = p0 + 2 * lane;
-        unsigned term2; // scM * (qlen - 1 - r + t) for the two cells of this lane
-        {
-            const int a0 = scM * ( c + t0 );
-            term2 = ( (unsigned)a0 & 0xFFFFu ) | ( (unsigned)( a0 + scM ) << 16 );
-        }
-        const unsigned termStep = ( (unsigned)( scM * 64 ) & 0xFFFFu ) * 0x10001u;
-        for( int base = p0; base <= en0; base += 64, t0 += 64 )
-        {
-            const int kk = ( t0 & M ) >> 1; // pair index in the window
-            const unsigned xo = px[ kk ], vo = pv[ kk ], x2o = px2[ kk ];
-            const __half2 ut = u2h( pu[ kk ] ), yo = u2h( py[ kk ] ), y2o = u2h( py2[ kk ] );
-            const unsigned hOld = pH[ kk ];
-            const __half2 tcp = u2h( ptc[ kk ] );
-            const __half2 qp = u2h( pq[ ( ( t0 + qsh ) & M ) >> 1 ] );
-            unsigned upx = __shfl_up_sync( FULL, xo, 1 ), upv = __shfl_up_sync( FULL, vo, 1 ),
-                     upx2 = __shfl_up_sync( FULL, x2o, 1 );
-            if( lane == 0 )
-                upx = cX, upv = cV, upx2 = cX2;
-            if( base + 64 <= en0 )
-                cX = __shfl_sync( FULL, xo, 31 ), cV = __shfl_sync( FULL, vo, 31 ), cX2 = __shfl_sync( FULL, x2o, 31 );
-            const __half2 xt1 = u2h( __byte_perm( upx, xo, 0x5432 ) ), vt1 = u2h( __byte_perm( upv, vo, 0x5432 ) ),
-                          x2t1 = u2h( __byte_perm( upx2, x2o, 0x5432 ) );
-            // score profile (:591-616): N scores -e2
-            unsigned z0 = sel2( __heq2_mask( tcp, qp ), uMatch, uMis );
-            z0 = sel2( __hge2_mask( __hmax2( tcp, qp ), hCodeN ), uN, z0 );
-            __half2 z = u2h( z0 );
-            const __half2 a = __hadd2( xt1, vt1 ), b = __hadd2( yo, ut ), a2 = __hadd2( x2t1, vt1 ),
-                          b2 = __hadd2( y2o, ut );
-            unsigned d;
-            if( LEFT )
-            {
-                d = __hgt2_mask( a, z ) & 0x00010001u;
-                z = __hmax2( z, a );
-                d = sel2( __hgt2_mask( b, z ), 0x00020002u, d );
-                z = __hmax2( z, b );
-                d = sel2( __hgt2_mask( a2, z ), 0x00030003u, d );
-                z = __hmax2( z, a2 );
-                d = sel2( __hgt2_mask( b2, z ), 0x00040004u, d );
-                z = __hmax2( z, b2 );
-            }
-            else
-            { // right-aligned: ties go to the gap, state 4 is never recorded (:693-699)
-                d = __hge2_mask( a, z ) & 0x00010001u;
-                z = __hmax2( z, a );
-                d = sel2( __hge2_mask( b, z ), 0x00020002u, d );
-                z = __hmax2( z, b );
-                d = sel2( __hge2_mask( a2, z ), 0x00030003u, d );
-                z = __hmax2( z, a2 );
-                z = __hmax2( z, b2 );
-            }
-            z = __hmin2( z, hMatch );
-            const __half2 un = __hsub2( z, vt1 ), vn = __hsub2( z, ut );
-            // x' = max(a - (z - q), 0) - (q + e) = max(a - z - e, -q - e); the continuation flag is a - z > -q
-            const __half2 az = __hsub2( a, z ), bz = __hsub2( b, z ), a2z = __hsub2( a2, z ), b2z = __hsub2( b2, z );
-            if( LEFT )
-            {
-                d |= __hgt2_mask( az, hNegQ ) & 0x00080008u;
-                d |= __hgt2_mask( bz, hNegQ ) & 0x00100010u;
-                d |= __hgt2_mask( a2z, hNegQ2 ) & 0x00200020u;
-                d |= __hgt2_mask( b2z, hNegQ2 ) & 0x00400040u;
-            }
-            else
-            {
-                d |= __hge2_mask( az, hNegQ ) & 0x00080008u;
-                d |= __hge2_mask( bz, hNegQ ) & 0x00100010u;
-                d |= __hge2_mask( a2z, hNegQ2 ) & 0x00200020u;
-                d |= __hge2_mask( b2z, hNegQ2 ) & 0x00400040u;
-            }
-            // H row (calcMaxScore): interior columns add v, the last column adds u to its left neighbour's old H
-            const int de = en0 - t0; // 0: the low cell is en0, 1: the high cell
-            const unsigned me = (unsigned)de < 2u ? ( 0xFFFFu << ( de << 4 ) ) : 0u;
-            const unsigned add = h2u( __hadd2( u2h( sel2( me & meEn, h2u( un ), h2u( vn ) ) ), hBias ) ) &
-                                 0x03FF03FFu; // 512 + value per half
-            const unsigned h = __vsub2( __vadd2( sel2( me, hprev2, hOld ), add ), 0x02000200u );
-            if( de >= 0 )
-            {
-                pu[ kk ] = h2u( un );
-                pv[ kk ] = h2u( vn );
-                px[ kk ] = h2u( __hmax2( __hsub2( az, hE ), hNegQE ) );
-                py[ kk ] = h2u( __hmax2( __hsub2( bz, hE ), hNegQE ) );
-                px2[ kk ] = h2u( __hmax2( __hsub2( a2z, hE2 ), hNegQE2 ) );
-                py2[ kk ] = h2u( __hmax2( __hsub2( b2z, hE2 ), hNegQE2 ) );
-                pH[ kk ] = h;
-                *reinterpret_cast<unsigned short*>( rowp + t0 ) = (unsigned short)__byte_perm( d, 0, 0x4420 );
-            }
-            // in-band cells only: row maximum and the early-stop bound
-            const unsigned vm = ( ( t0 >= st0 && de >= 0 ) ? 0xFFFFu : 0u ) | ( de >= 1 ? 0xFFFF0000u : 0u );
-            const unsigned hm = sel2( vm, h, 0x80008000u );
-            m2 = __vmaxs2( m2, hm );
-            hb2 = __vmaxs2( hb2, __vadd2( hm, term2 & vm ) );
-            term2 = __vadd2( term2, termStep );
-        }
-        const int max_H = __reduce_max_sync( FULL, max( (int)(short)( m2 & 0xFFFFu ), (int)m2 >> 16 ) );
-        __syncwarp( );
-        if( max_H > ez.max )
-        { // new maximum: keep its H row, the lane-blocked position is resolved when (if) it is consumed
-            ez.max = max_H;
-            pend = true, bR = r, bSt0 = st0, bEn0 = en0;
-            for( int t = p0 + 2 * lane; t <= en0; t += 64 )
-                pHs[ ( t & M ) >> 1 ] = pH[ ( t & M ) >> 1 ];
-        }
-        else if( zdrop >= 0 && ez.max - max_H > zdrop )
-        { // ksw_apply_zdrop (:22-44) can only fire here (l * e2 >= 0)
-            if( pend )
-            {
-                __syncwarp( );
-                ez.max_t = ksw_p2_argmax( sm.Hs, M, bSt0, bEn0, lane ), ez.max_q = bR - ez.max_t;
-                pend = false;
-            }
-            const int max_t = ksw_p2_argmax( sm.H, M, st0, en0, lane );
-            if( max_t >= ez.max_t && r - max_t >= ez.max_q )
-            {
-                const int tl = max_t - ez.max_t, ql = ( r - max_t ) - ez.max_q;
-                const int l = tl > ql ? tl - ql : ql - tl;
-                if( ez.max - max_H > zdrop + l * e2 )
-                {
-                    ez.zdropped = 1;
-                    break;
-                }
-            }
-        }
-        {
-            const int B = __reduce_max_sync( FULL, max( (int)(short)( hb2 & 0xFFFFu ), (int)hb2 >> 16 ) );
-            if( r >= qlen && prevB != NONE_T )
-            { // all terms are < 2^31: is16 bounds qlen, tlen and the scores
-                const int j = r + 1;
-                const int T = T0 - min( q + e * j, q2 + e2 * j );
-                if( max( max( B, prevB ), T ) <= ez.max )
-                    break;
-            }
-            prevB = B;
-        }
-    }
-    if( pend )
-    {
-        __syncwarp( );
-        ez.max_t = ksw_p2_argmax( sm.Hs, M, bSt0, bEn0, lane ), ez.max_q = bR - ez.max_t;
-    }
-    ez.cells = cells;
-    __syncwarp( );
-    return true;
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // Packed path, TWO anti-diagonals per pass. A lane keeps its column pair in registers over rows r and r + 1: the
 // state arrays are loaded and stored once per two rows, the left neighbour of row r + 1 comes from a second shuffle
 // of the values just computed, and the per-row bookkeeping (band, staging, reductions, bound test) runs once per
 // pass. Row r + 1 enters column r + 1 (if the band still grows): its u / y / y2 start values are injected in
 // registers. Three rotating H buffers: the input row, the two output rows; the buffer of the row that holds the
-// running maximum is never overwritten (deferred arg-max, see ksw_rows_p2).
+// running maximum is never overwritten (deferred arg-max, see above).
 template <int W> struct KswSmemQ
 {
     __half u[ W ], v[ W ], x[ W ], y[ W ], x2[ W ], y2[ W ], tc[ W ];
@@ -1152,17 +908,12 @@ __device__ __forceinline__ bool ksw_rows_p2x2( const KswScore& P, const SeqAcces
     return true;
 }
 
-#ifndef MA_KSW_P2X2
-#define MA_KSW_P2X2 1
-#endif
 // bytes of shared memory per warp: the scalar window and, for the narrow bins, the packed one share the space
 template <int W> struct KswSmemBytes
 {
     static constexpr bool kPacked = W <= 512;
     static constexpr size_t kScalar = sizeof( KswSmem<W> );
-    static constexpr size_t kP2a = kPacked ? sizeof( KswSmemP < W <= 512 ? W : 2 > ) : 0;
-    static constexpr size_t kP2b = kPacked ? sizeof( KswSmemQ < W <= 512 ? W : 2 > ) : 0;
-    static constexpr size_t kP2 = kP2a > kP2b ? kP2a : kP2b;
+    static constexpr size_t kP2 = kPacked ? sizeof( KswSmemQ < W <= 512 ? W : 2 > ) : 0;
     static constexpr size_t value = ( ( kScalar > kP2 ? kScalar : kP2 ) + 15 ) / 16 * 16;
 };
 
@@ -1192,15 +943,9 @@ __device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int
         if( bEarlyStop && bInBandPays && is16 && qlen + 4 <= W && ( qlen < tlen ? qlen : tlen ) + 40 <= W &&
             ksw_p2_params_ok( P ) )
         {
-#if MA_KSW_P2X2
             KswSmemQ<W>& sp = reinterpret_cast<KswSmemQ<W>&>( sm );
             const bool ok = bLeft ? ksw_rows_p2x2<W, true>( P, seq, qlen, tlen, w, zdrop, sp, tb, ez )
                                   : ksw_rows_p2x2<W, false>( P, seq, qlen, tlen, w, zdrop, sp, tb, ez );
-#else
-            KswSmemP<W>& sp = reinterpret_cast<KswSmemP<W>&>( sm );
-            const bool ok = bLeft ? ksw_rows_p2<W, true>( P, seq, qlen, tlen, w, zdrop, sp, tb, ez )
-                                  : ksw_rows_p2<W, false>( P, seq, qlen, tlen, w, zdrop, sp, tb, ez );
-#endif
             if( ok )
                 return;
             ez.max_q = ez.max_t = ez.mqe_t = ez.mte_q = -1;

@@ -801,7 +801,7 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
         // ---------------- stage 1: seeding
         const int maxL = ctx->max_read_len;
         const int list_cap = std::min( maxL + 2, 1024 ), fseg_cap = std::min( 2 * maxL + 8, 1 << 16 );
-        const int SB = MA_SEED_BLOCK; // seed_kernel_rec runs with the same block size
+        const int SB = MA_SEED_BLOCK;
         int grid = full_grid( ctx, seed_kernel, SB, n );
         const size_t perThread = (size_t)( 2 * list_cap + 8 ) * sizeof( SegRec ) + (size_t)fseg_cap * sizeof( FSeg );
         grid = (int)std::max<size_t>( 1, std::min<size_t>( grid, ( (size_t)8 << 30 ) / ( perThread * SB ) ) );
@@ -826,12 +826,7 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
             A.dbg_segs = ctx->dbg_cap ? ctx->dbg_segs.p : nullptr;
             A.dbg_nsegs = ctx->dbg_cap ? ctx->dbg_nsegs.p : nullptr, A.dbg_cap = ctx->dbg_cap;
             A.ctrl = ctx->ctrl.p;
-            // default: the convergent state-machine kernel; MA_B200_SEED_SM=0 selects the recursive formulation (A/B)
-            static const bool bSM = !( getenv( "MA_B200_SEED_SM" ) && atoi( getenv( "MA_B200_SEED_SM" ) ) == 0 );
-            if( bSM )
-                seed_kernel<<<grid, SB, 0, s>>>( A );
-            else
-                seed_kernel_rec<<<grid, SB, 0, s>>>( A );
+            seed_kernel<<<grid, SB, 0, s>>>( A );
             MA_CUDA( cudaGetLastError( ) );
             ctx->launches++;
             read_ctrl( ctx );

@@ -127,67 +127,6 @@ struct SeedSink
     }
 };
 
-// Recursive formulation (one divergent call tree per lane).
-__global__ void __launch_bounds__( 128 ) seed_kernel_rec( SeedKernelArgs A )
-{
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    SegRec* la = A.lists + (size_t)tid * ( 2 * A.list_cap + 8 );
-    FSeg* fs = A.fsegs + (size_t)tid * A.fseg_cap;
-    unsigned long long nExtLocal = 0, nDropped = 0;
-    while( true )
-    {
-        const int read = atomicAdd( &A.ctrl->next_read, 1 );
-        if( read >= A.n_reads )
-            break;
-        const long long off = A.read_off[ read ];
-        const int L = (int)( A.read_off[ read + 1 ] - off );
-        SegRec* dbg = A.dbg_segs ? A.dbg_segs + (size_t)read * A.dbg_cap : nullptr;
-        SeedSink sink( A.P, fs, A.fseg_cap, dbg, A.dbg_cap );
-        Seeder<SeedSink> S( A.I, A.P, A.reads + off, L, SeedScratch{ la, la + A.list_cap, A.list_cap }, sink );
-        S.run( );
-        nExtLocal += (unsigned long long)S.nExt;
-        if( S.overflow )
-            atomicExch( &A.ctrl->overflow_lists, 1 );
-        if( sink.overflow )
-            atomicExch( &A.ctrl->overflow_fseg, 1 );
-        bool bClear = !A.P.disable_heuristics && A.P.drop_min_size != 0 &&
-                      (double)sink.dropSum < A.P.drop_factor * (double)L &&
-                      (unsigned long long)A.P.genome_size_disable < (unsigned long long)A.I.ref_len;
-        if( bClear )
-            nDropped++;
-        if( A.dbg_nsegs )
-            A.dbg_nsegs[ read ] = bClear ? 0 : sink.nAll;
-        const long long nSeeds = bClear ? 0 : sink.nSeeds;
-        long long so = 0;
-        if( nSeeds > 0 )
-            so = (long long)atomicAdd( &A.ctrl->seed_cursor, (unsigned long long)nSeeds );
-        ReadInfo ri;
-        ri.seed_off = so, ri.n_seeds = (int)nSeeds, ri.set_off = 0, ri.n_sets = 0, ri.pad = 0;
-        A.info[ read ] = ri;
-        if( nSeeds > 0 && so + nSeeds <= A.seed_cap && !sink.overflow )
-        {
-            long long k = so;
-            const int nf = sink.n;
-            for( int i = 0; i < nf; i++ )
-            {
-                const FSeg f = fs[ i ];
-                for( int j = 0; j < f.sa_size; j++ )
-                {
-                    DSeed d;
-                    d.q = f.start, d.len = f.size + 1;
-                    d.r = f.sa_start + j;
-                    d.amb = (unsigned int)f.sa_size, d.fw = 1, d.delta = read;
-                    A.seeds[ k++ ] = d;
-                }
-            }
-        }
-    }
-    if( nExtLocal )
-        atomicAdd( &A.ctrl->n_ext, nExtLocal ), atomicAdd( &A.ctrl->n_lookup, nExtLocal );
-    if( nDropped )
-        atomicAdd( &A.ctrl->n_dropped, nDropped );
-}
-
 // Every lane runs the resumable SeederSM of its current read; all lanes of a warp meet at the single
 // extend_backward call site, so the warp always has up to 64 independent 64-byte occ-block loads in flight.
 // The SMEM interval list of every thread lives in shared memory (first MA_SEED_K entries, 20 bytes each, see SegList);
