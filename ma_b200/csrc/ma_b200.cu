@@ -695,7 +695,7 @@ static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
 {
     static const int Ws[ 5 ] = { 128, 256, 512, 1024, 2048 };
     const KswScore score = make_score( ctx->params );
-    if( ctx->hctrl.bin_count[ 5 ] > 0 )
+    if( ctx->hctrl.bin_count[ MA_NBINS - 1 ] > 0 )
         throw std::runtime_error( "DP band wider than the largest supported window (2000 columns)" );
     ctx->task_out.reserve( (size_t)ctx->n_tasks + 1 );
     ctx->ksw_ctrl.reserve( 64 );
@@ -706,18 +706,18 @@ static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
         cigCap = (long long)ctx->task_cigar.cap;
         MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p, 0, 64 * sizeof( unsigned long long ), ctx->stream ) );
         const long long budget = 48ll << 30; // traceback + cigar scratch of all resident warps (180 GB of HBM per GPU)
-        long long grids[ 5 ];
+        long long grids[ MA_NBINS - 1 ];
         size_t tbNeed = 0, csNeed = 0;
-        for( int b = 0; b < 5; b++ )
+        for( int b = 0; b < MA_NBINS - 1; b++ )
         {
             grids[ b ] = 0;
             if( ctx->hctrl.bin_count[ b ] == 0 )
                 continue;
             KswHostBin bin;
-            bin.W = Ws[ b ];
+            bin.W = Ws[ b / 3 ];
             bin.order.resize( ctx->hctrl.bin_count[ b ] ); // only its size is used
             bin.tb_stride = (long long)ctx->hctrl.bin_tb[ b ], bin.cig_stride = ctx->hctrl.bin_cig[ b ];
-            switch( b )
+            switch( b / 3 )
             {
                 case 0: grids[ b ] = ksw_bin_grid<128>( ctx, bin, budget ); break;
                 case 1: grids[ b ] = ksw_bin_grid<256>( ctx, bin, budget ); break;
@@ -730,7 +730,7 @@ static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
         }
         ctx->ksw_tb.reserve( tbNeed + 256 );
         ctx->ksw_cigscratch.reserve( csNeed + 64 );
-        for( int b = 0; b < 5; b++ )
+        for( int b = 0; b < MA_NBINS - 1; b++ )
         {
             if( ctx->hctrl.bin_count[ b ] == 0 )
                 continue;
@@ -751,7 +751,7 @@ static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
             A.cells_total = ctx->ksw_ctrl.p + 48;
             A.score = score;
             MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p + 16, 0, sizeof( unsigned long long ), ctx->stream ) );
-            switch( b )
+            switch( b / 3 )
             {
                 case 0: launch_ksw_bin<128>( ctx, A, grids[ b ] ); break;
                 case 1: launch_ksw_bin<256>( ctx, A, grids[ b ] ); break;
@@ -896,12 +896,12 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
         if( upto_stage >= 3 )
         {
             const int nSets = (int)ctx->n_sets;
-            long long taskCap = std::max<long long>( ( ctx->bin_order.cap / 6 ), 3ll * nSets + 1024 );
+            long long taskCap = std::max<long long>( ( ctx->bin_order.cap / MA_NBINS ), 3ll * nSets + 1024 );
             if( nSets > 0 )
                 for( int attempt = 0;; attempt++ )
                 {
                     ctx->tasks.reserve( (size_t)taskCap );
-                    ctx->bin_order.reserve( (size_t)taskCap * 6 );
+                    ctx->bin_order.reserve( (size_t)taskCap * MA_NBINS );
                     NwPlanArgs A;
                     A.I = ctx->index, A.P = make_nw_params( ctx->params ), A.read_off = ctx->read_off.p;
                     A.sets = ctx->sets.p, A.n_sets = nSets, A.set_seeds = ctx->set_seeds.p;

@@ -19,6 +19,7 @@
 namespace ma
 {
 
+#define MA_NBINS 16
 // control block in device memory; every counter that many threads bump at the same time sits in its own 128-byte
 // line (same-line atomics serialise in the L2 slice that owns the line)
 struct PipeCtrl
@@ -40,9 +41,10 @@ struct PipeCtrl
     unsigned long long n_dropped; // reads cleared by the seeding drop-off heuristic
     int overflow_lists, overflow_fseg, overflow_runs, overflow_pair;
     int max_reported; // largest MappingQuality result vector of the batch
-    alignas( 128 ) int bin_count[ 8 ];
-    alignas( 128 ) unsigned long long bin_tb[ 8 ];
-    alignas( 128 ) int bin_cig[ 8 ];
+    // DP task bins: window class (5) x kind (exact / early-stop left / early-stop right), + 1 for "band too wide"
+    alignas( 128 ) int bin_count[ MA_NBINS ];
+    alignas( 128 ) unsigned long long bin_tb[ MA_NBINS ];
+    alignas( 128 ) int bin_cig[ MA_NBINS ];
 };
 
 struct ReadInfo // per read
@@ -472,13 +474,17 @@ __global__ void __launch_bounds__( 256 ) nwbin_kernel( NwBinArgs A )
     for( int base = ( blockIdx.x * blockDim.x + threadIdx.x ) & ~31; base < A.n_tasks; base += gridDim.x * blockDim.x )
     {
         const int ti = base + lane;
-        int b = 7; // lanes beyond the end form their own group
+        int b = MA_NBINS; // lanes beyond the end form their own group
         unsigned int tb = 0, cig = 0;
         if( ti < A.n_tasks )
         {
             const KswTask T = A.tasks[ ti ];
             const int nc = ksw_ncol16( T.qlen, T.tlen, T.w );
-            b = ksw_bin_of( nc );
+            // all warps of a launch should run the same instantiation of the row loop (the kernel is large and a mix
+            // of code paths thrashes the instruction cache): tasks are binned by window class AND kind
+            const int wc = ksw_bin_of( nc );
+            const int kind = !( T.tag & MA_TASK_EARLYSTOP ) ? 0 : ( T.flag & MA_KSW_RIGHT ) ? 2 : 1;
+            b = wc < 5 ? wc * 3 + kind : MA_NBINS - 1;
             const unsigned long long bytes = ( ( (unsigned long long)T.qlen + T.tlen ) * nc + 255 ) >> 8;
             tb = bytes > 0xffffffffull ? 0xffffffffu : (unsigned int)bytes; // in units of 256 bytes
             cig = (unsigned int)( ( T.qlen + T.tlen + 2 + 63 ) & ~63 );
@@ -487,14 +493,14 @@ __global__ void __launch_bounds__( 256 ) nwbin_kernel( NwBinArgs A )
         const int leader = __ffs( m ) - 1;
         const unsigned mtb = __reduce_max_sync( m, tb ), mcig = __reduce_max_sync( m, cig );
         int slot0 = 0;
-        if( lane == leader && b < 7 )
+        if( lane == leader && b < MA_NBINS )
         {
             slot0 = atomicAdd( &A.ctrl->bin_count[ b ], __popc( m ) );
             atomicMax( &A.ctrl->bin_tb[ b ], (unsigned long long)mtb << 8 );
             atomicMax( &A.ctrl->bin_cig[ b ], (int)mcig );
         }
         slot0 = __shfl_sync( FULL, slot0, leader );
-        if( b < 6 )
+        if( b < MA_NBINS )
             A.bin_order[ (long long)b * A.task_cap + slot0 + __popc( m & ( ( 1u << lane ) - 1 ) ) ] = ti;
     }
 }
