@@ -107,12 +107,44 @@ struct Alignment // alignment.h:55-95
     }
 };
 
+// Pack's sequence descriptors (pack.h:39-176): name, start on the forward strand, length; read from <prefix>.ann
+struct ContigTable
+{
+    std::vector<std::string> vNames;
+    std::vector<int64_t> vStart, vLength;
+    int64_t iForwardLength = 0;
+    void vLoad( const std::string& sPrefix ) // Pack::vLoadCollection (pack.h:799-812), .ann part
+    {
+        std::ifstream ann( sPrefix + ".ann" );
+        if( !ann )
+            throw std::runtime_error( "File opening error: " + sPrefix + ".ann" );
+        int64_t nSeq, seedv;
+        ann >> iForwardLength >> nSeq >> seedv;
+        vNames.clear( ), vStart.assign( nSeq, 0 ), vLength.assign( nSeq, 0 );
+        std::string line;
+        std::getline( ann, line );
+        for( int64_t i = 0; i < nSeq; i++ )
+        {
+            std::getline( ann, line ); // "<gi> <name> <comment>"
+            std::istringstream xL( line );
+            std::string sGi, sName;
+            xL >> sGi >> sName;
+            vNames.push_back( sName );
+            int64_t holes;
+            ann >> vStart[ i ] >> vLength[ i ] >> holes;
+            std::getline( ann, line );
+        }
+    }
+};
+
 // One CUDA device: context + the replicated FMIndex / Pack (fMIndex.h, pack.h). Loads the reference's index files.
 class FMIndex
 {
     ma_b200_ctx* pCtx = nullptr;
 
   public:
+    ContigTable xContigs; // Pack's sequence descriptors
+
     explicit FMIndex( int iDevice = 0 )
     {
         if( ma_b200_create( iDevice, &pCtx ) != MA_B200_OK )
@@ -153,21 +185,9 @@ class FMIndex
         std::vector<int64_t> sa( nSa );
         sa[ 0 ] = -1;
         memcpy( &sa[ 1 ], s.data( ) + 52, ( nSa - 1 ) * 8 );
-        std::ifstream ann( sPrefix + ".ann" );
-        if( !ann )
-            throw std::runtime_error( "File opening error: " + sPrefix + ".ann" );
-        int64_t fwdLen, nSeq, seedv;
-        ann >> fwdLen >> nSeq >> seedv;
-        std::vector<int64_t> cs( nSeq ), cl( nSeq );
-        std::string line;
-        std::getline( ann, line );
-        for( int64_t i = 0; i < nSeq; i++ )
-        {
-            std::getline( ann, line );
-            int64_t holes;
-            ann >> cs[ i ] >> cl[ i ] >> holes;
-            std::getline( ann, line );
-        }
+        xContigs.vLoad( sPrefix );
+        const std::vector<int64_t>&cs = xContigs.vStart, &cl = xContigs.vLength;
+        const int64_t fwdLen = xContigs.iForwardLength, nSeq = (int64_t)cs.size( );
         auto p = slurp( sPrefix + ".pac" );
         check( ma_b200_index_upload( pCtx, (const uint32_t*)( b.data( ) + 40 ), nWords, L2, primary, refLen, sa.data( ),
                                      nSa, saIntv, (const uint8_t*)p.data( ), ( fwdLen + 3 ) / 4, fwdLen, cs.data( ),
@@ -425,6 +445,10 @@ class Aligner
     ParameterSetManager& params( )
     {
         return xParams;
+    }
+    const FMIndex& index( ) const
+    {
+        return xIndex;
     }
     // NeedlemanWunsch results per read
     std::vector<std::vector<Alignment>> align( const std::vector<NucSeq>& vReads, ma_b200_align_stats* pStats = nullptr )

@@ -1,0 +1,210 @@
+// SAM output of the alignment records (writer side), host C++17, header only.
+//
+// Restates, line for line of OUTPUT, the reference's writers with their default ("no NGMLR emulation") settings:
+//   FileWriter::execute        libs/ma/src/module/fileWriter.cpp:11-156
+//   PairedFileWriter::execute  libs/ma/src/module/fileWriter.cpp:158-372
+//   header                     libs/ma/inc/ma/module/fileWriter.h:386-398
+//   Alignment::cigarStringWithMInsteadOfXandEqual / cigarString / getSamFlag / getContig / getSamPosition /
+//   getQuerySequence           libs/ma/inc/ma/container/alignment.h:367-467, 576-617
+//   Pack::posInSequence / iAbsolutePosition / uiSequenceIdForPosition  libs/ma/inc/ma/container/pack.h:900-1067
+// Parity: tests/golden/gold_*.sam are written by the reference's own writers (oracle/ref_dump.cpp `sam`).
+// Not covered: the NGMLR tag emulation ("Emulate NGMLR's tag output", off in every preset) and the CG:B:I tag for
+// CIGARs of 65 536 operations or more.
+#pragma once
+#include "ma_b200_modules.hpp"
+#include <cmath>
+#include <string>
+
+namespace libMA_b200
+{
+
+class SamWriter
+{
+    const ContigTable& rIdx;
+    bool bOutputM, bSoftClip, bNoSecondary, bNoSupplementary;
+
+    bool onReverse( nucSeqIndex p ) const
+    {
+        return p >= (nucSeqIndex)rIdx.iForwardLength;
+    }
+    size_t contigOf( nucSeqIndex uiPos ) const // Pack::uiSequenceIdForPosition of the position mapped to the forward strand
+    {
+        const int64_t a = onReverse( uiPos ) ? 2 * rIdx.iForwardLength - ( (int64_t)uiPos + 1 ) : (int64_t)uiPos;
+        size_t i = 0;
+        while( i + 1 < rIdx.vStart.size( ) && rIdx.vStart[ i + 1 ] <= a )
+            i++;
+        return i;
+    }
+    std::string contig( const Alignment& a ) const
+    {
+        return rIdx.vNames[ contigOf( a.uiBeginOnRef ) ];
+    }
+    nucSeqIndex samPosition( const Alignment& a ) const // alignment.h:591-598, pack.h:917-920, 1063-1067
+    {
+        const int64_t abs = onReverse( a.uiEndOnRef ) ? 2 * rIdx.iForwardLength - ( (int64_t)a.uiEndOnRef + 1 )
+                                                      : (int64_t)a.uiBeginOnRef;
+        int64_t r = abs - rIdx.vStart[ contigOf( (nucSeqIndex)abs ) ];
+        if( onReverse( a.uiBeginOnRef ) )
+            r += 1;
+        return (nucSeqIndex)( r + 1 );
+    }
+    uint32_t samFlag( const Alignment& a ) const
+    {
+        return ( onReverse( a.uiBeginOnRef ) ? 0x10u : 0u ) | ( a.bSecondary ? 0x100u : 0u ) |
+               ( a.bSupplementary ? 0x800u : 0u );
+    }
+    std::string cigar( const Alignment& a, size_t uiQuerySize ) const
+    {
+        const bool bRev = onReverse( a.uiBeginOnRef );
+        const char* sClip = bSoftClip ? "S" : "H";
+        std::string s;
+        if( bRev )
+        {
+            if( a.uiEndOnQuery < uiQuerySize )
+                s.append( std::to_string( uiQuerySize - a.uiEndOnQuery ) ).append( sClip );
+        }
+        else if( a.uiBeginOnQuery > 0 )
+            s.append( std::to_string( a.uiBeginOnQuery ) ).append( sClip );
+        size_t uiM = 0;
+        const size_t n = a.data.size( );
+        for( size_t k = 0; k < n; k++ )
+        {
+            const auto& d = a.data[ bRev ? n - 1 - k : k ];
+            if( bOutputM )
+            {
+                if( d.first == MatchType::insertion || d.first == MatchType::deletion )
+                {
+                    if( uiM > 0 )
+                        s.append( std::to_string( uiM ) ).append( "M" ), uiM = 0;
+                    s.append( std::to_string( d.second ) ).append( d.first == MatchType::insertion ? "I" : "D" );
+                }
+                else
+                    uiM += d.second;
+            }
+            else
+                s.append( std::to_string( d.second ) )
+                    .append( d.first == MatchType::missmatch   ? "X"
+                             : d.first == MatchType::insertion ? "I"
+                             : d.first == MatchType::deletion  ? "D"
+                                                               : "=" );
+        }
+        if( uiM > 0 )
+            s.append( std::to_string( uiM ) ).append( "M" );
+        if( bRev )
+        {
+            if( a.uiBeginOnQuery > 0 )
+                s.append( std::to_string( a.uiBeginOnQuery ) ).append( sClip );
+        }
+        else if( a.uiEndOnQuery < uiQuerySize )
+            s.append( std::to_string( uiQuerySize - a.uiEndOnQuery ) ).append( sClip );
+        return s;
+    }
+    static std::string text( const NucSeq& q, size_t b, size_t e, bool bComplement )
+    {
+        std::string s;
+        if( bComplement )
+            for( size_t i = e; i > b; i-- )
+                s += "TGCAN"[ q.vSeq[ i - 1 ] < 4 ? q.vSeq[ i - 1 ] : 4 ];
+        else
+            for( size_t i = b; i < e && i < q.length( ); i++ )
+                s += "ACGTN"[ q.vSeq[ i ] < 4 ? q.vSeq[ i ] : 4 ];
+        return s;
+    }
+    std::string segment( const Alignment& a, const NucSeq& q ) const
+    {
+        if( bSoftClip )
+            return text( q, 0, q.length( ), onReverse( a.uiBeginOnRef ) );
+        return text( q, a.uiBeginOnQuery, a.uiEndOnQuery, onReverse( a.uiBeginOnRef ) );
+    }
+    static std::string mapq( const Alignment& a, bool bClamp )
+    {
+        if( std::isnan( a.fMappingQuality ) )
+            return "255";
+        const int v = static_cast<int>( std::ceil( a.fMappingQuality * 254 ) );
+        return std::to_string( bClamp ? std::min( v, 255 ) : v );
+    }
+
+  public:
+    // bOutputM: "Use M in CIGAR" (default true); bSoftClip: "Soft clip" (default false); parameter.h:743-755
+    explicit SamWriter( const ContigTable& rIndex, bool bOutputM = true, bool bSoftClip = false, bool bNoSecondary = false,
+                        bool bNoSupplementary = false )
+        : rIdx( rIndex ), bOutputM( bOutputM ), bSoftClip( bSoftClip ), bNoSecondary( bNoSecondary ),
+          bNoSupplementary( bNoSupplementary )
+    {}
+    std::string header( ) const
+    {
+        std::string s;
+        for( size_t i = 0; i < rIdx.vNames.size( ); i++ )
+            s += "@SQ\tSN:" + rIdx.vNames[ i ] + "\tLN:" + std::to_string( rIdx.vLength[ i ] ) + "\n";
+        return s + "@PG\tID:ma\tPN:ma\tVN:0.1.0\tCL:na\n";
+    }
+    // FileWriter::execute: the records of one read (MappingQuality's result vector)
+    std::string single( const NucSeq& q, const std::vector<Alignment>& v ) const
+    {
+        std::string s;
+        for( const Alignment& a : v )
+        {
+            if( a.uiLength == 0 || ( bNoSecondary && a.bSecondary ) || ( bNoSupplementary && a.bSupplementary ) )
+                continue;
+            s += q.sName + "\t" + std::to_string( samFlag( a ) ) + "\t" + contig( a ) + "\t" +
+                 std::to_string( samPosition( a ) ) + "\t" + mapq( a, false ) + "\t" + cigar( a, q.length( ) ) +
+                 "\t*\t0\t0\t" + segment( a, q ) + "\t*\n";
+        }
+        if( v.empty( ) )
+            s += q.sName + "\t4\t*\t0\t255\t*\t*\t0\t0\t" + text( q, 0, q.length( ), false ) + "\t*\n";
+        if( s.empty( ) )
+            s += q.sName + "\t4\t*\t0\t0\t*\t*\t0\t0\t" + text( q, 0, q.length( ), false ) + "\t*\n";
+        return s;
+    }
+    // PairedFileWriter::execute: the records of one pair (PairedReads' result vector; bFirst tells the mate)
+    std::string paired( const NucSeq& q1, const NucSeq& q2, const std::vector<Alignment>& v ) const
+    {
+        std::string s;
+        bool bHas1 = false, bHas2 = false;
+        // PairedReads links the two chosen alignments (xStats.pOther); a passed-through vector has no links
+        const bool bLinked = v.size( ) == 2 && v[ 0 ].bFirst != v[ 1 ].bFirst;
+        for( size_t k = 0; k < v.size( ); k++ )
+        {
+            const Alignment& a = v[ k ];
+            if( a.uiLength == 0 || ( bNoSecondary && a.bSecondary ) || ( bNoSupplementary && a.bSupplementary ) )
+                continue;
+            ( a.bFirst ? bHas1 : bHas2 ) = true;
+            const NucSeq& q = a.bFirst ? q1 : q2;
+            uint32_t flag = samFlag( a ) | 0x1u | 0x2u | ( a.bFirst ? 0x40u : 0x80u );
+            std::string sContigOther = "*", sPosOther = "0";
+            const std::string sRef = contig( a );
+            if( bLinked )
+            {
+                const Alignment& o = v[ 1 - k ];
+                if( onReverse( o.uiBeginOnRef ) )
+                    flag |= 0x20u;
+                sContigOther = contig( o );
+                if( sContigOther == sRef )
+                    sContigOther = "=";
+                sPosOther = std::to_string( samPosition( o ) );
+            }
+            // (the CIGAR's clip lengths use the FIRST mate's length for both mates, fileWriter.cpp:196-198)
+            s += q.sName + "\t" + std::to_string( flag ) + "\t" + sRef + "\t" + std::to_string( samPosition( a ) ) + "\t" +
+                 mapq( a, true ) + "\t" + cigar( a, q1.length( ) ) + "\t" + sContigOther + "\t" + sPosOther + "\t0\t" +
+                 segment( a, q ) + "\t*\n";
+        }
+        if( !bHas1 && !bHas2 )
+        {
+            s += q1.sName + "\t" + std::to_string( 0x4 | 0x1 | 0x40 | 0x8 ) + "\t*\t0\t0\t*\t*\t0\t0\t" +
+                 text( q1, 0, q1.length( ), false ) + "\t*\n";
+            s += q2.sName + "\t" + std::to_string( 0x4 | 0x1 | 0x80 | 0x8 ) + "\t*\t0\t0\t*\t*\t0\t0\t" +
+                 text( q2, 0, q2.length( ), false ) + "\t*\n";
+        }
+        else if( !bHas1 || !bHas2 )
+        {
+            const Alignment& a0 = v[ 0 ];
+            const std::string sPos = std::to_string( samPosition( a0 ) );
+            const NucSeq& q = !bHas1 ? q1 : q2;
+            s += q.sName + "\t" + std::to_string( 0x4 | 0x1 | ( !bHas1 ? 0x40 : 0x80 ) ) + "\t" + contig( a0 ) + "\t" + sPos +
+                 "\t0\t*\t=\t" + sPos + "\t0\t" + text( q, 0, q.length( ), false ) + "\t*\n";
+        }
+        return s;
+    }
+};
+
+} // namespace libMA_b200

@@ -25,6 +25,7 @@
 #include "ma/container/fMIndex.h"
 #include "ma/container/pack.h"
 #include "ma/module/binarySeeding.h"
+#include "ma/module/fileWriter.h"
 #include "ma/module/harmonization.h"
 #include "ma/module/mappingQuality.h"
 #include "ma/module/needlemanWunsch.h"
@@ -343,6 +344,50 @@ static int cmdAlign( int argc, char** argv )
     return 0;
 }
 
+// ref_dump sam <index prefix> <reads.txt> <preset> <out.sam> [srand_base]
+// The reference's own FileWriter / PairedFileWriter (fileWriter.cpp:11-156, 158-372) behind the path, reads named r<i>;
+// for presets with "Use Paired Reads" the reads 2k, 2k+1 are mates.
+static int cmdSam( int argc, char** argv )
+{
+    std::string sPrefix = argv[ 2 ];
+    auto vReads = readLines( argv[ 3 ] );
+    ParameterSetManager xP;
+    selectPreset( xP, argv[ 4 ] );
+    int64_t iSrandBase = argc > 6 ? atoll( argv[ 6 ] ) : -1;
+    auto pPack = std::make_shared<Pack>( sPrefix );
+    auto pFM = std::make_shared<FMIndex>( sPrefix );
+    Modules xM( xP );
+    const bool bPaired = xP.getSelected( )->xUsePairedReads->get( );
+    std::shared_ptr<FileWriter> pW;
+    std::shared_ptr<PairedFileWriter> pPW;
+    if( bPaired )
+        pPW = std::make_shared<PairedFileWriter>( xP, std::string( argv[ 5 ] ), pPack );
+    else
+        pW = std::make_shared<FileWriter>( xP, std::string( argv[ 5 ] ), pPack );
+    std::shared_ptr<NucSeq> pPrevQ;
+    std::shared_ptr<ContainerVector<std::shared_ptr<Alignment>>> pPrevMQ;
+    for( size_t uiRead = 0; uiRead < vReads.size( ); uiRead++ )
+    {
+        auto pQ = std::make_shared<NucSeq>( vReads[ uiRead ] );
+        pQ->sName = "r" + std::to_string( uiRead );
+        auto pSeg = xM.xSeeding.execute( pFM, pQ );
+        auto pSeeds = xM.xSoC.xExtractHelper.execute( pSeg, pFM, pQ, pPack );
+        auto pSoCs = xM.xSoC.xHelper.execute( pSeeds, pQ, pPack );
+        if( iSrandBase >= 0 )
+            srand( (unsigned int)( iSrandBase + uiRead ) );
+        auto pHarm = xM.xHarm.execute( pSoCs, pQ, pFM );
+        auto pAln = xM.xNW.execute( pHarm, pQ, pPack );
+        auto pMQ = xM.xMQ.execute( pQ, pAln );
+        if( !bPaired )
+            pW->execute( pQ, pMQ, pPack );
+        else if( uiRead % 2 == 0 )
+            pPrevQ = pQ, pPrevMQ = pMQ;
+        else
+            pPW->execute( pPrevQ, pQ, xM.xPR.execute( pPrevQ, pQ, pPrevMQ, pMQ, pPack ), pPack );
+    }
+    return 0;
+}
+
 struct KswPair
 {
     int w, zdrop, flag;
@@ -520,6 +565,8 @@ int main( int argc, char** argv )
             return cmdIndex( argc, argv );
         if( sCmd == "align" && argc >= 6 )
             return cmdAlign( argc, argv );
+        if( sCmd == "sam" && argc >= 6 )
+            return cmdSam( argc, argv );
         if( sCmd == "ksw" && argc >= 4 )
             return cmdKsw( argc, argv );
         if( sCmd == "bench" && argc >= 6 )

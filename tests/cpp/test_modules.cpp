@@ -2,6 +2,7 @@
 // reference's own probe: load index, select preset, run the modules over a read file.
 //   test_modules <index prefix> <reads.txt> <preset> <srand_base>   -> prints one line per alignment
 #include "../../include/ma_b200_modules.hpp"
+#include "../../include/ma_b200_sam.hpp"
 #include <cstdio>
 #include <iostream>
 
@@ -35,6 +36,22 @@ int main( int argc, char** argv )
                             (unsigned long long)a.uiBeginOnRef, (unsigned long long)a.uiEndOnRef, (long long)a.score( ),
                             (int)a.bSecondary | ( (int)a.bSupplementary << 1 ), bits );
                 }
+            return 0;
+        }
+        if( argc > 5 && std::string( argv[ 5 ] ) == "sam" )
+        { // SAM text as the reference's FileWriter / PairedFileWriter write it (reads named r<i>)
+            for( size_t i = 0; i < vReads.size( ); i++ )
+                vReads[ i ].sName = "r" + std::to_string( i );
+            auto vRep = xAligner.report( vReads, &st );
+            SamWriter xW( xAligner.index( ).xContigs );
+            std::string sOut = xW.header( );
+            if( xAligner.params( ).xParams.use_paired_reads )
+                for( size_t p = 0; p < vRep.size( ); p++ )
+                    sOut += xW.paired( vReads[ 2 * p ], vReads[ 2 * p + 1 ], vRep[ p ] );
+            else
+                for( size_t i = 0; i < vRep.size( ); i++ )
+                    sOut += xW.single( vReads[ i ], vRep[ i ] );
+            fwrite( sOut.data( ), 1, sOut.size( ), stdout );
             return 0;
         }
         auto vAln = xAligner.align( vReads, &st );

@@ -2,6 +2,7 @@
 
   tests/golden/gold.{bwt,sa,pac,ann,amb}   index of a 3-contig 60 kbp synthetic genome (reference's own builder)
   tests/golden/gold_reads_short.txt / gold_reads_long.txt / gold_reads_pairs.txt (mates interleaved: 2k, 2k+1)
+  tests/golden/gold_<preset>.sam            SAM of the reference's own writers (illumina, illuminapaired, pacbio)
   tests/golden/gold_<preset>.npz            per-stage dumps (segments, seeds, SoC pops, harmonized sets, DP calls,
                                             alignments, MappingQuality results, PairedReads results of consecutive
                                             reads) with srand(1000 + read index) before Harmonization::execute
@@ -64,6 +65,10 @@ def main():
             else:
                 comp[k] = v
         np.savez_compressed(os.path.join(H.GOLDEN, "gold_%s.npz" % preset), **comp)
+        if preset in ("illumina", "illuminapaired", "pacbio"):
+            # SAM text written by the reference's own FileWriter / PairedFileWriter
+            H.run_ref("sam", os.path.join(H.GOLDEN, "gold"), os.path.join(H.GOLDEN, rf), preset,
+                      os.path.join(H.GOLDEN, "gold_%s.sam" % preset), SRAND)
         print(preset, {k: len(v) for k, v in d.items() if k.endswith("_off")})
 
 

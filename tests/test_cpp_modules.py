@@ -68,3 +68,17 @@ def test_cpp_report_matches_reference_golden(tmp_path, preset):
                 g = gold["aln"][8 * (gold["aln_off"][i] + idx):][:8]
                 exp.append([i, 1, int(g[0]), int(g[1]), int(g[2]), int(g[3]), int(g[4]), int(flags), int(bits)])
     assert rows == exp
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset", ["illumina", "illuminapaired", "pacbio"])
+def test_cpp_sam_output_matches_reference_writers(tmp_path, preset):
+    """SURVEY.md §8(f) N2 (writer side): include/ma_b200_sam.hpp against the SAM text of the reference's own
+    FileWriter / PairedFileWriter (tests/golden/gold_<preset>.sam)."""
+    exe = build(tmp_path)
+    out = subprocess.check_output([exe, PC.GOLD_PREFIX, PC.gold_reads(preset), preset, str(PC.SRAND), "sam"]).decode()
+    exp = open(os.path.join(H.GOLDEN, "gold_%s.sam" % preset)).read()
+    got_lines, exp_lines = out.splitlines(), exp.splitlines()
+    assert len(got_lines) == len(exp_lines)
+    for i, (g, e) in enumerate(zip(got_lines, exp_lines)):
+        assert g == e, (i, g[:120], e[:120])

@@ -1,0 +1,55 @@
+"""SURVEY.md §8(f) N2, writer side: include/ma_b200_sam.hpp must print what the reference's FileWriter /
+PairedFileWriter print (tests/golden/gold_<preset>.sam, written by the compiled reference). CPU only: the reported
+alignments come from the golden dumps of the reference."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as H
+import pipeline_common as PC
+
+
+def records(preset, paired):
+    g = PC.load_gold(preset)
+    reads = [l.strip() for l in open(PC.gold_reads(preset)) if l.strip()]
+    out = ["Q r%d %s" % (i, r or "-") for i, r in enumerate(reads)]
+
+    def aln_row(read, idx):
+        j = g["aln_off"][read] + idx
+        a = g["aln"][8 * j:8 * j + 8]
+        runs = g["alndata"][2 * g["alndata_off"][j]:2 * g["alndata_off"][j + 1]].reshape(-1, 2)
+        return a, " ".join("%d:%d" % (t, n) for t, n in runs)
+
+    if paired:
+        pr = g["pr"].reshape(-1, 4)
+        for p in range(len(g["pr_off"]) - 1):
+            for mate, idx, flags, bits in pr[g["pr_off"][p]:g["pr_off"][p + 1]]:
+                a, runs = aln_row(2 * p + mate, idx)
+                out.append("A %d %d %d %d %d %d %d %d %d %d %d %s" % (p, 1 - mate, a[0], a[1], a[2], a[3], a[4], a[6],
+                                                                      flags & 1, flags >> 1, bits, runs))
+    else:
+        mq = g["mq"].reshape(-1, 3)
+        for i in range(len(g["mq_off"]) - 1):
+            for idx, flags, bits in mq[g["mq_off"][i]:g["mq_off"][i + 1]]:
+                a, runs = aln_row(i, idx)
+                out.append("A %d 0 %d %d %d %d %d %d %d %d %d %s" % (i, a[0], a[1], a[2], a[3], a[4], a[6], flags & 1,
+                                                                     flags >> 1, bits, runs))
+    return "\n".join(out) + "\n"
+
+
+@pytest.mark.parametrize("preset", ["illumina", "illuminapaired", "pacbio"])
+def test_sam_writer_matches_reference_writers(tmp_path, preset):
+    exe = str(tmp_path / "test_sam")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(H.ROOT, "tests", "cpp", "test_sam.cpp"),
+                           "-L" + os.path.join(H.ROOT, "ma_b200"), "-lma_b200",
+                           "-Wl,-rpath," + os.path.join(H.ROOT, "ma_b200")])
+    paired = preset == "illuminapaired"
+    got = subprocess.run([exe, PC.GOLD_PREFIX, "1" if paired else "0"], input=records(preset, paired).encode(),
+                         capture_output=True, check=True).stdout.decode()
+    exp = open(os.path.join(H.GOLDEN, "gold_%s.sam" % preset)).read()
+    gl, el = got.splitlines(), exp.splitlines()
+    for i, (a, b) in enumerate(zip(gl, el)):
+        assert a == b, (i, a[:140], b[:140])
+    assert len(gl) == len(el)
