@@ -50,6 +50,7 @@ class NucSeq
 {
   public:
     std::vector<uint8_t> vSeq;
+    std::vector<uint8_t> vQual; // ASCII qualities as read from FASTQ; empty = none (nucSeq.h WITH_QUALITY)
     std::string sName = "unknown";
     NucSeq( ) = default;
     explicit NucSeq( const std::string& sText )

@@ -1,4 +1,4 @@
-// SAM output of the alignment records (writer side), host C++17, header only.
+// SAM output of the alignment records and FASTA/FASTQ input, host C++17, header only.
 //
 // Restates, line for line of OUTPUT, the reference's writers with their default ("no NGMLR emulation") settings:
 //   FileWriter::execute        libs/ma/src/module/fileWriter.cpp:11-156
@@ -116,6 +116,15 @@ class SamWriter
             return text( q, 0, q.length( ), onReverse( a.uiBeginOnRef ) );
         return text( q, a.uiBeginOnQuery, a.uiEndOnQuery, onReverse( a.uiBeginOnRef ) );
     }
+    static std::string qual( const NucSeq& q, size_t b, size_t e ) // NucSeq::fromToQual / toQualString: never reversed
+    {
+        if( q.vQual.empty( ) )
+            return "*";
+        std::string s;
+        for( size_t i = b; i < e && i < q.length( ); i++ )
+            s += (char)q.vQual[ i ];
+        return s;
+    }
     static std::string mapq( const Alignment& a, bool bClamp )
     {
         if( std::isnan( a.fMappingQuality ) )
@@ -148,12 +157,14 @@ class SamWriter
                 continue;
             s += q.sName + "\t" + std::to_string( samFlag( a ) ) + "\t" + contig( a ) + "\t" +
                  std::to_string( samPosition( a ) ) + "\t" + mapq( a, false ) + "\t" + cigar( a, q.length( ) ) +
-                 "\t*\t0\t0\t" + segment( a, q ) + "\t*\n";
+                 "\t*\t0\t0\t" + segment( a, q ) + "\t" + qual( q, a.uiBeginOnQuery, a.uiEndOnQuery ) + "\n";
         }
         if( v.empty( ) )
-            s += q.sName + "\t4\t*\t0\t255\t*\t*\t0\t0\t" + text( q, 0, q.length( ), false ) + "\t*\n";
+            s += q.sName + "\t4\t*\t0\t255\t*\t*\t0\t0\t" + text( q, 0, q.length( ), false ) + "\t" +
+                 qual( q, 0, q.length( ) ) + "\n";
         if( s.empty( ) )
-            s += q.sName + "\t4\t*\t0\t0\t*\t*\t0\t0\t" + text( q, 0, q.length( ), false ) + "\t*\n";
+            s += q.sName + "\t4\t*\t0\t0\t*\t*\t0\t0\t" + text( q, 0, q.length( ), false ) + "\t" +
+                 qual( q, 0, q.length( ) ) + "\n";
         return s;
     }
     // PairedFileWriter::execute: the records of one pair (PairedReads' result vector; bFirst tells the mate)
@@ -186,14 +197,14 @@ class SamWriter
             // (the CIGAR's clip lengths use the FIRST mate's length for both mates, fileWriter.cpp:196-198)
             s += q.sName + "\t" + std::to_string( flag ) + "\t" + sRef + "\t" + std::to_string( samPosition( a ) ) + "\t" +
                  mapq( a, true ) + "\t" + cigar( a, q1.length( ) ) + "\t" + sContigOther + "\t" + sPosOther + "\t0\t" +
-                 segment( a, q ) + "\t*\n";
+                 segment( a, q ) + "\t" + qual( q, a.uiBeginOnQuery, a.uiEndOnQuery ) + "\n";
         }
         if( !bHas1 && !bHas2 )
         {
             s += q1.sName + "\t" + std::to_string( 0x4 | 0x1 | 0x40 | 0x8 ) + "\t*\t0\t0\t*\t*\t0\t0\t" +
-                 text( q1, 0, q1.length( ), false ) + "\t*\n";
+                 text( q1, 0, q1.length( ), false ) + "\t" + qual( q1, 0, q1.length( ) ) + "\n";
             s += q2.sName + "\t" + std::to_string( 0x4 | 0x1 | 0x80 | 0x8 ) + "\t*\t0\t0\t*\t*\t0\t0\t" +
-                 text( q2, 0, q2.length( ), false ) + "\t*\n";
+                 text( q2, 0, q2.length( ), false ) + "\t" + qual( q2, 0, q2.length( ) ) + "\n";
         }
         else if( !bHas1 || !bHas2 )
         {
@@ -204,6 +215,138 @@ class SamWriter
                  "\t0\t*\t=\t" + sPos + "\t0\t" + text( q, 0, q.length( ), false ) + "\t*\n";
         }
         return s;
+    }
+};
+
+// FileReader::execute (libs/ma/src/module/fileReader.cpp:37-203, default build: WITH_QUALITY == 1): (multi-)FASTA and
+// FASTQ with multi-line records, LF / CR / CRLF line ends (fileReader.h:151-186), the name ends at the first blank,
+// trailing characters of a sequence line that are no IUPAC nucleotide codes are cut (fileReader.cpp:12-27), every
+// letter other than ACGTacgt becomes N (nucSeq.cpp:17-28).
+class ReadParser
+{
+    std::string sData;
+    size_t uiPos = 0;
+
+    bool eof( ) const
+    {
+        return uiPos >= sData.size( );
+    }
+    char peek( ) const
+    {
+        return eof( ) ? (char)-1 : sData[ uiPos ];
+    }
+    std::string line( )
+    {
+        std::string t;
+        while( uiPos < sData.size( ) )
+        {
+            const char c = sData[ uiPos++ ];
+            if( c == '\n' )
+                return t;
+            if( c == '\r' )
+            {
+                if( uiPos < sData.size( ) && sData[ uiPos ] == '\n' )
+                    uiPos++;
+                return t;
+            }
+            t += c;
+        }
+        return t;
+    }
+    static bool validNuc( char c )
+    {
+        for( char c2 : { 'A', 'C', 'G', 'T', 'N', 'U', 'R', 'Y', 'K', 'M', 'S', 'W', 'B', 'D', 'H', 'V' } )
+            if( c2 == toupper( c ) )
+                return true;
+        return false;
+    }
+    static size_t len( const std::string& s )
+    {
+        size_t n = s.size( );
+        while( n > 0 && !validNuc( s[ n - 1 ] ) )
+            n--;
+        return n;
+    }
+    static void append( NucSeq& q, const std::string& s, size_t n )
+    {
+        for( size_t i = 0; i < n; i++ )
+        {
+            const char c = s[ i ];
+            q.vSeq.push_back( c == 'A' || c == 'a' ? 0 : c == 'C' || c == 'c' ? 1 : c == 'G' || c == 'g' ? 2
+                                                   : c == 'T' || c == 't' ? 3 : 4 );
+        }
+    }
+    void advanceTillNext( )
+    {
+        while( !( eof( ) || peek( ) == '>' || peek( ) == '@' ) )
+            uiPos++;
+    }
+
+  public:
+    explicit ReadParser( const std::string& sFileName )
+    {
+        std::ifstream in( sFileName, std::ios::binary );
+        if( !in )
+            throw std::runtime_error( "Unable to open file " + sFileName );
+        sData.assign( ( std::istreambuf_iterator<char>( in ) ), std::istreambuf_iterator<char>( ) );
+    }
+    // next read; false at the end of the file
+    bool next( NucSeq& q )
+    {
+        if( eof( ) )
+            return false;
+        q = NucSeq( );
+        std::string s;
+        if( peek( ) == '>' )
+        {
+            s = line( );
+            q.sName = s.substr( 1, s.find( ' ' ) - 1 );
+            while( !eof( ) && peek( ) != '>' && peek( ) != ' ' )
+            {
+                s = line( );
+                if( !s.empty( ) )
+                    append( q, s, len( s ) );
+            }
+        }
+        else if( peek( ) == '@' )
+        {
+            s = line( );
+            q.sName = s.substr( 1, s.find( ' ' ) - 1 );
+            while( !eof( ) && peek( ) != '+' && peek( ) != ' ' )
+            {
+                s = line( );
+                if( !s.empty( ) )
+                    append( q, s, len( s ) );
+            }
+            q.vQual.assign( q.vSeq.size( ), 126 ); // NucSeq::addQuality fills with 126 (nucSeq.h resize default)
+            s = line( );
+            if( !s.empty( ) && s[ 0 ] == '+' )
+            {
+                size_t uiQ = 0;
+                while( !eof( ) && ( peek( ) != '@' || uiQ == 0 ) )
+                {
+                    s = line( );
+                    if( s.empty( ) )
+                        continue;
+                    size_t n = s.size( );
+                    while( n > 0 && ( s[ n - 1 ] == '\n' || s[ n - 1 ] == '\r' ) )
+                        n--;
+                    for( size_t i = 0; i < n; i++ )
+                    {
+                        if( uiQ + i >= q.vQual.size( ) )
+                            q.vQual.resize( uiQ + i + 1, 126 );
+                        q.vQual[ uiQ + i ] = (uint8_t)s[ i ];
+                    }
+                    uiQ += n;
+                }
+            }
+        }
+        else
+            throw std::runtime_error( "Error while reading file.\nIs your input really in FASTA/Q format?" );
+        if( q.length( ) == 0 )
+            throw std::runtime_error( "found empty read: " + q.sName );
+        advanceTillNext( );
+        return true;
     }
 };
 

@@ -25,6 +25,7 @@
 #include "ma/container/fMIndex.h"
 #include "ma/container/pack.h"
 #include "ma/module/binarySeeding.h"
+#include "ma/module/fileReader.h"
 #include "ma/module/fileWriter.h"
 #include "ma/module/harmonization.h"
 #include "ma/module/mappingQuality.h"
@@ -347,12 +348,45 @@ static int cmdAlign( int argc, char** argv )
 // ref_dump sam <index prefix> <reads.txt> <preset> <out.sam> [srand_base]
 // The reference's own FileWriter / PairedFileWriter (fileWriter.cpp:11-156, 158-372) behind the path, reads named r<i>;
 // for presets with "Use Paired Reads" the reads 2k, 2k+1 are mates.
+// reads of a FASTA / FASTQ file through the reference's own FileReader (fileReader.cpp:37-203); plain sequence lines
+// (the fixture format of this repo) are named r<i>
+static std::vector<std::shared_ptr<NucSeq>> readQueries( const ParameterSetManager& rP, const std::string& sFile )
+{
+    std::vector<std::shared_ptr<NucSeq>> vRet;
+    std::ifstream xProbe( sFile );
+    const int c = xProbe.peek( );
+    if( c == '>' || c == '@' )
+    {
+        FileReader xReader( rP );
+        auto pStream = std::make_shared<FileStreamFromPath>( sFile );
+        while( auto pQ = xReader.execute( pStream ) )
+            vRet.push_back( pQ );
+        return vRet;
+    }
+    auto vLines = readLines( sFile );
+    for( size_t i = 0; i < vLines.size( ); i++ )
+    {
+        vRet.push_back( std::make_shared<NucSeq>( vLines[ i ] ) );
+        vRet.back( )->sName = "r" + std::to_string( i );
+    }
+    return vRet;
+}
+
+// ref_dump reads <file>: name, sequence and quality of every read as the reference's FileReader delivers them
+static int cmdReads( int argc, char** argv )
+{
+    ParameterSetManager xP;
+    for( auto pQ : readQueries( xP, argv[ 2 ] ) )
+        std::cout << pQ->sName << "\t" << pQ->toString( ) << "\t" << pQ->toQualString( ) << "\n";
+    return 0;
+}
+
 static int cmdSam( int argc, char** argv )
 {
     std::string sPrefix = argv[ 2 ];
-    auto vReads = readLines( argv[ 3 ] );
     ParameterSetManager xP;
     selectPreset( xP, argv[ 4 ] );
+    auto vReads = readQueries( xP, argv[ 3 ] );
     int64_t iSrandBase = argc > 6 ? atoll( argv[ 6 ] ) : -1;
     auto pPack = std::make_shared<Pack>( sPrefix );
     auto pFM = std::make_shared<FMIndex>( sPrefix );
@@ -368,8 +402,7 @@ static int cmdSam( int argc, char** argv )
     std::shared_ptr<ContainerVector<std::shared_ptr<Alignment>>> pPrevMQ;
     for( size_t uiRead = 0; uiRead < vReads.size( ); uiRead++ )
     {
-        auto pQ = std::make_shared<NucSeq>( vReads[ uiRead ] );
-        pQ->sName = "r" + std::to_string( uiRead );
+        auto pQ = vReads[ uiRead ];
         auto pSeg = xM.xSeeding.execute( pFM, pQ );
         auto pSeeds = xM.xSoC.xExtractHelper.execute( pSeg, pFM, pQ, pPack );
         auto pSoCs = xM.xSoC.xHelper.execute( pSeeds, pQ, pPack );
@@ -565,6 +598,8 @@ int main( int argc, char** argv )
             return cmdIndex( argc, argv );
         if( sCmd == "align" && argc >= 6 )
             return cmdAlign( argc, argv );
+        if( sCmd == "reads" && argc >= 3 )
+            return cmdReads( argc, argv );
         if( sCmd == "sam" && argc >= 6 )
             return cmdSam( argc, argv );
         if( sCmd == "ksw" && argc >= 4 )

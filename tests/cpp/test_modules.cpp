@@ -18,8 +18,17 @@ int main( int argc, char** argv )
         xAligner.params( ).xParams.srand_base = (uint32_t)atoll( argv[ 4 ] );
         std::vector<NucSeq> vReads;
         std::ifstream in( argv[ 2 ] );
+        bool bNamed = false;
+        if( in.peek( ) == '>' || in.peek( ) == '@' )
+        { // FASTA / FASTQ through the reader that mirrors the reference's FileReader
+            ReadParser xParser( argv[ 2 ] );
+            NucSeq xQ;
+            while( xParser.next( xQ ) )
+                vReads.push_back( xQ );
+            bNamed = true;
+        }
         std::string line;
-        while( std::getline( in, line ) )
+        while( !bNamed && std::getline( in, line ) )
             if( !line.empty( ) )
                 vReads.emplace_back( line );
         ma_b200_align_stats st;
@@ -40,7 +49,7 @@ int main( int argc, char** argv )
         }
         if( argc > 5 && std::string( argv[ 5 ] ) == "sam" )
         { // SAM text as the reference's FileWriter / PairedFileWriter write it (reads named r<i>)
-            for( size_t i = 0; i < vReads.size( ); i++ )
+            for( size_t i = 0; !bNamed && i < vReads.size( ); i++ )
                 vReads[ i ].sName = "r" + std::to_string( i );
             auto vRep = xAligner.report( vReads, &st );
             SamWriter xW( xAligner.index( ).xContigs );

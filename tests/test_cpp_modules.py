@@ -82,3 +82,13 @@ def test_cpp_sam_output_matches_reference_writers(tmp_path, preset):
     assert len(got_lines) == len(exp_lines)
     for i, (g, e) in enumerate(zip(got_lines, exp_lines)):
         assert g == e, (i, g[:120], e[:120])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("reads,preset,gold", [("gold_reads.fq", "illuminapaired", "gold_fq_illuminapaired.sam"),
+                                               ("gold_reads.fa", "illumina", "gold_fa_illumina.sam")])
+def test_cpp_fastq_to_sam_matches_reference(tmp_path, reads, preset, gold):
+    """FASTQ / FASTA in, SAM out (names, qualities, mate fields) == reference FileReader -> path -> (Paired)FileWriter."""
+    exe = build(tmp_path)
+    out = subprocess.check_output([exe, PC.GOLD_PREFIX, os.path.join(H.GOLDEN, reads), preset, str(PC.SRAND), "sam"])
+    assert out.decode() == open(os.path.join(H.GOLDEN, gold)).read()

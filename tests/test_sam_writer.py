@@ -53,3 +53,15 @@ def test_sam_writer_matches_reference_writers(tmp_path, preset):
     for i, (a, b) in enumerate(zip(gl, el)):
         assert a == b, (i, a[:140], b[:140])
     assert len(gl) == len(el)
+
+
+@pytest.mark.parametrize("name", ["fq", "fa"])
+def test_read_parser_matches_reference_file_reader(tmp_path, name):
+    """FASTQ (multi-line records, CRLF, lower case, descriptions, blank lines) and FASTA (wrapped lines, IUPAC codes)
+    parsed like the reference's FileReader (tests/golden/gold_reads_<name>.parsed written by `ref_dump reads`)."""
+    exe = str(tmp_path / "test_reader")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(H.ROOT, "tests", "cpp", "test_reader.cpp"),
+                           "-L" + os.path.join(H.ROOT, "ma_b200"), "-lma_b200",
+                           "-Wl,-rpath," + os.path.join(H.ROOT, "ma_b200")])
+    got = subprocess.check_output([exe, os.path.join(H.GOLDEN, "gold_reads.%s" % name)]).decode()
+    assert got == open(os.path.join(H.GOLDEN, "gold_reads_%s.parsed" % name)).read()
