@@ -318,15 +318,20 @@ def main():
     gather_gbs = ctx.gather_probe(occ_bytes)
     gather_hbm_gbs = ctx.gather_probe(8 << 30)
     seed_ach = kernels["seed_kernel"]["GB/s"]
-    roofline_seeding = {"kernel": "seed_kernel", "bound": "hbm (random 64-byte blocks; the %d MB occ table is mostly "
-                        "L2-resident on this configuration)" % (occ_bytes // 1_000_000),
+    table_gbs = 128.0 * last["n_lookup"] / per["ms_seed"] / 1e6 if per["ms_seed"] > 0 else None
+    residency = "mostly L2-resident (126 MB L2)" if occ_bytes <= 126_000_000 else "HBM-resident (larger than the 126 MB L2)"
+    roofline_seeding = {"kernel": "seed_kernel", "bound": "hbm (random 64-byte blocks; the %d MB occ table is %s on "
+                        "this configuration)" % (occ_bytes // 1_000_000, residency),
                         "achieved": seed_ach, "peak": gather_gbs, "unit": "GB/s", "frac": seed_ach / gather_gbs,
                         "peak_hbm_resident_buffer": gather_hbm_gbs,
-                        "table_reads_GBs": 128.0 * last["n_lookup"] / per["ms_seed"] / 1e6 if per["ms_seed"] > 0 else None,
+                        "table_reads_GBs": table_gbs,
+                        "frac_table_reads": table_gbs / gather_gbs if table_gbs else None,
                         "lookup_share": last["n_lookup"] / max(1, last["n_ext"]),
                         "note": "achieved = 128 B x extend_backward calls of the reference algorithm / kernel time; "
                                 "the kernel reads the table for lookup_share of them and reuses the previous result "
-                                "for entries with the same SA interval (table_reads_GBs is that real traffic)",
+                                "for entries with the same SA interval (table_reads_GBs is that real traffic, "
+                                "frac_table_reads its share of the gather rate; a frac above 1 means that reuse and "
+                                "the cached top of the table beat independent random gathers)",
                         "peak_source": "ma_b200_gather_probe: independent random 64-byte reads over a buffer of the "
                                        "occ table's size (and over 8 GiB for the HBM-resident figure), this run"}
     sm_mhz = peaks.get("sm_max_mhz", 1965.0)

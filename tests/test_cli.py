@@ -1,0 +1,70 @@
+"""maCMD_b200 (ma_b200/cli): the reference CLI's options for the alignment path (cmdMa.cpp:252-431), FASTA/FASTQ in,
+SAM out, compared with the SAM text the UNMODIFIED reference wrote for the same files (tests/golden/make_golden_reads.py:
+FileReader -> modules -> FileWriter / PairedFileWriter)."""
+import os
+import subprocess
+
+import pytest
+
+import helpers as H
+import pipeline_common as PC
+
+CLI = os.path.join(H.ROOT, "ma_b200", "cli", "maCMD_b200")
+
+
+def build_cli():
+    subprocess.check_call(["make", "-s", "-C", os.path.dirname(CLI)])
+    return CLI
+
+
+def test_cli_builds_and_rejects_bad_usage(tmp_path):
+    """CPU: the front end links against the C-ABI library; bad options fail with a message, and without a CUDA device the
+    program stops with an error (no CPU fallback)."""
+    exe = build_cli()
+    r = subprocess.run([exe, "--NoSuchOption", "1"], capture_output=True)
+    assert r.returncode == 1 and b"unknown option" in r.stderr
+    r = subprocess.run([exe, "-x", PC.GOLD_PREFIX], capture_output=True)
+    assert r.returncode == 1 and b"usage" in r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "-x", PC.GOLD_PREFIX, "-i", os.path.join(H.GOLDEN, "gold_reads.fa")],
+                           capture_output=True)
+        assert r.returncode == 1 and b"no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch", [1000000, 8])
+def test_cli_interleaved_pairs_sam_matches_reference(tmp_path, batch):
+    exe = build_cli()
+    out = str(tmp_path / "o.sam")
+    subprocess.check_call([exe, "-x", PC.GOLD_PREFIX, "-i", os.path.join(H.GOLDEN, "gold_reads.fq"), "-p",
+                           "Illumina_Paired", "--Interleaved", "--Srand", str(PC.SRAND), "--Batch", str(batch),
+                           "-o", out, "-t", "4"])
+    assert open(out).read() == open(os.path.join(H.GOLDEN, "gold_fq_illuminapaired.sam")).read()
+
+
+@pytest.mark.gpu
+def test_cli_mate_files_switch_pairing_on(tmp_path):
+    """-i reads -m mates with the unpaired Illumina presetting == Illumina_Paired (cmdMa.cpp:323-330); two input files."""
+    exe = build_cli()
+    recs = open(os.path.join(H.GOLDEN, "gold_reads.fq"), "rb").read().replace(b"\r\n", b"\n").replace(b"\n\n", b"\n")
+    parts = [b"@pair" + r for r in recs.split(b"@pair")[1:]]
+    assert len(parts) == 40
+    names = []
+    for k, (lo, hi) in enumerate([(0, 14), (14, 40)]):  # two files per mate: the comma separated list of the reference
+        for m in (0, 1):
+            fn = str(tmp_path / ("m%d_%d.fq" % (m, k)))
+            open(fn, "wb").write(b"".join(parts[lo + m:hi:2]))
+            names.append(fn)
+    # the RANSAC stream of a read is srand(base + index in input order): pairs are read 2k (from -i), 2k+1 (from -m)
+    out = subprocess.check_output([exe, "-x", PC.GOLD_PREFIX, "-i", names[0] + "," + names[2], "-m",
+                                   names[1] + "," + names[3], "-p", "Illumina", "--Srand", str(PC.SRAND)])
+    assert out.decode() == open(os.path.join(H.GOLDEN, "gold_fq_illuminapaired.sam")).read()
+
+
+@pytest.mark.gpu
+def test_cli_fasta_single_end_sam_matches_reference(tmp_path):
+    exe = build_cli()
+    out = subprocess.check_output([exe, "-x", PC.GOLD_PREFIX, "-i", os.path.join(H.GOLDEN, "gold_reads.fa"), "-p",
+                                   "Illumina", "--Srand", str(PC.SRAND), "--Batch", "6"])
+    assert out.decode() == open(os.path.join(H.GOLDEN, "gold_fa_illumina.sam")).read()
