@@ -75,6 +75,11 @@ const char* ma_b200_last_error( const ma_b200_ctx* ctx );
 int ma_b200_set_params( ma_b200_ctx* ctx, const ma_b200_params* params );
 /* number of kernels this context has launched so far (for bench.py's gpu_launches) */
 int64_t ma_b200_launch_count( const ma_b200_ctx* ctx );
+/* Page-locked host memory for the caller's batch buffers (reads slab, record arrays): copies from pageable memory are
+ * staged by the driver at a fraction of the link rate.  The role AlignedMemoryManager (kswcpp_mem.h:319-334) plays for
+ * the reference's DP scratch: caller-owned, reused across calls.  NULL if the allocation fails. */
+void* ma_b200_host_alloc( int64_t bytes );
+void ma_b200_host_free( void* p );
 
 /* ---- banded DP: replaces kswcpp_dispatch (libs/kswcpp/inc/kswcpp.h:165-190) -------------------------------- */
 #define MA_B200_KSW_RIGHT 0x02 /* KSW_EZ_RIGHT */

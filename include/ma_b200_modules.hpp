@@ -22,6 +22,7 @@
 #include <stdexcept>
 #include <limits>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace libMA_b200
@@ -46,6 +47,67 @@ class ParameterSetManager
 };
 
 // NucSeq (nucSeq.h:61-153): 1 byte per base, A=0 C=1 G=2 T=3 N=4
+// Host buffer in page-locked memory (ma_b200_host_alloc) for the arrays that cross the C ABI in every batch; grows,
+// never shrinks, resize() does not keep the contents.
+template <typename T> class PinnedVector
+{
+    T* pData = nullptr;
+    size_t uiSize = 0, uiCapacity = 0;
+
+  public:
+    PinnedVector( ) = default;
+    PinnedVector( const PinnedVector& ) = delete;
+    PinnedVector& operator=( const PinnedVector& ) = delete;
+    PinnedVector( PinnedVector&& o ) noexcept : pData( o.pData ), uiSize( o.uiSize ), uiCapacity( o.uiCapacity )
+    {
+        o.pData = nullptr, o.uiSize = o.uiCapacity = 0;
+    }
+    PinnedVector& operator=( PinnedVector&& o ) noexcept
+    {
+        std::swap( pData, o.pData ), std::swap( uiSize, o.uiSize ), std::swap( uiCapacity, o.uiCapacity );
+        return *this;
+    }
+    ~PinnedVector( )
+    {
+        ma_b200_host_free( pData );
+    }
+    void resize( size_t n )
+    {
+        if( n > uiCapacity )
+        {
+            ma_b200_host_free( pData );
+            uiCapacity = n + n / 4 + 64;
+            pData = (T*)ma_b200_host_alloc( (int64_t)( uiCapacity * sizeof( T ) ) );
+            if( !pData )
+            {
+                uiCapacity = uiSize = 0;
+                throw std::runtime_error( "ma_b200_host_alloc failed" );
+            }
+        }
+        uiSize = n;
+    }
+    size_t size( ) const
+    {
+        return uiSize;
+    }
+    T* data( )
+    {
+        return pData;
+    }
+    const T* data( ) const
+    {
+        return pData;
+    }
+    T& operator[]( size_t i )
+    {
+        return pData[ i ];
+    }
+    const T& operator[]( size_t i ) const
+    {
+        return pData[ i ];
+    }
+};
+
 class NucSeq
 {
   public:
@@ -342,7 +404,7 @@ class NeedlemanWunsch
 
 namespace detail
 {
-inline Alignment toAlignment( const ma_b200_alignment& a, const std::vector<uint32_t>& vRuns )
+inline Alignment toAlignment( const ma_b200_alignment& a, const uint32_t* vRuns )
 {
     Alignment x;
     x.uiBeginOnRef = (nucSeqIndex)a.begin_ref, x.uiEndOnRef = (nucSeqIndex)a.end_ref;
@@ -351,6 +413,7 @@ inline Alignment toAlignment( const ma_b200_alignment& a, const std::vector<uint
     x.fMappingQuality = a.mapq;
     x.bSecondary = ( a.flags & MA_B200_ALN_SECONDARY ) != 0, x.bSupplementary = ( a.flags & MA_B200_ALN_SUPPLEMENTARY ) != 0;
     x.bFirst = ( a.flags & MA_B200_ALN_FIRST_MATE ) != 0;
+    x.data.reserve( (size_t)a.n_runs );
     for( int j = 0; j < a.n_runs; j++ )
         x.data.emplace_back( (MatchType)( vRuns[ a.run_off + j ] & 7 ), vRuns[ a.run_off + j ] >> 3 );
     return x;
@@ -373,9 +436,41 @@ inline void runMapq( FMIndex& rIdx, ParameterSetManager xP, bool bPaired, const 
                                         (int64_t)vRuns.size( ) ) );
     for( size_t i = 0; i < vQueries.size( ); i++ )
         for( int k = 0; k < vInfo[ i ].n_sets; k++ )
-            fVisit( i, vAln[ vInfo[ i ].set_off + k ], vRuns );
+            fVisit( i, vAln[ vInfo[ i ].set_off + k ], vRuns.data( ) );
 }
 } // namespace detail
+
+// The report of a batch as the C ABI delivers it: per-read info, alignment records, run words. records( i ) is what
+// the reference's writer receives for read i (MappingQuality's vector) or, for paired presets, for pair i (PairedReads'
+// vector over the mates 2i, 2i + 1).
+struct RawReport
+{
+    PinnedVector<ma_b200_read_info> vInfo;
+    PinnedVector<ma_b200_alignment> vAln;
+    PinnedVector<uint32_t> vRuns;
+    bool bPaired = false;
+
+    size_t units( ) const
+    {
+        return bPaired ? vInfo.size( ) / 2 : vInfo.size( );
+    }
+    std::vector<Alignment> records( size_t i ) const
+    {
+        std::vector<Alignment> v;
+        for( size_t uiRead = bPaired ? 2 * i : i; uiRead < ( bPaired ? 2 * i + 2 : i + 1 ); uiRead++ )
+            for( int k = 0; k < vInfo[ uiRead ].n_sets; k++ )
+            {
+                const auto& a = vAln[ vInfo[ uiRead ].set_off + k ];
+                const int iRank = bPaired ? a.pair_rank : a.rank_mq;
+                if( iRank < 0 )
+                    continue;
+                if( v.size( ) <= (size_t)iRank )
+                    v.resize( (size_t)iRank + 1 );
+                v[ iRank ] = detail::toAlignment( a, vRuns.data( ) );
+            }
+        return v;
+    }
+};
 
 // MappingQuality::execute for every read of the batch (mappingQuality.cpp:11-131): the reported alignments in the
 // order of the reference's result vector, with bSecondary / bSupplementary / fMappingQuality set.
@@ -391,7 +486,7 @@ class MappingQuality
     {
         std::vector<std::vector<Alignment>> vRet( vQueries.size( ) );
         detail::runMapq( rIdx, rParams, false, vQueries, pStats,
-                         [ & ]( size_t i, const ma_b200_alignment& a, const std::vector<uint32_t>& vRuns ) {
+                         [ & ]( size_t i, const ma_b200_alignment& a, const uint32_t* vRuns ) {
                              if( a.rank_mq < 0 )
                                  return;
                              if( vRet[ i ].size( ) <= (size_t)a.rank_mq )
@@ -418,7 +513,7 @@ class PairedReads
             throw std::runtime_error( "PairedReads: the batch must hold the mates interleaved (2k, 2k+1)" );
         std::vector<std::vector<Alignment>> vRet( vQueries.size( ) / 2 );
         detail::runMapq( rIdx, rParams, true, vQueries, pStats,
-                         [ & ]( size_t i, const ma_b200_alignment& a, const std::vector<uint32_t>& vRuns ) {
+                         [ & ]( size_t i, const ma_b200_alignment& a, const uint32_t* vRuns ) {
                              if( a.pair_rank < 0 )
                                  return;
                              auto& v = vRet[ i / 2 ];
@@ -460,10 +555,58 @@ class Aligner
     std::vector<std::vector<Alignment>> report( const std::vector<NucSeq>& vReads,
                                                 ma_b200_align_stats* pStats = nullptr )
     {
-        if( xParams.xParams.use_paired_reads )
-            return PairedReads( xParams ).execute( xIndex, vReads, pStats );
-        return MappingQuality( xParams ).execute( xIndex, vReads, pStats );
+        const RawReport xRaw = reportRaw( vReads, pStats );
+        std::vector<std::vector<Alignment>> vRet( xRaw.units( ) );
+        for( size_t i = 0; i < vRet.size( ); i++ )
+            vRet[ i ] = xRaw.records( i );
+        return vRet;
     }
+    // the same result as the C ABI delivers it (record arrays of the whole batch); RawReport::records( i ) converts
+    // one read (or pair) and is safe to call from several host threads at once
+    RawReport reportRaw( const std::vector<NucSeq>& vReads, ma_b200_align_stats* pStats = nullptr )
+    {
+        RawReport xRaw;
+        reportRaw( vReads, xRaw, pStats );
+        return xRaw;
+    }
+    // into a caller-owned RawReport whose buffers are reused from batch to batch
+    void reportRaw( const std::vector<NucSeq>& vReads, RawReport& xRaw, ma_b200_align_stats* pStats = nullptr )
+    {
+        xRaw.bPaired = xParams.xParams.use_paired_reads != 0;
+        if( xRaw.bPaired && vReads.size( ) % 2 )
+            throw std::runtime_error( "PairedReads: the batch must hold the mates interleaved (2k, 2k+1)" );
+        xIndex.check( ma_b200_set_params( xIndex.ctx( ), &xParams.xParams ) );
+        size_t uiBytes = 0;
+        for( auto& r : vReads )
+            uiBytes += r.vSeq.size( );
+        vSlab.resize( uiBytes + 1 );
+        vOffsets.resize( vReads.size( ) + 1 );
+        uiBytes = 0;
+        for( size_t i = 0; i < vReads.size( ); i++ )
+        {
+            vOffsets[ i ] = (int64_t)uiBytes;
+            if( !vReads[ i ].vSeq.empty( ) )
+                memcpy( vSlab.data( ) + uiBytes, vReads[ i ].vSeq.data( ), vReads[ i ].vSeq.size( ) );
+            uiBytes += vReads[ i ].vSeq.size( );
+        }
+        vOffsets[ vReads.size( ) ] = (int64_t)uiBytes;
+        vSlab[ uiBytes ] = 0;
+        xIndex.check( ma_b200_align_upload( xIndex.ctx( ), (int64_t)vReads.size( ), vSlab.data( ), vOffsets.data( ) ) );
+        ma_b200_align_stats st;
+        xIndex.check( ma_b200_align_run( xIndex.ctx( ), MA_B200_STAGE_MAPQ, 0, &st ) );
+        if( pStats )
+            *pStats = st;
+        xRaw.vInfo.resize( vReads.size( ) );
+        xRaw.vAln.resize( (size_t)st.n_sets + 1 );
+        xRaw.vRuns.resize( (size_t)st.n_runs + 1 );
+        xIndex.check( ma_b200_align_download( xIndex.ctx( ), xRaw.vInfo.data( ), xRaw.vAln.data( ),
+                                              (int64_t)xRaw.vAln.size( ), xRaw.vRuns.data( ),
+                                              (int64_t)xRaw.vRuns.size( ) ) );
+    }
+
+  private:
+    PinnedVector<uint8_t> vSlab; // the reads of the current batch as the C ABI takes them, kept between batches
+    PinnedVector<int64_t> vOffsets;
 };
 
 } // namespace libMA_b200

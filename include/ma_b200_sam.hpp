@@ -13,7 +13,11 @@
 #pragma once
 #include "ma_b200_modules.hpp"
 #include <cmath>
+#include <fcntl.h>
 #include <string>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 namespace libMA_b200
 {
@@ -224,118 +228,116 @@ class SamWriter
 // letter other than ACGTacgt becomes N (nucSeq.cpp:17-28).
 class ReadParser
 {
-    std::string sData;
-    size_t uiPos = 0;
+    // the file, memory mapped (falls back to reading it when it cannot be mapped, e.g. a pipe)
+    const char* pData = nullptr;
+    size_t uiSize = 0, uiPos = 0;
+    void* pMap = nullptr;
+    std::string sBuffer;
 
-    bool eof( ) const
+    // one line [b, e) starting at uiAt; uiAt moves behind its LF / CR / CR LF
+    static void line( const char* p, size_t uiEnd, size_t& uiAt, size_t& b, size_t& e )
     {
-        return uiPos >= sData.size( );
-    }
-    char peek( ) const
-    {
-        return eof( ) ? (char)-1 : sData[ uiPos ];
-    }
-    std::string line( )
-    {
-        std::string t;
-        while( uiPos < sData.size( ) )
+        b = uiAt;
+        const char* pLf = (const char*)memchr( p + uiAt, '\n', uiEnd - uiAt );
+        const size_t uiLf = pLf ? (size_t)( pLf - p ) : uiEnd;
+        const char* pCr = (const char*)memchr( p + uiAt, '\r', uiLf - uiAt );
+        if( pCr )
         {
-            const char c = sData[ uiPos++ ];
-            if( c == '\n' )
-                return t;
-            if( c == '\r' )
-            {
-                if( uiPos < sData.size( ) && sData[ uiPos ] == '\n' )
-                    uiPos++;
-                return t;
-            }
-            t += c;
+            e = (size_t)( pCr - p );
+            uiAt = e + 1;
+            if( uiAt < uiEnd && p[ uiAt ] == '\n' )
+                uiAt++;
         }
-        return t;
+        else
+        {
+            e = uiLf;
+            uiAt = uiLf < uiEnd ? uiLf + 1 : uiEnd;
+        }
     }
     static bool validNuc( char c )
     {
-        for( char c2 : { 'A', 'C', 'G', 'T', 'N', 'U', 'R', 'Y', 'K', 'M', 'S', 'W', 'B', 'D', 'H', 'V' } )
-            if( c2 == toupper( c ) )
+        switch( c )
+        {
+            case 'A': case 'C': case 'G': case 'T': case 'N': case 'U': case 'R': case 'Y': case 'K': case 'M': case 'S':
+            case 'W': case 'B': case 'D': case 'H': case 'V':
+            case 'a': case 'c': case 'g': case 't': case 'n': case 'u': case 'r': case 'y': case 'k': case 'm': case 's':
+            case 'w': case 'b': case 'd': case 'h': case 'v':
                 return true;
-        return false;
-    }
-    static size_t len( const std::string& s )
-    {
-        size_t n = s.size( );
-        while( n > 0 && !validNuc( s[ n - 1 ] ) )
-            n--;
-        return n;
-    }
-    static void append( NucSeq& q, const std::string& s, size_t n )
-    {
-        for( size_t i = 0; i < n; i++ )
-        {
-            const char c = s[ i ];
-            q.vSeq.push_back( c == 'A' || c == 'a' ? 0 : c == 'C' || c == 'c' ? 1 : c == 'G' || c == 'g' ? 2
-                                                   : c == 'T' || c == 't' ? 3 : 4 );
+            default:
+                return false;
         }
     }
-    void advanceTillNext( )
+    static void append( NucSeq& q, const char* p, size_t b, size_t e )
     {
-        while( !( eof( ) || peek( ) == '>' || peek( ) == '@' ) )
-            uiPos++;
-    }
-
-  public:
-    explicit ReadParser( const std::string& sFileName )
-    {
-        std::ifstream in( sFileName, std::ios::binary );
-        if( !in )
-            throw std::runtime_error( "Unable to open file " + sFileName );
-        sData.assign( ( std::istreambuf_iterator<char>( in ) ), std::istreambuf_iterator<char>( ) );
-    }
-    // next read; false at the end of the file
-    bool next( NucSeq& q )
-    {
-        if( eof( ) )
-            return false;
-        q = NucSeq( );
-        std::string s;
-        if( peek( ) == '>' )
+        while( e > b && !validNuc( p[ e - 1 ] ) ) // fileReader.cpp:12-27
+            e--;
+        const size_t o = q.vSeq.size( );
+        q.vSeq.resize( o + ( e - b ) );
+        static const struct Lut
         {
-            s = line( );
-            q.sName = s.substr( 1, s.find( ' ' ) - 1 );
-            while( !eof( ) && peek( ) != '>' && peek( ) != ' ' )
+            uint8_t a[ 256 ];
+            Lut( )
             {
-                s = line( );
-                if( !s.empty( ) )
-                    append( q, s, len( s ) );
+                memset( a, 4, sizeof( a ) ); // every other letter becomes N (nucSeq.cpp:17-28)
+                a[ 'A' ] = a[ 'a' ] = 0, a[ 'C' ] = a[ 'c' ] = 1, a[ 'G' ] = a[ 'g' ] = 2, a[ 'T' ] = a[ 't' ] = 3;
+            }
+        } xLut;
+        uint8_t* pOut = q.vSeq.data( ) + o;
+        for( size_t i = b; i < e; i++ )
+            pOut[ i - b ] = xLut.a[ (unsigned char)p[ i ] ];
+    }
+    static void name( NucSeq& q, const char* p, size_t b, size_t e )
+    {
+        const char* pBlank = (const char*)memchr( p + b, ' ', e - b );
+        q.sName.assign( p + b + 1, ( pBlank ? (size_t)( pBlank - p ) : e ) - b - 1 );
+    }
+    // FileReader::execute on [uiAt, uiEnd): with STORE the read goes to *pQ, without it only uiAt moves to the record
+    // that follows (same control flow, so that record boundaries found by one pass hold for the other)
+    template <bool STORE> static void parseOne( const char* p, const size_t uiEnd, size_t& uiAt, NucSeq* pQ )
+    {
+        size_t b, e;
+        if( STORE ) // cleared, not replaced: a recycled NucSeq keeps its buffers
+            pQ->vSeq.clear( ), pQ->vQual.clear( ), pQ->sName.clear( );
+        if( p[ uiAt ] == '>' )
+        {
+            line( p, uiEnd, uiAt, b, e );
+            if( STORE )
+                name( *pQ, p, b, e );
+            while( uiAt < uiEnd && p[ uiAt ] != '>' && p[ uiAt ] != ' ' )
+            {
+                line( p, uiEnd, uiAt, b, e );
+                if( STORE && e > b )
+                    append( *pQ, p, b, e );
             }
         }
-        else if( peek( ) == '@' )
+        else if( p[ uiAt ] == '@' )
         {
-            s = line( );
-            q.sName = s.substr( 1, s.find( ' ' ) - 1 );
-            while( !eof( ) && peek( ) != '+' && peek( ) != ' ' )
+            line( p, uiEnd, uiAt, b, e );
+            if( STORE )
+                name( *pQ, p, b, e );
+            while( uiAt < uiEnd && p[ uiAt ] != '+' && p[ uiAt ] != ' ' )
             {
-                s = line( );
-                if( !s.empty( ) )
-                    append( q, s, len( s ) );
+                line( p, uiEnd, uiAt, b, e );
+                if( STORE && e > b )
+                    append( *pQ, p, b, e );
             }
-            q.vQual.assign( q.vSeq.size( ), 126 ); // NucSeq::addQuality fills with 126 (nucSeq.h resize default)
-            s = line( );
-            if( !s.empty( ) && s[ 0 ] == '+' )
+            if( STORE )
+                pQ->vQual.assign( pQ->vSeq.size( ), 126 ); // NucSeq::addQuality fills with 126 (nucSeq.h resize default)
+            line( p, uiEnd, uiAt, b, e );
+            if( e > b && p[ b ] == '+' )
             {
                 size_t uiQ = 0;
-                while( !eof( ) && ( peek( ) != '@' || uiQ == 0 ) )
+                while( uiAt < uiEnd && ( p[ uiAt ] != '@' || uiQ == 0 ) )
                 {
-                    s = line( );
-                    if( s.empty( ) )
+                    line( p, uiEnd, uiAt, b, e );
+                    const size_t n = e - b;
+                    if( n == 0 )
                         continue;
-                    size_t n = s.size( );
-                    while( n > 0 && ( s[ n - 1 ] == '\n' || s[ n - 1 ] == '\r' ) )
-                        n--;
-                    for( size_t i = 0; i < n; i++ )
+                    if( STORE )
                     {
-                        if( uiQ + i >= q.vQual.size( ) )
-                            q.vQual.resize( uiQ + i + 1, 126 );
-                        q.vQual[ uiQ + i ] = (uint8_t)s[ i ];
+                        if( uiQ + n > pQ->vQual.size( ) )
+                            pQ->vQual.resize( uiQ + n, 126 );
+                        memcpy( pQ->vQual.data( ) + uiQ, p + b, n );
                     }
                     uiQ += n;
                 }
@@ -343,10 +345,67 @@ class ReadParser
         }
         else
             throw std::runtime_error( "Error while reading file.\nIs your input really in FASTA/Q format?" );
-        if( q.length( ) == 0 )
-            throw std::runtime_error( "found empty read: " + q.sName );
-        advanceTillNext( );
+        if( STORE && pQ->length( ) == 0 )
+            throw std::runtime_error( "found empty read: " + pQ->sName );
+        while( uiAt < uiEnd && p[ uiAt ] != '>' && p[ uiAt ] != '@' ) // advanceTillNext
+            uiAt++;
+    }
+
+  public:
+    explicit ReadParser( const std::string& sFileName )
+    {
+        const int fd = open( sFileName.c_str( ), O_RDONLY );
+        if( fd < 0 )
+            throw std::runtime_error( "Unable to open file " + sFileName );
+        struct stat xStat;
+        if( fstat( fd, &xStat ) == 0 && S_ISREG( xStat.st_mode ) && xStat.st_size > 0 )
+        {
+            void* pM = mmap( nullptr, (size_t)xStat.st_size, PROT_READ, MAP_PRIVATE, fd, 0 );
+            if( pM != MAP_FAILED )
+            {
+                pMap = pM, pData = (const char*)pM, uiSize = (size_t)xStat.st_size;
+                madvise( pM, uiSize, MADV_SEQUENTIAL );
+            }
+        }
+        if( !pMap )
+        {
+            char aBuf[ 1 << 16 ];
+            ssize_t n;
+            while( ( n = read( fd, aBuf, sizeof( aBuf ) ) ) > 0 )
+                sBuffer.append( aBuf, (size_t)n );
+            pData = sBuffer.data( ), uiSize = sBuffer.size( );
+        }
+        close( fd );
+    }
+    ReadParser( const ReadParser& ) = delete;
+    ReadParser& operator=( const ReadParser& ) = delete;
+    ~ReadParser( )
+    {
+        if( pMap )
+            munmap( pMap, uiSize );
+    }
+    // next read; false at the end of the file
+    bool next( NucSeq& q )
+    {
+        if( uiPos >= uiSize )
+            return false;
+        parseOne<true>( pData, uiSize, uiPos, &q );
         return true;
+    }
+    // Two-pass use for host threads: nextRecord() is the serial pass (line ends and first characters only) that yields
+    // the byte range of the next record; parseRecord() converts one such range and may run on any thread.
+    bool nextRecord( size_t& uiBegin, size_t& uiEnd )
+    {
+        if( uiPos >= uiSize )
+            return false;
+        uiBegin = uiPos;
+        parseOne<false>( pData, uiSize, uiPos, nullptr );
+        uiEnd = uiPos;
+        return true;
+    }
+    void parseRecord( size_t uiBegin, size_t uiEnd, NucSeq& q ) const
+    {
+        parseOne<true>( pData, uiEnd, uiBegin, &q );
     }
 };
 

@@ -9,17 +9,26 @@
 //   -m, --MateIn       mate file(s); switches "Use Paired Reads" on like the reference (cmdMa.cpp:323-330)
 //   -o, --Out          SAM file (default: standard output)
 //   -p, --Presetting   Default | Illumina | Illumina_Paired | PacBio | Nanopore (default: Default)
-//   -t                 accepted and ignored (the reference's host thread count)
+//   -t                 host threads that format SAM records (default: all; the alignment itself runs on the GPU)
+//   --Verbose          prints the busy time of the host stages
 //   --Interleaved      with a paired presetting and no -m: reads 2k, 2k+1 of -i are mates (not in the reference)
-//   --Device <n>       CUDA device (default 0)
-//   --Batch <n>        reads per GPU batch (default 1000000; pairs are never split)
+//   --Devices <a,b,..> CUDA devices (default 0). The index is replicated on every device, batches go to whichever device
+//                      is free, no collective is involved; the output order does not depend on it
+//   --Batch <n>        reads per GPU batch (default 500000; pairs are never split)
 //   --Srand <n>        RANSAC stream of read i is srand(n + i) (parity contract; default 0)
 //
 // Records are written in input order. There is no CPU path: the program fails when no CUDA device is present.
 #include "../../include/ma_b200_modules.hpp"
 #include "../../include/ma_b200_sam.hpp"
+#include <chrono>
+#include <condition_variable>
 #include <cstdio>
+#include <deque>
+#include <exception>
 #include <iostream>
+#include <map>
+#include <mutex>
+#include <thread>
 
 using namespace libMA_b200;
 
@@ -45,6 +54,47 @@ static std::string lower( std::string s )
         c = (char)tolower( c );
     return s;
 }
+
+// hand-over between the host stages; push() returns false once the queue is closed
+template <typename T> class BoundedQueue
+{
+    std::mutex xMutex;
+    std::condition_variable xCv;
+    std::deque<T> vItems;
+    size_t uiCapacity;
+    bool bClosed = false;
+
+  public:
+    explicit BoundedQueue( size_t uiCap ) : uiCapacity( uiCap )
+    {}
+    bool push( T x )
+    {
+        std::unique_lock<std::mutex> xLock( xMutex );
+        xCv.wait( xLock, [ & ]( ) { return bClosed || vItems.size( ) < uiCapacity; } );
+        if( bClosed )
+            return false;
+        vItems.push_back( std::move( x ) );
+        xCv.notify_all( );
+        return true;
+    }
+    bool pop( T& x ) // false: closed and drained
+    {
+        std::unique_lock<std::mutex> xLock( xMutex );
+        xCv.wait( xLock, [ & ]( ) { return bClosed || !vItems.empty( ); } );
+        if( vItems.empty( ) )
+            return false;
+        x = std::move( vItems.front( ) );
+        vItems.pop_front( );
+        xCv.notify_all( );
+        return true;
+    }
+    void close( )
+    {
+        std::lock_guard<std::mutex> xLock( xMutex );
+        bClosed = true;
+        xCv.notify_all( );
+    }
+};
 
 // one stream of reads over several files
 class ReadStream
@@ -77,10 +127,11 @@ int main( int argc, char** argv )
 {
     std::string sIndex, sOut, sPreset = "Default";
     std::vector<std::string> vIn, vMate;
-    int iDevice = 0;
-    size_t uiBatch = 1000000;
+    std::vector<int> vDevices( 1, 0 );
+    size_t uiBatch = 500000;
     uint32_t uiSrand = 0;
-    bool bInterleaved = false;
+    bool bInterleaved = false, bVerbose = false;
+    size_t uiThreads = std::max( 1u, std::thread::hardware_concurrency( ) );
     try
     {
         for( int i = 1; i < argc; i++ )
@@ -102,11 +153,19 @@ int main( int argc, char** argv )
             else if( sOpt == "-p" || sLow == "--presetting" )
                 sPreset = value( );
             else if( sOpt == "-t" )
-                value( );
+                uiThreads = (size_t)std::max( 1, atoi( value( ).c_str( ) ) );
+            else if( sLow == "--verbose" )
+                bVerbose = true;
             else if( sLow == "--interleaved" )
                 bInterleaved = true;
-            else if( sLow == "--device" )
-                iDevice = atoi( value( ).c_str( ) );
+            else if( sLow == "--device" || sLow == "--devices" )
+            {
+                vDevices.clear( );
+                for( auto& d : splitList( value( ) ) )
+                    vDevices.push_back( atoi( d.c_str( ) ) );
+                if( vDevices.empty( ) )
+                    throw std::runtime_error( "--Devices needs a list of CUDA devices" );
+            }
             else if( sLow == "--batch" )
                 uiBatch = (size_t)atoll( value( ).c_str( ) );
             else if( sLow == "--srand" )
@@ -119,9 +178,14 @@ int main( int argc, char** argv )
             std::cerr << "usage: maCMD_b200 -x <index prefix> -i <reads> [-m <mates>] [-o <out.sam>] [-p <presetting>]\n";
             return argc <= 1 ? 0 : 1;
         }
-        Aligner xAligner( sIndex, sPreset, iDevice );
-        if( !vMate.empty( ) )
-            xAligner.params( ).xParams.use_paired_reads = 1;
+        std::vector<std::unique_ptr<Aligner>> vAligners;
+        for( int iDevice : vDevices )
+        {
+            vAligners.emplace_back( new Aligner( sIndex, sPreset, iDevice ) );
+            if( !vMate.empty( ) )
+                vAligners.back( )->params( ).xParams.use_paired_reads = 1;
+        }
+        Aligner& xAligner = *vAligners[ 0 ];
         const bool bPaired = xAligner.params( ).xParams.use_paired_reads != 0;
         if( bPaired && vMate.empty( ) && !bInterleaved )
             throw std::runtime_error( "paired presetting: give the mates with -m (or --Interleaved)" );
@@ -136,43 +200,177 @@ int main( int argc, char** argv )
         const std::string sHead = xWriter.header( );
         fwrite( sHead.data( ), 1, sHead.size( ), pOut );
 
-        ReadStream xIn( vIn ), xMate( vMate );
-        std::vector<NucSeq> vReads;
-        size_t uiDone = 0;
-        bool bMore = true;
-        while( bMore )
+        // three host stages run concurrently: the reader parses batch k + 1 while the GPU aligns batch k and the writer
+        // formats batch k - 1 on uiThreads host threads (records of different reads are independent)
+        struct Batch
         {
-            vReads.clear( );
-            NucSeq xQ;
-            while( vReads.size( ) < uiBatch && ( bMore = xIn.next( xQ ) ) )
+            std::vector<NucSeq> vReads;
+            size_t uiFirst = 0, uiSeq = 0;
+            RawReport xRaw;
+        };
+        const size_t uiPool = 3 + 2 * vAligners.size( );
+        BoundedQueue<std::unique_ptr<Batch>> xParsed( 2 ), xAligned( 2 + vAligners.size( ) ), xFree( uiPool );
+        for( size_t i = 0; i < uiPool; i++ )
+            xFree.push( std::make_unique<Batch>( ) );
+        std::exception_ptr pReaderError, pWriterError;
+        double fParse = 0, fGpu = 0, fFormat = 0, fWrite = 0;
+        auto now = []( ) { return std::chrono::steady_clock::now( ); };
+        auto secs = []( std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b ) {
+            return std::chrono::duration<double>( b - a ).count( );
+        };
+
+        std::thread xReader( [ & ]( ) {
+            try
             {
-                vReads.push_back( xQ );
-                if( !vMate.empty( ) )
+                ReadStream xIn( vIn ), xMate( vMate );
+                size_t uiDone = 0, uiSeq = 0;
+                bool bMore = true;
+                while( bMore )
                 {
-                    if( !xMate.next( xQ ) )
-                        throw std::runtime_error( "fewer mates than reads" );
-                    vReads.push_back( xQ );
+                    std::unique_ptr<Batch> pB;
+                    if( !xFree.pop( pB ) ) // recycled: the reads of a used batch keep their buffers
+                        return;
+                    const auto t0 = now( );
+                    pB->uiFirst = uiDone, pB->uiSeq = uiSeq++;
+                    auto& v = pB->vReads;
+                    size_t n = 0;
+                    while( n < uiBatch )
+                    {
+                        if( v.size( ) < n + 2 )
+                            v.resize( n + 2 );
+                        if( !( bMore = xIn.next( v[ n ] ) ) )
+                            break;
+                        n++;
+                        if( !vMate.empty( ) )
+                        {
+                            if( !xMate.next( v[ n ] ) )
+                                throw std::runtime_error( "fewer mates than reads" );
+                            n++;
+                        }
+                    }
+                    v.resize( n );
+                    if( n == 0 )
+                        break;
+                    if( bPaired && n % 2 )
+                        throw std::runtime_error( "odd number of reads for a paired presetting" );
+                    uiDone += n;
+                    fParse += secs( t0, now( ) );
+                    if( !xParsed.push( std::move( pB ) ) )
+                        return;
+                }
+                NucSeq xQ;
+                if( !vMate.empty( ) && xMate.next( xQ ) )
+                    throw std::runtime_error( "more mates than reads" );
+            }
+            catch( ... )
+            {
+                pReaderError = std::current_exception( );
+            }
+            xParsed.close( );
+        } );
+
+        std::thread xWriterThread( [ & ]( ) {
+            try
+            {
+                std::unique_ptr<Batch> pNext;
+                std::vector<std::string> vText; // kept over the batches: the buffers are reused
+                std::map<size_t, std::unique_ptr<Batch>> xPending; // batches of other devices that finished early
+                size_t uiDone = 0, uiSeq = 0;
+                while( xAligned.pop( pNext ) )
+                {
+                    xPending[ pNext->uiSeq ] = std::move( pNext );
+                    while( !xPending.empty( ) && xPending.begin( )->first == uiSeq )
+                    {
+                    std::unique_ptr<Batch> pB = std::move( xPending.begin( )->second );
+                    xPending.erase( xPending.begin( ) );
+                    uiSeq++;
+                    const auto t0 = now( );
+                    const size_t uiUnits = pB->xRaw.units( );
+                    const size_t uiChunks = std::max<size_t>( 1, std::min<size_t>( uiThreads, uiUnits / 256 + 1 ) );
+                    vText.resize( std::max( vText.size( ), uiChunks ) );
+                    for( auto& sText : vText )
+                        sText.clear( );
+                    std::vector<std::thread> vWorkers;
+                    std::vector<std::exception_ptr> vErr( uiChunks );
+                    for( size_t c = 0; c < uiChunks; c++ )
+                        vWorkers.emplace_back( [ &, c ]( ) {
+                            try
+                            {
+                                std::string& sText = vText[ c ];
+                                for( size_t u = uiUnits * c / uiChunks; u < uiUnits * ( c + 1 ) / uiChunks; u++ )
+                                    if( bPaired )
+                                        sText += xWriter.paired( pB->vReads[ 2 * u ], pB->vReads[ 2 * u + 1 ],
+                                                                 pB->xRaw.records( u ) );
+                                    else
+                                        sText += xWriter.single( pB->vReads[ u ], pB->xRaw.records( u ) );
+                            }
+                            catch( ... )
+                            {
+                                vErr[ c ] = std::current_exception( );
+                            }
+                        } );
+                    for( auto& t : vWorkers )
+                        t.join( );
+                    for( auto& e : vErr )
+                        if( e )
+                            std::rethrow_exception( e );
+                    const auto t1 = now( );
+                    for( auto& sText : vText )
+                        if( fwrite( sText.data( ), 1, sText.size( ), pOut ) != sText.size( ) )
+                            throw std::runtime_error( "write error on " + ( sOut.empty( ) ? std::string( "stdout" ) : sOut ) );
+                    fFormat += secs( t0, t1 ), fWrite += secs( t1, now( ) );
+                    uiDone += pB->vReads.size( );
+                    std::cerr << "\r" << uiDone << " reads aligned." << std::flush;
+                    xFree.push( std::move( pB ) );
+                    }
                 }
             }
-            if( vReads.empty( ) )
-                break;
-            if( bPaired && vReads.size( ) % 2 )
-                throw std::runtime_error( "odd number of reads for a paired presetting" );
-            xAligner.params( ).xParams.srand_base = uiSrand + (uint32_t)uiDone;
-            auto vRep = xAligner.report( vReads );
-            std::string sText;
-            if( bPaired )
-                for( size_t p = 0; p < vRep.size( ); p++ )
-                    sText += xWriter.paired( vReads[ 2 * p ], vReads[ 2 * p + 1 ], vRep[ p ] );
-            else
-                for( size_t k = 0; k < vRep.size( ); k++ )
-                    sText += xWriter.single( vReads[ k ], vRep[ k ] );
-            fwrite( sText.data( ), 1, sText.size( ), pOut );
-            uiDone += vReads.size( );
-            std::cerr << "\r" << uiDone << " reads aligned." << std::flush;
-        }
-        if( !vMate.empty( ) && xMate.next( vReads.emplace_back( ) ) )
-            throw std::runtime_error( "more mates than reads" );
+            catch( ... )
+            {
+                pWriterError = std::current_exception( );
+                xAligned.close( ), xFree.close( );
+            }
+        } );
+
+        std::vector<std::exception_ptr> vGpuError( vAligners.size( ) );
+        std::vector<double> vGpuBusy( vAligners.size( ), 0.0 );
+        std::vector<std::thread> vGpuThreads;
+        for( size_t g = 0; g < vAligners.size( ); g++ ) // one host thread per device (a context is not re-entrant)
+            vGpuThreads.emplace_back( [ &, g ]( ) {
+                try
+                {
+                    std::unique_ptr<Batch> pB;
+                    while( xParsed.pop( pB ) )
+                    {
+                        const auto t0 = now( );
+                        vAligners[ g ]->params( ).xParams.srand_base = uiSrand + (uint32_t)pB->uiFirst;
+                        vAligners[ g ]->reportRaw( pB->vReads, pB->xRaw );
+                        vGpuBusy[ g ] += secs( t0, now( ) );
+                        if( !xAligned.push( std::move( pB ) ) )
+                            break;
+                    }
+                }
+                catch( ... )
+                {
+                    vGpuError[ g ] = std::current_exception( );
+                    xParsed.close( );
+                }
+            } );
+        for( auto& t : vGpuThreads )
+            t.join( );
+        xParsed.close( ), xFree.close( ); // releases a reader that still waits after the devices stopped early
+        for( double f : vGpuBusy )
+            fGpu = std::max( fGpu, f );
+        xAligned.close( );
+        xReader.join( );
+        xWriterThread.join( );
+        vGpuError.push_back( pReaderError ), vGpuError.push_back( pWriterError );
+        for( auto& e : vGpuError )
+            if( e )
+                std::rethrow_exception( e );
+        if( bVerbose )
+            fprintf( stderr, "\rbusy seconds: reader %.3f, gpu stage (upload, kernels, download; max over %zu devices) %.3f, "
+                             "format %.3f (%zu threads), write %.3f\n", fParse, vAligners.size( ), fGpu, fFormat, uiThreads, fWrite );
         if( pOut != stdout )
             fclose( pOut );
         std::cerr << "\rdone.                         " << std::endl;

@@ -226,6 +226,23 @@ extern "C" int64_t ma_b200_launch_count( const ma_b200_ctx* ctx )
     return ctx ? ctx->launches : 0;
 }
 
+extern "C" void* ma_b200_host_alloc( int64_t bytes )
+{
+    void* p = nullptr;
+    if( bytes <= 0 || cudaHostAlloc( &p, (size_t)bytes, cudaHostAllocPortable ) != cudaSuccess )
+    {
+        cudaGetLastError( );
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void ma_b200_host_free( void* p )
+{
+    if( p )
+        cudaFreeHost( p );
+}
+
 extern "C" int ma_b200_set_params( ma_b200_ctx* ctx, const ma_b200_params* params )
 {
     if( !ctx || !params )

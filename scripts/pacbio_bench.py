@@ -1,0 +1,86 @@
+"""configs[3]-shaped measurement: PacBio preset, simulated 10 kbp reads with 12 % error (4 % subst + 4 % ins + 4 % del)
+on a synthetic genome (default 1000 Mbp: the largest the GPU index builder takes, HBM-resident index), next to the
+UNMODIFIED reference (oracle/_ref/ref_dump bench, all host threads) on a bounded sample of the same reads.
+
+  python scripts/pacbio_bench.py [--reads 4000] [--len 10000] [--genome-mbp 1000] [--cpu-sample 160] [--out f.json]
+
+Prints one JSON line. Device time = CUDA-event stage times of the C ABI's stats; reads are resident in HBM.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench as B  # noqa: E402
+from ma_b200 import api, synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reads", type=int, default=4000)
+    ap.add_argument("--len", type=int, default=10000)
+    ap.add_argument("--genome-mbp", type=int, default=1000)
+    ap.add_argument("--cpu-sample", type=int, default=160)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    n_contigs = 10
+    genome = synth.random_genome([a.genome_mbp * 1_000_000 // n_contigs] * n_contigs, 3)
+    reads, *_ = synth.simulate_long_reads(genome, a.reads, a.len, 4)
+    ctx = api.Context(0, "pacbio")
+    lens = [len(c) for c in genome]
+    t = time.time()
+    ctx.index_build(np.concatenate(genome), np.cumsum([0] + lens[:-1]), lens)
+    t_index = time.time() - t
+    data, off = api.pack_reads(reads)
+    ctx.align_upload(data, off)
+    ctx.align_run()  # warm-up: sizes the slabs
+    best = None
+    for _ in range(a.steps):
+        t = time.time()
+        st = ctx.align_run()
+        st["wall_ms"] = (time.time() - t) * 1e3
+        if best is None or st["wall_ms"] < best["wall_ms"]:
+            best = st
+    info, alns, runs = ctx.download_alignments()
+    ms = best["wall_ms"]
+    line = {"metric": "aligned reads/sec (PacBio preset, %d bp reads, 12%% error)" % a.len,
+            "value": a.reads / ms * 1e3, "unit": "reads/s", "Mbp_per_s": a.reads * a.len / ms / 1e3,
+            "config": {"workload": "configs[3]-shaped: %d simulated reads of %d bp, 4%% subst + 4%% ins + 4%% del, "
+                                   "synthetic %d Mbp genome (10 contigs), PacBio preset" % (a.reads, a.len, a.genome_mbp)},
+            "ms_per_step": ms, "index_build_s": t_index,
+            "stage_ms": {k: round(v, 3) for k, v in best.items() if k.startswith("ms_")},
+            "work": {k: int(v) for k, v in best.items() if k.startswith("n_") or k == "dp_cells"},
+            "dp_gcups": best["dp_cells"] / best["ms_dp"] / 1e6 if best.get("ms_dp") else None,
+            "aligned_reads": int((info["n_sets"] > 0).sum()), "alignments": int(len(alns))}
+    if a.cpu_sample > 0 and os.path.exists(B.REF_DUMP):
+        prefix, how = B.ensure_index_files(genome, a.genome_mbp, 3, ctx)
+        threads = os.cpu_count() or 1
+        os.makedirs(B.CACHE, exist_ok=True)
+        rf = os.path.join(B.CACHE, "pb_sample_%d.txt" % os.getpid())
+        with open(rf, "w") as f:
+            for r in reads[:a.cpu_sample]:
+                f.write("".join("ACGTN"[c] for c in r) + "\n")
+        import subprocess
+        try:
+            out = subprocess.check_output([B.REF_DUMP, "bench", prefix, rf, "pacbio", str(threads)]).decode()
+        finally:
+            os.remove(rf)
+        ref = json.loads(out.strip().splitlines()[-1])
+        line["cpu_baseline"] = {"value": ref["reads_per_s"], "unit": "reads/s", "cores": threads, "kind": "reference",
+                                "sample": "first %d reads, ref_dump bench pacbio (index: %s)" % (a.cpu_sample, how),
+                                "stage_cpu_s": ref.get("stage_cpu_s")}
+    s = json.dumps(line)
+    print(s)
+    if a.out:
+        open(a.out, "w").write(s + "\n")
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
