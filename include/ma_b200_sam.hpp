@@ -12,6 +12,7 @@
 // CIGARs of 65 536 operations or more.
 #pragma once
 #include "ma_b200_modules.hpp"
+#include <algorithm>
 #include <cmath>
 #include <fcntl.h>
 #include <string>
@@ -59,16 +60,21 @@ class SamWriter
     }
     std::string cigar( const Alignment& a, size_t uiQuerySize ) const
     {
-        const bool bRev = onReverse( a.uiBeginOnRef );
-        const char* sClip = bSoftClip ? "S" : "H";
         std::string s;
+        cigar( s, a, uiQuerySize );
+        return s;
+    }
+    void cigar( std::string& s, const Alignment& a, size_t uiQuerySize ) const
+    {
+        const bool bRev = onReverse( a.uiBeginOnRef );
+        const char cClip = bSoftClip ? 'S' : 'H';
         if( bRev )
         {
             if( a.uiEndOnQuery < uiQuerySize )
-                s.append( std::to_string( uiQuerySize - a.uiEndOnQuery ) ).append( sClip );
+                num( s, uiQuerySize - a.uiEndOnQuery ), s += cClip;
         }
         else if( a.uiBeginOnQuery > 0 )
-            s.append( std::to_string( a.uiBeginOnQuery ) ).append( sClip );
+            num( s, a.uiBeginOnQuery ), s += cClip;
         size_t uiM = 0;
         const size_t n = a.data.size( );
         for( size_t k = 0; k < n; k++ )
@@ -79,39 +85,44 @@ class SamWriter
                 if( d.first == MatchType::insertion || d.first == MatchType::deletion )
                 {
                     if( uiM > 0 )
-                        s.append( std::to_string( uiM ) ).append( "M" ), uiM = 0;
-                    s.append( std::to_string( d.second ) ).append( d.first == MatchType::insertion ? "I" : "D" );
+                        num( s, uiM ), s += 'M', uiM = 0;
+                    num( s, d.second ), s += d.first == MatchType::insertion ? 'I' : 'D';
                 }
                 else
                     uiM += d.second;
             }
             else
-                s.append( std::to_string( d.second ) )
-                    .append( d.first == MatchType::missmatch   ? "X"
-                             : d.first == MatchType::insertion ? "I"
-                             : d.first == MatchType::deletion  ? "D"
-                                                               : "=" );
+                num( s, d.second ), s += d.first == MatchType::missmatch   ? 'X'
+                                         : d.first == MatchType::insertion ? 'I'
+                                         : d.first == MatchType::deletion  ? 'D'
+                                                                           : '=';
         }
         if( uiM > 0 )
-            s.append( std::to_string( uiM ) ).append( "M" );
+            num( s, uiM ), s += 'M';
         if( bRev )
         {
             if( a.uiBeginOnQuery > 0 )
-                s.append( std::to_string( a.uiBeginOnQuery ) ).append( sClip );
+                num( s, a.uiBeginOnQuery ), s += cClip;
         }
         else if( a.uiEndOnQuery < uiQuerySize )
-            s.append( std::to_string( uiQuerySize - a.uiEndOnQuery ) ).append( sClip );
-        return s;
+            num( s, uiQuerySize - a.uiEndOnQuery ), s += cClip;
     }
     static std::string text( const NucSeq& q, size_t b, size_t e, bool bComplement )
     {
         std::string s;
         if( bComplement )
-            for( size_t i = e; i > b; i-- )
-                s += "TGCAN"[ q.vSeq[ i - 1 ] < 4 ? q.vSeq[ i - 1 ] : 4 ];
+        {
+            s.resize( e > b ? e - b : 0 );
+            for( size_t i = e, k = 0; i > b; i--, k++ )
+                s[ k ] = "TGCAN"[ q.vSeq[ i - 1 ] < 4 ? q.vSeq[ i - 1 ] : 4 ];
+        }
         else
-            for( size_t i = b; i < e && i < q.length( ); i++ )
-                s += "ACGTN"[ q.vSeq[ i ] < 4 ? q.vSeq[ i ] : 4 ];
+        {
+            e = std::min( e, q.length( ) );
+            s.resize( e > b ? e - b : 0 );
+            for( size_t i = b; i < e; i++ )
+                s[ i - b ] = "ACGTN"[ q.vSeq[ i ] < 4 ? q.vSeq[ i ] : 4 ];
+        }
         return s;
     }
     std::string segment( const Alignment& a, const NucSeq& q ) const
@@ -124,10 +135,8 @@ class SamWriter
     {
         if( q.vQual.empty( ) )
             return "*";
-        std::string s;
-        for( size_t i = b; i < e && i < q.length( ); i++ )
-            s += (char)q.vQual[ i ];
-        return s;
+        e = std::min( e, q.length( ) );
+        return e > b ? std::string( (const char*)q.vQual.data( ) + b, e - b ) : std::string( );
     }
     static std::string mapq( const Alignment& a, bool bClamp )
     {
@@ -135,6 +144,51 @@ class SamWriter
             return "255";
         const int v = static_cast<int>( std::ceil( a.fMappingQuality * 254 ) );
         return std::to_string( bClamp ? std::min( v, 255 ) : v );
+    }
+
+    static void num( std::string& s, uint64_t v )
+    {
+        char a[ 24 ];
+        int n = 0;
+        do
+            a[ n++ ] = (char)( '0' + v % 10 ), v /= 10;
+        while( v );
+        while( n )
+            s += a[ --n ];
+    }
+    static void text( std::string& s, const NucSeq& q, size_t b, size_t e, bool bComplement )
+    {
+        if( !bComplement )
+            e = std::min( e, q.length( ) );
+        if( e <= b )
+            return;
+        const size_t o = s.size( );
+        s.resize( o + ( e - b ) );
+        char* p = &s[ o ];
+        if( bComplement )
+            for( size_t i = e, k = 0; i > b; i--, k++ )
+                p[ k ] = "TGCAN"[ q.vSeq[ i - 1 ] < 4 ? q.vSeq[ i - 1 ] : 4 ];
+        else
+            for( size_t i = b; i < e; i++ )
+                p[ i - b ] = "ACGTN"[ q.vSeq[ i ] < 4 ? q.vSeq[ i ] : 4 ];
+    }
+    void segment( std::string& s, const Alignment& a, const NucSeq& q ) const
+    {
+        if( bSoftClip )
+            text( s, q, 0, q.length( ), onReverse( a.uiBeginOnRef ) );
+        else
+            text( s, q, a.uiBeginOnQuery, a.uiEndOnQuery, onReverse( a.uiBeginOnRef ) );
+    }
+    static void qual( std::string& s, const NucSeq& q, size_t b, size_t e )
+    {
+        if( q.vQual.empty( ) )
+        {
+            s += '*';
+            return;
+        }
+        e = std::min( e, q.length( ) );
+        if( e > b )
+            s.append( (const char*)q.vQual.data( ) + b, e - b );
     }
 
   public:
@@ -155,26 +209,42 @@ class SamWriter
     std::string single( const NucSeq& q, const std::vector<Alignment>& v ) const
     {
         std::string s;
+        single( s, q, v );
+        return s;
+    }
+    // the same, appended to a caller-owned buffer (no temporaries: the writer threads of maCMD_b200 use these)
+    void single( std::string& s, const NucSeq& q, const std::vector<Alignment>& v ) const
+    {
+        const size_t uiBefore = s.size( );
         for( const Alignment& a : v )
         {
             if( a.uiLength == 0 || ( bNoSecondary && a.bSecondary ) || ( bNoSupplementary && a.bSupplementary ) )
                 continue;
-            s += q.sName + "\t" + std::to_string( samFlag( a ) ) + "\t" + contig( a ) + "\t" +
-                 std::to_string( samPosition( a ) ) + "\t" + mapq( a, false ) + "\t" + cigar( a, q.length( ) ) +
-                 "\t*\t0\t0\t" + segment( a, q ) + "\t" + qual( q, a.uiBeginOnQuery, a.uiEndOnQuery ) + "\n";
+            s.append( q.sName ), s += '\t', num( s, samFlag( a ) ), s += '\t', s.append( contig( a ) ), s += '\t';
+            num( s, samPosition( a ) ), s += '\t', s.append( mapq( a, false ) ), s += '\t';
+            cigar( s, a, q.length( ) ), s.append( "\t*\t0\t0\t" );
+            segment( s, a, q ), s += '\t', qual( s, q, a.uiBeginOnQuery, a.uiEndOnQuery ), s += '\n';
         }
         if( v.empty( ) )
-            s += q.sName + "\t4\t*\t0\t255\t*\t*\t0\t0\t" + text( q, 0, q.length( ), false ) + "\t" +
-                 qual( q, 0, q.length( ) ) + "\n";
-        if( s.empty( ) )
-            s += q.sName + "\t4\t*\t0\t0\t*\t*\t0\t0\t" + text( q, 0, q.length( ), false ) + "\t" +
-                 qual( q, 0, q.length( ) ) + "\n";
-        return s;
+        {
+            s.append( q.sName ), s.append( "\t4\t*\t0\t255\t*\t*\t0\t0\t" ), text( s, q, 0, q.length( ), false );
+            s += '\t', qual( s, q, 0, q.length( ) ), s += '\n';
+        }
+        if( s.size( ) == uiBefore )
+        {
+            s.append( q.sName ), s.append( "\t4\t*\t0\t0\t*\t*\t0\t0\t" ), text( s, q, 0, q.length( ), false );
+            s += '\t', qual( s, q, 0, q.length( ) ), s += '\n';
+        }
     }
     // PairedFileWriter::execute: the records of one pair (PairedReads' result vector; bFirst tells the mate)
     std::string paired( const NucSeq& q1, const NucSeq& q2, const std::vector<Alignment>& v ) const
     {
         std::string s;
+        paired( s, q1, q2, v );
+        return s;
+    }
+    void paired( std::string& s, const NucSeq& q1, const NucSeq& q2, const std::vector<Alignment>& v ) const
+    {
         bool bHas1 = false, bHas2 = false;
         // PairedReads links the two chosen alignments (xStats.pOther); a passed-through vector has no links
         const bool bLinked = v.size( ) == 2 && v[ 0 ].bFirst != v[ 1 ].bFirst;
@@ -186,39 +256,48 @@ class SamWriter
             ( a.bFirst ? bHas1 : bHas2 ) = true;
             const NucSeq& q = a.bFirst ? q1 : q2;
             uint32_t flag = samFlag( a ) | 0x1u | 0x2u | ( a.bFirst ? 0x40u : 0x80u );
-            std::string sContigOther = "*", sPosOther = "0";
-            const std::string sRef = contig( a );
+            const size_t uiRef = contigOf( a.uiBeginOnRef );
+            size_t uiRefOther = uiRef;
+            nucSeqIndex uiPosOther = 0;
             if( bLinked )
             {
                 const Alignment& o = v[ 1 - k ];
                 if( onReverse( o.uiBeginOnRef ) )
                     flag |= 0x20u;
-                sContigOther = contig( o );
-                if( sContigOther == sRef )
-                    sContigOther = "=";
-                sPosOther = std::to_string( samPosition( o ) );
+                uiRefOther = contigOf( o.uiBeginOnRef );
+                uiPosOther = samPosition( o );
             }
             // (the CIGAR's clip lengths use the FIRST mate's length for both mates, fileWriter.cpp:196-198)
-            s += q.sName + "\t" + std::to_string( flag ) + "\t" + sRef + "\t" + std::to_string( samPosition( a ) ) + "\t" +
-                 mapq( a, true ) + "\t" + cigar( a, q1.length( ) ) + "\t" + sContigOther + "\t" + sPosOther + "\t0\t" +
-                 segment( a, q ) + "\t" + qual( q, a.uiBeginOnQuery, a.uiEndOnQuery ) + "\n";
+            s.append( q.sName ), s += '\t', num( s, flag ), s += '\t', s.append( rIdx.vNames[ uiRef ] ), s += '\t';
+            num( s, samPosition( a ) ), s += '\t', s.append( mapq( a, true ) ), s += '\t';
+            cigar( s, a, q1.length( ) ), s += '\t';
+            if( !bLinked )
+                s.append( "*\t0" );
+            else
+            { // the other contig by NAME: "=" if the names are equal
+                if( rIdx.vNames[ uiRefOther ] == rIdx.vNames[ uiRef ] )
+                    s += '=';
+                else
+                    s.append( rIdx.vNames[ uiRefOther ] );
+                s += '\t', num( s, uiPosOther );
+            }
+            s.append( "\t0\t" ), segment( s, a, q ), s += '\t', qual( s, q, a.uiBeginOnQuery, a.uiEndOnQuery ), s += '\n';
         }
         if( !bHas1 && !bHas2 )
         {
-            s += q1.sName + "\t" + std::to_string( 0x4 | 0x1 | 0x40 | 0x8 ) + "\t*\t0\t0\t*\t*\t0\t0\t" +
-                 text( q1, 0, q1.length( ), false ) + "\t" + qual( q1, 0, q1.length( ) ) + "\n";
-            s += q2.sName + "\t" + std::to_string( 0x4 | 0x1 | 0x80 | 0x8 ) + "\t*\t0\t0\t*\t*\t0\t0\t" +
-                 text( q2, 0, q2.length( ), false ) + "\t" + qual( q2, 0, q2.length( ) ) + "\n";
+            s.append( q1.sName ), s += '\t', num( s, 0x4 | 0x1 | 0x40 | 0x8 ), s.append( "\t*\t0\t0\t*\t*\t0\t0\t" );
+            text( s, q1, 0, q1.length( ), false ), s += '\t', qual( s, q1, 0, q1.length( ) ), s += '\n';
+            s.append( q2.sName ), s += '\t', num( s, 0x4 | 0x1 | 0x80 | 0x8 ), s.append( "\t*\t0\t0\t*\t*\t0\t0\t" );
+            text( s, q2, 0, q2.length( ), false ), s += '\t', qual( s, q2, 0, q2.length( ) ), s += '\n';
         }
         else if( !bHas1 || !bHas2 )
         {
             const Alignment& a0 = v[ 0 ];
-            const std::string sPos = std::to_string( samPosition( a0 ) );
             const NucSeq& q = !bHas1 ? q1 : q2;
-            s += q.sName + "\t" + std::to_string( 0x4 | 0x1 | ( !bHas1 ? 0x40 : 0x80 ) ) + "\t" + contig( a0 ) + "\t" + sPos +
-                 "\t0\t*\t=\t" + sPos + "\t0\t" + text( q, 0, q.length( ), false ) + "\t*\n";
+            s.append( q.sName ), s += '\t', num( s, 0x4 | 0x1 | ( !bHas1 ? 0x40 : 0x80 ) ), s += '\t';
+            s.append( contig( a0 ) ), s += '\t', num( s, samPosition( a0 ) ), s.append( "\t0\t*\t=\t" );
+            num( s, samPosition( a0 ) ), s.append( "\t0\t" ), text( s, q, 0, q.length( ), false ), s.append( "\t*\n" );
         }
-        return s;
     }
 };
 

@@ -9,7 +9,7 @@
 //   -m, --MateIn       mate file(s); switches "Use Paired Reads" on like the reference (cmdMa.cpp:323-330)
 //   -o, --Out          SAM file (default: standard output)
 //   -p, --Presetting   Default | Illumina | Illumina_Paired | PacBio | Nanopore (default: Default)
-//   -t                 host threads that format SAM records (default: all; the alignment itself runs on the GPU)
+//   -t                 host threads that format SAM records (default: all but three; the alignment itself runs on the GPU)
 //   --Verbose          prints the busy time of the host stages
 //   --Interleaved      with a paired presetting and no -m: reads 2k, 2k+1 of -i are mates (not in the reference)
 //   --Devices <a,b,..> CUDA devices (default 0). The index is replicated on every device, batches go to whichever device
@@ -131,7 +131,7 @@ int main( int argc, char** argv )
     size_t uiBatch = 500000;
     uint32_t uiSrand = 0;
     bool bInterleaved = false, bVerbose = false;
-    size_t uiThreads = std::max( 1u, std::thread::hardware_concurrency( ) );
+    size_t uiThreads = (size_t)std::max( 1, (int)std::thread::hardware_concurrency( ) - 3 ); // reader, device, writer
     try
     {
         for( int i = 1; i < argc; i++ )
@@ -299,10 +299,10 @@ int main( int argc, char** argv )
                                 std::string& sText = vText[ c ];
                                 for( size_t u = uiUnits * c / uiChunks; u < uiUnits * ( c + 1 ) / uiChunks; u++ )
                                     if( bPaired )
-                                        sText += xWriter.paired( pB->vReads[ 2 * u ], pB->vReads[ 2 * u + 1 ],
-                                                                 pB->xRaw.records( u ) );
+                                        xWriter.paired( sText, pB->vReads[ 2 * u ], pB->vReads[ 2 * u + 1 ],
+                                                        pB->xRaw.records( u ) );
                                     else
-                                        sText += xWriter.single( pB->vReads[ u ], pB->xRaw.records( u ) );
+                                        xWriter.single( sText, pB->vReads[ u ], pB->xRaw.records( u ) );
                             }
                             catch( ... )
                             {
@@ -333,7 +333,7 @@ int main( int argc, char** argv )
         } );
 
         std::vector<std::exception_ptr> vGpuError( vAligners.size( ) );
-        std::vector<double> vGpuBusy( vAligners.size( ), 0.0 );
+        std::vector<double> vGpuBusy( vAligners.size( ), 0.0 ), vKernelMs( vAligners.size( ), 0.0 );
         std::vector<std::thread> vGpuThreads;
         for( size_t g = 0; g < vAligners.size( ); g++ ) // one host thread per device (a context is not re-entrant)
             vGpuThreads.emplace_back( [ &, g ]( ) {
@@ -344,8 +344,9 @@ int main( int argc, char** argv )
                     {
                         const auto t0 = now( );
                         vAligners[ g ]->params( ).xParams.srand_base = uiSrand + (uint32_t)pB->uiFirst;
-                        vAligners[ g ]->reportRaw( pB->vReads, pB->xRaw );
-                        vGpuBusy[ g ] += secs( t0, now( ) );
+                        ma_b200_align_stats xStats;
+                        vAligners[ g ]->reportRaw( pB->vReads, pB->xRaw, &xStats );
+                        vGpuBusy[ g ] += secs( t0, now( ) ), vKernelMs[ g ] += xStats.ms_total;
                         if( !xAligned.push( std::move( pB ) ) )
                             break;
                     }
@@ -359,8 +360,9 @@ int main( int argc, char** argv )
         for( auto& t : vGpuThreads )
             t.join( );
         xParsed.close( ), xFree.close( ); // releases a reader that still waits after the devices stopped early
-        for( double f : vGpuBusy )
-            fGpu = std::max( fGpu, f );
+        double fKernels = 0;
+        for( size_t g = 0; g < vGpuBusy.size( ); g++ )
+            fGpu = std::max( fGpu, vGpuBusy[ g ] ), fKernels = std::max( fKernels, vKernelMs[ g ] * 1e-3 );
         xAligned.close( );
         xReader.join( );
         xWriterThread.join( );
@@ -369,8 +371,8 @@ int main( int argc, char** argv )
             if( e )
                 std::rethrow_exception( e );
         if( bVerbose )
-            fprintf( stderr, "\rbusy seconds: reader %.3f, gpu stage (upload, kernels, download; max over %zu devices) %.3f, "
-                             "format %.3f (%zu threads), write %.3f\n", fParse, vAligners.size( ), fGpu, fFormat, uiThreads, fWrite );
+            fprintf( stderr, "\rbusy seconds: reader %.3f, gpu stage (upload, kernels, download; max over %zu devices) %.3f of which "
+                             "kernels %.3f, format %.3f (%zu threads), write %.3f\n", fParse, vAligners.size( ), fGpu, fKernels, fFormat, uiThreads, fWrite );
         if( pOut != stdout )
             fclose( pOut );
         std::cerr << "\rdone.                         " << std::endl;

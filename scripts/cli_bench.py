@@ -40,8 +40,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=2_000_000)
     ap.add_argument("--genome-mbp", type=int, default=100)
     ap.add_argument("--devices", default="0")
-    ap.add_argument("--batch", type=int, default=1_000_000)
-    ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
+    ap.add_argument("--batch", type=int, default=500_000)
+    ap.add_argument("--threads", type=int, default=max(1, (os.cpu_count() or 4) - 3))
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     subprocess.check_call(["make", "-s", "-C", os.path.dirname(CLI)])
