@@ -35,6 +35,9 @@ class ParameterSetManager
 {
   public:
     ma_b200_params xParams;
+    // "Detect Small Inversions" / "Z Drop Inversions" (parameter.h:640-647): read by the host-side SmallInversions only
+    bool bSearchInversions = false;
+    int iZDropInversion = 100;
     ParameterSetManager( )
     {
         ma_b200_params_preset( "default", &xParams );
@@ -168,6 +171,37 @@ struct Alignment // alignment.h:55-95
     {
         return iScore;
     }
+    // Alignment::append (alignment.cpp:11-98): run-length data, ends and the score with the capped affine gap cost
+    void append( MatchType type, nucSeqIndex size, const ma_b200_params& P )
+    {
+        if( size == 0 )
+            return;
+        if( type == MatchType::seed || type == MatchType::match )
+            iScore += (int64_t)P.match * (int64_t)size, uiEndOnRef += size, uiEndOnQuery += size;
+        else if( type == MatchType::missmatch )
+            iScore -= (int64_t)P.mismatch * (int64_t)size, uiEndOnRef += size, uiEndOnQuery += size;
+        else
+        {
+            ( type == MatchType::insertion ? uiEndOnQuery : uiEndOnRef ) += size;
+            auto cost = [ & ]( nucSeqIndex n ) {
+                const nucSeqIndex c = (nucSeqIndex)P.extend * n + (nucSeqIndex)P.gap;
+                return (int64_t)( c < (nucSeqIndex)P.sv_penalty ? c : (nucSeqIndex)P.sv_penalty );
+            };
+            if( !data.empty( ) && data.back( ).first == type )
+            {
+                size += data.back( ).second;
+                uiLength -= data.back( ).second;
+                iScore += cost( data.back( ).second );
+                data.pop_back( );
+            }
+            iScore -= cost( size );
+        }
+        if( !data.empty( ) && data.back( ).first == type )
+            data.back( ).second += size;
+        else
+            data.emplace_back( type, size );
+        uiLength += size;
+    }
 };
 
 // Pack's sequence descriptors (pack.h:39-176): name, start on the forward strand, length; read from <prefix>.ann
@@ -231,10 +265,13 @@ class FMIndex
     void vLoad( const std::string& sPrefix )
     {
         auto slurp = []( const std::string& f ) {
-            std::ifstream in( f, std::ios::binary );
+            std::ifstream in( f, std::ios::binary | std::ios::ate );
             if( !in )
                 throw std::runtime_error( "File opening error: " + f );
-            return std::vector<char>( ( std::istreambuf_iterator<char>( in ) ), std::istreambuf_iterator<char>( ) );
+            std::vector<char> v( (size_t)in.tellg( ) );
+            in.seekg( 0 );
+            in.read( v.data( ), (std::streamsize)v.size( ) );
+            return v;
         };
         auto b = slurp( sPrefix + ".bwt" );
         int64_t primary, L2[ 5 ] = { 0, 0, 0, 0, 0 };
@@ -255,7 +292,32 @@ class FMIndex
         check( ma_b200_index_upload( pCtx, (const uint32_t*)( b.data( ) + 40 ), nWords, L2, primary, refLen, sa.data( ),
                                      nSa, saIntv, (const uint8_t*)p.data( ), ( fwdLen + 3 ) / 4, fwdLen, cs.data( ),
                                      cl.data( ), (int32_t)nSeq ) );
+        vPac.assign( p.begin( ), p.begin( ) + ( fwdLen + 3 ) / 4 );
     }
+    // Pack::vExtract( begin, end ) (pack.h:1147-1236, 1440-1448; holes are not restored): [begin, end) of the forward
+    // strand followed by its reverse complement; throws like the reference for ranges that bridge the strands
+    std::vector<uint8_t> vExtract( int64_t iBegin, int64_t iEnd ) const
+    {
+        const int64_t iFwd = xContigs.iForwardLength, iTotal = 2 * iFwd;
+        if( iBegin < 0 || iBegin >= iTotal || iEnd < 0 || iEnd > iTotal )
+            throw std::runtime_error( "Pack (vExtractSubsection): out of range" );
+        if( ( iBegin >= iFwd ) != ( iEnd - 1 >= iFwd ) )
+            throw std::runtime_error( "(vExtractSubsection) Try to extract bridging sequence. This is impossible." );
+        if( !( iBegin <= iEnd ) )
+            throw std::runtime_error( "(vExtractSubsection) Try to extract with begin greater than end." );
+        auto nuc = [ & ]( int64_t p ) { return (uint8_t)( ( vPac[ (size_t)( p >> 2 ) ] >> ( ( ~p & 3 ) << 1 ) ) & 3 ); };
+        std::vector<uint8_t> v( (size_t)( iEnd - iBegin ) );
+        if( iBegin < iFwd )
+            for( int64_t p = iBegin; p < iEnd; p++ )
+                v[ (size_t)( p - iBegin ) ] = nuc( p );
+        else
+            for( int64_t p = iBegin; p < iEnd; p++ )
+                v[ (size_t)( p - iBegin ) ] = (uint8_t)( 3 - nuc( iTotal - 1 - p ) );
+        return v;
+    }
+
+  private:
+    std::vector<uint8_t> vPac; // host copy of the 2-bit forward strand (0.25 byte per base) for vExtract
 };
 
 namespace detail
@@ -525,6 +587,155 @@ class PairedReads
     }
 };
 
+// SmallInversions::execute (smallInversions.h:22-221) for every read of a batch: vAlignments[ i ] is MappingQuality's
+// vector of read i (the module sits between MappingQuality and the writer, export.cpp:109-112). Host glue as in the
+// reference; the DP calls of the whole batch (kswcpp_dispatch, smallInversions.h:125-127) run as ONE ma_b200_ksw_batch.
+class SmallInversions
+{
+    const ParameterSetManager& rParams;
+
+    struct Candidate
+    {
+        size_t uiRead, uiAlignment;
+        nucSeqIndex uiStartQ, uiEndQ, uiStartRRev;
+        std::vector<uint8_t> vRef;
+    };
+
+    // forAllDropPos (smallInversions.h:54-115): regions between two seeds in which the running score drops faster
+    // than "Z Drop Inversions"
+    template <typename F> void forAllDropPos( const Alignment& a, F fDo ) const
+    {
+        const ma_b200_params& P = rParams.xParams;
+        nucSeqIndex uiMaxScorePosQ = a.uiBeginOnQuery, uiPosQ = a.uiBeginOnQuery, uiStartQ = a.uiBeginOnQuery;
+        nucSeqIndex uiMaxScorePosR = a.uiBeginOnRef, uiPosR = a.uiBeginOnRef, uiStartR = a.uiBeginOnRef;
+        int iMaxScore = std::numeric_limits<int>::min( ), iCurrScore = 0, iMaxDrop = 0;
+        for( const auto& section : a.data )
+        {
+            switch( section.first )
+            {
+                case MatchType::seed:
+                    if( iMaxDrop >= rParams.iZDropInversion )
+                        fDo( uiStartQ, uiStartR, uiPosQ, uiPosR );
+                    uiStartQ = section.second + uiPosQ, uiStartR = section.second + uiPosR;
+                    iMaxDrop = 0, iCurrScore = 0, iMaxScore = std::numeric_limits<int>::min( );
+                    [[fallthrough]];
+                case MatchType::match:
+                    iCurrScore += P.match * (int)section.second;
+                    uiPosQ += section.second, uiPosR += section.second;
+                    break;
+                case MatchType::missmatch:
+                    iCurrScore -= P.mismatch * (int)section.second;
+                    uiPosQ += section.second, uiPosR += section.second;
+                    break;
+                case MatchType::insertion:
+                    iCurrScore -= P.gap + P.extend * (int)section.second;
+                    uiPosQ += section.second;
+                    break;
+                case MatchType::deletion:
+                    iCurrScore -= P.gap + P.extend * (int)section.second;
+                    uiPosR += section.second;
+                    break;
+            }
+            if( iCurrScore >= iMaxScore )
+                iMaxScore = iCurrScore, uiMaxScorePosQ = uiPosQ, uiMaxScorePosR = uiPosR;
+            else
+            {
+                const int iDiff = (int)std::max( uiPosQ - uiMaxScorePosQ, uiPosR - uiMaxScorePosR );
+                iMaxDrop = std::max( iMaxDrop, iMaxScore - iCurrScore - iDiff * P.extend );
+            }
+        }
+    }
+
+  public:
+    explicit SmallInversions( const ParameterSetManager& rParameters ) : rParams( rParameters )
+    {}
+    std::vector<std::vector<Alignment>> execute( FMIndex& rIdx, const std::vector<std::vector<Alignment>>& vAlignments,
+                                                 const std::vector<NucSeq>& vQueries )
+    {
+        const ma_b200_params& P = rParams.xParams;
+        const nucSeqIndex uiTotal = 2 * (nucSeqIndex)rIdx.xContigs.iForwardLength;
+        std::vector<Candidate> vCand;
+        for( size_t i = 0; i < vAlignments.size( ); i++ )
+            for( size_t k = 0; k < vAlignments[ i ].size( ); k++ )
+                forAllDropPos( vAlignments[ i ][ k ],
+                               [ & ]( nucSeqIndex uiStartQ, nucSeqIndex uiStartR, nucSeqIndex uiEndQ, nucSeqIndex uiEndR ) {
+                                   // the window on the other strand (Pack::uiPositionToReverseStrand, pack.h:924-927)
+                                   const nucSeqIndex uiStartRRev = uiTotal - ( uiEndR + 1 ),
+                                                     uiEndRRev = uiTotal - ( uiStartR + 1 );
+                                   vCand.push_back( Candidate{ i, k, uiStartQ, uiEndQ, uiStartRRev,
+                                                               rIdx.vExtract( (int64_t)uiStartRRev, (int64_t)uiEndRRev ) } );
+                               } );
+        // tryInversionExtension (smallInversions.h:117-171): global-mode kswcpp call with the extension bandwidth
+        std::vector<ma_b200_ksw_task> vTasks( vCand.size( ) );
+        std::vector<uint8_t> vSeq;
+        size_t uiCigarCap = 16;
+        for( size_t c = 0; c < vCand.size( ); c++ )
+        {
+            const Candidate& x = vCand[ c ];
+            const NucSeq& q = vQueries[ x.uiRead ];
+            ma_b200_ksw_task& t = vTasks[ c ];
+            t.qoff = (int64_t)vSeq.size( ), t.qlen = (int32_t)( (int)x.uiEndQ - (int)x.uiStartQ );
+            vSeq.insert( vSeq.end( ), q.vSeq.begin( ) + x.uiStartQ, q.vSeq.begin( ) + x.uiEndQ );
+            t.toff = (int64_t)vSeq.size( ), t.tlen = (int32_t)x.vRef.size( );
+            vSeq.insert( vSeq.end( ), x.vRef.begin( ), x.vRef.end( ) );
+            t.w = P.bandwidth_ext, t.zdrop = P.zdrop, t.flag = 0, t.tag = 0;
+            uiCigarCap += (size_t)t.qlen + (size_t)t.tlen + 8;
+        }
+        std::vector<ma_b200_ksw_result> vRes( vCand.size( ) + 1 );
+        std::vector<uint32_t> vCigar( uiCigarCap );
+        int64_t iWords = 0;
+        if( !vCand.empty( ) )
+        {
+            vSeq.push_back( 0 );
+            rIdx.check( ma_b200_set_params( rIdx.ctx( ), &P ) );
+            rIdx.check( ma_b200_ksw_batch( rIdx.ctx( ), (int64_t)vTasks.size( ), vTasks.data( ), vSeq.data( ),
+                                           (int64_t)vSeq.size( ), vRes.data( ), vCigar.data( ), (int64_t)vCigar.size( ),
+                                           &iWords ) );
+        }
+        std::vector<std::vector<Alignment>> vRet( vAlignments.size( ) );
+        size_t c = 0;
+        for( size_t i = 0; i < vAlignments.size( ); i++ )
+            for( size_t k = 0; k < vAlignments[ i ].size( ); k++ )
+            {
+                vRet[ i ].push_back( vAlignments[ i ][ k ] );
+                for( ; c < vCand.size( ) && vCand[ c ].uiRead == i && vCand[ c ].uiAlignment == k; c++ )
+                {
+                    const Candidate& x = vCand[ c ];
+                    const NucSeq& q = vQueries[ i ];
+                    Alignment xInv;
+                    nucSeqIndex qPos = x.uiStartQ, rPos = 0;
+                    for( int j = 0; j < vRes[ c ].n_cigar; j++ )
+                    {
+                        const uint32_t uiWord = vCigar[ (size_t)vRes[ c ].cigar_off + j ];
+                        const uint32_t uiSymbol = uiWord & 0xf, uiAmount = uiWord >> 4;
+                        if( uiSymbol == 0 )
+                        {
+                            for( uint32_t u = 0; u < uiAmount; u++ )
+                                xInv.append( q.vSeq[ u + qPos ] == x.vRef[ u + rPos ] ? MatchType::match
+                                                                                      : MatchType::missmatch, 1, P );
+                            qPos += uiAmount, rPos += uiAmount;
+                        }
+                        else if( uiSymbol == 1 )
+                            xInv.append( MatchType::insertion, uiAmount, P ), qPos += uiAmount;
+                        else
+                            xInv.append( MatchType::deletion, uiAmount, P ), rPos += uiAmount;
+                    }
+                    if( P.disable_heuristics || xInv.score( ) > (int64_t)P.harm_score_min * P.match )
+                    {
+                        xInv.uiBeginOnQuery += x.uiStartQ, xInv.uiEndOnQuery += x.uiStartQ;
+                        xInv.uiBeginOnRef += x.uiStartRRev, xInv.uiEndOnRef += x.uiStartRRev;
+                        xInv.bSupplementary = true;
+                        xInv.index_of_strip = vAlignments[ i ][ k ].index_of_strip; // xStats of the parent
+                        xInv.bFirst = vAlignments[ i ][ k ].bFirst;
+                        xInv.fMappingQuality = 0;
+                        vRet[ i ].push_back( xInv );
+                    }
+                }
+            }
+        return vRet;
+    }
+};
+
 // The batched graph: what setUpCompGraph / setUpCompGraphPaired (export.cpp:72-202) wire per thread, executed for a
 // whole batch on one GPU.
 class Aligner
@@ -546,6 +757,12 @@ class Aligner
     {
         return xIndex;
     }
+    // SmallInversions over the records of a batch (unpaired graphs; one DP batch on this aligner's device)
+    std::vector<std::vector<Alignment>> inversions( const std::vector<std::vector<Alignment>>& vRecords,
+                                                    const std::vector<NucSeq>& vReads )
+    {
+        return SmallInversions( xParams ).execute( xIndex, vRecords, vReads );
+    }
     // NeedlemanWunsch results per read
     std::vector<std::vector<Alignment>> align( const std::vector<NucSeq>& vReads, ma_b200_align_stats* pStats = nullptr )
     {
@@ -559,6 +776,12 @@ class Aligner
         std::vector<std::vector<Alignment>> vRet( xRaw.units( ) );
         for( size_t i = 0; i < vRet.size( ); i++ )
             vRet[ i ] = xRaw.records( i );
+        if( xParams.bSearchInversions )
+        { // "Detect Small Inversions": SmallInversions between MappingQuality and the writer (export.cpp:109-112)
+            if( xRaw.bPaired )
+                throw std::runtime_error( "Detect Small Inversions is not supported together with Use Paired Reads" );
+            return SmallInversions( xParams ).execute( xIndex, vRet, vReads );
+        }
         return vRet;
     }
     // the same result as the C ABI delivers it (record arrays of the whole batch); RawReport::records( i ) converts

@@ -11,6 +11,8 @@
 //   -p, --Presetting   Default | Illumina | Illumina_Paired | PacBio | Nanopore (default: Default)
 //   -t                 host threads that format SAM records (default: all but three; the alignment itself runs on the GPU)
 //   --Verbose          prints the busy time of the host stages
+//   --Detect_Small_Inversions [true|false], --Z_Drop_Inversions <n>   the reference's parameters of that name:
+//                      SmallInversions between MappingQuality and the writer (unpaired input only)
 //   --Interleaved      with a paired presetting and no -m: reads 2k, 2k+1 of -i are mates (not in the reference)
 //   --Devices <a,b,..> CUDA devices (default 0). The index is replicated on every device, batches go to whichever device
 //                      is free, no collective is involved; the output order does not depend on it
@@ -130,7 +132,8 @@ int main( int argc, char** argv )
     std::vector<int> vDevices( 1, 0 );
     size_t uiBatch = 500000;
     uint32_t uiSrand = 0;
-    bool bInterleaved = false, bVerbose = false;
+    bool bInterleaved = false, bVerbose = false, bInversions = false;
+    int iZDropInversion = 100;
     size_t uiThreads = (size_t)std::max( 1, (int)std::thread::hardware_concurrency( ) - 3 ); // reader, device, writer
     try
     {
@@ -158,6 +161,14 @@ int main( int argc, char** argv )
                 bVerbose = true;
             else if( sLow == "--interleaved" )
                 bInterleaved = true;
+            else if( sLow == "--detect_small_inversions" )
+            { // a flag of the reference ("Detect Small Inversions"); an explicit true / false may follow
+                bInversions = true;
+                if( i + 1 < argc && ( lower( argv[ i + 1 ] ) == "true" || lower( argv[ i + 1 ] ) == "false" ) )
+                    bInversions = lower( argv[ ++i ] ) == "true";
+            }
+            else if( sLow == "--z_drop_inversions" )
+                iZDropInversion = atoi( value( ).c_str( ) );
             else if( sLow == "--device" || sLow == "--devices" )
             {
                 vDevices.clear( );
@@ -184,9 +195,13 @@ int main( int argc, char** argv )
             vAligners.emplace_back( new Aligner( sIndex, sPreset, iDevice ) );
             if( !vMate.empty( ) )
                 vAligners.back( )->params( ).xParams.use_paired_reads = 1;
+            vAligners.back( )->params( ).bSearchInversions = bInversions;
+            vAligners.back( )->params( ).iZDropInversion = iZDropInversion;
         }
         Aligner& xAligner = *vAligners[ 0 ];
         const bool bPaired = xAligner.params( ).xParams.use_paired_reads != 0;
+        if( bPaired && bInversions )
+            throw std::runtime_error( "--Detect_Small_Inversions is not supported together with paired reads" );
         if( bPaired && vMate.empty( ) && !bInterleaved )
             throw std::runtime_error( "paired presetting: give the mates with -m (or --Interleaved)" );
         if( uiBatch < 2 )
@@ -207,6 +222,7 @@ int main( int argc, char** argv )
             std::vector<NucSeq> vReads;
             size_t uiFirst = 0, uiSeq = 0;
             RawReport xRaw;
+            std::vector<std::vector<Alignment>> vRecords; // with --Detect_Small_Inversions: SmallInversions' vectors
         };
         const size_t uiPool = 3 + 2 * vAligners.size( );
         BoundedQueue<std::unique_ptr<Batch>> xParsed( 2 ), xAligned( 2 + vAligners.size( ) ), xFree( uiPool );
@@ -302,7 +318,8 @@ int main( int argc, char** argv )
                                         xWriter.paired( sText, pB->vReads[ 2 * u ], pB->vReads[ 2 * u + 1 ],
                                                         pB->xRaw.records( u ) );
                                     else
-                                        xWriter.single( sText, pB->vReads[ u ], pB->xRaw.records( u ) );
+                                        xWriter.single( sText, pB->vReads[ u ],
+                                                        pB->vRecords.empty( ) ? pB->xRaw.records( u ) : pB->vRecords[ u ] );
                             }
                             catch( ... )
                             {
@@ -346,6 +363,14 @@ int main( int argc, char** argv )
                         vAligners[ g ]->params( ).xParams.srand_base = uiSrand + (uint32_t)pB->uiFirst;
                         ma_b200_align_stats xStats;
                         vAligners[ g ]->reportRaw( pB->vReads, pB->xRaw, &xStats );
+                        pB->vRecords.clear( );
+                        if( bInversions )
+                        { // the DP of SmallInversions runs on this device as one more batch
+                            std::vector<std::vector<Alignment>> vRec( pB->xRaw.units( ) );
+                            for( size_t u = 0; u < vRec.size( ); u++ )
+                                vRec[ u ] = pB->xRaw.records( u );
+                            pB->vRecords = vAligners[ g ]->inversions( vRec, pB->vReads );
+                        }
                         vGpuBusy[ g ] += secs( t0, now( ) ), vKernelMs[ g ] += xStats.ms_total;
                         if( !xAligned.push( std::move( pB ) ) )
                             break;

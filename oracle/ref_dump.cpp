@@ -31,6 +31,7 @@
 #include "ma/module/mappingQuality.h"
 #include "ma/module/needlemanWunsch.h"
 #include "ma/module/pairedReads.h"
+#include "ma/module/smallInversions.h"
 #include "ma/module/stripOfConsideration.h"
 #include <atomic>
 #include <chrono>
@@ -345,7 +346,7 @@ static int cmdAlign( int argc, char** argv )
     return 0;
 }
 
-// ref_dump sam <index prefix> <reads.txt> <preset> <out.sam> [srand_base]
+// ref_dump sam <index prefix> <reads.txt> <preset> <out.sam> [srand_base [inv]]
 // The reference's own FileWriter / PairedFileWriter (fileWriter.cpp:11-156, 158-372) behind the path, reads named r<i>;
 // for presets with "Use Paired Reads" the reads 2k, 2k+1 are mates.
 // reads of a FASTA / FASTQ file through the reference's own FileReader (fileReader.cpp:37-203); plain sequence lines
@@ -388,9 +389,15 @@ static int cmdSam( int argc, char** argv )
     selectPreset( xP, argv[ 4 ] );
     auto vReads = readQueries( xP, argv[ 3 ] );
     int64_t iSrandBase = argc > 6 ? atoll( argv[ 6 ] ) : -1;
+    // "inv": "Detect Small Inversions" on, SmallInversions between MappingQuality and the writer (export.cpp:109-112)
+    // "inv" or "inv=<Z Drop Inversions>"
+    const bool bInversions = argc > 7 && std::string( argv[ 7 ] ).substr( 0, 3 ) == "inv";
+    if( bInversions && std::string( argv[ 7 ] ).size( ) > 4 )
+        xP.getSelected( )->xZDropInversion->set( atoi( argv[ 7 ] + 4 ) );
     auto pPack = std::make_shared<Pack>( sPrefix );
     auto pFM = std::make_shared<FMIndex>( sPrefix );
     Modules xM( xP );
+    SmallInversions xInv( xP );
     const bool bPaired = xP.getSelected( )->xUsePairedReads->get( );
     std::shared_ptr<FileWriter> pW;
     std::shared_ptr<PairedFileWriter> pPW;
@@ -411,6 +418,8 @@ static int cmdSam( int argc, char** argv )
         auto pHarm = xM.xHarm.execute( pSoCs, pQ, pFM );
         auto pAln = xM.xNW.execute( pHarm, pQ, pPack );
         auto pMQ = xM.xMQ.execute( pQ, pAln );
+        if( bInversions )
+            pMQ = xInv.execute( pMQ, pQ, pPack );
         if( !bPaired )
             pW->execute( pQ, pMQ, pPack );
         else if( uiRead % 2 == 0 )

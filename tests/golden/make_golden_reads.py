@@ -12,6 +12,12 @@ reference (oracle/_ref/ref_dump):
   tests/golden/gold_fq_illuminapaired.sam FileReader -> alignment path -> PairedFileWriter (srand(1000 + read index))
   tests/golden/gold_fa_illumina.sam       FileReader -> alignment path -> FileWriter
 
+  tests/golden/gold_reads_inv.fa          reads with short inverted segments that hold no seed (a substitution every
+                                          12 bases inside the inverted part), both strands, 250 and 1000 bases
+  tests/golden/gold_inv_default_z20.sam   ... -> MappingQuality -> SmallInversions -> FileWriter, Default presetting
+                                          with "Z Drop Inversions" 20 (14 inversion records)
+  tests/golden/gold_inv_illumina.sam      the same with the Illumina presetting and the default threshold of 100
+
 Run in the build container after make_golden_pipeline.py (needs /root/reference -> `make -C oracle ref`).
 """
 import os
@@ -20,6 +26,7 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 import helpers as H  # noqa: E402
 
 SRAND = 1000
@@ -73,5 +80,44 @@ def main():
               os.path.join(H.GOLDEN, "gold_fa_illumina.sam"), SRAND)
 
 
+def inversions():
+    from ma_b200 import index as maindex
+    ix = maindex.load_index(os.path.join(H.GOLDEN, "gold"))
+    g = np.asarray(ix.forward_codes() if callable(ix.forward_codes) else ix.forward_codes, dtype=np.uint8)
+    rng = np.random.Generator(np.random.PCG64(22))
+
+    def rc(x):
+        return (3 - x[::-1]).astype(np.uint8)
+
+    def make(L, inv_len, contig, revstrand, sub=0.0, n_inv=1):
+        s0, cl = int(ix.contig_start[contig]), int(ix.contig_len[contig])
+        p = int(rng.integers(s0 + 10, s0 + cl - L - 10))
+        r = g[p:p + L].copy()
+        for k in range(n_inv):
+            a = (k + 1) * L // (n_inv + 1) - inv_len // 2
+            seg = rc(r[a:a + inv_len])
+            for j in range(int(rng.integers(6, 10)), inv_len, 12):  # break every seed inside the inverted part
+                seg[j] = (seg[j] + 1 + int(rng.integers(0, 3))) & 3
+            r[a:a + inv_len] = seg
+        if sub > 0:
+            m = rng.random(L) < sub
+            r[m] = (r[m] + rng.integers(1, 4, m.sum())) & 3
+        return rc(r) if revstrand else r
+
+    reads = [make(250, [36, 44, 52, 60, 70, 80][k % 6], k % 3, k % 2 == 1, 0.0 if k < 6 else 0.01) for k in range(12)]
+    reads += [make(1000, [40, 50, 60, 70, 80, 90][k], k % 3, k % 2 == 0, 0.01, n_inv=1 + k % 3) for k in range(6)]
+    reads.append(g[1000:1250].copy())  # no inversion
+    reads.append(rng.integers(0, 4, 250).astype(np.uint8))  # does not align
+    fa = os.path.join(H.GOLDEN, "gold_reads_inv.fa")
+    with open(fa, "w") as f:
+        for i, r in enumerate(reads):
+            f.write(">inv%d\n%s\n" % (i, "".join("ACGT"[c] for c in r)))
+    H.run_ref("sam", os.path.join(H.GOLDEN, "gold"), fa, "default", os.path.join(H.GOLDEN, "gold_inv_default_z20.sam"),
+              SRAND, "inv=20")
+    H.run_ref("sam", os.path.join(H.GOLDEN, "gold"), fa, "illumina", os.path.join(H.GOLDEN, "gold_inv_illumina.sam"),
+              SRAND, "inv")
+
+
 if __name__ == "__main__":
     main()
+    inversions()

@@ -68,3 +68,17 @@ def test_cli_fasta_single_end_sam_matches_reference(tmp_path):
     out = subprocess.check_output([exe, "-x", PC.GOLD_PREFIX, "-i", os.path.join(H.GOLDEN, "gold_reads.fa"), "-p",
                                    "Illumina", "--Srand", str(PC.SRAND), "--Batch", "6"])
     assert out.decode() == open(os.path.join(H.GOLDEN, "gold_fa_illumina.sam")).read()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset,extra,gold", [("Default", ["--Z_Drop_Inversions", "20"], "gold_inv_default_z20.sam"),
+                                               ("Illumina", [], "gold_inv_illumina.sam")])
+def test_cli_small_inversions_sam_matches_reference(tmp_path, preset, extra, gold):
+    """--Detect_Small_Inversions == the reference's SmallInversions between MappingQuality and the
+    writer (host glue of include/ma_b200_modules.hpp, its DP calls as one ma_b200_ksw_batch on the GPU)."""
+    exe = build_cli()
+    out = subprocess.check_output([exe, "-x", PC.GOLD_PREFIX, "-i", os.path.join(H.GOLDEN, "gold_reads_inv.fa"), "-p",
+                                   preset, "--Srand", str(PC.SRAND), "--Detect_Small_Inversions", "true"] + extra)
+    exp = open(os.path.join(H.GOLDEN, gold)).read()
+    assert sum(1 for l in exp.splitlines() if not l.startswith("@") and int(l.split("\t")[1]) & 0x800) >= 1
+    assert out.decode() == exp
