@@ -5,7 +5,7 @@
 // The reference's own pybind module does not build against Python 3.12; this one is built against
 // the system pybind11 by __graft_entry__.build() / `make -C ma_b200/pybind`. Modules take a batch (list of NucSeq)
 // where the reference takes one read — one GPU launch per read would waste the device.
-#include "../../include/ma_b200_modules.hpp"
+#include "../../include/ma_b200_sam.hpp"
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
@@ -32,6 +32,8 @@ PYBIND11_MODULE( ma_b200_py, m )
               } )
         .def_property( "srand_base", []( ParameterSetManager& p ) { return p.xParams.srand_base; },
                        []( ParameterSetManager& p, uint32_t v ) { p.xParams.srand_base = v; } )
+        .def_readwrite( "detect_small_inversions", &ParameterSetManager::bSearchInversions )
+        .def_readwrite( "z_drop_inversions", &ParameterSetManager::iZDropInversion )
         .def_property( "use_paired_reads", []( ParameterSetManager& p ) { return p.xParams.use_paired_reads != 0; },
                        []( ParameterSetManager& p, bool v ) { p.xParams.use_paired_reads = v ? 1 : 0; } );
 
@@ -120,4 +122,31 @@ PYBIND11_MODULE( ma_b200_py, m )
     py::class_<PairedReads>( m, "PairedReads" )
         .def( py::init<const ParameterSetManager&>( ), py::keep_alive<1, 2>( ) )
         .def( "execute", []( PairedReads& x, FMIndex& i, const std::vector<NucSeq>& q ) { return x.execute( i, q ); } );
+    // SmallInversions (export.cpp:58): alignments per read as MappingQuality returns them, the reads, the index
+    py::class_<SmallInversions>( m, "SmallInversions" )
+        .def( py::init<const ParameterSetManager&>( ), py::keep_alive<1, 2>( ) )
+        .def( "execute", []( SmallInversions& x, FMIndex& i, const std::vector<std::vector<Alignment>>& a,
+                             const std::vector<NucSeq>& q ) { return x.execute( i, a, q ); } );
+    // FileReader (fileReader.h): all reads of a FASTA / FASTQ file
+    m.def( "read_file", []( const std::string& sFile ) {
+        ReadParser xParser( sFile );
+        std::vector<NucSeq> v;
+        NucSeq q;
+        while( xParser.next( q ) )
+            v.push_back( q );
+        return v;
+    } );
+    // FileWriter / PairedFileWriter (fileWriter.h): the SAM text of a batch for the reads of a loaded index
+    m.def( "sam_header", []( const FMIndex& i ) { return SamWriter( i.xContigs ).header( ); } );
+    m.def( "sam_records", []( const FMIndex& i, const std::vector<NucSeq>& q, const std::vector<std::vector<Alignment>>& r,
+                              bool bPaired ) {
+        SamWriter xW( i.xContigs );
+        std::string s;
+        for( size_t u = 0; u < r.size( ); u++ )
+            if( bPaired )
+                xW.paired( s, q.at( 2 * u ), q.at( 2 * u + 1 ), r[ u ] );
+            else
+                xW.single( s, q.at( u ), r[ u ] );
+        return s;
+    }, py::arg( "fm_index" ), py::arg( "queries" ), py::arg( "records" ), py::arg( "paired" ) = false );
 }

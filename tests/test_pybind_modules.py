@@ -22,7 +22,8 @@ def test_pybind_module_names_and_loud_failure_without_gpu():
     import torch
     m = load()
     for name in ("ParameterSetManager", "NucSeq", "Seed", "Seeds", "Segment", "Alignment", "FMIndex", "BinarySeeding",
-                 "Harmonization", "NeedlemanWunsch", "MappingQuality", "PairedReads"):
+                 "Harmonization", "NeedlemanWunsch", "MappingQuality", "PairedReads", "SmallInversions", "read_file",
+                 "sam_header", "sam_records"):
         assert hasattr(m, name), name
     p = m.ParameterSetManager()
     p.set_selected("illumina_paired")
@@ -31,6 +32,9 @@ def test_pybind_module_names_and_loud_failure_without_gpu():
         p.set_selected("no such preset")
     q = m.NucSeq("ACGTNacgt")
     assert len(q) == 9 and str(q) == "ACGTNACGT"
+    reads = m.read_file(os.path.join(H.GOLDEN, "gold_reads.fq"))
+    parsed = [l.split("\t") for l in open(os.path.join(H.GOLDEN, "gold_reads_fq.parsed")).read().splitlines()]
+    assert [(r.name, str(r)) for r in reads] == [(p[0], p[1]) for p in parsed]
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CUDA device"):
             m.FMIndex(0)
@@ -65,3 +69,21 @@ def test_pybind_modules_match_reference_golden():
             assert np.float64(a.mapping_quality).view(np.int64) == exp[k][2] or (
                 np.isnan(a.mapping_quality) and np.isnan(np.int64(exp[k][2]).view(np.float64)))
             k += 1
+
+
+@pytest.mark.gpu
+def test_pybind_small_inversions_and_sam_text_match_reference():
+    """read_file -> MappingQuality -> SmallInversions -> sam_records == the reference's SAM (gold_inv_default_z20.sam)."""
+    m = load()
+    p = m.ParameterSetManager()
+    p.set_selected("default")
+    p.srand_base = PC.SRAND
+    p.z_drop_inversions = 20
+    fm = m.FMIndex(0)
+    fm.load(PC.GOLD_PREFIX)
+    reads = m.read_file(os.path.join(H.GOLDEN, "gold_reads_inv.fa"))
+    mq = m.MappingQuality(p).execute(fm, reads)
+    inv = m.SmallInversions(p).execute(fm, mq, reads)
+    assert sum(len(v) for v in inv) == sum(len(v) for v in mq) + 14
+    text = m.sam_header(fm) + m.sam_records(fm, reads, inv)
+    assert text == open(os.path.join(H.GOLDEN, "gold_inv_default_z20.sam")).read()
