@@ -307,8 +307,18 @@ def main():
     }
     dom = max(("seed_kernel", "locate_kernel", "ksw_batch_kernel"), key=lambda k: kernels[k]["ms"])
     ach = kernels[dom]["algorithmic_bytes"] / kernels[dom]["ms"] / 1e6
+    traffic = None  # DRAM bytes per step of the dominant kernel from the committed ncu capture of this configuration
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if cap["workload"] == {"genome_mbp": args.genome_mbp, "pairs": args.pairs} and dom in cap:
+            traffic = cap[dom]["dram_read_bytes"] + cap[dom]["dram_write_bytes"]
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
+                "traffic_source": "profiles/ncu_traffic.json (ncu --set full, same workload; bytes per step = all "
+                                  "launches of the kernel)" if traffic else None,
+                "algorithmic_bytes_per_step": kernels[dom]["algorithmic_bytes"], "peak_source": peak_src,
                 "share_of_step": kernels[dom]["ms"] / per["ms_total"],
                 "note": "algorithmic bytes: 128 B per extend_backward, 64 B per invPsi step + 8 B per SA sample, "
                         "1 B traceback per DP cell + sequences (SURVEY.md §8(d)); the DP kernel is integer-ALU "

@@ -716,6 +716,15 @@ static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
         throw std::runtime_error( "DP band wider than the largest supported window (2000 columns)" );
     ctx->task_out.reserve( (size_t)ctx->n_tasks + 1 );
     ctx->ksw_ctrl.reserve( 64 );
+    // MA_B200_DP_BINS=1: time and cells of every DP launch (window class x kind) on stderr
+    static const bool bBinStats = getenv( "MA_B200_DP_BINS" ) != nullptr;
+    static cudaEvent_t binEv[ MA_NBINS ][ 2 ];
+    if( bBinStats && !binEv[ 0 ][ 0 ] )
+        for( auto& e : binEv )
+        {
+            MA_CUDA( cudaEventCreate( &e[ 0 ] ) );
+            MA_CUDA( cudaEventCreate( &e[ 1 ] ) );
+        }
     long long cigCap = std::max<long long>( ctx->task_cigar.cap, std::max<long long>( 12 * ctx->n_tasks, 1 << 16 ) );
     for( int attempt = 0; attempt < 2; attempt++ )
     {
@@ -765,9 +774,11 @@ static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
             A.cigscratch = ctx->ksw_cigscratch.p, A.cigscratch_stride = ctx->hctrl.bin_cig[ b ];
             A.next = (int*)( ctx->ksw_ctrl.p + 16 );
             A.error = (int*)( ctx->ksw_ctrl.p + 32 );
-            A.cells_total = ctx->ksw_ctrl.p + 48;
+            A.cells_total = ctx->ksw_ctrl.p + 49 + b; // one counter per bin (slots 49..63), summed below
             A.score = score;
             MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p + 16, 0, sizeof( unsigned long long ), ctx->stream ) );
+            if( bBinStats )
+                MA_CUDA( cudaEventRecord( binEv[ b ][ 0 ], ctx->stream ) );
             switch( b / 3 )
             {
                 case 0: launch_ksw_bin<128>( ctx, A, grids[ b ] ); break;
@@ -776,11 +787,25 @@ static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
                 case 3: launch_ksw_bin<1024>( ctx, A, grids[ b ] ); break;
                 default: launch_ksw_bin<2048>( ctx, A, grids[ b ] ); break;
             }
+            if( bBinStats )
+                MA_CUDA( cudaEventRecord( binEv[ b ][ 1 ], ctx->stream ) );
         }
         unsigned long long c[ 64 ];
         MA_CUDA( cudaMemcpyAsync( c, ctx->ksw_ctrl.p, sizeof( c ), cudaMemcpyDeviceToHost, ctx->stream ) );
         MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
         ctx->n_task_cigar = (int64_t)c[ 0 ];
+        c[ 48 ] = 0;
+        for( int b = 0; b < MA_NBINS - 1; b++ )
+            c[ 48 ] += c[ 49 + b ];
+        if( bBinStats )
+            for( int b = 0; b < MA_NBINS - 1; b++ )
+                if( ctx->hctrl.bin_count[ b ] > 0 )
+                {
+                    const float ms = ev_ms( binEv[ b ][ 0 ], binEv[ b ][ 1 ] );
+                    static const char* kKind[ 3 ] = { "all fields (exact)", "early-stop left", "early-stop right" };
+                    fprintf( stderr, "ma_b200 dp bin W=%d %s: %d tasks, %llu cells, %.3f ms, %.1f GCUPS\n", Ws[ b / 3 ],
+                             kKind[ b % 3 ], ctx->hctrl.bin_count[ b ], c[ 49 + b ], ms, c[ 49 + b ] / ms / 1e6 );
+                }
         ctx->ksw_cigar_used = c[ 48 ]; // reused as dp cell counter for the pipeline stats
         if( !(int)c[ 32 ] )
             return;

@@ -82,3 +82,17 @@ def test_cli_small_inversions_sam_matches_reference(tmp_path, preset, extra, gol
     exp = open(os.path.join(H.GOLDEN, gold)).read()
     assert sum(1 for l in exp.splitlines() if not l.startswith("@") and int(l.split("\t")[1]) & 0x800) >= 1
     assert out.decode() == exp
+
+
+@pytest.mark.gpu
+def test_cli_two_devices_keep_input_order(tmp_path):
+    """--Devices 0,1: batches go to whichever GPU is free (index replicated, no collective); the SAM
+    file is the same as with one device. Needs two GPUs (gpurun --gpus 2)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    exe = build_cli()
+    out = subprocess.check_output([exe, "-x", PC.GOLD_PREFIX, "-i", os.path.join(H.GOLDEN, "gold_reads.fq"), "-p",
+                                   "Illumina_Paired", "--Interleaved", "--Srand", str(PC.SRAND), "--Batch", "4",
+                                   "--Devices", "0,1"])
+    assert out.decode() == open(os.path.join(H.GOLDEN, "gold_fq_illuminapaired.sam")).read()
