@@ -103,12 +103,19 @@ class ReadStream
 {
     std::vector<std::string> vFiles;
     size_t uiFile = 0;
-    std::unique_ptr<ReadParser> pParser;
+    std::shared_ptr<ReadParser> pParser;
 
   public:
+    // byte range of one record in the file of pOwner (converted later, possibly on another thread)
+    struct Record
+    {
+        const ReadParser* pOwner;
+        size_t uiBegin, uiEnd;
+    };
     explicit ReadStream( std::vector<std::string> v ) : vFiles( std::move( v ) )
     {}
-    bool next( NucSeq& q )
+    // serial pass: the next record; vKeepAlive collects the parsers whose records are still to be converted
+    bool next( Record& r, std::vector<std::shared_ptr<ReadParser>>& vKeepAlive )
     {
         while( true )
         {
@@ -116,10 +123,15 @@ class ReadStream
             {
                 if( uiFile >= vFiles.size( ) )
                     return false;
-                pParser.reset( new ReadParser( vFiles[ uiFile++ ] ) );
+                pParser = std::make_shared<ReadParser>( vFiles[ uiFile++ ] );
             }
-            if( pParser->next( q ) )
+            if( pParser->nextRecord( r.uiBegin, r.uiEnd ) )
+            {
+                r.pOwner = pParser.get( );
+                if( vKeepAlive.empty( ) || vKeepAlive.back( ) != pParser )
+                    vKeepAlive.push_back( pParser );
                 return true;
+            }
             pParser.reset( );
         }
     }
@@ -189,6 +201,7 @@ int main( int argc, char** argv )
             std::cerr << "usage: maCMD_b200 -x <index prefix> -i <reads> [-m <mates>] [-o <out.sam>] [-p <presetting>]\n";
             return argc <= 1 ? 0 : 1;
         }
+        const auto tStart = std::chrono::steady_clock::now( );
         std::vector<std::unique_ptr<Aligner>> vAligners;
         for( int iDevice : vDevices )
         {
@@ -198,6 +211,7 @@ int main( int argc, char** argv )
             vAligners.back( )->params( ).bSearchInversions = bInversions;
             vAligners.back( )->params( ).iZDropInversion = iZDropInversion;
         }
+        const double fStartup = std::chrono::duration<double>( std::chrono::steady_clock::now( ) - tStart ).count( );
         Aligner& xAligner = *vAligners[ 0 ];
         const bool bPaired = xAligner.params( ).xParams.use_paired_reads != 0;
         if( bPaired && bInversions )
@@ -239,6 +253,9 @@ int main( int argc, char** argv )
             try
             {
                 ReadStream xIn( vIn ), xMate( vMate );
+                std::vector<ReadStream::Record> vRecords;
+                std::vector<std::shared_ptr<ReadParser>> vKeepAlive;
+                const size_t uiParseThreads = std::max<size_t>( 1, std::min<size_t>( 4, uiThreads / 3 ) );
                 size_t uiDone = 0, uiSeq = 0;
                 bool bMore = true;
                 while( bMore )
@@ -248,25 +265,47 @@ int main( int argc, char** argv )
                         return;
                     const auto t0 = now( );
                     pB->uiFirst = uiDone, pB->uiSeq = uiSeq++;
-                    auto& v = pB->vReads;
-                    size_t n = 0;
-                    while( n < uiBatch )
+                    // serial pass over the line ends: the records of the batch ...
+                    vRecords.clear( ), vKeepAlive.clear( );
+                    ReadStream::Record xR;
+                    while( vRecords.size( ) < uiBatch )
                     {
-                        if( v.size( ) < n + 2 )
-                            v.resize( n + 2 );
-                        if( !( bMore = xIn.next( v[ n ] ) ) )
+                        if( !( bMore = xIn.next( xR, vKeepAlive ) ) )
                             break;
-                        n++;
+                        vRecords.push_back( xR );
                         if( !vMate.empty( ) )
                         {
-                            if( !xMate.next( v[ n ] ) )
+                            if( !xMate.next( xR, vKeepAlive ) )
                                 throw std::runtime_error( "fewer mates than reads" );
-                            n++;
+                            vRecords.push_back( xR );
                         }
                     }
-                    v.resize( n );
+                    const size_t n = vRecords.size( );
                     if( n == 0 )
                         break;
+                    // ... converted to NucSeq (names, base codes, qualities) on a few threads
+                    auto& v = pB->vReads;
+                    v.resize( n );
+                    const size_t uiParts = std::max<size_t>( 1, std::min<size_t>( uiParseThreads, n / 4096 + 1 ) );
+                    std::vector<std::exception_ptr> vErr( uiParts );
+                    std::vector<std::thread> vWorkers;
+                    for( size_t c = 0; c < uiParts; c++ )
+                        vWorkers.emplace_back( [ &, c ]( ) {
+                            try
+                            {
+                                for( size_t k = n * c / uiParts; k < n * ( c + 1 ) / uiParts; k++ )
+                                    vRecords[ k ].pOwner->parseRecord( vRecords[ k ].uiBegin, vRecords[ k ].uiEnd, v[ k ] );
+                            }
+                            catch( ... )
+                            {
+                                vErr[ c ] = std::current_exception( );
+                            }
+                        } );
+                    for( auto& t : vWorkers )
+                        t.join( );
+                    for( auto& e : vErr )
+                        if( e )
+                            std::rethrow_exception( e );
                     if( bPaired && n % 2 )
                         throw std::runtime_error( "odd number of reads for a paired presetting" );
                     uiDone += n;
@@ -274,8 +313,8 @@ int main( int argc, char** argv )
                     if( !xParsed.push( std::move( pB ) ) )
                         return;
                 }
-                NucSeq xQ;
-                if( !vMate.empty( ) && xMate.next( xQ ) )
+                ReadStream::Record xR;
+                if( !vMate.empty( ) && xMate.next( xR, vKeepAlive ) )
                     throw std::runtime_error( "more mates than reads" );
             }
             catch( ... )
@@ -396,7 +435,10 @@ int main( int argc, char** argv )
             if( e )
                 std::rethrow_exception( e );
         if( bVerbose )
-            fprintf( stderr, "\rbusy seconds: reader %.3f, gpu stage (upload, kernels, download; max over %zu devices) %.3f of which "
+            fprintf( stderr, "\rstart-up (CUDA context, index files -> device) %.3f s, total %.3f s\n", fStartup,
+                     secs( tStart, now( ) ) );
+        if( bVerbose )
+            fprintf( stderr, "busy seconds: reader %.3f, gpu stage (upload, kernels, download; max over %zu devices) %.3f of which "
                              "kernels %.3f, format %.3f (%zu threads), write %.3f\n", fParse, vAligners.size( ), fGpu, fKernels, fFormat, uiThreads, fWrite );
         if( pOut != stdout )
             fclose( pOut );

@@ -64,7 +64,8 @@ def main():
         if r.returncode:
             raise SystemExit(r.stderr.decode()[-2000:])
         busy = [l for l in r.stderr.decode().replace("\r", "\n").splitlines() if l.startswith("busy seconds")]
-        runs.append({"wall_s": dt, "busy": busy[-1] if busy else None})
+        start = [l for l in r.stderr.decode().replace("\r", "\n").splitlines() if l.startswith("start-up")]
+        runs.append({"wall_s": dt, "busy": busy[-1] if busy else None, "startup": start[-1] if start else None})
     n_lines = int(subprocess.check_output(["wc", "-l", out]).split()[0])
     best = min(runs, key=lambda x: x["wall_s"])
     line = {"metric": "aligned reads/sec, FASTQ files in -> SAM file out (maCMD_b200, whole process incl. index load)",
