@@ -795,31 +795,48 @@ class Aligner
     // into a caller-owned RawReport whose buffers are reused from batch to batch
     void reportRaw( const std::vector<NucSeq>& vReads, RawReport& xRaw, ma_b200_align_stats* pStats = nullptr )
     {
+        fillSlab( vReads, vSlab, vOffsets );
+        reportRaw( vReads.size( ), vSlab.data( ), vOffsets.data( ), xRaw, pStats );
+    }
+    // the reads of a batch as the C ABI takes them: concatenated base codes + offsets (uiParts-th part iPart of the
+    // copy, so that several host threads can share it; offsets must have been filled by slabOffsets)
+    static void slabOffsets( const std::vector<NucSeq>& vReads, PinnedVector<uint8_t>& rSlab,
+                             PinnedVector<int64_t>& rOffsets )
+    {
+        rOffsets.resize( vReads.size( ) + 1 );
+        size_t uiBytes = 0;
+        for( size_t i = 0; i < vReads.size( ); i++ )
+            rOffsets[ i ] = (int64_t)uiBytes, uiBytes += vReads[ i ].vSeq.size( );
+        rOffsets[ vReads.size( ) ] = (int64_t)uiBytes;
+        rSlab.resize( uiBytes + 1 );
+        rSlab[ uiBytes ] = 0;
+    }
+    static void slabCopy( const std::vector<NucSeq>& vReads, PinnedVector<uint8_t>& rSlab,
+                          const PinnedVector<int64_t>& rOffsets, size_t iPart = 0, size_t uiParts = 1 )
+    {
+        for( size_t i = vReads.size( ) * iPart / uiParts; i < vReads.size( ) * ( iPart + 1 ) / uiParts; i++ )
+            if( !vReads[ i ].vSeq.empty( ) )
+                memcpy( rSlab.data( ) + rOffsets[ i ], vReads[ i ].vSeq.data( ), vReads[ i ].vSeq.size( ) );
+    }
+    static void fillSlab( const std::vector<NucSeq>& vReads, PinnedVector<uint8_t>& rSlab, PinnedVector<int64_t>& rOffsets )
+    {
+        slabOffsets( vReads, rSlab, rOffsets );
+        slabCopy( vReads, rSlab, rOffsets );
+    }
+    // with the slab prepared by the caller (maCMD_b200's reader threads do that while the device is busy)
+    void reportRaw( size_t uiReads, const uint8_t* pSlab, const int64_t* pOffsets, RawReport& xRaw,
+                    ma_b200_align_stats* pStats = nullptr )
+    {
         xRaw.bPaired = xParams.xParams.use_paired_reads != 0;
-        if( xRaw.bPaired && vReads.size( ) % 2 )
+        if( xRaw.bPaired && uiReads % 2 )
             throw std::runtime_error( "PairedReads: the batch must hold the mates interleaved (2k, 2k+1)" );
         xIndex.check( ma_b200_set_params( xIndex.ctx( ), &xParams.xParams ) );
-        size_t uiBytes = 0;
-        for( auto& r : vReads )
-            uiBytes += r.vSeq.size( );
-        vSlab.resize( uiBytes + 1 );
-        vOffsets.resize( vReads.size( ) + 1 );
-        uiBytes = 0;
-        for( size_t i = 0; i < vReads.size( ); i++ )
-        {
-            vOffsets[ i ] = (int64_t)uiBytes;
-            if( !vReads[ i ].vSeq.empty( ) )
-                memcpy( vSlab.data( ) + uiBytes, vReads[ i ].vSeq.data( ), vReads[ i ].vSeq.size( ) );
-            uiBytes += vReads[ i ].vSeq.size( );
-        }
-        vOffsets[ vReads.size( ) ] = (int64_t)uiBytes;
-        vSlab[ uiBytes ] = 0;
-        xIndex.check( ma_b200_align_upload( xIndex.ctx( ), (int64_t)vReads.size( ), vSlab.data( ), vOffsets.data( ) ) );
+        xIndex.check( ma_b200_align_upload( xIndex.ctx( ), (int64_t)uiReads, pSlab, pOffsets ) );
         ma_b200_align_stats st;
         xIndex.check( ma_b200_align_run( xIndex.ctx( ), MA_B200_STAGE_MAPQ, 0, &st ) );
         if( pStats )
             *pStats = st;
-        xRaw.vInfo.resize( vReads.size( ) );
+        xRaw.vInfo.resize( uiReads );
         xRaw.vAln.resize( (size_t)st.n_sets + 1 );
         xRaw.vRuns.resize( (size_t)st.n_runs + 1 );
         xIndex.check( ma_b200_align_download( xIndex.ctx( ), xRaw.vInfo.data( ), xRaw.vAln.data( ),

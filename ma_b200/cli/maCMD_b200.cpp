@@ -27,6 +27,7 @@
 #include <cstdio>
 #include <deque>
 #include <exception>
+#include <functional>
 #include <iostream>
 #include <map>
 #include <mutex>
@@ -237,9 +238,13 @@ int main( int argc, char** argv )
             size_t uiFirst = 0, uiSeq = 0;
             RawReport xRaw;
             std::vector<std::vector<Alignment>> vRecords; // with --Detect_Small_Inversions: SmallInversions' vectors
+            PinnedVector<uint8_t> vSlab; // the reads as the C ABI takes them, filled by the reader's threads
+            PinnedVector<int64_t> vOffsets;
+            std::vector<std::string> vText; // SAM text of the batch, one piece per formatting thread
+            size_t uiChunks = 0;
         };
-        const size_t uiPool = 3 + 2 * vAligners.size( );
-        BoundedQueue<std::unique_ptr<Batch>> xParsed( 2 ), xAligned( 2 + vAligners.size( ) ), xFree( uiPool );
+        const size_t uiPool = 4 + 2 * vAligners.size( );
+        BoundedQueue<std::unique_ptr<Batch>> xParsed( 2 ), xAligned( 2 + vAligners.size( ) ), xFormatted( 1 ), xFree( uiPool );
         for( size_t i = 0; i < uiPool; i++ )
             xFree.push( std::make_unique<Batch>( ) );
         std::exception_ptr pReaderError, pWriterError;
@@ -287,25 +292,33 @@ int main( int argc, char** argv )
                     auto& v = pB->vReads;
                     v.resize( n );
                     const size_t uiParts = std::max<size_t>( 1, std::min<size_t>( uiParseThreads, n / 4096 + 1 ) );
-                    std::vector<std::exception_ptr> vErr( uiParts );
-                    std::vector<std::thread> vWorkers;
-                    for( size_t c = 0; c < uiParts; c++ )
-                        vWorkers.emplace_back( [ &, c ]( ) {
-                            try
-                            {
-                                for( size_t k = n * c / uiParts; k < n * ( c + 1 ) / uiParts; k++ )
-                                    vRecords[ k ].pOwner->parseRecord( vRecords[ k ].uiBegin, vRecords[ k ].uiEnd, v[ k ] );
-                            }
-                            catch( ... )
-                            {
-                                vErr[ c ] = std::current_exception( );
-                            }
-                        } );
-                    for( auto& t : vWorkers )
-                        t.join( );
-                    for( auto& e : vErr )
-                        if( e )
-                            std::rethrow_exception( e );
+                    auto parallel = [ & ]( std::function<void( size_t )> fPart ) {
+                        std::vector<std::exception_ptr> vErr( uiParts );
+                        std::vector<std::thread> vWorkers;
+                        for( size_t c = 0; c < uiParts; c++ )
+                            vWorkers.emplace_back( [ &, c ]( ) {
+                                try
+                                {
+                                    fPart( c );
+                                }
+                                catch( ... )
+                                {
+                                    vErr[ c ] = std::current_exception( );
+                                }
+                            } );
+                        for( auto& t : vWorkers )
+                            t.join( );
+                        for( auto& e : vErr )
+                            if( e )
+                                std::rethrow_exception( e );
+                    };
+                    parallel( [ & ]( size_t c ) {
+                        for( size_t k = n * c / uiParts; k < n * ( c + 1 ) / uiParts; k++ )
+                            vRecords[ k ].pOwner->parseRecord( vRecords[ k ].uiBegin, vRecords[ k ].uiEnd, v[ k ] );
+                    } );
+                    // ... and gathered into the page-locked slab the device stage uploads
+                    Aligner::slabOffsets( v, pB->vSlab, pB->vOffsets );
+                    parallel( [ & ]( size_t c ) { Aligner::slabCopy( v, pB->vSlab, pB->vOffsets, c, uiParts ); } );
                     if( bPaired && n % 2 )
                         throw std::runtime_error( "odd number of reads for a paired presetting" );
                     uiDone += n;
@@ -328,9 +341,8 @@ int main( int argc, char** argv )
             try
             {
                 std::unique_ptr<Batch> pNext;
-                std::vector<std::string> vText; // kept over the batches: the buffers are reused
                 std::map<size_t, std::unique_ptr<Batch>> xPending; // batches of other devices that finished early
-                size_t uiDone = 0, uiSeq = 0;
+                size_t uiSeq = 0;
                 while( xAligned.pop( pNext ) )
                 {
                     xPending[ pNext->uiSeq ] = std::move( pNext );
@@ -342,9 +354,11 @@ int main( int argc, char** argv )
                     const auto t0 = now( );
                     const size_t uiUnits = pB->xRaw.units( );
                     const size_t uiChunks = std::max<size_t>( 1, std::min<size_t>( uiThreads, uiUnits / 256 + 1 ) );
+                    auto& vText = pB->vText; // kept with the batch: the buffers are reused
                     vText.resize( std::max( vText.size( ), uiChunks ) );
                     for( auto& sText : vText )
                         sText.clear( );
+                    pB->uiChunks = uiChunks;
                     std::vector<std::thread> vWorkers;
                     std::vector<std::exception_ptr> vErr( uiChunks );
                     for( size_t c = 0; c < uiChunks; c++ )
@@ -370,14 +384,9 @@ int main( int argc, char** argv )
                     for( auto& e : vErr )
                         if( e )
                             std::rethrow_exception( e );
-                    const auto t1 = now( );
-                    for( auto& sText : vText )
-                        if( fwrite( sText.data( ), 1, sText.size( ), pOut ) != sText.size( ) )
-                            throw std::runtime_error( "write error on " + ( sOut.empty( ) ? std::string( "stdout" ) : sOut ) );
-                    fFormat += secs( t0, t1 ), fWrite += secs( t1, now( ) );
-                    uiDone += pB->vReads.size( );
-                    std::cerr << "\r" << uiDone << " reads aligned." << std::flush;
-                    xFree.push( std::move( pB ) );
+                    fFormat += secs( t0, now( ) );
+                    if( !xFormatted.push( std::move( pB ) ) ) // the file is written while the next batch is formatted
+                        return;
                     }
                 }
             }
@@ -385,6 +394,32 @@ int main( int argc, char** argv )
             {
                 pWriterError = std::current_exception( );
                 xAligned.close( ), xFree.close( );
+            }
+            xFormatted.close( );
+        } );
+
+        std::exception_ptr pOutputError;
+        std::thread xOutputThread( [ & ]( ) {
+            try
+            {
+                std::unique_ptr<Batch> pB;
+                size_t uiDone = 0;
+                while( xFormatted.pop( pB ) )
+                {
+                    const auto t0 = now( );
+                    for( size_t c = 0; c < pB->uiChunks; c++ )
+                        if( fwrite( pB->vText[ c ].data( ), 1, pB->vText[ c ].size( ), pOut ) != pB->vText[ c ].size( ) )
+                            throw std::runtime_error( "write error on " + ( sOut.empty( ) ? std::string( "stdout" ) : sOut ) );
+                    fWrite += secs( t0, now( ) );
+                    uiDone += pB->vReads.size( );
+                    std::cerr << "\r" << uiDone << " reads aligned." << std::flush;
+                    xFree.push( std::move( pB ) );
+                }
+            }
+            catch( ... )
+            {
+                pOutputError = std::current_exception( );
+                xFormatted.close( ), xAligned.close( ), xFree.close( );
             }
         } );
 
@@ -401,7 +436,7 @@ int main( int argc, char** argv )
                         const auto t0 = now( );
                         vAligners[ g ]->params( ).xParams.srand_base = uiSrand + (uint32_t)pB->uiFirst;
                         ma_b200_align_stats xStats;
-                        vAligners[ g ]->reportRaw( pB->vReads, pB->xRaw, &xStats );
+                        vAligners[ g ]->reportRaw( pB->vReads.size( ), pB->vSlab.data( ), pB->vOffsets.data( ), pB->xRaw, &xStats );
                         pB->vRecords.clear( );
                         if( bInversions )
                         { // the DP of SmallInversions runs on this device as one more batch
@@ -430,7 +465,8 @@ int main( int argc, char** argv )
         xAligned.close( );
         xReader.join( );
         xWriterThread.join( );
-        vGpuError.push_back( pReaderError ), vGpuError.push_back( pWriterError );
+        xOutputThread.join( );
+        vGpuError.push_back( pReaderError ), vGpuError.push_back( pWriterError ), vGpuError.push_back( pOutputError );
         for( auto& e : vGpuError )
             if( e )
                 std::rethrow_exception( e );

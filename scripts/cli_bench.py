@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--devices", default="0")
     ap.add_argument("--batch", type=int, default=500_000)
     ap.add_argument("--threads", type=int, default=max(1, (os.cpu_count() or 4) - 3))
+    ap.add_argument("--repeat", type=int, default=1, help="list every input file this many times (longer run, same data)")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     subprocess.check_call(["make", "-s", "-C", os.path.dirname(CLI)])
@@ -58,7 +59,7 @@ def main():
     runs = []
     for _ in range(2):  # the first run warms the page cache and the driver
         t = time.time()
-        r = subprocess.run([CLI, "-x", prefix, "-i", f1, "-m", f2, "-p", "Illumina", "-o", out, "--Devices", a.devices,
+        r = subprocess.run([CLI, "-x", prefix, "-i", ",".join([f1] * a.repeat), "-m", ",".join([f2] * a.repeat), "-p", "Illumina", "-o", out, "--Devices", a.devices,
                             "--Batch", str(a.batch), "-t", str(a.threads), "--Verbose"], capture_output=True)
         dt = time.time() - t
         if r.returncode:
@@ -69,11 +70,11 @@ def main():
     n_lines = int(subprocess.check_output(["wc", "-l", out]).split()[0])
     best = min(runs, key=lambda x: x["wall_s"])
     line = {"metric": "aligned reads/sec, FASTQ files in -> SAM file out (maCMD_b200, whole process incl. index load)",
-            "value": 2 * a.pairs / best["wall_s"], "unit": "reads/s", "wall_s": best["wall_s"], "runs": runs,
+            "value": 2 * a.pairs * a.repeat / best["wall_s"], "unit": "reads/s", "wall_s": best["wall_s"], "runs": runs,
             "config": {"workload": "configs[1]: %d Mbp genome, %d pairs 2x150, -p Illumina -i m1.fq -m m2.fq" %
-                                   (a.genome_mbp, a.pairs), "devices": a.devices, "batch": a.batch,
+                                   (a.genome_mbp, a.pairs) + (" (files listed %d times)" % a.repeat if a.repeat > 1 else ""), "devices": a.devices, "batch": a.batch,
                        "format_threads": a.threads, "files_on": tmp},
-            "input_bytes": in_bytes, "output_bytes": os.path.getsize(out), "sam_lines": n_lines}
+            "input_bytes": in_bytes * a.repeat, "output_bytes": os.path.getsize(out), "sam_lines": n_lines}
     s = json.dumps(line)
     print(s)
     if a.out:

@@ -1,0 +1,101 @@
+"""BASELINE.json configs[1] at FULL size (100 Mbp genome, 1 M simulated 2x150 pairs, Illumina_Paired preset) through the
+C ABI: the oracle cannot be run at this size, so the checks are size-independent properties of the path —
+  * accuracy against the simulation's truth (the primary alignment of a mate starts where the mate was drawn),
+  * determinism (two runs give the same records),
+  * sharding invariance: a contiguous shard of pairs aligned on its own, with the RANSAC stream offset
+    by its first read index, gives the records it has inside the full batch,
+  * conservation: every read is reported, mates of a pair stay together, counters add up.
+Bit-exact parity with the reference is established at oracle sizes in test_pipeline_gpu.py; this file guards the scale."""
+import numpy as np
+import pytest
+
+from ma_b200 import api, synth
+
+N_PAIRS = 1_000_000
+GENOME_MBP = 100
+SRAND = 77
+
+
+def record_table(info, alns, runs):
+    """One row per alignment, ordered by (read, rank): everything the writer consumes, with a checksum of the runs."""
+    order = np.lexsort((alns["rank"], alns["read"]))
+    a = alns[order]
+    n_runs = a["n_runs"].astype(np.int64)
+    start = np.repeat(a["run_off"], n_runs)
+    within = np.arange(n_runs.sum(), dtype=np.int64) - np.repeat(np.cumsum(n_runs) - n_runs, n_runs)
+    words = runs[start + within].astype(np.uint64)
+    mixed = words * (within.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(1))
+    csum = np.zeros(len(a), dtype=np.uint64)
+    nz = n_runs > 0
+    csum[nz] = np.add.reduceat(mixed, (np.cumsum(n_runs) - n_runs)[nz])
+    cols = [a["read"].astype(np.int64), a["rank"].astype(np.int64), a["begin_ref"], a["end_ref"], a["score"],
+            a["begin_q"].astype(np.int64), a["end_q"].astype(np.int64), a["flags"].astype(np.int64),
+            a["mapq"].view(np.int64), a["rank_mq"].astype(np.int64), a["pair_rank"].astype(np.int64),
+            csum.view(np.int64)]
+    return np.stack(cols, axis=1)
+
+
+@pytest.mark.gpu
+def test_full_size_configs1_properties():
+    n_contigs = 10
+    genome = synth.random_genome([GENOME_MBP * 1_000_000 // n_contigs] * n_contigs, 2)
+    m1, m2, cid, pos, flen, rev = synth.simulate_pairs(genome, N_PAIRS, 150, 2017)
+    reads = np.empty((2 * N_PAIRS, 150), dtype=np.uint8)
+    reads[0::2], reads[1::2] = m1, m2
+    lens = np.array([len(c) for c in genome], dtype=np.int64)
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    fwd = int(lens.sum())
+
+    def make(srand):
+        ctx = api.Context(0, "illumina_paired")
+        p = api.preset("illumina_paired")
+        p.srand_base = srand
+        ctx.set_params(p)
+        return ctx
+
+    ctx = make(SRAND)
+    ctx.index_build(np.concatenate(genome), starts, lens.tolist())
+    data, off = api.pack_reads(reads)
+    ctx.align_upload(data, off)
+    st = ctx.align_run(api.STAGE_MAPQ)
+    info, alns, runs = ctx.download_alignments()
+    assert st["n_reads"] == 2 * N_PAIRS and st["n_dropped"] == 0
+    assert int(info["n_sets"].sum()) == st["n_sets"] == len(alns)
+    full = record_table(info, alns, runs)
+
+    # conservation: (almost) every simulated read gets an alignment; every record belongs to its read's slab range
+    assert (info["n_sets"] > 0).mean() > 0.999
+    assert (alns["read"] >= 0).all() and (alns["read"] < 2 * N_PAIRS).all()
+
+    # accuracy against the truth of the simulation
+    prim = alns[alns["rank_mq"] == 0]
+    r = prim["read"].astype(np.int64)
+    pair, mate = r // 2, r % 2
+    g0 = starts[cid[pair]] + pos[pair]
+    is_left = (mate == 0) != rev[pair]  # the mate drawn from the fragment's 5' end on the forward strand
+    expect = np.where(is_left, g0, 2 * fwd - g0 - flen[pair])
+    got = prim["begin_ref"] - prim["begin_q"]
+    ok = np.abs(got - expect) <= 10
+    assert len(prim) > 0.999 * 2 * N_PAIRS
+    assert ok.mean() > 0.98, ok.mean()
+
+    # determinism: the same batch again
+    st2 = ctx.align_run(api.STAGE_MAPQ)
+    info2, alns2, runs2 = ctx.download_alignments()
+    assert st2["n_sets"] == st["n_sets"] and st2["dp_cells"] == st["dp_cells"]
+    assert np.array_equal(record_table(info2, alns2, runs2), full)
+    ctx.close()
+
+    # sharding invariance: pairs [lo, hi) on their own context (index replicated, no exchange between shards)
+    lo, hi = 2 * 400_000, 2 * 500_000
+    c2 = make(SRAND + lo)
+    c2.index_build(np.concatenate(genome), starts, lens.tolist())
+    d2, o2 = api.pack_reads(reads[lo:hi])
+    c2.align_upload(d2, o2)
+    c2.align_run(api.STAGE_MAPQ)
+    i2, a2, r2 = c2.download_alignments()
+    shard = record_table(i2, a2, r2)
+    shard[:, 0] += lo
+    sel = (full[:, 0] >= lo) & (full[:, 0] < hi)
+    assert np.array_equal(shard, full[sel])
+    c2.close()
