@@ -258,8 +258,8 @@ int main( int argc, char** argv )
             try
             {
                 ReadStream xIn( vIn ), xMate( vMate );
-                std::vector<ReadStream::Record> vRecords;
-                std::vector<std::shared_ptr<ReadParser>> vKeepAlive;
+                std::vector<ReadStream::Record> vRecords, vFirst, vSecond;
+                std::vector<std::shared_ptr<ReadParser>> vKeepAlive, vKeepAliveMate;
                 const size_t uiParseThreads = std::max<size_t>( 1, std::min<size_t>( 4, uiThreads / 3 ) );
                 size_t uiDone = 0, uiSeq = 0;
                 bool bMore = true;
@@ -270,20 +270,53 @@ int main( int argc, char** argv )
                         return;
                     const auto t0 = now( );
                     pB->uiFirst = uiDone, pB->uiSeq = uiSeq++;
-                    // serial pass over the line ends: the records of the batch ...
-                    vRecords.clear( ), vKeepAlive.clear( );
-                    ReadStream::Record xR;
-                    while( vRecords.size( ) < uiBatch )
+                    // serial pass over the line ends: the records of the batch (the mate file on its own thread) ...
+                    vKeepAlive.clear( ), vKeepAliveMate.clear( );
+                    auto scan = []( ReadStream& rStream, std::vector<ReadStream::Record>& vOut, size_t uiMax,
+                                    std::vector<std::shared_ptr<ReadParser>>& vKeep ) {
+                        vOut.clear( );
+                        ReadStream::Record xR;
+                        while( vOut.size( ) < uiMax && rStream.next( xR, vKeep ) )
+                            vOut.push_back( xR );
+                    };
+                    if( vMate.empty( ) )
                     {
-                        if( !( bMore = xIn.next( xR, vKeepAlive ) ) )
-                            break;
-                        vRecords.push_back( xR );
-                        if( !vMate.empty( ) )
+                        scan( xIn, vRecords, uiBatch, vKeepAlive );
+                        bMore = vRecords.size( ) == uiBatch;
+                    }
+                    else
+                    {
+                        std::exception_ptr pMateError;
+                        std::thread xMateScan( [ & ]( ) {
+                            try
+                            {
+                                scan( xMate, vSecond, uiBatch / 2, vKeepAliveMate );
+                            }
+                            catch( ... )
+                            {
+                                pMateError = std::current_exception( );
+                            }
+                        } );
+                        try
                         {
-                            if( !xMate.next( xR, vKeepAlive ) )
-                                throw std::runtime_error( "fewer mates than reads" );
-                            vRecords.push_back( xR );
+                            scan( xIn, vFirst, uiBatch / 2, vKeepAlive );
                         }
+                        catch( ... )
+                        {
+                            xMateScan.join( );
+                            throw;
+                        }
+                        xMateScan.join( );
+                        if( pMateError )
+                            std::rethrow_exception( pMateError );
+                        if( vSecond.size( ) < vFirst.size( ) )
+                            throw std::runtime_error( "fewer mates than reads" );
+                        if( vSecond.size( ) > vFirst.size( ) )
+                            throw std::runtime_error( "more mates than reads" );
+                        bMore = vFirst.size( ) == uiBatch / 2;
+                        vRecords.resize( 2 * vFirst.size( ) );
+                        for( size_t k = 0; k < vFirst.size( ); k++ )
+                            vRecords[ 2 * k ] = vFirst[ k ], vRecords[ 2 * k + 1 ] = vSecond[ k ];
                     }
                     const size_t n = vRecords.size( );
                     if( n == 0 )
@@ -327,7 +360,7 @@ int main( int argc, char** argv )
                         return;
                 }
                 ReadStream::Record xR;
-                if( !vMate.empty( ) && xMate.next( xR, vKeepAlive ) )
+                if( !vMate.empty( ) && xMate.next( xR, vKeepAliveMate ) )
                     throw std::runtime_error( "more mates than reads" );
             }
             catch( ... )

@@ -96,3 +96,21 @@ def test_cli_two_devices_keep_input_order(tmp_path):
                                    "Illumina_Paired", "--Interleaved", "--Srand", str(PC.SRAND), "--Batch", "4",
                                    "--Devices", "0,1"])
     assert out.decode() == open(os.path.join(H.GOLDEN, "gold_fq_illuminapaired.sam")).read()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("drop_from,message", [(1, b"fewer mates than reads"), (0, b"more mates than reads")])
+def test_cli_unequal_mate_files_fail_loudly(tmp_path, drop_from, message):
+    exe = build_cli()
+    recs = open(os.path.join(H.GOLDEN, "gold_reads.fq"), "rb").read().replace(b"\r\n", b"\n").replace(b"\n\n", b"\n")
+    parts = [b"@pair" + r for r in recs.split(b"@pair")[1:]]
+    files = []
+    for m in (0, 1):
+        mine = parts[m::2]
+        if m == drop_from:
+            mine = mine[:-1]
+        files.append(str(tmp_path / ("m%d.fq" % m)))
+        open(files[-1], "wb").write(b"".join(mine))
+    r = subprocess.run([exe, "-x", PC.GOLD_PREFIX, "-i", files[0], "-m", files[1], "-p", "Illumina", "-o",
+                        str(tmp_path / "o.sam")], capture_output=True)
+    assert r.returncode == 1 and message in r.stderr, r.stderr[-300:]
