@@ -65,3 +65,34 @@ def test_read_parser_matches_reference_file_reader(tmp_path, name):
                            "-Wl,-rpath," + os.path.join(H.ROOT, "ma_b200")])
     got = subprocess.check_output([exe, os.path.join(H.GOLDEN, "gold_reads.%s" % name)]).decode()
     assert got == open(os.path.join(H.GOLDEN, "gold_reads_%s.parsed" % name)).read()
+
+
+def _build_reader2(tmp_path):
+    exe = str(tmp_path / "test_reader2")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(H.ROOT, "tests", "cpp", "test_reader2.cpp"),
+                           "-lpthread", "-L" + os.path.join(H.ROOT, "ma_b200"), "-lma_b200",
+                           "-Wl,-rpath," + os.path.join(H.ROOT, "ma_b200")])
+    return exe
+
+
+@pytest.mark.parametrize("name", ["fq", "fa"])
+def test_read_parser_two_pass_equals_serial_and_reference(tmp_path, name):
+    """nextRecord() + parseRecord() on several threads (what maCMD_b200's reader does) == next() == the reference."""
+    exe = _build_reader2(tmp_path)
+    got = subprocess.check_output([exe, os.path.join(H.GOLDEN, "gold_reads.%s" % name)]).decode()
+    assert got == open(os.path.join(H.GOLDEN, "gold_reads_%s.parsed" % name)).read()
+
+
+@pytest.mark.parametrize("text,message", [(b"ACGT\n", b"FASTA/Q"), (b">empty\n\n>next\nACGT\n", b"found empty read"),
+                                          (b"", None)])
+def test_read_parser_rejects_malformed_input(tmp_path, text, message):
+    """Error behaviour of FileReader::execute (fileReader.cpp:37-203): not FASTA/FASTQ, empty read; an empty file
+    holds no reads."""
+    exe = _build_reader2(tmp_path)
+    f = tmp_path / "in.txt"
+    f.write_bytes(text)
+    r = subprocess.run([exe, str(f)], capture_output=True)
+    if message is None:
+        assert r.returncode == 0 and r.stdout == b""
+    else:
+        assert r.returncode == 3 and message in r.stderr, r.stderr
