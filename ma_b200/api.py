@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libma_b200.so")
+# MA_B200_LIB: another build of the same library (A/B of compile-time knobs, scripts/); never a different backend
+LIB_PATH = os.environ.get("MA_B200_LIB") or os.path.join(_HERE, "libma_b200.so")
 
 KSW_RIGHT = 0x02
 KSW_EXTZ_ONLY = 0x40

@@ -1039,7 +1039,10 @@ struct KswBatchArgs
 #ifndef MA_KSW_MINB
 #define MA_KSW_MINB 2
 #endif
-template <int W> __global__ void __launch_bounds__( 256, MA_KSW_MINB ) ksw_batch_kernel( KswBatchArgs A )
+#ifndef MA_KSW_WARPS
+#define MA_KSW_WARPS 8 // warps (DP problems in flight) per CTA
+#endif
+template <int W> __global__ void __launch_bounds__( 32 * MA_KSW_WARPS, MA_KSW_MINB ) ksw_batch_kernel( KswBatchArgs A )
 {
     extern __shared__ __align__( 16 ) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

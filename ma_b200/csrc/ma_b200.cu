@@ -256,11 +256,11 @@ static const int kKswWindows[] = { 128, 256, 512, 1024, 2048 };
 
 template <int W> static long long ksw_bin_grid( ma_b200_ctx* ctx, const KswHostBin& bin, long long tbBudget )
 {
-    const int warpsPerCta = 8;
+    const int warpsPerCta = MA_KSW_WARPS;
     const size_t smem = KswSmemBytes<W>::value * warpsPerCta;
     MA_CUDA( cudaFuncSetAttribute( ksw_batch_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) );
     int perSm = 0;
-    MA_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, ksw_batch_kernel<W>, 256, smem ) );
+    MA_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, ksw_batch_kernel<W>, 32 * MA_KSW_WARPS, smem ) );
     if( perSm < 1 )
         perSm = 1;
     long long grid = (long long)perSm * ctx->num_sms;
@@ -273,8 +273,8 @@ template <int W> static long long ksw_bin_grid( ma_b200_ctx* ctx, const KswHostB
 
 template <int W> static void launch_ksw_bin( ma_b200_ctx* ctx, const KswBatchArgs& A, long long grid )
 {
-    const size_t smem = KswSmemBytes<W>::value * 8;
-    ksw_batch_kernel<W><<<(unsigned)grid, 256, smem, ctx->stream>>>( A );
+    const size_t smem = KswSmemBytes<W>::value * MA_KSW_WARPS;
+    ksw_batch_kernel<W><<<(unsigned)grid, 32 * MA_KSW_WARPS, smem, ctx->stream>>>( A );
     MA_CUDA( cudaGetLastError( ) );
     ctx->launches++;
 }
@@ -390,8 +390,8 @@ static int ksw_run_once( ma_b200_ctx* ctx )
                 default: g = ksw_bin_grid<2048>( ctx, bin, budget ); break;
             }
         grids.push_back( g );
-        tbNeed = std::max<size_t>( tbNeed, (size_t)( g * 8 * bin.tb_stride ) );
-        csNeed = std::max<size_t>( csNeed, (size_t)( g * 8 * bin.cig_stride ) );
+        tbNeed = std::max<size_t>( tbNeed, (size_t)( g * MA_KSW_WARPS * bin.tb_stride ) );
+        csNeed = std::max<size_t>( csNeed, (size_t)( g * MA_KSW_WARPS * bin.cig_stride ) );
     }
     ctx->ksw_tb.reserve( tbNeed + 256 );
     ctx->ksw_cigscratch.reserve( csNeed + 64 );
@@ -751,8 +751,8 @@ static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
                 case 3: grids[ b ] = ksw_bin_grid<1024>( ctx, bin, budget ); break;
                 default: grids[ b ] = ksw_bin_grid<2048>( ctx, bin, budget ); break;
             }
-            tbNeed = std::max<size_t>( tbNeed, (size_t)( grids[ b ] * 8 * bin.tb_stride ) );
-            csNeed = std::max<size_t>( csNeed, (size_t)( grids[ b ] * 8 * bin.cig_stride ) );
+            tbNeed = std::max<size_t>( tbNeed, (size_t)( grids[ b ] * MA_KSW_WARPS * bin.tb_stride ) );
+            csNeed = std::max<size_t>( csNeed, (size_t)( grids[ b ] * MA_KSW_WARPS * bin.cig_stride ) );
         }
         ctx->ksw_tb.reserve( tbNeed + 256 );
         ctx->ksw_cigscratch.reserve( csNeed + 64 );
