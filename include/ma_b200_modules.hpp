@@ -15,6 +15,7 @@
 //   setUpCompGraph (export.cpp:72-128)                                      Aligner::align(reads)
 #pragma once
 #include "ma_b200.h"
+#include <algorithm>
 #include <cstring>
 #include <fstream>
 #include <memory>
@@ -466,18 +467,24 @@ class NeedlemanWunsch
 
 namespace detail
 {
-inline Alignment toAlignment( const ma_b200_alignment& a, const uint32_t* vRuns )
+// (into an existing object: its run vector keeps its capacity)
+inline void fillAlignment( const ma_b200_alignment& a, const uint32_t* vRuns, Alignment& x )
 {
-    Alignment x;
     x.uiBeginOnRef = (nucSeqIndex)a.begin_ref, x.uiEndOnRef = (nucSeqIndex)a.end_ref;
     x.uiBeginOnQuery = (nucSeqIndex)a.begin_q, x.uiEndOnQuery = (nucSeqIndex)a.end_q;
     x.iScore = a.score, x.uiLength = (nucSeqIndex)a.length, x.index_of_strip = a.soc_index;
     x.fMappingQuality = a.mapq;
     x.bSecondary = ( a.flags & MA_B200_ALN_SECONDARY ) != 0, x.bSupplementary = ( a.flags & MA_B200_ALN_SUPPLEMENTARY ) != 0;
     x.bFirst = ( a.flags & MA_B200_ALN_FIRST_MATE ) != 0;
+    x.data.clear( );
     x.data.reserve( (size_t)a.n_runs );
     for( int j = 0; j < a.n_runs; j++ )
         x.data.emplace_back( (MatchType)( vRuns[ a.run_off + j ] & 7 ), vRuns[ a.run_off + j ] >> 3 );
+}
+inline Alignment toAlignment( const ma_b200_alignment& a, const uint32_t* vRuns )
+{
+    Alignment x;
+    fillAlignment( a, vRuns, x );
     return x;
 }
 // runs the path through MA_B200_STAGE_MAPQ and hands every alignment record to fVisit( read, record, runs )
@@ -519,18 +526,34 @@ struct RawReport
     std::vector<Alignment> records( size_t i ) const
     {
         std::vector<Alignment> v;
-        for( size_t uiRead = bPaired ? 2 * i : i; uiRead < ( bPaired ? 2 * i + 2 : i + 1 ); uiRead++ )
+        records( i, v );
+        return v;
+    }
+    // into a caller-owned vector that is reused from unit to unit (no allocation once its elements have grown)
+    void records( size_t i, std::vector<Alignment>& v ) const
+    {
+        const size_t uiFrom = bPaired ? 2 * i : i, uiTo = bPaired ? 2 * i + 2 : i + 1;
+        size_t n = 0;
+        for( size_t uiRead = uiFrom; uiRead < uiTo; uiRead++ )
+            for( int k = 0; k < vInfo[ uiRead ].n_sets; k++ )
+            {
+                const auto& a = vAln[ vInfo[ uiRead ].set_off + k ];
+                n = std::max( n, (size_t)( ( bPaired ? a.pair_rank : a.rank_mq ) + 1 ) );
+            }
+        if( v.size( ) < n )
+            v.resize( n );
+        else
+            v.erase( v.begin( ) + n, v.end( ) );
+        for( auto& x : v ) // a rank without a record (never produced by the device stages) reads as an empty alignment
+            x.uiLength = 0, x.data.clear( );
+        for( size_t uiRead = uiFrom; uiRead < uiTo; uiRead++ )
             for( int k = 0; k < vInfo[ uiRead ].n_sets; k++ )
             {
                 const auto& a = vAln[ vInfo[ uiRead ].set_off + k ];
                 const int iRank = bPaired ? a.pair_rank : a.rank_mq;
-                if( iRank < 0 )
-                    continue;
-                if( v.size( ) <= (size_t)iRank )
-                    v.resize( (size_t)iRank + 1 );
-                v[ iRank ] = detail::toAlignment( a, vRuns.data( ) );
+                if( iRank >= 0 )
+                    detail::fillAlignment( a, vRuns.data( ), v[ (size_t)iRank ] );
             }
-        return v;
     }
 };
 

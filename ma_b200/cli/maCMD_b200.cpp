@@ -399,13 +399,17 @@ int main( int argc, char** argv )
                             try
                             {
                                 std::string& sText = vText[ c ];
+                                std::vector<Alignment> vScratch; // reused from unit to unit
                                 for( size_t u = uiUnits * c / uiChunks; u < uiUnits * ( c + 1 ) / uiChunks; u++ )
+                                {
+                                    if( pB->vRecords.empty( ) )
+                                        pB->xRaw.records( u, vScratch );
                                     if( bPaired )
-                                        xWriter.paired( sText, pB->vReads[ 2 * u ], pB->vReads[ 2 * u + 1 ],
-                                                        pB->xRaw.records( u ) );
+                                        xWriter.paired( sText, pB->vReads[ 2 * u ], pB->vReads[ 2 * u + 1 ], vScratch );
                                     else
                                         xWriter.single( sText, pB->vReads[ u ],
-                                                        pB->vRecords.empty( ) ? pB->xRaw.records( u ) : pB->vRecords[ u ] );
+                                                        pB->vRecords.empty( ) ? vScratch : pB->vRecords[ u ] );
+                                }
                             }
                             catch( ... )
                             {
