@@ -19,6 +19,9 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#ifdef MA_B200_WITH_ZLIB // gzip-compressed input like the reference's GzFileStream (fileReader.h:286-400, WITH_ZLIB)
+#include <zlib.h>
+#endif
 
 namespace libMA_b200
 {
@@ -436,7 +439,31 @@ class ReadParser
         const int fd = open( sFileName.c_str( ), O_RDONLY );
         if( fd < 0 )
             throw std::runtime_error( "Unable to open file " + sFileName );
+        unsigned char aMagic[ 2 ] = { 0, 0 };
+        const bool bGzip = pread( fd, aMagic, 2, 0 ) == 2 && aMagic[ 0 ] == 0x1f && aMagic[ 1 ] == 0x8b;
         struct stat xStat;
+        if( bGzip )
+        { // inflated into memory as a whole (the record scan needs random access)
+            close( fd );
+#ifdef MA_B200_WITH_ZLIB
+            gzFile pGz = gzopen( sFileName.c_str( ), "rb" );
+            if( !pGz )
+                throw std::runtime_error( "Unable to open file " + sFileName );
+            gzbuffer( pGz, 1 << 20 );
+            std::vector<char> vChunk( 1 << 22 );
+            int n;
+            while( ( n = gzread( pGz, vChunk.data( ), (unsigned)vChunk.size( ) ) ) > 0 )
+                sBuffer.append( vChunk.data( ), (size_t)n );
+            const bool bBad = n < 0;
+            gzclose( pGz );
+            if( bBad )
+                throw std::runtime_error( "Error while inflating " + sFileName );
+            pData = sBuffer.data( ), uiSize = sBuffer.size( );
+            return;
+#else
+            throw std::runtime_error( sFileName + " is gzip-compressed: build with -DMA_B200_WITH_ZLIB -lz" );
+#endif
+        }
         if( fstat( fd, &xStat ) == 0 && S_ISREG( xStat.st_mode ) && xStat.st_size > 0 )
         {
             void* pM = mmap( nullptr, (size_t)xStat.st_size, PROT_READ, MAP_PRIVATE, fd, 0 );

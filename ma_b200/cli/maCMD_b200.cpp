@@ -5,7 +5,7 @@
 //   maCMD_b200 -x <index prefix> -i <reads.fq[,more.fq]> [-m <mates.fq[,more.fq]>] [-o <out.sam>] [-p <presetting>]
 //
 //   -x, --Index        prefix of the reference's index files (.bwt .sa .pac .ann .amb), as written by maCMD --Create_Index
-//   -i, --In           FASTA / FASTQ file(s), comma separated
+//   -i, --In           FASTA / FASTQ file(s), plain or gzip-compressed, comma separated
 //   -m, --MateIn       mate file(s); switches "Use Paired Reads" on like the reference (cmdMa.cpp:323-330)
 //   -o, --Out          SAM file (default: standard output)
 //   -p, --Presetting   Default | Illumina | Illumina_Paired | PacBio | Nanopore (default: Default)

@@ -114,3 +114,15 @@ def test_cli_unequal_mate_files_fail_loudly(tmp_path, drop_from, message):
     r = subprocess.run([exe, "-x", PC.GOLD_PREFIX, "-i", files[0], "-m", files[1], "-p", "Illumina", "-o",
                         str(tmp_path / "o.sam")], capture_output=True)
     assert r.returncode == 1 and message in r.stderr, r.stderr[-300:]
+
+
+@pytest.mark.gpu
+def test_cli_gzip_input(tmp_path):
+    import gzip
+    exe = build_cli()
+    f = tmp_path / "reads.fq.gz"
+    with gzip.open(f, "wb") as g:
+        g.write(open(os.path.join(H.GOLDEN, "gold_reads.fq"), "rb").read())
+    out = subprocess.check_output([exe, "-x", PC.GOLD_PREFIX, "-i", str(f), "-p", "Illumina_Paired", "--Interleaved",
+                                   "--Srand", str(PC.SRAND)])
+    assert out.decode() == open(os.path.join(H.GOLDEN, "gold_fq_illuminapaired.sam")).read()

@@ -70,7 +70,7 @@ def test_read_parser_matches_reference_file_reader(tmp_path, name):
 def _build_reader2(tmp_path):
     exe = str(tmp_path / "test_reader2")
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(H.ROOT, "tests", "cpp", "test_reader2.cpp"),
-                           "-lpthread", "-L" + os.path.join(H.ROOT, "ma_b200"), "-lma_b200",
+                           "-DMA_B200_WITH_ZLIB", "-lpthread", "-L" + os.path.join(H.ROOT, "ma_b200"), "-lma_b200", "-lz",
                            "-Wl,-rpath," + os.path.join(H.ROOT, "ma_b200")])
     return exe
 
@@ -96,3 +96,14 @@ def test_read_parser_rejects_malformed_input(tmp_path, text, message):
         assert r.returncode == 0 and r.stdout == b""
     else:
         assert r.returncode == 3 and message in r.stderr, r.stderr
+
+
+def test_read_parser_reads_gzip_input(tmp_path):
+    """.gz input like the reference's GzFileStream (fileReader.h:286-400): same reads as from the plain file."""
+    import gzip
+    exe = _build_reader2(tmp_path)
+    f = tmp_path / "reads.fq.gz"
+    with gzip.open(f, "wb") as g:
+        g.write(open(os.path.join(H.GOLDEN, "gold_reads.fq"), "rb").read())
+    got = subprocess.check_output([exe, str(f)]).decode()
+    assert got == open(os.path.join(H.GOLDEN, "gold_reads_fq.parsed")).read()
