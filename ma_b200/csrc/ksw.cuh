@@ -269,7 +269,7 @@ __device__ __forceinline__ bool ksw_rows( const KswScore& P, const SeqAccess& se
             sm.u[ r & M ] = (signed char)first_col;
         }
         // old H left of en0, read before the pass updates it (:194-195); row 0: H[0] = v[0] - (q + e) (:247)
-        const int hprev = r == 0 ? -qe : ( en0 > 0 ? sm.H[ ( en0 - 1 ) & M ] : sm.H[ en0 & M ] );
+        const int hprev = r == 0 ? -P.qe_row0 : ( en0 > 0 ? sm.H[ ( en0 - 1 ) & M ] : sm.H[ en0 & M ] );
         __syncwarp( );
         const int en1 = st0 + ( ( en0 - st0 ) & SMASK );
         int bh = NONE_H, bt = NONE_T; // this lane's SSE-lane candidate: first block reaching the lane maximum
@@ -752,7 +752,7 @@ __device__ __forceinline__ bool ksw_rows_p2x2( const KswScore& P, const SeqAcces
         }
         unsigned cXb = cX, cX2b = cX2, cHb = cH; // the same column after row r
         // old H left of en0, read before the pass updates it (:194-195); row 0: H[0] = v[0] - (q + e) (:247)
-        const int hprev = r == 0 ? -qe : (int)Hin[ ( en0 - ( en0 > 0 ? 1 : 0 ) ) & M ];
+        const int hprev = r == 0 ? -P.qe_row0 : (int)Hin[ ( en0 - ( en0 > 0 ? 1 : 0 ) ) & M ];
         const unsigned hprev2 = ( (unsigned)hprev & 0xFFFFu ) * 0x10001u;
         __syncwarp( );
         const int c = qlen - 1 - r; // reversed-query index of column t is t + c (row r), t + c - 1 (row r + 1)

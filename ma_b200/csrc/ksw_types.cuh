@@ -23,6 +23,7 @@ struct KswScore
 {
     int match, mismatch; // mismatch as a (negative) score
     int q, e, q2, e2; // after the q/q2 swap of kswcpp_core.h:367-375
+    int qe_row0; // q + e BEFORE that swap: the reference's scalar qe (kswcpp_core.h:338) enters H[0] of row 0 (:247)
     int long_thres, long_diff;
     int min16; // iOverallMinScr (negative) for the int16/int32 switch, kswcpp.h:101-115
     int early_return; // -min_sc > 2(q+e): the reference returns right after ksw_reset_extz

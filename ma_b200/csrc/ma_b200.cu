@@ -94,6 +94,7 @@ static KswScore make_score( const ma_b200_params& p )
     s.match = p.match;
     s.mismatch = -p.mismatch;
     int q = p.gap, e = p.extend, q2 = p.gap2, e2 = p.extend2;
+    s.qe_row0 = q + e;
     if( q2 + e2 < q + e ) // kswcpp_core.h:367-375
         std::swap( q, q2 ), std::swap( e, e2 );
     s.q = q, s.e = e, s.q2 = q2, s.e2 = e2;

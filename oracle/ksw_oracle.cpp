@@ -93,6 +93,7 @@ void core( int qlen, const uint8_t* query, int tlen, const uint8_t* target, cons
     int8_t q = (int8_t)sc.gap, e = (int8_t)sc.extend, q2 = (int8_t)sc.gap2, e2 = (int8_t)sc.extend2;
     const int8_t sc_mch = (int8_t)sc.match, sc_mis = (int8_t)-sc.mismatch;
     const bool bLeft = !( flag & MA_KSW_RIGHT );
+    const int qe_row0 = q + e; // sic: the scalar qe of H[0] = v[0] - qe is initialised BEFORE the swap (:338, :247)
     if( q2 + e2 < q + e ) // kswcpp_core.h:367-375
         std::swap( q, q2 ), std::swap( e, e2 );
     const int qe = q + e, qe2 = q2 + e2;
@@ -259,7 +260,7 @@ void core( int qlen, const uint8_t* query, int tlen, const uint8_t* target, cons
         }
         else
         {
-            H[ 0 ] = (TS)( v[ 0 ] - qe );
+            H[ 0 ] = (TS)( v[ 0 ] - qe_row0 );
             max_H = H[ 0 ];
             max_t = 0;
         }

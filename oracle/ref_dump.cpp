@@ -459,7 +459,11 @@ static std::vector<KswPair> readPairs( const std::string& sFile )
 static int cmdKsw( int argc, char** argv )
 {
     auto vPairs = readPairs( argv[ 2 ] );
-    KswCppParam<5> xParam( 2, 4, 4, 2, 24, 1 );
+    // optional: match mismatch gap extend gap2 extend2 (KswCppParam<5>, kswcpp.h:44-129); default = pGlobalParams
+    int aS[ 6 ] = { 2, 4, 4, 2, 24, 1 };
+    for( int i = 0; i < 6 && argc > 4 + i; i++ )
+        aS[ i ] = atoi( argv[ 4 + i ] );
+    KswCppParam<5> xParam( aS[ 0 ], aS[ 1 ], aS[ 2 ], aS[ 3 ], aS[ 4 ], aS[ 5 ] );
     KswLog xLog;
     AlignedMemoryManager xMem;
     pKswLog = &xLog;

@@ -180,3 +180,32 @@ def test_extension_only_band_limited_falls_back(gpu_ctx):
 
 def test_extension_only_long_int32_mode(gpu_ctx):
     check_extension_only(gpu_ctx, _ext_pairs(6, 83, 3000, 20000, 21000, 0.05))
+
+
+@pytest.mark.parametrize("name", ["bwa_like", "swapped", "large", "early_return"])
+def test_golden_reference_vectors_with_other_scores(name):
+    """Non-default KswCppParam<5> (ParameterSetManager: Match / Mismatch / Gap / Extend / Gap2 / Extend2) against vectors
+    written by the compiled reference: BWA-like costs, the q2 + e2 < q + e swap (whose row-0 H keeps the pre-swap
+    q + e, kswcpp_core.h:338/247), scores beyond the 8-bit range of the packed mode, the early return. All fields and
+    CIGARs, plus the early-stop mode of the extensions (max, position, CIGAR)."""
+    g = np.load(os.path.join(H.GOLDEN, "ksw_golden_%s.npz" % name))
+    d = {"ksw_calls": g["calls"].astype(np.int64), "ksw_seq": g["seq"], "ksw_cigar": g["cigar"]}
+    sc = [int(x) for x in g["score"]]
+    calls = list(H.split_ksw_dump(d))
+    ctx = api.Context(0)
+    p = api.preset("default")
+    p.match, p.mismatch, p.gap, p.extend, p.gap2, p.extend2 = sc
+    ctx.set_params(p)
+    tasks, seq = api.pack_ksw_tasks([(f["w"], f["zdrop"], f["flag"], q, t) for f, q, t, c in calls])
+    for ext_only in (False, True):
+        ctx.ksw_set_extension_only(ext_only)
+        res, cig = ctx.ksw_batch(tasks, seq)
+        for i, (f, q, t, c) in enumerate(calls):
+            is_ext = bool(f["flag"] & 0x40)
+            if ext_only and not is_ext:
+                continue
+            for k in (["max", "max_q", "max_t", "n_cigar"] if ext_only else FIELDS):
+                assert int(res[k][i]) == f[k], (name, ext_only, i, k, int(res[k][i]), f[k], f)
+            got = cig[res["cigar_off"][i]:res["cigar_off"][i] + res["n_cigar"][i]]
+            assert np.array_equal(got, c), (name, ext_only, i, f)
+    ctx.close()

@@ -50,3 +50,26 @@ def test_oracle_matches_live_reference(tmp_path):
     for f, q, t, c in H.split_ksw_dump(H.load_dump(str(tmp_path / "k.dump"))):
         res, cig, _ = H.oracle_ksw(q, t, f["w"], f["zdrop"], f["flag"])
         assert all(res[k] == f[k] for k in res) and np.array_equal(cig, c)
+
+
+SCORE_SETS = ["bwa_like", "swapped", "large", "early_return"]
+
+
+def golden_calls_for(name):
+    g = np.load(os.path.join(H.GOLDEN, "ksw_golden_%s.npz" % name))
+    d = {"ksw_calls": g["calls"].astype(np.int64), "ksw_seq": g["seq"], "ksw_cigar": g["cigar"]}
+    return [int(x) for x in g["score"]], list(H.split_ksw_dump(d))
+
+
+@pytest.mark.parametrize("name", SCORE_SETS)
+def test_oracle_matches_reference_golden_with_other_scores(name):
+    """Non-default KswCppParam<5> (tests/golden/make_golden_ksw.py SCORE_SETS, written by the compiled reference):
+    BWA-like one-piece costs, the q2 + e2 < q + e swap, scores beyond the 8-bit difference range, the early return."""
+    sc, calls = golden_calls_for(name)
+    score = H.OracleScore(*sc)
+    assert len(calls) > 250
+    for f, q, t, c in calls:
+        res, cig, _ = H.oracle_ksw(q, t, f["w"], f["zdrop"], f["flag"], score)
+        for k, v in res.items():
+            assert v == f[k], (name, k, v, f)
+        assert np.array_equal(cig, c)
