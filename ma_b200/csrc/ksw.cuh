@@ -724,7 +724,7 @@ __device__ __forceinline__ bool ksw_rows_p2x2( const KswScore& P, const SeqAcces
             inited_end += 32;
         }
         unsigned short fcA = fc3, fcB = fc3;
-        if( r <= P.long_thres )
+        if( r == 0 || r <= P.long_thres ) // (a negative threshold, q2 + e2 < q + e, still has the row-0 value)
         {
             fcA = r == 0 ? fc0 : r < P.long_thres ? fc1 : fc2;
             fcB = r + 1 < P.long_thres ? fc1 : r + 1 == P.long_thres ? fc2 : fc3;
