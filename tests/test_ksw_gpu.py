@@ -209,3 +209,30 @@ def test_golden_reference_vectors_with_other_scores(name):
             got = cig[res["cigar_off"][i]:res["cigar_off"][i] + res["n_cigar"][i]]
             assert np.array_equal(got, c), (name, ext_only, i, f)
     ctx.close()
+
+
+def test_random_score_sets_vs_oracle():
+    """Random scoring parameters (the oracle is pinned to the reference for such sets in test_ksw_oracle.py): every field
+    and CIGAR, and the early-stop mode of the extensions."""
+    from test_ksw_oracle import random_score_sets
+    for i, sc in enumerate(random_score_sets(14, 77)):
+        pairs = dpgen.random_pairs(50, seed=3000 + i, lengths=(1, 2, 3, 8, 17, 33, 50, 100, 150, 300, 700))
+        pairs += dpgen.sweep_pairs(4, 110, 512, dpgen.EXT, 0.03, seed=i) + dpgen.sweep_pairs(4, 110, 512, dpgen.EXT_RIGHT, 0.03, seed=50 + i)
+        score = H.OracleScore(*sc)
+        ctx = api.Context(0)
+        p = api.preset("default")
+        p.match, p.mismatch, p.gap, p.extend, p.gap2, p.extend2 = sc
+        ctx.set_params(p)
+        tasks, seq = api.pack_ksw_tasks(pairs)
+        exp = [H.oracle_ksw(q, t, w, zd, fl, score) for w, zd, fl, q, t in pairs]
+        for ext_only in (False, True):
+            ctx.ksw_set_extension_only(ext_only)
+            res, cig = ctx.ksw_batch(tasks, seq)
+            for k, ((w, zd, fl, q, t), (e, ecig, _)) in enumerate(zip(pairs, exp)):
+                if ext_only and not (fl & 0x40):
+                    continue
+                for name in (["max", "max_q", "max_t", "n_cigar"] if ext_only else FIELDS):
+                    assert int(res[name][k]) == e[name], (sc, ext_only, k, name, int(res[name][k]), e[name], len(q), len(t), w, zd, fl)
+                got = cig[res["cigar_off"][k]:res["cigar_off"][k] + res["n_cigar"][k]]
+                assert np.array_equal(got, ecig), (sc, ext_only, k)
+        ctx.close()

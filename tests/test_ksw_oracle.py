@@ -73,3 +73,22 @@ def test_oracle_matches_reference_golden_with_other_scores(name):
         for k, v in res.items():
             assert v == f[k], (name, k, v, f)
         assert np.array_equal(cig, c)
+
+
+def random_score_sets(n, seed):
+    rng = np.random.default_rng(seed)
+    return [(int(rng.integers(1, 7)), int(rng.integers(1, 11)), int(rng.integers(0, 13)), int(rng.integers(1, 5)),
+             int(rng.integers(0, 41)), int(rng.integers(1, 4))) for _ in range(n)]
+
+
+@pytest.mark.skipif(not H.have_ref(), reason="compiled reference (oracle/_ref) not present")
+def test_oracle_matches_live_reference_random_scores(tmp_path):
+    """Random KswCppParam<5> sets (gap 0, e == e2, q2 < q, match up to 6 ...) against the reference run here."""
+    for i, sc in enumerate(random_score_sets(10, 5)):
+        pairs = dpgen.random_pairs(40, seed=1000 + i, lengths=(1, 2, 3, 8, 17, 33, 50, 100, 150, 300))
+        H.write_pairs(str(tmp_path / "p.txt"), pairs)
+        H.run_ref("ksw", tmp_path / "p.txt", tmp_path / "k.dump", *sc)
+        score = H.OracleScore(*sc)
+        for f, q, t, c in H.split_ksw_dump(H.load_dump(str(tmp_path / "k.dump"))):
+            res, cig, _ = H.oracle_ksw(q, t, f["w"], f["zdrop"], f["flag"], score)
+            assert all(res[k] == f[k] for k in res) and np.array_equal(cig, c), (sc, f)
