@@ -44,6 +44,12 @@ extern "C" void ma_oracle_set_overrides( const int* p )
     for( int i = 0; i < 5; i++ )
         g_aiOverride[ i ] = p ? p[ i ] : -1;
 }
+// "Minimum Genome Size for Heuristics" (parameter.h:873); negative keeps the preset's 10 M
+static long long g_iMinGenomeSize = -1;
+extern "C" void ma_oracle_set_min_genome_size( long long v )
+{
+    g_iMinGenomeSize = v;
+}
 
 extern "C" int ma_oracle_align_dump( const char* prefix, const char* reads_txt, const char* preset, const char* out,
                                      long long srand_base, int stages, char* err, int errcap )
@@ -55,6 +61,8 @@ extern "C" int ma_oracle_align_dump( const char* prefix, const char* reads_txt, 
         Params P;
         if( !P.preset( preset ) )
             throw std::runtime_error( "unknown preset" );
+        if( g_iMinGenomeSize >= 0 )
+            P.genome_size_disable = g_iMinGenomeSize;
         if( g_aiOverride[ 0 ] >= 0 )
             P.bandwidth_ext = g_aiOverride[ 0 ];
         if( g_aiOverride[ 1 ] >= 0 )

@@ -130,6 +130,10 @@ static void selectPreset( ParameterSetManager& rP, std::string sPreset )
     for( auto& c : sPreset )
         c = std::tolower( c );
     rP.setSelected( sPreset );
+    // MA_REF_MIN_GENOME_SIZE: "Minimum Genome Size for Heuristics" (parameter.h:873, default 10 M): 0 switches the
+    // heuristics for large genomes (seeding drop-off, SoC minimal length) on for the small golden genome
+    if( const char* pMin = getenv( "MA_REF_MIN_GENOME_SIZE" ) )
+        rP.getSelected( )->xGenomeSizeDisable->set( atoi( pMin ) );
 }
 
 static int cmdIndex( int argc, char** argv )

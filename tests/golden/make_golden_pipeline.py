@@ -20,6 +20,8 @@ import helpers as H  # noqa: E402
 from ma_b200 import synth  # noqa: E402
 
 SRAND = 1000
+HEURISTIC_RUNS = [("illumina", "gold_reads_short.txt"), ("illuminapaired", "gold_reads_pairs.txt"),
+                  ("pacbio", "gold_reads_long.txt")]
 
 
 def main():
@@ -70,6 +72,22 @@ def main():
             H.run_ref("sam", os.path.join(H.GOLDEN, "gold"), os.path.join(H.GOLDEN, rf), preset,
                       os.path.join(H.GOLDEN, "gold_%s.sam" % preset), SRAND)
         print(preset, {k: len(v) for k, v in d.items() if k.endswith("_off")})
+    # the heuristics for large genomes (seeding drop-off binarySeeding.cpp:172-175, SoC minimal length
+    # stripOfConsideration.cpp:21-23) are off for a genome below "Minimum Genome Size for Heuristics" (10 M): these
+    # sets switch them on for the small golden genome, which is how BASELINE's 100 Mbp configuration runs
+    for preset, rf in HEURISTIC_RUNS:
+        out = os.path.join(H.GOLDEN, "tmp.dump")
+        os.environ["MA_REF_MIN_GENOME_SIZE"] = "0"
+        try:
+            H.run_ref("align", os.path.join(H.GOLDEN, "gold"), os.path.join(H.GOLDEN, rf), preset, out, SRAND)
+        finally:
+            del os.environ["MA_REF_MIN_GENOME_SIZE"]
+        d = H.load_dump(out)
+        os.remove(out)
+        comp = {k: (v.astype(np.uint8) if k == "ksw_seq" else v.astype(np.uint32) if k == "ksw_cigar" else v)
+                for k, v in d.items()}
+        np.savez_compressed(os.path.join(H.GOLDEN, "gold_%s_heur.npz" % preset), **comp)
+        print(preset, "heuristics on", {k: len(v) for k, v in d.items() if k.endswith("_off")})
 
 
 if __name__ == "__main__":

@@ -109,9 +109,12 @@ def write_pairs(path: str, pairs) -> None:
 
 
 def oracle_align_dump(prefix: str, reads_txt: str, preset: str, out: str, srand_base: int = -1, stages: int = 5,
-                      overrides=None):
-    """overrides: dict with any of bandwidth_ext, zdrop, padding, max_gap_area, min_bandwidth_gap."""
+                      overrides=None, min_genome_size: int = -1):
+    """overrides: dict with any of bandwidth_ext, zdrop, padding, max_gap_area, min_bandwidth_gap;
+    min_genome_size: "Minimum Genome Size for Heuristics" (-1: the preset's 10 M)."""
     lib = oracle_lib()
+    lib.ma_oracle_set_min_genome_size.argtypes = [ctypes.c_longlong]
+    lib.ma_oracle_set_min_genome_size(min_genome_size)
     keys = ["bandwidth_ext", "zdrop", "padding", "max_gap_area", "min_bandwidth_gap"]
     ov = (ctypes.c_int * 5)(*[int((overrides or {}).get(k, -1)) for k in keys])
     lib.ma_oracle_set_overrides(ov)

@@ -22,6 +22,16 @@ def test_oracle_pipeline_matches_reference_golden(preset, tmp_path):
         assert np.array_equal(o[k], gold[k]), k
 
 
+@pytest.mark.parametrize("preset", ["illumina", "illuminapaired", "pacbio"])
+def test_oracle_pipeline_matches_reference_golden_with_large_genome_heuristics(preset, tmp_path):
+    """ "Minimum Genome Size for Heuristics" = 0: seeding drop-off and SoC minimal length active (gold_<preset>_heur.npz)."""
+    gold = PC.load_gold(preset + "_heur")
+    o = H.oracle_align_dump(PC.GOLD_PREFIX, PC.gold_reads(preset), preset, str(tmp_path / "o.dump"), PC.SRAND, 5,
+                            min_genome_size=0)
+    for k in gold:
+        assert np.array_equal(o[k], gold[k]), k
+
+
 @pytest.mark.skipif(not H.have_ref(), reason="compiled reference (oracle/_ref) not present")
 def test_oracle_matches_live_reference_multi_contig(tmp_path):
     g = synth.random_genome([120_000, 40_000], 11)

@@ -56,6 +56,30 @@ def test_mapping_quality_and_pairing_match_reference_golden(preset, gold_index):
     ctx.close()
 
 
+@pytest.mark.parametrize("preset", ["illumina", "illuminapaired", "pacbio"])
+def test_large_genome_heuristics_match_reference_golden(preset, gold_index):
+    """The heuristics that only run for genomes above "Minimum Genome Size for Heuristics" (10 M; seeding drop-off,
+    SoC minimal length) — i.e. on BASELINE's 100 Mbp configuration — switched on for the golden genome by setting that
+    parameter to 0 (tests/golden/gold_<preset>_heur.npz, written by the compiled reference): every stage, mapping
+    quality and pairing."""
+    ctx = api.Context(0, preset)
+    p = api.preset(preset)
+    p.srand_base = PC.SRAND
+    p.genome_size_disable = 0
+    ctx.set_params(p)
+    ctx.index_upload(gold_index)
+    gold = PC.load_gold(preset + "_heur")
+    base = PC.load_gold(preset)
+    assert len(gold["seg"]) < len(base["seg"]) or len(gold["soc"]) < len(base["soc"])  # the heuristics do bite
+    reads = PC.read_reads_txt(PC.gold_reads(preset))
+    got = PC.gpu_stage_dump(ctx, reads)
+    PC.assert_same_stages(got, gold, what=preset + " heuristics")
+    mq = PC.gpu_mapq_dump(ctx, reads, p)
+    for k in ("mq_off", "mq", "pr_off", "pr"):
+        assert np.array_equal(mq[k], gold[k]), (preset, k)
+    ctx.close()
+
+
 def test_gpu_index_build_is_bit_identical(gold_index):
     ctx = make_ctx("illumina")
     ctx.index_build(gold_index.forward_codes(), gold_index.contig_start, gold_index.contig_len)
