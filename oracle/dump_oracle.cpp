@@ -6,6 +6,7 @@
 #include <cstring>
 #include <fstream>
 #include <list>
+#include <sstream>
 #include <stdexcept>
 
 using namespace oracle;
@@ -44,6 +45,42 @@ extern "C" void ma_oracle_set_overrides( const int* p )
     for( int i = 0; i < 5; i++ )
         g_aiOverride[ i ] = p ? p[ i ] : -1;
 }
+// parameters of the preset by the names of ma_oracle.h's Params ("name=value;name=value"), applied after the preset
+static std::string g_sParamSet;
+extern "C" void ma_oracle_set_params( const char* p )
+{
+    g_sParamSet = p ? p : "";
+}
+static void applyParamSet( Params& P )
+{
+    std::stringstream xS( g_sParamSet );
+    std::string sItem;
+    while( std::getline( xS, sItem, ';' ) )
+    {
+        const size_t uiEq = sItem.find( '=' );
+        if( uiEq == std::string::npos )
+            continue;
+        const std::string n = sItem.substr( 0, uiEq );
+        const double v = atof( sItem.c_str( ) + uiEq + 1 );
+#define MA_SET( field )                                                                                                \
+    if( n == #field )                                                                                                  \
+    {                                                                                                                  \
+        P.field = (decltype( P.field ))v;                                                                              \
+        continue;                                                                                                      \
+    }
+        MA_SET( seeding_technique ) MA_SET( min_seed_length ) MA_SET( min_ambiguity ) MA_SET( max_ambiguity )
+        MA_SET( seed_drop_min_size ) MA_SET( seed_drop_factor ) MA_SET( max_num_soc ) MA_SET( min_num_soc )
+        MA_SET( soc_width ) MA_SET( soc_score_drop ) MA_SET( harm_score_min ) MA_SET( harm_score_min_rel )
+        MA_SET( score_diff_tolerance ) MA_SET( max_score_lookahead ) MA_SET( switch_qlen ) MA_SET( max_delta_dist )
+        MA_SET( min_delta_dist ) MA_SET( optimistic_gap_estimation ) MA_SET( gap_cost_cutting ) MA_SET( max_gap_area )
+        MA_SET( genome_size_disable ) MA_SET( disable_heuristics ) MA_SET( padding ) MA_SET( bandwidth_ext )
+        MA_SET( min_bandwidth_gap ) MA_SET( zdrop ) MA_SET( report_n ) MA_SET( min_alignment_score )
+        MA_SET( max_supplementary_per_prim ) MA_SET( max_overlap_supplementary ) MA_SET( paired_mean )
+        MA_SET( paired_std ) MA_SET( paired_bonus )
+#undef MA_SET
+        throw std::runtime_error( "ma_oracle_set_params: unknown parameter " + n );
+    }
+}
 // "Minimum Genome Size for Heuristics" (parameter.h:873); negative keeps the preset's 10 M
 static long long g_iMinGenomeSize = -1;
 extern "C" void ma_oracle_set_min_genome_size( long long v )
@@ -63,6 +100,7 @@ extern "C" int ma_oracle_align_dump( const char* prefix, const char* reads_txt, 
             throw std::runtime_error( "unknown preset" );
         if( g_iMinGenomeSize >= 0 )
             P.genome_size_disable = g_iMinGenomeSize;
+        applyParamSet( P );
         if( g_aiOverride[ 0 ] >= 0 )
             P.bandwidth_ext = g_aiOverride[ 0 ];
         if( g_aiOverride[ 1 ] >= 0 )

@@ -22,6 +22,7 @@
 //   ref_dump bench <prefix> <reads.txt> <preset> <threads> [srand_base]
 //        times the five modules over all reads with <threads> host threads; prints one JSON line.
 //   ref_dump kswbench <pairs.txt> <threads> <repeat>
+#include <sstream>
 #include "ma/container/fMIndex.h"
 #include "ma/container/pack.h"
 #include "ma/module/binarySeeding.h"
@@ -134,6 +135,20 @@ static void selectPreset( ParameterSetManager& rP, std::string sPreset )
     // heuristics for large genomes (seeding drop-off, SoC minimal length) on for the small golden genome
     if( const char* pMin = getenv( "MA_REF_MIN_GENOME_SIZE" ) )
         rP.getSelected( )->xGenomeSizeDisable->set( atoi( pMin ) );
+    // MA_REF_SET="Name=value;Name=value": parameters of the selected presetting by their reference names, set the way
+    // the reference's CLI does it (cmdMa.cpp:347-358: byName( ... )->setByText( ... ))
+    if( const char* pSet = getenv( "MA_REF_SET" ) )
+    {
+        std::stringstream xS( pSet );
+        std::string sItem;
+        while( std::getline( xS, sItem, ';' ) )
+        {
+            const size_t uiEq = sItem.find( '=' );
+            if( uiEq == std::string::npos )
+                continue;
+            rP.getSelected( )->byName( sItem.substr( 0, uiEq ) )->setByText( sItem.substr( uiEq + 1 ) );
+        }
+    }
 }
 
 static int cmdIndex( int argc, char** argv )

@@ -109,10 +109,14 @@ def write_pairs(path: str, pairs) -> None:
 
 
 def oracle_align_dump(prefix: str, reads_txt: str, preset: str, out: str, srand_base: int = -1, stages: int = 5,
-                      overrides=None, min_genome_size: int = -1):
+                      overrides=None, min_genome_size: int = -1, params=None):
     """overrides: dict with any of bandwidth_ext, zdrop, padding, max_gap_area, min_bandwidth_gap;
-    min_genome_size: "Minimum Genome Size for Heuristics" (-1: the preset's 10 M)."""
+    min_genome_size: "Minimum Genome Size for Heuristics" (-1: the preset's 10 M);
+    params: dict of ma_b200_params field names -> values applied after the preset (PARAM_NAMES maps them to the
+    reference's parameter names)."""
     lib = oracle_lib()
+    lib.ma_oracle_set_params.argtypes = [ctypes.c_char_p]
+    lib.ma_oracle_set_params(";".join("%s=%r" % kv for kv in (params or {}).items()).encode())
     lib.ma_oracle_set_min_genome_size.argtypes = [ctypes.c_longlong]
     lib.ma_oracle_set_min_genome_size(min_genome_size)
     keys = ["bandwidth_ext", "zdrop", "padding", "max_gap_area", "min_bandwidth_gap"]
@@ -126,3 +130,37 @@ def oracle_align_dump(prefix: str, reads_txt: str, preset: str, out: str, srand_
     if rc != 0:
         raise RuntimeError("oracle: " + err.value.decode())
     return load_dump(out)
+
+
+# ma_b200_params field -> the reference's parameter name (libs/ms/inc/ms/util/parameter.h:621-880)
+PARAM_NAMES = {
+    "seeding_technique": "Seeding Technique", "min_seed_length": "Minimal Seed Length",
+    "max_ambiguity": "Maximal Ambiguity", "seed_drop_min_size": "Seeding Drop-off A - Minimal Seed Size",
+    "seed_drop_factor": "Seeding Drop-off B - Factor", "max_num_soc": "Maximal Number of SoCs",
+    "min_num_soc": "Minimal Number of SoCs", "soc_score_drop": "SoC Score Drop-off",
+    "harm_score_min": "Minimal Harmonization Score", "harm_score_min_rel": "Relative Minimal Harmonization Score",
+    "score_diff_tolerance": "Harmonization Drop-off A - Score Difference",
+    "max_score_lookahead": "Harmonization Drop-off B - Lookahead",
+    "switch_qlen": "Harmonization Score Drop-off - Minimal Query Length",
+    "max_delta_dist": "Artifact Filter A - Maximal Delta Distance",
+    "min_delta_dist": "Artifact Filter B - Minimal Delta Distance",
+    "optimistic_gap_estimation": "Pick Local Seed Set B - Optimistic Gap Estimation",
+    "gap_cost_cutting": "Pick Local Seed Set A - Enabled", "max_gap_area": "Maximal Gap Size",
+    "genome_size_disable": "Minimum Genome Size for Heuristics", "disable_heuristics": "Disable All Heuristics",
+    "padding": "Padding", "bandwidth_ext": "Bandwidth for Extensions", "min_bandwidth_gap": "Minimal Bandwidth in Gaps",
+    "zdrop": "Z Drop", "report_n": "Maximal Number of Reported Alignments",
+    "min_alignment_score": "Minimal Alignment Score", "max_supplementary_per_prim": "Number Supplementary Alignments",
+    "max_overlap_supplementary": "Maximal Supplementary Overlap", "paired_mean": "Mean Distance of Paired Reads",
+    "paired_std": "Standard Deviation of Paired Reads", "paired_bonus": "Score Factor for Paired Reads",
+}
+
+
+def ref_param_env(params: dict) -> dict:
+    """Environment for `ref_dump` that sets the same parameters on the reference (MA_REF_SET, by reference name)."""
+    def text(k, v):
+        if k == "seeding_technique":
+            return "1" if v else "0"  # a choice parameter: index into { maxSpan, SMEMs, MEMs }
+        if k in ("disable_heuristics", "optimistic_gap_estimation", "gap_cost_cutting"):
+            return "true" if v else "false"
+        return repr(v)
+    return {"MA_REF_SET": ";".join("%s=%s" % (PARAM_NAMES[k], text(k, v)) for k, v in params.items())}

@@ -156,3 +156,24 @@ def mismatching_reads(got, exp):
         if len(ga) != len(ea) or not np.array_equal(ga, ea):
             bad += 1
     return bad
+
+
+# Parameter variations of the presets (ma_b200_params field names) that change at least one stage's output on the
+# golden reads. test_pipeline_cpu.py pins the oracle to the LIVE reference for each of them (where /root/reference
+# exists), test_pipeline_gpu.py compares the device path with the oracle. "genome_size_disable": 0 switches the
+# large-genome heuristics on (they are off below 10 M bases).
+_H = {"genome_size_disable": 0}
+PARAM_VARIATIONS = [
+    ("illumina", {"min_seed_length": 10}), ("illumina", {"min_seed_length": 25}),
+    ("illumina", {"max_num_soc": 1, "min_num_soc": 1}), ("illumina", {"seeding_technique": 0}),
+    ("pacbio", {"seeding_technique": 1}), ("illumina", dict(_H, harm_score_min=40)),
+    ("illumina", dict(_H, harm_score_min_rel=0.2)), ("illumina", dict(_H, seed_drop_min_size=30, seed_drop_factor=0.05)),
+    ("illumina", dict(_H, disable_heuristics=1)), ("illumina", dict(_H, max_ambiguity=1)),
+    ("pacbio", dict(_H, max_ambiguity=1)), ("pacbio", dict(_H, min_num_soc=1, max_num_soc=1)),
+    ("pacbio", dict(_H, harm_score_min=200)), ("pacbio", {"max_gap_area": 200}), ("illumina", {"max_gap_area": 0}),
+    ("illumina", {"padding": 50}), ("pacbio", {"bandwidth_ext": 64, "zdrop": 50}), ("illumina", {"report_n": 1}),
+    ("illumina", {"min_alignment_score": 10, "max_supplementary_per_prim": 3, "max_overlap_supplementary": 0.5}),
+    ("illuminapaired", {"paired_mean": 300.0, "paired_std": 20.0, "paired_bonus": 2.0}),
+    ("illumina", dict(_H, soc_score_drop=0.9, switch_qlen=10, score_diff_tolerance=0.5, max_score_lookahead=1)),
+    ("pacbio", dict(_H, max_delta_dist=0.01, min_delta_dist=100, gap_cost_cutting=0, optimistic_gap_estimation=0)),
+]

@@ -33,6 +33,25 @@ def test_oracle_pipeline_matches_reference_golden_with_large_genome_heuristics(p
 
 
 @pytest.mark.skipif(not H.have_ref(), reason="compiled reference (oracle/_ref) not present")
+@pytest.mark.parametrize("preset,params", PC.PARAM_VARIATIONS, ids=lambda v: v if isinstance(v, str) else "-".join(v))
+def test_oracle_matches_live_reference_parameter_variations(preset, params, tmp_path):
+    """Parameters of the presetting set on the reference the way its CLI does (byName()->setByText(), MA_REF_SET in
+    oracle/ref_dump.cpp) and on the oracle: every dumped stage identical."""
+    env = dict(os.environ)
+    env.update(H.ref_param_env(params))
+    out = str(tmp_path / "r.dump")
+    subprocess.check_call([H.REF_DUMP, "align", PC.GOLD_PREFIX, PC.gold_reads(preset), preset, out, str(PC.SRAND)], env=env)
+    ref = H.load_dump(out)
+    o = H.oracle_align_dump(PC.GOLD_PREFIX, PC.gold_reads(preset), preset, str(tmp_path / "o.dump"), PC.SRAND, 5,
+                            params=params)
+    base = PC.load_gold(preset)
+    assert any(not np.array_equal(ref[k], base[k]) for k in ("seg", "seed", "soc", "harmseed", "aln", "mq", "pr")), \
+        "the variation does not change anything"
+    for k in ref:
+        assert np.array_equal(o[k], ref[k]), k
+
+
+@pytest.mark.skipif(not H.have_ref(), reason="compiled reference (oracle/_ref) not present")
 def test_oracle_matches_live_reference_multi_contig(tmp_path):
     g = synth.random_genome([120_000, 40_000], 11)
     synth.write_genome_txt(str(tmp_path / "g.txt"), g)

@@ -80,6 +80,30 @@ def test_large_genome_heuristics_match_reference_golden(preset, gold_index):
     ctx.close()
 
 
+@pytest.mark.parametrize("preset,params", PC.PARAM_VARIATIONS, ids=lambda v: v if isinstance(v, str) else "-".join(v))
+def test_parameter_variations_against_oracle(preset, params, gold_index, tmp_path):
+    """Non-preset values of the presetting's parameters (seeding, SoC, harmonization heuristics, DP, reporting, pairing):
+    every stage, mapping quality and pairing against the oracle, which test_pipeline_cpu.py pins to the live reference
+    for the same variations."""
+    ctx = api.Context(0, preset)
+    p = api.preset(preset)
+    p.srand_base = PC.SRAND
+    for k, v in params.items():
+        assert hasattr(p, k), k
+        setattr(p, k, v)
+    ctx.set_params(p)
+    ctx.index_upload(gold_index)
+    exp = H.oracle_align_dump(PC.GOLD_PREFIX, PC.gold_reads(preset), preset, str(tmp_path / "o.dump"), PC.SRAND, 5,
+                              params=params)
+    reads = PC.read_reads_txt(PC.gold_reads(preset))
+    got = PC.gpu_stage_dump(ctx, reads)
+    PC.assert_same_stages(got, exp, what="%s %s" % (preset, params))
+    mq = PC.gpu_mapq_dump(ctx, reads, p)
+    for k in ("mq_off", "mq", "pr_off", "pr"):
+        assert np.array_equal(mq[k], exp[k]), (preset, params, k)
+    ctx.close()
+
+
 def test_gpu_index_build_is_bit_identical(gold_index):
     ctx = make_ctx("illumina")
     ctx.index_build(gold_index.forward_codes(), gold_index.contig_start, gold_index.contig_len)
