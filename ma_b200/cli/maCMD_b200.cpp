@@ -13,6 +13,8 @@
 //   --Verbose          prints the busy time of the host stages
 //   --Detect_Small_Inversions [true|false], --Z_Drop_Inversions <n>   the reference's parameters of that name:
 //                      SmallInversions between MappingQuality and the writer (unpaired input only)
+//   --Use_M_in_CIGAR [true|false], --Soft_clip, --Omit_Secondary_Alignments, --Omit_Supplementary_Alignments
+//                      the writers' flags of the reference (default: M CIGARs, hard clips, everything written)
 //   --Interleaved      with a paired presetting and no -m: reads 2k, 2k+1 of -i are mates (not in the reference)
 //   --Devices <a,b,..> CUDA devices (default 0). The index is replicated on every device, batches go to whichever device
 //                      is free, no collective is involved; the output order does not depend on it
@@ -146,6 +148,7 @@ int main( int argc, char** argv )
     size_t uiBatch = 500000;
     uint32_t uiSrand = 0;
     bool bInterleaved = false, bVerbose = false, bInversions = false;
+    bool bOutputM = true, bSoftClip = false, bNoSecondary = false, bNoSupplementary = false;
     int iZDropInversion = 100;
     size_t uiThreads = (size_t)std::max( 1, (int)std::thread::hardware_concurrency( ) - 3 ); // reader, device, writer
     try
@@ -182,6 +185,15 @@ int main( int argc, char** argv )
             }
             else if( sLow == "--z_drop_inversions" )
                 iZDropInversion = atoi( value( ).c_str( ) );
+            else if( sLow == "--use_m_in_cigar" || sLow == "--soft_clip" || sLow == "--omit_secondary_alignments" ||
+                     sLow == "--omit_supplementary_alignments" )
+            { // the writers' flags (parameter.h:726-755); an explicit true / false may follow
+                bool bValue = true;
+                if( i + 1 < argc && ( lower( argv[ i + 1 ] ) == "true" || lower( argv[ i + 1 ] ) == "false" ) )
+                    bValue = lower( argv[ ++i ] ) == "true";
+                ( sLow == "--use_m_in_cigar" ? bOutputM : sLow == "--soft_clip" ? bSoftClip
+                  : sLow == "--omit_secondary_alignments" ? bNoSecondary : bNoSupplementary ) = bValue;
+            }
             else if( sLow == "--device" || sLow == "--devices" )
             {
                 vDevices.clear( );
@@ -226,7 +238,7 @@ int main( int argc, char** argv )
         FILE* pOut = sOut.empty( ) ? stdout : fopen( sOut.c_str( ), "wb" );
         if( !pOut )
             throw std::runtime_error( "Unable to open file " + sOut );
-        SamWriter xWriter( xAligner.index( ).xContigs );
+        SamWriter xWriter( xAligner.index( ).xContigs, bOutputM, bSoftClip, bNoSecondary, bNoSupplementary );
         const std::string sHead = xWriter.header( );
         fwrite( sHead.data( ), 1, sHead.size( ), pOut );
 

@@ -146,7 +146,14 @@ static void selectPreset( ParameterSetManager& rP, std::string sPreset )
             const size_t uiEq = sItem.find( '=' );
             if( uiEq == std::string::npos )
                 continue;
-            rP.getSelected( )->byName( sItem.substr( 0, uiEq ) )->setByText( sItem.substr( uiEq + 1 ) );
+            auto pParam = rP.getSelected( )->byName( sItem.substr( 0, uiEq ) );
+            const std::string sValue = sItem.substr( uiEq + 1 );
+            // flags are set directly: the reference's text conversion returns true for "false" as well
+            // (libs/ms/src/util/parameter.cpp:40-43), so that its CLI can only switch flags on
+            if( auto pFlag = std::dynamic_pointer_cast<AlignerParameter<bool>>( pParam ) )
+                pFlag->set( sValue == "true" );
+            else
+                pParam->setByText( sValue );
         }
     }
 }

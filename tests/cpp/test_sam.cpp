@@ -1,6 +1,6 @@
 // CPU test of include/ma_b200_sam.hpp: reads the reported alignments of every read / pair as text (produced from the
 // golden dumps of the compiled reference by tests/test_sam_writer.py) and prints the SAM file.
-//   test_sam <index prefix> <paired 0|1> < records
+//   test_sam <index prefix> <paired 0|1> [<use M 0|1> <soft clip 0|1> <omit secondary 0|1> <omit supplementary 0|1>] < records
 // records:  Q <name> <sequence>      one per read, in read order
 //           A <unit> <first 0|1> <begin_q> <end_q> <begin_ref> <end_ref> <score> <length> <sec> <supp> <mapq bits> <type:len>...
 //           (unit = read index, or pair index for paired output; records of a unit in result-vector order)
@@ -48,7 +48,8 @@ int main( int argc, char** argv )
             xUnits[ uiUnit ].push_back( a );
         }
     }
-    SamWriter xW( xC );
+    auto flag = [ & ]( int i, bool bDefault ) { return argc > i ? atoi( argv[ i ] ) != 0 : bDefault; };
+    SamWriter xW( xC, flag( 3, true ), flag( 4, false ), flag( 5, false ), flag( 6, false ) );
     std::string sOut = xW.header( );
     if( bPaired )
         for( size_t p = 0; 2 * p + 1 < vQ.size( ); p++ )

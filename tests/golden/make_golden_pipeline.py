@@ -20,6 +20,10 @@ import helpers as H  # noqa: E402
 from ma_b200 import synth  # noqa: E402
 
 SRAND = 1000
+SAM_OPTION_RUNS = [("illumina", "gold_reads_short.txt", "x_soft", "Use M in CIGAR=false;Soft clip=true"),
+                   ("illuminapaired", "gold_reads_pairs.txt", "nosec_soft",
+                    "Omit Secondary Alignments=true;Omit Supplementary Alignments=true;Soft clip=true"),
+                   ("pacbio", "gold_reads_long.txt", "x_nosupp", "Use M in CIGAR=false;Omit Supplementary Alignments=true")]
 HEURISTIC_RUNS = [("illumina", "gold_reads_short.txt"), ("illuminapaired", "gold_reads_pairs.txt"),
                   ("pacbio", "gold_reads_long.txt")]
 
@@ -72,6 +76,14 @@ def main():
             H.run_ref("sam", os.path.join(H.GOLDEN, "gold"), os.path.join(H.GOLDEN, rf), preset,
                       os.path.join(H.GOLDEN, "gold_%s.sam" % preset), SRAND)
         print(preset, {k: len(v) for k, v in d.items() if k.endswith("_off")})
+    # SAM text with non-default writer options (MA_REF_SET in oracle/ref_dump.cpp sets them on the presetting)
+    for preset, rf, tag, opts in SAM_OPTION_RUNS:
+        os.environ["MA_REF_SET"] = opts
+        try:
+            H.run_ref("sam", os.path.join(H.GOLDEN, "gold"), os.path.join(H.GOLDEN, rf), preset,
+                      os.path.join(H.GOLDEN, "gold_%s_%s.sam" % (preset, tag)), SRAND)
+        finally:
+            del os.environ["MA_REF_SET"]
     # the heuristics for large genomes (seeding drop-off binarySeeding.cpp:172-175, SoC minimal length
     # stripOfConsideration.cpp:21-23) are off for a genome below "Minimum Genome Size for Heuristics" (10 M): these
     # sets switch them on for the small golden genome, which is how BASELINE's 100 Mbp configuration runs

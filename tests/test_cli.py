@@ -126,3 +126,16 @@ def test_cli_gzip_input(tmp_path):
     out = subprocess.check_output([exe, "-x", PC.GOLD_PREFIX, "-i", str(f), "-p", "Illumina_Paired", "--Interleaved",
                                    "--Srand", str(PC.SRAND)])
     assert out.decode() == open(os.path.join(H.GOLDEN, "gold_fq_illuminapaired.sam")).read()
+
+
+@pytest.mark.gpu
+def test_cli_writer_flags(tmp_path):
+    """--Use_M_in_CIGAR false --Soft_clip == the reference's FileWriter with those flags (gold_illumina_x_soft.sam)."""
+    exe = build_cli()
+    fa = tmp_path / "r.fa"
+    with open(fa, "w") as f:
+        for i, l in enumerate(x.strip() for x in open(PC.gold_reads("illumina")) if x.strip()):
+            f.write(">r%d\n%s\n" % (i, l))
+    out = subprocess.check_output([exe, "-x", PC.GOLD_PREFIX, "-i", str(fa), "-p", "Illumina", "--Srand", str(PC.SRAND),
+                                   "--Use_M_in_CIGAR", "false", "--Soft_clip"])
+    assert out.decode() == open(os.path.join(H.GOLDEN, "gold_illumina_x_soft.sam")).read()

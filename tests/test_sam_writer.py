@@ -107,3 +107,23 @@ def test_read_parser_reads_gzip_input(tmp_path):
         g.write(open(os.path.join(H.GOLDEN, "gold_reads.fq"), "rb").read())
     got = subprocess.check_output([exe, str(f)]).decode()
     assert got == open(os.path.join(H.GOLDEN, "gold_reads_fq.parsed")).read()
+
+
+@pytest.mark.parametrize("preset,tag,flags", [("illumina", "x_soft", [0, 1, 0, 0]),
+                                               ("illuminapaired", "nosec_soft", [1, 1, 1, 1]),
+                                               ("pacbio", "x_nosupp", [0, 0, 0, 1])])
+def test_sam_writer_options_match_reference_writers(tmp_path, preset, tag, flags):
+    """The writers' options ("Use M in CIGAR" off -> =/X, "Soft clip", "Omit Secondary / Supplementary Alignments"):
+    tests/golden/gold_<preset>_<tag>.sam written by the reference's FileWriter / PairedFileWriter with them set."""
+    exe = str(tmp_path / "test_sam")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(H.ROOT, "tests", "cpp", "test_sam.cpp"),
+                           "-L" + os.path.join(H.ROOT, "ma_b200"), "-lma_b200",
+                           "-Wl,-rpath," + os.path.join(H.ROOT, "ma_b200")])
+    paired = preset == "illuminapaired"
+    got = subprocess.run([exe, PC.GOLD_PREFIX, "1" if paired else "0"] + [str(f) for f in flags],
+                         input=records(preset, paired).encode(), capture_output=True, check=True).stdout.decode()
+    exp = open(os.path.join(H.GOLDEN, "gold_%s_%s.sam" % (preset, tag))).read()
+    gl, el = got.splitlines(), exp.splitlines()
+    for i, (a, b) in enumerate(zip(gl, el)):
+        assert a == b, (i, a[:160], b[:160])
+    assert len(gl) == len(el)
