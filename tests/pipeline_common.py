@@ -177,3 +177,39 @@ PARAM_VARIATIONS = [
     ("illumina", dict(_H, soc_score_drop=0.9, switch_qlen=10, score_diff_tolerance=0.5, max_score_lookahead=1)),
     ("pacbio", dict(_H, max_delta_dist=0.01, min_delta_dist=100, gap_cost_cutting=0, optimistic_gap_estimation=0)),
 ]
+
+
+def repeat_rich_genome(seed=31):
+    """Two contigs full of repeats: a tandem array of 60 diverged 300 bp units, 40 interspersed exact copies (and
+    reverse complements) of a 120 bp unit, a dinucleotide repeat and a homopolymer. Reads from it carry hundreds of
+    ambiguous seeds: long std::sort / heap runs with many equal keys (SURVEY.md A-6), overlapping SoC windows."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+
+    def mutate(u, rate):
+        u = u.copy()
+        m = rng.random(len(u)) < rate
+        u[m] = (u[m] + rng.integers(1, 4, m.sum())) & 3
+        return u
+
+    unit = rng.integers(0, 4, 300).astype(np.uint8)
+    c1 = [rng.integers(0, 4, 5000).astype(np.uint8)] + [mutate(unit, 0.02) for _ in range(60)]
+    c1.append(rng.integers(0, 4, 5000).astype(np.uint8))
+    unit2 = rng.integers(0, 4, 120).astype(np.uint8)
+    c2 = []
+    for k in range(40):
+        c2.append(rng.integers(0, 4, int(rng.integers(200, 600))).astype(np.uint8))
+        c2.append(unit2 if k % 3 else (3 - unit2[::-1]).astype(np.uint8))
+    c2.append(np.tile(np.array([0, 1], dtype=np.uint8), 200))
+    c2.append(np.zeros(300, dtype=np.uint8))
+    c2.append(rng.integers(0, 4, 3000).astype(np.uint8))
+    return [np.concatenate(c1), np.concatenate(c2)]
+
+
+REPEAT_RUNS = [("illumina", False), ("default", False), ("pacbio", True), ("nanopore", True)]
+
+
+def repeat_rich_reads(genome, long_reads):
+    from ma_b200 import synth
+    if long_reads:
+        return synth.simulate_long_reads(genome, 10, 3000, 33)[0]
+    return synth.simulate_reads(genome, 500, 150, 32, sub_rate=0.01, ins_rate=0.002, del_rate=0.002)[0]

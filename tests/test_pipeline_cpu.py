@@ -65,6 +65,23 @@ def test_oracle_matches_live_reference_multi_contig(tmp_path):
         assert np.array_equal(o[k], r[k]), k
 
 
+@pytest.mark.skipif(not H.have_ref(), reason="compiled reference (oracle/_ref) not present")
+@pytest.mark.parametrize("preset,long_reads", PC.REPEAT_RUNS)
+def test_oracle_matches_live_reference_repeat_rich(preset, long_reads, tmp_path):
+    """Reads with hundreds of ambiguous seeds (tandem / interspersed / low-complexity repeats): tie order of the
+    reference's std::sort and heap operations, overlapping SoC windows, ambiguity limits."""
+    g = PC.repeat_rich_genome()
+    synth.write_genome_txt(str(tmp_path / "g.txt"), g)
+    H.run_ref("index", tmp_path / "g.txt", tmp_path / "g")
+    synth.write_reads_txt(str(tmp_path / "r.txt"), PC.repeat_rich_reads(g, long_reads))
+    H.run_ref("align", tmp_path / "g", tmp_path / "r.txt", preset, tmp_path / "r.dump", PC.SRAND)
+    r = H.load_dump(str(tmp_path / "r.dump"))
+    assert int(np.diff(r["seed_off"]).max()) > 100
+    o = H.oracle_align_dump(str(tmp_path / "g"), str(tmp_path / "r.txt"), preset, str(tmp_path / "o.dump"), PC.SRAND, 5)
+    for k in r:
+        assert np.array_equal(o[k], r[k]), k
+
+
 def test_hostsim_device_routines_match_oracle():
     """The MA_HD routines that the kernels wrap (seeding, SoC/harmonization, NW glue, exact std::sort/heap), compiled
     for the host, against the oracle."""

@@ -251,6 +251,25 @@ def test_config1_scale_against_oracle(tmp_path):
     ctx.close()
 
 
+@pytest.mark.parametrize("preset,long_reads", PC.REPEAT_RUNS)
+def test_repeat_rich_genome_against_oracle(preset, long_reads, tmp_path):
+    """Repeat-rich genome (tests/pipeline_common.py repeat_rich_genome; the oracle is pinned to the live reference on it
+    in test_pipeline_cpu.py): GPU-built index, reads with up to several hundred seeds, every stage."""
+    g = PC.repeat_rich_genome()
+    lens = np.array([len(c) for c in g], dtype=np.int64)
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    ctx = make_ctx(preset)
+    ctx.index_build(np.concatenate(g), starts, lens)
+    index.store_index(ctx.index_download(["chr1", "chr2"]), str(tmp_path / "g"))
+    reads = PC.repeat_rich_reads(g, long_reads)
+    synth.write_reads_txt(str(tmp_path / "r.txt"), reads)
+    exp = H.oracle_align_dump(str(tmp_path / "g"), str(tmp_path / "r.txt"), preset, str(tmp_path / "o.dump"), PC.SRAND, 5)
+    assert int(np.diff(exp["seed_off"]).max()) > 100
+    got = PC.gpu_stage_dump(ctx, reads, keep_segments=8192 if long_reads else 4096)
+    PC.assert_same_stages(got, exp, what="repeat-rich " + preset)
+    ctx.close()
+
+
 def test_long_reads_against_oracle(tmp_path):
     """PacBio preset (maxSpan seeding, long banded DP incl. the 1024-column window): 30 x 4 kbp reads, 12 % error."""
     g = synth.random_genome([400_000, 200_000], 21)
