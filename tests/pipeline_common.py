@@ -213,3 +213,35 @@ def repeat_rich_reads(genome, long_reads):
     if long_reads:
         return synth.simulate_long_reads(genome, 10, 3000, 33)[0]
     return synth.simulate_reads(genome, 500, 150, 32, sub_rate=0.01, ins_rate=0.002, del_rate=0.002)[0]
+
+
+RAGGED_LENGTHS = [17, 18, 20, 35, 50, 75, 100, 151, 250, 400, 799, 800, 801, 1200, 2000]
+
+
+def ragged_reads(fwd, seed=41):
+    """Reads of many lengths from the golden genome (both strands, 2 % substitutions, a few indels): minimal seed
+    length, the 800-base switch of the harmonization heuristics, reads longer than the DP padding."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = []
+    for L in RAGGED_LENGTHS:
+        for k in range(6):
+            p = int(rng.integers(0, len(fwd) - L - 5))
+            r = fwd[p:p + L].copy()
+            m = rng.random(L) < 0.02
+            r[m] = (r[m] + rng.integers(1, 4, m.sum())) & 3
+            if L > 40 and k % 3 == 1:
+                c = int(rng.integers(10, L - 10))
+                r = np.delete(r, c)
+            if L > 40 and k % 3 == 2:
+                c = int(rng.integers(10, L - 10))
+                r = np.insert(r, c, rng.integers(0, 4, 2))
+            if k % 2:
+                r = (3 - r[::-1]).astype(np.uint8)
+            out.append(r.astype(np.uint8))
+    return out
+
+
+def write_ragged_txt(path, reads):
+    with open(path, "w") as f:
+        for r in reads:
+            f.write("".join("ACGTN"[c] for c in r) + "\n")

@@ -82,6 +82,19 @@ def test_oracle_matches_live_reference_repeat_rich(preset, long_reads, tmp_path)
         assert np.array_equal(o[k], r[k]), k
 
 
+@pytest.mark.skipif(not H.have_ref(), reason="compiled reference (oracle/_ref) not present")
+@pytest.mark.parametrize("preset", ["illumina", "default", "nanopore"])
+def test_oracle_matches_live_reference_ragged_read_lengths(preset, tmp_path):
+    """Read lengths from 17 to 2000 in one batch (PC.RAGGED_LENGTHS)."""
+    reads = PC.ragged_reads(index.load_index(PC.GOLD_PREFIX).forward_codes())
+    PC.write_ragged_txt(str(tmp_path / "r.txt"), reads)
+    H.run_ref("align", PC.GOLD_PREFIX, tmp_path / "r.txt", preset, tmp_path / "r.dump", PC.SRAND)
+    r = H.load_dump(str(tmp_path / "r.dump"))
+    o = H.oracle_align_dump(PC.GOLD_PREFIX, str(tmp_path / "r.txt"), preset, str(tmp_path / "o.dump"), PC.SRAND, 5)
+    for k in r:
+        assert np.array_equal(o[k], r[k]), k
+
+
 def test_hostsim_device_routines_match_oracle():
     """The MA_HD routines that the kernels wrap (seeding, SoC/harmonization, NW glue, exact std::sort/heap), compiled
     for the host, against the oracle."""

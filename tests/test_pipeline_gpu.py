@@ -270,6 +270,23 @@ def test_repeat_rich_genome_against_oracle(preset, long_reads, tmp_path):
     ctx.close()
 
 
+@pytest.mark.parametrize("preset", ["illumina", "default", "nanopore"])
+def test_ragged_read_lengths_against_oracle(preset, gold_index, tmp_path):
+    """Read lengths from 17 to 2000 in one batch: minimal seed length, the 800-base switch of the harmonization
+    heuristics, reads longer than the DP padding (oracle pinned to the live reference in test_pipeline_cpu.py)."""
+    reads = PC.ragged_reads(gold_index.forward_codes())
+    PC.write_ragged_txt(str(tmp_path / "r.txt"), reads)
+    exp = H.oracle_align_dump(PC.GOLD_PREFIX, str(tmp_path / "r.txt"), preset, str(tmp_path / "o.dump"), PC.SRAND, 5)
+    ctx = make_ctx(preset)
+    ctx.index_upload(gold_index)
+    got = PC.gpu_stage_dump(ctx, reads, keep_segments=8192)
+    PC.assert_same_stages(got, exp, what="ragged " + preset)
+    mq = PC.gpu_mapq_dump(ctx, reads, api.preset(preset))
+    for k in ("mq_off", "mq"):
+        assert np.array_equal(mq[k], exp[k]), (preset, k)
+    ctx.close()
+
+
 def test_long_reads_against_oracle(tmp_path):
     """PacBio preset (maxSpan seeding, long banded DP incl. the 1024-column window): 30 x 4 kbp reads, 12 % error."""
     g = synth.random_genome([400_000, 200_000], 21)
