@@ -95,6 +95,25 @@ def test_oracle_matches_live_reference_ragged_read_lengths(preset, tmp_path):
         assert np.array_equal(o[k], r[k]), k
 
 
+@pytest.mark.skipif(not H.have_ref(), reason="compiled reference (oracle/_ref) not present")
+def test_oracle_matches_live_reference_above_heuristics_threshold(tmp_path):
+    """A 12 Mbp genome (24 M-base text > "Minimum Genome Size for Heuristics"): the large-genome heuristics run
+    without any parameter override, as on BASELINE's configurations; paired Illumina reads, every stage."""
+    g = synth.random_genome([6_000_000] * 2, 7)
+    synth.write_genome_txt(str(tmp_path / "g.txt"), g)
+    H.run_ref("index", tmp_path / "g.txt", tmp_path / "g")
+    m1, m2, *_ = synth.simulate_pairs(g, 1500, 150, 2017)
+    reads = np.empty((3000, 150), dtype=np.uint8)
+    reads[0::2], reads[1::2] = m1, m2
+    synth.write_reads_txt(str(tmp_path / "r.txt"), reads)
+    H.run_ref("align", tmp_path / "g", tmp_path / "r.txt", "illuminapaired", tmp_path / "r.dump", PC.SRAND)
+    r = H.load_dump(str(tmp_path / "r.dump"))
+    o = H.oracle_align_dump(str(tmp_path / "g"), str(tmp_path / "r.txt"), "illuminapaired", str(tmp_path / "o.dump"),
+                            PC.SRAND, 5)
+    for k in r:
+        assert np.array_equal(o[k], r[k]), k
+
+
 def test_hostsim_device_routines_match_oracle():
     """The MA_HD routines that the kernels wrap (seeding, SoC/harmonization, NW glue, exact std::sort/heap), compiled
     for the host, against the oracle."""
