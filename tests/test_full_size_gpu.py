@@ -137,3 +137,15 @@ def test_full_size_sample_against_oracle(workload, tmp_path):
     for k in ("mq_off", "mq", "pr_off", "pr"):
         assert np.array_equal(mq[k], exp[k]), k
     ctx.close()
+    # ... and, without the oracle in between, what the UNMODIFIED reference produced for these reads on the index of its
+    # own builder (tests/golden/make_golden_full_size.py): SHA-1 of every stage's dump
+    import hashlib
+    import json
+    import os
+    pin = json.load(open(os.path.join(H.GOLDEN, "full_size_sample_sha1.json")))
+    assert pin["n_reads"] == n and pin["srand_base"] == PC.SRAND
+    if bad == 0:
+        got.update(mq)
+        for k, h in pin["sha1"].items():
+            mine = hashlib.sha1(np.ascontiguousarray(np.asarray(got[k], dtype=np.int64)).tobytes()).hexdigest()
+            assert mine == h, "stage %s differs from the reference's dump" % k
