@@ -1,6 +1,7 @@
 """Pins the BASELINE.json configs[1] workload to the UNMODIFIED reference: builds the index of the 100 Mbp synthetic
 genome with the reference's own builder (bwtLarge, ~2 min), runs its modules over the first 3 000 reads of the
-1 M simulated pairs (Illumina_Paired preset, srand(1000 + read index)) and stores the SHA-1 of every stage's dump in
+1 M simulated pairs (Illumina_Paired preset, srand(1000 + read index)) and over 200 simulated 10 kbp PacBio reads
+(PacBio preset) and stores the SHA-1 of every stage's dump in
 tests/golden/full_size_sample_sha1.json. tests/test_full_size_gpu.py compares the device path with these hashes.
 
 Run in the build container (needs /root/reference -> `make -C oracle ref`):  python tests/golden/make_golden_full_size.py
@@ -38,8 +39,15 @@ def main():
         H.run_ref("align", os.path.join(d, "g"), os.path.join(d, "r.txt"), "illuminapaired", os.path.join(d, "r.dump"),
                   PC.SRAND)
         r = H.load_dump(os.path.join(d, "r.dump"))
+        # configs[3]-shaped: 200 simulated PacBio reads of 10 kbp (12 % error) on the same index, PacBio preset
+        long_reads, *_ = synth.simulate_long_reads(genome, 200, 10000, 4)
+        synth.write_reads_txt(os.path.join(d, "l.txt"), long_reads)
+        H.run_ref("align", os.path.join(d, "g"), os.path.join(d, "l.txt"), "pacbio", os.path.join(d, "l.dump"), PC.SRAND)
+        rl = H.load_dump(os.path.join(d, "l.dump"))
     out = {"n_reads": N_READS, "srand_base": PC.SRAND,
-           "sha1": {k: sha1(r[k]) for k in PC.STAGE_KEYS + ["mq_off", "mq", "pr_off", "pr"]}}
+           "sha1": {k: sha1(r[k]) for k in PC.STAGE_KEYS + ["mq_off", "mq", "pr_off", "pr"]},
+           "pacbio": {"n_reads": 200, "read_len": 10000, "seed": 4,
+                      "sha1": {k: sha1(rl[k]) for k in PC.STAGE_KEYS + ["mq_off", "mq"]}}}
     with open(os.path.join(H.GOLDEN, "full_size_sample_sha1.json"), "w") as f:
         json.dump(out, f, indent=1)
     print(out)

@@ -151,3 +151,28 @@ def test_full_size_sample_against_oracle(workload, tmp_path):
             mine = hashlib.sha1(np.ascontiguousarray(np.asarray(got[k], dtype=np.int64)).tobytes()).hexdigest()
             assert mine == h, "stage %s differs from the reference's dump" % k
         print("full-size sample: all %d stage dumps hash-identical to the unmodified reference" % len(pin["sha1"]))
+
+
+@pytest.mark.gpu
+def test_full_size_pacbio_sample_against_reference(workload):
+    """configs[3]-shaped long reads (200 x 10 kbp, 12 % error, PacBio preset) on the 100 Mbp index: every stage and the
+    mapping qualities hash-identical to the unmodified reference's dumps (tests/golden/full_size_sample_sha1.json)."""
+    import hashlib
+    import json
+    import os
+    import helpers as H
+    import pipeline_common as PC
+    genome, _, _, lens, starts = workload
+    pin = json.load(open(os.path.join(H.GOLDEN, "full_size_sample_sha1.json")))["pacbio"]
+    reads, *_ = synth.simulate_long_reads(genome, pin["n_reads"], pin["read_len"], pin["seed"])
+    ctx = api.Context(0, "pacbio")
+    p = api.preset("pacbio")
+    p.srand_base = PC.SRAND
+    ctx.set_params(p)
+    ctx.index_build(np.concatenate(genome), starts, lens.tolist())
+    got = PC.gpu_stage_dump(ctx, reads, keep_segments=16384)
+    got.update(PC.gpu_mapq_dump(ctx, reads, p))
+    ctx.close()
+    diff = [k for k, h in pin["sha1"].items()
+            if hashlib.sha1(np.ascontiguousarray(np.asarray(got[k], dtype=np.int64)).tobytes()).hexdigest() != h]
+    assert not diff, diff
