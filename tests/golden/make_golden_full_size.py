@@ -39,6 +39,10 @@ def main():
         H.run_ref("align", os.path.join(d, "g"), os.path.join(d, "r.txt"), "illuminapaired", os.path.join(d, "r.dump"),
                   PC.SRAND)
         r = H.load_dump(os.path.join(d, "r.dump"))
+        # the SAM file of the reference's PairedFileWriter for the same reads (named r<i>)
+        H.run_ref("sam", os.path.join(d, "g"), os.path.join(d, "r.txt"), "illuminapaired", os.path.join(d, "r.sam"),
+                  PC.SRAND)
+        sam = open(os.path.join(d, "r.sam"), "rb").read()
         # configs[3]-shaped: 200 simulated PacBio reads of 10 kbp (12 % error) on the same index, PacBio preset
         long_reads, *_ = synth.simulate_long_reads(genome, 200, 10000, 4)
         synth.write_reads_txt(os.path.join(d, "l.txt"), long_reads)
@@ -46,6 +50,7 @@ def main():
         rl = H.load_dump(os.path.join(d, "l.dump"))
     out = {"n_reads": N_READS, "srand_base": PC.SRAND,
            "sha1": {k: sha1(r[k]) for k in PC.STAGE_KEYS + ["mq_off", "mq", "pr_off", "pr"]},
+           "sam_sha1": hashlib.sha1(sam).hexdigest(), "sam_lines": sam.count(b"\n"),
            "pacbio": {"n_reads": 200, "read_len": 10000, "seed": 4,
                       "sha1": {k: sha1(rl[k]) for k in PC.STAGE_KEYS + ["mq_off", "mq"]}}}
     with open(os.path.join(H.GOLDEN, "full_size_sample_sha1.json"), "w") as f:

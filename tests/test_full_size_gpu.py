@@ -176,3 +176,33 @@ def test_full_size_pacbio_sample_against_reference(workload):
     diff = [k for k, h in pin["sha1"].items()
             if hashlib.sha1(np.ascontiguousarray(np.asarray(got[k], dtype=np.int64)).tobytes()).hexdigest() != h]
     assert not diff, diff
+
+
+@pytest.mark.gpu
+def test_full_size_cli_sam_against_reference(workload, tmp_path):
+    """End to end on the BASELINE configuration: index files written from the GPU-built index, the first 3 000 reads as
+    FASTA, maCMD_b200 -> SAM; the file is byte-identical (SHA-1) to the one the unmodified reference's FileReader-free
+    harness + PairedFileWriter wrote for the index of its own builder."""
+    import hashlib
+    import json
+    import os
+    import subprocess
+    import helpers as H
+    import pipeline_common as PC
+    from ma_b200 import index
+    genome, reads, _, lens, starts = workload
+    pin = json.load(open(os.path.join(H.GOLDEN, "full_size_sample_sha1.json")))
+    n = pin["n_reads"]
+    ctx = api.Context(0, "illumina_paired")
+    ctx.index_build(np.concatenate(genome), starts, lens.tolist())
+    index.store_index(ctx.index_download(["chr%d" % (i + 1) for i in range(len(lens))]), str(tmp_path / "g"))
+    ctx.close()
+    with open(tmp_path / "r.fa", "w") as f:
+        for i in range(n):
+            f.write(">r%d\n%s\n" % (i, "".join("ACGT"[c] for c in reads[i])))
+    cli = os.path.join(H.ROOT, "ma_b200", "cli", "maCMD_b200")
+    subprocess.check_call(["make", "-s", "-C", os.path.dirname(cli)])
+    out = subprocess.check_output([cli, "-x", str(tmp_path / "g"), "-i", str(tmp_path / "r.fa"), "-p", "Illumina_Paired",
+                                   "--Interleaved", "--Srand", str(pin["srand_base"]), "--Batch", "1024"])
+    assert out.count(b"\n") == pin["sam_lines"]
+    assert hashlib.sha1(out).hexdigest() == pin["sam_sha1"]
