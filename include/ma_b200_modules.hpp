@@ -23,6 +23,7 @@
 #include <stdexcept>
 #include <limits>
 #include <string>
+#include <tuple>
 #include <utility>
 #include <vector>
 
@@ -759,6 +760,92 @@ class SmallInversions
     }
 };
 
+// PairedReads::execute (pairedReads.cpp:15-121) on the host, for graphs that run a host module between MappingQuality
+// and PairedReads (SmallInversions, export.cpp:176-184); the device stage (PairedReads above) is the fast path.
+// Restated with the reference's own runtime facilities: std::sort on the tuples (unstable, like the reference's),
+// float arithmetic for the pair's mapping quality.
+class PairedReadsHost
+{
+    const ma_b200_params& P;
+    const int64_t iForwardLength;
+
+  public:
+    PairedReadsHost( const ParameterSetManager& rParameters, const FMIndex& rIdx )
+        : P( rParameters.xParams ), iForwardLength( rIdx.xContigs.iForwardLength )
+    {}
+    std::vector<Alignment> execute( const NucSeq& q1, const NucSeq& q2, std::vector<Alignment> v1,
+                                    std::vector<Alignment> v2 ) const
+    {
+        for( auto& a : v1 )
+            a.bFirst = true;
+        for( auto& a : v2 )
+            a.bFirst = false;
+        if( v1.empty( ) )
+            return v2;
+        if( v2.empty( ) )
+            return v1;
+        const size_t uiMean = (size_t)P.paired_mean;
+        auto onReverse = [ & ]( nucSeqIndex p ) { return p >= (nucSeqIndex)iForwardLength; };
+        std::vector<std::tuple<int64_t, bool, size_t, size_t>> vScores;
+        for( size_t i = 0; i < v1.size( ); i++ )
+        {
+            if( v1[ i ].uiLength == 0 )
+                continue;
+            for( size_t j = 0; j < v2.size( ); j++ )
+            {
+                if( v2[ j ].uiLength == 0 )
+                    continue;
+                int64_t iScore = v1[ i ].score( ) + v2[ j ].score( );
+                bool bIsPaired = false;
+                if( onReverse( v1[ i ].uiBeginOnRef ) != onReverse( v2[ j ].uiBeginOnRef ) )
+                {
+                    const nucSeqIndex uiP1 = v1[ i ].uiBeginOnRef;
+                    const nucSeqIndex uiP2 = 2 * (nucSeqIndex)iForwardLength - ( v2[ j ].uiBeginOnRef + 1 );
+                    const nucSeqIndex d = uiP1 < uiP2 ? uiP2 - uiP1 : uiP1 - uiP2;
+                    if( ( (double)d ) >= ( (double)uiMean ) - P.paired_std * 3 &&
+                        ( (double)d ) <= ( (double)uiMean ) + P.paired_std * 3 )
+                    {
+                        iScore = (int64_t)( iScore * P.paired_bonus );
+                        bIsPaired = true;
+                    }
+                }
+                vScores.emplace_back( iScore, bIsPaired, i, j );
+            }
+        }
+        std::sort( vScores.begin( ), vScores.end( ),
+                   []( const std::tuple<int64_t, bool, size_t, size_t>& rtA,
+                       const std::tuple<int64_t, bool, size_t, size_t>& rtB ) {
+                       if( std::get<0>( rtA ) == std::get<0>( rtB ) )
+                           return std::get<1>( rtA ) && !std::get<1>( rtB );
+                       return std::get<0>( rtA ) > std::get<0>( rtB );
+                   } );
+        Alignment& a1 = v1[ std::get<2>( vScores[ 0 ] ) ];
+        Alignment& a2 = v2[ std::get<3>( vScores[ 0 ] ) ];
+        a1.bSecondary = a2.bSecondary = false;
+        a1.bSupplementary = a2.bSupplementary = false;
+        if( std::get<1>( vScores[ 0 ] ) && vScores.size( ) > 1 )
+        {
+            float fMapQ = ( (float)( std::get<0>( vScores[ 0 ] ) - std::get<0>( vScores[ 1 ] ) ) ) / std::get<0>( vScores[ 0 ] );
+            auto numSeeds = []( const Alignment& a ) {
+                size_t n = 0;
+                for( auto& d : a.data )
+                    n += d.first == MatchType::seed;
+                return n;
+            };
+            if( numSeeds( a1 ) <= 1 && numSeeds( a2 ) <= 1 )
+                fMapQ /= 2;
+            if( a1.score( ) >= P.match * q1.length( ) * 0.8 && v1.size( ) >= 3 )
+                fMapQ *= 2;
+            else if( a2.score( ) >= P.match * q2.length( ) * 0.8 && v2.size( ) >= 3 )
+                fMapQ *= 2;
+            if( fMapQ > 1 )
+                fMapQ = 1;
+            a1.fMappingQuality = fMapQ, a2.fMappingQuality = fMapQ;
+        }
+        return { a1, a2 };
+    }
+};
+
 // The batched graph: what setUpCompGraph / setUpCompGraphPaired (export.cpp:72-202) wire per thread, executed for a
 // whole batch on one GPU.
 class Aligner
@@ -795,16 +882,31 @@ class Aligner
     std::vector<std::vector<Alignment>> report( const std::vector<NucSeq>& vReads,
                                                 ma_b200_align_stats* pStats = nullptr )
     {
+        if( xParams.bSearchInversions )
+            return reportWithInversions( vReads );
         const RawReport xRaw = reportRaw( vReads, pStats );
         std::vector<std::vector<Alignment>> vRet( xRaw.units( ) );
         for( size_t i = 0; i < vRet.size( ); i++ )
             vRet[ i ] = xRaw.records( i );
-        if( xParams.bSearchInversions )
-        { // "Detect Small Inversions": SmallInversions between MappingQuality and the writer (export.cpp:109-112)
-            if( xRaw.bPaired )
-                throw std::runtime_error( "Detect Small Inversions is not supported together with Use Paired Reads" );
-            return SmallInversions( xParams ).execute( xIndex, vRet, vReads );
-        }
+        return vRet;
+    }
+    // "Detect Small Inversions": MappingQuality on the device, SmallInversions (host glue, DP on the device) per read,
+    // then the writer's input: those vectors (export.cpp:109-112) or, for paired reads, PairedReads of the two mates'
+    // vectors on the host (export.cpp:176-184)
+    std::vector<std::vector<Alignment>> reportWithInversions( const std::vector<NucSeq>& vReads )
+    {
+        const bool bPaired = xParams.xParams.use_paired_reads != 0;
+        if( bPaired && vReads.size( ) % 2 )
+            throw std::runtime_error( "PairedReads: the batch must hold the mates interleaved (2k, 2k+1)" );
+        ParameterSetManager xUnpaired = xParams;
+        xUnpaired.xParams.use_paired_reads = 0;
+        auto vInv = SmallInversions( xParams ).execute( xIndex, MappingQuality( xUnpaired ).execute( xIndex, vReads ), vReads );
+        if( !bPaired )
+            return vInv;
+        std::vector<std::vector<Alignment>> vRet( vReads.size( ) / 2 );
+        PairedReadsHost xPairing( xParams, xIndex );
+        for( size_t p = 0; p < vRet.size( ); p++ )
+            vRet[ p ] = xPairing.execute( vReads[ 2 * p ], vReads[ 2 * p + 1 ], vInv[ 2 * p ], vInv[ 2 * p + 1 ] );
         return vRet;
     }
     // the same result as the C ABI delivers it (record arrays of the whole batch); RawReport::records( i ) converts

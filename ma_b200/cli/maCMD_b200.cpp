@@ -12,7 +12,7 @@
 //   -t                 host threads that format SAM records (default: all but three; the alignment itself runs on the GPU)
 //   --Verbose          prints the busy time of the host stages
 //   --Detect_Small_Inversions [true|false], --Z_Drop_Inversions <n>   the reference's parameters of that name:
-//                      SmallInversions between MappingQuality and the writer (unpaired input only)
+//                      SmallInversions between MappingQuality and the writer / PairedReads (then paired on the host)
 //   --Use_M_in_CIGAR [true|false], --Soft_clip, --Omit_Secondary_Alignments, --Omit_Supplementary_Alignments
 //                      the writers' flags of the reference (default: M CIGARs, hard clips, everything written)
 //   --Interleaved      with a paired presetting and no -m: reads 2k, 2k+1 of -i are mates (not in the reference)
@@ -227,8 +227,6 @@ int main( int argc, char** argv )
         const double fStartup = std::chrono::duration<double>( std::chrono::steady_clock::now( ) - tStart ).count( );
         Aligner& xAligner = *vAligners[ 0 ];
         const bool bPaired = xAligner.params( ).xParams.use_paired_reads != 0;
-        if( bPaired && bInversions )
-            throw std::runtime_error( "--Detect_Small_Inversions is not supported together with paired reads" );
         if( bPaired && vMate.empty( ) && !bInterleaved )
             throw std::runtime_error( "paired presetting: give the mates with -m (or --Interleaved)" );
         if( uiBatch < 2 )
@@ -254,6 +252,7 @@ int main( int argc, char** argv )
             PinnedVector<int64_t> vOffsets;
             std::vector<std::string> vText; // SAM text of the batch, one piece per formatting thread
             size_t uiChunks = 0;
+            bool bHasRecords = false;
         };
         const size_t uiPool = 4 + 2 * vAligners.size( );
         BoundedQueue<std::unique_ptr<Batch>> xParsed( 2 ), xAligned( 2 + vAligners.size( ) ), xFormatted( 1 ), xFree( uiPool );
@@ -397,7 +396,7 @@ int main( int argc, char** argv )
                     xPending.erase( xPending.begin( ) );
                     uiSeq++;
                     const auto t0 = now( );
-                    const size_t uiUnits = pB->xRaw.units( );
+                    const size_t uiUnits = pB->bHasRecords ? pB->vRecords.size( ) : pB->xRaw.units( );
                     const size_t uiChunks = std::max<size_t>( 1, std::min<size_t>( uiThreads, uiUnits / 256 + 1 ) );
                     auto& vText = pB->vText; // kept with the batch: the buffers are reused
                     vText.resize( std::max( vText.size( ), uiChunks ) );
@@ -414,13 +413,13 @@ int main( int argc, char** argv )
                                 std::vector<Alignment> vScratch; // reused from unit to unit
                                 for( size_t u = uiUnits * c / uiChunks; u < uiUnits * ( c + 1 ) / uiChunks; u++ )
                                 {
-                                    if( pB->vRecords.empty( ) )
+                                    if( !pB->bHasRecords )
                                         pB->xRaw.records( u, vScratch );
+                                    const std::vector<Alignment>& vRec = pB->bHasRecords ? pB->vRecords[ u ] : vScratch;
                                     if( bPaired )
-                                        xWriter.paired( sText, pB->vReads[ 2 * u ], pB->vReads[ 2 * u + 1 ], vScratch );
+                                        xWriter.paired( sText, pB->vReads[ 2 * u ], pB->vReads[ 2 * u + 1 ], vRec );
                                     else
-                                        xWriter.single( sText, pB->vReads[ u ],
-                                                        pB->vRecords.empty( ) ? vScratch : pB->vRecords[ u ] );
+                                        xWriter.single( sText, pB->vReads[ u ], vRec );
                                 }
                             }
                             catch( ... )
@@ -485,15 +484,15 @@ int main( int argc, char** argv )
                         const auto t0 = now( );
                         vAligners[ g ]->params( ).xParams.srand_base = uiSrand + (uint32_t)pB->uiFirst;
                         ma_b200_align_stats xStats;
-                        vAligners[ g ]->reportRaw( pB->vReads.size( ), pB->vSlab.data( ), pB->vOffsets.data( ), pB->xRaw, &xStats );
+                        memset( &xStats, 0, sizeof( xStats ) );
                         pB->vRecords.clear( );
-                        if( bInversions )
-                        { // the DP of SmallInversions runs on this device as one more batch
-                            std::vector<std::vector<Alignment>> vRec( pB->xRaw.units( ) );
-                            for( size_t u = 0; u < vRec.size( ); u++ )
-                                vRec[ u ] = pB->xRaw.records( u );
-                            pB->vRecords = vAligners[ g ]->inversions( vRec, pB->vReads );
-                        }
+                        pB->bHasRecords = bInversions;
+                        if( bInversions ) // MappingQuality on the device, SmallInversions' DP as one more device batch,
+                                          // pairing (if any) on the host
+                            pB->vRecords = vAligners[ g ]->reportWithInversions( pB->vReads );
+                        else
+                            vAligners[ g ]->reportRaw( pB->vReads.size( ), pB->vSlab.data( ), pB->vOffsets.data( ), pB->xRaw,
+                                                       &xStats );
                         vGpuBusy[ g ] += secs( t0, now( ) ), vKernelMs[ g ] += xStats.ms_total;
                         if( !xAligned.push( std::move( pB ) ) )
                             break;

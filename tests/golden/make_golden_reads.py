@@ -116,6 +116,32 @@ def inversions():
               SRAND, "inv=20")
     H.run_ref("sam", os.path.join(H.GOLDEN, "gold"), fa, "illumina", os.path.join(H.GOLDEN, "gold_inv_illumina.sam"),
               SRAND, "inv")
+    # pairs (mates of 250 bases, fragments of ~500) in which one or both mates carry a seedless inversion:
+    # MappingQuality -> SmallInversions per mate -> PairedReads -> PairedFileWriter (export.cpp:176-184)
+    pairs = []
+    for k in range(16):
+        contig = k % 3
+        s0, cl = int(ix.contig_start[contig]), int(ix.contig_len[contig])
+        p = int(rng.integers(s0 + 10, s0 + cl - 700))
+        frag = g[p:p + 520].copy()
+        m1, m2 = frag[:250].copy(), rc(frag[-250:])
+        for m, has in ((m1, k % 4 != 3), (m2, k % 2 == 0)):
+            if has:
+                n = [44, 52, 60, 70][k % 4]
+                a = 125 - n // 2
+                seg = rc(m[a:a + n])
+                for j in range(int(rng.integers(6, 10)), n, 12):
+                    seg[j] = (seg[j] + 1 + int(rng.integers(0, 3))) & 3
+                m[a:a + n] = seg
+        if k % 5 == 4:
+            m1, m2 = m2, m1
+        pairs += [m1, m2]
+    fq = os.path.join(H.GOLDEN, "gold_reads_inv_pairs.fa")
+    with open(fq, "w") as f:
+        for i, r in enumerate(pairs):
+            f.write(">invpair%d/%d\n%s\n" % (i // 2, i % 2 + 1, "".join("ACGT"[c] for c in r)))
+    H.run_ref("sam", os.path.join(H.GOLDEN, "gold"), fq, "illuminapaired",
+              os.path.join(H.GOLDEN, "gold_inv_illuminapaired_z20.sam"), SRAND, "inv=20")
 
 
 if __name__ == "__main__":

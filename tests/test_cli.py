@@ -139,3 +139,19 @@ def test_cli_writer_flags(tmp_path):
     out = subprocess.check_output([exe, "-x", PC.GOLD_PREFIX, "-i", str(fa), "-p", "Illumina", "--Srand", str(PC.SRAND),
                                    "--Use_M_in_CIGAR", "false", "--Soft_clip"])
     assert out.decode() == open(os.path.join(H.GOLDEN, "gold_illumina_x_soft.sam")).read()
+
+
+@pytest.mark.gpu
+def test_cli_small_inversions_with_paired_reads(tmp_path):
+    """Paired graph with "Detect Small Inversions" (export.cpp:176-184): MappingQuality on the device, SmallInversions
+    per mate (host glue, DP on the device), PairedReads on the host (include/ma_b200_modules.hpp PairedReadsHost) — the
+    inversion records enter the pairing and the pair's mapping quality."""
+    exe = build_cli()
+    out = subprocess.check_output([exe, "-x", PC.GOLD_PREFIX, "-i", os.path.join(H.GOLDEN, "gold_reads_inv_pairs.fa"),
+                                   "-p", "Illumina_Paired", "--Interleaved", "--Srand", str(PC.SRAND),
+                                   "--Detect_Small_Inversions", "--Z_Drop_Inversions", "20", "--Batch", "10"])
+    assert out.decode() == open(os.path.join(H.GOLDEN, "gold_inv_illuminapaired_z20.sam")).read()
+    # and it differs from the run without the module (the module is not a no-op on this set)
+    plain = subprocess.check_output([exe, "-x", PC.GOLD_PREFIX, "-i", os.path.join(H.GOLDEN, "gold_reads_inv_pairs.fa"),
+                                     "-p", "Illumina_Paired", "--Interleaved", "--Srand", str(PC.SRAND)])
+    assert plain != out
