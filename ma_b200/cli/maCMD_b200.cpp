@@ -5,6 +5,8 @@
 //   maCMD_b200 -x <index prefix> -i <reads.fq[,more.fq]> [-m <mates.fq[,more.fq]>] [-o <out.sam>] [-p <presetting>]
 //
 //   -x, --Index        prefix of the reference's index files (.bwt .sa .pac .ann .amb), as written by maCMD --Create_Index
+//   -X, --Create_Index <fasta>,<folder>,<name>   builds the index on the GPU and writes the reference's index files
+//                      (genomes below 2^30 bases without N); -x also takes the <name>.json written here
 //   -i, --In           FASTA / FASTQ file(s), plain or gzip-compressed, comma separated
 //   -m, --MateIn       mate file(s); switches "Use Paired Reads" on like the reference (cmdMa.cpp:323-330)
 //   -o, --Out          SAM file (default: standard output)
@@ -29,6 +31,7 @@
 #include <cstdio>
 #include <deque>
 #include <exception>
+#include <fstream>
 #include <functional>
 #include <iostream>
 #include <map>
@@ -140,6 +143,130 @@ class ReadStream
     }
 };
 
+// --Create_Index <fasta>,<folder>,<name> (cmdMa.cpp:332-345, ExecutionContext::makeIndexAndPackForGenome,
+// execution-context.h:108-138): <folder>/<fasta stem>.{bwt,sa,pac,ann,amb} in the reference's file formats (fMIndex.h:
+// 515-599, pack.h:275-451) and <folder>/<name>.json. The index is built on the GPU (ma_b200_index_build, bit-identical
+// to the reference's FMIndex( pPack )) for genomes below 2^30 bases without N.
+static void createIndex( const std::string& sFasta, const std::string& sFolder, const std::string& sTitle, int iDevice )
+{
+    std::ifstream xIn( sFasta );
+    if( !xIn )
+        throw std::runtime_error( "Unable to open file " + sFasta );
+    std::vector<uint8_t> vFwd;
+    std::vector<std::string> vNames, vComments;
+    std::vector<int64_t> vStart, vLength;
+    std::string sLine;
+    while( std::getline( xIn, sLine ) )
+    {
+        while( !sLine.empty( ) && ( sLine.back( ) == '\r' || sLine.back( ) == ' ' ) )
+            sLine.pop_back( );
+        if( sLine.empty( ) )
+            continue;
+        if( sLine[ 0 ] == '>' )
+        {
+            const size_t uiBlank = sLine.find( ' ' );
+            vNames.push_back( sLine.substr( 1, uiBlank == std::string::npos ? std::string::npos : uiBlank - 1 ) );
+            vComments.push_back( uiBlank == std::string::npos ? "" : sLine.substr( uiBlank + 1 ) );
+            vStart.push_back( (int64_t)vFwd.size( ) ), vLength.push_back( 0 );
+            continue;
+        }
+        if( vNames.empty( ) )
+            throw std::runtime_error( sFasta + " is not a FASTA file" );
+        for( char c : sLine )
+        {
+            const int b = c == 'A' || c == 'a' ? 0 : c == 'C' || c == 'c' ? 1 : c == 'G' || c == 'g' ? 2
+                                                   : c == 'T' || c == 't' ? 3 : -1;
+            if( b < 0 )
+                throw std::runtime_error( "--Create_Index: '" + std::string( 1, c ) + "' in " + vNames.back( ) +
+                                          ": only genomes without N / IUPAC codes can be indexed here (the reference "
+                                          "replaces them by random bases and records holes)" );
+            vFwd.push_back( (uint8_t)b );
+        }
+        vLength.back( ) = (int64_t)vFwd.size( ) - vStart.back( );
+    }
+    if( vFwd.empty( ) )
+        throw std::runtime_error( "--Create_Index: no sequence in " + sFasta );
+    ma_b200_ctx* pCtx = nullptr;
+    if( ma_b200_create( iDevice, &pCtx ) != MA_B200_OK )
+        throw std::runtime_error( "ma_b200_create failed: no CUDA device (there is no CPU fallback)" );
+    auto check = [ & ]( int rc ) {
+        if( rc != MA_B200_OK )
+        {
+            const std::string sErr = ma_b200_last_error( pCtx );
+            ma_b200_destroy( pCtx );
+            throw std::runtime_error( "ma_b200: " + sErr );
+        }
+    };
+    check( ma_b200_index_build( pCtx, vFwd.data( ), (int64_t)vFwd.size( ), vStart.data( ), vLength.data( ),
+                                (int32_t)vNames.size( ) ) );
+    int64_t nWords = 0, nSa = 0, nPac = 0, iPrimary = 0, aL2[ 5 ] = { 0, 0, 0, 0, 0 };
+    check( ma_b200_index_sizes( pCtx, &nWords, &nSa, &nPac, &iPrimary, aL2 ) );
+    std::vector<uint32_t> vBwt( (size_t)nWords );
+    std::vector<int64_t> vSa( (size_t)nSa );
+    std::vector<uint8_t> vPac( (size_t)nPac );
+    check( ma_b200_index_download( pCtx, vBwt.data( ), vSa.data( ), vPac.data( ) ) );
+    ma_b200_destroy( pCtx );
+
+    std::string sStem = sFasta.substr( sFasta.find_last_of( '/' ) == std::string::npos ? 0 : sFasta.find_last_of( '/' ) + 1 );
+    if( sStem.find_last_of( '.' ) != std::string::npos )
+        sStem = sStem.substr( 0, sStem.find_last_of( '.' ) );
+    const std::string sPrefix = sFolder + "/" + sStem;
+    auto open = [ & ]( const std::string& sExt ) {
+        FILE* p = fopen( ( sPrefix + sExt ).c_str( ), "wb" );
+        if( !p )
+            throw std::runtime_error( "Unable to open file " + sPrefix + sExt );
+        return p;
+    };
+    const int64_t iFwd = (int64_t)vFwd.size( ), iRefLen = aL2[ 4 ];
+    const int32_t iSaIntv = 32;
+    FILE* p = open( ".bwt" ); // primary, L2[1..4], occurrence blocks
+    fwrite( &iPrimary, 8, 1, p ), fwrite( aL2 + 1, 8, 4, p ), fwrite( vBwt.data( ), 4, vBwt.size( ), p ), fclose( p );
+    p = open( ".sa" ); // primary, L2[1..4], interval, length, samples 1..
+    fwrite( &iPrimary, 8, 1, p ), fwrite( aL2 + 1, 8, 4, p ), fwrite( &iSaIntv, 4, 1, p ), fwrite( &iRefLen, 8, 1, p );
+    fwrite( vSa.data( ) + 1, 8, vSa.size( ) - 1, p ), fclose( p );
+    p = open( ".pac" ); // 2 bit per base, a zero byte if the length is a multiple of 4, the length modulo 4
+    fwrite( vPac.data( ), 1, (size_t)( ( iFwd + 3 ) / 4 ), p );
+    if( iFwd % 4 == 0 )
+        fputc( 0, p );
+    fputc( (int)( iFwd % 4 ), p ), fclose( p );
+    p = open( ".ann" );
+    fprintf( p, "%lld %zu %d\n", (long long)iFwd, vNames.size( ), 11 );
+    for( size_t i = 0; i < vNames.size( ); i++ )
+        fprintf( p, "0 %s %s\n%lld %lld 0\n", vNames[ i ].c_str( ), vComments[ i ].empty( ) ? "(null)" : vComments[ i ].c_str( ),
+                 (long long)vStart[ i ], (long long)vLength[ i ] );
+    fclose( p );
+    p = open( ".amb" );
+    fprintf( p, "%lld %zu 0\n", (long long)iFwd, vNames.size( ) ), fclose( p );
+    p = fopen( ( sFolder + "/" + sTitle + ".json" ).c_str( ), "wb" );
+    if( !p )
+        throw std::runtime_error( "Unable to open file " + sFolder + "/" + sTitle + ".json" );
+    fprintf( p, "{\n    \"name\": \"%s\",\n    \"prefix\": \"%s\",\n    \"type\": \"MA Genome\",\n    \"version\": {\n"
+                "        \"major\": 1,\n        \"minor\": 0\n    }\n}\n", sTitle.c_str( ), sStem.c_str( ) );
+    fclose( p );
+    std::cerr << "index of " << iFwd << " bases in " << vNames.size( ) << " sequences: " << sPrefix << ".*" << std::endl;
+}
+
+// -x <prefix> or, like the reference (ExecutionContext::loadGenome, execution-context.h:60-93), the genome's .json
+static std::string indexPrefix( const std::string& sArg )
+{
+    if( sArg.size( ) < 5 || sArg.substr( sArg.size( ) - 5 ) != ".json" )
+        return sArg;
+    std::ifstream xIn( sArg );
+    if( !xIn )
+        throw std::runtime_error( "Unable to open file " + sArg );
+    const std::string sText( ( std::istreambuf_iterator<char>( xIn ) ), std::istreambuf_iterator<char>( ) );
+    if( sText.find( "\"MA Genome\"" ) == std::string::npos )
+        throw std::runtime_error( "JSON file does not contain valid MA genome information." );
+    size_t uiAt = sText.find( "\"prefix\"" );
+    if( uiAt == std::string::npos )
+        throw std::runtime_error( "JSON file does not contain valid MA genome information." );
+    uiAt = sText.find( '"', sText.find( ':', uiAt ) );
+    const size_t uiEnd = sText.find( '"', uiAt + 1 );
+    const size_t uiSlash = sArg.find_last_of( '/' );
+    return ( uiSlash == std::string::npos ? std::string( ) : sArg.substr( 0, uiSlash + 1 ) ) +
+           sText.substr( uiAt + 1, uiEnd - uiAt - 1 );
+}
+
 int main( int argc, char** argv )
 {
     std::string sIndex, sOut, sPreset = "Default";
@@ -162,7 +289,15 @@ int main( int argc, char** argv )
                 return argv[ ++i ];
             };
             if( sOpt == "-x" || sLow == "--index" )
-                sIndex = value( );
+                sIndex = indexPrefix( value( ) );
+            else if( sOpt == "-X" || sLow == "--create_index" || sLow == "--createindex" )
+            {
+                const auto vParts = splitList( value( ) );
+                if( vParts.size( ) != 3 )
+                    throw std::runtime_error( "--Index needs exactly three parameters" );
+                createIndex( vParts[ 0 ], vParts[ 1 ], vParts[ 2 ], vDevices[ 0 ] );
+                return 0;
+            }
             else if( sOpt == "-i" || sLow == "--in" )
                 vIn = splitList( value( ) );
             else if( sOpt == "-m" || sLow == "--matein" )

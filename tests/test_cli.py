@@ -155,3 +155,30 @@ def test_cli_small_inversions_with_paired_reads(tmp_path):
     plain = subprocess.check_output([exe, "-x", PC.GOLD_PREFIX, "-i", os.path.join(H.GOLDEN, "gold_reads_inv_pairs.fa"),
                                      "-p", "Illumina_Paired", "--Interleaved", "--Srand", str(PC.SRAND)])
     assert plain != out
+
+
+@pytest.mark.gpu
+def test_cli_create_index_writes_the_reference_files(tmp_path):
+    """-X <fasta>,<folder>,<name> (cmdMa.cpp:332-345): the files of the reference's own builder for the golden genome,
+    byte for byte (.ann up to its random seed field), and -x <name>.json loads them."""
+    from ma_b200 import index
+    exe = build_cli()
+    ix = index.load_index(PC.GOLD_PREFIX)
+    fwd = ix.forward_codes()
+    with open(tmp_path / "genome.fa", "w") as f:
+        for name, s, l in zip(ix.contig_names, ix.contig_start, ix.contig_len):
+            seq = "".join("ACGT"[c] for c in fwd[int(s):int(s) + int(l)])
+            f.write(">%s synthetic\n" % name)
+            f.write("\n".join(seq[k:k + 70] for k in range(0, len(seq), 70)) + "\n")
+    subprocess.check_call([exe, "-X", "%s,%s,%s" % (tmp_path / "genome.fa", tmp_path, "gold2")])
+    for ext in (".bwt", ".sa", ".pac", ".amb"):
+        assert open(str(tmp_path / "genome") + ext, "rb").read() == open(PC.GOLD_PREFIX + ext, "rb").read(), ext
+    mine = open(str(tmp_path / "genome") + ".ann").read().split("\n")
+    ref = open(PC.GOLD_PREFIX + ".ann").read().split("\n")
+    assert mine[0].split()[:2] == ref[0].split()[:2] and mine[1:] == ref[1:]
+    out = subprocess.check_output([exe, "-x", str(tmp_path / "gold2.json"), "-i", os.path.join(H.GOLDEN, "gold_reads.fa"),
+                                   "-p", "Illumina", "--Srand", str(PC.SRAND)])
+    assert out.decode() == open(os.path.join(H.GOLDEN, "gold_fa_illumina.sam")).read()
+    r = subprocess.run([exe, "-X", "%s,%s,%s" % (os.path.join(H.GOLDEN, "gold_reads.fa"), tmp_path, "bad")],
+                       capture_output=True)
+    assert r.returncode == 1 and b"without N" in r.stderr  # IUPAC codes in that file
