@@ -94,24 +94,32 @@ def index_prefix(genome_mbp, seed):
 
 
 def ensure_index_files(genome, genome_mbp, seed, ctx=None):
-    """Index in the reference's file formats (for the reference arm / cpu_baseline). Built on the GPU when a
-    context is available (bit-identical to the reference's builder, tests/test_pipeline_gpu.py), else by ref_dump."""
+    """Index in the reference's file formats (for the reference arm / cpu_baseline). ctx is None (the reference arm):
+    built by the reference's own builder (ref_dump index), cached as <prefix>_ref. With a context (our arm's
+    cpu_baseline): that cached index if it exists, else the GPU-built one (bit-identical to the reference builder's,
+    tests/test_pipeline_gpu.py, tests/test_cli.py)."""
     prefix = index_prefix(genome_mbp, seed)
-    if all(os.path.exists(prefix + e) for e in (".bwt", ".sa", ".pac", ".ann", ".amb")):
-        return prefix, "cached"
+    exts = (".bwt", ".sa", ".pac", ".ann", ".amb")
+    if all(os.path.exists(prefix + "_ref" + e) for e in exts):
+        return prefix + "_ref", "cached, reference builder (ref_dump index)"
     os.makedirs(CACHE, exist_ok=True)
     if ctx is not None:
+        if all(os.path.exists(prefix + e) for e in exts):
+            return prefix, "cached, ma_b200_index_build"
         ix = ctx.index_download()
         tmp = prefix + ".tmp%d" % os.getpid()
         maindex.store_index(ix, tmp)
-        for e in (".bwt", ".sa", ".pac", ".ann", ".amb"):
+        for e in exts:
             os.replace(tmp + e, prefix + e)
         return prefix, "ma_b200_index_build (bit-identical to the reference builder)"
     gt = prefix + ".genome.txt"
+    tmp = prefix + "_ref.tmp%d" % os.getpid()
     synth.write_genome_txt(gt, genome)
-    subprocess.check_call([REF_DUMP, "index", gt, prefix])
+    subprocess.check_call([REF_DUMP, "index", gt, tmp], stdout=subprocess.DEVNULL)
     os.remove(gt)
-    return prefix, "reference builder (ref_dump index)"
+    for e in exts:
+        os.replace(tmp + e, prefix + "_ref" + e)
+    return prefix + "_ref", "reference builder (ref_dump index)"
 
 
 def run_reference(prefix, reads, threads, srand=-1):
@@ -160,17 +168,9 @@ def main():
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_dump not built"}))
             return 0
         genome, reads = make_workload(args.genome_mbp, max(args.cpu_sample // 2, 1), seed)
-        ctx = None
-        try:
-            from ma_b200 import api
-            ctx = api.Context(0, "illumina_paired")
-            ctx.index_build(np.concatenate(genome), np.cumsum([0] + [len(c) for c in genome[:-1]]),
-                            [len(c) for c in genome])
-        except Exception:
-            ctx = None
-        prefix, how = ensure_index_files(genome, args.genome_mbp, seed, ctx)
-        if ctx is not None:
-            ctx.close()
+        # nothing of this repository's engine on this arm: the index comes from the reference's own builder (about two
+        # minutes for 100 Mbp, cached under MA_B200_CACHE for the runs that follow on the same box)
+        prefix, how = ensure_index_files(genome, args.genome_mbp, seed, None)
         threads = os.cpu_count() or 1
         sample = reads[:args.cpu_sample]
         for _ in range(max(args.warmup, 0) and 1):
