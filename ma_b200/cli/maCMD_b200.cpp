@@ -400,35 +400,38 @@ int main( int argc, char** argv )
             return std::chrono::duration<double>( b - a ).count( );
         };
 
-        std::thread xReader( [ & ]( ) {
+        // reader, first half: the serial pass over the line ends that finds the records of a batch (the mate file on
+        // its own thread); it runs ahead of the conversion of the previous batch
+        struct ScanJob
+        {
+            std::vector<ReadStream::Record> vRecords;
+            std::vector<std::shared_ptr<ReadParser>> vKeepAlive, vKeepAliveMate;
+        };
+        BoundedQueue<std::unique_ptr<ScanJob>> xScanned( 2 );
+        std::exception_ptr pScanError;
+        double fScan = 0;
+        std::thread xScanner( [ & ]( ) {
             try
             {
                 ReadStream xIn( vIn ), xMate( vMate );
-                std::vector<ReadStream::Record> vRecords, vFirst, vSecond;
-                std::vector<std::shared_ptr<ReadParser>> vKeepAlive, vKeepAliveMate;
-                const size_t uiParseThreads = std::max<size_t>( 1, std::min<size_t>( 4, uiThreads / 3 ) );
-                size_t uiDone = 0, uiSeq = 0;
+                std::vector<ReadStream::Record> vFirst, vSecond;
+                auto scan = []( ReadStream& rStream, std::vector<ReadStream::Record>& vOut, size_t uiMax,
+                                std::vector<std::shared_ptr<ReadParser>>& vKeep ) {
+                    vOut.clear( );
+                    ReadStream::Record xR;
+                    while( vOut.size( ) < uiMax && rStream.next( xR, vKeep ) )
+                        vOut.push_back( xR );
+                };
                 bool bMore = true;
+                std::vector<std::shared_ptr<ReadParser>> vLastMateKeep;
                 while( bMore )
                 {
-                    std::unique_ptr<Batch> pB;
-                    if( !xFree.pop( pB ) ) // recycled: the reads of a used batch keep their buffers
-                        return;
                     const auto t0 = now( );
-                    pB->uiFirst = uiDone, pB->uiSeq = uiSeq++;
-                    // serial pass over the line ends: the records of the batch (the mate file on its own thread) ...
-                    vKeepAlive.clear( ), vKeepAliveMate.clear( );
-                    auto scan = []( ReadStream& rStream, std::vector<ReadStream::Record>& vOut, size_t uiMax,
-                                    std::vector<std::shared_ptr<ReadParser>>& vKeep ) {
-                        vOut.clear( );
-                        ReadStream::Record xR;
-                        while( vOut.size( ) < uiMax && rStream.next( xR, vKeep ) )
-                            vOut.push_back( xR );
-                    };
+                    auto pJob = std::make_unique<ScanJob>( );
                     if( vMate.empty( ) )
                     {
-                        scan( xIn, vRecords, uiBatch, vKeepAlive );
-                        bMore = vRecords.size( ) == uiBatch;
+                        scan( xIn, pJob->vRecords, uiBatch, pJob->vKeepAlive );
+                        bMore = pJob->vRecords.size( ) == uiBatch;
                     }
                     else
                     {
@@ -436,7 +439,7 @@ int main( int argc, char** argv )
                         std::thread xMateScan( [ & ]( ) {
                             try
                             {
-                                scan( xMate, vSecond, uiBatch / 2, vKeepAliveMate );
+                                scan( xMate, vSecond, uiBatch / 2, pJob->vKeepAliveMate );
                             }
                             catch( ... )
                             {
@@ -445,7 +448,7 @@ int main( int argc, char** argv )
                         } );
                         try
                         {
-                            scan( xIn, vFirst, uiBatch / 2, vKeepAlive );
+                            scan( xIn, vFirst, uiBatch / 2, pJob->vKeepAlive );
                         }
                         catch( ... )
                         {
@@ -460,14 +463,46 @@ int main( int argc, char** argv )
                         if( vSecond.size( ) > vFirst.size( ) )
                             throw std::runtime_error( "more mates than reads" );
                         bMore = vFirst.size( ) == uiBatch / 2;
-                        vRecords.resize( 2 * vFirst.size( ) );
+                        pJob->vRecords.resize( 2 * vFirst.size( ) );
                         for( size_t k = 0; k < vFirst.size( ); k++ )
-                            vRecords[ 2 * k ] = vFirst[ k ], vRecords[ 2 * k + 1 ] = vSecond[ k ];
+                            pJob->vRecords[ 2 * k ] = vFirst[ k ], pJob->vRecords[ 2 * k + 1 ] = vSecond[ k ];
+                        vLastMateKeep = pJob->vKeepAliveMate;
                     }
-                    const size_t n = vRecords.size( );
-                    if( n == 0 )
+                    fScan += secs( t0, now( ) );
+                    if( pJob->vRecords.empty( ) )
                         break;
-                    // ... converted to NucSeq (names, base codes, qualities) on a few threads
+                    if( bPaired && pJob->vRecords.size( ) % 2 )
+                        throw std::runtime_error( "odd number of reads for a paired presetting" );
+                    if( !xScanned.push( std::move( pJob ) ) )
+                        return;
+                }
+                ReadStream::Record xR;
+                if( !vMate.empty( ) && xMate.next( xR, vLastMateKeep ) )
+                    throw std::runtime_error( "more mates than reads" );
+            }
+            catch( ... )
+            {
+                pScanError = std::current_exception( );
+            }
+            xScanned.close( );
+        } );
+
+        // reader, second half: the records converted to NucSeq and gathered into the batch's slab on a few threads
+        std::thread xReader( [ & ]( ) {
+            try
+            {
+                const size_t uiParseThreads = std::max<size_t>( 1, std::min<size_t>( 4, uiThreads / 3 ) );
+                size_t uiDone = 0, uiSeq = 0;
+                std::unique_ptr<ScanJob> pJob;
+                while( xScanned.pop( pJob ) )
+                {
+                    std::unique_ptr<Batch> pB;
+                    if( !xFree.pop( pB ) ) // recycled: the reads of a used batch keep their buffers
+                        break;
+                    const auto t0 = now( );
+                    pB->uiFirst = uiDone, pB->uiSeq = uiSeq++;
+                    const auto& vRecords = pJob->vRecords;
+                    const size_t n = vRecords.size( );
                     auto& v = pB->vReads;
                     v.resize( n );
                     const size_t uiParts = std::max<size_t>( 1, std::min<size_t>( uiParseThreads, n / 4096 + 1 ) );
@@ -498,21 +533,17 @@ int main( int argc, char** argv )
                     // ... and gathered into the page-locked slab the device stage uploads
                     Aligner::slabOffsets( v, pB->vSlab, pB->vOffsets );
                     parallel( [ & ]( size_t c ) { Aligner::slabCopy( v, pB->vSlab, pB->vOffsets, c, uiParts ); } );
-                    if( bPaired && n % 2 )
-                        throw std::runtime_error( "odd number of reads for a paired presetting" );
                     uiDone += n;
                     fParse += secs( t0, now( ) );
                     if( !xParsed.push( std::move( pB ) ) )
-                        return;
+                        break;
                 }
-                ReadStream::Record xR;
-                if( !vMate.empty( ) && xMate.next( xR, vKeepAliveMate ) )
-                    throw std::runtime_error( "more mates than reads" );
             }
             catch( ... )
             {
                 pReaderError = std::current_exception( );
             }
+            xScanned.close( ); // releases the scanner if this half stopped early
             xParsed.close( );
         } );
 
@@ -646,10 +677,13 @@ int main( int argc, char** argv )
         for( size_t g = 0; g < vGpuBusy.size( ); g++ )
             fGpu = std::max( fGpu, vGpuBusy[ g ] ), fKernels = std::max( fKernels, vKernelMs[ g ] * 1e-3 );
         xAligned.close( );
+        xScanned.close( );
+        xScanner.join( );
         xReader.join( );
         xWriterThread.join( );
         xOutputThread.join( );
-        vGpuError.push_back( pReaderError ), vGpuError.push_back( pWriterError ), vGpuError.push_back( pOutputError );
+        vGpuError.push_back( pScanError ), vGpuError.push_back( pReaderError ), vGpuError.push_back( pWriterError ),
+            vGpuError.push_back( pOutputError );
         for( auto& e : vGpuError )
             if( e )
                 std::rethrow_exception( e );
@@ -657,8 +691,8 @@ int main( int argc, char** argv )
             fprintf( stderr, "\rstart-up (CUDA context, index files -> device) %.3f s, total %.3f s\n", fStartup,
                      secs( tStart, now( ) ) );
         if( bVerbose )
-            fprintf( stderr, "busy seconds: reader %.3f, gpu stage (upload, kernels, download; max over %zu devices) %.3f of which "
-                             "kernels %.3f, format %.3f (%zu threads), write %.3f\n", fParse, vAligners.size( ), fGpu, fKernels, fFormat, uiThreads, fWrite );
+            fprintf( stderr, "busy seconds: scan %.3f, reader %.3f, gpu stage (upload, kernels, download; max over %zu devices) %.3f of which "
+                             "kernels %.3f, format %.3f (%zu threads), write %.3f\n", fScan, fParse, vAligners.size( ), fGpu, fKernels, fFormat, uiThreads, fWrite );
         if( pOut != stdout )
             fclose( pOut );
         std::cerr << "\rdone.                         " << std::endl;
