@@ -122,15 +122,21 @@ def ensure_index_files(genome, genome_mbp, seed, ctx=None):
     return prefix + "_ref", "reference builder (ref_dump index)"
 
 
-def run_reference(prefix, reads, threads, srand=-1):
+def run_reference(prefix, reads, threads, srand=-1, preset="illuminapaired"):
+    """The cpu_baseline leg: the unmodified reference's modules (oracle/_ref/ref_dump bench) over a sample of reads."""
     os.makedirs(CACHE, exist_ok=True)
     rf = os.path.join(CACHE, "sample_%d_%d.txt" % (os.getpid(), len(reads)))
     synth.write_reads_txt(rf, reads)
     try:
-        out = subprocess.check_output([REF_DUMP, "bench", prefix, rf, "illuminapaired", str(threads)]).decode()
+        out = subprocess.check_output([REF_DUMP, "bench", prefix, rf, preset, str(threads)]).decode()
     finally:
         os.remove(rf)
     return json.loads(out.strip().splitlines()[-1])
+
+
+def run_reference_ksw(pairs_file, threads, repeat):
+    """cpu_baseline leg of the DP-only sweep (scripts/dp_sweep_bench.py --cpu): the unmodified kswcpp_dispatch."""
+    return json.loads(subprocess.check_output([REF_DUMP, "kswbench", pairs_file, str(threads), str(repeat)]))
 
 
 def dist_env():

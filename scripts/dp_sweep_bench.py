@@ -24,10 +24,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+import bench  # noqa: E402
 import dpgen  # noqa: E402
 from ma_b200 import api  # noqa: E402
 
-REF_DUMP = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
+REF_DUMP = bench.REF_DUMP
 MODES = {"global": dpgen.GLOBAL, "ext": dpgen.EXT, "ext_right": dpgen.EXT_RIGHT}
 
 
@@ -82,7 +83,7 @@ def main():
                         write_pairs(pf, base)
                         rep = max(1, int(2e8 / (cells / reps)))
                         for th in (1, threads):
-                            o = json.loads(subprocess.check_output([REF_DUMP, "kswbench", pf, str(th), str(rep * (th if th > 1 else 1))]))
+                            o = bench.run_reference_ksw(pf, th, rep * (th if th > 1 else 1))  # bench.py's cpu_baseline leg
                             row["cpu_gcups_%dt" % th] = (cells / reps) * (o["calls"] / len(base)) / o["seconds"] / 1e9
                 points.append(row)
                 print(json.dumps(row), flush=True)

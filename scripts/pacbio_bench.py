@@ -61,17 +61,7 @@ def main():
     if a.cpu_sample > 0 and os.path.exists(B.REF_DUMP):
         prefix, how = B.ensure_index_files(genome, a.genome_mbp, 3, ctx)
         threads = os.cpu_count() or 1
-        os.makedirs(B.CACHE, exist_ok=True)
-        rf = os.path.join(B.CACHE, "pb_sample_%d.txt" % os.getpid())
-        with open(rf, "w") as f:
-            for r in reads[:a.cpu_sample]:
-                f.write("".join("ACGTN"[c] for c in r) + "\n")
-        import subprocess
-        try:
-            out = subprocess.check_output([B.REF_DUMP, "bench", prefix, rf, "pacbio", str(threads)]).decode()
-        finally:
-            os.remove(rf)
-        ref = json.loads(out.strip().splitlines()[-1])
+        ref = B.run_reference(prefix, reads[:a.cpu_sample], threads, preset="pacbio")  # bench.py's cpu_baseline leg
         line["cpu_baseline"] = {"value": ref["reads_per_s"], "unit": "reads/s", "cores": threads, "kind": "reference",
                                 "sample": "first %d reads, ref_dump bench pacbio (index: %s)" % (a.cpu_sample, how),
                                 "stage_cpu_s": ref.get("stage_cpu_s")}
