@@ -648,7 +648,7 @@ static HarmParams make_harm_params( const ma_b200_params& p )
 static NwParams make_nw_params( const ma_b200_params& p )
 {
     return NwParams{ p.match, p.mismatch, p.gap, p.extend, p.sv_penalty, p.max_gap_area, p.padding,
-                     p.bandwidth_ext, p.min_bandwidth_gap, p.zdrop };
+                     p.bandwidth_ext, p.min_bandwidth_gap, p.zdrop, make_score( p ).early_return ? 0 : 1 };
 }
 
 extern "C" int ma_b200_align_upload( ma_b200_ctx* ctx, int64_t n_reads, const uint8_t* reads, const int64_t* offsets )

@@ -22,6 +22,11 @@ struct NwParams
 {
     int match, mismatch, gap, extend, sv_penalty;
     int max_gap_area, padding, bandwidth_ext, min_bandwidth_gap, zdrop;
+    // 1: a 1 x 1 gap between two seeds needs no DP call. The reference's global kswcpp call on one query and one
+    // reference base returns the CIGAR 1M whenever it computes at all: the only alternative, an insertion plus a
+    // deletion, costs at least 2 (q + e), and a substitution costlier than that makes kswcpp return before the first
+    // cell (kswcpp_core.h:411-412, "-min_sc > 2 (q + e)") - the one case in which this flag is 0.
+    int one_by_one_is_match = 0;
 };
 
 enum
@@ -172,6 +177,8 @@ struct NwPlanner
             else
             {
                 const int qlen = (int)( tq - fq ), tlen = (int)( tr - fr );
+                if( qlen == 1 && tlen == 1 && P.one_by_one_is_match )
+                    return; // 64 % of the gap fills of Illumina reads: a substitution between two seeds
                 int w = P.min_bandwidth_gap;
                 const int d = tlen - qlen < 0 ? qlen - tlen : tlen - qlen;
                 if( d + 10 > w )
@@ -468,6 +475,8 @@ struct NwAssembler
         {
             if( toQuery - fromQuery > (u64)P.max_gap_area || toRef - fromRef > (u64)P.max_gap_area )
                 dual( fromQuery, toQuery, fromRef, toRef );
+            else if( toQuery - fromQuery == 1 && toRef - fromRef == 1 && P.one_by_one_is_match )
+                matches( fromQuery, fromRef, 1 ); // the CIGAR 1M of the reference's call, no leftovers
             else
             {
                 const KswOut& ez = res[ next++ ];

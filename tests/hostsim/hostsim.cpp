@@ -92,7 +92,7 @@ int main( int argc, char** argv )
     MapqParams MP{ OP.match, OP.report_n, OP.min_alignment_score, OP.max_supplementary_per_prim,
                    OP.max_overlap_supplementary, OP.paired_mean, OP.paired_std, OP.paired_bonus };
     NwParams NP{ OP.match, OP.mismatch, OP.gap, OP.extend, OP.sv_penalty, OP.max_gap_area, OP.padding,
-                 OP.bandwidth_ext, OP.min_bandwidth_gap, OP.zdrop };
+                 OP.bandwidth_ext, OP.min_bandwidth_gap, OP.zdrop, 1 /* default scores: 1 x 1 gaps without DP */ };
     ma_oracle_score_t osc{ OP.match, OP.mismatch, OP.gap, OP.extend, OP.gap2, OP.extend2 };
     { // glibc rand() emulation check
         GlibcRand g;
