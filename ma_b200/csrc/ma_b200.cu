@@ -575,8 +575,17 @@ extern "C" int ma_b200_index_build( ma_b200_ctx* ctx, const uint8_t* fwd, int64_
     if( !fwd || fwd_len <= 0 || !contig_start || !contig_len || n_contigs <= 0 )
         throw std::runtime_error( "index_build: bad arguments" );
     ctx->have_index = false;
-    IndexBuildResult R = build_index_gpu( ctx->stream, ctx->num_sms, fwd, fwd_len, ctx->ix_bwt, ctx->ix_sa,
-                                          ctx->ix_pac, ctx->launches );
+    // Small texts: whole suffix array by prefix doubling. From 2^31 - 1 suffixes on (or on request: MA_B200_IB_LARGE=1,
+    // chunk size in suffixes via MA_B200_IB_CHUNK — the tests run the bucketed builder on small genomes that way) the
+    // suffixes are sorted bucket by bucket (index_build.cuh build_index_gpu_large).
+    const char* sLarge = getenv( "MA_B200_IB_LARGE" );
+    const char* sChunk = getenv( "MA_B200_IB_CHUNK" );
+    const bool bLarge = 2 * fwd_len >= 0x7fffffffll || ( sLarge && atoi( sLarge ) != 0 );
+    IndexBuildResult R =
+        bLarge ? build_index_gpu_large( ctx->stream, ctx->num_sms, fwd, fwd_len, sChunk ? atoll( sChunk ) : 0,
+                                        ctx->ix_bwt, ctx->ix_sa, ctx->ix_pac, ctx->launches )
+               : build_index_gpu( ctx->stream, ctx->num_sms, fwd, fwd_len, ctx->ix_bwt, ctx->ix_sa, ctx->ix_pac,
+                                  ctx->launches );
     ctx->ix_contigs.reserve( (size_t)2 * n_contigs );
     MA_CUDA( cudaMemcpyAsync( ctx->ix_contigs.p, contig_start, n_contigs * 8, cudaMemcpyHostToDevice, ctx->stream ) );
     MA_CUDA( cudaMemcpyAsync( ctx->ix_contigs.p + n_contigs, contig_len, n_contigs * 8, cudaMemcpyHostToDevice,

@@ -119,6 +119,46 @@ def test_gpu_index_build_is_bit_identical(gold_index):
     ctx.close()
 
 
+def _index_arrays_equal(a, b):
+    return (a.primary == b.primary and np.array_equal(a.L2, b.L2) and np.array_equal(a.bwt, b.bwt) and
+            np.array_equal(a.sa, b.sa) and np.array_equal(a.pac, b.pac))
+
+
+@pytest.mark.parametrize("chunk", [1 << 29, 40_000, 1_000])
+def test_bucketed_index_builder_is_bit_identical(gold_index, chunk, monkeypatch):
+    """The builder for human-sized genomes (index_build.cuh build_index_gpu_large: suffixes sorted bucket by bucket,
+    ties refined 29 bases at a time) forced onto small genomes: one chunk, a few chunks, one chunk per 10-mer bin.
+    Must equal the reference's index files (golden genome) and the prefix-doubling builder (repeat-rich genome:
+    tandem arrays, homopolymer runs, reverse-complemented copies -> many refinement rounds)."""
+    monkeypatch.setenv("MA_B200_IB_LARGE", "1")
+    monkeypatch.setenv("MA_B200_IB_CHUNK", str(chunk))
+    ctx = make_ctx("illumina")
+    ctx.index_build(gold_index.forward_codes(), gold_index.contig_start, gold_index.contig_len)
+    ix = ctx.index_download(gold_index.contig_names)
+    assert ix.primary == gold_index.primary
+    assert np.array_equal(ix.L2, gold_index.L2)
+    assert np.array_equal(ix.bwt, gold_index.bwt)
+    assert np.array_equal(ix.sa, gold_index.sa)
+    assert np.array_equal(ix.pac[:len(gold_index.pac)], gold_index.pac)
+    g = PC.repeat_rich_genome()
+    lens = np.array([len(c) for c in g], dtype=np.int64)
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    ctx.index_build(np.concatenate(g), starts, lens)
+    big = ctx.index_download(["chr1", "chr2"])
+    monkeypatch.setenv("MA_B200_IB_LARGE", "0")
+    ctx.index_build(np.concatenate(g), starts, lens)
+    assert _index_arrays_equal(big, ctx.index_download(["chr1", "chr2"]))
+    # degenerate texts: a homopolymer (every suffix ties until the end of the text), a two-base text, period 2
+    for fwd in (np.zeros(3000, dtype=np.uint8), np.array([1, 2], dtype=np.uint8), np.tile([0, 3], 777).astype(np.uint8)):
+        monkeypatch.setenv("MA_B200_IB_LARGE", "1")
+        ctx.index_build(fwd, np.array([0]), np.array([len(fwd)]))
+        a = ctx.index_download(["c"])
+        monkeypatch.setenv("MA_B200_IB_LARGE", "0")
+        ctx.index_build(fwd, np.array([0]), np.array([len(fwd)]))
+        assert _index_arrays_equal(a, ctx.index_download(["c"])), len(fwd)
+    ctx.close()
+
+
 def test_batch_call_equals_staged_calls_and_sharding(gold_index):
     """ma_b200_align_batch == upload/run/download; splitting the batch (read sharding) gives the
     same records when the shard's srand_base is offset by its first read index."""
