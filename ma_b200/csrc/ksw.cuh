@@ -16,6 +16,7 @@
 #pragma once
 #include "fmindex.cuh"
 #include "ksw_types.cuh"
+#include "ksw_qs.cuh"
 #include <cstdint>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -129,34 +130,6 @@ __device__ inline int ksw_backtrack( const unsigned char* tb, int ncol16, int ql
     }
     return n > cap ? -1 : n;
 }
-
-// Where the two sequences of a problem live. Standalone batches (ma_b200_ksw_batch) read both from a byte slab;
-// the alignment pipeline reads the query from the read slab (forwards or backwards) and the target straight from
-// the 2-bit pack through its virtual forward+reverse-complement text, so no reference window is ever materialised.
-struct SeqAccess
-{
-    const unsigned char* qbase;
-    long long qoff;
-    int qstep;
-    const unsigned char* tslab;
-    const unsigned char* pac;
-    long long fwd_len;
-    long long toff;
-    int tstep;
-    __device__ __forceinline__ int Q( long long i ) const
-    {
-        return qbase[ qoff + qstep * i ];
-    }
-    __device__ __forceinline__ int T( long long i ) const
-    {
-        const long long p = toff + tstep * i;
-        if( pac == nullptr )
-            return tslab[ p ];
-        const long long f = p < fwd_len ? p : 2 * fwd_len - 1 - p;
-        const int b = pac[ f >> 2 ] >> ( ( ~f & 3 ) << 1 ) & 3;
-        return p < fwd_len ? b : 3 - b;
-    }
-};
 
 // One warp, one problem. All lanes return the same KswOut (cigar_off/n_cigar are filled by the caller).
 // tb: per-warp traceback slab of >= (qlen+tlen-1)*ncol16 bytes.
@@ -489,16 +462,6 @@ __device__ __forceinline__ bool ksw_rows( const KswScore& P, const SeqAccess& se
 // The lane-blocked position of the row maximum (calcMaxScore, :178-250) is NOT tracked per cell: it is recomputed
 // from the finished H row only in the rows that consume it (new maximum, or a z-drop test that can fire).
 // mqe / mte / score are not produced (never read by early-stop callers, see ksw_rows).
-
-__host__ __device__ inline bool ksw_p2_params_ok( const KswScore& P )
-{
-    const int Q = P.q + P.e > P.q2 + P.e2 ? P.q + P.e : P.q2 + P.e2;
-    const int mis = -P.mismatch > P.e2 ? -P.mismatch : P.e2;
-    const int gq = P.q > P.q2 ? P.q : P.q2;
-    const int ld = P.long_diff < 0 ? -P.long_diff : P.long_diff;
-    return P.match > 0 && P.q >= 0 && P.e >= 0 && P.q2 >= 0 && P.e2 >= 0 && P.mismatch <= 0 &&
-           2 * Q + P.match + mis + gq + ld <= 127;
-}
 
 __device__ __forceinline__ unsigned h2u( __half2 h )
 {
@@ -1034,7 +997,23 @@ struct KswBatchArgs
     int* error;
     unsigned long long* cells_total; // optional: sum of band cells (GCUPS accounting)
     KswScore score;
+    // ksw_qs_kernel only: where a problem that left the kernel's regime is handed over to ksw_batch_kernel.
+    // Pipeline: the device-side bins of nwbin_kernel (redo_count != nullptr); standalone batches: one list.
+    int* redo_count; // [15] tasks per (window class, kind) bin
+    unsigned long long* redo_tb; // [15] traceback bytes per warp
+    int* redo_cig; // [15] cigar scratch words per warp
+    int* redo_order; // [bins][redo_cap] task ids (pipeline) / [redo_cap] (list form, its length in redo_n)
+    long long redo_cap;
+    int* redo_n;
+    QsK qsk[ 2 ]; // packed constants of ksw_qs_kernel: [0] left-aligned, [1] right-aligned
 };
+
+// window class of ksw_batch_kernel for an aligned band width
+MA_HD inline int ksw_bin_of( int ncol16 )
+{
+    const int need = ncol16 + 48;
+    return need <= 128 ? 0 : need <= 256 ? 1 : need <= 512 ? 2 : need <= 1024 ? 3 : need <= 2048 ? 4 : 5;
+}
 
 #ifndef MA_KSW_MINB
 #define MA_KSW_MINB 2
@@ -1104,6 +1083,113 @@ template <int W> __global__ void __launch_bounds__( 32 * MA_KSW_WARPS, MA_KSW_MI
         }
         __syncwarp( );
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Query-stationary register kernel (ksw_qs.cuh): one warp per early-stop extension with a query of <= 64 NB bases.
+#ifndef MA_QS_WARPS
+#define MA_QS_WARPS 8
+#endif
+#ifndef MA_QS_MINB
+#define MA_QS_MINB 3
+#endif
+// bytes of traceback one warp needs for a problem of this kernel
+MA_HD inline long long ksw_qs_tb_bytes( int nb, int qlen, int tlen, int w )
+{
+    if( w < 0 )
+        w = tlen > qlen ? tlen : qlen;
+    const long long rows = (long long)qlen + tlen < (long long)w + 2 ? (long long)qlen + tlen : (long long)w + 2;
+    return ( rows * 64 * nb + 255 ) & ~255ll;
+}
+
+template <int NB, bool LEFT>
+__global__ void __launch_bounds__( 32 * MA_QS_WARPS, MA_QS_MINB ) ksw_qs_kernel( KswBatchArgs A )
+{
+    __shared__ KswQsSmem<NB> smAll[ MA_QS_WARPS ];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    KswQsSmem<NB>& sm = smAll[ warp ];
+    const long long gw = (long long)blockIdx.x * MA_QS_WARPS + warp;
+    unsigned char* tb = A.tb + gw * A.tb_stride;
+    unsigned int* cs = A.cigscratch + gw * A.cigscratch_stride;
+    unsigned long long cellsLocal = 0;
+    while( true )
+    {
+        int slot = 0;
+        if( lane == 0 )
+            slot = atomicAdd( A.next, 1 );
+        slot = __shfl_sync( 0xffffffffu, slot, 0 );
+        if( slot >= A.n )
+            break;
+        const int ti = A.order[ slot ];
+        const KswTask T = A.tasks[ ti ];
+        KswOut ez;
+        ez.max_q = ez.max_t = ez.mqe_t = ez.mte_q = -1;
+        ez.max = 0;
+        ez.score = ez.mqe = ez.mte = (int)0x80000000;
+        ez.n_cigar = 0, ez.zdropped = 0, ez.reach_end = 0, ez.status = 0, ez.cells = 0, ez.cigar_off = 0;
+        SeqAccess sa;
+        sa.qbase = A.seq, sa.qoff = T.qoff, sa.qstep = ( T.tag & MA_TASK_QREV ) ? -1 : 1;
+        sa.tslab = A.seq, sa.toff = T.toff, sa.tstep = ( T.tag & MA_TASK_TREV ) ? -1 : 1;
+        sa.pac = ( T.tag & MA_TASK_TPACK ) ? A.pac : nullptr, sa.fwd_len = A.fwd_len;
+        const int w = T.w < 0 ? ( T.tlen > T.qlen ? T.tlen : T.qlen ) : T.w;
+        const bool ok = ksw_qs_rows<NB, LEFT>( A.qsk[ LEFT ? 0 : 1 ], A.score, sa, T.qlen, T.tlen, w, T.zdrop, sm, tb, ez );
+        if( !ok )
+        { // hand the problem over to ksw_batch_kernel
+            if( lane == 0 )
+            {
+                if( A.redo_count )
+                {
+                    const int nc = ksw_ncol16( T.qlen, T.tlen, T.w );
+                    const int wc = ksw_bin_of( nc );
+                    const int b = wc < 5 ? wc * 3 + ( LEFT ? 1 : 2 ) : 15;
+                    const int s = atomicAdd( &A.redo_count[ b ], 1 );
+                    if( s < A.redo_cap )
+                        A.redo_order[ (long long)b * A.redo_cap + s ] = ti;
+                    atomicMax( &A.redo_tb[ b ], ( ( (unsigned long long)T.qlen + T.tlen ) * nc + 255 ) & ~255ull );
+                    atomicMax( &A.redo_cig[ b ], ( T.qlen + T.tlen + 2 + 63 ) & ~63 );
+                }
+                else
+                {
+                    const int s = atomicAdd( A.redo_n, 1 );
+                    if( s < A.redo_cap )
+                        A.redo_order[ s ] = ti;
+                }
+            }
+            __syncwarp( );
+            continue;
+        }
+        int n = 0;
+        if( ez.max_t >= 0 && ez.max_q >= 0 )
+        {
+            __syncwarp( );
+            if( lane == 0 )
+                n = ksw_qs_backtrack( tb, 64 * NB, LEFT, T.qlen, T.tlen, w, ez.max_t, ez.max_q, cs, A.cigscratch_stride );
+            n = __shfl_sync( 0xffffffffu, n, 0 );
+            unsigned long long o = 0;
+            if( n > 0 && lane == 0 )
+                o = atomicAdd( A.cigar_cursor, (unsigned long long)n );
+            o = __shfl_sync( 0xffffffffu, o, 0 );
+            if( n < 0 || (long long)( o + ( n > 0 ? n : 0 ) ) > A.cigar_cap )
+            {
+                if( lane == 0 )
+                    atomicExch( A.error, 1 );
+                ez.status = 1;
+                n = 0;
+            }
+            __syncwarp( );
+            const bool rev = T.flag & MA_KSW_REV_CIGAR;
+            for( int k = lane; k < n; k += 32 )
+                A.cigar[ o + k ] = rev ? cs[ k ] : cs[ n - 1 - k ];
+            ez.n_cigar = n;
+            ez.cigar_off = (long long)o;
+        }
+        if( lane == 0 )
+            A.out[ ti ] = ez;
+        cellsLocal += (unsigned long long)ez.cells;
+        __syncwarp( );
+    }
+    if( lane == 0 && A.cells_total && cellsLocal )
+        atomicAdd( A.cells_total, cellsLocal );
 }
 
 } // namespace ma

@@ -39,4 +39,44 @@ struct KswScore
 #define MA_KSW_EXTZ_ONLY 0x40
 #define MA_KSW_REV_CIGAR 0x80
 
+// Where the two sequences of a problem live. Standalone batches (ma_b200_ksw_batch) read both from a byte slab;
+// the alignment pipeline reads the query from the read slab (forwards or backwards) and the target straight from
+// the 2-bit pack through its virtual forward+reverse-complement text, so no reference window is ever materialised.
+struct SeqAccess
+{
+    const unsigned char* qbase;
+    long long qoff;
+    int qstep;
+    const unsigned char* tslab;
+    const unsigned char* pac;
+    long long fwd_len;
+    long long toff;
+    int tstep;
+    MA_HD inline int Q( long long i ) const
+    {
+        return qbase[ qoff + qstep * i ];
+    }
+    MA_HD inline int T( long long i ) const
+    {
+        const long long p = toff + tstep * i;
+        if( pac == nullptr )
+            return tslab[ p ];
+        const long long f = p < fwd_len ? p : 2 * fwd_len - 1 - p;
+        const int b = pac[ f >> 2 ] >> ( ( ~f & 3 ) << 1 ) & 3;
+        return p < fwd_len ? b : 3 - b;
+    }
+};
+
+// scoring parameters for which the reference's int8 difference arithmetic can never wrap (see ksw.cuh, packed path)
+MA_HD inline bool ksw_p2_params_ok( const KswScore& P )
+{
+    const int Q = P.q + P.e > P.q2 + P.e2 ? P.q + P.e : P.q2 + P.e2;
+    const int mis = -P.mismatch > P.e2 ? -P.mismatch : P.e2;
+    const int gq = P.q > P.q2 ? P.q : P.q2;
+    const int ld = P.long_diff < 0 ? -P.long_diff : P.long_diff;
+    return P.match > 0 && P.q >= 0 && P.e >= 0 && P.q2 >= 0 && P.e2 >= 0 && P.mismatch <= 0 &&
+           2 * Q + P.match + mis + gq + ld <= 127;
+}
+
+
 } // namespace ma

@@ -14,10 +14,11 @@ using namespace ma;
 
 struct KswHostBin
 {
-    int W;
+    int W; // window class of ksw_batch_kernel; 0 for the bins of ksw_qs_kernel
     std::vector<int> order;
     long long tb_stride = 0;
     int cig_stride = 0;
+    int qs = 0; // ksw_qs_kernel: 1 + (blocks - 1) * 2 + right-aligned
 };
 
 struct ma_b200_ctx
@@ -43,6 +44,9 @@ struct ma_b200_ctx
     DevBuf<unsigned long long> ksw_ctrl; // [0] cigar cursor, [16] next (as int), [32] error (as int), [48] cells: one 128-byte line each
     std::vector<KswHostBin> ksw_bins;
     unsigned long long ksw_cigar_used = 0;
+    std::vector<KswTask> ksw_host_tasks; // host copy (device tags): bins the problems ksw_qs_kernel hands over
+    DevBuf<int> ksw_redo; // [0] count, [1 ..] task ids handed over by ksw_qs_kernel (standalone batches)
+    cudaEvent_t binEv[ MA_NBINS ][ 2 ] = { { nullptr } }; // MA_B200_DP_BINS=1: per-launch times
 
     // ---- index (replicated per context / GPU)
     bool have_index = false;
@@ -214,6 +218,13 @@ extern "C" void ma_b200_destroy( ma_b200_ctx* ctx )
         ma_b200_destroy( ctx->shadow );
     if( ctx->stream )
         cudaStreamDestroy( ctx->stream );
+    for( auto& e : ctx->binEv )
+        for( auto& f : e )
+            if( f )
+                cudaEventDestroy( f );
+    for( auto& e : ctx->ev )
+        if( e )
+            cudaEventDestroy( e );
     delete ctx;
 }
 
@@ -280,11 +291,66 @@ template <int W> static void launch_ksw_bin( ma_b200_ctx* ctx, const KswBatchArg
     ctx->launches++;
 }
 
-static void ksw_plan( ma_b200_ctx* ctx, int64_t n, const ma_b200_ksw_task* tasks )
+// ksw_qs_kernel: qs = 1 + (blocks - 1) * 2 + right-aligned
+template <int NB, bool LEFT>
+static long long ksw_qs_grid_t( ma_b200_ctx* ctx, long long nTasks, long long tbStride, int cigStride, long long tbBudget )
 {
+    int perSm = 0;
+    MA_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, ksw_qs_kernel<NB, LEFT>, 32 * MA_QS_WARPS, 0 ) );
+    if( perSm < 1 )
+        perSm = 1;
+    long long grid = (long long)perSm * ctx->num_sms;
+    grid = std::min<long long>( grid, ( nTasks + MA_QS_WARPS - 1 ) / MA_QS_WARPS );
+    const long long perCta = ( tbStride + 4ll * cigStride ) * MA_QS_WARPS;
+    if( perCta > 0 )
+        grid = std::min<long long>( grid, std::max<long long>( 1, tbBudget / perCta ) );
+    return std::max<long long>( grid, 1 );
+}
+static long long ksw_qs_grid( ma_b200_ctx* ctx, int qs, long long nTasks, long long tbStride, int cigStride,
+                              long long tbBudget )
+{
+    switch( qs )
+    {
+        case 1: return ksw_qs_grid_t<1, true>( ctx, nTasks, tbStride, cigStride, tbBudget );
+        case 2: return ksw_qs_grid_t<1, false>( ctx, nTasks, tbStride, cigStride, tbBudget );
+        case 3: return ksw_qs_grid_t<2, true>( ctx, nTasks, tbStride, cigStride, tbBudget );
+        case 4: return ksw_qs_grid_t<2, false>( ctx, nTasks, tbStride, cigStride, tbBudget );
+        case 5: return ksw_qs_grid_t<3, true>( ctx, nTasks, tbStride, cigStride, tbBudget );
+        default: return ksw_qs_grid_t<3, false>( ctx, nTasks, tbStride, cigStride, tbBudget );
+    }
+}
+static void launch_ksw_qs( ma_b200_ctx* ctx, int qs, const KswBatchArgs& A, long long grid )
+{
+    const unsigned g = (unsigned)grid, b = 32 * MA_QS_WARPS;
+    switch( qs )
+    {
+        case 1: ksw_qs_kernel<1, true><<<g, b, 0, ctx->stream>>>( A ); break;
+        case 2: ksw_qs_kernel<1, false><<<g, b, 0, ctx->stream>>>( A ); break;
+        case 3: ksw_qs_kernel<2, true><<<g, b, 0, ctx->stream>>>( A ); break;
+        case 4: ksw_qs_kernel<2, false><<<g, b, 0, ctx->stream>>>( A ); break;
+        case 5: ksw_qs_kernel<3, true><<<g, b, 0, ctx->stream>>>( A ); break;
+        default: ksw_qs_kernel<3, false><<<g, b, 0, ctx->stream>>>( A ); break;
+    }
+    MA_CUDA( cudaGetLastError( ) );
+    ctx->launches++;
+}
+static bool use_qs( )
+{
+    static const bool b = !( getenv( "MA_B200_NO_QS" ) && atoi( getenv( "MA_B200_NO_QS" ) ) != 0 );
+    return b;
+}
+
+// bins the (device-tagged) tasks: ksw_qs_kernel where it applies, else the window classes of ksw_batch_kernel.
+// A band wider than the largest window fails that TASK (status 2), not the batch.
+static void ksw_plan( ma_b200_ctx* ctx, const std::vector<KswTask>& tasks, std::vector<int>& tooWide )
+{
+    const KswScore score = make_score( ctx->params );
+    const int64_t n = (int64_t)tasks.size( );
     ctx->ksw_bins.clear( );
     for( int W : kKswWindows )
-        ctx->ksw_bins.push_back( KswHostBin{ W, { }, 0, 0 } );
+        ctx->ksw_bins.push_back( KswHostBin{ W, { }, 0, 0, 0 } );
+    for( int qs = 1; qs <= 6; qs++ )
+        ctx->ksw_bins.push_back( KswHostBin{ 0, { }, 0, 0, qs } );
     long long bound = 0;
     std::vector<long long> cost( n );
     for( int64_t i = 0; i < n; i++ )
@@ -293,19 +359,30 @@ static void ksw_plan( ma_b200_ctx* ctx, int64_t n, const ma_b200_ksw_task* tasks
         if( t.qlen < 0 || t.tlen < 0 )
             throw std::runtime_error( "ksw task with negative length" );
         const int nc = ksw_ncol16( t.qlen, t.tlen, t.w );
+        const long long rows = (long long)t.qlen + t.tlen;
         int b = -1;
-        for( size_t k = 0; k < ctx->ksw_bins.size( ); k++ )
-            if( ctx->ksw_bins[ k ].W >= nc + 48 )
-            {
-                b = (int)k;
-                break;
-            }
+        long long tbBytes = ( rows * nc + 255 ) & ~255ll;
+        const int nb = use_qs( ) ? ksw_qs_class( score, t.qlen, t.tlen, t.w, t.tag ) : 0;
+        if( nb > 0 )
+        {
+            b = (int)( sizeof( kKswWindows ) / sizeof( int ) ) + ( nb - 1 ) * 2 + ( ( t.flag & MA_KSW_RIGHT ) ? 1 : 0 );
+            tbBytes = ksw_qs_tb_bytes( nb, t.qlen, t.tlen, t.w );
+        }
+        else
+            for( size_t k = 0; k < sizeof( kKswWindows ) / sizeof( int ); k++ )
+                if( ctx->ksw_bins[ k ].W >= nc + 48 )
+                {
+                    b = (int)k;
+                    break;
+                }
         if( b < 0 )
-            throw std::runtime_error( "ksw task: band wider than the largest supported window (2000 columns)" );
+        {
+            tooWide.push_back( (int)i );
+            continue;
+        }
         auto& bin = ctx->ksw_bins[ b ];
         bin.order.push_back( (int)i );
-        const long long rows = (long long)t.qlen + t.tlen;
-        bin.tb_stride = std::max( bin.tb_stride, ( rows * nc + 255 ) & ~255ll );
+        bin.tb_stride = std::max( bin.tb_stride, tbBytes );
         bin.cig_stride = std::max<int>( bin.cig_stride, (int)( ( rows + 2 + 63 ) & ~63ll ) );
         cost[ i ] = rows * nc;
         bound += rows + 2;
@@ -336,23 +413,26 @@ extern "C" int ma_b200_ksw_upload( ma_b200_ctx* ctx, int64_t n, const ma_b200_ks
             throw std::runtime_error( "ksw_upload: task sequence range outside the slab" );
     static_assert( sizeof( ma_b200_ksw_task ) == sizeof( KswTask ), "task layout" );
     static_assert( sizeof( ma_b200_ksw_result ) == sizeof( KswOut ), "result layout" );
-    ksw_plan( ctx, n, tasks );
+    // `tag` is the caller's cookie; on the device the field carries the internal addressing mode (0 = byte slab)
+    std::vector<KswTask>& vTasks = ctx->ksw_host_tasks;
+    vTasks.resize( (size_t)n );
+    if( n > 0 )
+        memcpy( vTasks.data( ), tasks, n * sizeof( KswTask ) );
+    for( auto& t : vTasks )
+        t.tag = ( ctx->ksw_extension_only && ( t.flag & MA_KSW_EXTZ_ONLY ) ) ? MA_TASK_EARLYSTOP : 0;
+    std::vector<int> tooWide;
+    ksw_plan( ctx, vTasks, tooWide );
     ctx->ksw_n = n;
     ctx->ksw_tasks.reserve( (size_t)n + 1 );
     ctx->ksw_seq.reserve( (size_t)seq_bytes + 1 );
     ctx->ksw_out.reserve( (size_t)n + 1 );
     ctx->ksw_order.reserve( (size_t)n + 1 );
-    ctx->ksw_ctrl.reserve( 64 );
+    ctx->ksw_redo.reserve( (size_t)n + 2 );
+    ctx->ksw_ctrl.reserve( 128 );
     if( n > 0 )
     {
-        // `tag` is the caller's cookie; on the device the field carries the internal addressing mode (0 = byte slab)
-        std::vector<KswTask> vTasks( (size_t)n );
-        memcpy( vTasks.data( ), tasks, n * sizeof( KswTask ) );
-        for( auto& t : vTasks )
-            t.tag = ( ctx->ksw_extension_only && ( t.flag & MA_KSW_EXTZ_ONLY ) ) ? MA_TASK_EARLYSTOP : 0;
         MA_CUDA( cudaMemcpyAsync( ctx->ksw_tasks.p, vTasks.data( ), n * sizeof( KswTask ), cudaMemcpyHostToDevice,
                                   ctx->stream ) );
-        MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
         MA_CUDA( cudaMemcpyAsync( ctx->ksw_seq.p, seq, seq_bytes, cudaMemcpyHostToDevice, ctx->stream ) );
         size_t o = 0;
         for( auto& bin : ctx->ksw_bins )
@@ -362,6 +442,15 @@ extern "C" int ma_b200_ksw_upload( ma_b200_ctx* ctx, int64_t n, const ma_b200_ks
                                           cudaMemcpyHostToDevice, ctx->stream ) );
             o += bin.order.size( );
         }
+        if( !tooWide.empty( ) )
+        { // status 2: band wider than the largest supported window (2000 columns); the rest of the batch is computed
+            KswOut bad;
+            memset( &bad, 0, sizeof( bad ) );
+            bad.max_q = bad.max_t = bad.mqe_t = bad.mte_q = -1, bad.status = 2;
+            for( int i : tooWide )
+                MA_CUDA( cudaMemcpyAsync( ctx->ksw_out.p + i, &bad, sizeof( bad ), cudaMemcpyHostToDevice, ctx->stream ) );
+            MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
+        }
     }
     // cigar slab: start with a typical size; ksw_run re-runs with the exact bound if it overflows
     ctx->ksw_cigar_cap = std::min<long long>( ctx->ksw_cigar_bound, std::max<long long>( 48 * n, 1 << 16 ) );
@@ -370,66 +459,132 @@ extern "C" int ma_b200_ksw_upload( ma_b200_ctx* ctx, int64_t n, const ma_b200_ks
     MA_API_END
 }
 
+static long long ksw_host_grid( ma_b200_ctx* ctx, const KswHostBin& bin, long long budget )
+{
+    if( bin.order.empty( ) )
+        return 0;
+    if( bin.qs )
+        return ksw_qs_grid( ctx, bin.qs, (long long)bin.order.size( ), bin.tb_stride, bin.cig_stride, budget );
+    switch( bin.W )
+    {
+        case 128: return ksw_bin_grid<128>( ctx, bin, budget );
+        case 256: return ksw_bin_grid<256>( ctx, bin, budget );
+        case 512: return ksw_bin_grid<512>( ctx, bin, budget );
+        case 1024: return ksw_bin_grid<1024>( ctx, bin, budget );
+        default: return ksw_bin_grid<2048>( ctx, bin, budget );
+    }
+}
+static void ksw_host_launch( ma_b200_ctx* ctx, const KswHostBin& bin, KswBatchArgs& A, long long grid )
+{
+    A.n = (int)bin.order.size( );
+    A.tb_stride = bin.tb_stride, A.cigscratch_stride = bin.cig_stride;
+    MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p + 16, 0, sizeof( unsigned long long ), ctx->stream ) );
+    if( bin.qs )
+        return launch_ksw_qs( ctx, bin.qs, A, grid );
+    switch( bin.W )
+    {
+        case 128: launch_ksw_bin<128>( ctx, A, grid ); break;
+        case 256: launch_ksw_bin<256>( ctx, A, grid ); break;
+        case 512: launch_ksw_bin<512>( ctx, A, grid ); break;
+        case 1024: launch_ksw_bin<1024>( ctx, A, grid ); break;
+        default: launch_ksw_bin<2048>( ctx, A, grid ); break;
+    }
+}
+
 static int ksw_run_once( ma_b200_ctx* ctx )
 {
-    MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p, 0, 64 * sizeof( unsigned long long ), ctx->stream ) );
+    MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p, 0, 128 * sizeof( unsigned long long ), ctx->stream ) );
+    MA_CUDA( cudaMemsetAsync( ctx->ksw_redo.p, 0, sizeof( int ), ctx->stream ) );
     const KswScore score = make_score( ctx->params );
     const long long budget = 48ll << 30; // traceback + cigar scratch of all resident warps (180 GB of HBM per GPU)
-    // size the per-warp scratch for the largest bin first: DevBuf::reserve may free + reallocate
-    std::vector<long long> grids;
-    size_t tbNeed = 0, csNeed = 0;
-    for( auto& bin : ctx->ksw_bins )
+    KswBatchArgs A;
+    A.tasks = ctx->ksw_tasks.p;
+    A.seq = ctx->ksw_seq.p;
+    A.pac = nullptr, A.fwd_len = 0;
+    A.out = ctx->ksw_out.p;
+    A.cigar = ctx->ksw_cigar.p;
+    A.cigar_cap = ctx->ksw_cigar_cap;
+    A.cigar_cursor = ctx->ksw_ctrl.p;
+    A.next = (int*)( ctx->ksw_ctrl.p + 16 );
+    A.error = (int*)( ctx->ksw_ctrl.p + 32 );
+    A.cells_total = nullptr;
+    A.score = score;
+    A.qsk[ 0 ] = ksw_qs_make_k( score, true ), A.qsk[ 1 ] = ksw_qs_make_k( score, false );
+    A.redo_count = nullptr, A.redo_tb = nullptr, A.redo_cig = nullptr;
+    A.redo_n = ctx->ksw_redo.p, A.redo_order = ctx->ksw_redo.p + 1, A.redo_cap = ctx->ksw_n;
+    // two phases: ksw_qs_kernel first (it may hand problems over), then ksw_batch_kernel. The per-warp scratch is sized
+    // per phase (DevBuf::reserve may free + reallocate: only between phases, after a synchronisation).
+    std::vector<KswHostBin> redoBins;
+    for( int phase = 0; phase < 2; phase++ )
     {
-        long long g = 0;
-        if( !bin.order.empty( ) )
-            switch( bin.W )
-            {
-                case 128: g = ksw_bin_grid<128>( ctx, bin, budget ); break;
-                case 256: g = ksw_bin_grid<256>( ctx, bin, budget ); break;
-                case 512: g = ksw_bin_grid<512>( ctx, bin, budget ); break;
-                case 1024: g = ksw_bin_grid<1024>( ctx, bin, budget ); break;
-                default: g = ksw_bin_grid<2048>( ctx, bin, budget ); break;
-            }
-        grids.push_back( g );
-        tbNeed = std::max<size_t>( tbNeed, (size_t)( g * MA_KSW_WARPS * bin.tb_stride ) );
-        csNeed = std::max<size_t>( csNeed, (size_t)( g * MA_KSW_WARPS * bin.cig_stride ) );
-    }
-    ctx->ksw_tb.reserve( tbNeed + 256 );
-    ctx->ksw_cigscratch.reserve( csNeed + 64 );
-    size_t o = 0, b = 0;
-    for( auto& bin : ctx->ksw_bins )
-    {
-        const long long grid = grids[ b++ ];
-        if( bin.order.empty( ) )
-            continue;
-        KswBatchArgs A;
-        A.tasks = ctx->ksw_tasks.p;
-        A.order = ctx->ksw_order.p + o;
-        A.n = (int)bin.order.size( );
-        A.seq = ctx->ksw_seq.p;
-        A.pac = nullptr, A.fwd_len = 0;
-        A.out = ctx->ksw_out.p;
-        A.cigar = ctx->ksw_cigar.p;
-        A.cigar_cap = ctx->ksw_cigar_cap;
-        A.cigar_cursor = ctx->ksw_ctrl.p;
-        A.tb = ctx->ksw_tb.p;
-        A.tb_stride = bin.tb_stride;
-        A.cigscratch = ctx->ksw_cigscratch.p;
-        A.cigscratch_stride = bin.cig_stride;
-        A.next = (int*)( ctx->ksw_ctrl.p + 16 );
-        A.error = (int*)( ctx->ksw_ctrl.p + 32 );
-        A.cells_total = nullptr;
-        A.score = score;
-        MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p + 16, 0, sizeof( unsigned long long ), ctx->stream ) );
-        switch( bin.W )
+        std::vector<const KswHostBin*> bins;
+        std::vector<const int*> orders;
+        size_t o = 0;
+        for( auto& bin : ctx->ksw_bins )
         {
-            case 128: launch_ksw_bin<128>( ctx, A, grid ); break;
-            case 256: launch_ksw_bin<256>( ctx, A, grid ); break;
-            case 512: launch_ksw_bin<512>( ctx, A, grid ); break;
-            case 1024: launch_ksw_bin<1024>( ctx, A, grid ); break;
-            default: launch_ksw_bin<2048>( ctx, A, grid ); break;
+            if( !bin.order.empty( ) && ( bin.qs != 0 ) == ( phase == 0 ) )
+                bins.push_back( &bin ), orders.push_back( ctx->ksw_order.p + o );
+            o += bin.order.size( );
         }
-        o += bin.order.size( );
+        if( phase == 1 )
+        { // problems handed over by ksw_qs_kernel, binned by window class
+            int nRedo = 0;
+            MA_CUDA( cudaMemcpyAsync( &nRedo, ctx->ksw_redo.p, sizeof( int ), cudaMemcpyDeviceToHost, ctx->stream ) );
+            MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
+            if( nRedo > 0 )
+            {
+                std::vector<int> ids( (size_t)nRedo );
+                MA_CUDA( cudaMemcpyAsync( ids.data( ), ctx->ksw_redo.p + 1, nRedo * sizeof( int ), cudaMemcpyDeviceToHost,
+                                          ctx->stream ) );
+                MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
+                std::sort( ids.begin( ), ids.end( ) );
+                for( int W : kKswWindows )
+                    redoBins.push_back( KswHostBin{ W, { }, 0, 0, 0 } );
+                for( int i : ids )
+                {
+                    const KswTask& t = ctx->ksw_host_tasks[ i ];
+                    const int nc = ksw_ncol16( t.qlen, t.tlen, t.w );
+                    const long long rows = (long long)t.qlen + t.tlen;
+                    for( auto& rb : redoBins )
+                        if( rb.W >= nc + 48 )
+                        {
+                            rb.order.push_back( i );
+                            rb.tb_stride = std::max( rb.tb_stride, ( rows * nc + 255 ) & ~255ll );
+                            rb.cig_stride = std::max<int>( rb.cig_stride, (int)( ( rows + 2 + 63 ) & ~63ll ) );
+                            break;
+                        }
+                }
+                size_t ro = 1;
+                for( auto& rb : redoBins )
+                {
+                    if( rb.order.empty( ) )
+                        continue;
+                    MA_CUDA( cudaMemcpyAsync( ctx->ksw_redo.p + ro, rb.order.data( ), rb.order.size( ) * sizeof( int ),
+                                              cudaMemcpyHostToDevice, ctx->stream ) );
+                    bins.push_back( &rb ), orders.push_back( ctx->ksw_redo.p + ro );
+                    ro += rb.order.size( );
+                }
+                MA_CUDA( cudaStreamSynchronize( ctx->stream ) ); // the host vectors stay alive, but keep it simple
+            }
+        }
+        std::vector<long long> grids;
+        size_t tbNeed = 0, csNeed = 0;
+        for( const KswHostBin* bin : bins )
+        {
+            const long long g = ksw_host_grid( ctx, *bin, budget );
+            grids.push_back( g );
+            const int wpc = bin->qs ? MA_QS_WARPS : MA_KSW_WARPS;
+            tbNeed = std::max<size_t>( tbNeed, (size_t)( g * wpc * bin->tb_stride ) );
+            csNeed = std::max<size_t>( csNeed, (size_t)( g * wpc * bin->cig_stride ) );
+        }
+        ctx->ksw_tb.reserve( tbNeed + 256 );
+        ctx->ksw_cigscratch.reserve( csNeed + 64 );
+        A.tb = ctx->ksw_tb.p, A.cigscratch = ctx->ksw_cigscratch.p;
+        for( size_t k = 0; k < bins.size( ); k++ )
+        {
+            A.order = orders[ k ];
+            ksw_host_launch( ctx, *bins[ k ], A, grids[ k ] );
+        }
     }
     unsigned long long ctrl[ 64 ];
     MA_CUDA( cudaMemcpyAsync( ctrl, ctx->ksw_ctrl.p, sizeof( ctrl ), cudaMemcpyDeviceToHost, ctx->stream ) );
@@ -717,104 +872,131 @@ template <typename K> static int full_grid( ma_b200_ctx* ctx, K kernel, int thre
     return (int)std::max<long long>( g, 1 );
 }
 
-// DP over the planned tasks, bins decided on the device by nwplan_kernel
+// DP over the planned tasks, bins decided on the device by nwbin_kernel. Two phases: the bins of ksw_qs_kernel, which
+// may hand problems over into the bins of ksw_batch_kernel (PipeCtrl::bin_*), then those.
 static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
 {
     static const int Ws[ 5 ] = { 128, 256, 512, 1024, 2048 };
     const KswScore score = make_score( ctx->params );
-    if( ctx->hctrl.bin_count[ MA_NBINS - 1 ] > 0 )
-        throw std::runtime_error( "DP band wider than the largest supported window (2000 columns)" );
     ctx->task_out.reserve( (size_t)ctx->n_tasks + 1 );
-    ctx->ksw_ctrl.reserve( 64 );
+    ctx->ksw_ctrl.reserve( 128 );
     // MA_B200_DP_BINS=1: time and cells of every DP launch (window class x kind) on stderr
     static const bool bBinStats = getenv( "MA_B200_DP_BINS" ) != nullptr;
-    static cudaEvent_t binEv[ MA_NBINS ][ 2 ];
-    if( bBinStats && !binEv[ 0 ][ 0 ] )
-        for( auto& e : binEv )
+    if( bBinStats && !ctx->binEv[ 0 ][ 0 ] )
+        for( auto& e : ctx->binEv )
         {
             MA_CUDA( cudaEventCreate( &e[ 0 ] ) );
             MA_CUDA( cudaEventCreate( &e[ 1 ] ) );
         }
+    int count0[ 16 ]; // bins of ksw_batch_kernel before ksw_qs_kernel adds to them
+    for( int b = 0; b < 16; b++ )
+        count0[ b ] = ctx->hctrl.bin_count[ b ];
     long long cigCap = std::max<long long>( ctx->task_cigar.cap, std::max<long long>( 12 * ctx->n_tasks, 1 << 16 ) );
+    const size_t offCount = (size_t) & ( ( (PipeCtrl*)0 )->bin_count );
     for( int attempt = 0; attempt < 2; attempt++ )
     {
         ctx->task_cigar.reserve( (size_t)cigCap );
         cigCap = (long long)ctx->task_cigar.cap;
-        MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p, 0, 64 * sizeof( unsigned long long ), ctx->stream ) );
+        MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p, 0, 128 * sizeof( unsigned long long ), ctx->stream ) );
+        if( attempt > 0 )
+            MA_CUDA( cudaMemcpyAsync( (char*)ctx->ctrl.p + offCount, count0, sizeof( count0 ), cudaMemcpyHostToDevice,
+                                      ctx->stream ) );
         const long long budget = 48ll << 30; // traceback + cigar scratch of all resident warps (180 GB of HBM per GPU)
-        long long grids[ MA_NBINS - 1 ];
-        size_t tbNeed = 0, csNeed = 0;
-        for( int b = 0; b < MA_NBINS - 1; b++ )
+        KswBatchArgs A;
+        A.tasks = ctx->tasks.p;
+        A.seq = ctx->reads.p;
+        A.pac = ctx->index.pac, A.fwd_len = ctx->index.fwd_len;
+        A.out = ctx->task_out.p;
+        A.cigar = ctx->task_cigar.p;
+        A.cigar_cap = cigCap;
+        A.cigar_cursor = ctx->ksw_ctrl.p;
+        A.next = (int*)( ctx->ksw_ctrl.p + 16 );
+        A.error = (int*)( ctx->ksw_ctrl.p + 32 );
+        A.score = score;
+        A.qsk[ 0 ] = ksw_qs_make_k( score, true ), A.qsk[ 1 ] = ksw_qs_make_k( score, false );
+        A.redo_count = ctx->ctrl.p->bin_count, A.redo_tb = ctx->ctrl.p->bin_tb, A.redo_cig = ctx->ctrl.p->bin_cig;
+        A.redo_order = ctx->bin_order.p, A.redo_cap = task_cap, A.redo_n = nullptr;
+        for( int phase = 0; phase < 2; phase++ )
         {
-            grids[ b ] = 0;
-            if( ctx->hctrl.bin_count[ b ] == 0 )
-                continue;
-            KswHostBin bin;
-            bin.W = Ws[ b / 3 ];
-            bin.order.resize( ctx->hctrl.bin_count[ b ] ); // only its size is used
-            bin.tb_stride = (long long)ctx->hctrl.bin_tb[ b ], bin.cig_stride = ctx->hctrl.bin_cig[ b ];
-            switch( b / 3 )
+            const int b0 = phase == 0 ? MA_QS_BIN0 : 0, b1 = phase == 0 ? MA_QS_BIN0 + 6 : 15;
+            if( phase == 1 )
             {
-                case 0: grids[ b ] = ksw_bin_grid<128>( ctx, bin, budget ); break;
-                case 1: grids[ b ] = ksw_bin_grid<256>( ctx, bin, budget ); break;
-                case 2: grids[ b ] = ksw_bin_grid<512>( ctx, bin, budget ); break;
-                case 3: grids[ b ] = ksw_bin_grid<1024>( ctx, bin, budget ); break;
-                default: grids[ b ] = ksw_bin_grid<2048>( ctx, bin, budget ); break;
+                read_ctrl( ctx ); // synchronises: the bins now hold what ksw_qs_kernel handed over
+                if( ctx->hctrl.bin_count[ 15 ] > 0 )
+                    throw std::runtime_error( "DP band wider than the largest supported window (2000 columns)" );
+                for( int b = 0; b < 15; b++ )
+                    if( ctx->hctrl.bin_count[ b ] > task_cap )
+                        throw std::runtime_error( "pipeline DP: bin list overflow (internal error)" );
             }
-            tbNeed = std::max<size_t>( tbNeed, (size_t)( grids[ b ] * MA_KSW_WARPS * bin.tb_stride ) );
-            csNeed = std::max<size_t>( csNeed, (size_t)( grids[ b ] * MA_KSW_WARPS * bin.cig_stride ) );
-        }
-        ctx->ksw_tb.reserve( tbNeed + 256 );
-        ctx->ksw_cigscratch.reserve( csNeed + 64 );
-        for( int b = 0; b < MA_NBINS - 1; b++ )
-        {
-            if( ctx->hctrl.bin_count[ b ] == 0 )
-                continue;
-            KswBatchArgs A;
-            A.tasks = ctx->tasks.p;
-            A.order = ctx->bin_order.p + (long long)b * task_cap;
-            A.n = ctx->hctrl.bin_count[ b ];
-            A.seq = ctx->reads.p;
-            A.pac = ctx->index.pac, A.fwd_len = ctx->index.fwd_len;
-            A.out = ctx->task_out.p;
-            A.cigar = ctx->task_cigar.p;
-            A.cigar_cap = cigCap;
-            A.cigar_cursor = ctx->ksw_ctrl.p;
-            A.tb = ctx->ksw_tb.p, A.tb_stride = (long long)ctx->hctrl.bin_tb[ b ];
-            A.cigscratch = ctx->ksw_cigscratch.p, A.cigscratch_stride = ctx->hctrl.bin_cig[ b ];
-            A.next = (int*)( ctx->ksw_ctrl.p + 16 );
-            A.error = (int*)( ctx->ksw_ctrl.p + 32 );
-            A.cells_total = ctx->ksw_ctrl.p + 49 + b; // one counter per bin (slots 49..63), summed below
-            A.score = score;
-            MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p + 16, 0, sizeof( unsigned long long ), ctx->stream ) );
-            if( bBinStats )
-                MA_CUDA( cudaEventRecord( binEv[ b ][ 0 ], ctx->stream ) );
-            switch( b / 3 )
+            long long grids[ MA_NBINS ];
+            size_t tbNeed = 0, csNeed = 0;
+            for( int b = b0; b < b1; b++ )
             {
-                case 0: launch_ksw_bin<128>( ctx, A, grids[ b ] ); break;
-                case 1: launch_ksw_bin<256>( ctx, A, grids[ b ] ); break;
-                case 2: launch_ksw_bin<512>( ctx, A, grids[ b ] ); break;
-                case 3: launch_ksw_bin<1024>( ctx, A, grids[ b ] ); break;
-                default: launch_ksw_bin<2048>( ctx, A, grids[ b ] ); break;
+                grids[ b ] = 0;
+                if( ctx->hctrl.bin_count[ b ] == 0 )
+                    continue;
+                KswHostBin bin;
+                bin.order.resize( ctx->hctrl.bin_count[ b ] ); // only its size is used
+                bin.tb_stride = (long long)ctx->hctrl.bin_tb[ b ], bin.cig_stride = ctx->hctrl.bin_cig[ b ];
+                if( phase == 0 )
+                    bin.W = 0, bin.qs = b - MA_QS_BIN0 + 1;
+                else
+                    bin.W = Ws[ b / 3 ], bin.qs = 0;
+                grids[ b ] = ksw_host_grid( ctx, bin, budget );
+                const int wpc = bin.qs ? MA_QS_WARPS : MA_KSW_WARPS;
+                tbNeed = std::max<size_t>( tbNeed, (size_t)( grids[ b ] * wpc * bin.tb_stride ) );
+                csNeed = std::max<size_t>( csNeed, (size_t)( grids[ b ] * wpc * bin.cig_stride ) );
             }
-            if( bBinStats )
-                MA_CUDA( cudaEventRecord( binEv[ b ][ 1 ], ctx->stream ) );
+            ctx->ksw_tb.reserve( tbNeed + 256 );
+            ctx->ksw_cigscratch.reserve( csNeed + 64 );
+            A.tb = ctx->ksw_tb.p, A.cigscratch = ctx->ksw_cigscratch.p;
+            for( int b = b0; b < b1; b++ )
+            {
+                if( ctx->hctrl.bin_count[ b ] == 0 )
+                    continue;
+                A.order = ctx->bin_order.p + (long long)b * task_cap;
+                A.n = ctx->hctrl.bin_count[ b ];
+                A.tb_stride = (long long)ctx->hctrl.bin_tb[ b ];
+                A.cigscratch_stride = ctx->hctrl.bin_cig[ b ];
+                A.cells_total = ctx->ksw_ctrl.p + 64 + b; // one counter per bin, summed below
+                MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p + 16, 0, sizeof( unsigned long long ), ctx->stream ) );
+                if( bBinStats )
+                    MA_CUDA( cudaEventRecord( ctx->binEv[ b ][ 0 ], ctx->stream ) );
+                if( phase == 0 )
+                    launch_ksw_qs( ctx, b - MA_QS_BIN0 + 1, A, grids[ b ] );
+                else
+                    switch( b / 3 )
+                    {
+                        case 0: launch_ksw_bin<128>( ctx, A, grids[ b ] ); break;
+                        case 1: launch_ksw_bin<256>( ctx, A, grids[ b ] ); break;
+                        case 2: launch_ksw_bin<512>( ctx, A, grids[ b ] ); break;
+                        case 3: launch_ksw_bin<1024>( ctx, A, grids[ b ] ); break;
+                        default: launch_ksw_bin<2048>( ctx, A, grids[ b ] ); break;
+                    }
+                if( bBinStats )
+                    MA_CUDA( cudaEventRecord( ctx->binEv[ b ][ 1 ], ctx->stream ) );
+            }
         }
-        unsigned long long c[ 64 ];
+        unsigned long long c[ 128 ];
         MA_CUDA( cudaMemcpyAsync( c, ctx->ksw_ctrl.p, sizeof( c ), cudaMemcpyDeviceToHost, ctx->stream ) );
         MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
         ctx->n_task_cigar = (int64_t)c[ 0 ];
         c[ 48 ] = 0;
-        for( int b = 0; b < MA_NBINS - 1; b++ )
-            c[ 48 ] += c[ 49 + b ];
+        for( int b = 0; b < MA_NBINS; b++ )
+            c[ 48 ] += c[ 64 + b ];
         if( bBinStats )
-            for( int b = 0; b < MA_NBINS - 1; b++ )
-                if( ctx->hctrl.bin_count[ b ] > 0 )
+            for( int b = 0; b < MA_NBINS; b++ )
+                if( b != 15 && ctx->hctrl.bin_count[ b ] > 0 && ctx->binEv[ b ][ 0 ] )
                 {
-                    const float ms = ev_ms( binEv[ b ][ 0 ], binEv[ b ][ 1 ] );
+                    const float ms = ev_ms( ctx->binEv[ b ][ 0 ], ctx->binEv[ b ][ 1 ] );
                     static const char* kKind[ 3 ] = { "all fields (exact)", "early-stop left", "early-stop right" };
-                    fprintf( stderr, "ma_b200 dp bin W=%d %s: %d tasks, %llu cells, %.3f ms, %.1f GCUPS\n", Ws[ b / 3 ],
-                             kKind[ b % 3 ], ctx->hctrl.bin_count[ b ], c[ 49 + b ], ms, c[ 49 + b ] / ms / 1e6 );
+                    if( b >= MA_QS_BIN0 )
+                        fprintf( stderr, "ma_b200 dp bin QS blocks=%d %s: %d tasks, %llu cells, %.3f ms, %.1f GCUPS\n",
+                                 ( b - MA_QS_BIN0 ) / 2 + 1, ( b - MA_QS_BIN0 ) % 2 ? "right" : "left",
+                                 ctx->hctrl.bin_count[ b ], c[ 64 + b ], ms, c[ 64 + b ] / ms / 1e6 );
+                    else
+                        fprintf( stderr, "ma_b200 dp bin W=%d %s: %d tasks, %llu cells, %.3f ms, %.1f GCUPS\n", Ws[ b / 3 ],
+                                 kKind[ b % 3 ], ctx->hctrl.bin_count[ b ], c[ 64 + b ], ms, c[ 64 + b ] / ms / 1e6 );
                 }
         ctx->ksw_cigar_used = c[ 48 ]; // reused as dp cell counter for the pipeline stats
         if( !(int)c[ 32 ] )
@@ -972,7 +1154,8 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
             ctx->n_tasks = nSets > 0 ? (int64_t)ctx->hctrl.task_cursor : 0;
             if( ctx->n_tasks > 0 )
             { // window bins of the tasks
-                NwBinArgs B{ ctx->tasks.p, (int)ctx->n_tasks, taskCap, ctx->bin_order.p, ctx->ctrl.p };
+                NwBinArgs B{ ctx->tasks.p, (int)ctx->n_tasks, taskCap, ctx->bin_order.p, ctx->ctrl.p, make_score( ctx->params ),
+                             use_qs( ) ? 1 : 0 };
                 nwbin_kernel<<<full_grid( ctx, nwbin_kernel, 256, ctx->n_tasks ), 256, 0, s>>>( B );
                 MA_CUDA( cudaGetLastError( ) );
                 ctx->launches++;

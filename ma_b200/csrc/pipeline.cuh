@@ -19,7 +19,8 @@
 namespace ma
 {
 
-#define MA_NBINS 16
+#define MA_NBINS 24 /* 0..14: ksw_batch_kernel (window class x kind), 15: band too wide, 16..21: ksw_qs_kernel */
+#define MA_QS_BIN0 16
 // control block in device memory; every counter that many threads bump at the same time sits in its own 128-byte
 // line (same-line atomics serialise in the L2 slice that owns the line)
 struct PipeCtrl
@@ -390,12 +391,6 @@ struct NwPlanArgs
     PipeCtrl* ctrl;
 };
 
-__device__ __forceinline__ int ksw_bin_of( int ncol16 )
-{
-    const int need = ncol16 + 48;
-    return need <= 128 ? 0 : need <= 256 ? 1 : need <= 512 ? 2 : need <= 1024 ? 3 : need <= 2048 ? 4 : 5;
-}
-
 // One thread per seed set: window, task count, one warp-aggregated slot allocation, tasks.
 __global__ void __launch_bounds__( 128 ) nwplan_kernel( NwPlanArgs A )
 {
@@ -464,6 +459,8 @@ struct NwBinArgs
     long long task_cap;
     int* bin_order; // [n_bins][task_cap] task ids per window bin
     PipeCtrl* ctrl;
+    KswScore score;
+    int use_qs; // route early-stop extensions with short queries to ksw_qs_kernel
 };
 
 // One thread per DP task: window bin, slot in the bin's order list (one atomic per warp and bin), slab sizes of the bin
@@ -484,8 +481,14 @@ __global__ void __launch_bounds__( 256 ) nwbin_kernel( NwBinArgs A )
             // of code paths thrashes the instruction cache): tasks are binned by window class AND kind
             const int wc = ksw_bin_of( nc );
             const int kind = !( T.tag & MA_TASK_EARLYSTOP ) ? 0 : ( T.flag & MA_KSW_RIGHT ) ? 2 : 1;
-            b = wc < 5 ? wc * 3 + kind : MA_NBINS - 1;
-            const unsigned long long bytes = ( ( (unsigned long long)T.qlen + T.tlen ) * nc + 255 ) >> 8;
+            b = wc < 5 ? wc * 3 + kind : 15;
+            unsigned long long bytes = ( ( (unsigned long long)T.qlen + T.tlen ) * nc + 255 ) >> 8;
+            const int qs = A.use_qs ? ksw_qs_class( A.score, T.qlen, T.tlen, T.w, T.tag ) : 0;
+            if( qs > 0 )
+            {
+                b = MA_QS_BIN0 + ( qs - 1 ) * 2 + ( kind == 2 ? 1 : 0 );
+                bytes = (unsigned long long)ksw_qs_tb_bytes( qs, T.qlen, T.tlen, T.w ) >> 8;
+            }
             tb = bytes > 0xffffffffull ? 0xffffffffu : (unsigned int)bytes; // in units of 256 bytes
             cig = (unsigned int)( ( T.qlen + T.tlen + 2 + 63 ) & ~63 );
         }
