@@ -13,6 +13,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # MA_B200_LIB: another build of the same library (A/B of compile-time knobs, scripts/); never a different backend
 LIB_PATH = os.environ.get("MA_B200_LIB") or os.path.join(_HERE, "libma_b200.so")
+# experiments only: another build of the same library (e.g. other kernel launch bounds)
+LIB_PATH = os.environ.get("MA_B200_LIB", LIB_PATH)
 
 KSW_RIGHT = 0x02
 KSW_EXTZ_ONLY = 0x40

@@ -1099,7 +1099,7 @@ MA_HD inline long long ksw_qs_tb_bytes( int nb, int qlen, int tlen, int w )
     if( w < 0 )
         w = tlen > qlen ? tlen : qlen;
     const long long rows = (long long)qlen + tlen < (long long)w + 2 ? (long long)qlen + tlen : (long long)w + 2;
-    return ( rows * 64 * nb + 255 ) & ~255ll;
+    return ( ( rows + 1 ) * 64 * nb + 255 ) & ~255ll; // (rows are stored in pairs)
 }
 
 template <int NB, bool LEFT>

@@ -134,6 +134,7 @@ MA_HD inline int ksw_qs_class( const KswScore& P, int qlen, int tlen, int w, int
     return ( qlen + 63 ) / 64;
 }
 
+
 template <int NB> struct KswQsSmem
 {
     unsigned int tp[ 256 ]; // tp[j & 255] = code(T[j]) | code(T[j - 1]) << 16, codes as c << 10
@@ -143,7 +144,7 @@ template <int NB> struct KswQsSmem
 
 struct QsK // packed s16x2 constants (built on the host: kernel parameters are constant-bank operands, not registers)
 {
-    unsigned zMis, zXor, cap, flA, flB, flA2, flB2, lowA, lowB, lowA2, lowB2, nlowA, nlowB, nlowA2, nlowB2, ne, ne2;
+    unsigned zMis, zXor, cap, flA, flB, flA2, flB2, lowA, lowB, lowA2, lowB2, nlowA, nlowB, nlowA2, nlowB2, ne, ne2, one;
 };
 
 MA_HD inline unsigned ksw_qs_pk( int v )
@@ -167,7 +168,7 @@ MA_HD inline QsK ksw_qs_make_k( const KswScore& P, bool bLeft )
     K.nlowA = ksw_qs_pk( -( 8 * ( -q - e ) + ta - lw ) ), K.nlowB = ksw_qs_pk( -( 8 * ( -q - e ) + tbb - lw ) );
     K.nlowA2 = ksw_qs_pk( -( 8 * ( -q2 - e2 ) + ta2 - lw ) ), K.nlowB2 = ksw_qs_pk( -( 8 * ( -q2 - e2 ) + tb2 - lw ) );
     // -e - z is formed as ~(z + 1) + (2 - e): there is no packed subtract (VIADD.16x2 only adds)
-    K.ne = ksw_qs_pk( -8 * e + 2 ), K.ne2 = ksw_qs_pk( -8 * e2 + 2 );
+    K.ne = ksw_qs_pk( -8 * e + 2 ), K.ne2 = ksw_qs_pk( -8 * e2 + 2 ), K.one = 0x00010001u;
     return K;
 }
 
@@ -213,29 +214,29 @@ QS_DEV int ksw_qs_argmax( const short* Hs, const int R, const int st0, const int
 }
 
 // one pair of cells. FRONT: the block holds query rows that have not entered the matrix yet (i > r): their own state
-// stays at its border value and they take no part in the maxima.
+// stays at its border value. Returns the traceback bytes of the two cells in bytes 0 and 2.
 template <bool LEFT, bool FRONT>
-QS_DEV void ksw_qs_cell( const QsK& K, unsigned& U, unsigned& V, unsigned& X, unsigned& Y, unsigned& X2, unsigned& Y2,
-                         unsigned& H8, const unsigned nbU, const unsigned nbY, const unsigned nbY2, const unsigned z0,
-                         const unsigned ent, const unsigned vOff, const unsigned term, unsigned& mrow, unsigned& hb,
-                         unsigned short* tbp )
+QS_DEV unsigned ksw_qs_cell( const QsK& K, unsigned& U, unsigned& V, unsigned& X, unsigned& Y, unsigned& X2,
+                             unsigned& Y2, unsigned& H8, const unsigned nbU, const unsigned nbY, const unsigned nbY2,
+                             const unsigned z0, const unsigned ent )
 {
     const unsigned a = __vadd2( X, V ), b = __vadd2( nbY, nbU ), a2 = __vadd2( X2, V ), b2 = __vadd2( nbY2, nbU );
-    unsigned d, z;
+    unsigned d, zc;
     if( LEFT )
     {
         const unsigned zt = __vimax3_s16x2( __vimax3_s16x2( z0, a, b ), a2, b2 );
         d = zt & 0x00070007u;
-        z = __vmins2( zt, K.cap ) & 0xFFF8FFF8u;
+        zc = __vmins2( zt, K.cap );
     }
     else
     { // right-aligned: ties go to the later candidate, state 4 is never recorded (kswcpp_core.h:693-699)
         const unsigned z4 = __vmaxs2( __vimax3_s16x2( z0, a, b ), a2 );
         d = z4 & 0x00070007u;
-        z = __vmins2( __vmaxs2( z4, b2 ), K.cap ) & 0xFFF8FFF8u;
+        zc = __vmins2( __vmaxs2( z4, b2 ), K.cap );
     }
-    // differences as sums of complements (a - b = a + ~b + 1 per half): z1 = z + 1, ~z1 = -z - 2
-    const unsigned z1 = z | 0x00010001u, nzc = ~z1;
+    // differences as sums of complements (a - b = a + ~b + 1 per half; there is no packed subtract):
+    // z1 = z + 1 (tag bits cleared), ~z1 = -z - 2
+    const unsigned z1 = ( zc & 0xFFF8FFF8u ) | K.one, nzc = ~z1;
     const unsigned un = __vadd2( z1, ~V ), vn = __vadd2( z1, ~nbU );
     const unsigned nz = __vadd2( nzc, K.ne ), nz2 = __vadd2( nzc, K.ne2 ); // -e - z
     // x' = max(a - z - e, -q - e); continuation flag a - z > -q (>= when right-aligned): 0 or 8
@@ -247,24 +248,16 @@ QS_DEV void ksw_qs_cell( const QsK& K, unsigned& U, unsigned& V, unsigned& X, un
     if( !LEFT )
         xn = __vmaxs2( xn, K.flA ), yn = __vmaxs2( yn, K.flB ), x2n = __vmaxs2( x2n, K.flA2 ),
         y2n = __vmaxs2( y2n, K.flB2 );
-    const unsigned tbv = fb2 * 8u + ( fa2 * 4u + ( fb * 2u + ( fa + d ) ) ); // < 128 per half: no carry between the halves
-    *tbp = (unsigned short)__byte_perm( tbv, 0, 0x4420 );
     const unsigned hn = __vadd2( H8, un );
     U = un, Y = yn, Y2 = y2n;
     if( FRONT )
     {
         V = ( vn & ent ) | ( V & ~ent ), X = ( xn & ent ) | ( X & ~ent ), X2 = ( x2n & ent ) | ( X2 & ~ent );
         H8 = ( hn & ent ) | ( H8 & ~ent );
-        const unsigned off = ( vOff & ent ) | ( qs_pk( -MA_QS_NEG ) & ~ent );
-        mrow = __viaddmax_s16x2( hn, off, mrow );
-        hb = __viaddmax_s16x2( hn, ( term & ent ) | ( qs_pk( -MA_QS_NEG ) & ~ent ), hb );
     }
     else
-    {
         V = vn, X = xn, X2 = x2n, H8 = hn;
-        mrow = __viaddmax_s16x2( hn, vOff, mrow );
-        hb = __viaddmax_s16x2( hn, term, hb );
-    }
+    return fb2 * 8u + ( fa2 * 4u + ( fb * 2u + ( fa + d ) ) ); // < 128 per half: no carry between the halves
 }
 
 QS_DEV int qs_hmax( unsigned v ) // larger half, sign extended
@@ -273,9 +266,60 @@ QS_DEV int qs_hmax( unsigned v ) // larger half, sign extended
     return lo > hi ? lo : hi;
 }
 
+// One anti-diagonal r over the blocks that hold entered query rows. STEADY: r >= 64 NB - 1 (every row has entered).
+// tbv[k] receives the traceback bytes of block k (bytes 0 and 2), mrow the packed row maximum.
+template <int NB, bool LEFT, bool STEADY>
+QS_DEV void ksw_qs_row( const QsK& K, const int r, const int lane, const int srcLane, const unsigned fcr,
+                        const unsigned* __restrict__ tp, const unsigned nivec0, unsigned ( &U )[ NB ], unsigned ( &V )[ NB ],
+                        unsigned ( &X )[ NB ], unsigned ( &Y )[ NB ], unsigned ( &X2 )[ NB ], unsigned ( &Y2 )[ NB ],
+                        unsigned ( &H8 )[ NB ], const unsigned ( &QP )[ NB ], unsigned ( &tbv )[ NB ], unsigned& mrow )
+{
+    const unsigned FULL = 0xffffffffu;
+    const int nbAct = STEADY ? NB : ( ( r >> 6 ) + 1 < NB ? ( r >> 6 ) + 1 : NB );
+    const int kf = ( !STEADY && ( r & 63 ) != 63 && ( r >> 6 ) < NB ) ? ( r >> 6 ) : -1; // block with rows not yet entered
+    const int tpi = r - 2 * lane;
+    mrow = ksw_qs_pk( -2 * MA_QS_NEG );
+#pragma unroll
+    for( int k = NB - 1; k >= 0; --k )
+    {
+        if( !STEADY && k >= nbAct )
+        {
+            tbv[ k ] = 0;
+            continue;
+        }
+        unsigned su = U[ k ], sy = Y[ k ], sy2 = Y2[ k ];
+        if( k > 0 && lane == 31 )
+            su = U[ k - 1 ], sy = Y[ k - 1 ], sy2 = Y2[ k - 1 ];
+        unsigned upU = __shfl_sync( FULL, su, srcLane ), upY = __shfl_sync( FULL, sy, srcLane ),
+                 upY2 = __shfl_sync( FULL, sy2, srcLane );
+        if( k == 0 && lane == 0 )
+            upU = fcr, upY = K.flB, upY2 = K.flB2;
+        const unsigned nbU = __byte_perm( upU, U[ k ], 0x5432 ), nbY = __byte_perm( upY, Y[ k ], 0x5432 ),
+                       nbY2 = __byte_perm( upY2, Y2[ k ], 0x5432 );
+        const unsigned tpw = tp[ ( tpi - 64 * k ) & 255 ];
+        const unsigned z0 = ( qs_eqmask2( tpw, QP[ k ] ) & K.zXor ) ^ K.zMis;
+        if( !STEADY && k == kf )
+        {
+            const unsigned tv = __vadd2( ksw_qs_pk( r - 64 * k ), nivec0 ); // r - i per half
+            const unsigned ent = ~qs_prmt( tv, 0, 0xBB99 ); // halves with i <= r
+            tbv[ k ] = ksw_qs_cell<LEFT, true>( K, U[ k ], V[ k ], X[ k ], Y[ k ], X2[ k ], Y2[ k ], H8[ k ], nbU, nbY, nbY2,
+                                                z0, ent );
+            mrow = __vmaxs2( mrow, ( H8[ k ] & ent ) | ( ksw_qs_pk( -2 * MA_QS_NEG ) & ~ent ) );
+        }
+        else
+        {
+            tbv[ k ] = ksw_qs_cell<LEFT, false>( K, U[ k ], V[ k ], X[ k ], Y[ k ], X2[ k ], Y2[ k ], H8[ k ], nbU, nbY, nbY2,
+                                                 z0, 0u );
+            mrow = __vmaxs2( mrow, H8[ k ] );
+        }
+    }
+}
+
 // One warp, one problem; all lanes return the same result. false: the problem left the regime of this kernel (band
 // term active, end of the target, an N) and must be redone by ksw_batch_kernel. Mirrors ksw_rows_p2x2 (ksw.cuh) row
 // for row: same z-drop test, same two-row cadence of the early-stop bound, hence the same `cells`.
+// Traceback layout: the bytes of rows r (even) and r + 1 of a cell pair share one 32-bit word:
+//   tb[(r >> 1) * 128 NB + 4 (i >> 1) + 2 (r & 1) + (i & 1)].
 template <int NB, bool LEFT>
 QS_DEV bool ksw_qs_rows( const QsK& K, const KswScore& P, const SeqAccess& seq, const int qlen, const int tlen,
                          const int w, const int zdrop, KswQsSmem<NB>& sm, unsigned char* __restrict__ tb, KswOut& ez )
@@ -283,11 +327,10 @@ QS_DEV bool ksw_qs_rows( const QsK& K, const KswScore& P, const SeqAccess& seq, 
     const unsigned FULL = 0xffffffffu;
     const int lane = qs_lane( );
     const int q = P.q, e = P.e, q2 = P.q2, e2 = P.e2, scM = P.match;
-    const int stride = 64 * NB;
     const int iSize = qlen > tlen ? qlen : tlen;
     const bool is16 = !( (long long)iSize * P.min16 < -32768 || (long long)iSize * P.match > 32767 );
     const int dl = q + e - P.qe_row0; // H[0] of row 0 uses the scalar qe from before the q / q2 swap (kswcpp_core.h:247)
-    unsigned U[ NB ], V[ NB ], X[ NB ], Y[ NB ], X2[ NB ], Y2[ NB ], H8[ NB ], QP[ NB ], TERM[ NB ], VOFF[ NB ];
+    unsigned U[ NB ], V[ NB ], X[ NB ], Y[ NB ], X2[ NB ], Y2[ NB ], H8[ NB ], QP[ NB ], tbA[ NB ], tbB[ NB ];
     bool anyN = false;
 #pragma unroll
     for( int k = 0; k < NB; k++ )
@@ -299,15 +342,16 @@ QS_DEV bool ksw_qs_rows( const QsK& K, const KswScore& P, const SeqAccess& seq, 
         U[ k ] = 0, Y[ k ] = K.flB, Y2[ k ] = K.flB2;
         X[ k ] = K.flA, X2[ k ] = K.flA2;
         V[ k ] = ( (unsigned)( 8 * ksw_qs_fc( P, i0 ) ) & 0xFFFFu ) | ( (unsigned)( 8 * ksw_qs_fc( P, i1 ) ) << 16 );
-        H8[ k ] = ( (unsigned)( 8 * ( ksw_qs_hborder( P, i0 ) + dl ) ) & 0xFFFFu ) |
-                  ( (unsigned)( 8 * ( ksw_qs_hborder( P, i1 ) + dl ) ) << 16 );
-        TERM[ k ] = ( (unsigned)( i0 < qlen ? 8 * scM * ( qlen - 1 - i0 ) : -MA_QS_NEG ) & 0xFFFFu ) |
-                    ( (unsigned)( i1 < qlen ? 8 * scM * ( qlen - 1 - i1 ) : -MA_QS_NEG ) << 16 );
-        VOFF[ k ] = ( i0 < qlen ? 0u : ( (unsigned)( -MA_QS_NEG ) & 0xFFFFu ) ) |
-                    ( i1 < qlen ? 0u : ( (unsigned)( -MA_QS_NEG ) << 16 ) );
+        // query rows beyond the query (they compute the matrix of a longer query that matches nothing) start MA_QS_NEG
+        // lower: they never reach a maximum
+        H8[ k ] = ( (unsigned)( 8 * ( ksw_qs_hborder( P, i0 ) + dl ) - ( i0 < qlen ? 0 : MA_QS_NEG ) ) & 0xFFFFu ) |
+                  ( (unsigned)( 8 * ( ksw_qs_hborder( P, i1 ) + dl ) - ( i1 < qlen ? 0 : MA_QS_NEG ) ) << 16 );
     }
     if( __any_sync( FULL, anyN ) )
         return false;
+    // early-stop bound: match * (query rows still below the cell), block 0; block k: - 64 k match
+    const unsigned term0 = ( (unsigned)( 8 * scM * ( qlen - 1 - 2 * lane ) ) & 0xFFFFu ) |
+                           ( (unsigned)( 8 * scM * ( qlen - 2 - 2 * lane ) ) << 16 );
     const unsigned nivec0 = ( (unsigned)( -2 * lane ) & 0xFFFFu ) | ( (unsigned)( -2 * lane - 1 ) << 16 ); // -i of block 0
     const int nrows = qlen + tlen - 1;
     const int T0 = scM * qlen;
@@ -315,21 +359,18 @@ QS_DEV bool ksw_qs_rows( const QsK& K, const KswScore& P, const SeqAccess& seq, 
     int lastc = 0; // code of the target base before the next staging chunk
     int ezmax8 = 0, bR = -1;
     unsigned cells = 0;
-    unsigned hbEven = qs_pk( -MA_QS_NEG );
-    bool has2 = false, stop = false;
+    bool stop = false;
     const int srcLane = ( lane + 31 ) & 31;
-    for( int r = 0; r < nrows && !stop; ++r )
+    unsigned* const tbw = reinterpret_cast<unsigned*>( tb ) + lane;
+    for( int r = 0; r < nrows && !stop; r += 2 )
     {
-        if( !( r & 1 ) )
-        {
-            has2 = r + 1 < nrows;
-            const int rl = r + ( has2 ? 1 : 0 );
-            if( rl > w || rl > tlen - 1 )
-                return false; // the band term would become active / the last target column is reached
-            cells += (unsigned)( r + 1 < qlen ? r + 1 : qlen ) + ( has2 ? (unsigned)( r + 2 < qlen ? r + 2 : qlen ) : 0u );
-        }
+        const bool has2 = r + 1 < nrows;
+        const int rl = r + ( has2 ? 1 : 0 );
+        if( rl > w || rl > tlen - 1 )
+            return false; // the band term would become active / the last target column is reached
+        cells += (unsigned)( r + 1 < qlen ? r + 1 : qlen ) + ( has2 ? (unsigned)( r + 2 < qlen ? r + 2 : qlen ) : 0u );
         if( staged <= r + 1 )
-        { // target codes of the next 32 columns (all of them exist: r + 1 < tlen is not required of staged + 31)
+        { // target codes of the next 32 columns
             const int idx = staged + lane;
             const int c = idx < tlen ? seq.T( idx ) : 0;
             if( __any_sync( FULL, c >= 4 ) )
@@ -342,87 +383,123 @@ QS_DEV bool ksw_qs_rows( const QsK& K, const KswScore& P, const SeqAccess& seq, 
             staged += 32;
             __syncwarp( );
         }
-        const int nbAct = ( r >> 6 ) + 1 < NB ? ( r >> 6 ) + 1 : NB;
-        const int kf = ( ( r & 63 ) != 63 && ( r >> 6 ) < NB ) ? ( r >> 6 ) : -1; // block with rows that have not entered
-        unsigned mrow = qs_pk( -MA_QS_NEG ), hb = qs_pk( -MA_QS_NEG );
-        unsigned short* const tbr = reinterpret_cast<unsigned short*>( tb + (size_t)r * stride ) + lane;
-        const int fcr = 8 * ksw_qs_fc( P, r ); // u(-1, r): the value entering query row 0 from above
-#pragma unroll
-        for( int k = NB - 1; k >= 0; --k )
+        // u(-1, r): the value entering query row 0 from above, in the high half
+        const unsigned fcA = (unsigned)( 8 * ksw_qs_fc( P, r ) ) << 16, fcB = (unsigned)( 8 * ksw_qs_fc( P, r + 1 ) ) << 16;
+        unsigned mrowA, mrowB = ksw_qs_pk( -2 * MA_QS_NEG );
+        unsigned hbA = 0, hbB = 0;
+        const bool bBound = has2 && rl >= qlen;
+        if( r >= 64 * NB )
         {
-            if( k >= nbAct )
-                continue;
-            unsigned su = U[ k ], sy = Y[ k ], sy2 = Y2[ k ];
-            if( k > 0 && lane == 31 )
-                su = U[ k - 1 ], sy = Y[ k - 1 ], sy2 = Y2[ k - 1 ];
-            unsigned upU = __shfl_sync( FULL, su, srcLane ), upY = __shfl_sync( FULL, sy, srcLane ),
-                     upY2 = __shfl_sync( FULL, sy2, srcLane );
-            if( k == 0 && lane == 0 )
-                upU = (unsigned)fcr << 16, upY = K.flB, upY2 = K.flB2;
-            const unsigned nbU = __byte_perm( upU, U[ k ], 0x5432 ), nbY = __byte_perm( upY, Y[ k ], 0x5432 ),
-                           nbY2 = __byte_perm( upY2, Y2[ k ], 0x5432 );
-            const unsigned tpw = sm.tp[ ( r - 2 * lane - 64 * k ) & 255 ];
-            const unsigned z0 = ( qs_eqmask2( tpw, QP[ k ] ) & K.zXor ) ^ K.zMis;
-            if( k == kf )
-            {
-                const unsigned tv = __vadd2( qs_pk( r - 64 * k ), nivec0 ); // r - i per half
-                const unsigned ent = ~qs_prmt( tv, 0, 0xBB99 ); // halves with i <= r
-                ksw_qs_cell<LEFT, true>( K, U[ k ], V[ k ], X[ k ], Y[ k ], X2[ k ], Y2[ k ], H8[ k ], nbU, nbY, nbY2, z0,
-                                         ent, VOFF[ k ], TERM[ k ], mrow, hb, tbr + 32 * k );
-            }
-            else
-                ksw_qs_cell<LEFT, false>( K, U[ k ], V[ k ], X[ k ], Y[ k ], X2[ k ], Y2[ k ], H8[ k ], nbU, nbY, nbY2, z0,
-                                          0u, VOFF[ k ], TERM[ k ], mrow, hb, tbr + 32 * k );
-        }
-        const int max8 = __reduce_max_sync( FULL, qs_hmax( mrow ) );
-        // ksw_apply_zdrop (kswcpp_core.h:22-44) with the position resolved only when it is consumed
-        if( max8 > ezmax8 )
-        {
-            ezmax8 = max8, bR = r;
-            __syncwarp( );
-#pragma unroll
-            for( int k = 0; k < NB; k++ )
-                sm.hbest[ lane + 32 * k ] = H8[ k ];
-        }
-        else if( zdrop >= 0 && ezmax8 - max8 > 8 * zdrop )
-        {
-            __syncwarp( );
+            ksw_qs_row<NB, LEFT, true>( K, r, lane, srcLane, fcA, sm.tp, nivec0, U, V, X, Y, X2, Y2, H8, QP, tbA, mrowA );
 #pragma unroll
             for( int k = 0; k < NB; k++ )
                 sm.hcur[ lane + 32 * k ] = H8[ k ];
-            __syncwarp( );
-            int bt = -1, bq = -1;
-            if( bR >= 0 )
-                bt = ksw_qs_argmax( reinterpret_cast<const short*>( sm.hbest ), bR, bR - qlen + 1 > 0 ? bR - qlen + 1 : 0,
-                                    bR, lane, is16 ),
-                bq = bR - bt;
-            const int max_t = ksw_qs_argmax( reinterpret_cast<const short*>( sm.hcur ), r,
-                                             r - qlen + 1 > 0 ? r - qlen + 1 : 0, r, lane, is16 );
-            if( max_t >= bt && r - max_t >= bq )
+            if( bBound )
             {
-                const int tl = max_t - bt, ql = ( r - max_t ) - bq;
-                const int l = tl > ql ? tl - ql : ql - tl;
-                if( ezmax8 - max8 > 8 * ( zdrop + l * e2 ) )
+                hbA = ksw_qs_pk( -2 * MA_QS_NEG );
+#pragma unroll
+                for( int k = 0; k < NB; k++ )
+                    hbA = __viaddmax_s16x2( H8[ k ], __vadd2( term0, ksw_qs_pk( -8 * scM * 64 * k ) ), hbA );
+            }
+            if( has2 )
+                ksw_qs_row<NB, LEFT, true>( K, r + 1, lane, srcLane, fcB, sm.tp, nivec0, U, V, X, Y, X2, Y2, H8, QP, tbB,
+                                            mrowB );
+        }
+        else
+        {
+            ksw_qs_row<NB, LEFT, false>( K, r, lane, srcLane, fcA, sm.tp, nivec0, U, V, X, Y, X2, Y2, H8, QP, tbA, mrowA );
+#pragma unroll
+            for( int k = 0; k < NB; k++ )
+                sm.hcur[ lane + 32 * k ] = H8[ k ];
+            if( bBound )
+            {
+                hbA = ksw_qs_pk( -2 * MA_QS_NEG );
+#pragma unroll
+                for( int k = 0; k < NB; k++ )
+                    hbA = __viaddmax_s16x2( H8[ k ], __vadd2( term0, ksw_qs_pk( -8 * scM * 64 * k ) ), hbA );
+            }
+            if( has2 )
+                ksw_qs_row<NB, LEFT, false>( K, r + 1, lane, srcLane, fcB, sm.tp, nivec0, U, V, X, Y, X2, Y2, H8, QP, tbB,
+                                             mrowB );
+        }
+        if( !has2 )
+        {
+#pragma unroll
+            for( int k = 0; k < NB; k++ )
+                tbB[ k ] = 0;
+        }
+        if( bBound )
+        {
+            hbB = ksw_qs_pk( -2 * MA_QS_NEG );
+#pragma unroll
+            for( int k = 0; k < NB; k++ )
+                hbB = __viaddmax_s16x2( H8[ k ], __vadd2( term0, ksw_qs_pk( -8 * scM * 64 * k ) ), hbB );
+        }
+        // traceback of the two rows: one word per cell pair
+        {
+            unsigned* const tw = tbw + (size_t)( r >> 1 ) * ( 32 * NB );
+#pragma unroll
+            for( int k = 0; k < NB; k++ )
+                tw[ 32 * k ] = __byte_perm( tbA[ k ], tbB[ k ], 0x6420 );
+        }
+        const int maxA = __reduce_max_sync( FULL, qs_hmax( mrowA ) );
+        // unconditional on purpose: ptxas 12.9 predicates `has2 ? __reduce_max_sync(..) : 0` (CREDUX) with a stale
+        // predicate register (profiles/r2c_ptxas_credux_predicate.md); without a second row mrowB is still -2 MA_QS_NEG
+        const int maxB = __reduce_max_sync( FULL, qs_hmax( mrowB ) );
+        // ksw_apply_zdrop (kswcpp_core.h:22-44) row by row, with the position resolved only when it is consumed
+        for( int k2 = 0; k2 < 2; k2++ )
+        {
+            if( k2 == 1 && !has2 )
+                break;
+            const int rr = r + k2, max8 = k2 ? maxB : maxA;
+            if( max8 > ezmax8 )
+            {
+                ezmax8 = max8, bR = rr;
+                __syncwarp( );
+#pragma unroll
+                for( int k = 0; k < NB; k++ )
+                    sm.hbest[ lane + 32 * k ] = k2 ? H8[ k ] : sm.hcur[ lane + 32 * k ];
+            }
+            else if( zdrop >= 0 && ezmax8 - max8 > 8 * zdrop )
+            {
+                __syncwarp( );
+                if( k2 )
                 {
-                    ez.zdropped = 1;
-                    stop = true;
+#pragma unroll
+                    for( int k = 0; k < NB; k++ )
+                        sm.hcur[ lane + 32 * k ] = H8[ k ];
+                }
+                __syncwarp( );
+                int bt = -1, bq = -1;
+                if( bR >= 0 )
+                    bt = ksw_qs_argmax( reinterpret_cast<const short*>( sm.hbest ), bR, bR - qlen + 1 > 0 ? bR - qlen + 1 : 0,
+                                        bR, lane, is16 ),
+                    bq = bR - bt;
+                const int max_t = ksw_qs_argmax( reinterpret_cast<const short*>( sm.hcur ), rr,
+                                                 rr - qlen + 1 > 0 ? rr - qlen + 1 : 0, rr, lane, is16 );
+                if( max_t >= bt && rr - max_t >= bq )
+                {
+                    const int tl = max_t - bt, ql = ( rr - max_t ) - bq;
+                    const int l = tl > ql ? tl - ql : ql - tl;
+                    if( ezmax8 - max8 > 8 * ( zdrop + l * e2 ) )
+                    {
+                        ez.zdropped = 1;
+                        stop = true;
+                        break;
+                    }
                 }
             }
         }
-        if( !( r & 1 ) )
-            hbEven = hb;
-        else if( !stop && r >= qlen )
+        if( !stop && bBound )
         { // early-stop bound over the two rows of the pass (ksw.cuh, ksw_rows_p2x2)
-            const int BA = __reduce_max_sync( FULL, qs_hmax( hbEven ) ), BB = __reduce_max_sync( FULL, qs_hmax( hb ) );
-            const int j = r + 1;
+            const int BA = __reduce_max_sync( FULL, qs_hmax( hbA ) ), BB = __reduce_max_sync( FULL, qs_hmax( hbB ) );
+            const int j = rl + 1;
             const int g1 = q + e * j, g2 = q2 + e2 * j;
             const int T = 8 * ( T0 - ( g1 < g2 ? g1 : g2 ) );
             const int B = BA > BB ? BA : BB;
             if( ( B > T ? B : T ) <= ezmax8 )
                 stop = true;
         }
-        if( stop && !( r & 1 ) && ez.zdropped )
-            break; // (the odd row of the pass is not evaluated after a z-drop in the even row)
     }
     ez.max = ezmax8 >> 3;
     if( bR >= 0 )
@@ -461,7 +538,7 @@ QS_DEV int ksw_qs_backtrack( const unsigned char* tb, const int stride, const bo
     while( i >= 0 && j >= 0 )
     {
         const int r = i + j;
-        const unsigned int tmp = tb[ (size_t)r * stride + j ];
+        const unsigned int tmp = tb[ (size_t)( r >> 1 ) * ( 2 * stride ) + 4 * ( j >> 1 ) + 2 * ( r & 1 ) + ( j & 1 ) ];
         const int tag = tmp & 7;
         const int cell = bLeft ? 4 - tag : tag;
         if( state == 0 )

@@ -7,6 +7,7 @@
 #include "../../oracle/oracle.h"
 #include <algorithm>
 #include <random>
+#include <string>
 #include <vector>
 
 using namespace ma;
@@ -49,7 +50,7 @@ static Result runQs( const KswScore& P, const std::vector<uint8_t>& q, const std
     sa.qbase = slab.data( ), sa.qoff = 0, sa.qstep = 1, sa.tslab = slab.data( ), sa.toff = (long long)q.size( ), sa.tstep = 1;
     sa.pac = nullptr, sa.fwd_len = 0;
     const int qlen = (int)q.size( ), tlen = (int)t.size( );
-    const int rows = std::min( w + 2, qlen + tlen );
+    const int rows = std::min( w + 2, qlen + tlen ) + 1;
     std::vector<unsigned char> tb( (size_t)rows * 64 * NB + 64, 0xEE );
     std::vector<unsigned> cs( (size_t)qlen + tlen + 8 );
     static KswQsSmem<NB> sm;
@@ -86,8 +87,60 @@ static Result runQs( const KswScore& P, const std::vector<uint8_t>& q, const std
     return R;
 }
 
+static int runFile( const char* path )
+{ // lines: w zdrop flag query target (digits), default scores
+    FILE* f = fopen( path, "r" );
+    if( !f )
+        return 2;
+    const KswScore P = makeScore( 2, 4, 4, 2, 24, 1 );
+    static char qb[ 1 << 16 ], tbuf[ 1 << 16 ];
+    int w, zd, fl, n = 0, bad = 0, bail = 0;
+    while( fscanf( f, "%d %d %d %65535s %65535s", &w, &zd, &fl, qb, tbuf ) == 5 )
+    {
+        std::vector<uint8_t> q, t;
+        for( char* c = qb; *c; c++ )
+            q.push_back( (uint8_t)( *c - '0' ) );
+        for( char* c = tbuf; *c; c++ )
+            t.push_back( (uint8_t)( *c - '0' ) );
+        const int ql = (int)q.size( ), tl = (int)t.size( );
+        const int nb = ksw_qs_class( P, ql, tl, w, MA_TASK_EARLYSTOP );
+        const bool left = !( fl & MA_KSW_RIGHT );
+        n++;
+        if( nb == 0 )
+            continue;
+        Result R;
+        if( left )
+            R = nb == 1 ? runQs<1, true>( P, q, t, w, zd, fl ) : nb == 2 ? runQs<2, true>( P, q, t, w, zd, fl )
+                                                                         : runQs<3, true>( P, q, t, w, zd, fl );
+        else
+            R = nb == 1 ? runQs<1, false>( P, q, t, w, zd, fl ) : nb == 2 ? runQs<2, false>( P, q, t, w, zd, fl )
+                                                                          : runQs<3, false>( P, q, t, w, zd, fl );
+        if( !R.ok )
+        {
+            bail++;
+            continue;
+        }
+        ma_oracle_score_t os{ 2, 4, 4, 2, 24, 1 };
+        ma_oracle_ksw_t oz;
+        std::vector<uint32_t> oc( (size_t)ql + tl + 8 );
+        int64_t cells = 0;
+        ma_oracle_ksw( ql, q.data( ), tl, t.data( ), &os, w, zd, fl, &oz, oc.data( ), (int)oc.size( ), &cells );
+        if( R.ez.max != oz.max || R.ez.max_q != oz.max_q || R.ez.max_t != oz.max_t )
+        {
+            bad++;
+            fprintf( stderr, "MISMATCH problem %d: got max %d q %d t %d | ref max %d q %d t %d (qlen %d tlen %d)\n", n - 1,
+                     R.ez.max, R.ez.max_q, R.ez.max_t, oz.max, oz.max_q, oz.max_t, ql, tl );
+        }
+    }
+    fclose( f );
+    printf( "qs_sim file: %d problems, %d handed over, %d MISMATCHES\n", n, bail, bad );
+    return bad ? 1 : 0;
+}
+
 int main( int argc, char** argv )
 {
+    if( argc > 2 && std::string( argv[ 1 ] ) == "file" )
+        return runFile( argv[ 2 ] );
     const int n = argc > 1 ? atoi( argv[ 1 ] ) : 200;
     const unsigned seed = argc > 2 ? (unsigned)atoi( argv[ 2 ] ) : 1;
     std::mt19937_64 rng( seed );
