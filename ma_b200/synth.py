@@ -48,7 +48,7 @@ def revcomp(codes: np.ndarray) -> np.ndarray:
 
 
 def simulate_reads(contigs, n_reads: int, read_len: int, seed: int, sub_rate=0.008, ins_rate=0.001, del_rate=0.001,
-                   strand_both=True, chunk=200_000):
+                   strand_both=True, chunk=200_000, flat=None):
     """Single-end reads: uniform windows, 50 % reverse-complemented, per-base substitution / insertion / deletion.
 
     Returns (reads[n, read_len] uint8, contig_id[n], pos[n], is_rev[n]).
@@ -56,7 +56,7 @@ def simulate_reads(contigs, n_reads: int, read_len: int, seed: int, sub_rate=0.0
     rng = np.random.Generator(np.random.PCG64(seed))
     lens = np.array([len(c) for c in contigs], dtype=np.int64)
     starts = np.concatenate([[0], np.cumsum(lens)])
-    genome = np.concatenate(contigs) if len(contigs) > 1 else contigs[0]
+    genome = flat if flat is not None else (np.concatenate(contigs) if len(contigs) > 1 else contigs[0])
     pad = max(16, int(read_len * (del_rate + ins_rate) * 8) + 16)
     tlen = read_len + pad
     usable = np.maximum(lens - tlen, 1)
@@ -99,7 +99,7 @@ def simulate_reads(contigs, n_reads: int, read_len: int, seed: int, sub_rate=0.0
 
 
 def simulate_pairs(contigs, n_pairs: int, read_len: int, seed: int, sub_rate=0.01, indel_rate=0.01, ins_mean=400,
-                   ins_sd=50, ins_min=300, ins_max=700, chunk=200_000):
+                   ins_sd=50, ins_min=300, ins_max=700, chunk=200_000, flat=None):
     """2x read_len FR pairs, insert size N(ins_mean, ins_sd) clipped to [ins_min, ins_max].
 
     Returns (mate1[n, L], mate2[n, L], contig_id, frag_pos, frag_len, frag_is_rev).  mate1 is the fragment's
@@ -108,7 +108,7 @@ def simulate_pairs(contigs, n_pairs: int, read_len: int, seed: int, sub_rate=0.0
     rng = np.random.Generator(np.random.PCG64(seed))
     lens = np.array([len(c) for c in contigs], dtype=np.int64)
     starts = np.concatenate([[0], np.cumsum(lens)])
-    genome = np.concatenate(contigs) if len(contigs) > 1 else contigs[0]
+    genome = flat if flat is not None else (np.concatenate(contigs) if len(contigs) > 1 else contigs[0])
     pad = 32
     usable = np.maximum(lens - ins_max - pad, 1)
     m1 = np.empty((n_pairs, read_len), dtype=np.uint8)
@@ -162,9 +162,77 @@ def simulate_pairs(contigs, n_pairs: int, read_len: int, seed: int, sub_rate=0.0
     return m1, m2, meta[0], meta[1], meta[2], rev_all
 
 
-def simulate_long_reads(contigs, n_reads: int, read_len: int, seed: int, sub_rate=0.04, ins_rate=0.04, del_rate=0.04):
+def simulate_long_reads(contigs, n_reads: int, read_len: int, seed: int, sub_rate=0.04, ins_rate=0.04, del_rate=0.04,
+                        flat=None):
     """PacBio-like reads (config 4). Same generator as simulate_reads with higher rates."""
-    return simulate_reads(contigs, n_reads, read_len, seed, sub_rate, ins_rate, del_rate, chunk=2000)
+    return simulate_reads(contigs, n_reads, read_len, seed, sub_rate, ins_rate, del_rate, chunk=2000, flat=flat)
+
+
+# ---- fixed read SETS that can be generated shard by shard (BASELINE configs[2] / configs[3]: one set of 10 M pairs /
+# 100 k long reads split over 1, 2, 4 or 8 GPUs): block b of the set is an independent stream seeded with (seed, b),
+# so a rank generates only the blocks its shard overlaps, in parallel worker processes.
+PAIR_BLOCK = 250_000
+LONG_BLOCK = 2_000
+_BLOCK_CTX = None
+
+
+def _block_seed(seed: int, b: int) -> int:
+    return seed * 1_000_003 + b
+
+
+def _pair_block(b):
+    contigs, flat, read_len, seed = _BLOCK_CTX
+    m1, m2, *_ = simulate_pairs(contigs, PAIR_BLOCK, read_len, _block_seed(seed, b), flat=flat)
+    out = np.empty((2 * PAIR_BLOCK, read_len), dtype=np.uint8)  # mates interleaved: read 2i, 2i+1 = pair i
+    out[0::2], out[1::2] = m1, m2
+    return out
+
+
+def _long_block(b):
+    contigs, flat, read_len, seed = _BLOCK_CTX
+    return simulate_long_reads(contigs, LONG_BLOCK, read_len, _block_seed(seed, b), flat=flat)[0]
+
+
+def _blocks(fn, first, last, per_block, ctx, workers):
+    """Units [first, last) of a block-structured set; `workers` forked processes (fork: the genome is shared)."""
+    global _BLOCK_CTX
+    _BLOCK_CTX = ctx
+    bs = list(range(first // per_block, (last + per_block - 1) // per_block)) if last > first else []
+    try:
+        if workers > 1 and len(bs) > 1:
+            import multiprocessing as mp
+            with mp.get_context("fork").Pool(min(workers, len(bs))) as pool:
+                parts = pool.map(fn, bs)
+        else:
+            parts = [fn(b) for b in bs]
+    finally:
+        _BLOCK_CTX = None
+    if not parts:
+        return np.empty((0, ctx[2]), dtype=np.uint8)
+    allr = np.concatenate(parts) if len(parts) > 1 else parts[0]
+    return allr, bs[0] * per_block
+
+
+def pair_set_reads(contigs, first_read: int, last_read: int, read_len: int, seed: int, workers: int = 1, flat=None):
+    """Reads [first_read, last_read) (mates interleaved) of the fixed pair set (seed): block b = PAIR_BLOCK pairs."""
+    if flat is None:
+        flat = np.concatenate(contigs) if len(contigs) > 1 else contigs[0]
+    r = _blocks(_pair_block, first_read // 2, (last_read + 1) // 2, PAIR_BLOCK, (contigs, flat, read_len, seed), workers)
+    if isinstance(r, np.ndarray):
+        return r
+    allr, base_pair = r
+    return allr[first_read - 2 * base_pair:last_read - 2 * base_pair]
+
+
+def long_set_reads(contigs, first_read: int, last_read: int, read_len: int, seed: int, workers: int = 1, flat=None):
+    """Reads [first_read, last_read) of the fixed long-read set (seed): block b = LONG_BLOCK reads."""
+    if flat is None:
+        flat = np.concatenate(contigs) if len(contigs) > 1 else contigs[0]
+    r = _blocks(_long_block, first_read, last_read, LONG_BLOCK, (contigs, flat, read_len, seed), workers)
+    if isinstance(r, np.ndarray):
+        return r
+    allr, base = r
+    return allr[first_read - base:last_read - base]
 
 
 def write_reads_txt(path: str, reads: np.ndarray) -> None:

@@ -8,5 +8,5 @@ grep "dp bin" gpurun_out/bench_err.txt | tail -14 | sort | uniq
 python - <<PY
 import json
 d = json.load(open("gpurun_out/bench_qs.json"))
-print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["kernels"]["ksw_batch_kernel"])
+print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["kernels"]["ksw_kernels"])
 PY

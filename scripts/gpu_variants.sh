@@ -10,6 +10,6 @@ for lib in ma_b200/libma_b200.so ma_b200/variants/*.so; do
   python - <<PY
 import json
 d = json.load(open("gpurun_out/bench_$(basename $lib).json"))
-print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["kernels"]["ksw_batch_kernel"])
+print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["kernels"]["ksw_kernels"])
 PY
 done
