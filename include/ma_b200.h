@@ -198,8 +198,14 @@ typedef struct /* per read: where its seeds / sets / alignments are */
     int32_t n_seeds;
     int32_t set_off; /* also the offset of the read's alignments (one per set) */
     int32_t n_sets;
-    int32_t pad;
+    int32_t status; /* 0, or MA_B200_READ_* bits: the read exceeded a capacity of this implementation; it has no (ELISTS,
+                     * ESEGMENTS, ESETS) or partial (EBAND: the seed sets concerned give empty records) results. The
+                     * reference has no such capacities; the other reads of the batch are not affected. */
 } ma_b200_read_info;
+#define MA_B200_READ_ELISTS 1 /* more than 1 024 SMEM interval-list entries for one seed centre */
+#define MA_B200_READ_ESEGMENTS 2 /* more than min(2 L + 8, 65 536) filtered segments */
+#define MA_B200_READ_ESETS 4 /* more than 128 harmonized seed sets (ma_b200_set_params rejects max_num_soc > 128) */
+#define MA_B200_READ_EBAND 8 /* a DP problem wider than the largest band window (about 2 000 columns) */
 
 typedef struct
 {
@@ -212,6 +218,7 @@ typedef struct
                          result of the same SA interval, see fmindex.cuh SeederSM) */
     float ms_seed, ms_locate, ms_socharm, ms_plan, ms_dp, ms_assemble, ms_total;
     int32_t launches;
+    int32_t n_failed; /* reads with a non-zero ma_b200_read_info::status */
 } ma_b200_align_stats;
 
 /* reads: concatenated, 1 byte per base; offsets[n_reads + 1].  Stays resident until the next upload. */

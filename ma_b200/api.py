@@ -13,8 +13,6 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # MA_B200_LIB: another build of the same library (A/B of compile-time knobs, scripts/); never a different backend
 LIB_PATH = os.environ.get("MA_B200_LIB") or os.path.join(_HERE, "libma_b200.so")
-# experiments only: another build of the same library (e.g. other kernel launch bounds)
-LIB_PATH = os.environ.get("MA_B200_LIB", LIB_PATH)
 
 KSW_RIGHT = 0x02
 KSW_EXTZ_ONLY = 0x40
@@ -64,7 +62,8 @@ ALN_DTYPE = np.dtype([("begin_ref", "<i8"), ("end_ref", "<i8"), ("score", "<i8")
                       ("run_off", "<i8"), ("rank", "<i4"), ("flags", "<i4"), ("mapq", "<f8"), ("rank_mq", "<i4"),
                       ("pair_rank", "<i4")])
 INFO_DTYPE = np.dtype([("seed_off", "<i8"), ("n_seeds", "<i4"), ("set_off", "<i4"), ("n_sets", "<i4"),
-                       ("pad", "<i4")])
+                       ("status", "<i4")])
+READ_ELISTS, READ_ESEGMENTS, READ_ESETS, READ_EBAND = 1, 2, 4, 8
 STAGE_SEEDS, STAGE_SETS, STAGE_ALIGN, STAGE_MAPQ = 1, 2, 3, 4
 ALN_SECONDARY, ALN_SUPPLEMENTARY, ALN_FIRST_MATE = 1, 2, 4
 
@@ -74,7 +73,8 @@ class AlignStats(ctypes.Structure):
                                               "n_cigar_words", "n_ext", "n_invpsi", "n_dropped", "dp_cells",
                                               "n_lookup")] + \
                [(n, ctypes.c_float) for n in ("ms_seed", "ms_locate", "ms_socharm", "ms_plan", "ms_dp",
-                                              "ms_assemble", "ms_total")] + [("launches", ctypes.c_int32)]
+                                              "ms_assemble", "ms_total")] + [("launches", ctypes.c_int32),
+                                                                              ("n_failed", ctypes.c_int32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -272,8 +272,15 @@ class Context:
         alns = np.zeros(cap_alns, dtype=ALN_DTYPE)
         runs = np.zeros(cap_runs, dtype=np.uint32)
         st = AlignStats()
-        self._check(self.lib.ma_b200_align_batch(self.h, n, _ptr(reads), _ptr(offsets), _ptr(info), _ptr(alns),
-                                                 cap_alns, _ptr(runs), cap_runs, ctypes.byref(st)))
+        rc = self.lib.ma_b200_align_batch(self.h, n, _ptr(reads), _ptr(offsets), _ptr(info), _ptr(alns),
+                                          cap_alns, _ptr(runs), cap_runs, ctypes.byref(st))
+        if rc == -3 and (st.n_sets > cap_alns or st.n_runs > cap_runs):
+            # MA_B200_ENOMEM: the record arrays were too small (long reads carry hundreds of runs per alignment); the
+            # results are still on the device and the stats hold the exact counts: fetch them into arrays of that size
+            alns = np.zeros(max(1, st.n_sets), dtype=ALN_DTYPE)
+            runs = np.zeros(max(1, st.n_runs), dtype=np.uint32)
+            rc = self.lib.ma_b200_align_download(self.h, _ptr(info), _ptr(alns), alns.size, _ptr(runs), runs.size)
+        self._check(rc)
         self._stats = st.as_dict()
         return info, alns[:st.n_sets], runs[:st.n_runs], self._stats
 

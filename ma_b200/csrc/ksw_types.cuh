@@ -34,6 +34,7 @@ struct KswScore
 #define MA_TASK_TREV 2 /* target element i is at toff - i */
 #define MA_TASK_TPACK 4 /* target lives in the pack: toff is a position in the virtual forward+reverse text */
 #define MA_TASK_EARLYSTOP 8 /* only max / max_q / max_t / CIGAR are consumed: stop once they are provably final */
+#define MA_TASK_SKIP 16 /* pipeline: the task's seed set was given up (band beyond the largest window), do not run it */
 
 #define MA_KSW_RIGHT 0x02
 #define MA_KSW_EXTZ_ONLY 0x40

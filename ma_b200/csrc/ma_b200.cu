@@ -90,6 +90,16 @@ struct ma_b200_ctx
     PipeCtrl hctrl;
     int64_t n_seeds = 0, n_sets = 0, n_set_seeds = 0, n_tasks = 0, n_runs = 0, n_task_cigar = 0;
     cudaEvent_t ev[ 8 ] = { nullptr };
+    // ---- ma_b200_align_batch, one-shot form: copies on a second stream under the kernels
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy[ 3 ] = { nullptr }; // [0] ready counter reset, [1] upload complete, [2] run words final
+    DevBuf<unsigned long long> reads_ready; // bytes of the read slab that have arrived
+    unsigned long long* h_ready = nullptr; // page-locked: the values copied into reads_ready after each chunk
+    bool upload_in_flight = false; // seed_kernel has to wait on reads_ready
+    uint32_t* early_runs = nullptr; // host destination of the run words, copied as soon as nwasm_kernel is done
+    int64_t early_runs_cap = 0;
+    bool early_runs_done = false;
+    DevBuf<int> off_check; // offsets_check_kernel's result
 };
 
 static KswScore make_score( const ma_b200_params& p )
@@ -225,6 +235,13 @@ extern "C" void ma_b200_destroy( ma_b200_ctx* ctx )
     for( auto& e : ctx->ev )
         if( e )
             cudaEventDestroy( e );
+    for( auto& e : ctx->ev_copy )
+        if( e )
+            cudaEventDestroy( e );
+    if( ctx->copy_stream )
+        cudaStreamDestroy( ctx->copy_stream );
+    if( ctx->h_ready )
+        cudaFreeHost( ctx->h_ready );
     delete ctx;
 }
 
@@ -259,6 +276,32 @@ extern "C" int ma_b200_set_params( ma_b200_ctx* ctx, const ma_b200_params* param
 {
     if( !ctx || !params )
         return MA_B200_EINVAL;
+    // values this implementation cannot honour are refused here instead of producing results that are neither of the
+    // reference's modes (the reference's own parameter classes check ranges the same way, parameter.h:160-215)
+    const ma_b200_params& p = *params;
+    const char* why = nullptr;
+    if( !p.rectangular_soc )
+        why = "rectangular_soc = 0: the strand-split non-rectangular SoC of the SV presets (stripOfConsideration.h:97-112) "
+              "is not implemented";
+    else if( p.seeding_technique != 0 && p.seeding_technique != 1 )
+        why = "seeding_technique must be 0 (maxSpan) or 1 (SMEMs)";
+    else if( p.match <= 0 || p.mismatch < 0 || p.gap < 0 || p.extend < 0 || p.gap2 < 0 || p.extend2 < 0 )
+        why = "scores: match must be positive, penalties non-negative";
+    else if( p.max_num_soc < 1 || p.max_num_soc > MA_MAX_SETS_PER_READ )
+        why = "max_num_soc must be in [1, 128]";
+    else if( p.min_num_soc < 0 || p.max_ambiguity < 0 || p.min_ambiguity < 0 || p.min_seed_length < 0 )
+        why = "min_num_soc, min/max_ambiguity and min_seed_length must be non-negative";
+    else if( p.padding < 0 || p.bandwidth_ext < 1 || p.min_bandwidth_gap < 1 || p.max_gap_area < 0 )
+        why = "padding, max_gap_area must be non-negative and the band widths positive";
+    else if( p.report_n < 0 || p.max_supplementary_per_prim < 0 )
+        why = "report_n and max_supplementary_per_prim must be non-negative";
+    else if( p.use_paired_reads && !( p.paired_std > 0 ) )
+        why = "paired_std must be positive with use_paired_reads";
+    if( why )
+    {
+        ctx->err = std::string( "set_params: " ) + why;
+        return MA_B200_EINVAL;
+    }
     ctx->params = *params;
     return MA_B200_OK;
 }
@@ -815,25 +858,93 @@ static NwParams make_nw_params( const ma_b200_params& p )
                      p.bandwidth_ext, p.min_bandwidth_gap, p.zdrop, make_score( p ).early_return ? 0 : 1 };
 }
 
-extern "C" int ma_b200_align_upload( ma_b200_ctx* ctx, int64_t n_reads, const uint8_t* reads, const int64_t* offsets )
+static void ensure_copy_stream( ma_b200_ctx* ctx )
 {
-    MA_API_BEGIN
+    if( ctx->copy_stream )
+        return;
+    MA_CUDA( cudaStreamCreateWithFlags( &ctx->copy_stream, cudaStreamNonBlocking ) );
+    for( auto& e : ctx->ev_copy )
+        MA_CUDA( cudaEventCreateWithFlags( &e, cudaEventDisableTiming ) );
+    MA_CUDA( cudaHostAlloc( (void**)&ctx->h_ready, 64 * sizeof( unsigned long long ), cudaHostAllocDefault ) );
+}
+
+// Upload of a batch. overlapped: the bases go up in chunks on the copy stream with a counter of arrived reads behind
+// every chunk (seed_kernel waits on it), the offsets are validated on the host while the copies run, and the call
+// returns without waiting for them (ma_b200_align_batch, one-shot form).
+static void align_upload_impl( ma_b200_ctx* ctx, int64_t n_reads, const uint8_t* reads, const int64_t* offsets,
+                               bool overlapped )
+{
     if( n_reads < 0 || n_reads > 0x7ffffff0 || ( n_reads > 0 && ( !reads || !offsets ) ) )
         throw std::runtime_error( "align_upload: bad arguments" );
-    int maxL = 0;
-    for( int64_t i = 0; i < n_reads; i++ )
+    ctx->upload_in_flight = false;
+    const int64_t total = n_reads ? offsets[ n_reads ] : 0;
+    bool bad = total < 0 || ( n_reads && offsets[ 0 ] < 0 );
+    const int nChunks = 16;
+    if( !overlapped || n_reads < 256 || total < ( 1 << 15 ) )
+        overlapped = false;
+    if( overlapped && !bad )
     {
-        const int64_t L = offsets[ i + 1 ] - offsets[ i ];
-        if( L < 0 || L > 0x3fffffff || offsets[ i ] < 0 )
-            throw std::runtime_error( "align_upload: bad offsets" );
-        maxL = std::max<int>( maxL, (int)L );
+        ensure_copy_stream( ctx );
+        ctx->reads.reserve( (size_t)total + 256 );
+        ctx->read_off.reserve( (size_t)n_reads + 1 );
+        ctx->reads_ready.reserve( 1 );
+        cudaStream_t cs = ctx->copy_stream;
+        MA_CUDA( cudaMemsetAsync( ctx->reads_ready.p, 0, sizeof( unsigned long long ), cs ) );
+        MA_CUDA( cudaMemcpyAsync( ctx->read_off.p, offsets, ( n_reads + 1 ) * 8, cudaMemcpyHostToDevice, cs ) );
+        MA_CUDA( cudaEventRecord( ctx->ev_copy[ 0 ], cs ) );
+        int64_t b0 = 0;
+        for( int c = 0; c < nChunks; c++ )
+        { // chunks end on 128-byte lines of the slab; the counter behind the last one covers the rounded-up end
+            int64_t b1 = c + 1 < nChunks ? ( ( total / nChunks * ( c + 1 ) ) + 127 ) & ~(int64_t)127 : total;
+            b1 = std::min( b1, total );
+            if( b1 > b0 )
+                MA_CUDA( cudaMemcpyAsync( ctx->reads.p + b0, reads + b0, b1 - b0, cudaMemcpyHostToDevice, cs ) );
+            ctx->h_ready[ c ] = c + 1 < nChunks ? (unsigned long long)b1 : (unsigned long long)total + 128;
+            MA_CUDA( cudaMemcpyAsync( ctx->reads_ready.p, ctx->h_ready + c, sizeof( unsigned long long ),
+                                      cudaMemcpyHostToDevice, cs ) );
+            b0 = b1;
+        }
+        MA_CUDA( cudaEventRecord( ctx->ev_copy[ 1 ], cs ) );
+        MA_CUDA( cudaStreamWaitEvent( ctx->stream, ctx->ev_copy[ 0 ], 0 ) ); // kernels: after the reset + the offsets
+        ctx->upload_in_flight = true;
+    }
+    int maxL = 0;
+    if( ctx->upload_in_flight )
+    { // the offsets are checked where they already are: one pass of a small kernel instead of a host loop over n reads
+        ctx->off_check.reserve( 2 );
+        int res[ 2 ] = { 0, 0 };
+        MA_CUDA( cudaMemsetAsync( ctx->off_check.p, 0, 2 * sizeof( int ), ctx->stream ) );
+        offsets_check_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>( ctx->read_off.p, n_reads, total, ctx->off_check.p );
+        MA_CUDA( cudaGetLastError( ) );
+        ctx->launches++;
+        MA_CUDA( cudaMemcpyAsync( res, ctx->off_check.p, 2 * sizeof( int ), cudaMemcpyDeviceToHost, ctx->stream ) );
+        MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
+        maxL = res[ 0 ], bad = res[ 1 ] != 0;
+    }
+    else
+        for( int64_t i = 0; i < n_reads && !bad; i++ )
+        {
+            const int64_t L = offsets[ i + 1 ] - offsets[ i ];
+            if( L < 0 || L > 0x3fffffff || offsets[ i ] < 0 )
+                bad = true;
+            maxL = std::max<int>( maxL, (int)L );
+        }
+    if( bad )
+    {
+        if( ctx->upload_in_flight )
+            cudaStreamSynchronize( ctx->copy_stream );
+        ctx->upload_in_flight = false;
+        ctx->n_reads = 0, ctx->stage_done = 0;
+        throw std::runtime_error( "align_upload: bad offsets" );
     }
     ctx->n_reads = n_reads, ctx->max_read_len = maxL, ctx->stage_done = 0;
-    ctx->reads_bytes = n_reads ? offsets[ n_reads ] : 0;
-    ctx->reads.reserve( (size_t)ctx->reads_bytes + 16 );
-    ctx->read_off.reserve( (size_t)n_reads + 1 );
+    ctx->reads_bytes = total;
     ctx->info.reserve( (size_t)n_reads + 1 );
     ctx->ctrl.reserve( 1 );
+    if( ctx->upload_in_flight )
+        return;
+    ctx->reads.reserve( (size_t)ctx->reads_bytes + 16 );
+    ctx->read_off.reserve( (size_t)n_reads + 1 );
     if( n_reads )
     {
         MA_CUDA( cudaMemcpyAsync( ctx->reads.p, reads, ctx->reads_bytes, cudaMemcpyHostToDevice, ctx->stream ) );
@@ -841,6 +952,12 @@ extern "C" int ma_b200_align_upload( ma_b200_ctx* ctx, int64_t n_reads, const ui
                                   ctx->stream ) );
     }
     MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
+}
+
+extern "C" int ma_b200_align_upload( ma_b200_ctx* ctx, int64_t n_reads, const uint8_t* reads, const int64_t* offsets )
+{
+    MA_API_BEGIN
+    align_upload_impl( ctx, n_reads, reads, offsets, false );
     MA_API_END
 }
 
@@ -922,8 +1039,8 @@ static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
             if( phase == 1 )
             {
                 read_ctrl( ctx ); // synchronises: the bins now hold what ksw_qs_kernel handed over
-                if( ctx->hctrl.bin_count[ 15 ] > 0 )
-                    throw std::runtime_error( "DP band wider than the largest supported window (2000 columns)" );
+                if( ctx->hctrl.bin_count[ 15 ] > 0 ) // (nwplan_kernel gives such sets up: MA_READ_EBAND)
+                    throw std::runtime_error( "DP band wider than the largest supported window (internal error)" );
                 for( int b = 0; b < 15; b++ )
                     if( ctx->hctrl.bin_count[ b ] > task_cap )
                         throw std::runtime_error( "pipeline DP: bin list overflow (internal error)" );
@@ -1060,12 +1177,11 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
             A.dbg_segs = ctx->dbg_cap ? ctx->dbg_segs.p : nullptr;
             A.dbg_nsegs = ctx->dbg_cap ? ctx->dbg_nsegs.p : nullptr, A.dbg_cap = ctx->dbg_cap;
             A.ctrl = ctx->ctrl.p;
+            A.reads_ready = ctx->upload_in_flight ? ctx->reads_ready.p : nullptr;
             seed_kernel<<<grid, SB, 0, s>>>( A );
             MA_CUDA( cudaGetLastError( ) );
             ctx->launches++;
             read_ctrl( ctx );
-            if( ctx->hctrl.overflow_lists || ctx->hctrl.overflow_fseg )
-                throw std::runtime_error( "seeding: per-read interval list capacity exceeded (read too repetitive)" );
             if( (long long)ctx->hctrl.seed_cursor <= seedCap )
                 break;
             if( attempt > 0 )
@@ -1076,6 +1192,8 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
         ctx->n_seeds = (int64_t)ctx->hctrl.seed_cursor;
         st.n_ext = (int64_t)ctx->hctrl.n_ext, st.n_lookup = (int64_t)ctx->hctrl.n_lookup, st.n_dropped = (int64_t)ctx->hctrl.n_dropped;
         MA_CUDA( cudaEventRecord( ctx->ev[ 1 ], s ) );
+        if( ctx->upload_in_flight )
+            MA_CUDA( cudaStreamWaitEvent( s, ctx->ev_copy[ 1 ], 0 ) );
         if( ctx->n_seeds > 0 )
         {
             LocateArgs A{ ctx->index, ctx->seeds.p, ctx->n_seeds, ctx->read_off.p, ctx->ctrl.p };
@@ -1107,8 +1225,6 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
                 MA_CUDA( cudaGetLastError( ) );
                 ctx->launches++;
                 read_ctrl( ctx );
-                if( ctx->hctrl.overflow_fseg )
-                    throw std::runtime_error( "harmonization: more than 128 seed sets for one read" );
                 if( ctx->hctrl.scratch_cursor > ctx->harm_scratch.cap )
                     throw std::runtime_error( "harmonization: scratch arena too small (internal error)" );
                 if( (long long)ctx->hctrl.set_seed_cursor <= setSeedCap && (long long)ctx->hctrl.set_cursor <= setCap )
@@ -1140,6 +1256,7 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
                     A.I = ctx->index, A.P = make_nw_params( ctx->params ), A.read_off = ctx->read_off.p;
                     A.sets = ctx->sets.p, A.n_sets = nSets, A.set_seeds = ctx->set_seeds.p;
                     A.tasks = ctx->tasks.p, A.task_cap = taskCap, A.bin_order = ctx->bin_order.p, A.ctrl = ctx->ctrl.p;
+                    A.info = ctx->info.p;
                     nwplan_kernel<<<full_grid( ctx, nwplan_kernel, 128, nSets ), 128, 0, s>>>( A );
                     MA_CUDA( cudaGetLastError( ) );
                     ctx->launches++;
@@ -1198,6 +1315,14 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
                     zero_field( ctx, &PipeCtrl::next_set );
                 }
                 ctx->n_runs = (int64_t)ctx->hctrl.run_cursor;
+                if( ctx->early_runs && ctx->n_runs > 0 && ctx->n_runs <= ctx->early_runs_cap )
+                { // the run words are final: their download runs under the kernels that follow
+                    MA_CUDA( cudaEventRecord( ctx->ev_copy[ 2 ], s ) );
+                    MA_CUDA( cudaStreamWaitEvent( ctx->copy_stream, ctx->ev_copy[ 2 ], 0 ) );
+                    MA_CUDA( cudaMemcpyAsync( ctx->early_runs, ctx->runs.p, ctx->n_runs * sizeof( unsigned int ),
+                                              cudaMemcpyDeviceToHost, ctx->copy_stream ) );
+                    ctx->early_runs_done = true;
+                }
                 AlnSortArgs B{ ctx->info.p, n, ctx->alns.p, ctx->ctrl.p };
                 alnsort_kernel<<<full_grid( ctx, alnsort_kernel, 128, n ), 128, 0, s>>>( B );
                 MA_CUDA( cudaGetLastError( ) );
@@ -1257,6 +1382,7 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
     st.ms_dp = ev_ms( ctx->ev[ 4 ], ctx->ev[ 5 ] ), st.ms_assemble = ev_ms( ctx->ev[ 5 ], ctx->ev[ 6 ] );
     st.ms_total = ev_ms( ctx->ev[ 0 ], ctx->ev[ 6 ] );
     st.launches = (int)( ctx->launches - launches0 );
+    st.n_failed = n > 0 ? ctx->hctrl.n_failed : 0;
     if( stats )
         *stats = st;
     MA_API_END
@@ -1365,10 +1491,12 @@ extern "C" int ma_b200_align_download( ma_b200_ctx* ctx, ma_b200_read_info* info
     if( ctx->n_sets )
         MA_CUDA( cudaMemcpyAsync( alns, ctx->alns.p, ctx->n_sets * sizeof( DAln ), cudaMemcpyDeviceToHost,
                                   ctx->stream ) );
-    if( ctx->n_runs )
+    if( ctx->n_runs && !( ctx->early_runs_done && runs == ctx->early_runs ) )
         MA_CUDA( cudaMemcpyAsync( runs, ctx->runs.p, ctx->n_runs * sizeof( unsigned int ), cudaMemcpyDeviceToHost,
                                   ctx->stream ) );
     MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    if( ctx->early_runs_done )
+        MA_CUDA( cudaStreamSynchronize( ctx->copy_stream ) );
     MA_API_END
 }
 
@@ -1473,14 +1601,38 @@ extern "C" int ma_b200_align_batch( ma_b200_ctx* ctx, int64_t n_reads, const uin
     if( !ctx )
         return MA_B200_EINVAL;
     if( ctx->batch_split <= 0 || n_reads < 2 * ( ctx->batch_split + ( ctx->batch_split & 1 ) ) || !ctx->have_index || !reads || !offsets || !info || !alns || !runs )
-    { // one shot (also the path that reports argument errors)
-        int rc = ma_b200_align_upload( ctx, n_reads, reads, offsets );
-        if( rc )
-            return rc;
-        rc = ma_b200_align_run( ctx, MA_B200_STAGE_MAPQ, 0, stats );
-        if( rc )
-            return rc;
-        return ma_b200_align_download( ctx, info, alns, cap_alns, runs, cap_runs );
+    { // one shot (also the path that reports argument errors): the upload runs under the seeding kernel, the download
+      // of the run words under the kernels of stage 4
+        int rc = MA_B200_OK;
+        try
+        {
+            MA_CUDA( cudaSetDevice( ctx->device ) );
+            ensure_copy_stream( ctx );
+            align_upload_impl( ctx, n_reads, reads, offsets, true );
+        }
+        catch( const ma::CudaError& e )
+        {
+            ctx->err = e.msg, rc = MA_B200_ECUDA;
+        }
+        catch( const std::exception& e )
+        {
+            ctx->err = e.what( ), rc = MA_B200_EINVAL;
+        }
+        ctx->early_runs = runs, ctx->early_runs_cap = runs ? cap_runs : 0, ctx->early_runs_done = false;
+        if( !rc )
+            rc = ma_b200_align_run( ctx, MA_B200_STAGE_MAPQ, 0, stats );
+        if( ctx->upload_in_flight )
+        { // whatever happened above, nothing of the caller's buffers may still be in flight when this call returns
+            cudaStreamSynchronize( ctx->copy_stream );
+            ctx->upload_in_flight = false;
+        }
+        ctx->early_runs = nullptr;
+        if( !rc )
+            rc = ma_b200_align_download( ctx, info, alns, cap_alns, runs, cap_runs );
+        else if( ctx->early_runs_done )
+            cudaStreamSynchronize( ctx->copy_stream );
+        ctx->early_runs_done = false;
+        return rc;
     }
     if( !ctx->shadow )
     {
@@ -1522,6 +1674,7 @@ extern "C" int ma_b200_align_batch( ma_b200_ctx* ctx, int64_t n_reads, const uin
             t.n_reads += s.n_reads, t.n_seeds += s.n_seeds, t.n_sets += s.n_sets, t.n_set_seeds += s.n_set_seeds;
             t.n_tasks += s.n_tasks, t.n_runs += s.n_runs, t.n_cigar_words += s.n_cigar_words, t.n_ext += s.n_ext;
             t.n_invpsi += s.n_invpsi, t.n_dropped += s.n_dropped, t.dp_cells += s.dp_cells, t.n_lookup += s.n_lookup;
+            t.n_failed += s.n_failed;
             t.ms_seed += s.ms_seed, t.ms_locate += s.ms_locate, t.ms_socharm += s.ms_socharm, t.ms_plan += s.ms_plan;
             t.ms_dp += s.ms_dp, t.ms_assemble += s.ms_assemble, t.ms_total += s.ms_total;
         }

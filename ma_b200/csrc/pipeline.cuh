@@ -42,11 +42,36 @@ struct PipeCtrl
     unsigned long long n_dropped; // reads cleared by the seeding drop-off heuristic
     int overflow_lists, overflow_fseg, overflow_runs, overflow_pair;
     int max_reported; // largest MappingQuality result vector of the batch
+    int n_failed; // reads with a non-zero ReadInfo::status
     // DP task bins: window class (5) x kind (exact / early-stop left / early-stop right), + 1 for "band too wide"
     alignas( 128 ) int bin_count[ MA_NBINS ];
     alignas( 128 ) unsigned long long bin_tb[ MA_NBINS ];
     alignas( 128 ) int bin_cig[ MA_NBINS ];
 };
+
+// read offsets of a batch checked on the device (ma_b200_align_batch: the host does not walk the array again):
+// out[0] = longest read, out[1] = 1 if an offset is negative, decreasing, beyond `total`, or a read longer than 2^30 - 1
+__global__ void __launch_bounds__( 256 ) offsets_check_kernel( const long long* off, long long n, long long total, int* out )
+{
+    int maxL = 0, bad = 0;
+    for( long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x )
+    {
+        const long long a = off[ i ], b = off[ i + 1 ];
+        const long long L = b - a;
+        if( a < 0 || L < 0 || L > 0x3fffffff || b > total )
+            bad = 1;
+        else
+            maxL = L > maxL ? (int)L : maxL;
+    }
+    maxL = __reduce_max_sync( 0xffffffffu, maxL ), bad = __reduce_max_sync( 0xffffffffu, bad );
+    if( ( threadIdx.x & 31 ) == 0 )
+    {
+        if( maxL )
+            atomicMax( &out[ 0 ], maxL );
+        if( bad )
+            atomicExch( &out[ 1 ], 1 );
+    }
+}
 
 struct ReadInfo // per read
 {
@@ -54,8 +79,12 @@ struct ReadInfo // per read
     int n_seeds;
     int set_off; // first set header
     int n_sets;
-    int pad;
+    int status; // 0, or MA_READ_* bits: the read ran into a capacity of this implementation and has no / partial results
 };
+#define MA_READ_ELISTS 1 /* more SMEM interval-list entries than the per-read capacity (seeding) */
+#define MA_READ_ESEGMENTS 2 /* more filtered segments than the per-read capacity (seeding) */
+#define MA_READ_ESETS 4 /* more harmonized seed sets than MA_MAX_SETS_PER_READ */
+#define MA_READ_EBAND 8 /* a DP problem of one of its seed sets needs a band wider than the largest window */
 
 struct SetHeader
 {
@@ -94,6 +123,9 @@ struct SeedKernelArgs
     int* dbg_nsegs;
     int dbg_cap;
     PipeCtrl* ctrl;
+    // ma_b200_align_batch: the bytes [0, *reads_ready) of the read slab have arrived (the upload runs under this kernel,
+    // in chunks that end on 128-byte lines); nullptr: all resident
+    const unsigned long long* reads_ready;
 };
 
 struct SeedSink
@@ -171,6 +203,12 @@ __global__ void __launch_bounds__( MA_SEED_BLOCK, MA_SEED_MINB ) seed_kernel( Se
             {
                 const long long off = A.read_off[ read ];
                 L = (int)( A.read_off[ read + 1 ] - off );
+                if( A.reads_ready )
+                { // every cache line this read touches must have arrived completely (lines are not re-fetched)
+                    const unsigned long long need = ( (unsigned long long)( off + L ) + 127ull ) & ~127ull;
+                    while( *( (const volatile unsigned long long*)A.reads_ready ) < need )
+                        __nanosleep( 500 );
+                }
                 sink.n = 0, sink.nSeeds = 0, sink.dropSum = 0, sink.overflow = false, sink.nAll = 0;
                 sink.dbg = A.dbg_segs ? A.dbg_segs + (size_t)read * A.dbg_cap : nullptr;
                 S.begin( A.reads + off, L );
@@ -185,10 +223,10 @@ __global__ void __launch_bounds__( MA_SEED_BLOCK, MA_SEED_MINB ) seed_kernel( Se
             if( !need )
             { // the read is finished: drop-off heuristic (binarySeeding.cpp:172-175) and seed enumeration
                 nExtLocal += (unsigned long long)S.nExt, nLookupLocal += (unsigned long long)S.nLookup;
-                if( S.overflow )
-                    atomicExch( &A.ctrl->overflow_lists, 1 );
-                if( sink.overflow )
-                    atomicExch( &A.ctrl->overflow_fseg, 1 );
+                // a read that exceeds a per-read capacity is reported as such and gets no seeds; the batch goes on
+                const int status = ( S.overflow ? MA_READ_ELISTS : 0 ) | ( sink.overflow ? MA_READ_ESEGMENTS : 0 );
+                if( status )
+                    atomicAdd( &A.ctrl->n_failed, 1 );
                 const bool bClear = !A.P.disable_heuristics && A.P.drop_min_size != 0 &&
                                     (double)sink.dropSum < A.P.drop_factor * (double)L &&
                                     (unsigned long long)A.P.genome_size_disable < (unsigned long long)A.I.ref_len;
@@ -196,14 +234,14 @@ __global__ void __launch_bounds__( MA_SEED_BLOCK, MA_SEED_MINB ) seed_kernel( Se
                     nDropped++;
                 if( A.dbg_nsegs )
                     A.dbg_nsegs[ read ] = bClear ? 0 : sink.nAll;
-                const long long nSeeds = bClear ? 0 : sink.nSeeds;
+                const long long nSeeds = ( bClear || status ) ? 0 : sink.nSeeds;
                 long long so = 0;
                 if( nSeeds > 0 )
                     so = (long long)atomicAdd( &A.ctrl->seed_cursor, (unsigned long long)nSeeds );
                 ReadInfo ri;
-                ri.seed_off = so, ri.n_seeds = (int)nSeeds, ri.set_off = 0, ri.n_sets = 0, ri.pad = 0;
+                ri.seed_off = so, ri.n_seeds = (int)nSeeds, ri.set_off = 0, ri.n_sets = 0, ri.status = status;
                 A.info[ read ] = ri;
-                if( nSeeds > 0 && so + nSeeds <= A.seed_cap && !sink.overflow )
+                if( nSeeds > 0 && so + nSeeds <= A.seed_cap )
                 {
                     long long k = so;
                     const int nf = sink.n;
@@ -302,7 +340,6 @@ struct DevSetSink
     int n[ MA_MAX_SETS_PER_READ ];
     unsigned int soc[ MA_MAX_SETS_PER_READ ];
     int count = 0;
-    bool overflow = false;
     __device__ void set( const DSeed* p, int m, unsigned int socIndex )
     {
         const long long o = (long long)atomicAdd( &ctrl->set_seed_cursor, (unsigned long long)m );
@@ -311,9 +348,7 @@ struct DevSetSink
                 slab[ o + i ] = p[ i ];
         if( count < MA_MAX_SETS_PER_READ )
             off[ count ] = o, n[ count ] = m, soc[ count ] = socIndex;
-        else
-            overflow = true;
-        count++;
+        count++; // (the caller checks the final count: pop_back may bring it back under the capacity)
     }
     __device__ void pop_back( unsigned int counter, unsigned int minTries )
     {
@@ -354,9 +389,13 @@ __global__ void __launch_bounds__( MA_SOC_BLOCK, MA_SOC_MINB ) socharm_kernel( S
                 sink.slab = A.set_seeds, sink.cap = A.set_seed_cap, sink.ctrl = A.ctrl, sink.read = read;
                 const int qlen = (int)( A.read_off[ read + 1 ] - A.read_off[ read ] );
                 soc_harm_read( A.I, A.P, S, n, qlen, A.srand_base + (unsigned int)read, W, sink, 0 );
-                if( sink.overflow )
-                    atomicExch( &A.ctrl->overflow_fseg, 1 );
-                const int ns = sink.count < MA_MAX_SETS_PER_READ ? sink.count : MA_MAX_SETS_PER_READ;
+                int ns = sink.count;
+                if( ns > MA_MAX_SETS_PER_READ )
+                { // reported per read (ma_b200_set_params rejects max_num_soc > MA_MAX_SETS_PER_READ, so: not reachable)
+                    if( !( ri.status & MA_READ_ESETS ) )
+                        atomicAdd( &A.ctrl->n_failed, 1 );
+                    ns = 0, ri.status |= MA_READ_ESETS;
+                }
                 if( ns > 0 )
                 {
                     const long long ho = (long long)atomicAdd( &A.ctrl->set_cursor, (unsigned long long)ns );
@@ -389,6 +428,7 @@ struct NwPlanArgs
     long long task_cap;
     int* bin_order; // [n_bins][task_cap] task ids per window bin
     PipeCtrl* ctrl;
+    ReadInfo* info;
 };
 
 // One thread per seed set: window, task count, one warp-aggregated slot allocation, tasks.
@@ -445,6 +485,19 @@ __global__ void __launch_bounds__( 128 ) nwplan_kernel( NwPlanArgs A )
                 {
                     NwPlanner pl( A.P, A.tasks + to, qbase, (long long)w.beginRef );
                     nw_walk( S, h.n, qlen, w, pl );
+                    // a band wider than the largest window of ksw_batch_kernel: the set yields no alignment and the
+                    // read is reported (ReadInfo::status), the batch goes on
+                    bool tooWide = false;
+                    for( int t = 0; t < nTasks; t++ )
+                        tooWide |= ksw_bin_of( ksw_ncol16( A.tasks[ to + t ].qlen, A.tasks[ to + t ].tlen, A.tasks[ to + t ].w ) ) >= 5;
+                    if( tooWide )
+                    {
+                        for( int t = 0; t < nTasks; t++ )
+                            A.tasks[ to + t ].tag |= MA_TASK_SKIP;
+                        h.valid = 0;
+                        if( !( atomicOr( &A.info[ h.read ].status, MA_READ_EBAND ) & MA_READ_EBAND ) )
+                            atomicAdd( &A.ctrl->n_failed, 1 );
+                    }
                 }
             }
             A.sets[ si ] = h;
@@ -477,6 +530,7 @@ __global__ void __launch_bounds__( 256 ) nwbin_kernel( NwBinArgs A )
         {
             const KswTask T = A.tasks[ ti ];
             const int nc = ksw_ncol16( T.qlen, T.tlen, T.w );
+            const bool skip = ( T.tag & MA_TASK_SKIP ) != 0;
             // all warps of a launch should run the same instantiation of the row loop (the kernel is large and a mix
             // of code paths thrashes the instruction cache): tasks are binned by window class AND kind
             const int wc = ksw_bin_of( nc );
@@ -491,6 +545,8 @@ __global__ void __launch_bounds__( 256 ) nwbin_kernel( NwBinArgs A )
             }
             tb = bytes > 0xffffffffull ? 0xffffffffu : (unsigned int)bytes; // in units of 256 bytes
             cig = (unsigned int)( ( T.qlen + T.tlen + 2 + 63 ) & ~63 );
+            if( skip )
+                b = MA_NBINS, tb = 0, cig = 0;
         }
         const unsigned m = __match_any_sync( FULL, b );
         const int leader = __ffs( m ) - 1;

@@ -360,3 +360,42 @@ def test_non_default_dp_parameters_against_oracle(gold_index, overrides, tmp_pat
                               PC.SRAND, 5, overrides)
     PC.assert_same_stages(got, exp, what=str(overrides))
     ctx.close()
+
+
+def test_set_params_rejects_what_is_not_implemented():
+    """Values the device path cannot honour are refused (MA_B200_EINVAL) instead of giving non-reference results:
+    the non-rectangular SoC of the SV presets, more SoCs than the per-read capacity, nonsense scores."""
+    ctx = api.Context(0, "illumina")
+    for field, value in (("rectangular_soc", 0), ("max_num_soc", 129), ("max_num_soc", 0), ("seeding_technique", 2),
+                         ("match", 0), ("extend2", -1), ("bandwidth_ext", 0)):
+        p = api.preset("illumina")
+        setattr(p, field, value)
+        with pytest.raises(api.MaB200Error, match="error -2"):
+            ctx.set_params(p)
+    ctx.set_params(api.preset("illumina"))  # the context keeps working
+    ctx.close()
+
+
+def test_read_beyond_a_capacity_is_reported_per_read(gold_index):
+    """A DP problem wider than the largest band window (bandwidth_ext 2500, a 2 300-base unalignable read tail) flags
+    ONE read (ma_b200_read_info.status, stats.n_failed) — the records of all other reads of the batch are the same as
+    without it (the reference has no such capacity; a batch must not die of one read)."""
+    reads = [r for r in PC.read_reads_txt(PC.gold_reads("pacbio"))]
+    fwd = gold_index.forward_codes()
+    rng = np.random.Generator(np.random.PCG64(5))
+    bad = np.concatenate([fwd[2000:3500], rng.integers(0, 4, 2300, dtype=np.uint8)])
+    out = []
+    for batch in (reads, reads + [bad]):
+        ctx = api.Context(0, "pacbio")
+        p = api.preset("pacbio")
+        p.srand_base, p.bandwidth_ext = PC.SRAND, 2500
+        ctx.set_params(p)
+        ctx.index_upload(gold_index)
+        data, off = api.pack_reads(batch)
+        info, alns, runs, st = ctx.align_batch(data, off)
+        out.append((info, _records(info, alns, runs, len(reads)), st))
+        ctx.close()
+    (i0, r0, s0), (i1, r1, s1) = out
+    assert s0["n_failed"] == 0 and (i0["status"] == 0).all()
+    assert s1["n_failed"] == 1 and (i1["status"][:-1] == 0).all() and i1["status"][-1] == api.READ_EBAND, (i1[-1], s1)
+    assert r0 == r1
