@@ -377,7 +377,7 @@ def test_set_params_rejects_what_is_not_implemented():
 
 
 def test_read_beyond_a_capacity_is_reported_per_read(gold_index):
-    """A DP problem wider than the largest band window (bandwidth_ext 2500, a 2 300-base unalignable read tail) flags
+    """A DP problem wider than the largest band window (bandwidth_ext 2500, padding 3000, a 2 300-base unalignable read tail) flags
     ONE read (ma_b200_read_info.status, stats.n_failed) — the records of all other reads of the batch are the same as
     without it (the reference has no such capacity; a batch must not die of one read)."""
     reads = [r for r in PC.read_reads_txt(PC.gold_reads("pacbio"))]
@@ -388,7 +388,7 @@ def test_read_beyond_a_capacity_is_reported_per_read(gold_index):
     for batch in (reads, reads + [bad]):
         ctx = api.Context(0, "pacbio")
         p = api.preset("pacbio")
-        p.srand_base, p.bandwidth_ext = PC.SRAND, 2500
+        p.srand_base, p.bandwidth_ext, p.padding = PC.SRAND, 2500, 3000
         ctx.set_params(p)
         ctx.index_upload(gold_index)
         data, off = api.pack_reads(batch)
@@ -396,6 +396,10 @@ def test_read_beyond_a_capacity_is_reported_per_read(gold_index):
         out.append((info, _records(info, alns, runs, len(reads)), st))
         ctx.close()
     (i0, r0, s0), (i1, r1, s1) = out
-    assert s0["n_failed"] == 0 and (i0["status"] == 0).all()
-    assert s1["n_failed"] == 1 and (i1["status"][:-1] == 0).all() and i1["status"][-1] == api.READ_EBAND, (i1[-1], s1)
-    assert r0 == r1
+    n = len(reads)
+    # (with these parameters a few of the golden reads run into the capacity themselves: equally in both batches)
+    assert np.array_equal(i0["status"], i1["status"][:n]) and (i0["status"] == 0).sum() >= 3
+    assert i1["status"][n] == api.READ_EBAND, (i1[n], s1)
+    assert s0["n_failed"] == int((i0["status"] != 0).sum()) and s1["n_failed"] == s0["n_failed"] + 1
+    ok = set(np.nonzero(i0["status"] == 0)[0].tolist())
+    assert [r for r in r0 if r[0] in ok] == [r for r in r1 if r[0] in ok] and len(ok) > 0
