@@ -349,26 +349,33 @@ QS_DEV bool ksw_qs_rows( const QsK& K, const KswScore& P, const SeqAccess& seq, 
     }
     if( __any_sync( FULL, anyN ) )
         return false;
-    // early-stop bound: match * (query rows still below the cell), block 0; block k: - 64 k match
-    const unsigned term0 = ( (unsigned)( 8 * scM * ( qlen - 1 - 2 * lane ) ) & 0xFFFFu ) |
-                           ( (unsigned)( 8 * scM * ( qlen - 2 - 2 * lane ) ) << 16 );
+    // early-stop bound: match * (query rows still below the cell) per block, kept in registers over the whole problem
+    // (the empty asm keeps the compiler from re-deriving them from the lane index in every pass)
+    unsigned TERM[ NB ];
+#pragma unroll
+    for( int k = 0; k < NB; k++ )
+    {
+        TERM[ k ] = ( (unsigned)( 8 * scM * ( qlen - 1 - 2 * lane - 64 * k ) ) & 0xFFFFu ) |
+                    ( (unsigned)( 8 * scM * ( qlen - 2 - 2 * lane - 64 * k ) ) << 16 );
+        asm volatile( "" : "+r"( TERM[ k ] ) );
+    }
     const unsigned nivec0 = ( (unsigned)( -2 * lane ) & 0xFFFFu ) | ( (unsigned)( -2 * lane - 1 ) << 16 ); // -i of block 0
     const int nrows = qlen + tlen - 1;
     const int T0 = scM * qlen;
+    const unsigned fcLate = (unsigned)( -8 * e2 ) << 16; // u(-1, r) of the rows beyond the long-gap threshold
     int staged = 0;
     int lastc = 0; // code of the target base before the next staging chunk
     int ezmax8 = 0, bR = -1;
-    unsigned cells = 0;
     bool stop = false;
     const int srcLane = ( lane + 31 ) & 31;
-    unsigned* const tbw = reinterpret_cast<unsigned*>( tb ) + lane;
-    for( int r = 0; r < nrows && !stop; r += 2 )
+    unsigned* tw = reinterpret_cast<unsigned*>( tb ) + lane; // traceback words of the current pass
+    int r = 0;
+    for( ; r < nrows && !stop; r += 2, tw += 32 * NB )
     {
         const bool has2 = r + 1 < nrows;
         const int rl = r + ( has2 ? 1 : 0 );
         if( rl > w || rl > tlen - 1 )
             return false; // the band term would become active / the last target column is reached
-        cells += (unsigned)( r + 1 < qlen ? r + 1 : qlen ) + ( has2 ? (unsigned)( r + 2 < qlen ? r + 2 : qlen ) : 0u );
         if( staged <= r + 1 )
         { // target codes of the next 32 columns
             const int idx = staged + lane;
@@ -384,23 +391,19 @@ QS_DEV bool ksw_qs_rows( const QsK& K, const KswScore& P, const SeqAccess& seq, 
             __syncwarp( );
         }
         // u(-1, r): the value entering query row 0 from above, in the high half
-        const unsigned fcA = (unsigned)( 8 * ksw_qs_fc( P, r ) ) << 16, fcB = (unsigned)( 8 * ksw_qs_fc( P, r + 1 ) ) << 16;
+        unsigned fcA = fcLate, fcB = fcLate;
+        if( r <= P.long_thres || r == 0 )
+            fcA = (unsigned)( 8 * ksw_qs_fc( P, r ) ) << 16, fcB = (unsigned)( 8 * ksw_qs_fc( P, r + 1 ) ) << 16;
         unsigned mrowA, mrowB = ksw_qs_pk( -2 * MA_QS_NEG );
-        unsigned hbA = 0, hbB = 0;
+        unsigned hb = ksw_qs_pk( -2 * MA_QS_NEG ); // bound over both rows of the pass (only its maximum is used)
+        unsigned HA[ NB ]; // H of row r (position of a maximum / z-drop test of that row)
         const bool bBound = has2 && rl >= qlen;
         if( r >= 64 * NB )
         {
             ksw_qs_row<NB, LEFT, true>( K, r, lane, srcLane, fcA, sm.tp, nivec0, U, V, X, Y, X2, Y2, H8, QP, tbA, mrowA );
 #pragma unroll
             for( int k = 0; k < NB; k++ )
-                sm.hcur[ lane + 32 * k ] = H8[ k ];
-            if( bBound )
-            {
-                hbA = ksw_qs_pk( -2 * MA_QS_NEG );
-#pragma unroll
-                for( int k = 0; k < NB; k++ )
-                    hbA = __viaddmax_s16x2( H8[ k ], __vadd2( term0, ksw_qs_pk( -8 * scM * 64 * k ) ), hbA );
-            }
+                HA[ k ] = H8[ k ];
             if( has2 )
                 ksw_qs_row<NB, LEFT, true>( K, r + 1, lane, srcLane, fcB, sm.tp, nivec0, U, V, X, Y, X2, Y2, H8, QP, tbB,
                                             mrowB );
@@ -410,14 +413,7 @@ QS_DEV bool ksw_qs_rows( const QsK& K, const KswScore& P, const SeqAccess& seq, 
             ksw_qs_row<NB, LEFT, false>( K, r, lane, srcLane, fcA, sm.tp, nivec0, U, V, X, Y, X2, Y2, H8, QP, tbA, mrowA );
 #pragma unroll
             for( int k = 0; k < NB; k++ )
-                sm.hcur[ lane + 32 * k ] = H8[ k ];
-            if( bBound )
-            {
-                hbA = ksw_qs_pk( -2 * MA_QS_NEG );
-#pragma unroll
-                for( int k = 0; k < NB; k++ )
-                    hbA = __viaddmax_s16x2( H8[ k ], __vadd2( term0, ksw_qs_pk( -8 * scM * 64 * k ) ), hbA );
-            }
+                HA[ k ] = H8[ k ];
             if( has2 )
                 ksw_qs_row<NB, LEFT, false>( K, r + 1, lane, srcLane, fcB, sm.tp, nivec0, U, V, X, Y, X2, Y2, H8, QP, tbB,
                                              mrowB );
@@ -430,18 +426,14 @@ QS_DEV bool ksw_qs_rows( const QsK& K, const KswScore& P, const SeqAccess& seq, 
         }
         if( bBound )
         {
-            hbB = ksw_qs_pk( -2 * MA_QS_NEG );
 #pragma unroll
             for( int k = 0; k < NB; k++ )
-                hbB = __viaddmax_s16x2( H8[ k ], __vadd2( term0, ksw_qs_pk( -8 * scM * 64 * k ) ), hbB );
+                hb = __viaddmax_s16x2( H8[ k ], TERM[ k ], __viaddmax_s16x2( HA[ k ], TERM[ k ], hb ) );
         }
         // traceback of the two rows: one word per cell pair
-        {
-            unsigned* const tw = tbw + (size_t)( r >> 1 ) * ( 32 * NB );
 #pragma unroll
-            for( int k = 0; k < NB; k++ )
-                tw[ 32 * k ] = __byte_perm( tbA[ k ], tbB[ k ], 0x6420 );
-        }
+        for( int k = 0; k < NB; k++ )
+            tw[ 32 * k ] = __byte_perm( tbA[ k ], tbB[ k ], 0x6420 );
         const int maxA = __reduce_max_sync( FULL, qs_hmax( mrowA ) );
         // unconditional on purpose: ptxas 12.9 predicates `has2 ? __reduce_max_sync(..) : 0` (CREDUX) with a stale
         // predicate register (profiles/r2c_ptxas_credux_predicate.md); without a second row mrowB is still -2 MA_QS_NEG
@@ -458,17 +450,14 @@ QS_DEV bool ksw_qs_rows( const QsK& K, const KswScore& P, const SeqAccess& seq, 
                 __syncwarp( );
 #pragma unroll
                 for( int k = 0; k < NB; k++ )
-                    sm.hbest[ lane + 32 * k ] = k2 ? H8[ k ] : sm.hcur[ lane + 32 * k ];
+                    sm.hbest[ lane + 32 * k ] = k2 ? H8[ k ] : HA[ k ];
             }
             else if( zdrop >= 0 && ezmax8 - max8 > 8 * zdrop )
             {
                 __syncwarp( );
-                if( k2 )
-                {
 #pragma unroll
-                    for( int k = 0; k < NB; k++ )
-                        sm.hcur[ lane + 32 * k ] = H8[ k ];
-                }
+                for( int k = 0; k < NB; k++ )
+                    sm.hcur[ lane + 32 * k ] = k2 ? H8[ k ] : HA[ k ];
                 __syncwarp( );
                 int bt = -1, bq = -1;
                 if( bR >= 0 )
@@ -492,15 +481,21 @@ QS_DEV bool ksw_qs_rows( const QsK& K, const KswScore& P, const SeqAccess& seq, 
         }
         if( !stop && bBound )
         { // early-stop bound over the two rows of the pass (ksw.cuh, ksw_rows_p2x2)
-            const int BA = __reduce_max_sync( FULL, qs_hmax( hbA ) ), BB = __reduce_max_sync( FULL, qs_hmax( hbB ) );
-            const int j = rl + 1;
-            const int g1 = q + e * j, g2 = q2 + e2 * j;
-            const int T = 8 * ( T0 - ( g1 < g2 ? g1 : g2 ) );
-            const int B = BA > BB ? BA : BB;
-            if( ( B > T ? B : T ) <= ezmax8 )
-                stop = true;
+            const int B = __reduce_max_sync( FULL, qs_hmax( hb ) );
+            if( B <= ezmax8 )
+            { // (the bound through query row 0 only matters once the cell bound has fallen below the maximum)
+                const int j = rl + 1;
+                const int g1 = q + e * j, g2 = q2 + e2 * j;
+                const int T = 8 * ( T0 - ( g1 < g2 ? g1 : g2 ) );
+                if( T <= ezmax8 )
+                    stop = true;
+            }
         }
     }
+    // band cells of the rows of all passes that were started (both rows of a pass count, as in ksw_rows_p2x2)
+    const long long nR = r < nrows ? r : nrows;
+    const unsigned cells =
+        (unsigned)( nR <= qlen ? nR * ( nR + 1 ) / 2 : (long long)qlen * ( qlen + 1 ) / 2 + ( nR - qlen ) * qlen );
     ez.max = ezmax8 >> 3;
     if( bR >= 0 )
     {
