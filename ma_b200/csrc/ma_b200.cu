@@ -377,6 +377,11 @@ static void launch_ksw_qs( ma_b200_ctx* ctx, int qs, const KswBatchArgs& A, long
     MA_CUDA( cudaGetLastError( ) );
     ctx->launches++;
 }
+static bool use_tiny( )
+{
+    static const bool b = !( getenv( "MA_B200_NO_TINY" ) && atoi( getenv( "MA_B200_NO_TINY" ) ) != 0 );
+    return b;
+}
 static bool use_qs( )
 {
     static const bool b = !( getenv( "MA_B200_NO_QS" ) && atoi( getenv( "MA_B200_NO_QS" ) ) != 0 );
@@ -1035,7 +1040,7 @@ static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
         A.redo_order = ctx->bin_order.p, A.redo_cap = task_cap, A.redo_n = nullptr;
         for( int phase = 0; phase < 2; phase++ )
         {
-            const int b0 = phase == 0 ? MA_QS_BIN0 : 0, b1 = phase == 0 ? MA_QS_BIN0 + 6 : 15;
+            const int b0 = phase == 0 ? MA_QS_BIN0 : 0, b1 = phase == 0 ? MA_TINY_BIN + 1 : 15;
             if( phase == 1 )
             {
                 read_ctrl( ctx ); // synchronises: the bins now hold what ksw_qs_kernel handed over
@@ -1052,6 +1057,11 @@ static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
                 grids[ b ] = 0;
                 if( ctx->hctrl.bin_count[ b ] == 0 )
                     continue;
+                if( b == MA_TINY_BIN )
+                { // one thread per problem, no slabs
+                    grids[ b ] = std::min<long long>( ( ctx->hctrl.bin_count[ b ] + 127 ) / 128, (long long)ctx->num_sms * 16 );
+                    continue;
+                }
                 KswHostBin bin;
                 bin.order.resize( ctx->hctrl.bin_count[ b ] ); // only its size is used
                 bin.tb_stride = (long long)ctx->hctrl.bin_tb[ b ], bin.cig_stride = ctx->hctrl.bin_cig[ b ];
@@ -1079,7 +1089,13 @@ static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
                 MA_CUDA( cudaMemsetAsync( ctx->ksw_ctrl.p + 16, 0, sizeof( unsigned long long ), ctx->stream ) );
                 if( bBinStats )
                     MA_CUDA( cudaEventRecord( ctx->binEv[ b ][ 0 ], ctx->stream ) );
-                if( phase == 0 )
+                if( b == MA_TINY_BIN )
+                {
+                    ksw_tiny_kernel<<<(unsigned)grids[ b ], 128, 0, ctx->stream>>>( A );
+                    MA_CUDA( cudaGetLastError( ) );
+                    ctx->launches++;
+                }
+                else if( phase == 0 )
                     launch_ksw_qs( ctx, b - MA_QS_BIN0 + 1, A, grids[ b ] );
                 else
                     switch( b / 3 )
@@ -1107,7 +1123,10 @@ static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
                 {
                     const float ms = ev_ms( ctx->binEv[ b ][ 0 ], ctx->binEv[ b ][ 1 ] );
                     static const char* kKind[ 3 ] = { "all fields (exact)", "early-stop left", "early-stop right" };
-                    if( b >= MA_QS_BIN0 )
+                    if( b == MA_TINY_BIN )
+                        fprintf( stderr, "ma_b200 dp bin tiny gap fills (one thread each): %d tasks, %llu cells, %.3f ms, %.1f GCUPS\n",
+                                 ctx->hctrl.bin_count[ b ], c[ 64 + b ], ms, c[ 64 + b ] / ms / 1e6 );
+                    else if( b >= MA_QS_BIN0 )
                         fprintf( stderr, "ma_b200 dp bin QS blocks=%d %s: %d tasks, %llu cells, %.3f ms, %.1f GCUPS\n",
                                  ( b - MA_QS_BIN0 ) / 2 + 1, ( b - MA_QS_BIN0 ) % 2 ? "right" : "left",
                                  ctx->hctrl.bin_count[ b ], c[ 64 + b ], ms, c[ 64 + b ] / ms / 1e6 );
@@ -1272,7 +1291,7 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
             if( ctx->n_tasks > 0 )
             { // window bins of the tasks
                 NwBinArgs B{ ctx->tasks.p, (int)ctx->n_tasks, taskCap, ctx->bin_order.p, ctx->ctrl.p, make_score( ctx->params ),
-                             use_qs( ) ? 1 : 0 };
+                             use_qs( ) ? 1 : 0, use_tiny( ) ? 1 : 0 };
                 nwbin_kernel<<<full_grid( ctx, nwbin_kernel, 256, ctx->n_tasks ), 256, 0, s>>>( B );
                 MA_CUDA( cudaGetLastError( ) );
                 ctx->launches++;

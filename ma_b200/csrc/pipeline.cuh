@@ -13,6 +13,7 @@
 // after a slab is full, so the host can grow the slab to the exact size and re-run the stage.
 #pragma once
 #include "ksw.cuh"
+#include "ksw_tiny.cuh"
 #include "nwglue.cuh"
 #include "mapq.cuh"
 
@@ -21,6 +22,7 @@ namespace ma
 
 #define MA_NBINS 24 /* 0..14: ksw_batch_kernel (window class x kind), 15: band too wide, 16..21: ksw_qs_kernel */
 #define MA_QS_BIN0 16
+#define MA_TINY_BIN 22 /* ksw_tiny_kernel: gap fills whose band covers the whole (<= 32 x 32) matrix */
 // control block in device memory; every counter that many threads bump at the same time sits in its own 128-byte
 // line (same-line atomics serialise in the L2 slice that owns the line)
 struct PipeCtrl
@@ -514,6 +516,7 @@ struct NwBinArgs
     PipeCtrl* ctrl;
     KswScore score;
     int use_qs; // route early-stop extensions with short queries to ksw_qs_kernel
+    int use_tiny; // route small gap fills to ksw_tiny_kernel
 };
 
 // One thread per DP task: window bin, slot in the bin's order list (one atomic per warp and bin), slab sizes of the bin
@@ -545,6 +548,8 @@ __global__ void __launch_bounds__( 256 ) nwbin_kernel( NwBinArgs A )
             }
             tb = bytes > 0xffffffffull ? 0xffffffffu : (unsigned int)bytes; // in units of 256 bytes
             cig = (unsigned int)( ( T.qlen + T.tlen + 2 + 63 ) & ~63 );
+            if( A.use_tiny && ksw_tiny_ok( A.score, T.qlen, T.tlen, T.w, T.flag, T.tag ) )
+                b = MA_TINY_BIN, tb = 0, cig = 0; // one thread per problem, state in thread-local memory
             if( skip )
                 b = MA_NBINS, tb = 0, cig = 0;
         }
