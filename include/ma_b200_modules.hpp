@@ -219,6 +219,8 @@ struct ContigTable
             throw std::runtime_error( "File opening error: " + sPrefix + ".ann" );
         int64_t nSeq, seedv;
         ann >> iForwardLength >> nSeq >> seedv;
+        if( !ann || iForwardLength < 0 || nSeq < 0 || nSeq > ( 1ll << 32 ) )
+            throw std::runtime_error( "Corrupt file (header): " + sPrefix + ".ann" );
         vNames.clear( ), vStart.assign( nSeq, 0 ), vLength.assign( nSeq, 0 );
         std::string line;
         std::getline( ann, line );
@@ -231,6 +233,8 @@ struct ContigTable
             vNames.push_back( sName );
             int64_t holes;
             ann >> vStart[ i ] >> vLength[ i ] >> holes;
+            if( !ann || vStart[ i ] < 0 || vLength[ i ] < 0 || vStart[ i ] + vLength[ i ] > iForwardLength )
+                throw std::runtime_error( "Corrupt file (contig " + std::to_string( i ) + "): " + sPrefix + ".ann" );
             std::getline( ann, line );
         }
     }
@@ -275,15 +279,32 @@ class FMIndex
             in.read( v.data( ), (std::streamsize)v.size( ) );
             return v;
         };
+        // sizes derived from the headers are checked against the files before anything is copied (a truncated or
+        // mismatched file must fail like the reference's loaders do, not read out of bounds)
+        auto bad = [ & ]( const char* ext, const char* why ) {
+            throw std::runtime_error( "Corrupt index file " + sPrefix + ext + ": " + why );
+        };
         auto b = slurp( sPrefix + ".bwt" );
+        if( b.size( ) < 40 || ( b.size( ) - 40 ) % 4 != 0 )
+            bad( ".bwt", "shorter than its header or not a whole number of words" );
         int64_t primary, L2[ 5 ] = { 0, 0, 0, 0, 0 };
         memcpy( &primary, b.data( ), 8 );
         memcpy( &L2[ 1 ], b.data( ) + 8, 32 );
         const int64_t nWords = (int64_t)( b.size( ) - 40 ) / 4, refLen = L2[ 4 ];
+        if( refLen <= 0 || L2[ 1 ] < 0 || L2[ 1 ] > L2[ 2 ] || L2[ 2 ] > L2[ 3 ] || L2[ 3 ] > L2[ 4 ] || primary < 0 || primary > refLen )
+            bad( ".bwt", "inconsistent cumulative counts / primary" );
+        if( nWords < ( refLen + 127 ) / 128 * 16 )
+            bad( ".bwt", "fewer occurrence blocks than the reference length needs" );
         auto s = slurp( sPrefix + ".sa" );
+        if( s.size( ) < 52 )
+            bad( ".sa", "shorter than its header" );
         int32_t saIntv;
         memcpy( &saIntv, s.data( ) + 40, 4 );
+        if( saIntv <= 0 || ( saIntv & ( saIntv - 1 ) ) != 0 )
+            bad( ".sa", "sampling interval must be a positive power of two" );
         const int64_t nSa = ( refLen + saIntv ) / saIntv;
+        if( (int64_t)s.size( ) < 52 + 8 * ( nSa - 1 ) )
+            bad( ".sa", "fewer samples than the reference length needs" );
         std::vector<int64_t> sa( nSa );
         sa[ 0 ] = -1;
         memcpy( &sa[ 1 ], s.data( ) + 52, ( nSa - 1 ) * 8 );
@@ -291,6 +312,10 @@ class FMIndex
         const std::vector<int64_t>&cs = xContigs.vStart, &cl = xContigs.vLength;
         const int64_t fwdLen = xContigs.iForwardLength, nSeq = (int64_t)cs.size( );
         auto p = slurp( sPrefix + ".pac" );
+        if( refLen != 2 * fwdLen )
+            bad( ".ann", "forward length does not match the BWT" );
+        if( (int64_t)p.size( ) < ( fwdLen + 3 ) / 4 )
+            bad( ".pac", "shorter than the forward strand" );
         check( ma_b200_index_upload( pCtx, (const uint32_t*)( b.data( ) + 40 ), nWords, L2, primary, refLen, sa.data( ),
                                      nSa, saIntv, (const uint8_t*)p.data( ), ( fwdLen + 3 ) / 4, fwdLen, cs.data( ),
                                      cl.data( ), (int32_t)nSeq ) );

@@ -38,10 +38,9 @@ class SamWriter
     size_t contigOf( nucSeqIndex uiPos ) const // Pack::uiSequenceIdForPosition of the position mapped to the forward strand
     {
         const int64_t a = onReverse( uiPos ) ? 2 * rIdx.iForwardLength - ( (int64_t)uiPos + 1 ) : (int64_t)uiPos;
-        size_t i = 0;
-        while( i + 1 < rIdx.vStart.size( ) && rIdx.vStart[ i + 1 ] <= a )
-            i++;
-        return i;
+        // the last contig that starts at or before a (fragmented assemblies have 10^5 contigs: no linear scan)
+        const auto it = std::upper_bound( rIdx.vStart.begin( ), rIdx.vStart.end( ), a );
+        return it == rIdx.vStart.begin( ) ? 0 : (size_t)( it - rIdx.vStart.begin( ) ) - 1;
     }
     std::string contig( const Alignment& a ) const
     {

@@ -4,6 +4,7 @@
 #include "pipeline.cuh"
 #include "index_build.cuh"
 #include <algorithm>
+#include <nvtx3/nvToolsExt.h> // header-only (the tools library is looked up at run time): ranges for nsys / ncu --nvtx
 #include <numeric>
 #include <condition_variable>
 #include <mutex>
@@ -19,6 +20,20 @@ struct KswHostBin
     long long tb_stride = 0;
     int cig_stride = 0;
     int qs = 0; // ksw_qs_kernel: 1 + (blocks - 1) * 2 + right-aligned
+};
+
+// Tracing hook: one NVTX range per API call and pipeline stage; free when no tool is attached.
+struct NvtxRange
+{
+    explicit NvtxRange( const char* name )
+    {
+        nvtxRangePushA( name );
+    }
+    ~NvtxRange( )
+    {
+        nvtxRangePop( );
+    }
+    NvtxRange( const NvtxRange& ) = delete;
 };
 
 struct ma_b200_ctx
@@ -643,6 +658,7 @@ static int ksw_run_once( ma_b200_ctx* ctx )
 
 extern "C" int ma_b200_ksw_run( ma_b200_ctx* ctx, float* kernel_ms )
 {
+    NvtxRange nvtxCall( "ma_b200_ksw_run" );
     MA_API_BEGIN
     if( kernel_ms )
         *kernel_ms = 0;
@@ -743,6 +759,7 @@ extern "C" int ma_b200_index_upload( ma_b200_ctx* ctx, const uint32_t* bwt_words
                                      int32_t sa_intv, const uint8_t* pac, int64_t n_pac_bytes, int64_t fwd_len,
                                      const int64_t* contig_start, const int64_t* contig_len, int32_t n_contigs )
 {
+    NvtxRange nvtxCall( "ma_b200_index_upload" );
     MA_API_BEGIN
     if( !bwt_words || !L2 || !sa || !pac || !contig_start || !contig_len || n_contigs <= 0 || n_words <= 0 ||
         sa_intv <= 0 || ( sa_intv & ( sa_intv - 1 ) ) || ref_len != 2 * fwd_len ||
@@ -774,6 +791,7 @@ extern "C" int ma_b200_index_upload( ma_b200_ctx* ctx, const uint32_t* bwt_words
 extern "C" int ma_b200_index_build( ma_b200_ctx* ctx, const uint8_t* fwd, int64_t fwd_len, const int64_t* contig_start,
                                     const int64_t* contig_len, int32_t n_contigs )
 {
+    NvtxRange nvtxCall( "ma_b200_index_build" );
     MA_API_BEGIN
     if( !fwd || fwd_len <= 0 || !contig_start || !contig_len || n_contigs <= 0 )
         throw std::runtime_error( "index_build: bad arguments" );
@@ -998,6 +1016,7 @@ template <typename K> static int full_grid( ma_b200_ctx* ctx, K kernel, int thre
 // may hand problems over into the bins of ksw_batch_kernel (PipeCtrl::bin_*), then those.
 static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
 {
+    NvtxRange nvtxDp( "banded DP (ksw_qs / ksw_tiny / ksw_batch kernels)" );
     static const int Ws[ 5 ] = { 128, 256, 512, 1024, 2048 };
     const KswScore score = make_score( ctx->params );
     ctx->task_out.reserve( (size_t)ctx->n_tasks + 1 );
@@ -1164,11 +1183,13 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
     ctx->n_seeds = ctx->n_sets = ctx->n_set_seeds = ctx->n_tasks = ctx->n_runs = ctx->n_task_cigar = 0;
     ctx->stage_done = 0;
     cudaStream_t s = ctx->stream;
+    NvtxRange nvtxRun( "ma_b200_align_run" );
     MA_CUDA( cudaEventRecord( ctx->ev[ 0 ], s ) );
     if( n > 0 )
     {
         MA_CUDA( cudaMemsetAsync( ctx->ctrl.p, 0, sizeof( PipeCtrl ), s ) );
         // ---------------- stage 1: seeding
+        nvtxRangePushA( "stage 1: BinarySeeding + ExtractSeeds" );
         const int maxL = ctx->max_read_len;
         const int list_cap = std::min( maxL + 2, 1024 ), fseg_cap = std::min( 2 * maxL + 8, 1 << 16 );
         const int SB = MA_SEED_BLOCK;
@@ -1221,10 +1242,12 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
             ctx->launches++;
         }
         MA_CUDA( cudaEventRecord( ctx->ev[ 2 ], s ) );
+        nvtxRangePop( );
         ctx->stage_done = 1;
         // ---------------- stage 2: SoC + harmonization
         if( upto_stage >= 2 )
         {
+            NvtxRange nvtxStage( "stage 2: StripOfConsideration + Harmonization" );
             const size_t scratchCap = ( ( (size_t)ctx->n_seeds * ( 340 + sizeof( DSeed ) ) + (size_t)n * 400 + 4096 ) + 255 ) & ~(size_t)255;
             ctx->harm_scratch.reserve( scratchCap );
             long long setSeedCap = std::max<long long>( ctx->set_seeds.cap, 2 * ctx->n_seeds + 1024 );
@@ -1264,6 +1287,7 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
         // ---------------- stage 3: NW
         if( upto_stage >= 3 )
         {
+            NvtxRange nvtxStage( "stage 3 + 4: NeedlemanWunsch, MappingQuality, PairedReads" );
             const int nSets = (int)ctx->n_sets;
             long long taskCap = std::max<long long>( ( ctx->bin_order.cap / MA_NBINS ), 3ll * nSets + 1024 );
             if( nSets > 0 )
@@ -1307,6 +1331,9 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
             {
                 const int runScratchCap = 2 * ctx->max_read_len + 4096;
                 int grid = full_grid( ctx, nwasm_kernel, 128, nSets );
+                // per-thread run scratch of 2 L + 4096 words: one 100 kbp read in the batch must not turn the full
+                // occupancy grid into a 100 GB allocation, so the grid is capped against a byte budget like stage 1's
+                grid = (int)std::max<size_t>( 1, std::min<size_t>( (size_t)grid, ( (size_t)8 << 30 ) / ( (size_t)128 * runScratchCap * sizeof( unsigned int ) ) ) );
                 ctx->run_scratch.reserve( (size_t)grid * 128 * runScratchCap );
                 long long runCap = std::max<long long>( ctx->runs.cap, 16ll * nSets + 4096 );
                 for( int attempt = 0;; attempt++ )
@@ -1492,6 +1519,7 @@ extern "C" int ma_b200_align_download_sets( ma_b200_ctx* ctx, ma_b200_seed_set* 
 extern "C" int ma_b200_align_download( ma_b200_ctx* ctx, ma_b200_read_info* info, ma_b200_alignment* alns,
                                        int64_t cap_alns, uint32_t* runs, int64_t cap_runs )
 {
+    NvtxRange nvtxCall( "ma_b200_align_download" );
     MA_API_BEGIN
     static_assert( sizeof( ma_b200_alignment ) == sizeof( DAln ), "alignment layout" );
     if( ctx->stage_done < 3 )
@@ -1617,6 +1645,7 @@ extern "C" int ma_b200_align_batch( ma_b200_ctx* ctx, int64_t n_reads, const uin
                                     ma_b200_read_info* info, ma_b200_alignment* alns, int64_t cap_alns,
                                     uint32_t* runs, int64_t cap_runs, ma_b200_align_stats* stats )
 {
+    NvtxRange nvtxCall( "ma_b200_align_batch" );
     if( !ctx )
         return MA_B200_EINVAL;
     if( ctx->batch_split <= 0 || n_reads < 2 * ( ctx->batch_split + ( ctx->batch_split & 1 ) ) || !ctx->have_index || !reads || !offsets || !info || !alns || !runs )

@@ -44,6 +44,8 @@ def load_index(prefix: str) -> Index:
     ix = Index()
     with open(prefix + ".bwt", "rb") as f:
         raw = f.read()
+    if len(raw) < 40 or (len(raw) - 40) % 4:
+        raise ValueError("corrupt index file %s.bwt: shorter than its header or not a whole number of words" % prefix)
     ix.primary = int(np.frombuffer(raw[:8], dtype=np.int64)[0])
     ix.L2 = np.zeros(5, dtype=np.int64)
     ix.L2[1:] = np.frombuffer(raw[8:40], dtype=np.int64)
@@ -51,8 +53,14 @@ def load_index(prefix: str) -> Index:
     ix.ref_len = int(ix.L2[4])
     with open(prefix + ".sa", "rb") as f:
         raw = f.read()
+    if len(raw) < 52:
+        raise ValueError("corrupt index file %s.sa: shorter than its header" % prefix)
     ix.sa_intv = int(np.frombuffer(raw[40:44], dtype=np.int32)[0])
+    if ix.sa_intv <= 0 or ix.ref_len <= 0:
+        raise ValueError("corrupt index files %s: sampling interval / reference length" % prefix)
     n_sa = (ix.ref_len + ix.sa_intv) // ix.sa_intv
+    if len(raw) < 52 + 8 * (n_sa - 1) or ix.bwt.size < (ix.ref_len + 127) // 128 * 16:
+        raise ValueError("corrupt index files %s: .sa / .bwt shorter than the reference length needs" % prefix)
     ix.sa = np.empty(n_sa, dtype=np.int64)
     ix.sa[0] = -1
     ix.sa[1:] = np.frombuffer(raw[52:52 + 8 * (n_sa - 1)], dtype=np.int64)
@@ -70,7 +78,8 @@ def load_index(prefix: str) -> Index:
     ix.contig_len = np.array(lens, dtype=np.int64)
     with open(prefix + ".pac", "rb") as f:
         ix.pac = np.frombuffer(f.read(), dtype=np.uint8)[:(ix.fwd_len + 3) // 4].copy()
-    assert ix.ref_len == 2 * ix.fwd_len
+    if ix.ref_len != 2 * ix.fwd_len or len(ix.pac) < (ix.fwd_len + 3) // 4:
+        raise ValueError("corrupt index files %s: .ann / .pac do not match the BWT" % prefix)
     return ix
 
 

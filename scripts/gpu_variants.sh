@@ -1,15 +1,10 @@
 #!/bin/bash
-# GPU box: the bench with the time of every DP launch, for the default library and the builds in ma_b200/variants/
+# GPU box: the default bench (1 M reads per step) for the default library and the builds in ma_b200/variants/
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-python -m pytest tests/test_ksw_gpu.py tests/test_pipeline_gpu.py -x -q -m gpu 2>&1 | tail -3
 for lib in ma_b200/libma_b200.so ma_b200/variants/*.so; do
-  echo "=== $lib"
-  MA_B200_LIB=$PWD/$lib MA_B200_DP_BINS=1 python bench.py --steps 3 --warmup 3 2>gpurun_out/err_$(basename $lib).txt | tail -1 > gpurun_out/bench_$(basename $lib).json
-  grep "dp bin" gpurun_out/err_$(basename $lib).txt | tail -12 | sort | uniq
-  python - <<PY
-import json
-d = json.load(open("gpurun_out/bench_$(basename $lib).json"))
-print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["kernels"]["ksw_kernels"])
-PY
+  MA_B200_LIB=$PWD/$lib python bench.py --pairs 500000 --steps 3 --warmup 2 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('$(basename $lib)', round(d['ms_per_step'],2), {k: round(v['ms'],2) for k,v in d['kernels'].items()})"
 done

@@ -21,6 +21,7 @@ import pipeline_common as PC  # noqa: E402
 from ma_b200 import synth  # noqa: E402
 
 N_READS = 3000
+N_LARGE = 100_000  # second, larger sample of the same batch: hashes only (key "large_sample")
 
 
 def sha1(a):
@@ -48,9 +49,18 @@ def main():
         synth.write_reads_txt(os.path.join(d, "l.txt"), long_reads)
         H.run_ref("align", os.path.join(d, "g"), os.path.join(d, "l.txt"), "pacbio", os.path.join(d, "l.dump"), PC.SRAND)
         rl = H.load_dump(os.path.join(d, "l.dump"))
+        # the first 100 000 reads of the batch (5 % of it): the reference is single-threaded here, about a minute
+        big = np.empty((N_LARGE, 150), dtype=np.uint8)
+        big[0::2], big[1::2] = m1[:N_LARGE // 2], m2[:N_LARGE // 2]
+        synth.write_reads_txt(os.path.join(d, "b.txt"), big)
+        H.run_ref("align", os.path.join(d, "g"), os.path.join(d, "b.txt"), "illuminapaired", os.path.join(d, "b.dump"),
+                  PC.SRAND)
+        rb = H.load_dump(os.path.join(d, "b.dump"))
     out = {"n_reads": N_READS, "srand_base": PC.SRAND,
            "sha1": {k: sha1(r[k]) for k in PC.STAGE_KEYS + ["mq_off", "mq", "pr_off", "pr"]},
            "sam_sha1": hashlib.sha1(sam).hexdigest(), "sam_lines": sam.count(b"\n"),
+           "large_sample": {"n_reads": N_LARGE,
+                            "sha1": {k: sha1(rb[k]) for k in PC.STAGE_KEYS + ["mq_off", "mq", "pr_off", "pr"]}},
            "pacbio": {"n_reads": 200, "read_len": 10000, "seed": 4,
                       "sha1": {k: sha1(rl[k]) for k in PC.STAGE_KEYS + ["mq_off", "mq"]}}}
     with open(os.path.join(H.GOLDEN, "full_size_sample_sha1.json"), "w") as f:

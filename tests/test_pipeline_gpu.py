@@ -1,9 +1,9 @@
 """GPU parity of the whole path through the C ABI: segments, located seeds, harmonized seed sets and alignment
 records must equal the reference's (golden dumps of the compiled reference, and the oracle at larger sizes).
 
-Integer work is compared bit-exactly.  Harmonization contains double-precision libm calls (atan/tan/sin/log); CUDA's
-libm may differ from glibc in the last ulp, so for the LARGE random set the stated tolerance is: at most 0.1 % of
-reads may differ in their alignment records (observed: 0); the golden sets must match exactly."""
+Everything is compared bit-exactly, including the records that depend on Harmonization's double-precision libm calls
+(atan/tan/sin/log): a last-ulp difference between CUDA's libm and glibc that changed an emitted alignment would fail
+these tests (none has been observed on the golden sets, 10 000 + 100 000 random reads)."""
 import os
 
 import numpy as np
@@ -273,10 +273,11 @@ def test_config1_scale_against_oracle(tmp_path):
                               PC.SRAND, 5)
     got = PC.gpu_stage_dump(ctx, reads)
     PC.assert_same_stages(got, exp, keys=["seg_off", "seg", "seed_off", "seed"], what="config1 seeding")
+    # Harmonization's double-precision libm calls (atan / tan / sin / log): north_star allows only a tolerance that does
+    # not change the emitted alignments, so NO read may differ (CUDA's libm has agreed with glibc on every input so far)
     bad = PC.mismatching_reads(got, exp)
-    assert bad <= 10, "%d of 10000 reads differ (tolerance 0.1 %%)" % bad
-    if bad == 0:
-        PC.assert_same_stages(got, exp, what="config1")
+    assert bad == 0, "%d of 10000 reads differ" % bad
+    PC.assert_same_stages(got, exp, what="config1")
     # accuracy sanity: primary alignment within 5 bp of the simulated origin for > 99 % of the reads
     ok = 0
     for i in range(len(reads)):
