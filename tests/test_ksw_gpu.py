@@ -54,6 +54,16 @@ def test_sweep_points_vs_oracle(gpu_ctx, mode, length, w):
     check_against_oracle(gpu_ctx, dpgen.sweep_pairs(n, length, w, mode, 0.05, seed=length * 7 + w))
 
 
+@pytest.mark.parametrize("mode", [dpgen.GLOBAL, dpgen.EXT, dpgen.EXT_RIGHT])
+@pytest.mark.parametrize("length,w,div", [(10000, 512, 0.05), (20000, 512, 0.05), (20000, 64, 0.01), (10000, 256, 0.15),
+                                          (3000, 128, 0.01), (3000, 128, 0.15), (300, 16, 0.15), (1000, 32, 0.01)])
+def test_sweep_long_and_divergent_points_vs_oracle(gpu_ctx, mode, length, w, div):
+    """The upper end of BASELINE configs[4] (10 and 20 kbp, int32 score mode, two-megabyte traceback per problem) and its
+    1 % / 15 % divergence levels: every kswcpp_extz_t field, the CIGAR and the band-cell count against the oracle."""
+    n = 3 if length >= 10000 else 8
+    check_against_oracle(gpu_ctx, dpgen.sweep_pairs(n, length, w, mode, div, seed=length * 11 + w))
+
+
 def test_illumina_like_end_extensions(gpu_ctx):
     """The dominant DP shape of the Illumina preset: ~50 bp read tail against a 1000 bp padded window, w=512."""
     rng = np.random.Generator(np.random.PCG64(31))

@@ -404,3 +404,38 @@ def test_read_beyond_a_capacity_is_reported_per_read(gold_index):
     assert s0["n_failed"] == int((i0["status"] != 0).sum()) and s1["n_failed"] == s0["n_failed"] + 1
     ok = set(np.nonzero(i0["status"] == 0)[0].tolist())
     assert [r for r in r0 if r[0] in ok] == [r for r in r1 if r[0] in ok] and len(ok) > 0
+
+
+def test_two_gpus_sharded_batch_equals_one_gpu(gold_index):
+    """SURVEY.md §8(e) on real devices: the index replicated on cuda:0 and cuda:1, the paired golden batch split into the
+    contiguous pair shards of ma_b200.dist.shard_pairs (what bench.py --config 2 does per rank), RANSAC streams offset by
+    the shard's first read — the concatenated records equal the one-GPU batch. Skips only on a box with one GPU."""
+    import torch
+    from ma_b200 import dist as madist
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    reads = PC.read_reads_txt(PC.gold_reads("illuminapaired"))
+    n = len(reads)
+
+    def run(device, lo, hi):
+        ctx = api.Context(device, "illuminapaired")
+        p = api.preset("illuminapaired")
+        p.srand_base = madist.shard_srand_base(PC.SRAND, lo)
+        ctx.set_params(p)
+        ctx.index_upload(gold_index)
+        data, off = api.pack_reads(reads[lo:hi])
+        info, alns, runs, st = ctx.align_batch(data, off)
+        rec = [(r[0] + lo,) + r[1:] for r in _records(info, alns, runs, hi - lo)]
+        flags = [(int(a["read"]) + lo, int(a["rank"]), int(a["flags"]), float(a["mapq"]) if a["mapq"] == a["mapq"] else -1.0,
+                  int(a["rank_mq"]), int(a["pair_rank"])) for a in alns]
+        ctx.close()
+        return rec, sorted(flags)
+
+    full, full_flags = run(0, 0, n)
+    parts, part_flags = [], []
+    for rank in range(2):
+        lo, hi = madist.shard_pairs(n // 2, rank, 2)
+        r, f = run(rank, lo, hi)
+        parts += r
+        part_flags += f
+    assert parts == full and sorted(part_flags) == full_flags
