@@ -244,6 +244,15 @@ int ma_b200_align_batch( ma_b200_ctx* ctx, int64_t n_reads, const uint8_t* reads
                          ma_b200_read_info* info, ma_b200_alignment* alns, int64_t cap_alns, uint32_t* runs,
                          int64_t cap_runs, ma_b200_align_stats* stats );
 
+/* PairedReads::execute (pairedReads.cpp:15-121) for ONE pair whose records are on the host: for graphs that run a host
+ * module between MappingQuality and PairedReads (SmallInversions adds records, export.cpp:176-184). Runs the same
+ * routine as the device stage (ma_b200/csrc/mapq.cuh paired_reads_pair, compiled for the host) on the records of the two
+ * mates — entries with rank_mq >= 0 take part, in that order — and sets pair_rank / flags / mapq on them in place.
+ * runs: the run words the records' run_off / n_runs point into. Returns the size of the module's result vector, or a
+ * negative MA_B200_E* code (MA_B200_EINVAL also where the reference itself would index an empty vector). */
+int ma_b200_paired_reads_host( const ma_b200_params* params, int64_t ref_len, ma_b200_alignment* mate1, int32_t n1,
+                               int64_t qlen1, ma_b200_alignment* mate2, int32_t n2, int64_t qlen2, const uint32_t* runs );
+
 /* ---- measurement helper ----------------------------------------------------------------------------------- */
 /* Measured bandwidth (GB/s) of independent random 64-byte block reads over a buffer of buffer_bytes: the roofline
  * of the seeding kernels (two such reads per extend_backward), SURVEY.md §8(d). */

@@ -650,48 +650,61 @@ class SmallInversions
         std::vector<uint8_t> vRef;
     };
 
-    // forAllDropPos (smallInversions.h:54-115): regions between two seeds in which the running score drops faster
-    // than "Z Drop Inversions"
+    // The drop scan of smallInversions.h:54-115 in two steps. The alignment is cut at its seeds into windows — a seed and
+    // everything up to the next seed (the leading window may start without one). Within a window the score of the path is
+    // followed run by run from 0: `best` is the highest value so far (the position where it was LAST reached), and after
+    // every run below it the drop is  best - score - extend * max(query, reference bases since best).  A window whose
+    // largest drop reaches "Z Drop Inversions" and that is CLOSED by a seed is reported as the region between the end
+    // of its own seed and the start of the closing one; the tail behind the last seed never is (the reference tests
+    // the drop only when it meets a seed).
+    struct RunStep // effect of one run of a given type: per-base query / reference advance, score per base and per run
+    {
+        int iQuery, iRef, iPerBase, iPerRun;
+    };
     template <typename F> void forAllDropPos( const Alignment& a, F fDo ) const
     {
         const ma_b200_params& P = rParams.xParams;
-        nucSeqIndex uiMaxScorePosQ = a.uiBeginOnQuery, uiPosQ = a.uiBeginOnQuery, uiStartQ = a.uiBeginOnQuery;
-        nucSeqIndex uiMaxScorePosR = a.uiBeginOnRef, uiPosR = a.uiBeginOnRef, uiStartR = a.uiBeginOnRef;
-        int iMaxScore = std::numeric_limits<int>::min( ), iCurrScore = 0, iMaxDrop = 0;
-        for( const auto& section : a.data )
+        const RunStep aStep[ 5 ] = { { 1, 1, P.match, 0 }, // seed (scored like a match)
+                                     { 1, 1, P.match, 0 }, // match
+                                     { 1, 1, -P.mismatch, 0 }, // missmatch
+                                     { 1, 0, -P.extend, -P.gap }, // insertion
+                                     { 0, 1, -P.extend, -P.gap } }; // deletion
+        const size_t n = a.data.size( );
+        // positions in front of every run
+        std::vector<nucSeqIndex> vQ( n + 1, a.uiBeginOnQuery ), vR( n + 1, a.uiBeginOnRef );
+        for( size_t k = 0; k < n; k++ )
         {
-            switch( section.first )
+            const RunStep& st = aStep[ (int)a.data[ k ].first ];
+            vQ[ k + 1 ] = vQ[ k ] + (nucSeqIndex)st.iQuery * a.data[ k ].second;
+            vR[ k + 1 ] = vR[ k ] + (nucSeqIndex)st.iRef * a.data[ k ].second;
+        }
+        size_t uiOpen = 0; // first run of the current window
+        for( size_t uiClose = 0; uiClose < n; uiClose++ )
+        {
+            if( a.data[ uiClose ].first != MatchType::seed )
+                continue;
+            // window [uiOpen, uiClose), closed by the seed at uiClose (empty in front of a leading seed: drop 0)
+            const bool bLeadingSeed = uiClose > uiOpen && a.data[ uiOpen ].first == MatchType::seed;
+            long long iScore = 0, iBest = std::numeric_limits<int>::min( ), iDrop = 0;
+            size_t uiBestAt = uiOpen; // index of the position (in front of run uiBestAt) of the best score
+            for( size_t k = uiOpen; k < uiClose; k++ )
             {
-                case MatchType::seed:
-                    if( iMaxDrop >= rParams.iZDropInversion )
-                        fDo( uiStartQ, uiStartR, uiPosQ, uiPosR );
-                    uiStartQ = section.second + uiPosQ, uiStartR = section.second + uiPosR;
-                    iMaxDrop = 0, iCurrScore = 0, iMaxScore = std::numeric_limits<int>::min( );
-                    [[fallthrough]];
-                case MatchType::match:
-                    iCurrScore += P.match * (int)section.second;
-                    uiPosQ += section.second, uiPosR += section.second;
-                    break;
-                case MatchType::missmatch:
-                    iCurrScore -= P.mismatch * (int)section.second;
-                    uiPosQ += section.second, uiPosR += section.second;
-                    break;
-                case MatchType::insertion:
-                    iCurrScore -= P.gap + P.extend * (int)section.second;
-                    uiPosQ += section.second;
-                    break;
-                case MatchType::deletion:
-                    iCurrScore -= P.gap + P.extend * (int)section.second;
-                    uiPosR += section.second;
-                    break;
+                const RunStep& st = aStep[ (int)a.data[ k ].first ];
+                iScore += (long long)st.iPerBase * (long long)a.data[ k ].second + st.iPerRun;
+                if( iScore >= iBest )
+                    iBest = iScore, uiBestAt = k + 1;
+                else
+                {
+                    const nucSeqIndex uiDist = std::max( vQ[ k + 1 ] - vQ[ uiBestAt ], vR[ k + 1 ] - vR[ uiBestAt ] );
+                    iDrop = std::max<long long>( iDrop, iBest - iScore - (long long)(int)uiDist * P.extend );
+                }
             }
-            if( iCurrScore >= iMaxScore )
-                iMaxScore = iCurrScore, uiMaxScorePosQ = uiPosQ, uiMaxScorePosR = uiPosR;
-            else
+            if( iDrop >= rParams.iZDropInversion )
             {
-                const int iDiff = (int)std::max( uiPosQ - uiMaxScorePosQ, uiPosR - uiMaxScorePosR );
-                iMaxDrop = std::max( iMaxDrop, iMaxScore - iCurrScore - iDiff * P.extend );
+                const size_t uiFrom = bLeadingSeed ? uiOpen + 1 : uiOpen; // region starts behind the window's own seed
+                fDo( vQ[ uiFrom ], vR[ uiFrom ], vQ[ uiClose ], vR[ uiClose ] );
             }
+            uiOpen = uiClose;
         }
     }
 
@@ -785,14 +798,32 @@ class SmallInversions
     }
 };
 
-// PairedReads::execute (pairedReads.cpp:15-121) on the host, for graphs that run a host module between MappingQuality
-// and PairedReads (SmallInversions, export.cpp:176-184); the device stage (PairedReads above) is the fast path.
-// Restated with the reference's own runtime facilities: std::sort on the tuples (unstable, like the reference's),
-// float arithmetic for the pair's mapping quality.
+// PairedReads for graphs that run a host module between MappingQuality and PairedReads (SmallInversions adds records,
+// export.cpp:176-184). No second implementation of the module: the records go through ma_b200_paired_reads_host, i.e. the
+// routine of the device stage (ma_b200/csrc/mapq.cuh) compiled for the host; this class only marshals.
 class PairedReadsHost
 {
     const ma_b200_params& P;
     const int64_t iForwardLength;
+
+    // the records the routine works on: what it reads of an alignment, and the run words for the seed count
+    static void toRecords( const std::vector<Alignment>& v, std::vector<ma_b200_alignment>& vRec, std::vector<uint32_t>& vRuns )
+    {
+        for( size_t k = 0; k < v.size( ); k++ )
+        {
+            ma_b200_alignment r;
+            memset( &r, 0, sizeof( r ) );
+            r.begin_ref = (int64_t)v[ k ].uiBeginOnRef, r.end_ref = (int64_t)v[ k ].uiEndOnRef, r.score = v[ k ].iScore;
+            r.begin_q = (int32_t)v[ k ].uiBeginOnQuery, r.end_q = (int32_t)v[ k ].uiEndOnQuery;
+            r.length = (int32_t)v[ k ].uiLength, r.soc_index = v[ k ].index_of_strip;
+            r.run_off = (int64_t)vRuns.size( ), r.n_runs = (int32_t)v[ k ].data.size( );
+            for( const auto& d : v[ k ].data )
+                vRuns.push_back( (uint32_t)d.second << 3 | (uint32_t)d.first );
+            r.rank = r.rank_mq = (int32_t)k, r.pair_rank = -1, r.mapq = v[ k ].fMappingQuality;
+            r.flags = ( v[ k ].bSecondary ? MA_B200_ALN_SECONDARY : 0 ) | ( v[ k ].bSupplementary ? MA_B200_ALN_SUPPLEMENTARY : 0 );
+            vRec.push_back( r );
+        }
+    }
 
   public:
     PairedReadsHost( const ParameterSetManager& rParameters, const FMIndex& rIdx )
@@ -801,73 +832,30 @@ class PairedReadsHost
     std::vector<Alignment> execute( const NucSeq& q1, const NucSeq& q2, std::vector<Alignment> v1,
                                     std::vector<Alignment> v2 ) const
     {
-        for( auto& a : v1 )
-            a.bFirst = true;
-        for( auto& a : v2 )
-            a.bFirst = false;
-        if( v1.empty( ) )
-            return v2;
-        if( v2.empty( ) )
-            return v1;
-        const size_t uiMean = (size_t)P.paired_mean;
-        auto onReverse = [ & ]( nucSeqIndex p ) { return p >= (nucSeqIndex)iForwardLength; };
-        std::vector<std::tuple<int64_t, bool, size_t, size_t>> vScores;
-        for( size_t i = 0; i < v1.size( ); i++ )
-        {
-            if( v1[ i ].uiLength == 0 )
-                continue;
-            for( size_t j = 0; j < v2.size( ); j++ )
+        std::vector<ma_b200_alignment> vRec1, vRec2;
+        std::vector<uint32_t> vRuns;
+        toRecords( v1, vRec1, vRuns ), toRecords( v2, vRec2, vRuns );
+        vRuns.push_back( 0 );
+        const int n = ma_b200_paired_reads_host( &P, 2 * iForwardLength, vRec1.data( ), (int32_t)vRec1.size( ),
+                                                 (int64_t)q1.length( ), vRec2.data( ), (int32_t)vRec2.size( ),
+                                                 (int64_t)q2.length( ), vRuns.data( ) );
+        if( n < 0 )
+            throw std::runtime_error( "PairedReads: no candidate pair for two aligned mates" );
+        std::vector<Alignment> vRet( (size_t)n );
+        auto collect = [ & ]( std::vector<Alignment>& v, const std::vector<ma_b200_alignment>& vRec, bool bFirstMate ) {
+            for( size_t k = 0; k < v.size( ); k++ )
             {
-                if( v2[ j ].uiLength == 0 )
+                v[ k ].bFirst = bFirstMate; // pairedReads.cpp:21-25: every alignment learns which mate it belongs to
+                if( vRec[ k ].pair_rank < 0 )
                     continue;
-                int64_t iScore = v1[ i ].score( ) + v2[ j ].score( );
-                bool bIsPaired = false;
-                if( onReverse( v1[ i ].uiBeginOnRef ) != onReverse( v2[ j ].uiBeginOnRef ) )
-                {
-                    const nucSeqIndex uiP1 = v1[ i ].uiBeginOnRef;
-                    const nucSeqIndex uiP2 = 2 * (nucSeqIndex)iForwardLength - ( v2[ j ].uiBeginOnRef + 1 );
-                    const nucSeqIndex d = uiP1 < uiP2 ? uiP2 - uiP1 : uiP1 - uiP2;
-                    if( ( (double)d ) >= ( (double)uiMean ) - P.paired_std * 3 &&
-                        ( (double)d ) <= ( (double)uiMean ) + P.paired_std * 3 )
-                    {
-                        iScore = (int64_t)( iScore * P.paired_bonus );
-                        bIsPaired = true;
-                    }
-                }
-                vScores.emplace_back( iScore, bIsPaired, i, j );
+                v[ k ].bSecondary = ( vRec[ k ].flags & MA_B200_ALN_SECONDARY ) != 0;
+                v[ k ].bSupplementary = ( vRec[ k ].flags & MA_B200_ALN_SUPPLEMENTARY ) != 0;
+                v[ k ].fMappingQuality = vRec[ k ].mapq;
+                vRet[ (size_t)vRec[ k ].pair_rank ] = v[ k ];
             }
-        }
-        std::sort( vScores.begin( ), vScores.end( ),
-                   []( const std::tuple<int64_t, bool, size_t, size_t>& rtA,
-                       const std::tuple<int64_t, bool, size_t, size_t>& rtB ) {
-                       if( std::get<0>( rtA ) == std::get<0>( rtB ) )
-                           return std::get<1>( rtA ) && !std::get<1>( rtB );
-                       return std::get<0>( rtA ) > std::get<0>( rtB );
-                   } );
-        Alignment& a1 = v1[ std::get<2>( vScores[ 0 ] ) ];
-        Alignment& a2 = v2[ std::get<3>( vScores[ 0 ] ) ];
-        a1.bSecondary = a2.bSecondary = false;
-        a1.bSupplementary = a2.bSupplementary = false;
-        if( std::get<1>( vScores[ 0 ] ) && vScores.size( ) > 1 )
-        {
-            float fMapQ = ( (float)( std::get<0>( vScores[ 0 ] ) - std::get<0>( vScores[ 1 ] ) ) ) / std::get<0>( vScores[ 0 ] );
-            auto numSeeds = []( const Alignment& a ) {
-                size_t n = 0;
-                for( auto& d : a.data )
-                    n += d.first == MatchType::seed;
-                return n;
-            };
-            if( numSeeds( a1 ) <= 1 && numSeeds( a2 ) <= 1 )
-                fMapQ /= 2;
-            if( a1.score( ) >= P.match * q1.length( ) * 0.8 && v1.size( ) >= 3 )
-                fMapQ *= 2;
-            else if( a2.score( ) >= P.match * q2.length( ) * 0.8 && v2.size( ) >= 3 )
-                fMapQ *= 2;
-            if( fMapQ > 1 )
-                fMapQ = 1;
-            a1.fMappingQuality = fMapQ, a2.fMappingQuality = fMapQ;
-        }
-        return { a1, a2 };
+        };
+        collect( v1, vRec1, true ), collect( v2, vRec2, false );
+        return vRet;
     }
 };
 

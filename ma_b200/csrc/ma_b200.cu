@@ -1733,6 +1733,23 @@ extern "C" int ma_b200_align_batch( ma_b200_ctx* ctx, int64_t n_reads, const uin
     return MA_B200_OK;
 }
 
+extern "C" int ma_b200_paired_reads_host( const ma_b200_params* params, int64_t ref_len, ma_b200_alignment* mate1,
+                                          int32_t n1, int64_t qlen1, ma_b200_alignment* mate2, int32_t n2, int64_t qlen2,
+                                          const uint32_t* runs )
+{
+    if( !params || n1 < 0 || n2 < 0 || ( n1 && !mate1 ) || ( n2 && !mate2 ) || n1 > 0x7fff || n2 > 0x7fff )
+        return MA_B200_EINVAL;
+    const ma_b200_params& p = *params;
+    const MapqParams M{ p.match, p.report_n, p.min_alignment_score, p.max_supplementary_per_prim,
+                        p.max_overlap_supplementary, p.paired_mean, p.paired_std, p.paired_bonus };
+    const int cap = std::max( 1, n1 * n2 );
+    std::vector<int> ord1( (size_t)n1 + 1 ), ord2( (size_t)n2 + 1 ), meta( 2 * (size_t)cap );
+    std::vector<long long> sc( (size_t)cap );
+    const int n = paired_reads_pair( M, ref_len, reinterpret_cast<DAln*>( mate1 ), n1, qlen1, reinterpret_cast<DAln*>( mate2 ),
+                                     n2, qlen2, runs, ord1.data( ), ord2.data( ), sc.data( ), meta.data( ), cap );
+    return n < 0 ? MA_B200_EINVAL : n;
+}
+
 // ------------------------------------------------------------------------------------------------ roofline probe
 extern "C" int ma_b200_gather_probe( ma_b200_ctx* ctx, int64_t buffer_bytes, double* gbs )
 {
