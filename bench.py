@@ -277,6 +277,7 @@ def main():
     ap.add_argument("--cpu-sample-long", type=int, default=320, help="... of long reads (config 3)")
     ap.add_argument("--split", type=int, default=0, help="reads per sub-batch of the pipelined align_batch (0: default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--all-records", action="store_true", help="e2e downloads every alignment record, not only the reported ones")
     args, rest = ap.parse_known_args()
     args.pairs_given = args.pairs is not None
     if args.pairs is None:
@@ -313,6 +314,10 @@ def main():
     ctx = api.Context(local_rank, cfg["preset"])
     if args.split > 0:
         ctx.set_batch_split(args.split)
+    if not args.all_records:
+        # the end-to-end call hands back what the reference's chain hands to its writer: the records MappingQuality /
+        # PairedReads return (ma_b200_set_reported_only); --all-records downloads every alignment NeedlemanWunsch computed
+        ctx.set_reported_only(True)
     t0 = time.time()
     lens = [len(c) for c in genome]
     ctx.index_build(fwd, np.cumsum([0] + lens[:-1]), lens)
@@ -359,7 +364,7 @@ def main():
                                          out["info"].data_ptr(), out["alns"].data_ptr(), out["cap_alns"],
                                          out["runs"].data_ptr(), out["cap_runs"], ctypes.byref(st))
         if rc == -3:  # MA_B200_ENOMEM: the record buffers of this bench were too small; grow them from the counts
-            out["cap_alns"] = max(out["cap_alns"], int(st.n_sets * 1.3) + 1024)
+            out["cap_alns"] = max(out["cap_alns"], int(max(st.n_sets if args.all_records else 0, st.n_reported) * 1.3) + 1024)
             out["cap_runs"] = max(out["cap_runs"], int(st.n_runs * 1.3) + 4096)
             alloc_out()
             return e2e_sub(sub, count)
@@ -410,7 +415,7 @@ def main():
         n_sets, n_runs = 0, 0
         for sub in subs:
             est, _a = e2e_sub(sub)
-            n_sets += est.n_sets
+            n_sets += est.n_sets if args.all_records else est.n_reported
             n_runs += est.n_runs
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t
@@ -529,7 +534,9 @@ def main():
               "reads_per_step": int(reads_all), "reads_per_step_per_gpu": n_reads, "sub_batches_per_gpu": len(subs),
               "genome_bp": cfg["genome_mbp"] * 1_000_000, "parallelism": "index replicated, reads sharded x%d" % world,
               "timed_region": "value: CUDA-event time of ma_b200_align_run over the sub-batches, reads resident in HBM; "
-                              "e2e: wall time of ma_b200_align_batch over the same sub-batches, pinned host buffers",
+                              "e2e: wall time of ma_b200_align_batch over the same sub-batches, pinned host buffers, "
+                              + ("every alignment record" if args.all_records else
+                                 "the records MappingQuality / PairedReads return (what the writer consumes) + all run words"),
               "l2": "inputs larger than L2 (reads %d MB + index %d MB per step, no flush needed)"
                     % (n_reads * L // 1_000_000, cfg["genome_mbp"] * 7 // 4)}
     line = {"metric": cfg["metric"], "value": value, "unit": "reads/s", "n_gpus": world, "steps": K, "warmup": args.warmup,

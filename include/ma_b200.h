@@ -219,6 +219,7 @@ typedef struct
     float ms_seed, ms_locate, ms_socharm, ms_plan, ms_dp, ms_assemble, ms_total;
     int32_t launches;
     int32_t n_failed; /* reads with a non-zero ma_b200_read_info::status */
+    int64_t n_reported; /* alignment records with rank_mq >= 0 (what ma_b200_set_reported_only downloads) */
 } ma_b200_align_stats;
 
 /* reads: concatenated, 1 byte per base; offsets[n_reads + 1].  Stays resident until the next upload. */
@@ -238,6 +239,13 @@ int ma_b200_align_download( ma_b200_ctx* ctx, ma_b200_read_info* info, ma_b200_a
  * Off (0) by default: on a PCIe Gen5 B200 box the copies of a 2 M read batch are 7 % of the step and the smaller
  * launches cost more than the overlap returns (bench.py --split); it pays when the link is slower or shared. */
 int ma_b200_set_batch_split( ma_b200_ctx* ctx, int64_t reads_per_subbatch );
+
+/* Reported-only output: with on != 0, ma_b200_align_download / ma_b200_align_batch after MA_B200_STAGE_MAPQ deliver only
+ * the records MappingQuality (and PairedReads) return — rank_mq >= 0, i.e. what the reference's writers consume — packed
+ * per read (info[i].set_off / n_sets index them; stats.n_reported of them in all; the run words stay complete). A
+ * human-sized genome gives ~3 seed sets but ~1.1 reported alignments per Illumina read: the record download shrinks 3x.
+ * Off by default: the staged downloads and the parity tests see every alignment NeedlemanWunsch computed. */
+int ma_b200_set_reported_only( ma_b200_ctx* ctx, int32_t on );
 
 /* One call, host buffers in and out (upload + all stages + download): the drop-in for a batch of reads. */
 int ma_b200_align_batch( ma_b200_ctx* ctx, int64_t n_reads, const uint8_t* reads, const int64_t* offsets,

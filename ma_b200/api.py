@@ -74,7 +74,8 @@ class AlignStats(ctypes.Structure):
                                               "n_lookup")] + \
                [(n, ctypes.c_float) for n in ("ms_seed", "ms_locate", "ms_socharm", "ms_plan", "ms_dp",
                                               "ms_assemble", "ms_total")] + [("launches", ctypes.c_int32),
-                                                                              ("n_failed", ctypes.c_int32)]
+                                                                              ("n_failed", ctypes.c_int32),
+                                                                              ("n_reported", ctypes.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -274,7 +275,7 @@ class Context:
         st = AlignStats()
         rc = self.lib.ma_b200_align_batch(self.h, n, _ptr(reads), _ptr(offsets), _ptr(info), _ptr(alns),
                                           cap_alns, _ptr(runs), cap_runs, ctypes.byref(st))
-        if rc == -3 and (st.n_sets > cap_alns or st.n_runs > cap_runs):
+        if rc == -3 and (st.n_sets > cap_alns or st.n_runs > cap_runs) and not getattr(self, "_reported_only", False):
             # MA_B200_ENOMEM: the record arrays were too small (long reads carry hundreds of runs per alignment); the
             # results are still on the device and the stats hold the exact counts: fetch them into arrays of that size
             alns = np.zeros(max(1, st.n_sets), dtype=ALN_DTYPE)
@@ -282,7 +283,13 @@ class Context:
             rc = self.lib.ma_b200_align_download(self.h, _ptr(info), _ptr(alns), alns.size, _ptr(runs), runs.size)
         self._check(rc)
         self._stats = st.as_dict()
-        return info, alns[:st.n_sets], runs[:st.n_runs], self._stats
+        n_out = st.n_reported if getattr(self, "_reported_only", False) else st.n_sets
+        return info, alns[:n_out], runs[:st.n_runs], self._stats
+
+    def set_reported_only(self, on: bool):
+        """Downloads after STAGE_MAPQ deliver only the records MappingQuality / PairedReads return (rank_mq >= 0)."""
+        self._check(self.lib.ma_b200_set_reported_only(self.h, 1 if on else 0))
+        self._reported_only = bool(on)
 
     def gather_probe(self, buffer_bytes: int) -> float:
         """Measured GB/s of independent random 64-byte reads over a buffer of this size (seeding roofline)."""

@@ -115,6 +115,11 @@ struct ma_b200_ctx
     int64_t early_runs_cap = 0;
     bool early_runs_done = false;
     DevBuf<int> off_check; // offsets_check_kernel's result
+    bool reported_only = false; // ma_b200_set_reported_only
+    bool compacted = false; // the last run filled info_out / alns_out
+    int64_t n_reported = 0;
+    DevBuf<ReadInfo> info_out;
+    DevBuf<DAln> alns_out;
 };
 
 static KswScore make_score( const ma_b200_params& p )
@@ -1181,7 +1186,7 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
     const int n = (int)ctx->n_reads;
     st.n_reads = n;
     ctx->n_seeds = ctx->n_sets = ctx->n_set_seeds = ctx->n_tasks = ctx->n_runs = ctx->n_task_cigar = 0;
-    ctx->stage_done = 0;
+    ctx->stage_done = 0, ctx->compacted = false, ctx->n_reported = 0;
     cudaStream_t s = ctx->stream;
     NvtxRange nvtxRun( "ma_b200_align_run" );
     MA_CUDA( cudaEventRecord( ctx->ev[ 0 ], s ) );
@@ -1401,6 +1406,17 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
                         if( ctx->hctrl.overflow_pair )
                             throw std::runtime_error( "PairedReads: no candidate pair for two aligned mates" );
                     }
+                    if( ctx->reported_only )
+                    { // the writer's records of every read next to each other (ma_b200_set_reported_only)
+                        ctx->info_out.reserve( (size_t)n + 1 );
+                        ctx->alns_out.reserve( (size_t)nSets + 1 );
+                        zero_field( ctx, &PipeCtrl::reported_cursor );
+                        CompactArgs C{ ctx->info.p, ctx->info_out.p, n, ctx->alns.p, ctx->alns_out.p, ctx->ctrl.p };
+                        compact_reported_kernel<<<full_grid( ctx, compact_reported_kernel, 128, n ), 128, 0, s>>>( C );
+                        MA_CUDA( cudaGetLastError( ) );
+                        ctx->launches++;
+                        ctx->compacted = true;
+                    }
                 }
             }
             ctx->stage_done = upto_stage;
@@ -1429,6 +1445,8 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
     st.ms_total = ev_ms( ctx->ev[ 0 ], ctx->ev[ 6 ] );
     st.launches = (int)( ctx->launches - launches0 );
     st.n_failed = n > 0 ? ctx->hctrl.n_failed : 0;
+    ctx->n_reported = ctx->compacted ? (int64_t)ctx->hctrl.reported_cursor : 0;
+    st.n_reported = ctx->n_reported;
     if( stats )
         *stats = st;
     MA_API_END
@@ -1527,17 +1545,19 @@ extern "C" int ma_b200_align_download( ma_b200_ctx* ctx, ma_b200_read_info* info
         ctx->err = "no alignments computed";
         return MA_B200_ESTATE;
     }
-    if( cap_alns < ctx->n_sets || cap_runs < ctx->n_runs )
+    const bool compact = ctx->compacted && ctx->stage_done == 4;
+    const int64_t nAlns = compact ? ctx->n_reported : ctx->n_sets;
+    if( cap_alns < nAlns || cap_runs < ctx->n_runs )
     {
         ctx->err = "alignment buffers too small";
         return MA_B200_ENOMEM;
     }
     if( ctx->n_reads && info )
-        MA_CUDA( cudaMemcpyAsync( info, ctx->info.p, ctx->n_reads * sizeof( ReadInfo ), cudaMemcpyDeviceToHost,
-                                  ctx->stream ) );
-    if( ctx->n_sets )
-        MA_CUDA( cudaMemcpyAsync( alns, ctx->alns.p, ctx->n_sets * sizeof( DAln ), cudaMemcpyDeviceToHost,
-                                  ctx->stream ) );
+        MA_CUDA( cudaMemcpyAsync( info, compact ? ctx->info_out.p : ctx->info.p, ctx->n_reads * sizeof( ReadInfo ),
+                                  cudaMemcpyDeviceToHost, ctx->stream ) );
+    if( nAlns )
+        MA_CUDA( cudaMemcpyAsync( alns, compact ? ctx->alns_out.p : ctx->alns.p, nAlns * sizeof( DAln ),
+                                  cudaMemcpyDeviceToHost, ctx->stream ) );
     if( ctx->n_runs && !( ctx->early_runs_done && runs == ctx->early_runs ) )
         MA_CUDA( cudaMemcpyAsync( runs, ctx->runs.p, ctx->n_runs * sizeof( unsigned int ), cudaMemcpyDeviceToHost,
                                   ctx->stream ) );
@@ -1545,6 +1565,16 @@ extern "C" int ma_b200_align_download( ma_b200_ctx* ctx, ma_b200_read_info* info
     if( ctx->early_runs_done )
         MA_CUDA( cudaStreamSynchronize( ctx->copy_stream ) );
     MA_API_END
+}
+
+extern "C" int ma_b200_set_reported_only( ma_b200_ctx* ctx, int32_t on )
+{
+    if( !ctx )
+        return MA_B200_EINVAL;
+    ctx->reported_only = on != 0;
+    if( ctx->shadow )
+        ctx->shadow->reported_only = ctx->reported_only;
+    return MA_B200_OK;
 }
 
 extern "C" int ma_b200_set_batch_split( ma_b200_ctx* ctx, int64_t reads_per_subbatch )
@@ -1611,7 +1641,7 @@ struct BatchPipe
             int64_t a0 = 0, u0 = 0;
             {
                 std::unique_lock<std::mutex> g( mtx );
-                nAlns[ k ] = c->n_sets, nRuns[ k ] = c->n_runs;
+                nAlns[ k ] = c->compacted ? c->n_reported : c->n_sets, nRuns[ k ] = c->n_runs;
                 cv.notify_all( );
                 cv.wait( g, [ & ] {
                     if( rc )
@@ -1626,7 +1656,8 @@ struct BatchPipe
                 for( int64_t j = 0; j < k; j++ )
                     a0 += nAlns[ j ], u0 += nRuns[ j ];
             }
-            if( a0 + c->n_sets > cap_alns || u0 + c->n_runs > cap_runs )
+            const int64_t nOut = c->compacted ? c->n_reported : c->n_sets;
+            if( a0 + nOut > cap_alns || u0 + c->n_runs > cap_runs )
                 return fail( MA_B200_ENOMEM, "alignment buffers too small" );
             e = ma_b200_align_download( c, info + r0, alns + a0, cap_alns - a0, runs + u0, cap_runs - u0 );
             if( e )
@@ -1634,7 +1665,7 @@ struct BatchPipe
             // sub-batch-relative indices -> batch-relative (seed_off keeps pointing into the device slab)
             for( int64_t i = 0; i < n; i++ )
                 info[ r0 + i ].set_off += (int32_t)a0;
-            for( int64_t j = 0; j < c->n_sets; j++ )
+            for( int64_t j = 0; j < nOut; j++ )
                 alns[ a0 + j ].read += (int32_t)r0, alns[ a0 + j ].run_off += u0;
         }
     }
@@ -1693,7 +1724,7 @@ extern "C" int ma_b200_align_batch( ma_b200_ctx* ctx, int64_t n_reads, const uin
     }
     ma_b200_ctx* sh = ctx->shadow;
     const ma_b200_params saved = ctx->params;
-    sh->params = ctx->params;
+    sh->params = ctx->params, sh->reported_only = ctx->reported_only;
     sh->index = ctx->index, sh->have_index = true; // a view: the index slabs stay owned by ctx
     const int64_t l0 = ctx->launches, l1 = sh->launches;
     BatchPipe P;
@@ -1722,7 +1753,7 @@ extern "C" int ma_b200_align_batch( ma_b200_ctx* ctx, int64_t n_reads, const uin
             t.n_reads += s.n_reads, t.n_seeds += s.n_seeds, t.n_sets += s.n_sets, t.n_set_seeds += s.n_set_seeds;
             t.n_tasks += s.n_tasks, t.n_runs += s.n_runs, t.n_cigar_words += s.n_cigar_words, t.n_ext += s.n_ext;
             t.n_invpsi += s.n_invpsi, t.n_dropped += s.n_dropped, t.dp_cells += s.dp_cells, t.n_lookup += s.n_lookup;
-            t.n_failed += s.n_failed;
+            t.n_failed += s.n_failed, t.n_reported += s.n_reported;
             t.ms_seed += s.ms_seed, t.ms_locate += s.ms_locate, t.ms_socharm += s.ms_socharm, t.ms_plan += s.ms_plan;
             t.ms_dp += s.ms_dp, t.ms_assemble += s.ms_assemble, t.ms_total += s.ms_total;
         }

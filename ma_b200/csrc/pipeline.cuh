@@ -45,6 +45,7 @@ struct PipeCtrl
     int overflow_lists, overflow_fseg, overflow_runs, overflow_pair;
     int max_reported; // largest MappingQuality result vector of the batch
     int n_failed; // reads with a non-zero ReadInfo::status
+    unsigned long long reported_cursor; // records of the compact (reported-only) alignment array
     // DP task bins: window class (5) x kind (exact / early-stop left / early-stop right), + 1 for "band too wide"
     alignas( 128 ) int bin_count[ MA_NBINS ];
     alignas( 128 ) unsigned long long bin_tb[ MA_NBINS ];
@@ -676,6 +677,38 @@ struct MapqArgs
     int pair_cap;
     PipeCtrl* ctrl;
 };
+
+// Reported-only output (ma_b200_set_reported_only): the records MappingQuality / PairedReads hand to the writer
+// (rank_mq >= 0) of every read, copied next to each other into a second array, with the read's info pointing at them. On a
+// human-sized genome a read has ~3 seed sets but ~1.1 reported alignments: the download of the records shrinks 3x.
+struct CompactArgs
+{
+    const ReadInfo* info;
+    ReadInfo* info_out;
+    int n_reads;
+    const DAln* alns;
+    DAln* alns_out;
+    PipeCtrl* ctrl;
+};
+__global__ void __launch_bounds__( 128 ) compact_reported_kernel( CompactArgs A )
+{
+    for( int read = blockIdx.x * blockDim.x + threadIdx.x; read < A.n_reads; read += gridDim.x * blockDim.x )
+    {
+        ReadInfo ri = A.info[ read ];
+        int n = 0;
+        for( int k = 0; k < ri.n_sets; k++ )
+            n += A.alns[ ri.set_off + k ].rank_mq >= 0 ? 1 : 0;
+        long long o = 0;
+        if( n > 0 )
+            o = (long long)atomicAdd( &A.ctrl->reported_cursor, (unsigned long long)n );
+        int w = 0;
+        for( int k = 0; k < ri.n_sets && w < n; k++ )
+            if( A.alns[ ri.set_off + k ].rank_mq >= 0 )
+                A.alns_out[ o + w++ ] = A.alns[ ri.set_off + k ];
+        ri.set_off = (int)o, ri.n_sets = n;
+        A.info_out[ read ] = ri;
+    }
+}
 
 // MappingQuality::execute, one thread per read; also records the largest result vector (sizes the pairing scratch)
 __global__ void __launch_bounds__( 128 ) mapq_kernel( MapqArgs A )

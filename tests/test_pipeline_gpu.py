@@ -439,3 +439,33 @@ def test_two_gpus_sharded_batch_equals_one_gpu(gold_index):
         parts += r
         part_flags += f
     assert parts == full and sorted(part_flags) == full_flags
+
+
+@pytest.mark.parametrize("preset", ["illumina", "illuminapaired", "pacbio"])
+def test_reported_only_output_is_the_mapping_quality_vector(preset, gold_index):
+    """ma_b200_set_reported_only: the batch call hands back exactly the records with rank_mq >= 0 of the full output
+    (same fields, same run words), packed per read, and stats.n_reported counts them."""
+    reads = PC.read_reads_txt(PC.gold_reads(preset))
+    data, off = api.pack_reads(reads)
+
+    def run(reported_only):
+        ctx = make_ctx(preset)
+        ctx.index_upload(gold_index)
+        ctx.set_reported_only(reported_only)
+        info, alns, runs, st = ctx.align_batch(data, off, cap_alns=20000, cap_runs=4_000_000)
+        ctx.close()
+        rows = []
+        for i in range(len(reads)):
+            a = alns[info["set_off"][i]:info["set_off"][i] + info["n_sets"][i]]
+            assert (a["read"] == i).all()
+            for x in a[np.argsort(a["rank"], kind="stable")]:
+                rows.append((i, int(x["rank"]), int(x["rank_mq"]), int(x["pair_rank"]), int(x["flags"]), int(x["score"]),
+                             int(x["begin_ref"]), int(x["end_ref"]), int(x["begin_q"]), int(x["end_q"]),
+                             x["mapq"].tobytes(), tuple(runs[x["run_off"]:x["run_off"] + x["n_runs"]].tolist())))
+        return rows, st
+
+    full, st_full = run(False)
+    rep, st_rep = run(True)
+    assert rep == [r for r in full if r[2] >= 0]
+    assert st_rep["n_reported"] == len(rep) and st_rep["n_sets"] == st_full["n_sets"]
+    assert len(rep) < len(full) if preset == "illumina" else len(rep) <= len(full)  # (illumina drops records, n-best)
