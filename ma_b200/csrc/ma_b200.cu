@@ -757,6 +757,32 @@ static void index_make_planes( ma_b200_ctx* ctx, long long n_words, long long re
                                                           (unsigned int*)ctx->ix_bwtp.p );
     MA_CUDA( cudaGetLastError( ) );
     ctx->launches++;
+    // Optional (MA_B200_L2_WINDOW=<hit ratio in percent>): an L2 access-policy window over the occurrence table, the
+    // north_star's "top BWT levels pinned in L2". The blocks of the shallow extension depths are NOT contiguous (the 4^d
+    // intervals of depth d lie all over the table), so the window can only cover the table as a whole, with a hit
+    // ratio that keeps the persisting part within the L2 set-aside. Measured in DESIGN.md §4.2.
+    if( const char* e = getenv( "MA_B200_L2_WINDOW" ) )
+    {
+        const int pct = atoi( e );
+        if( pct > 0 )
+        {
+            cudaDeviceProp prop;
+            MA_CUDA( cudaGetDeviceProperties( &prop, ctx->device ) );
+            const size_t bytes = (size_t)nblk * 64;
+            const size_t setAside = std::min<size_t>( (size_t)prop.persistingL2CacheMaxSize, bytes );
+            MA_CUDA( cudaDeviceSetLimit( cudaLimitPersistingL2CacheSize, setAside ) );
+            cudaStreamAttrValue attr;
+            memset( &attr, 0, sizeof( attr ) );
+            attr.accessPolicyWindow.base_ptr = ctx->ix_bwtp.p;
+            attr.accessPolicyWindow.num_bytes = std::min<size_t>( bytes, (size_t)prop.accessPolicyMaxWindowSize );
+            attr.accessPolicyWindow.hitRatio = std::min( 1.0f, pct / 100.0f );
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            MA_CUDA( cudaStreamSetAttribute( ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr ) );
+            fprintf( stderr, "ma_b200: L2 window over %zu MB of the occurrence table (max window %d MB), set-aside %zu MB, hit ratio %.2f\n",
+                     bytes >> 20, prop.accessPolicyMaxWindowSize >> 20, setAside >> 20, attr.accessPolicyWindow.hitRatio );
+        }
+    }
 }
 
 extern "C" int ma_b200_index_upload( ma_b200_ctx* ctx, const uint32_t* bwt_words, int64_t n_words, const int64_t* L2,
