@@ -16,10 +16,14 @@
 #include "ma/container/fMIndex.h"
 #include "ma/container/nucSeq.h"
 #include "ma/container/pack.h"
+#include "ma/module/fileReader.h"
+#include "ma/module/fileWriter.h"
+#include "ms/module/splitter.h"
 #include "ma_b200.h"
 #include "ms/container/container.h"
 #include "ms/module/module.h"
 #include "ms/util/parameter.h"
+#include <chrono>
 #include <condition_variable>
 #include <fstream>
 #include <mutex>
@@ -217,10 +221,12 @@ class GpuAlign : public libMS::Module<libMS::ContainerVector<std::shared_ptr<Ali
     std::vector<std::pair<int, std::shared_ptr<Alignment>>> vPendingMate;
 };
 
-/* Per-read front of GpuAlign for the reference's one-graph-per-thread model: every graph thread calls
- * execute( read, index ) and blocks; the call that completes a batch of uiBatch reads — or finds every other
- * participant already waiting — runs the batch on the GPU and wakes the others. One object is shared by all graphs
- * (like the reference's shared FileWriter, which serialises itself with a mutex: fileWriter.h:386-398). */
+/* Per-read front of GpuAlign for the reference's one-graph-per-thread model (SURVEY.md §8(b) option (i)): every graph
+ * thread calls execute( read, index ) and blocks; the call that completes a batch of uiBatch reads runs the batch on the
+ * GPU and wakes the others. A graph thread cannot tell the module that it has run out of reads, so a waiting call that
+ * sees no progress for uiPatienceMicroseconds flushes what is open (the last, short batches of a run). One object is
+ * shared by all graphs, like the reference's shared FileWriter, which serialises itself with a mutex
+ * (fileWriter.h:386-398). */
 class GpuAlignPerRead : public libMS::Module<AlignmentVector, false, NucSeq, GpuIndex>
 {
     struct Slot
@@ -232,14 +238,14 @@ class GpuAlignPerRead : public libMS::Module<AlignmentVector, false, NucSeq, Gpu
     };
     GpuAlign xBatch;
     const size_t uiBatch;
-    size_t uiParticipants; /* graph threads that still deliver reads; a flush happens when all of them wait */
+    const unsigned int uiPatienceMicroseconds;
     std::mutex xMutex;
     std::condition_variable xCv;
     std::vector<std::shared_ptr<Slot>> vOpen;
     uint64_t uiReadCounter = 0;
 
-    void flush( std::unique_lock<std::mutex>& rLock, std::shared_ptr<GpuIndex> pIdx )
-    { /* called with the lock held by the thread that completes the batch; the GPU call runs without the lock */
+    void flush( std::shared_ptr<GpuIndex> pIdx )
+    { /* with the lock held: one context, one GPU call at a time; reads that arrive meanwhile wait for the lock */
         std::vector<std::shared_ptr<Slot>> vMine;
         vMine.swap( vOpen );
         const uint64_t uiFirst = uiReadCounter;
@@ -253,7 +259,7 @@ class GpuAlignPerRead : public libMS::Module<AlignmentVector, false, NucSeq, Gpu
         {
             if( xBatch.bSrand )
                 xBatch.uiSrandBase = (uint32_t)( uiSrandFirst + uiFirst );
-            pRes = xBatch.execute( pReads, pIdx ); /* (the lock is kept: one context, one GPU call at a time) */
+            pRes = xBatch.execute( pReads, pIdx );
         }
         catch( const std::exception& e )
         {
@@ -266,26 +272,17 @@ class GpuAlignPerRead : public libMS::Module<AlignmentVector, false, NucSeq, Gpu
                 vMine[ i ]->pResult = ( *pRes )[ i ];
             vMine[ i ]->bDone = true;
         }
-        (void)rLock;
         xCv.notify_all( );
     }
 
   public:
     uint64_t uiSrandFirst = 0;
-    GpuAlignPerRead( const ParameterSetManager& rParameters, size_t uiBatch, size_t uiThreads )
-        : xBatch( rParameters ), uiBatch( uiBatch ), uiParticipants( uiThreads )
+    GpuAlignPerRead( const ParameterSetManager& rParameters, size_t uiBatch, unsigned int uiPatienceMicroseconds = 2000 )
+        : xBatch( rParameters ), uiBatch( uiBatch ), uiPatienceMicroseconds( uiPatienceMicroseconds )
     {}
     void setSrand( uint64_t uiBase )
     {
         xBatch.bSrand = true, uiSrandFirst = uiBase;
-    }
-    /* a graph thread that has run out of reads leaves: the remaining ones must not wait for it */
-    void leave( std::shared_ptr<GpuIndex> pIdx )
-    {
-        std::unique_lock<std::mutex> xLock( xMutex );
-        uiParticipants--;
-        if( !vOpen.empty( ) && vOpen.size( ) >= uiParticipants )
-            flush( xLock, pIdx );
     }
     virtual std::shared_ptr<AlignmentVector> execute( std::shared_ptr<NucSeq> pQuery, std::shared_ptr<GpuIndex> pIdx )
     {
@@ -293,14 +290,52 @@ class GpuAlignPerRead : public libMS::Module<AlignmentVector, false, NucSeq, Gpu
         pSlot->pQuery = pQuery;
         std::unique_lock<std::mutex> xLock( xMutex );
         vOpen.push_back( pSlot );
-        if( vOpen.size( ) >= uiBatch || vOpen.size( ) >= uiParticipants )
-            flush( xLock, pIdx );
-        else
-            xCv.wait( xLock, [ & ] { return pSlot->bDone; } );
+        if( vOpen.size( ) >= uiBatch )
+            flush( pIdx );
+        while( !pSlot->bDone )
+            if( !xCv.wait_for( xLock, std::chrono::microseconds( uiPatienceMicroseconds ), [ & ] { return pSlot->bDone; } ) )
+                if( !pSlot->bDone ) /* nobody completed the batch in time: the other graphs are busy or out of reads */
+                    flush( pIdx );
         if( !pSlot->sError.empty( ) )
             throw std::runtime_error( pSlot->sError );
         return pSlot->pResult;
     }
 };
+
+/* setUpCompGraph (libs/ma/src/util/export.cpp:72-128) with the five CPU modules BinarySeeding .. MappingQuality replaced
+ * by ONE shared GpuAlignPerRead: the same file-stream queue, lock, FileReader, writer, progress printer and unlock
+ * modules, one graph per thread, evaluated by BasePledge::simultaneousGet exactly like ExecutionContext::doAlign does
+ * (execution-context.h:291-406) — a GPU build of doAlign calls this instead of setUpCompGraph. */
+/* the writer interface of setUpCompGraph (TP_WRITER, ma/util/export.h:166-167; that header also pulls in the minimizer
+ * modules, which are not part of this build) */
+typedef libMS::Module<libMS::Container, false, NucSeq, libMS::ContainerVector<std::shared_ptr<Alignment>>, Pack> TP_GPU_WRITER;
+
+inline std::vector<std::shared_ptr<libMS::BasePledge>>
+setUpCompGraphGpu( const ParameterSetManager& rParameters, std::shared_ptr<libMS::Pledge<Pack>> pPack,
+                   std::shared_ptr<libMS::Pledge<GpuIndex>> pGpuIndex,
+                   std::shared_ptr<libMS::Pledge<FileStreamQueue, false>> pQueue, std::shared_ptr<TP_GPU_WRITER> pWriter,
+                   std::shared_ptr<GpuAlignPerRead> pGpuAlign, unsigned int uiThreads )
+{
+    using namespace libMS;
+    auto pFileStreamPicker = std::make_shared<QueuePicker<FileStream>>( rParameters );
+    auto pLock = std::make_shared<Lock<FileStream>>( rParameters );
+    auto pFileReader = std::make_shared<FileReader>( rParameters );
+    auto pFileStreamPlacer = std::make_shared<QueuePlacer<NucSeq, FileStream>>( rParameters );
+    auto pProgressPrinter = std::make_shared<ProgressPrinter<FileStreamQueue>>( rParameters );
+    std::vector<std::shared_ptr<BasePledge>> aRet;
+    BasePledge::parallelGraph( uiThreads, [ & ]( ) {
+        auto pPickedFile = promiseMe( pFileStreamPicker, pQueue );
+        auto pLockedFile = promiseMe( pLock, pPickedFile );
+        auto pQuery_ = promiseMe( pFileReader, pLockedFile );
+        auto pQuery = promiseMe( pFileStreamPlacer, pQuery_, pLockedFile, pQueue );
+        auto pAlignmentsWQuality = promiseMe( pGpuAlign, pQuery, pGpuIndex ); /* seeding .. MappingQuality on the GPU */
+        auto pEmptyContainer = promiseMe( pWriter, pQuery, pAlignmentsWQuality, pPack );
+        auto pEmptyContainer_ = promiseMe( pProgressPrinter, pEmptyContainer, pQueue );
+        auto pUnlockResult =
+            promiseMe( std::make_shared<UnLock<libMS::Container>>( rParameters, pLockedFile ), pEmptyContainer_ );
+        aRet.push_back( pUnlockResult );
+    } );
+    return aRet;
+}
 
 } // namespace libMA

@@ -4,6 +4,9 @@
 // compiled reference) and libma_b200.so. Test infrastructure for the boundary, not part of the product.
 //   ref_gpu_sam batch   <index prefix> <reads> <preset> <out.sam> <srand base>
 //   ref_gpu_sam perread <index prefix> <reads> <preset> <out.sam> <srand base> <threads> <batch>
+//   ref_gpu_sam graph   <index prefix> <reads.fa|fq> <preset> <out.sam> <srand base> <threads> <batch>
+//       the reference's computational graph itself: setUpCompGraphGpu + BasePledge::simultaneousGet, i.e. what
+//       ExecutionContext::doAlign does with the GPU module in place of the five CPU modules
 #include "gpu_align.h"
 #include "ma/module/fileReader.h"
 #include "ma/module/fileWriter.h"
@@ -50,7 +53,7 @@ int main( int argc, char** argv )
         for( auto& c : sPreset )
             c = std::tolower( c );
         xP.setSelected( sPreset );
-        auto vReads = readQueries( xP, argv[ 3 ] );
+        auto vReads = sMode == "graph" ? std::vector<std::shared_ptr<NucSeq>>( ) : readQueries( xP, argv[ 3 ] );
         auto pIdx = std::make_shared<GpuIndex>( 0, sPrefix );
         auto pPack = pIdx->pPack;
         const bool bPaired = xP.getSelected( )->xUsePairedReads->get( );
@@ -77,11 +80,30 @@ int main( int argc, char** argv )
             }
             return 0;
         }
+        if( sMode == "graph" )
+        {
+            const unsigned int uiThreads = argc > 7 ? (unsigned int)atoi( argv[ 7 ] ) : 4;
+            const size_t uiBatch = argc > 8 ? (size_t)atoi( argv[ 8 ] ) : 64;
+            auto pAlign = std::make_shared<GpuAlignPerRead>( xP, uiBatch );
+            pAlign->setSrand( uiSrand );
+            auto pPackPledge = std::make_shared<Pledge<Pack>>( );
+            pPackPledge->set( pPack );
+            auto pIdxPledge = std::make_shared<Pledge<GpuIndex>>( );
+            pIdxPledge->set( pIdx );
+            auto pInitVec = std::make_shared<ContainerVector<std::shared_ptr<FileStream>>>( );
+            pInitVec->push_back( std::make_shared<FileStreamFromPath>( std::string( argv[ 3 ] ) ) );
+            auto pQueuePledge = std::make_shared<Pledge<FileStreamQueue>>( );
+            pQueuePledge->set( std::make_shared<FileStreamQueue>( pInitVec ) );
+            std::shared_ptr<TP_GPU_WRITER> pWriter( new FileWriter( xP, std::string( argv[ 5 ] ), pPack ) );
+            auto aGraphSinks = setUpCompGraphGpu( xP, pPackPledge, pIdxPledge, pQueuePledge, pWriter, pAlign, uiThreads );
+            BasePledge::simultaneousGet( aGraphSinks );
+            return 0;
+        }
         // per-read graphs: T threads, each the loop of one computational graph of setUpCompGraph (reader -> aligner ->
         // writer); the aligner module is shared and batches behind the scenes. Output order is the threads' order, as
         // with the reference's own shared FileWriter.
         const size_t uiThreads = argc > 7 ? (size_t)atoi( argv[ 7 ] ) : 4, uiBatch = argc > 8 ? (size_t)atoi( argv[ 8 ] ) : 64;
-        auto pAlign = std::make_shared<GpuAlignPerRead>( xP, uiBatch, uiThreads );
+        auto pAlign = std::make_shared<GpuAlignPerRead>( xP, uiBatch );
         auto pW = std::make_shared<FileWriter>( xP, std::string( argv[ 5 ] ), pPack );
         std::mutex xNext;
         size_t uiNext = 0;
@@ -112,7 +134,6 @@ int main( int argc, char** argv )
                 {
                     vErr[ t ] = e.what( );
                 }
-                pAlign->leave( pIdx );
             } );
         for( auto& t : vT )
             t.join( );

@@ -62,3 +62,29 @@ def test_per_read_blocking_batcher_many_graph_threads(tmp_path):
                                    not int(l.split("\t")[1]) & 0x900)
     assert primary(got) == primary(gold)
     assert [l for l in got if l.startswith("@")] == [l for l in gold if l.startswith("@")]
+
+
+def test_reference_computational_graph_with_gpu_module_one_thread_is_exact(tmp_path):
+    """setUpCompGraphGpu: the reference's own graph (QueuePicker, Lock, FileReader, QueuePlacer, FileWriter,
+    ProgressPrinter, UnLock wired with promiseMe and evaluated by BasePledge::simultaneousGet, as
+    ExecutionContext::doAlign does, execution-context.h:291-406) with GpuAlignPerRead in place of the five CPU modules.
+    One graph thread: batches follow the file order, the SAM file is the reference chain's."""
+    _need_exe()
+    out = str(tmp_path / "o.sam")
+    subprocess.run([EXE, "graph", PC.GOLD_PREFIX, os.path.join(H.GOLDEN, "gold_reads.fa"), "illumina", out, str(PC.SRAND),
+                    "1", "8"], check=True, timeout=120)
+    assert open(out).read() == open(os.path.join(H.GOLDEN, "gold_fa_illumina.sam")).read()
+
+
+def test_reference_computational_graph_with_gpu_module_many_threads(tmp_path):
+    """Six graph threads on the shared module: every read is written exactly once, the run ends (no thread waits for a
+    batch that never fills once the others have run out of reads)."""
+    _need_exe()
+    out = str(tmp_path / "o.sam")
+    subprocess.run([EXE, "graph", PC.GOLD_PREFIX, os.path.join(H.GOLDEN, "gold_reads.fa"), "illumina", out, str(PC.SRAND),
+                    "6", "16"], check=True, timeout=120)
+    gold = open(os.path.join(H.GOLDEN, "gold_fa_illumina.sam")).read().splitlines()
+    got = open(out).read().splitlines()
+    primary = lambda lines: sorted(l.split("\t")[0] for l in lines if not l.startswith("@") and
+                                   not int(l.split("\t")[1]) & 0x900)
+    assert primary(got) == primary(gold)
