@@ -337,18 +337,18 @@ def main():
     per_read_alns, per_read_runs = (3, 40) if cfg["kind"] == "pairs" else (8, 12 * L // 10)
     out = {"cap_alns": per_read_alns * max_n + 1024, "cap_runs": per_read_runs * max_n + 4096}
 
-    def alloc_out():
-        out["info"] = torch.empty(max_n * api.INFO_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
-        out["alns"] = torch.empty(out["cap_alns"] * api.ALN_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
-        out["runs"] = torch.empty(out["cap_runs"], dtype=torch.int32, pin_memory=True)
+    def alloc_out(o):
+        o["info"] = torch.empty(max_n * api.INFO_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
+        o["alns"] = torch.empty(o["cap_alns"] * api.ALN_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
+        o["runs"] = torch.empty(o["cap_runs"], dtype=torch.int32, pin_memory=True)
 
-    alloc_out()
+    alloc_out(out)
 
-    def set_shard_params(sub):
+    def set_shard_params(sub, c=None):
         # RANSAC streams follow the GLOBAL read index: results do not depend on the sharding
         p = api.preset(cfg["preset"])
         p.srand_base = madist.shard_srand_base(base_params.srand_base, first_read + sub["lo"])
-        ctx.set_params(p)
+        (c or ctx).set_params(p)
 
     def barrier():
         torch.cuda.synchronize()
@@ -356,22 +356,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def e2e_sub(sub, count=False):
+    def e2e_sub(sub, count=False, c=None, o=None):
         """ma_b200_align_batch: pinned host reads in, alignment records in pinned host memory out."""
-        set_shard_params(sub)
+        c, o = c or ctx, o or out
+        set_shard_params(sub, c)
         st = api.AlignStats()
-        rc = ctx.lib.ma_b200_align_batch(ctx.h, sub["n"], sub["reads"].data_ptr(), sub["offsets"].ctypes.data,
-                                         out["info"].data_ptr(), out["alns"].data_ptr(), out["cap_alns"],
-                                         out["runs"].data_ptr(), out["cap_runs"], ctypes.byref(st))
+        rc = c.lib.ma_b200_align_batch(c.h, sub["n"], sub["reads"].data_ptr(), sub["offsets"].ctypes.data,
+                                       o["info"].data_ptr(), o["alns"].data_ptr(), o["cap_alns"],
+                                       o["runs"].data_ptr(), o["cap_runs"], ctypes.byref(st))
         if rc == -3:  # MA_B200_ENOMEM: the record buffers of this bench were too small; grow them from the counts
-            out["cap_alns"] = max(out["cap_alns"], int(max(st.n_sets if args.all_records else 0, st.n_reported) * 1.3) + 1024)
-            out["cap_runs"] = max(out["cap_runs"], int(st.n_runs * 1.3) + 4096)
-            alloc_out()
-            return e2e_sub(sub, count)
-        ctx._check(rc)
+            o["cap_alns"] = max(o["cap_alns"], int(max(st.n_sets if args.all_records else 0, st.n_reported) * 1.3) + 1024)
+            o["cap_runs"] = max(o["cap_runs"], int(st.n_runs * 1.3) + 4096)
+            alloc_out(o)
+            return e2e_sub(sub, count, c, o)
+        c._check(rc)
         if not count:
             return st, 0
-        info = np.frombuffer(out["info"].numpy(), dtype=api.INFO_DTYPE)[:sub["n"]]
+        info = np.frombuffer(o["info"].numpy(), dtype=api.INFO_DTYPE)[:sub["n"]]
         return st, int((info["n_sets"] > 0).sum())
 
     def device_pass(collect=None):
@@ -404,7 +405,11 @@ def main():
     launches = ctx.launch_count - launches0
     K = args.steps
     last = {k: v / K for k, v in work.items()}  # per step (sum over the sub-batches)
-    # ---- end to end timing: `e2e`
+    # ---- end to end timing: `e2e`. Every step goes through ma_b200_align_batch with pinned HOST buffers (reads in,
+    # records out). Two batches are kept in flight — two host threads, each with its own context (the second one a sibling
+    # that shares the index) and its own record buffers — so that the copies of one batch run under the kernels of the
+    # other: the way a caller with a stream of batches uses the call (maCMD_b200 does it per GPU). The figure of ONE
+    # call at a time is measured as well (e2e.single_call).
     aligned = 0
     for sub in subs:  # warm-up pass of the end-to-end path; the aligned reads are counted here, outside the timed region
         aligned += e2e_sub(sub, True)[1]
@@ -412,30 +417,63 @@ def main():
     barrier()
     t = time.perf_counter()
     for _ in range(args.steps):
-        n_sets, n_runs = 0, 0
         for sub in subs:
-            est, _a = e2e_sub(sub)
-            n_sets += est.n_sets if args.all_records else est.n_reported
-            n_runs += est.n_runs
+            e2e_sub(sub)
+    torch.cuda.synchronize()
+    e2e_single_s = time.perf_counter() - t
+    ctx2 = ctx.sibling()
+    out2 = {"cap_alns": out["cap_alns"], "cap_runs": out["cap_runs"]}
+    alloc_out(out2)
+    items = [sub for _ in range(args.steps) for sub in subs]
+    lanes = [(ctx, out, items[0::2]), (ctx2, out2, items[1::2])]
+    for c, o, mine in lanes:  # warm-up of both pipelines (slab sizes of the sibling)
+        for sub in mine[:max(1, len(subs) // 2)] or items[:1]:
+            e2e_sub(sub, False, c, o)
+    counts = [[0, 0], [0, 0]]
+    errors = []
+
+    def lane(k):
+        c, o, mine = lanes[k]
+        try:
+            torch.cuda.set_device(local_rank)
+            for sub in mine:
+                est, _a = e2e_sub(sub, False, c, o)
+                counts[k][0] += est.n_sets if args.all_records else est.n_reported
+                counts[k][1] += est.n_runs
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    barrier()
+    t = time.perf_counter()
+    threads = [threading.Thread(target=lane, args=(k,)) for k in range(2)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t
+    if errors:
+        raise errors[0]
     barrier()
+    n_sets = (counts[0][0] + counts[1][0]) // args.steps
+    n_runs = (counts[0][1] + counts[1][1]) // args.steps
+    ctx2.close()
     sampler.stop_flag = True
     sampler.join(timeout=2)
     h2d = n_reads * L + (n_reads + len(subs)) * 8
     d2h = n_reads * api.INFO_DTYPE.itemsize + n_sets * api.ALN_DTYPE.itemsize + n_runs * 4
 
-    times = torch.tensor([dev_ms, e2e_s * 1000.0, float(aligned), float(h2d), float(d2h), float(n_reads)],
+    times = torch.tensor([dev_ms, e2e_s * 1000.0, float(aligned), float(h2d), float(d2h), float(n_reads), e2e_single_s * 1000.0],
                          dtype=torch.float64, device="cuda")
     if world > 1:
         mx = times.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = times.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        dev_ms_max, e2e_ms_max = float(mx[0]), float(mx[1])
+        dev_ms_max, e2e_ms_max, e2e_single_ms_max = float(mx[0]), float(mx[1]), float(mx[6])
         aligned_all, h2d_all, d2h_all, reads_all = float(sm[2]), float(sm[3]), float(sm[4]), float(sm[5])
     else:
-        dev_ms_max, e2e_ms_max = dev_ms, e2e_s * 1000.0
+        dev_ms_max, e2e_ms_max, e2e_single_ms_max = dev_ms, e2e_s * 1000.0, e2e_single_s * 1000.0
         aligned_all, h2d_all, d2h_all, reads_all = float(aligned), float(h2d), float(d2h), float(n_reads)
     if rank != 0:
         ctx.close()
@@ -534,7 +572,7 @@ def main():
               "reads_per_step": int(reads_all), "reads_per_step_per_gpu": n_reads, "sub_batches_per_gpu": len(subs),
               "genome_bp": cfg["genome_mbp"] * 1_000_000, "parallelism": "index replicated, reads sharded x%d" % world,
               "timed_region": "value: CUDA-event time of ma_b200_align_run over the sub-batches, reads resident in HBM; "
-                              "e2e: wall time of ma_b200_align_batch over the same sub-batches, pinned host buffers, "
+                              "e2e: wall time of ma_b200_align_batch over the same sub-batches, pinned host buffers, two batches in flight, "
                               + ("every alignment record" if args.all_records else
                                  "the records MappingQuality / PairedReads return (what the writer consumes) + all run words"),
               "l2": "inputs larger than L2 (reads %d MB + index %d MB per step, no flush needed)"
@@ -543,7 +581,13 @@ def main():
             "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
             "dtype": "u8/int64 (f64 in Harmonization)", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d_all),
-                    "d2h_bytes_per_step": int(d2h_all), "ms_per_step": e2e_ms_max / K},
+                    "d2h_bytes_per_step": int(d2h_all), "ms_per_step": e2e_ms_max / K, "batches_in_flight": 2,
+                    "single_call": {"value": aligned_all * K / (e2e_single_ms_max / 1000.0), "ms_per_step": e2e_single_ms_max / K,
+                                    "note": "one ma_b200_align_batch at a time (upload under the seeding kernel, run "
+                                            "words down under stage 4, records down after the last kernel)"},
+                    "note": "K steps through ma_b200_align_batch from two host threads on two contexts of the GPU (the "
+                            "second a sibling sharing the index): the host<->device copies of one batch run under the "
+                            "kernels of the other"},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
             "roofline_seeding": roofline_seeding, "kernels": kernels, "cpu_baseline": cpu_baseline,
             "aligned_reads_per_step": aligned_all, "Mbp_per_s": value * L / 1e6, "index_build_s": t_index,

@@ -71,6 +71,12 @@ int ma_b200_params_preset( const char* name, ma_b200_params* out );
 /* ---- context ---------------------------------------------------------------------------------------------- */
 int ma_b200_create( int device, ma_b200_ctx** out );
 void ma_b200_destroy( ma_b200_ctx* ctx );
+/* A second context on the same device that SHARES the index of ctx (a view: ctx keeps owning it and must outlive the
+ * sibling; re-uploading / rebuilding the index of ctx invalidates the view until ma_b200_create_sibling is called again)
+ * and starts with its parameters. For a stream of batches: two host threads, each calling ma_b200_align_batch on its own
+ * context, keep two batches in flight — the host<->device copies of one run under the kernels of the other (what
+ * maCMD_b200 does per GPU, and bench.py's e2e figure). A context itself stays single-threaded. */
+int ma_b200_create_sibling( ma_b200_ctx* ctx, ma_b200_ctx** out );
 const char* ma_b200_last_error( const ma_b200_ctx* ctx );
 int ma_b200_set_params( ma_b200_ctx* ctx, const ma_b200_params* params );
 /* number of kernels this context has launched so far (for bench.py's gpu_launches) */

@@ -109,6 +109,8 @@ def load_library():
     lib.ma_b200_set_params.argtypes = [vp, ctypes.POINTER(Params)]
     lib.ma_b200_ksw_set_extension_only.argtypes = [vp, ctypes.c_int32]
     lib.ma_b200_set_batch_split.argtypes = [vp, i64]
+    lib.ma_b200_create_sibling.argtypes = [vp, ctypes.POINTER(vp)]
+    lib.ma_b200_set_reported_only.argtypes = [vp, ctypes.c_int32]
     lib.ma_b200_ksw_upload.argtypes = [vp, i64, vp, vp, i64]
     lib.ma_b200_ksw_run.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     lib.ma_b200_ksw_download.argtypes = [vp, vp, vp, i64, ctypes.POINTER(i64)]
@@ -155,6 +157,19 @@ class Context:
         self.h = h
         self.params = preset(preset_name)
         self.set_params(self.params)
+
+    def sibling(self):
+        """A second context on the same device sharing this one's index (ma_b200_create_sibling): for two batches in
+        flight from two host threads. This context must outlive it."""
+        other = Context.__new__(Context)
+        other.lib = self.lib
+        h = ctypes.c_void_p()
+        self._check(self.lib.ma_b200_create_sibling(self.h, ctypes.byref(h)))
+        other.h = h
+        other.params = self.params
+        other._stats, other._n_reads = {}, 0
+        other._reported_only = getattr(self, "_reported_only", False)
+        return other
 
     def close(self):
         if getattr(self, "h", None):

@@ -239,6 +239,23 @@ extern "C" int ma_b200_create( int device, ma_b200_ctx** out )
     return MA_B200_OK;
 }
 
+extern "C" int ma_b200_create_sibling( ma_b200_ctx* ctx, ma_b200_ctx** out )
+{
+    if( !ctx || !out )
+        return MA_B200_EINVAL;
+    if( !ctx->have_index )
+    {
+        ctx->err = "create_sibling: no index uploaded";
+        return MA_B200_ESTATE;
+    }
+    const int rc = ma_b200_create( ctx->device, out );
+    if( rc )
+        return rc;
+    ( *out )->params = ctx->params, ( *out )->reported_only = ctx->reported_only;
+    ( *out )->index = ctx->index, ( *out )->have_index = true; // a view: the index slabs stay owned by ctx
+    return MA_B200_OK;
+}
+
 extern "C" void ma_b200_destroy( ma_b200_ctx* ctx )
 {
     if( !ctx )
