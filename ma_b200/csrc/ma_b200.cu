@@ -118,6 +118,8 @@ struct ma_b200_ctx
     bool reported_only = false; // ma_b200_set_reported_only
     bool compacted = false; // the last run filled info_out / alns_out
     int64_t n_reported = 0;
+    DevBuf<unsigned long long> soc_scratch; // socbuild_kernel -> harmonize_kernel
+    DevBuf<int> soc_nmax;
     DevBuf<ReadInfo> info_out;
     DevBuf<DAln> alns_out;
 };
@@ -1311,9 +1313,25 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
                 A.scratch = ctx->harm_scratch.p, A.scratch_cap = ctx->harm_scratch.cap;
                 A.set_seeds = ctx->set_seeds.p, A.set_seed_cap = setSeedCap, A.sets = ctx->sets.p, A.set_cap = setCap;
                 A.srand_base = ctx->params.srand_base, A.ctrl = ctx->ctrl.p;
-                socharm_kernel<<<full_grid( ctx, socharm_kernel, MA_SOC_BLOCK, n ), MA_SOC_BLOCK, 0, s>>>( A );
-                MA_CUDA( cudaGetLastError( ) );
-                ctx->launches++;
+                static const bool bOneKernel = getenv( "MA_B200_SOC_ONE_KERNEL" ) && atoi( getenv( "MA_B200_SOC_ONE_KERNEL" ) );
+                if( bOneKernel )
+                {
+                    A.soc_scratch = nullptr, A.soc_nmax = nullptr;
+                    socharm_kernel<<<full_grid( ctx, socharm_kernel, MA_SOC_BLOCK, n ), MA_SOC_BLOCK, 0, s>>>( A );
+                    MA_CUDA( cudaGetLastError( ) );
+                    ctx->launches++;
+                }
+                else
+                {
+                    ctx->soc_scratch.reserve( (size_t)n + 1 );
+                    ctx->soc_nmax.reserve( (size_t)n + 1 );
+                    A.soc_scratch = ctx->soc_scratch.p, A.soc_nmax = ctx->soc_nmax.p;
+                    socbuild_kernel<<<full_grid( ctx, socbuild_kernel, MA_SOC_BLOCK, n ), MA_SOC_BLOCK, 0, s>>>( A );
+                    MA_CUDA( cudaGetLastError( ) );
+                    harmonize_kernel<<<full_grid( ctx, harmonize_kernel, MA_SOC_BLOCK, n ), MA_SOC_BLOCK, 0, s>>>( A );
+                    MA_CUDA( cudaGetLastError( ) );
+                    ctx->launches += 2;
+                }
                 read_ctrl( ctx );
                 if( ctx->hctrl.scratch_cursor > ctx->harm_scratch.cap )
                     throw std::runtime_error( "harmonization: scratch arena too small (internal error)" );
@@ -1327,6 +1345,7 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
                 zero_field( ctx, &PipeCtrl::set_cursor );
                 zero_field( ctx, &PipeCtrl::scratch_cursor );
                 zero_field( ctx, &PipeCtrl::next_read2 );
+                zero_field( ctx, &PipeCtrl::next_read3 );
             }
             ctx->n_sets = (int64_t)ctx->hctrl.set_cursor, ctx->n_set_seeds = (int64_t)ctx->hctrl.set_seed_cursor;
             ctx->stage_done = 2;

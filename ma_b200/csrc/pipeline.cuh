@@ -328,6 +328,10 @@ struct SocHarmArgs
     long long set_cap;
     unsigned int srand_base;
     PipeCtrl* ctrl;
+    // the stage as two kernels (socbuild_kernel -> harmonize_kernel): per read, where its scratch starts (~0: none) and
+    // how many windows soc_build left in the queue
+    unsigned long long* soc_scratch;
+    int* soc_nmax;
 };
 
 #define MA_MAX_SETS_PER_READ 128
@@ -413,6 +417,87 @@ __global__ void __launch_bounds__( MA_SOC_BLOCK, MA_SOC_MINB ) socharm_kernel( S
                             A.sets[ ho + i ] = h;
                         }
                 }
+            }
+        }
+        A.info[ read ] = ri;
+    }
+}
+
+// The same stage as two kernels. The one-kernel form is 16 k instructions that every warp walks at its own pace (ncu:
+// issue 16 %, instruction-fetch stalls dominant); split, the warps of a launch stay within one half of that code: sort +
+// sweep + heap in the first kernel, RANSAC + linesweeps + filters in the second.
+__global__ void __launch_bounds__( MA_SOC_BLOCK, MA_SOC_MINB ) socbuild_kernel( SocHarmArgs A )
+{
+    while( true )
+    {
+        const int read = atomicAdd( &A.ctrl->next_read2, 1 );
+        if( read >= A.n_reads )
+            break;
+        const ReadInfo ri = A.info[ read ];
+        unsigned long long where = ~0ull;
+        int nMax = 0;
+        if( ri.n_seeds > 0 )
+        {
+            const int n = ri.n_seeds;
+            // the SoC sorts its seeds in place: work on a copy so that the stage can be re-run after a slab grew
+            const size_t copyBytes = ( (size_t)n * sizeof( DSeed ) + 15 ) & ~(size_t)15;
+            const size_t need = harm_scratch_need( (size_t)n ) + copyBytes + 64;
+            const unsigned long long so = atomicAdd( &A.ctrl->scratch_cursor, (unsigned long long)need );
+            if( so + need <= A.scratch_cap )
+            {
+                DSeed* S = (DSeed*)( A.scratch + so );
+                for( int i = 0; i < n; i++ )
+                    S[ i ] = A.seeds[ ri.seed_off + i ];
+                HarmScratch W = harm_scratch_carve( A.scratch + so + copyBytes, (size_t)n );
+                const int qlen = (int)( A.read_off[ read + 1 ] - A.read_off[ read ] );
+                nMax = soc_build( A.I, A.P, S, n, qlen, W.maxima, W.vref );
+                where = so;
+            }
+        }
+        A.soc_scratch[ read ] = where, A.soc_nmax[ read ] = nMax;
+    }
+}
+
+__global__ void __launch_bounds__( MA_SOC_BLOCK, MA_SOC_MINB ) harmonize_kernel( SocHarmArgs A )
+{
+    while( true )
+    {
+        const int read = atomicAdd( &A.ctrl->next_read3, 1 );
+        if( read >= A.n_reads )
+            break;
+        ReadInfo ri = A.info[ read ];
+        ri.n_sets = 0, ri.set_off = 0;
+        const unsigned long long so = A.soc_scratch[ read ];
+        if( ri.n_seeds > 0 && so != ~0ull )
+        {
+            const int n = ri.n_seeds;
+            const size_t copyBytes = ( (size_t)n * sizeof( DSeed ) + 15 ) & ~(size_t)15;
+            const DSeed* S = (const DSeed*)( A.scratch + so );
+            HarmScratch W = harm_scratch_carve( A.scratch + so + copyBytes, (size_t)n );
+            DevSetSink sink;
+            sink.slab = A.set_seeds, sink.cap = A.set_seed_cap, sink.ctrl = A.ctrl, sink.read = read;
+            const int qlen = (int)( A.read_off[ read + 1 ] - A.read_off[ read ] );
+            soc_harm_pops( A.I, A.P, S, n, qlen, A.srand_base + (unsigned int)read, W, sink, A.soc_nmax[ read ] );
+            int ns = sink.count;
+            if( ns > MA_MAX_SETS_PER_READ )
+            { // reported per read (ma_b200_set_params rejects max_num_soc > MA_MAX_SETS_PER_READ, so: not reachable)
+                if( !( ri.status & MA_READ_ESETS ) )
+                    atomicAdd( &A.ctrl->n_failed, 1 );
+                ns = 0, ri.status |= MA_READ_ESETS;
+            }
+            if( ns > 0 )
+            {
+                const long long ho = (long long)atomicAdd( &A.ctrl->set_cursor, (unsigned long long)ns );
+                ri.set_off = (int)ho, ri.n_sets = ns;
+                if( ho + ns <= A.set_cap )
+                    for( int i = 0; i < ns; i++ )
+                    {
+                        SetHeader h;
+                        h.read = read, h.ordinal = i, h.soc_index = sink.soc[ i ], h.n = sink.n[ i ];
+                        h.seed_off = sink.off[ i ], h.task_off = 0, h.n_tasks = 0;
+                        h.win_begin = h.win_end = 0, h.valid = 0, h.pad = 0;
+                        A.sets[ ho + i ] = h;
+                    }
             }
         }
         A.info[ read ] = ri;

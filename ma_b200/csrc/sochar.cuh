@@ -617,12 +617,12 @@ MA_HD inline int apply_filters( const HarmParams& P, DSeed* in, int n )
 }
 
 // Sink: void set( const DSeed* seeds, int n, unsigned soc_index )
+// Harmonization::execute over the SoC queue that soc_build left in W.maxima[0..nMax) (S: the read's seeds as soc_build
+// ordered them): pops, RANSAC / linesweep / filters per strip, the heuristics that end the loop
 template <class Sink>
-MA_HD inline void soc_harm_read( const DevIndex& I, const HarmParams& P, DSeed* S, int n, int qlen,
-                                 unsigned int srand_seed, HarmScratch& W, Sink& sink, int uiMinTriesOutCount )
+MA_HD inline void soc_harm_pops( const DevIndex& I, const HarmParams& P, const DSeed* S, int n, int qlen,
+                                 unsigned int srand_seed, HarmScratch& W, Sink& sink, int nMax )
 {
-    (void)uiMinTriesOutCount;
-    int nMax = soc_build( I, P, S, n, qlen, W.maxima, W.vref );
     auto heapOrder = []( const DSoC& a, const DSoC& b ) { return soc_less( a.o, b.o ); };
     GlibcRand rng;
     rng.seed( srand_seed );
@@ -705,6 +705,16 @@ MA_HD inline void soc_harm_read( const DevIndex& I, const HarmParams& P, DSeed* 
     }
     if( bDoHeuristics )
         sink.pop_back( uiSoCRepeatCounter, uiMinTries ); // for(ui < counter && size > uiMinTries) pop_back()
+}
+
+// StripOfConsiderationSeeds::execute + Harmonization::execute for one read
+template <class Sink>
+MA_HD inline void soc_harm_read( const DevIndex& I, const HarmParams& P, DSeed* S, int n, int qlen,
+                                 unsigned int srand_seed, HarmScratch& W, Sink& sink, int uiMinTriesOutCount )
+{
+    (void)uiMinTriesOutCount;
+    const int nMax = soc_build( I, P, S, n, qlen, W.maxima, W.vref );
+    soc_harm_pops( I, P, S, n, qlen, srand_seed, W, sink, nMax );
 }
 
 } // namespace ma
