@@ -276,10 +276,20 @@ struct NwAssembler
         }
         length += size;
     }
+    // the M run of a CIGAR split into match / missmatch runs (needlemanWunsch.cpp:131-144 appends base by base; k
+    // appends of one type are the same integer additions as one append of k, so equal neighbours are appended together)
     MA_HD void matches( u64 qPos, u64 rPos, unsigned int n )
     {
+        unsigned int runLen = 0;
+        int runType = MT_MATCH;
         for( unsigned int i = 0; i < n; i++ )
-            append( q[ qPos + i ] == refBase( rPos + i ) ? MT_MATCH : MT_MISSMATCH, 1 );
+        {
+            const int t = q[ qPos + i ] == refBase( rPos + i ) ? MT_MATCH : MT_MISSMATCH;
+            if( t != runType && runLen )
+                append( runType, runLen ), runLen = 0;
+            runType = t, runLen++;
+        }
+        append( runType, runLen );
     }
     MA_HD void seed( u64 n )
     {
