@@ -931,6 +931,12 @@ static NwParams make_nw_params( const ma_b200_params& p )
                      p.bandwidth_ext, p.min_bandwidth_gap, p.zdrop, make_score( p ).early_return ? 0 : 1 };
 }
 
+static std::mutex& device_turnstile( int device )
+{
+    static std::mutex m[ 64 ];
+    return m[ device & 63 ];
+}
+
 static void ensure_copy_stream( ma_b200_ctx* ctx )
 {
     if( ctx->copy_stream )
@@ -1761,7 +1767,13 @@ extern "C" int ma_b200_align_batch( ma_b200_ctx* ctx, int64_t n_reads, const uin
         }
         ctx->early_runs = runs, ctx->early_runs_cap = runs ? cap_runs : 0, ctx->early_runs_done = false;
         if( !rc )
+        { // One batch at a time computes on a device: when two host threads keep two batches in flight on sibling
+          // contexts, the kernels of the two would otherwise interleave, both batches would finish together and their
+          // downloads would find the GPU idle. With the turnstile the upload of a batch (enqueued above) and the
+          // download of its records (below) run under the OTHER batch's kernels.
+            std::lock_guard<std::mutex> turn( device_turnstile( ctx->device ) );
             rc = ma_b200_align_run( ctx, MA_B200_STAGE_MAPQ, 0, stats );
+        }
         if( ctx->upload_in_flight )
         { // whatever happened above, nothing of the caller's buffers may still be in flight when this call returns
             cudaStreamSynchronize( ctx->copy_stream );

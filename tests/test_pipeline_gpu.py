@@ -469,3 +469,37 @@ def test_reported_only_output_is_the_mapping_quality_vector(preset, gold_index):
     assert rep == [r for r in full if r[2] >= 0]
     assert st_rep["n_reported"] == len(rep) and st_rep["n_sets"] == st_full["n_sets"]
     assert len(rep) < len(full) if preset == "illumina" else len(rep) <= len(full)  # (illumina drops records, n-best)
+
+
+def test_sibling_context_shares_the_index_two_batches_in_flight(gold_index):
+    """ma_b200_create_sibling: a second context on the device that views the first one's index. Two host threads, one
+    batch each at the same time (what bench.py's e2e figure and maCMD_b200 do): both get the records of a single call;
+    destroying the sibling leaves the parent intact."""
+    import threading
+    reads = PC.read_reads_txt(PC.gold_reads("illumina"))
+    data, off = api.pack_reads(reads)
+    ctx = make_ctx("illumina")
+    ctx.index_upload(gold_index)
+    info, alns, runs, _ = ctx.align_batch(data, off)
+    expect = _records(info, alns, runs, len(reads))
+    sib = ctx.sibling()
+    p = api.preset("illumina")
+    p.srand_base = PC.SRAND
+    sib.set_params(p)
+    got = {}
+
+    def work(name, c):
+        for _ in range(3):
+            i, a, r, _st = c.align_batch(data, off)
+            got[name] = _records(i, a, r, len(reads))
+
+    ts = [threading.Thread(target=work, args=("parent", ctx)), threading.Thread(target=work, args=("sibling", sib))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert got["parent"] == expect and got["sibling"] == expect
+    sib.close()
+    info, alns, runs, _ = ctx.align_batch(data, off)
+    assert _records(info, alns, runs, len(reads)) == expect
+    ctx.close()
