@@ -17,6 +17,7 @@
 #include "fmindex.cuh"
 #include "ksw_types.cuh"
 #include "ksw_qs.cuh"
+#include "ksw_bx.cuh"
 #include <cstdint>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -27,16 +28,6 @@ namespace ma
 __device__ __forceinline__ int w8( int x )
 {
     return (int)(signed char)x;
-}
-
-// aligned band width in cells: n_col_ * 16 (kswcpp_core.h:401-402)
-__host__ __device__ inline int ksw_ncol16( int qlen, int tlen, int w )
-{
-    if( w < 0 )
-        w = tlen > qlen ? tlen : qlen;
-    int n = qlen < tlen ? qlen : tlen;
-    n = n < w + 1 ? n : w + 1;
-    return ( ( n + 15 ) / 16 + 1 ) * 16;
 }
 
 // band limits of anti-diagonal r (kswcpp_core.h:541-548); returns false when out of band
@@ -67,69 +58,6 @@ template <int W> struct KswSmem
     static constexpr int QC = 2 * W <= 1024 ? 2 * W : 1024;
     unsigned char qc[ QC ];
 };
-
-// lane 0 only. Walks the traceback slab (kswcpp_core.h:76-150, is_rot = 1, min_intron_len = 0) and pushes run-length
-// ops in backtrack order into cig[]; returns the number of words or -1 on overflow.
-__device__ inline int ksw_backtrack( const unsigned char* tb, int ncol16, int qlen, int tlen, int w, int i0, int j0,
-                                     unsigned int* cig, int cap )
-{
-    int i = i0, j = j0; // qlen + tlen < 2^31
-    int state = 0, n = 0;
-    unsigned int cur = 0; // current run: len<<4|op, 0 = none
-    auto push = [ & ]( unsigned int op, unsigned int len ) {
-        if( cur != 0 && ( cur & 0xf ) == op )
-            cur += len << 4;
-        else
-        {
-            if( cur != 0 )
-            {
-                if( n < cap )
-                    cig[ n ] = cur;
-                n++;
-            }
-            cur = len << 4 | op;
-        }
-    };
-    while( i >= 0 && j >= 0 )
-    {
-        const int r = i + j;
-        // band limits of row r (kswcpp_core.h:541-548)
-        const int st0 = max( max( 0, r - qlen + 1 ), ( r - w + 1 ) >> 1 );
-        const int en0 = min( min( tlen - 1, r ), ( r + w ) >> 1 );
-        const int off = st0 & ~15, off_end = en0 | 15;
-        int force_state = -1;
-        if( i < off )
-            force_state = 2;
-        if( i > off_end )
-            force_state = 1;
-        unsigned int tmp = force_state < 0 ? tb[ (long long)r * ncol16 + ( i - off ) ] : 0;
-        if( state == 0 )
-            state = tmp & 7;
-        else if( !( tmp >> ( state + 2 ) & 1 ) )
-            state = 0;
-        if( state == 0 )
-            state = tmp & 7;
-        if( force_state >= 0 )
-            state = force_state;
-        if( state == 0 )
-            push( 0, 1 ), --i, --j;
-        else if( state == 1 || state == 3 )
-            push( 2, 1 ), --i;
-        else
-            push( 1, 1 ), --j;
-    }
-    if( i >= 0 )
-        push( 2, (unsigned int)i + 1 );
-    if( j >= 0 )
-        push( 1, (unsigned int)j + 1 );
-    if( cur != 0 )
-    {
-        if( n < cap )
-            cig[ n ] = cur;
-        n++;
-    }
-    return n > cap ? -1 : n;
-}
 
 // One warp, one problem. All lanes return the same KswOut (cigar_off/n_cigar are filled by the caller).
 // tb: per-warp traceback slab of >= (qlen+tlen-1)*ncol16 bytes.
@@ -875,14 +803,17 @@ __device__ __forceinline__ bool ksw_rows_p2x2( const KswScore& P, const SeqAcces
 template <int W> struct KswSmemBytes
 {
     static constexpr bool kPacked = W <= 512;
+    static constexpr bool kBx = W <= 1024; // packed banded exact mode (ksw_bx.cuh): 28 W bytes per warp
     static constexpr size_t kScalar = sizeof( KswSmem<W> );
     static constexpr size_t kP2 = kPacked ? sizeof( KswSmemQ < W <= 512 ? W : 2 > ) : 0;
-    static constexpr size_t value = ( ( kScalar > kP2 ? kScalar : kP2 ) + 15 ) / 16 * 16;
+    static constexpr size_t kB = kBx ? sizeof( KswBxSmem < W <= 1024 ? W : 2 > ) : 0;
+    static constexpr size_t kMax2 = kScalar > kP2 ? kScalar : kP2;
+    static constexpr size_t value = ( ( kMax2 > kB ? kMax2 : kB ) + 15 ) / 16 * 16;
 };
 
 template <int W>
-__device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int tlen, int w, int zdrop, int flag,
-                          bool bEarlyStop, KswSmem<W>& sm, unsigned char* __restrict__ tb, KswOut& ez )
+__device__ void ksw_warp( const KswScore& P, const BxK* bxk, const bool bBx, const SeqAccess& seq, int qlen, int tlen, int w, int zdrop,
+                          int flag, bool bEarlyStop, KswSmem<W>& sm, unsigned char* __restrict__ tb, KswOut& ez )
 {
     const int lane = threadIdx.x & 31;
     ez.max_q = ez.max_t = ez.mqe_t = ez.mte_q = -1;
@@ -916,6 +847,18 @@ __device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int
             ez.score = ez.mqe = ez.mte = (int)0x80000000;
             ez.zdropped = 0, ez.cells = 0;
             __syncwarp( );
+        }
+    }
+    if constexpr( KswSmemBytes<W>::kBx )
+    { // packed banded exact mode: scoring parameters whose int8 arithmetic cannot wrap
+        if( bBx && ksw_bx_params_ok( P ) )
+        {
+            KswBxSmem<W>& sb = reinterpret_cast<KswBxSmem<W>&>( sm );
+            if( bLeft )
+                ksw_bx_rows<W, true>( bxk[ 0 ], P, seq, qlen, tlen, w, zdrop, bEarlyStop, sb, tb, ez );
+            else
+                ksw_bx_rows<W, false>( bxk[ 1 ], P, seq, qlen, tlen, w, zdrop, bEarlyStop, sb, tb, ez );
+            return;
         }
     }
     // stage the query in shared memory when it fits
@@ -955,28 +898,6 @@ __device__ void ksw_warp( const KswScore& P, const SeqAccess& seq, int qlen, int
     }
 }
 
-// decide where the backtrack starts (kswcpp_core.h:796-835); returns false if there is no backtrack
-__device__ __forceinline__ bool ksw_bt_start( KswOut& ez, int qlen, int tlen, int flag, int& i0, int& j0 )
-{
-    if( !ez.zdropped && !( flag & MA_KSW_EXTZ_ONLY ) )
-    {
-        i0 = tlen - 1, j0 = qlen - 1;
-        return true;
-    }
-    if( !ez.zdropped && ( flag & MA_KSW_EXTZ_ONLY ) && ez.mqe > ez.max )
-    {
-        ez.reach_end = 1;
-        i0 = ez.mqe_t, j0 = qlen - 1;
-        return true;
-    }
-    if( ez.max_t >= 0 && ez.max_q >= 0 )
-    {
-        i0 = ez.max_t, j0 = ez.max_q;
-        return true;
-    }
-    return false;
-}
-
 struct KswBatchArgs
 {
     const KswTask* tasks;
@@ -1006,6 +927,8 @@ struct KswBatchArgs
     long long redo_cap;
     int* redo_n;
     QsK qsk[ 2 ]; // packed constants of ksw_qs_kernel: [0] left-aligned, [1] right-aligned
+    BxK bxk[ 2 ]; // ... of ksw_bx_rows
+    int no_bx; // 1: scalar exact mode instead of ksw_bx_rows (measurements)
 };
 
 // window class of ksw_batch_kernel for an aligned band width
@@ -1021,7 +944,9 @@ MA_HD inline int ksw_bin_of( int ncol16 )
 #ifndef MA_KSW_WARPS
 #define MA_KSW_WARPS 8 // warps (DP problems in flight) per CTA
 #endif
-template <int W> __global__ void __launch_bounds__( 32 * MA_KSW_WARPS, MA_KSW_MINB ) ksw_batch_kernel( KswBatchArgs A )
+// (the shared memory of the widest packed class admits one CTA per SM: its register budget is not capped at 128)
+template <int W>
+__global__ void __launch_bounds__( 32 * MA_KSW_WARPS, W == 1024 ? 1 : MA_KSW_MINB ) ksw_batch_kernel( KswBatchArgs A )
 {
     extern __shared__ __align__( 16 ) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1044,7 +969,7 @@ template <int W> __global__ void __launch_bounds__( 32 * MA_KSW_WARPS, MA_KSW_MI
         sa.qbase = A.seq, sa.qoff = T.qoff, sa.qstep = ( T.tag & MA_TASK_QREV ) ? -1 : 1;
         sa.tslab = A.seq, sa.toff = T.toff, sa.tstep = ( T.tag & MA_TASK_TREV ) ? -1 : 1;
         sa.pac = ( T.tag & MA_TASK_TPACK ) ? A.pac : nullptr, sa.fwd_len = A.fwd_len;
-        ksw_warp<W>( A.score, sa, T.qlen, T.tlen, T.w, T.zdrop, T.flag, ( T.tag & MA_TASK_EARLYSTOP ) != 0, sm, tb, ez );
+        ksw_warp<W>( A.score, A.bxk, A.no_bx == 0, sa, T.qlen, T.tlen, T.w, T.zdrop, T.flag, ( T.tag & MA_TASK_EARLYSTOP ) != 0, sm, tb, ez );
         ez.cigar_off = 0;
         int i0 = 0, j0 = 0, n = 0;
         const bool bBt = ( T.qlen > 0 && T.tlen > 0 && !A.score.early_return ) &&

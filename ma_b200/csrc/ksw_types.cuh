@@ -80,4 +80,106 @@ MA_HD inline bool ksw_p2_params_ok( const KswScore& P )
 }
 
 
+// aligned band width in cells: n_col_ * 16 (kswcpp_core.h:401-402)
+MA_HD inline int ksw_ncol16( int qlen, int tlen, int w )
+{
+    if( w < 0 )
+        w = tlen > qlen ? tlen : qlen;
+    int n = qlen < tlen ? qlen : tlen;
+    n = n < w + 1 ? n : w + 1;
+    return ( ( n + 15 ) / 16 + 1 ) * 16;
+}
+
+
+// lane 0 only. Walks the traceback slab (kswcpp_core.h:76-150, is_rot = 1, min_intron_len = 0) and pushes run-length
+// ops in backtrack order into cig[]; returns the number of words or -1 on overflow.
+MA_HD inline int ksw_backtrack( const unsigned char* tb, int ncol16, int qlen, int tlen, int w, int i0, int j0,
+                                     unsigned int* cig, int cap )
+{
+    int i = i0, j = j0; // qlen + tlen < 2^31
+    int state = 0, n = 0;
+    unsigned int cur = 0; // current run: len<<4|op, 0 = none
+    auto push = [ & ]( unsigned int op, unsigned int len ) {
+        if( cur != 0 && ( cur & 0xf ) == op )
+            cur += len << 4;
+        else
+        {
+            if( cur != 0 )
+            {
+                if( n < cap )
+                    cig[ n ] = cur;
+                n++;
+            }
+            cur = len << 4 | op;
+        }
+    };
+    while( i >= 0 && j >= 0 )
+    {
+        const int r = i + j;
+        // band limits of row r (kswcpp_core.h:541-548)
+        int st0 = r - qlen + 1 > 0 ? r - qlen + 1 : 0;
+        if( st0 < ( ( r - w + 1 ) >> 1 ) )
+            st0 = ( r - w + 1 ) >> 1;
+        int en0 = tlen - 1 < r ? tlen - 1 : r;
+        if( en0 > ( ( r + w ) >> 1 ) )
+            en0 = ( r + w ) >> 1;
+        const int off = st0 & ~15, off_end = en0 | 15;
+        int force_state = -1;
+        if( i < off )
+            force_state = 2;
+        if( i > off_end )
+            force_state = 1;
+        unsigned int tmp = force_state < 0 ? tb[ (long long)r * ncol16 + ( i - off ) ] : 0;
+        if( state == 0 )
+            state = tmp & 7;
+        else if( !( tmp >> ( state + 2 ) & 1 ) )
+            state = 0;
+        if( state == 0 )
+            state = tmp & 7;
+        if( force_state >= 0 )
+            state = force_state;
+        if( state == 0 )
+            push( 0, 1 ), --i, --j;
+        else if( state == 1 || state == 3 )
+            push( 2, 1 ), --i;
+        else
+            push( 1, 1 ), --j;
+    }
+    if( i >= 0 )
+        push( 2, (unsigned int)i + 1 );
+    if( j >= 0 )
+        push( 1, (unsigned int)j + 1 );
+    if( cur != 0 )
+    {
+        if( n < cap )
+            cig[ n ] = cur;
+        n++;
+    }
+    return n > cap ? -1 : n;
+}
+
+
+// decide where the backtrack starts (kswcpp_core.h:796-835); returns false if there is no backtrack
+MA_HD inline bool ksw_bt_start( KswOut& ez, int qlen, int tlen, int flag, int& i0, int& j0 )
+{
+    if( !ez.zdropped && !( flag & MA_KSW_EXTZ_ONLY ) )
+    {
+        i0 = tlen - 1, j0 = qlen - 1;
+        return true;
+    }
+    if( !ez.zdropped && ( flag & MA_KSW_EXTZ_ONLY ) && ez.mqe > ez.max )
+    {
+        ez.reach_end = 1;
+        i0 = ez.mqe_t, j0 = qlen - 1;
+        return true;
+    }
+    if( ez.max_t >= 0 && ez.max_q >= 0 )
+    {
+        i0 = ez.max_t, j0 = ez.max_q;
+        return true;
+    }
+    return false;
+}
+
+
 } // namespace ma

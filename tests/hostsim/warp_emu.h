@@ -216,6 +216,10 @@ inline unsigned __vimax3_s16x2( unsigned a, unsigned b, unsigned c )
 {
     return __vmaxs2( __vmaxs2( a, b ), c );
 }
+inline unsigned __vimin3_s16x2( unsigned a, unsigned b, unsigned c )
+{
+    return __vmins2( __vmins2( a, b ), c );
+}
 inline unsigned __viaddmax_s16x2( unsigned a, unsigned b, unsigned c )
 {
     return __vmaxs2( __vadd2( a, b ), c );

@@ -168,3 +168,29 @@ def test_synth_generators_are_deterministic():
     assert np.array_equal(r1, r2) and r1.shape == (50, 150)
     a, b, *_ = synth.simulate_pairs(g1, 20, 150, 5)
     assert a.shape == b.shape == (20, 150)
+
+
+def test_warp_emulated_dp_kernels_match_oracle(tmp_path):
+    """The source of the warp-synchronous DP kernels (ksw_bx.cuh: packed banded exact mode, ksw_qs.cuh: query-stationary
+    register mode) runs unchanged on a lock-step warp emulator (tests/hostsim/warp_emu.h) against the oracle: every
+    kswcpp_extz_t field and the CIGAR for random problems (bands 0..900, N bases, z-drops, score sets whose int8
+    arithmetic wraps in the reference) and for the reference's own golden DP calls of two such score sets (the GPU
+    suite runs all of them, tests/test_ksw_gpu.py)."""
+    d = os.path.join(H.ROOT, "tests", "hostsim")
+    subprocess.check_call(["make", "-s", "-C", d])
+    assert subprocess.call([os.path.join(d, "bx_sim"), "600", "21", "160"]) == 0
+    assert subprocess.call([os.path.join(d, "bx_sim"), "40", "22", "1000"]) == 0
+    assert subprocess.call([os.path.join(d, "qs_sim"), "300", "5"]) == 0
+    for name in ("_swapped", "_large"):  # (a sample of each set: the emulator runs ~10 problems a second)
+        g = np.load(os.path.join(H.GOLDEN, "ksw_golden%s.npz" % name))
+        dd = {"ksw_calls": g["calls"].astype(np.int64), "ksw_seq": g["seq"], "ksw_cigar": g["cigar"]}
+        sc = [int(x) for x in g["score"]] if "score" in g else [2, 4, 4, 2, 24, 1]
+        path = str(tmp_path / ("calls%s.txt" % name))
+        n = 0
+        with open(path, "w") as f:
+            for fl, q, t, c in H.split_ksw_dump(dd):
+                if len(q) and len(t) and n < 90:
+                    f.write("%d %d %d %s %s\n" % (fl["w"], fl["zdrop"], fl["flag"], "".join(map(str, q)), "".join(map(str, t))))
+                    n += 1
+        assert n == 90
+        assert subprocess.call([os.path.join(d, "bx_sim"), "file", path] + [str(x) for x in sc]) == 0, name
