@@ -17,7 +17,7 @@
 #include "fmindex.cuh"
 #include "ksw_types.cuh"
 #include "ksw_qs.cuh"
-#include "ksw_bx.cuh"
+#include "ksw_bn.cuh"
 #include <cstdint>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -378,8 +378,13 @@ __device__ __forceinline__ bool ksw_rows( const KswScore& P, const SeqAccess& se
 // in-band cells matter) in the reference's int16 score mode, with scoring parameters for which the int8 difference
 // arithmetic of the reference can never wrap. For every cell of the recurrence (kswcpp_core.h:640-760)
 //     x' in [-q-e, -e],  u' = z - v >= x >= -Q,  u' <= match + Q   (Q = max(q+e, q2+e2); same for v, y, x2, y2)
-// holds for ANY inputs inside these intervals (z >= a = x + v and z <= match are enforced by the cell itself), so by
-// induction all stored values and all intermediates stay within +-(2Q + match + max(|mismatch|, e2) + max(q, q2)).
+// holds for any inputs inside these intervals as long as the cell's maximum z (>= a = x + v by construction) also is
+// <= match WITHOUT the clip of kswcpp_core.h:702, so by induction all stored values and all intermediates stay within
+// +-(2Q + match + max(|mismatch|, e2) + max(q, q2)). A consistent DP never clips (adding a base to each sequence
+// raises the best score by at most one match); an inconsistent first column does (negative long-gap threshold of
+// swapped pieces with e < e2, tests/golden/ksw_golden_swapped.npz): there x' = a - z - e grows from cell to cell until
+// the reference's int8 wraps. The packed kernels therefore track the largest UNCLIPPED maximum over their in-band cells
+// and hand a problem that ever clipped over to the banded exact mode (ksw_bx.cuh), which wraps like the reference.
 // If that bound is <= 127 (ksw_p2_params_ok) the int8 wrap-around is the identity and small-integer half
 // arithmetic (exact up to 2048) gives the same numbers: HADD2 / HMNMX2 / HSET2 masks work on two cells at once, the
 // six difference arrays and the target / reversed-query codes are kept as halves in shared memory so that one
@@ -466,6 +471,7 @@ template <int W> struct KswSmemQ
 struct P2Cell
 {
     __half2 un, vn, xn, yn, x2n, y2n;
+    __half2 zt; // the five-way maximum before it is clipped at the match score
     unsigned d;
 };
 
@@ -503,6 +509,7 @@ __device__ __forceinline__ P2Cell p2_cell( const P2Const& K, const __half2 xt1, 
         z = __hmax2( z, a2 );
         z = __hmax2( z, b2 );
     }
+    o.zt = z;
     z = __hmin2( z, K.hMatch );
     o.un = __hsub2( z, vt1 ), o.vn = __hsub2( z, ut );
     // x' = max(a - (z - q), 0) - (q + e) = max(a - z - e, -q - e); the continuation flag is a - z > -q
@@ -591,6 +598,7 @@ __device__ __forceinline__ bool ksw_rows_p2x2( const KswScore& P, const SeqAcces
     // H buffers: hin holds the H row of the last finished row; hbest the row of the running maximum (-1: none yet)
     int hin = 0, hbest = -1;
     int bR = 0, bSt0 = 0, bEn0 = 0;
+    __half2 zmx = u2h( 0xFBFFFBFFu ); // largest unclipped maximum over the in-band cells (-65504: none yet)
     const int T0 = scM * qlen;
     unsigned char* rowBase = tb; // tb + r * ncol16
     bool stop = false;
@@ -691,6 +699,7 @@ __device__ __forceinline__ bool ksw_rows_p2x2( const KswScore& P, const SeqAcces
             const unsigned hmA = sel2( vmA, hA, 0x80008000u );
             mA = __vmaxs2( mA, hmA );
             hbA = __vmaxs2( hbA, __vadd2( hmA, termA & vmA ) );
+            zmx = __hmax2( zmx, u2h( sel2( vmA, h2u( A.zt ), 0xFBFFFBFFu ) ) );
             if( deA >= 0 )
             {
                 pH1[ kk ] = hA;
@@ -725,6 +734,7 @@ __device__ __forceinline__ bool ksw_rows_p2x2( const KswScore& P, const SeqAcces
             const unsigned hmB = sel2( vmB, hB, 0x80008000u );
             mB = __vmaxs2( mB, hmB );
             hbB = __vmaxs2( hbB, __vadd2( hmB, __vsub2( termA, scM2 ) & vmB ) );
+            zmx = __hmax2( zmx, u2h( sel2( vmB, h2u( B.zt ), 0xFBFFFBFFu ) ) );
             termA = __vadd2( termA, termStep );
             if( has2 )
             {
@@ -796,7 +806,11 @@ __device__ __forceinline__ bool ksw_rows_p2x2( const KswScore& P, const SeqAcces
     }
     ez.cells = cells;
     __syncwarp( );
-    return true;
+    // The no-wrap argument above needs z >= a, b, a2, b2 AND z <= match in every cell: true as long as the clip at the
+    // match score (kswcpp_core.h:702) never changed a maximum. A consistent DP never clips; an inconsistent border
+    // (negative long-gap threshold of swapped pieces) does, and the reference's int8 values may then wrap: such a
+    // problem is redone in the banded exact mode (ksw_bx.cuh), whose arithmetic wraps like the reference's.
+    return __reduce_max_sync( FULL, (int)fmaxf( __low2float( zmx ), __high2float( zmx ) ) ) <= scM;
 }
 
 // bytes of shared memory per warp: the scalar window and, for the narrow bins, the packed one share the space
@@ -812,7 +826,7 @@ template <int W> struct KswSmemBytes
 };
 
 template <int W>
-__device__ void ksw_warp( const KswScore& P, const BxK* bxk, const bool bBx, const SeqAccess& seq, int qlen, int tlen, int w, int zdrop,
+__device__ void ksw_warp( const KswScore& P, const BxK* bxk, const bool bBx, const bool bP2, const bool bBn, const SeqAccess& seq, int qlen, int tlen, int w, int zdrop,
                           int flag, bool bEarlyStop, KswSmem<W>& sm, unsigned char* __restrict__ tb, KswOut& ez )
 {
     const int lane = threadIdx.x & 31;
@@ -834,7 +848,7 @@ __device__ void ksw_warp( const KswScore& P, const BxK* bxk, const bool bBx, con
     { // packed fast path: early-stop extensions in int16 score mode whose int8 arithmetic cannot wrap
         const int iSize = qlen > tlen ? qlen : tlen;
         const bool is16 = !( (long long)iSize * P.min16 < -32768 || (long long)iSize * P.match > 32767 );
-        if( bEarlyStop && bInBandPays && is16 && qlen + 4 <= W && ( qlen < tlen ? qlen : tlen ) + 40 <= W &&
+        if( bP2 && bEarlyStop && bInBandPays && is16 && qlen + 4 <= W && ( qlen < tlen ? qlen : tlen ) + 40 <= W &&
             ksw_p2_params_ok( P ) )
         {
             KswSmemQ<W>& sp = reinterpret_cast<KswSmemQ<W>&>( sm );
@@ -853,6 +867,34 @@ __device__ void ksw_warp( const KswScore& P, const BxK* bxk, const bool bBx, con
     { // packed banded exact mode: scoring parameters whose int8 arithmetic cannot wrap
         if( bBx && ksw_bx_params_ok( P ) )
         {
+            if constexpr( W <= 256 )
+            { // register-resident narrow-band kernel (ksw_bn.cuh): aligned ranges of at most three 64-column chunks
+                static_assert( sizeof( KswBnSmem ) <= KswSmemBytes<W>::value, "narrow-band scratch" );
+                const int nch = ( ksw_ncol16( qlen, tlen, w ) + 63 ) / 64;
+                if( bBn && nch <= MA_BN_MAXC )
+                {
+                    KswBnSmem& sn = reinterpret_cast<KswBnSmem&>( sm );
+#define MA_BN_CALL( N )                                                                                                \
+    if( bLeft )                                                                                                        \
+        ksw_bn_rows<N, true>( bxk[ 0 ], P, seq, qlen, tlen, w, zdrop, bEarlyStop, sn, tb, ez );                        \
+    else                                                                                                               \
+        ksw_bn_rows<N, false>( bxk[ 1 ], P, seq, qlen, tlen, w, zdrop, bEarlyStop, sn, tb, ez );
+                    if( W == 128 && nch == 1 )
+                    {
+                        MA_BN_CALL( 1 )
+                    }
+                    else if( nch <= 2 )
+                    {
+                        MA_BN_CALL( 2 )
+                    }
+                    else
+                    {
+                        MA_BN_CALL( 3 )
+                    }
+#undef MA_BN_CALL
+                    return;
+                }
+            }
             KswBxSmem<W>& sb = reinterpret_cast<KswBxSmem<W>&>( sm );
             if( bLeft )
                 ksw_bx_rows<W, true>( bxk[ 0 ], P, seq, qlen, tlen, w, zdrop, bEarlyStop, sb, tb, ez );
@@ -928,7 +970,7 @@ struct KswBatchArgs
     int* redo_n;
     QsK qsk[ 2 ]; // packed constants of ksw_qs_kernel: [0] left-aligned, [1] right-aligned
     BxK bxk[ 2 ]; // ... of ksw_bx_rows
-    int no_bx; // 1: scalar exact mode instead of ksw_bx_rows (measurements)
+    int no_bx; // bit 0: scalar exact mode instead of ksw_bx_rows, bit 1: no ksw_rows_p2x2, bit 2: no ksw_bn_rows (measurements)
 };
 
 // window class of ksw_batch_kernel for an aligned band width
@@ -969,7 +1011,7 @@ __global__ void __launch_bounds__( 32 * MA_KSW_WARPS, W == 1024 ? 1 : MA_KSW_MIN
         sa.qbase = A.seq, sa.qoff = T.qoff, sa.qstep = ( T.tag & MA_TASK_QREV ) ? -1 : 1;
         sa.tslab = A.seq, sa.toff = T.toff, sa.tstep = ( T.tag & MA_TASK_TREV ) ? -1 : 1;
         sa.pac = ( T.tag & MA_TASK_TPACK ) ? A.pac : nullptr, sa.fwd_len = A.fwd_len;
-        ksw_warp<W>( A.score, A.bxk, A.no_bx == 0, sa, T.qlen, T.tlen, T.w, T.zdrop, T.flag, ( T.tag & MA_TASK_EARLYSTOP ) != 0, sm, tb, ez );
+        ksw_warp<W>( A.score, A.bxk, ( A.no_bx & 1 ) == 0, ( A.no_bx & 2 ) == 0, ( A.no_bx & 4 ) == 0, sa, T.qlen, T.tlen, T.w, T.zdrop, T.flag, ( T.tag & MA_TASK_EARLYSTOP ) != 0, sm, tb, ez );
         ez.cigar_off = 0;
         int i0 = 0, j0 = 0, n = 0;
         const bool bBt = ( T.qlen > 0 && T.tlen > 0 && !A.score.early_return ) &&

@@ -218,7 +218,7 @@ QS_DEV int ksw_qs_argmax( const short* Hs, const int R, const int st0, const int
 template <bool LEFT, bool FRONT>
 QS_DEV unsigned ksw_qs_cell( const QsK& K, unsigned& U, unsigned& V, unsigned& X, unsigned& Y, unsigned& X2,
                              unsigned& Y2, unsigned& H8, const unsigned nbU, const unsigned nbY, const unsigned nbY2,
-                             const unsigned z0, const unsigned ent )
+                             const unsigned z0, const unsigned ent, unsigned& zmx )
 {
     const unsigned a = __vadd2( X, V ), b = __vadd2( nbY, nbU ), a2 = __vadd2( X2, V ), b2 = __vadd2( nbY2, nbU );
     unsigned d, zc;
@@ -227,12 +227,15 @@ QS_DEV unsigned ksw_qs_cell( const QsK& K, unsigned& U, unsigned& V, unsigned& X
         const unsigned zt = __vimax3_s16x2( __vimax3_s16x2( z0, a, b ), a2, b2 );
         d = zt & 0x00070007u;
         zc = __vmins2( zt, K.cap );
+        zmx = __vmaxs2( zmx, zt );
     }
     else
     { // right-aligned: ties go to the later candidate, state 4 is never recorded (kswcpp_core.h:693-699)
         const unsigned z4 = __vmaxs2( __vimax3_s16x2( z0, a, b ), a2 );
         d = z4 & 0x00070007u;
-        zc = __vmins2( __vmaxs2( z4, b2 ), K.cap );
+        const unsigned zt = __vmaxs2( z4, b2 );
+        zc = __vmins2( zt, K.cap );
+        zmx = __vmaxs2( zmx, zt );
     }
     // differences as sums of complements (a - b = a + ~b + 1 per half; there is no packed subtract):
     // z1 = z + 1 (tag bits cleared), ~z1 = -z - 2
@@ -272,7 +275,8 @@ template <int NB, bool LEFT, bool STEADY>
 QS_DEV void ksw_qs_row( const QsK& K, const int r, const int lane, const int srcLane, const unsigned fcr,
                         const unsigned* __restrict__ tp, const unsigned nivec0, unsigned ( &U )[ NB ], unsigned ( &V )[ NB ],
                         unsigned ( &X )[ NB ], unsigned ( &Y )[ NB ], unsigned ( &X2 )[ NB ], unsigned ( &Y2 )[ NB ],
-                        unsigned ( &H8 )[ NB ], const unsigned ( &QP )[ NB ], unsigned ( &tbv )[ NB ], unsigned& mrow )
+                        unsigned ( &H8 )[ NB ], const unsigned ( &QP )[ NB ], unsigned ( &tbv )[ NB ], unsigned& mrow,
+                        unsigned& zmx )
 {
     const unsigned FULL = 0xffffffffu;
     const int nbAct = STEADY ? NB : ( ( r >> 6 ) + 1 < NB ? ( r >> 6 ) + 1 : NB );
@@ -303,13 +307,13 @@ QS_DEV void ksw_qs_row( const QsK& K, const int r, const int lane, const int src
             const unsigned tv = __vadd2( ksw_qs_pk( r - 64 * k ), nivec0 ); // r - i per half
             const unsigned ent = ~qs_prmt( tv, 0, 0xBB99 ); // halves with i <= r
             tbv[ k ] = ksw_qs_cell<LEFT, true>( K, U[ k ], V[ k ], X[ k ], Y[ k ], X2[ k ], Y2[ k ], H8[ k ], nbU, nbY, nbY2,
-                                                z0, ent );
+                                                z0, ent, zmx );
             mrow = __vmaxs2( mrow, ( H8[ k ] & ent ) | ( ksw_qs_pk( -2 * MA_QS_NEG ) & ~ent ) );
         }
         else
         {
             tbv[ k ] = ksw_qs_cell<LEFT, false>( K, U[ k ], V[ k ], X[ k ], Y[ k ], X2[ k ], Y2[ k ], H8[ k ], nbU, nbY, nbY2,
-                                                 z0, 0u );
+                                                 z0, 0u, zmx );
             mrow = __vmaxs2( mrow, H8[ k ] );
         }
     }
@@ -366,6 +370,7 @@ QS_DEV bool ksw_qs_rows( const QsK& K, const KswScore& P, const SeqAccess& seq, 
     int staged = 0;
     int lastc = 0; // code of the target base before the next staging chunk
     int ezmax8 = 0, bR = -1;
+    unsigned zmx = ksw_qs_pk( -2 * MA_QS_NEG ); // the largest five-way maximum BEFORE it is clipped at the match score
     bool stop = false;
     const int srcLane = ( lane + 31 ) & 31;
     unsigned* tw = reinterpret_cast<unsigned*>( tb ) + lane; // traceback words of the current pass
@@ -400,23 +405,23 @@ QS_DEV bool ksw_qs_rows( const QsK& K, const KswScore& P, const SeqAccess& seq, 
         const bool bBound = has2 && rl >= qlen;
         if( r >= 64 * NB )
         {
-            ksw_qs_row<NB, LEFT, true>( K, r, lane, srcLane, fcA, sm.tp, nivec0, U, V, X, Y, X2, Y2, H8, QP, tbA, mrowA );
+            ksw_qs_row<NB, LEFT, true>( K, r, lane, srcLane, fcA, sm.tp, nivec0, U, V, X, Y, X2, Y2, H8, QP, tbA, mrowA, zmx );
 #pragma unroll
             for( int k = 0; k < NB; k++ )
                 HA[ k ] = H8[ k ];
             if( has2 )
                 ksw_qs_row<NB, LEFT, true>( K, r + 1, lane, srcLane, fcB, sm.tp, nivec0, U, V, X, Y, X2, Y2, H8, QP, tbB,
-                                            mrowB );
+                                            mrowB, zmx );
         }
         else
         {
-            ksw_qs_row<NB, LEFT, false>( K, r, lane, srcLane, fcA, sm.tp, nivec0, U, V, X, Y, X2, Y2, H8, QP, tbA, mrowA );
+            ksw_qs_row<NB, LEFT, false>( K, r, lane, srcLane, fcA, sm.tp, nivec0, U, V, X, Y, X2, Y2, H8, QP, tbA, mrowA, zmx );
 #pragma unroll
             for( int k = 0; k < NB; k++ )
                 HA[ k ] = H8[ k ];
             if( has2 )
                 ksw_qs_row<NB, LEFT, false>( K, r + 1, lane, srcLane, fcB, sm.tp, nivec0, U, V, X, Y, X2, Y2, H8, QP, tbB,
-                                             mrowB );
+                                             mrowB, zmx );
         }
         if( !has2 )
         {
@@ -506,7 +511,11 @@ QS_DEV bool ksw_qs_rows( const QsK& K, const KswScore& P, const SeqAccess& seq, 
     }
     ez.cells = cells;
     __syncwarp( );
-    return true;
+    // The no-wrap argument of this kernel (ksw.cuh, packed path) needs z >= a, b, a2, b2 AND z <= match in every cell,
+    // which holds as long as the clip at the match score (kswcpp_core.h:702) never changed a maximum: a consistent DP
+    // never clips, an inconsistent border (negative long-gap threshold of swapped pieces) does, and then the
+    // reference's int8 values can grow until they wrap. Such a problem is handed over.
+    return __reduce_max_sync( FULL, qs_hmax( zmx ) ) <= 8 * scM + 7;
 }
 
 // lane 0 only: the walk of kswcpp_core.h:76-150 over this kernel's traceback layout; ops in backtrack order

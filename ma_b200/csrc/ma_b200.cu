@@ -421,9 +421,10 @@ static bool use_tiny( )
     static const bool b = !( getenv( "MA_B200_NO_TINY" ) && atoi( getenv( "MA_B200_NO_TINY" ) ) != 0 );
     return b;
 }
-static bool use_bx( )
-{ // packed banded exact mode (ksw_bx.cuh); MA_B200_NO_BX=1 runs the scalar exact mode instead (A/B measurements)
-    static const bool b = !( getenv( "MA_B200_NO_BX" ) && atoi( getenv( "MA_B200_NO_BX" ) ) != 0 );
+static int no_bx_bits( )
+{ // A/B measurements: MA_B200_NO_BX=1 runs the scalar exact mode instead of the packed banded one (ksw_bx.cuh),
+  // MA_B200_NO_BX=2 skips the half2 two-row mode (ksw_rows_p2x2), 4 the register-resident narrow-band mode (ksw_bn.cuh); bits add
+    static const int b = getenv( "MA_B200_NO_BX" ) ? atoi( getenv( "MA_B200_NO_BX" ) ) : 0;
     return b;
 }
 static bool use_qs( )
@@ -603,7 +604,7 @@ static int ksw_run_once( ma_b200_ctx* ctx )
     A.score = score;
     A.qsk[ 0 ] = ksw_qs_make_k( score, true ), A.qsk[ 1 ] = ksw_qs_make_k( score, false );
     A.bxk[ 0 ] = ksw_bx_make_k( score, true ), A.bxk[ 1 ] = ksw_bx_make_k( score, false );
-    A.no_bx = use_bx( ) ? 0 : 1;
+    A.no_bx = no_bx_bits( );
     A.redo_count = nullptr, A.redo_tb = nullptr, A.redo_cig = nullptr;
     A.redo_n = ctx->ksw_redo.p, A.redo_order = ctx->ksw_redo.p + 1, A.redo_cap = ctx->ksw_n;
     // two phases: ksw_qs_kernel first (it may hand problems over), then ksw_batch_kernel. The per-warp scratch is sized
@@ -1119,7 +1120,7 @@ static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
         A.score = score;
         A.qsk[ 0 ] = ksw_qs_make_k( score, true ), A.qsk[ 1 ] = ksw_qs_make_k( score, false );
     A.bxk[ 0 ] = ksw_bx_make_k( score, true ), A.bxk[ 1 ] = ksw_bx_make_k( score, false );
-    A.no_bx = use_bx( ) ? 0 : 1;
+    A.no_bx = no_bx_bits( );
         A.redo_count = ctx->ctrl.p->bin_count, A.redo_tb = ctx->ctrl.p->bin_tb, A.redo_cig = ctx->ctrl.p->bin_cig;
         A.redo_order = ctx->bin_order.p, A.redo_cap = task_cap, A.redo_n = nullptr;
         for( int phase = 0; phase < 2; phase++ )

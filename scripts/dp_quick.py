@@ -23,7 +23,11 @@ for name, pairs in [("illumina_ext_50x1000_w512", illumina_like(100000)),
                     ("ext_3000_w256", dpgen.sweep_pairs(300, 3000, 256, dpgen.EXT, 0.05, 4) * 10),
                     ("global_1000_w128", dpgen.sweep_pairs(600, 1000, 128, dpgen.GLOBAL, 0.05, 5) * 10),
                     ("ext_10000_w512", dpgen.sweep_pairs(60, 10000, 512, dpgen.EXT, 0.12, 6) * 20),
-                    ("ext_20000_w32", dpgen.sweep_pairs(60, 20000, 32, dpgen.EXT_RIGHT, 0.05, 7) * 20)]:
+                    ("ext_20000_w32", dpgen.sweep_pairs(60, 20000, 32, dpgen.EXT_RIGHT, 0.05, 7) * 20),
+                    ("ext_3000_w16", dpgen.sweep_pairs(500, 3000, 16, dpgen.EXT, 0.05, 8) * 20),
+                    ("global_3000_w32", dpgen.sweep_pairs(500, 3000, 32, dpgen.GLOBAL, 0.05, 9) * 20),
+                    ("ext_3000_w64", dpgen.sweep_pairs(500, 3000, 64, dpgen.EXT_RIGHT, 0.05, 10) * 20),
+                    ("global_3000_w128", dpgen.sweep_pairs(400, 3000, 128, dpgen.GLOBAL, 0.05, 11) * 20)]:
     tasks, seq = api.pack_ksw_tasks(pairs)
     ctx.ksw_upload(tasks, seq)
     ctx.ksw_run()

@@ -3,8 +3,8 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_ksw_gpu.py tests/test_pipeline_gpu.py -x -q -m gpu 2>&1 | tail -6 | cut -c1-400
-echo "--- dp_quick bx"; timeout 300 python scripts/dp_quick.py 2>&1 | tail -6
-if [ -n "$BX_AB" ]; then echo "--- dp_quick scalar"; MA_B200_NO_BX=1 timeout 300 python scripts/dp_quick.py 2>&1 | tail -6; fi
+echo "--- dp_quick bx"; timeout 300 python scripts/dp_quick.py 2>&1 | tail -10
+if [ -n "$BX_AB" ]; then echo "--- dp_quick NO_BX=$BX_AB"; MA_B200_NO_BX=$BX_AB timeout 300 python scripts/dp_quick.py 2>&1 | tail -10; fi
 for m in 0 $BX_AB; do
   echo "--- pacbio 3000 reads NO_BX=$m"
   MA_B200_NO_BX=$m MA_B200_DP_BINS=1 timeout 600 python bench.py --config 3 --long-reads 3000 --long-batch 3000 --steps 2 --warmup 1 --no-cpu-baseline 2>gpurun_out/bx_pacbio_err_$m.txt | tail -1 > gpurun_out/bx_pacbio_$m.json

@@ -3,7 +3,7 @@
 //   bx_sim <n_problems> <seed> [maxlen]     exit code 0 = all identical
 #include "warp_emu.h"
 #define MA_WARP_EMU 1
-#include "../../ma_b200/csrc/ksw_bx.cuh"
+#include "../../ma_b200/csrc/ksw_bn.cuh"
 #include "../../oracle/oracle.h"
 #include <algorithm>
 #include <random>
@@ -32,6 +32,8 @@ static KswScore makeScore( int match, int mismatch, int gap, int extend, int gap
     return s;
 }
 
+static bool g_bNarrow = false; // BX_NARROW=1: problems of at most three chunks run ksw_bn_rows
+
 struct Result
 {
     bool ok;
@@ -54,7 +56,10 @@ static Result runBx( const KswScore& P, const std::vector<uint8_t>& q, const std
     std::vector<unsigned char> tb( (size_t)( qlen + tlen ) * nc + 64, 0xEE );
     std::vector<unsigned> cs( (size_t)qlen + tlen + 8 );
     static KswBxSmem<W> sm;
+    static KswBnSmem smn;
     memset( &sm, 0xA5, sizeof( sm ) );
+    memset( &smn, 0xA5, sizeof( smn ) );
+    const int nch = ( nc + 63 ) / 64; // register-resident narrow-band kernel (ksw_bn.cuh) where it applies
     KswOut outs[ 32 ];
     bool ok[ 32 ];
     int ncig = 0;
@@ -65,7 +70,14 @@ static Result runBx( const KswScore& P, const std::vector<uint8_t>& q, const std
         ez.score = ez.mqe = ez.mte = (int)0x80000000;
         ez.n_cigar = 0, ez.zdropped = 0, ez.reach_end = 0, ez.status = 0, ez.cells = 0, ez.cigar_off = 0;
         const BxK K = ksw_bx_make_k( P, LEFT );
-        ksw_bx_rows<W, LEFT>( K, P, sa, qlen, tlen, w, zdrop, bEarly, sm, tb.data( ), ez );
+        if( g_bNarrow && nch == 1 )
+            ksw_bn_rows<1, LEFT>( K, P, sa, qlen, tlen, w, zdrop, bEarly, smn, tb.data( ), ez );
+        else if( g_bNarrow && nch == 2 )
+            ksw_bn_rows<2, LEFT>( K, P, sa, qlen, tlen, w, zdrop, bEarly, smn, tb.data( ), ez );
+        else if( g_bNarrow && nch == 3 )
+            ksw_bn_rows<3, LEFT>( K, P, sa, qlen, tlen, w, zdrop, bEarly, smn, tb.data( ), ez );
+        else
+            ksw_bx_rows<W, LEFT>( K, P, sa, qlen, tlen, w, zdrop, bEarly, sm, tb.data( ), ez );
         const bool b = true;
         const int lane = warpemu::lane( );
         ok[ lane ] = b;
@@ -187,6 +199,7 @@ static int runFile( int argc, char** argv )
 
 int main( int argc, char** argv )
 {
+    g_bNarrow = getenv( "BX_NARROW" ) != nullptr;
     if( argc > 2 && std::string( argv[ 1 ] ) == "file" )
         return runFile( argc, argv );
     const int n = argc > 1 ? atoi( argv[ 1 ] ) : 200;

@@ -171,15 +171,18 @@ def test_synth_generators_are_deterministic():
 
 
 def test_warp_emulated_dp_kernels_match_oracle(tmp_path):
-    """The source of the warp-synchronous DP kernels (ksw_bx.cuh: packed banded exact mode, ksw_qs.cuh: query-stationary
-    register mode) runs unchanged on a lock-step warp emulator (tests/hostsim/warp_emu.h) against the oracle: every
+    """The source of the warp-synchronous DP kernels (ksw_bx.cuh: packed banded exact mode, ksw_bn.cuh: its register-resident
+    form for narrow bands, ksw_qs.cuh: query-stationary register mode) runs unchanged on a lock-step warp emulator (tests/hostsim/warp_emu.h) against the oracle: every
     kswcpp_extz_t field and the CIGAR for random problems (bands 0..900, N bases, z-drops, score sets whose int8
     arithmetic wraps in the reference) and for the reference's own golden DP calls of two such score sets (the GPU
     suite runs all of them, tests/test_ksw_gpu.py)."""
     d = os.path.join(H.ROOT, "tests", "hostsim")
     subprocess.check_call(["make", "-s", "-C", d])
-    assert subprocess.call([os.path.join(d, "bx_sim"), "600", "21", "160"]) == 0
-    assert subprocess.call([os.path.join(d, "bx_sim"), "40", "22", "1000"]) == 0
+    assert subprocess.call([os.path.join(d, "bx_sim"), "500", "21", "160"]) == 0
+    assert subprocess.call([os.path.join(d, "bx_sim"), "30", "22", "1000"]) == 0
+    narrow = dict(os.environ, BX_NARROW="1")  # ksw_bn.cuh (register-resident narrow bands) where it applies
+    assert subprocess.call([os.path.join(d, "bx_sim"), "500", "23", "200"], env=narrow) == 0
+    assert subprocess.call([os.path.join(d, "bx_sim"), "40", "24", "1500"], env=narrow) == 0
     assert subprocess.call([os.path.join(d, "qs_sim"), "300", "5"]) == 0
     for name in ("_swapped", "_large"):  # (a sample of each set: the emulator runs ~10 problems a second)
         g = np.load(os.path.join(H.GOLDEN, "ksw_golden%s.npz" % name))
