@@ -236,11 +236,16 @@ QS_DEV void ksw_bn_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
                 *reinterpret_cast<unsigned short*>( rowp + t0 ) = (unsigned short)__byte_perm( C.tbyte, 0, 0x4420 );
             }
         }
-        const int Hen0 = colval( H0, H1, en0, base );
         // the row maximum is the exact maximum of the row (only its POSITION is lane-blocked in the reference)
         const int max_H = __reduce_max_sync( FULL, m );
-        if( en0 == tlen - 1 && Hen0 > ez.mte )
-            ez.mte = Hen0, ez.mte_q = r - en; // sic: the aligned en
+        if( en0 == tlen - 1 )
+        { // (H[en0] is only consumed in the last target column: mte, and score in the last row)
+            const int Hen0 = colval( H0, H1, en0, base );
+            if( Hen0 > ez.mte )
+                ez.mte = Hen0, ez.mte_q = r - en; // sic: the aligned en
+            if( r == nrows - 1 )
+                ez.score = Hen0;
+        }
         if( r - st0 == qlen - 1 )
         {
             const int Hst0 = colval( H0, H1, st0, base );
@@ -272,8 +277,6 @@ QS_DEV void ksw_bn_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
                 }
             }
         }
-        if( r == nrows - 1 && en0 == tlen - 1 )
-            ez.score = Hen0;
         if( bEarlyStop )
         { // see ksw.cuh, ksw_rows
             const int B = __reduce_max_sync( FULL, hb );
