@@ -813,14 +813,37 @@ __device__ __forceinline__ bool ksw_rows_p2x2( const KswScore& P, const SeqAcces
     return __reduce_max_sync( FULL, (int)fmaxf( __low2float( zmx ), __high2float( zmx ) ) ) <= scM;
 }
 
+#ifndef MA_KSW_MINB
+#define MA_KSW_MINB 2
+#endif
+#ifndef MA_KSW_WARPS
+#define MA_KSW_WARPS 8 // warps (DP problems in flight) per CTA
+#endif
+// Window classes of ksw_batch_kernel: W is the (power-of-two) window of the scalar modes and the name of the class. The
+// class "1024" takes aligned band widths up to MA_KSW_CAP1024 - 48 = 592 columns — the band of 512 of the presets'
+// end extensions and of the configs[4] sweep needs 544 — so that the packed banded mode runs it with a window of 640
+// columns (17.5 KB of shared memory per warp: 12 warps per SM as two CTAs of six warps; a window of 1024 columns left
+// 8); wider bands go to the 2048 class.
+#define MA_KSW_CAP1024 640
+MA_HD inline int ksw_class_cap( int W )
+{
+    return W == 1024 ? MA_KSW_CAP1024 : W;
+}
+template <int W> struct KswClass
+{
+    static constexpr int WB = W == 1024 ? MA_KSW_CAP1024 : W; // window of ksw_bx_rows
+    static constexpr int WARPS = W == 1024 ? 6 : MA_KSW_WARPS; // warps (DP problems in flight) per CTA
+    static constexpr int MINB = MA_KSW_MINB;
+};
+
 // bytes of shared memory per warp: the scalar window and, for the narrow bins, the packed one share the space
 template <int W> struct KswSmemBytes
 {
     static constexpr bool kPacked = W <= 512;
-    static constexpr bool kBx = W <= 1024; // packed banded exact mode (ksw_bx.cuh): 28 W bytes per warp
+    static constexpr bool kBx = W <= 1024; // packed banded exact mode (ksw_bx.cuh): 28 bytes per window column and warp
     static constexpr size_t kScalar = sizeof( KswSmem<W> );
     static constexpr size_t kP2 = kPacked ? sizeof( KswSmemQ < W <= 512 ? W : 2 > ) : 0;
-    static constexpr size_t kB = kBx ? sizeof( KswBxSmem < W <= 1024 ? W : 2 > ) : 0;
+    static constexpr size_t kB = kBx ? sizeof( KswBxSmem < W <= 1024 ? KswClass<W>::WB : 2 > ) : 0;
     static constexpr size_t kMax2 = kScalar > kP2 ? kScalar : kP2;
     static constexpr size_t value = ( ( kMax2 > kB ? kMax2 : kB ) + 15 ) / 16 * 16;
 };
@@ -895,11 +918,12 @@ __device__ void ksw_warp( const KswScore& P, const BxK* bxk, const bool bBx, con
                     return;
                 }
             }
-            KswBxSmem<W>& sb = reinterpret_cast<KswBxSmem<W>&>( sm );
+            constexpr int WB = KswClass<W>::WB;
+            KswBxSmem<WB>& sb = reinterpret_cast<KswBxSmem<WB>&>( sm );
             if( bLeft )
-                ksw_bx_rows<W, true>( bxk[ 0 ], P, seq, qlen, tlen, w, zdrop, bEarlyStop, sb, tb, ez );
+                ksw_bx_rows<WB, true>( bxk[ 0 ], P, seq, qlen, tlen, w, zdrop, bEarlyStop, sb, tb, ez );
             else
-                ksw_bx_rows<W, false>( bxk[ 1 ], P, seq, qlen, tlen, w, zdrop, bEarlyStop, sb, tb, ez );
+                ksw_bx_rows<WB, false>( bxk[ 1 ], P, seq, qlen, tlen, w, zdrop, bEarlyStop, sb, tb, ez );
             return;
         }
     }
@@ -977,18 +1001,11 @@ struct KswBatchArgs
 MA_HD inline int ksw_bin_of( int ncol16 )
 {
     const int need = ncol16 + 48;
-    return need <= 128 ? 0 : need <= 256 ? 1 : need <= 512 ? 2 : need <= 1024 ? 3 : need <= 2048 ? 4 : 5;
+    return need <= 128 ? 0 : need <= 256 ? 1 : need <= 512 ? 2 : need <= MA_KSW_CAP1024 ? 3 : need <= 2048 ? 4 : 5;
 }
 
-#ifndef MA_KSW_MINB
-#define MA_KSW_MINB 2
-#endif
-#ifndef MA_KSW_WARPS
-#define MA_KSW_WARPS 8 // warps (DP problems in flight) per CTA
-#endif
-// (the shared memory of the widest packed class admits one CTA per SM: its register budget is not capped at 128)
 template <int W>
-__global__ void __launch_bounds__( 32 * MA_KSW_WARPS, W == 1024 ? 1 : MA_KSW_MINB ) ksw_batch_kernel( KswBatchArgs A )
+__global__ void __launch_bounds__( 32 * KswClass<W>::WARPS, KswClass<W>::MINB ) ksw_batch_kernel( KswBatchArgs A )
 {
     extern __shared__ __align__( 16 ) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

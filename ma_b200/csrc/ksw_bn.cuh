@@ -263,9 +263,9 @@ QS_DEV void ksw_bn_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
         {
             int bt = -1, bq = -1;
             if( bR >= 0 )
-                bt = ksw_bx_argmax( sm.HBS, 255, bSt0, bEn0, lane, SMASK ), bq = bR - bt;
+                bt = ksw_bx_argmax<256>( sm.HBS, bSt0, bEn0, lane, SMASK ), bq = bR - bt;
             spill( sm.HS );
-            const int max_t = ksw_bx_argmax( sm.HS, 255, st0, en0, lane, SMASK );
+            const int max_t = ksw_bx_argmax<256>( sm.HS, st0, en0, lane, SMASK );
             if( max_t >= bt && r - max_t >= bq )
             {
                 const int tl = max_t - bt, ql = ( r - max_t ) - bq;
@@ -293,7 +293,7 @@ QS_DEV void ksw_bn_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
         }
     }
     if( bR >= 0 )
-        ez.max_t = ksw_bx_argmax( sm.HBS, 255, bSt0, bEn0, lane, SMASK ), ez.max_q = bR - ez.max_t;
+        ez.max_t = ksw_bx_argmax<256>( sm.HBS, bSt0, bEn0, lane, SMASK ), ez.max_q = bR - ez.max_t;
     ez.cells = cells;
     __syncwarp( );
 }

@@ -96,6 +96,17 @@ MA_HD inline BxK ksw_bx_make_k( const KswScore& P, bool bLeft )
     return K;
 }
 
+// index of column x >= 0 in a circular window of W columns (W need not be a power of two: the band-512 class uses 640)
+template <int W> QS_DEV int bx_wc( const int x )
+{
+    return ( W & ( W - 1 ) ) == 0 ? ( x & ( W - 1 ) ) : (int)( (unsigned)x % (unsigned)W );
+}
+// word index of query pair k (k >= -W) in the query window of W / 2 words
+template <int W> QS_DEV int bx_wq( const int k )
+{
+    return ( W & ( W - 1 ) ) == 0 ? ( k & ( W / 2 - 1 ) ) : (int)( (unsigned)( k + 64 * ( W / 2 ) ) % (unsigned)( W / 2 ) );
+}
+
 template <int W> struct KswBxSmem
 {
     unsigned U[ W / 2 ], V[ W / 2 ], X[ W / 2 ], Y[ W / 2 ], X2[ W / 2 ], Y2[ W / 2 ]; // pair (t, t + 1) at [(t & (W-1)) >> 1]
@@ -107,7 +118,8 @@ template <int W> struct KswBxSmem
 };
 
 // position of the row maximum exactly as calcMaxScore finds it (kswcpp_core.h:178-250), from the finished H row
-QS_DEV int ksw_bx_argmax( const int* H, const int M, const int st0, const int en0, const int lane, const int SMASK )
+template <int W>
+QS_DEV int ksw_bx_argmax( const int* H, const int st0, const int en0, const int lane, const int SMASK )
 {
     const unsigned FULL = 0xffffffffu;
     const int NONE_T = 0x7fffffff, NONE_H = (int)0x80000000;
@@ -115,7 +127,7 @@ QS_DEV int ksw_bx_argmax( const int* H, const int M, const int st0, const int en
     int bh = NONE_H, bt = NONE_T, th = NONE_H, tt_ = NONE_T;
     for( int dt = lane; dt < nB; dt += 32 )
     {
-        const int h = H[ ( st0 + dt ) & M ];
+        const int h = H[ bx_wc<W>( st0 + dt ) ];
         if( dt < nV )
         {
             if( bt == NONE_T || h > bh )
@@ -124,7 +136,7 @@ QS_DEV int ksw_bx_argmax( const int* H, const int M, const int st0, const int en
         else if( tt_ == NONE_T || h > th )
             th = h, tt_ = st0 + dt;
     }
-    const int Hen0 = H[ en0 & M ];
+    const int Hen0 = H[ bx_wc<W>( en0 ) ];
     for( int o = 16; o >= -SMASK; o >>= 1 )
     {
         const int oh = __shfl_xor_sync( FULL, bh, o ), ot = __shfl_xor_sync( FULL, bt, o );
@@ -208,7 +220,6 @@ QS_DEV void ksw_bx_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = qs_lane( );
-    const int M = W - 1, MP = W / 2 - 1;
     const int NEG_M = -0x40000000; // removes a cell from a maximum
     const int q = P.q, e = P.e, q2 = P.q2, e2 = P.e2, scM = P.match;
     const int T16 = ( ( tlen + 15 ) / 16 ) * 16;
@@ -254,10 +265,10 @@ QS_DEV void ksw_bx_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
             bool n = false;
             for( int idx = inited_end + 2 * lane; idx < need; idx += 64 )
             {
-                const int kk = ( idx & M ) >> 1;
+                const int ki = bx_wc<W>( idx ), kk = ki >> 1;
                 sm.U[ kk ] = K.iUV, sm.V[ kk ] = K.iUV, sm.X[ kk ] = K.iX, sm.Y[ kk ] = K.iY;
                 sm.X2[ kk ] = K.iX2, sm.Y2[ kk ] = K.iY2, sm.S[ kk ] = K.iS;
-                sm.H[ idx & M ] = NEG_INF, sm.H[ ( idx & M ) + 1 ] = NEG_INF;
+                sm.H[ ki ] = NEG_INF, sm.H[ ki + 1 ] = NEG_INF;
                 const int c0 = idx < tlen ? seq.T( idx ) : 0, c1 = idx + 1 < tlen ? seq.T( idx + 1 ) : 0;
                 n |= c0 >= 4 || c1 >= 4;
                 sm.TC[ kk ] = ( (unsigned)c0 << 10 ) | ( (unsigned)c1 << 26 );
@@ -272,7 +283,7 @@ QS_DEV void ksw_bx_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
             const int jl = 2 * k + ( lane >> 4 );
             const int c0 = (unsigned)jl < (unsigned)qlen ? seq.Q( jl ) : 0;
             const int c1 = (unsigned)( jl - 1 ) < (unsigned)qlen ? seq.Q( jl - 1 ) : 0;
-            ( lane < 16 ? sm.QE : sm.QO )[ k & MP ] = ( (unsigned)c0 << 10 ) | ( (unsigned)c1 << 26 );
+            ( lane < 16 ? sm.QE : sm.QO )[ bx_wq<W>( k ) ] = ( (unsigned)c0 << 10 ) | ( (unsigned)c1 << 26 );
             anyN |= __any_sync( FULL, c0 >= 4 || c1 >= 4 );
             qend += 32;
         }
@@ -283,7 +294,7 @@ QS_DEV void ksw_bx_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
         {
             if( st - 1 >= last_st && st - 1 <= last_en )
             {
-                const int kp = ( st - 1 ) & M;
+                const int kp = bx_wc<W>( st - 1 );
                 cX = (unsigned)sX[ kp ] << 16, cX2 = (unsigned)sX2[ kp ] << 16, cV = (unsigned)sV[ kp ] << 16;
             }
         }
@@ -291,17 +302,20 @@ QS_DEV void ksw_bx_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
             cV = (unsigned)( first_col * 256 ) << 16;
         if( en >= r && lane == 0 )
         {
-            sY[ r & M ] = (unsigned short)( K.iY & 0xFFFFu );
-            sY2[ r & M ] = (unsigned short)( K.iY2 & 0xFFFFu );
-            sU[ r & M ] = (unsigned short)( first_col * 256 );
+            const int kr = bx_wc<W>( r );
+            sY[ kr ] = (unsigned short)( K.iY & 0xFFFFu );
+            sY2[ kr ] = (unsigned short)( K.iY2 & 0xFFFFu );
+            sU[ kr ] = (unsigned short)( first_col * 256 );
         }
         // old H left of en0, read before the pass updates it (:194-195); row 0: H[0] = v[0] - (q + e) (:247)
-        const int hprev = r == 0 ? -P.qe_row0 : ( en0 > 0 ? sm.H[ ( en0 - 1 ) & M ] : sm.H[ en0 & M ] );
+        const int ken0 = bx_wc<W>( en0 );
+        const int hprev = r == 0 ? -P.qe_row0 : ( en0 > 0 ? sm.H[ ken0 > 0 ? ken0 - 1 : W - 1 ] : sm.H[ ken0 ] );
         __syncwarp( );
         const unsigned nS = (unsigned)( sEnd - st0 ), nB = (unsigned)( en0 - st0 );
         const unsigned* const qw = ( r & 1 ) ? sm.QO : sm.QE; // r - t0 has the parity of r
         int m = NEG_M, hb = NEG_M;
         unsigned char* const rowp = tb + rowOff - st;
+        int kbase = bx_wc<W>( st ), qb = bx_wq<W>( ( r - st ) >> 1 ); // window indices of column st / its query pair
         // NCH consecutive 64-column chunks from column `base`. The chunks of a row only read values of the previous row:
         // all loads are issued first, so that the chunks are independent instruction streams. EDGE: the chunk may hold
         // cells outside [st0, en0) (stale profile, not part of the row maximum, H left of st0 kept) or lanes beyond en.
@@ -315,12 +329,17 @@ QS_DEV void ksw_bx_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
             for( int c = 0; c < NCH; c++ )
             {
                 const int t0 = base + 64 * c + 2 * lane;
-                kk[ c ] = ( t0 & M ) >> 1;
+                int kc = kbase + 64 * c + 2 * lane; // window index of column t0 (kbase: of column `base`)
+                kc = kc >= W ? kc - W : kc;
+                kk[ c ] = kc >> 1;
+                int kq = qb - 32 * c - lane; // ... of the query pair ((r - t0) >> 1)
+                kq = kq < 0 ? kq + W / 2 : kq;
                 xo[ c ] = sm.X[ kk[ c ] ], vo[ c ] = sm.V[ kk[ c ] ], x2o[ c ] = sm.X2[ kk[ c ] ];
                 uo[ c ] = sm.U[ kk[ c ] ], yo[ c ] = sm.Y[ kk[ c ] ], y2o[ c ] = sm.Y2[ kk[ c ] ];
                 tcp[ c ] = sm.TC[ kk[ c ] ];
-                qp[ c ] = qw[ ( ( r - t0 ) >> 1 ) & MP ];
-                hOld[ c ] = *reinterpret_cast<const unsigned long long*>( &sm.H[ t0 & M ] );
+                qp[ c ] = qw[ kq ];
+                hOld[ c ] = *reinterpret_cast<const unsigned long long*>( &sm.H[ kc ] );
+                (void)t0;
                 so[ c ] = EDGE ? sm.S[ kk[ c ] ] : 0u;
             }
             unsigned upx[ NCH ], upv[ NCH ], upx2[ NCH ];
@@ -379,14 +398,14 @@ QS_DEV void ksw_bx_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
                     // (H of a column left of the band stays: it is read once more as the left neighbour of en0 when the
                     // band has shrunk to one column; right of en0 any value does, the column is set when it enters)
                     if( !EDGE )
-                        *reinterpret_cast<unsigned long long*>( &sm.H[ t0 & M ] ) =
+                        *reinterpret_cast<unsigned long long*>( &sm.H[ 2 * k ] ) =
                             (unsigned long long)(unsigned)h0 | ( (unsigned long long)(unsigned)h1 << 32 );
                     else
                     {
                         if( keep0 )
-                            sm.H[ t0 & M ] = h0;
+                            sm.H[ 2 * k ] = h0;
                         if( keep1 )
-                            sm.H[ ( t0 & M ) + 1 ] = h1;
+                            sm.H[ 2 * k + 1 ] = h1;
                     }
                     *reinterpret_cast<unsigned short*>( rowp + t0 ) = (unsigned short)__byte_perm( C.tbyte, 0, 0x4420 );
                 }
@@ -395,20 +414,21 @@ QS_DEV void ksw_bx_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
         for( int base = st; base <= en; )
         {
             // interior chunk: every cell is in [st0, en0), hence fresh profile and part of the row maximum
+            int n = 1;
             if( base < st0 || base + 63 >= en0 )
-                pass( BxTag<bool, true>( ), BxTag<int, 1>( ), base ), base += 64;
-            else if( W >= 1024 && base + 255 < en0 ) // (the widest class runs one CTA per SM: registers for four streams)
-                pass( BxTag<bool, false>( ), BxTag<int, W >= 1024 ? 4 : 1>( ), base ), base += 256;
+                pass( BxTag<bool, true>( ), BxTag<int, 1>( ), base );
             else if( base + 127 < en0 )
-                pass( BxTag<bool, false>( ), BxTag<int, 2>( ), base ), base += 128;
+                pass( BxTag<bool, false>( ), BxTag<int, 2>( ), base ), n = 2;
             else
-                pass( BxTag<bool, false>( ), BxTag<int, 1>( ), base ), base += 64;
+                pass( BxTag<bool, false>( ), BxTag<int, 1>( ), base );
+            base += 64 * n, kbase += 64 * n, qb -= 32 * n;
+            kbase = kbase >= W ? kbase - W : kbase, qb = qb < 0 ? qb + W / 2 : qb;
         }
         __syncwarp( );
         // the column at en0 adds u to the old H of its left neighbour (v in column 0)
         int Hen0;
         {
-            const int d8 = (short)( en0 > 0 ? sU[ en0 & M ] : sV[ en0 & M ] );
+            const int d8 = (short)( en0 > 0 ? sU[ ken0 ] : sV[ ken0 ] );
             Hen0 = (int)( (unsigned)hprev + (unsigned)( d8 >> 8 ) );
             if( is16 )
                 Hen0 = (short)Hen0;
@@ -419,8 +439,8 @@ QS_DEV void ksw_bx_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
             const int t0 = en + 1 + 2 * lane;
             if( t0 < sEnd )
             {
-                const int kk = ( t0 & M ) >> 1;
-                const unsigned tcp = sm.TC[ kk ], qp = qw[ ( ( r - t0 ) >> 1 ) & MP ];
+                const int kk = bx_wc<W>( t0 ) >> 1;
+                const unsigned tcp = sm.TC[ kk ], qp = qw[ bx_wq<W>( ( r - t0 ) >> 1 ) ];
                 unsigned z0 = ( qs_eqmask2( tcp, qp ) & K.zXor ) ^ K.zMis;
                 const unsigned nm = bx_nmask2( tcp, qp );
                 z0 = ( K.zN & nm ) | ( z0 & ~nm );
@@ -429,7 +449,7 @@ QS_DEV void ksw_bx_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
             }
         }
         if( lane == 0 )
-            sm.H[ en0 & M ] = Hen0;
+            sm.H[ ken0 ] = Hen0;
         __syncwarp( );
         // the row maximum is the exact maximum of the row (only its POSITION is lane-blocked in the reference): the
         // position of a new maximum is consumed by a later z-drop test that can fire or at the end, so the H row of the
@@ -439,7 +459,7 @@ QS_DEV void ksw_bx_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
             ez.mte = Hen0, ez.mte_q = r - en; // sic: the aligned en
         if( r - st0 == qlen - 1 )
         {
-            const int Hst0 = sm.H[ st0 & M ];
+            const int Hst0 = sm.H[ bx_wc<W>( st0 ) ];
             if( Hst0 > ez.mqe )
                 ez.mqe = Hst0, ez.mqe_t = st0;
         }
@@ -449,8 +469,10 @@ QS_DEV void ksw_bx_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
             ez.max = max_H;
             bR = r, bSt0 = st0, bEn0 = en0;
             for( int t = ( st0 & ~1 ) + 2 * lane; t <= en0; t += 64 )
-                *reinterpret_cast<unsigned long long*>( &sm.HB[ t & M ] ) =
-                    *reinterpret_cast<const unsigned long long*>( &sm.H[ t & M ] );
+            {
+                const int kt = bx_wc<W>( t );
+                *reinterpret_cast<unsigned long long*>( &sm.HB[ kt ] ) = *reinterpret_cast<const unsigned long long*>( &sm.H[ kt ] );
+            }
         }
         else if( zdrop >= 0 && ez.max - max_H > zdrop )
         {
@@ -458,9 +480,9 @@ QS_DEV void ksw_bx_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
             if( bR >= 0 )
             {
                 __syncwarp( );
-                bt = ksw_bx_argmax( sm.HB, M, bSt0, bEn0, lane, SMASK ), bq = bR - bt;
+                bt = ksw_bx_argmax<W>( sm.HB, bSt0, bEn0, lane, SMASK ), bq = bR - bt;
             }
-            const int max_t = ksw_bx_argmax( sm.H, M, st0, en0, lane, SMASK );
+            const int max_t = ksw_bx_argmax<W>( sm.H, st0, en0, lane, SMASK );
             if( max_t >= bt && r - max_t >= bq )
             {
                 const int tl = max_t - bt, ql = ( r - max_t ) - bq;
@@ -493,7 +515,7 @@ QS_DEV void ksw_bx_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
     if( bR >= 0 )
     {
         __syncwarp( );
-        ez.max_t = ksw_bx_argmax( sm.HB, M, bSt0, bEn0, lane, SMASK ), ez.max_q = bR - ez.max_t;
+        ez.max_t = ksw_bx_argmax<W>( sm.HB, bSt0, bEn0, lane, SMASK ), ez.max_q = bR - ez.max_t;
     }
     ez.cells = cells;
     __syncwarp( );

@@ -350,11 +350,11 @@ static const int kKswWindows[] = { 128, 256, 512, 1024, 2048 };
 
 template <int W> static long long ksw_bin_grid( ma_b200_ctx* ctx, const KswHostBin& bin, long long tbBudget )
 {
-    const int warpsPerCta = MA_KSW_WARPS;
+    const int warpsPerCta = KswClass<W>::WARPS;
     const size_t smem = KswSmemBytes<W>::value * warpsPerCta;
     MA_CUDA( cudaFuncSetAttribute( ksw_batch_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) );
     int perSm = 0;
-    MA_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, ksw_batch_kernel<W>, 32 * MA_KSW_WARPS, smem ) );
+    MA_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &perSm, ksw_batch_kernel<W>, 32 * warpsPerCta, smem ) );
     if( perSm < 1 )
         perSm = 1;
     long long grid = (long long)perSm * ctx->num_sms;
@@ -367,8 +367,8 @@ template <int W> static long long ksw_bin_grid( ma_b200_ctx* ctx, const KswHostB
 
 template <int W> static void launch_ksw_bin( ma_b200_ctx* ctx, const KswBatchArgs& A, long long grid )
 {
-    const size_t smem = KswSmemBytes<W>::value * MA_KSW_WARPS;
-    ksw_batch_kernel<W><<<(unsigned)grid, 32 * MA_KSW_WARPS, smem, ctx->stream>>>( A );
+    const size_t smem = KswSmemBytes<W>::value * KswClass<W>::WARPS;
+    ksw_batch_kernel<W><<<(unsigned)grid, 32 * KswClass<W>::WARPS, smem, ctx->stream>>>( A );
     MA_CUDA( cudaGetLastError( ) );
     ctx->launches++;
 }
@@ -463,7 +463,7 @@ static void ksw_plan( ma_b200_ctx* ctx, const std::vector<KswTask>& tasks, std::
         }
         else
             for( size_t k = 0; k < sizeof( kKswWindows ) / sizeof( int ); k++ )
-                if( ctx->ksw_bins[ k ].W >= nc + 48 )
+                if( ksw_class_cap( ctx->ksw_bins[ k ].W ) >= nc + 48 )
                 {
                     b = (int)k;
                     break;
@@ -641,7 +641,7 @@ static int ksw_run_once( ma_b200_ctx* ctx )
                     const int nc = ksw_ncol16( t.qlen, t.tlen, t.w );
                     const long long rows = (long long)t.qlen + t.tlen;
                     for( auto& rb : redoBins )
-                        if( rb.W >= nc + 48 )
+                        if( ksw_class_cap( rb.W ) >= nc + 48 )
                         {
                             rb.order.push_back( i );
                             rb.tb_stride = std::max( rb.tb_stride, ( rows * nc + 255 ) & ~255ll );
@@ -668,7 +668,7 @@ static int ksw_run_once( ma_b200_ctx* ctx )
         {
             const long long g = ksw_host_grid( ctx, *bin, budget );
             grids.push_back( g );
-            const int wpc = bin->qs ? MA_QS_WARPS : MA_KSW_WARPS;
+            const int wpc = bin->qs ? MA_QS_WARPS : ( bin->W == 1024 ? KswClass<1024>::WARPS : MA_KSW_WARPS );
             tbNeed = std::max<size_t>( tbNeed, (size_t)( g * wpc * bin->tb_stride ) );
             csNeed = std::max<size_t>( csNeed, (size_t)( g * wpc * bin->cig_stride ) );
         }
@@ -1155,7 +1155,7 @@ static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
                 else
                     bin.W = Ws[ b / 3 ], bin.qs = 0;
                 grids[ b ] = ksw_host_grid( ctx, bin, budget );
-                const int wpc = bin.qs ? MA_QS_WARPS : MA_KSW_WARPS;
+                const int wpc = bin.qs ? MA_QS_WARPS : ( bin.W == 1024 ? KswClass<1024>::WARPS : MA_KSW_WARPS );
                 tbNeed = std::max<size_t>( tbNeed, (size_t)( grids[ b ] * wpc * bin.tb_stride ) );
                 csNeed = std::max<size_t>( csNeed, (size_t)( grids[ b ] * wpc * bin.cig_stride ) );
             }

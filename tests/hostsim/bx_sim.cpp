@@ -112,6 +112,8 @@ static Result runW( const KswScore& P, const std::vector<uint8_t>& q, const std:
         return runBx<256, LEFT>( P, q, t, w, zdrop, flag, bEarly );
     if( need <= 512 )
         return runBx<512, LEFT>( P, q, t, w, zdrop, flag, bEarly );
+    if( need <= 640 ) // the band-512 class: a window that is not a power of two
+        return runBx<640, LEFT>( P, q, t, w, zdrop, flag, bEarly );
     return runBx<1024, LEFT>( P, q, t, w, zdrop, flag, bEarly );
 }
 
