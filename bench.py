@@ -416,9 +416,12 @@ def main():
     out["uploaded"] = False
     barrier()
     t = time.perf_counter()
+    e2e_stage = {}
     for _ in range(args.steps):
         for sub in subs:
-            e2e_sub(sub)
+            est, _a = e2e_sub(sub)
+            for k in ("ms_seed", "ms_locate", "ms_socharm", "ms_plan", "ms_dp", "ms_assemble", "ms_total"):
+                e2e_stage[k] = e2e_stage.get(k, 0.0) + getattr(est, k) / args.steps
     torch.cuda.synchronize()
     e2e_single_s = time.perf_counter() - t
     ctx2 = ctx.sibling()
@@ -430,6 +433,7 @@ def main():
         for sub in mine[:max(1, len(subs) // 2)] or items[:1]:
             e2e_sub(sub, False, c, o)
     counts = [[0, 0], [0, 0]]
+    stage2 = [{kk: 0.0 for kk in ("ms_seed", "ms_locate", "ms_socharm", "ms_plan", "ms_dp", "ms_assemble", "ms_total")} for _ in range(2)]
     errors = []
 
     def lane(k):
@@ -440,6 +444,8 @@ def main():
                 est, _a = e2e_sub(sub, False, c, o)
                 counts[k][0] += est.n_sets if args.all_records else est.n_reported
                 counts[k][1] += est.n_runs
+                for kk in stage2[k]:
+                    stage2[k][kk] += getattr(est, kk) / args.steps
         except Exception as e:  # noqa: BLE001
             errors.append(e)
 
@@ -582,7 +588,9 @@ def main():
             "dtype": "u8/int64 (f64 in Harmonization)", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d_all),
                     "d2h_bytes_per_step": int(d2h_all), "ms_per_step": e2e_ms_max / K, "batches_in_flight": 2,
+                    "device_stage_ms": {kk: round(stage2[0][kk] + stage2[1][kk], 2) for kk in stage2[0]},
                     "single_call": {"value": aligned_all * K / (e2e_single_ms_max / 1000.0), "ms_per_step": e2e_single_ms_max / K,
+                                    "device_stage_ms": {k: round(v, 2) for k, v in e2e_stage.items()},
                                     "note": "one ma_b200_align_batch at a time (upload under the seeding kernel, run "
                                             "words down under stage 4, records down after the last kernel)"},
                     "note": "K steps through ma_b200_align_batch from two host threads on two contexts of the GPU (the "

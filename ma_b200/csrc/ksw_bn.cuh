@@ -66,7 +66,7 @@ QS_DEV void ksw_bn_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
     int qend = -32; // query bases j < qend are staged
     unsigned cells = 0;
     int prevB = 0x7fffffff;
-    int bR = -1, bSt0 = 0, bEn0 = 0; // row and band of the running maximum
+    int bR = -1, bSt0 = 0, bEn0 = 0, bT = -1; // row, band and (once resolved) position of the running maximum
     int Hleft = NEG_INF; // H of column base - 1 (it left the window; read once more when the band is the one column `base`)
     // value of column t of a two-register row, on all lanes
     auto colval = [ & ]( const int( &A0 )[ NC ], const int( &A1 )[ NC ], const int t, const int wbase ) {
@@ -238,13 +238,13 @@ QS_DEV void ksw_bn_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
         }
         // the row maximum is the exact maximum of the row (only its POSITION is lane-blocked in the reference)
         const int max_H = __reduce_max_sync( FULL, m );
+        int scoreLast = 0;
         if( en0 == tlen - 1 )
         { // (H[en0] is only consumed in the last target column: mte, and score in the last row)
             const int Hen0 = colval( H0, H1, en0, base );
             if( Hen0 > ez.mte )
                 ez.mte = Hen0, ez.mte_q = r - en; // sic: the aligned en
-            if( r == nrows - 1 )
-                ez.score = Hen0;
+            scoreLast = Hen0;
         }
         if( r - st0 == qlen - 1 )
         {
@@ -256,14 +256,14 @@ QS_DEV void ksw_bn_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
         if( max_H > ez.max )
         {
             ez.max = max_H;
-            bR = r, bSt0 = st0, bEn0 = en0;
+            bR = r, bSt0 = st0, bEn0 = en0, bT = -1;
             spill( sm.HBS );
         }
         else if( zdrop >= 0 && ez.max - max_H > zdrop )
         {
-            int bt = -1, bq = -1;
-            if( bR >= 0 )
-                bt = ksw_bx_argmax<256>( sm.HBS, bSt0, bEn0, lane, SMASK ), bq = bR - bt;
+            if( bR >= 0 && bT < 0 ) // resolved once per maximum
+                bT = ksw_bx_argmax<256>( sm.HBS, bSt0, bEn0, lane, SMASK );
+            const int bt = bT, bq = bR >= 0 ? bR - bT : -1;
             spill( sm.HS );
             const int max_t = ksw_bx_argmax<256>( sm.HS, st0, en0, lane, SMASK );
             if( max_t >= bt && r - max_t >= bq )
@@ -277,23 +277,23 @@ QS_DEV void ksw_bn_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
                 }
             }
         }
+        if( r == nrows - 1 && en0 == tlen - 1 ) // (after the z-drop test: a drop in the last row leaves no score)
+            ez.score = scoreLast;
         if( bEarlyStop )
         { // see ksw.cuh, ksw_rows
             const int B = __reduce_max_sync( FULL, hb );
-            if( r >= qlen && prevB != 0x7fffffff )
-            {
+            if( r >= qlen && prevB != 0x7fffffff && bx_max( B, prevB ) <= ez.max )
+            { // (the bound through query row 0 only matters once the cell bound has fallen below the maximum)
                 const long long j = r + 1;
                 const long long g1 = q + (long long)e * j, g2 = q2 + (long long)e2 * j;
-                const long long T = (long long)scM * qlen - ( g1 < g2 ? g1 : g2 );
-                const long long bnd = (long long)bx_max( B, prevB ) > T ? (long long)bx_max( B, prevB ) : T;
-                if( bnd <= (long long)ez.max )
+                if( (long long)scM * qlen - ( g1 < g2 ? g1 : g2 ) <= (long long)ez.max )
                     break;
             }
             prevB = B;
         }
     }
     if( bR >= 0 )
-        ez.max_t = ksw_bx_argmax<256>( sm.HBS, bSt0, bEn0, lane, SMASK ), ez.max_q = bR - ez.max_t;
+        ez.max_t = bT >= 0 ? bT : ksw_bx_argmax<256>( sm.HBS, bSt0, bEn0, lane, SMASK ), ez.max_q = bR - ez.max_t;
     ez.cells = cells;
     __syncwarp( );
 }

@@ -241,7 +241,7 @@ QS_DEV void ksw_bx_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
     int last_st = -1, last_en = -1;
     unsigned cells = 0; // < 2^31 rows * band
     int prevB = 0x7fffffff;
-    int bR = -1, bSt0 = 0, bEn0 = 0; // row and band of the running maximum (its H row: sm.HB)
+    int bR = -1, bSt0 = 0, bEn0 = 0, bT = -1; // row, band and (once resolved) position of the running maximum (H row: sm.HB)
     long long rowOff = 0; // r * ncol16
     for( int r = 0; r < nrows; ++r, rowOff += ncol16 )
     {
@@ -467,7 +467,7 @@ QS_DEV void ksw_bx_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
         if( max_H > ez.max )
         {
             ez.max = max_H;
-            bR = r, bSt0 = st0, bEn0 = en0;
+            bR = r, bSt0 = st0, bEn0 = en0, bT = -1;
             for( int t = ( st0 & ~1 ) + 2 * lane; t <= en0; t += 64 )
             {
                 const int kt = bx_wc<W>( t );
@@ -476,12 +476,12 @@ QS_DEV void ksw_bx_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
         }
         else if( zdrop >= 0 && ez.max - max_H > zdrop )
         {
-            int bt = -1, bq = -1;
-            if( bR >= 0 )
-            {
+            if( bR >= 0 && bT < 0 )
+            { // resolved once per maximum
                 __syncwarp( );
-                bt = ksw_bx_argmax<W>( sm.HB, bSt0, bEn0, lane, SMASK ), bq = bR - bt;
+                bT = ksw_bx_argmax<W>( sm.HB, bSt0, bEn0, lane, SMASK );
             }
+            const int bt = bT, bq = bR >= 0 ? bR - bT : -1;
             const int max_t = ksw_bx_argmax<W>( sm.H, st0, en0, lane, SMASK );
             if( max_t >= bt && r - max_t >= bq )
             {
@@ -500,13 +500,11 @@ QS_DEV void ksw_bx_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
         if( bEarlyStop )
         { // see ksw.cuh, ksw_rows
             const int B = bx_max( __reduce_max_sync( FULL, hb ), Hen0 + scM * ( qlen - 1 - r + en0 ) );
-            if( r >= qlen && prevB != 0x7fffffff )
-            {
+            if( r >= qlen && prevB != 0x7fffffff && bx_max( B, prevB ) <= ez.max )
+            { // (the bound through query row 0 only matters once the cell bound has fallen below the maximum)
                 const long long j = r + 1;
                 const long long g1 = q + (long long)e * j, g2 = q2 + (long long)e2 * j;
-                const long long T = (long long)scM * qlen - ( g1 < g2 ? g1 : g2 );
-                const long long bnd = (long long)bx_max( B, prevB ) > T ? (long long)bx_max( B, prevB ) : T;
-                if( bnd <= (long long)ez.max )
+                if( (long long)scM * qlen - ( g1 < g2 ? g1 : g2 ) <= (long long)ez.max )
                     break;
             }
             prevB = B;
@@ -515,7 +513,7 @@ QS_DEV void ksw_bx_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
     if( bR >= 0 )
     {
         __syncwarp( );
-        ez.max_t = ksw_bx_argmax<W>( sm.HB, bSt0, bEn0, lane, SMASK ), ez.max_q = bR - ez.max_t;
+        ez.max_t = bT >= 0 ? bT : ksw_bx_argmax<W>( sm.HB, bSt0, bEn0, lane, SMASK ), ez.max_q = bR - ez.max_t;
     }
     ez.cells = cells;
     __syncwarp( );

@@ -1,6 +1,7 @@
 // libma_b200.so — C ABI (include/ma_b200.h) over the sm_100a kernels. Host side of the drop-in boundary.
 #include "common.cuh"
 #include "ksw.cuh"
+#include <chrono>
 #include "pipeline.cuh"
 #include "index_build.cuh"
 #include <algorithm>
@@ -1227,6 +1228,10 @@ static void run_pipeline_dp( ma_b200_ctx* ctx, long long task_cap )
     throw std::runtime_error( "pipeline DP: cigar slab overflow after growing (internal error)" );
 }
 
+__global__ void stream_to_compute_kernel( )
+{
+}
+
 extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t keep_segments,
                                   ma_b200_align_stats* stats )
 {
@@ -1250,7 +1255,20 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
     ctx->stage_done = 0, ctx->compacted = false, ctx->n_reported = 0;
     cudaStream_t s = ctx->stream;
     NvtxRange nvtxRun( "ma_b200_align_run" );
+    // The last operation of this stream was a device-to-host copy (the offsets check of the upload, the records of the
+    // previous batch): an event recorded right behind it is queued on that copy engine, and with a second batch in
+    // flight on the device it then waits for the OTHER batch's 200 MB record download (6 ms). An empty kernel moves the
+    // stream to the compute engine first.
+    stream_to_compute_kernel<<<1, 32, 0, s>>>( );
     MA_CUDA( cudaEventRecord( ctx->ev[ 0 ], s ) );
+    static const bool bTraceRun = getenv( "MA_B200_E2E_TRACE" ) != nullptr;
+    const auto tRun0 = std::chrono::steady_clock::now( );
+    if( bTraceRun )
+    { // how long the stream takes to reach the start of this run
+        MA_CUDA( cudaEventSynchronize( ctx->ev[ 0 ] ) );
+        fprintf( stderr, "ma_b200 e2e trace ctx %p: run start reached by the stream after %.2f ms\n", (void*)ctx,
+                 std::chrono::duration<double, std::milli>( std::chrono::steady_clock::now( ) - tRun0 ).count( ) );
+    }
     if( n > 0 )
     {
         MA_CUDA( cudaMemsetAsync( ctx->ctrl.p, 0, sizeof( PipeCtrl ), s ) );
@@ -1448,8 +1466,11 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
                 { // the run words are final: their download runs under the kernels that follow
                     MA_CUDA( cudaEventRecord( ctx->ev_copy[ 2 ], s ) );
                     MA_CUDA( cudaStreamWaitEvent( ctx->copy_stream, ctx->ev_copy[ 2 ], 0 ) );
-                    MA_CUDA( cudaMemcpyAsync( ctx->early_runs, ctx->runs.p, ctx->n_runs * sizeof( unsigned int ),
-                                              cudaMemcpyDeviceToHost, ctx->copy_stream ) );
+                    // (in pieces: the control read-backs of the kernels that follow share the copy engine)
+                    const size_t bytes = (size_t)ctx->n_runs * sizeof( unsigned int ), piece = 4u << 20;
+                    for( size_t o = 0; o < bytes; o += piece )
+                        MA_CUDA( cudaMemcpyAsync( (char*)ctx->early_runs + o, (const char*)ctx->runs.p + o,
+                                                  std::min( piece, bytes - o ), cudaMemcpyDeviceToHost, ctx->copy_stream ) );
                     ctx->early_runs_done = true;
                 }
                 AlnSortArgs B{ ctx->info.p, n, ctx->alns.p, ctx->ctrl.p };
@@ -1515,6 +1536,10 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
     }
     MA_CUDA( cudaEventRecord( ctx->ev[ 6 ], s ) );
     MA_CUDA( cudaEventSynchronize( ctx->ev[ 6 ] ) );
+    if( bTraceRun )
+        fprintf( stderr, "ma_b200 e2e trace ctx %p: run wall %.2f ms, event span %.2f ms\n", (void*)ctx,
+                 std::chrono::duration<double, std::milli>( std::chrono::steady_clock::now( ) - tRun0 ).count( ),
+                 ev_ms( ctx->ev[ 0 ], ctx->ev[ 6 ] ) );
     st.n_seeds = ctx->n_seeds, st.n_sets = ctx->n_sets, st.n_set_seeds = ctx->n_set_seeds, st.n_tasks = ctx->n_tasks;
     st.n_runs = ctx->n_runs, st.n_cigar_words = ctx->n_task_cigar;
     st.ms_seed = ev_ms( ctx->ev[ 0 ], ctx->ev[ 1 ] ), st.ms_locate = ev_ms( ctx->ev[ 1 ], ctx->ev[ 2 ] );
@@ -1630,15 +1655,20 @@ extern "C" int ma_b200_align_download( ma_b200_ctx* ctx, ma_b200_read_info* info
         ctx->err = "alignment buffers too small";
         return MA_B200_ENOMEM;
     }
+    // in pieces: with two batches in flight on a device (sibling contexts) the small control read-backs of the OTHER
+    // batch's stages share the copy engine and would otherwise wait for a whole 200 MB record download
+    auto down = [ & ]( void* dst, const void* src, size_t bytes ) {
+        const size_t piece = 4u << 20;
+        for( size_t o = 0; o < bytes; o += piece )
+            MA_CUDA( cudaMemcpyAsync( (char*)dst + o, (const char*)src + o, std::min( piece, bytes - o ), cudaMemcpyDeviceToHost,
+                                      ctx->stream ) );
+    };
     if( ctx->n_reads && info )
-        MA_CUDA( cudaMemcpyAsync( info, compact ? ctx->info_out.p : ctx->info.p, ctx->n_reads * sizeof( ReadInfo ),
-                                  cudaMemcpyDeviceToHost, ctx->stream ) );
+        down( info, compact ? ctx->info_out.p : ctx->info.p, ctx->n_reads * sizeof( ReadInfo ) );
     if( nAlns )
-        MA_CUDA( cudaMemcpyAsync( alns, compact ? ctx->alns_out.p : ctx->alns.p, nAlns * sizeof( DAln ),
-                                  cudaMemcpyDeviceToHost, ctx->stream ) );
+        down( alns, compact ? ctx->alns_out.p : ctx->alns.p, nAlns * sizeof( DAln ) );
     if( ctx->n_runs && !( ctx->early_runs_done && runs == ctx->early_runs ) )
-        MA_CUDA( cudaMemcpyAsync( runs, ctx->runs.p, ctx->n_runs * sizeof( unsigned int ), cudaMemcpyDeviceToHost,
-                                  ctx->stream ) );
+        down( runs, ctx->runs.p, ctx->n_runs * sizeof( unsigned int ) );
     MA_CUDA( cudaStreamSynchronize( ctx->stream ) );
     if( ctx->early_runs_done )
         MA_CUDA( cudaStreamSynchronize( ctx->copy_stream ) );
@@ -1761,6 +1791,11 @@ extern "C" int ma_b200_align_batch( ma_b200_ctx* ctx, int64_t n_reads, const uin
     { // one shot (also the path that reports argument errors): the upload runs under the seeding kernel, the download
       // of the run words under the kernels of stage 4
         int rc = MA_B200_OK;
+        // MA_B200_E2E_TRACE=1: host time stamps of the phases of every call (ms since the first call) on stderr
+        static const bool bTrace = getenv( "MA_B200_E2E_TRACE" ) != nullptr;
+        static const auto t00 = std::chrono::steady_clock::now( );
+        auto now = [ & ]( ) { return std::chrono::duration<double, std::milli>( std::chrono::steady_clock::now( ) - t00 ).count( ); };
+        const double tEnter = now( );
         try
         {
             MA_CUDA( cudaSetDevice( ctx->device ) );
@@ -1776,13 +1811,17 @@ extern "C" int ma_b200_align_batch( ma_b200_ctx* ctx, int64_t n_reads, const uin
             ctx->err = e.what( ), rc = MA_B200_EINVAL;
         }
         ctx->early_runs = runs, ctx->early_runs_cap = runs ? cap_runs : 0, ctx->early_runs_done = false;
+        double tUp = 0, tLock = 0, tRun = 0;
         if( !rc )
         { // One batch at a time computes on a device: when two host threads keep two batches in flight on sibling
           // contexts, the kernels of the two would otherwise interleave, both batches would finish together and their
           // downloads would find the GPU idle. With the turnstile the upload of a batch (enqueued above) and the
           // download of its records (below) run under the OTHER batch's kernels.
+            tUp = now( );
             std::lock_guard<std::mutex> turn( device_turnstile( ctx->device ) );
+            tLock = now( );
             rc = ma_b200_align_run( ctx, MA_B200_STAGE_MAPQ, 0, stats );
+            tRun = now( );
         }
         if( ctx->upload_in_flight )
         { // whatever happened above, nothing of the caller's buffers may still be in flight when this call returns
@@ -1795,6 +1834,9 @@ extern "C" int ma_b200_align_batch( ma_b200_ctx* ctx, int64_t n_reads, const uin
         else if( ctx->early_runs_done )
             cudaStreamSynchronize( ctx->copy_stream );
         ctx->early_runs_done = false;
+        if( bTrace )
+            fprintf( stderr, "ma_b200 e2e trace ctx %p: enter %.2f upload-call %.2f lock-wait %.2f run %.2f download %.2f (end %.2f)\n",
+                     (void*)ctx, tEnter, tUp - tEnter, tLock - tUp, tRun - tLock, now( ) - tRun, now( ) );
         return rc;
     }
     if( !ctx->shadow )
