@@ -1260,6 +1260,7 @@ extern "C" int ma_b200_align_run( ma_b200_ctx* ctx, int32_t upto_stage, int32_t 
     // flight on the device it then waits for the OTHER batch's 200 MB record download (6 ms). An empty kernel moves the
     // stream to the compute engine first.
     stream_to_compute_kernel<<<1, 32, 0, s>>>( );
+    ctx->launches++;
     MA_CUDA( cudaEventRecord( ctx->ev[ 0 ], s ) );
     static const bool bTraceRun = getenv( "MA_B200_E2E_TRACE" ) != nullptr;
     const auto tRun0 = std::chrono::steady_clock::now( );
