@@ -147,6 +147,7 @@ QS_DEV void ksw_bn_rows( const BxK& K, const KswScore& P, const SeqAccess& seq, 
         }
         while( qend <= r - st0 + 1 )
         { // the next 32 query bases: lanes 0-15 write QE, lanes 16-31 QO
+            __syncwarp( ); // (the entries they replace were read 128+ rows ago; the rows of this kernel have no barrier)
             const int k = ( qend >> 1 ) + ( lane & 15 );
             const int jl = 2 * k + ( lane >> 4 );
             const int c0 = (unsigned)jl < (unsigned)qlen ? seq.Q( jl ) : 0;
