@@ -4,7 +4,16 @@
 //   /root/reference/libs/kswcpp/inc/kswcpp.h:165-190, kswcpp_core.h:308-841 (recurrence + traceback byte),
 //   kswcpp_core.h:157-299 (H row, lane-blocked arg-max, mte/mqe), :22-44 (z-drop), :76-150 (backtrack).
 //
-// B200 mapping:
+// This file: ksw_batch_kernel (one warp per problem, dynamic task queue, window classes) and the modes it dispatches to
+// in ksw_warp, most specific first:
+//   ksw_rows_p2x2 (here)   in-band early-stop extensions, half2, two rows per pass; hands over if a maximum was clipped;
+//   ksw_bn_rows (ksw_bn.cuh)  any problem of at most three 64-column chunks: state in registers, int8 wrap exact;
+//   ksw_bx_rows (ksw_bx.cuh)  any other problem of an int8-representable score set: packed s16x2 in a shared-memory
+//                             window, int8 wrap exact;
+//   ksw_rows<FAST> / ksw_rows (here)  the scalar modes: score sets beyond int8, the 2048-column class.
+// ksw_qs_kernel (ksw_qs.cuh) and ksw_tiny_kernel (ksw_tiny.cuh) are launched for their own bins.
+//
+// B200 mapping of the scalar modes:
 //  * lanes run along the anti-diagonal (target index t); the reference's 16-aligned column range [st,en] is kept
 //    because its out-of-band cells feed band-edge cells (they are computed from stale state on purpose);
 //  * the seven int8 difference arrays + the H row live in a per-warp CIRCULAR window in shared memory
