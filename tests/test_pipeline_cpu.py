@@ -180,6 +180,7 @@ def test_warp_emulated_dp_kernels_match_oracle(tmp_path):
     subprocess.check_call(["make", "-s", "-C", d])
     assert subprocess.call([os.path.join(d, "bx_sim"), "500", "21", "160"]) == 0
     assert subprocess.call([os.path.join(d, "bx_sim"), "30", "22", "1000"]) == 0
+    assert subprocess.call([os.path.join(d, "bx_sim"), "4", "71", "20000"]) == 0  # int32 H rows (lengths beyond int16)
     narrow = dict(os.environ, BX_NARROW="1")  # ksw_bn.cuh (register-resident narrow bands) where it applies
     assert subprocess.call([os.path.join(d, "bx_sim"), "500", "23", "200"], env=narrow) == 0
     assert subprocess.call([os.path.join(d, "bx_sim"), "40", "24", "1500"], env=narrow) == 0
